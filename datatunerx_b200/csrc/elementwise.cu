@@ -1,0 +1,581 @@
+// HBM-bound kernels of the LoRA-SFT step (SURVEY §2.3 K1,K2,K5,K9,K11,K13 + SwiGLU elementwise).
+// All of them are single-pass over their algorithmic bytes with 16-byte vector accesses, fp32 math,
+// warp-shuffle reductions and fixed (deterministic) summation orders.  None uses tensor cores:
+// they are bandwidth-bound and are measured against the HBM roofline.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dtx {
+
+namespace {
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// block-wide sum, result broadcast to all threads. blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += sh[i];  // fixed order
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: embedding gather.  HF nn.Embedding forward (transformers LlamaModel.embed_tokens).
+// ------------------------------------------------------------------------------------------
+__global__ void embedding_kernel(const int32_t* __restrict__ ids, const bf16* __restrict__ table, bf16* __restrict__ out,
+                                 int d, int vocab) {
+  const int m = blockIdx.x;
+  int id = ids[m];
+  if (id < 0 || id >= vocab) id = 0;
+  const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * d);
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * d);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: RMSNorm.  One warp per row, the row lives in registers between the reduce and the scale.
+//   y = w * (x * rsqrt(mean(x^2) + eps)), all math fp32 (HF LlamaRMSNorm computes in fp32).
+// ------------------------------------------------------------------------------------------
+template <int MAXCH>
+__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                          bf16* __restrict__ y, float* __restrict__ rstd, int M, int d,
+                                                          float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d);
+  const int nvec = d >> 3;
+  uint4 buf[MAXCH];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int v = i * 32 + lane;
+    if (v < nvec) {
+      buf[i] = ldg_stream(xr + v);
+      float f[8];
+      bf16x8_to_f32(buf[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+  }
+  ss = warp_sum(ss);
+  const float r = rsqrtf(ss / static_cast<float>(d) + eps);
+  if (lane == 0 && rstd) rstd[row] = r;
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * d);
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int v = i * 32 + lane;
+    if (v < nvec) {
+      float f[8], g[8];
+      bf16x8_to_f32(buf[i], f);
+      bf16x8_to_f32(__ldg(wr + v), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = f[j] * r * g[j];
+      yr[v] = f32_to_bf16x8(f);
+    }
+  }
+}
+
+// dx = rstd * (w*dy) - x * rstd^3 * mean(w*dy*x) (+ dres).  Base weights are frozen: no dw.
+template <int MAXCH>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                          const bf16* __restrict__ w, const float* __restrict__ rstd,
+                                                          const bf16* __restrict__ dres, bf16* __restrict__ dx, int M,
+                                                          int d) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const size_t off = static_cast<size_t>(row) * d;
+  const uint4* dyr = reinterpret_cast<const uint4*>(dy + off);
+  const uint4* xr = reinterpret_cast<const uint4*>(x + off);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  const int nvec = d >> 3;
+  uint4 bx[MAXCH], bg[MAXCH];  // x and w*dy (as bf16-packed inputs; products recomputed in fp32)
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int v = i * 32 + lane;
+    if (v < nvec) {
+      bx[i] = ldg_stream(xr + v);
+      bg[i] = ldg_stream(dyr + v);
+      float fx[8], fg[8], fw[8];
+      bf16x8_to_f32(bx[i], fx);
+      bf16x8_to_f32(bg[i], fg);
+      bf16x8_to_f32(__ldg(wr + v), fw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot += fg[j] * fw[j] * fx[j];
+    }
+  }
+  dot = warp_sum(dot);
+  const float r = rstd[row];
+  const float c = dot * r * r * r / static_cast<float>(d);
+  uint4* dxr = reinterpret_cast<uint4*>(dx + off);
+  const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + off) : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int v = i * 32 + lane;
+    if (v < nvec) {
+      float fx[8], fg[8], fw[8], o[8];
+      bf16x8_to_f32(bx[i], fx);
+      bf16x8_to_f32(bg[i], fg);
+      bf16x8_to_f32(__ldg(wr + v), fw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fg[j] * fw[j] * r - fx[j] * c;
+      if (rr) {
+        float fr[8];
+        bf16x8_to_f32(ldg_stream(rr + v), fr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += fr[j];
+      }
+      dxr[v] = f32_to_bf16x8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: rotary embedding, half-split convention (HF rotate_half), in place on q and k of packed qkv.
+//   out[i] = x[i] cos - x[i+D/2] sin ; out[i+D/2] = x[i+D/2] cos + x[i] sin ; inverse flips sin.
+// cs table: [S][D/2] float2(cos, sin), built in double precision on the host.
+// ------------------------------------------------------------------------------------------
+__global__ void rope_kernel(bf16* __restrict__ qkv, const float2* __restrict__ cs, int S, int H, int D, int inverse,
+                            long long total_vec) {
+  // one thread handles 8 consecutive i (one uint4 from each half) of one (token, q|k, head)
+  const int half = D >> 1;
+  const int vec_per_head = half >> 3;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total_vec;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int iv = static_cast<int>(t % vec_per_head);
+    long long r = t / vec_per_head;
+    const int h = static_cast<int>(r % H);
+    r /= H;
+    const int which = static_cast<int>(r % 2);  // 0 = q, 1 = k
+    const long long m = r / 2;
+    const int pos = static_cast<int>(m % S);
+    bf16* base = qkv + m * (3LL * H * D) + static_cast<long long>(which) * H * D + static_cast<long long>(h) * D + iv * 8;
+    uint4 lo = *reinterpret_cast<uint4*>(base);
+    uint4 hi = *reinterpret_cast<uint4*>(base + half);
+    float a[8], b[8];
+    bf16x8_to_f32(lo, a);
+    bf16x8_to_f32(hi, b);
+    const float2* c = cs + static_cast<size_t>(pos) * half + iv * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 v = __ldg(c + j);
+      const float sn = inverse ? -v.y : v.y;
+      const float x0 = a[j], x1 = b[j];
+      a[j] = x0 * v.x - x1 * sn;
+      b[j] = x1 * v.x + x0 * sn;
+    }
+    *reinterpret_cast<uint4*>(base) = f32_to_bf16x8(a);
+    *reinterpret_cast<uint4*>(base + half) = f32_to_bf16x8(b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SwiGLU elementwise (HF LlamaMLP: down(silu(gate(x)) * up(x))) on packed [gate | up].
+// ------------------------------------------------------------------------------------------
+__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int M, int F) {
+  const int vecF = F >> 3;
+  const long long total = static_cast<long long>(M) * vecF;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = t / vecF;
+    const int v = static_cast<int>(t % vecF);
+    const uint4* g = reinterpret_cast<const uint4*>(gu + m * 2LL * F) + v;
+    const uint4* u = reinterpret_cast<const uint4*>(gu + m * 2LL * F + F) + v;
+    float fg[8], fu[8];
+    bf16x8_to_f32(ldg_stream(g), fg);
+    bf16x8_to_f32(ldg_stream(u), fu);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = 1.f / (1.f + __expf(-fg[j]));
+      fg[j] = fg[j] * s * fu[j];
+    }
+    reinterpret_cast<uint4*>(act + m * static_cast<long long>(F))[v] = f32_to_bf16x8(fg);
+  }
+}
+__global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __restrict__ gu, bf16* __restrict__ dgu,
+                                  int M, int F) {
+  const int vecF = F >> 3;
+  const long long total = static_cast<long long>(M) * vecF;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = t / vecF;
+    const int v = static_cast<int>(t % vecF);
+    float fg[8], fu[8], fd[8], og[8], ou[8];
+    bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(gu + m * 2LL * F) + v), fg);
+    bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(gu + m * 2LL * F + F) + v), fu);
+    bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(dact + m * static_cast<long long>(F)) + v), fd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = 1.f / (1.f + __expf(-fg[j]));
+      const float silu = fg[j] * s;
+      ou[j] = fd[j] * silu;
+      og[j] = fd[j] * fu[j] * (s + silu * (1.f - s));  // d/dg [g*sigmoid(g)] = s + g*s*(1-s)
+    }
+    reinterpret_cast<uint4*>(dgu + m * 2LL * F)[v] = f32_to_bf16x8(og);
+    reinterpret_cast<uint4*>(dgu + m * 2LL * F + F)[v] = f32_to_bf16x8(ou);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K9: shifted-label cross entropy (HF ForCausalLMLoss: logits[..., :-1] vs labels[..., 1:],
+// ignore_index -100, mean over valid tokens).
+// ------------------------------------------------------------------------------------------
+__global__ void shift_labels_kernel(const int32_t* __restrict__ labels, int32_t* __restrict__ shifted,
+                                    int32_t* __restrict__ n_valid, int B, int S) {
+  __shared__ int sh[32];
+  int cnt = 0;
+  const int total = B * S;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int t = i % S;
+    int v = (t == S - 1) ? -100 : labels[i + 1];
+    shifted[i] = v;
+    cnt += (v >= 0) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    *n_valid = t;
+  }
+}
+
+// one block per row: online (max, sum-exp) in one read, then p - onehot scaled by 1/n_valid.
+__global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logits, long long ldl,
+                                                 const int32_t* __restrict__ labels, const int32_t* __restrict__ n_valid,
+                                                 float* __restrict__ row_loss, bf16* __restrict__ dlogits, long long ldd,
+                                                 int V) {
+  __shared__ float shm[8], shs[8];
+  __shared__ float s_max, s_sum;
+  const int row = blockIdx.x;
+  const int label = labels[row];
+  bf16* drow = dlogits ? dlogits + static_cast<long long>(row) * ldd : nullptr;
+  const int nv4 = V >> 2;
+  if (label < 0 || label >= V) {  // ignored token: zero gradient row, zero loss
+    if (threadIdx.x == 0) row_loss[row] = 0.f;
+    if (drow) {
+      uint2 z = make_uint2(0u, 0u);
+      for (int i = threadIdx.x; i < nv4; i += blockDim.x) reinterpret_cast<uint2*>(drow)[i] = z;
+      for (int i = (nv4 << 2) + threadIdx.x; i < V; i += blockDim.x) drow[i] = __float2bfloat16_rn(0.f);
+    }
+    return;
+  }
+  const float* lrow = logits + static_cast<long long>(row) * ldl;
+  float mx = -INFINITY, sm = 0.f;
+  for (int i = threadIdx.x; i < nv4; i += blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(lrow) + i);
+    const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    if (m4 > mx) { sm *= __expf(mx - m4); mx = m4; }
+    sm += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+  }
+  for (int i = (nv4 << 2) + threadIdx.x; i < V; i += blockDim.x) {
+    const float v = lrow[i];
+    if (v > mx) { sm *= __expf(mx - v); mx = v; }
+    sm += __expf(v - mx);
+  }
+  // warp then block combine of (max, sum)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sm, o);
+    const float nm = fmaxf(mx, om);
+    sm = sm * __expf(mx - nm) + os * __expf(om - nm);
+    mx = nm;
+  }
+  if ((threadIdx.x & 31) == 0) { shm[threadIdx.x >> 5] = mx; shs[threadIdx.x >> 5] = sm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M0 = shm[0], S0 = shs[0];
+    for (int i = 1; i < (blockDim.x >> 5); ++i) {
+      const float nm = fmaxf(M0, shm[i]);
+      S0 = S0 * __expf(M0 - nm) + shs[i] * __expf(shm[i] - nm);
+      M0 = nm;
+    }
+    s_max = M0;
+    s_sum = S0;
+    row_loss[row] = (M0 + logf(S0)) - lrow[label];
+  }
+  __syncthreads();
+  if (!drow) return;
+  const float M0 = s_max;
+  const float inv = 1.f / s_sum;
+  const float scale = 1.f / static_cast<float>(max(*n_valid, 1));
+  for (int i = threadIdx.x; i < nv4; i += blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(lrow) + i);
+    float p0 = __expf(v.x - M0) * inv, p1 = __expf(v.y - M0) * inv, p2 = __expf(v.z - M0) * inv, p3 = __expf(v.w - M0) * inv;
+    const int c = i << 2;
+    if (label >= c && label < c + 4) {
+      if (label == c) p0 -= 1.f; else if (label == c + 1) p1 -= 1.f; else if (label == c + 2) p2 -= 1.f; else p3 -= 1.f;
+    }
+    uint2 o;
+    o.x = pack_bf16x2(p0 * scale, p1 * scale);
+    o.y = pack_bf16x2(p2 * scale, p3 * scale);
+    reinterpret_cast<uint2*>(drow)[i] = o;
+  }
+  for (int i = (nv4 << 2) + threadIdx.x; i < V; i += blockDim.x) {
+    float p = __expf(lrow[i] - M0) * inv;
+    if (i == label) p -= 1.f;
+    drow[i] = __float2bfloat16_rn(p * scale);
+  }
+}
+
+__global__ void loss_reduce_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ n_valid,
+                                   float* __restrict__ loss, int M) {
+  __shared__ float sh[32];
+  // fixed assignment of rows to threads + fixed-order combine => bitwise reproducible
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) acc += static_cast<double>(row_loss[i]);
+  float v = static_cast<float>(acc);
+  v = block_sum(v, sh);
+  if (threadIdx.x == 0) *loss = v / static_cast<float>(max(*n_valid, 1));
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n, int splits) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[k * n + i];
+    out[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K11: gradient norm (deterministic two-stage) and K13: fused clip + AdamW
+// ------------------------------------------------------------------------------------------
+constexpr int SUMSQ_BLOCKS = 296;
+__global__ void sumsq_stage1(const float* __restrict__ g, long long n, float* __restrict__ scratch) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) acc += g[i] * g[i];
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = acc;
+}
+__global__ void sumsq_stage2(const float* __restrict__ scratch, int nblocks, float* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < nblocks; ++i) s += static_cast<double>(scratch[i]);
+    *out = static_cast<float>(s);
+  }
+}
+
+// torch.optim.AdamW (decoupled weight decay, no amsgrad) fused with torch.nn.utils.clip_grad_norm_:
+//   clip = min(1, max_norm / (||g|| + 1e-6));  p *= 1 - lr*wd;  m,v update;  p -= lr/bias1 * m / (sqrt(v)/sqrt(bias2) + eps)
+__global__ void adamw_kernel(AdamWArgs a) {
+  float gs = a.grad_scale;
+  if (a.sumsq) {
+    const float norm = sqrtf(*a.sumsq) * a.grad_scale;
+    if (a.grad_norm_out && blockIdx.x == 0 && threadIdx.x == 0) *a.grad_norm_out = norm;
+    if (a.max_grad_norm > 0.f) {
+      const float coef = a.max_grad_norm / (norm + 1e-6f);
+      if (coef < 1.f) gs *= coef;
+    }
+  }
+  const float step = a.lr / a.bias1;
+  const float rs2 = rsqrtf(a.bias2);
+  const float decay = 1.f - a.lr * a.weight_decay;
+  const long long n4 = a.n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 p = reinterpret_cast<float4*>(a.p)[i];
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.g) + i);
+    float4 m = reinterpret_cast<float4*>(a.m)[i];
+    float4 v = reinterpret_cast<float4*>(a.v)[i];
+    float* pp = &p.x; const float* gp = &g4.x; float* mp = &m.x; float* vp = &v.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = gp[j] * gs;
+      pp[j] *= decay;
+      mp[j] = a.beta1 * mp[j] + (1.f - a.beta1) * g;
+      vp[j] = a.beta2 * vp[j] + (1.f - a.beta2) * g * g;
+      const float denom = sqrtf(vp[j]) * rs2 + a.eps;
+      pp[j] -= step * (mp[j] / denom);
+    }
+    reinterpret_cast<float4*>(a.p)[i] = p;
+    reinterpret_cast<float4*>(a.m)[i] = m;
+    reinterpret_cast<float4*>(a.v)[i] = v;
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = (n4 << 2) + threadIdx.x; i < a.n; i += blockDim.x) {
+      const float g = a.g[i] * gs;
+      float p = a.p[i] * decay;
+      const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+      const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+      p -= step * (m / (sqrtf(v) * rs2 + a.eps));
+      a.p[i] = p; a.m[i] = m; a.v[i] = v;
+    }
+  }
+}
+
+__global__ void cast2d_kernel(const float* __restrict__ src, long long lds, bf16* __restrict__ dst, long long ldd, int rows,
+                              int cols, float scale, int transpose) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(t / cols), c = static_cast<int>(t % cols);
+    const float v = src[r * lds + c] * scale;
+    if (transpose) dst[c * ldd + r] = __float2bfloat16_rn(v);
+    else dst[r * ldd + c] = __float2bfloat16_rn(v);
+  }
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void fill_normal_kernel(bf16* __restrict__ p, long long n, float std, uint64_t seed) {
+  const long long n2 = (n + 1) >> 1;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint64_t h = splitmix64(seed * 0x100000001B3ull + static_cast<uint64_t>(i));
+    const float u1 = (static_cast<float>(h >> 40) + 1.f) * (1.f / 16777217.f);
+    const float u2 = static_cast<float>((h >> 8) & 0xFFFFFFull) * (1.f / 16777216.f);
+    const float r = sqrtf(-2.f * logf(u1));
+    float s, c;
+    sincosf(6.283185307179586f * u2, &s, &c);
+    p[2 * i] = __float2bfloat16_rn(r * c * std);
+    if (2 * i + 1 < n) p[2 * i + 1] = __float2bfloat16_rn(r * s * std);
+  }
+}
+__global__ void fill_const_kernel(bf16* __restrict__ p, long long n, float v) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    p[i] = __float2bfloat16_rn(v);
+}
+
+inline int grid_for(long long work, int block, int max_blocks = 148 * 16) {
+  long long g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+cudaError_t embedding_fwd(const int32_t* ids, const bf16* table, bf16* out, int M, int d, int vocab, cudaStream_t s) {
+  if (d % 8) return cudaErrorInvalidValue;
+  embedding_kernel<<<M, 256, 0, s>>>(ids, table, out, d, vocab);
+  return cudaGetLastError();
+}
+
+cudaError_t rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int M, int d, float eps, cudaStream_t s) {
+  if (d % 8 || d > 8192) return cudaErrorInvalidValue;
+  const int rows_per_block = 8;
+  const int grid = (M + rows_per_block - 1) / rows_per_block;
+  if (d <= 1024) rmsnorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, w, y, rstd, M, d, eps);
+  else if (d <= 4096) rmsnorm_fwd_kernel<16><<<grid, 256, 0, s>>>(x, w, y, rstd, M, d, eps);
+  else rmsnorm_fwd_kernel<32><<<grid, 256, 0, s>>>(x, w, y, rstd, M, d, eps);
+  return cudaGetLastError();
+}
+
+cudaError_t rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx, int M,
+                        int d, cudaStream_t s) {
+  if (d % 8 || d > 8192) return cudaErrorInvalidValue;
+  const int rows_per_block = 8;
+  const int grid = (M + rows_per_block - 1) / rows_per_block;
+  if (d <= 1024) rmsnorm_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres, dx, M, d);
+  else if (d <= 4096) rmsnorm_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres, dx, M, d);
+  else rmsnorm_bwd_kernel<32><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres, dx, M, d);
+  return cudaGetLastError();
+}
+
+cudaError_t rope_qk_inplace_table(bf16* qkv, const float2* cs, int B, int S, int H, int D, int inverse, cudaStream_t s) {
+  if (D % 16) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(B) * S * 2 * H * (D / 16);
+  rope_kernel<<<grid_for(total, 256), 256, 0, s>>>(qkv, cs, S, H, D, inverse, total);
+  return cudaGetLastError();
+}
+
+cudaError_t swiglu_fwd(const bf16* gu, bf16* act, int M, int F, cudaStream_t s) {
+  if (F % 8) return cudaErrorInvalidValue;
+  swiglu_fwd_kernel<<<grid_for(static_cast<long long>(M) * (F / 8), 256), 256, 0, s>>>(gu, act, M, F);
+  return cudaGetLastError();
+}
+cudaError_t swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int M, int F, cudaStream_t s) {
+  if (F % 8) return cudaErrorInvalidValue;
+  swiglu_bwd_kernel<<<grid_for(static_cast<long long>(M) * (F / 8), 256), 256, 0, s>>>(dact, gu, dgu, M, F);
+  return cudaGetLastError();
+}
+
+cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_valid, int B, int S, cudaStream_t s) {
+  shift_labels_kernel<<<1, 1024, 0, s>>>(labels, shifted, n_valid, B, S);
+  return cudaGetLastError();
+}
+
+cudaError_t cross_entropy_fwd_bwd(const float* logits, int64_t ldl, const int32_t* labels, const int32_t* n_valid,
+                                  float* row_loss, bf16* dlogits, int64_t ldd, int M, int V, cudaStream_t s) {
+  if ((ldl & 3) || (ldd & 3)) return cudaErrorInvalidValue;
+  ce_kernel<<<M, 256, 0, s>>>(logits, ldl, labels, n_valid, row_loss, dlogits, ldd, V);
+  return cudaGetLastError();
+}
+
+cudaError_t loss_reduce(const float* row_loss, const int32_t* n_valid, float* loss, int M, cudaStream_t s) {
+  loss_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, n_valid, loss, M);
+  return cudaGetLastError();
+}
+
+cudaError_t sum_partials(const float* partial, float* out, int64_t n, int splits, cudaStream_t s) {
+  sum_partials_kernel<<<grid_for(n, 256), 256, 0, s>>>(partial, out, n, splits);
+  return cudaGetLastError();
+}
+
+cudaError_t sumsq(const float* g, int64_t n, float* scratch, float* out, cudaStream_t s) {
+  sumsq_stage1<<<SUMSQ_BLOCKS, 256, 0, s>>>(g, n, scratch);
+  sumsq_stage2<<<1, 32, 0, s>>>(scratch, SUMSQ_BLOCKS, out);
+  return cudaGetLastError();
+}
+
+cudaError_t adamw_step(const AdamWArgs& a, cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(a.p) | reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.m) |
+       reinterpret_cast<uintptr_t>(a.v)) & 15)
+    return cudaErrorInvalidValue;
+  adamw_kernel<<<grid_for(a.n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t cast_f32_to_bf16_2d(const float* src, int64_t lds, bf16* dst, int64_t ldd, int rows, int cols, float scale,
+                                int transpose, cudaStream_t s) {
+  cast2d_kernel<<<grid_for(static_cast<long long>(rows) * cols, 256), 256, 0, s>>>(src, lds, dst, ldd, rows, cols, scale,
+                                                                                  transpose);
+  return cudaGetLastError();
+}
+
+cudaError_t fill_normal_bf16(bf16* p, int64_t n, float std, uint64_t seed, cudaStream_t s) {
+  fill_normal_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, s>>>(p, n, std, seed);
+  return cudaGetLastError();
+}
+cudaError_t fill_const_bf16(bf16* p, int64_t n, float v, cudaStream_t s) {
+  fill_const_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, v);
+  return cudaGetLastError();
+}
+
+}  // namespace dtx

@@ -1,0 +1,395 @@
+// tcgen05 / TMA bf16 GEMM for sm_100a — the contraction engine of the LoRA-SFT step.
+//
+// Replaces the cuBLAS hgemm calls hidden behind nn.Linear / peft lora.Linear on the reference's hot
+// path (SURVEY §2.3 K3,K4,K7,K8,K10; call sites cmd/tuning/train.py:236-242,268-280,299).
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer     : cp.async.bulk.tensor loads of A/B k-blocks into a STAGES-deep smem ring
+//   warp 1      MMA issuer       : one thread issues tcgen05.mma (128 x BN x 16 per instruction), accumulator in TMEM
+//   warps 2..5  epilogue         : tcgen05.ld TMEM -> registers -> (convert / +residual) -> global
+// TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+// The contraction may be extended by a second (A2,B2) segment: that is how the rank-r LoRA update is
+// accumulated into the same TMEM tile as the frozen base weight (one extra k-block, no extra pass).
+#include "common.cuh"
+#include "kernels.h"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace dtx {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr int GROUP_M = 16;
+
+struct GemmKParams {
+  int M, N;
+  int kb1, kb2;     // 64-wide k-blocks in segment 1 / segment 2
+  int split_k;
+  int kb_per_split;
+  int m_tiles, n_tiles;
+  void* C;
+  long long ldc;
+  const bf16* R;
+  long long ldr;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128 : powers of two >= 32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB2);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int kb_total = p.kb1 + p.kb2;
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int total_tiles = tiles_mn * p.split_k;
+
+  auto decode = [&](int tile, int& m_blk, int& n_blk, int& split, int& kb_begin, int& kb_end) {
+    split = tile / tiles_mn;
+    int t = tile - split * tiles_mn;
+    const int per_group = GROUP_M * p.n_tiles;
+    int group = t / per_group;
+    int first_m = group * GROUP_M;
+    int gsz = min(GROUP_M, p.m_tiles - first_m);
+    int r = t - group * per_group;
+    m_blk = first_m + (r % gsz);
+    n_blk = r / gsz;
+    kb_begin = split * p.kb_per_split;
+    kb_end = min(kb_total, kb_begin + p.kb_per_split);
+  };
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m_blk, n_blk, split, kb_begin, kb_end;
+        decode(tile, m_blk, n_blk, split, kb_begin, kb_end);
+        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          const bool seg2 = kb >= p.kb1;
+          const int kk = (seg2 ? kb - p.kb1 : kb) * BK;
+          const CUtensorMap* ma = seg2 ? &tmA2 : &tmA;
+          const CUtensorMap* mb = seg2 ? &tmB2 : &tmB;
+          if (!A_MN) {
+            tma_load_2d(a_dst, ma, &full_bar[stage], kk, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, ma, &full_bar[stage], m0 + 64 * j, kk);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, mb, &full_bar[stage], kk, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, mb, &full_bar[stage], n0 + 64 * j, kk);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m_blk, n_blk, split, kb_begin, kb_end;
+        decode(tile, m_blk, n_blk, split, kb_begin, kb_end);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) {
+            const uint64_t da = A_MN ? umma_desc_mnmajor(a_base + k16 * 2048, 8192) : umma_desc_kmajor(a_base + k16 * 32);
+            const uint64_t db = B_MN ? umma_desc_mnmajor(b_base + k16 * 2048, 8192) : umma_desc_kmajor(b_base + k16 * 32);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb_begin || k16 > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m_blk, n_blk, split, kb_begin, kb_end;
+      decode(tile, m_blk, n_blk, split, kb_begin, kb_end);
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const bool full = (col0 + 32 <= p.N);
+        if (EPI == EPI_F32) {
+          float* crow = reinterpret_cast<float*>(p.C) + static_cast<long long>(split) * p.M * p.ldc +
+                        static_cast<long long>(row) * p.ldc + col0;
+          if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<uint4*>(crow)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __uint_as_float(v[j]);
+          }
+        } else {
+          bf16* crow = reinterpret_cast<bf16*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (EPI == EPI_BF16_ADD) {
+            const bf16* rrow = p.R + static_cast<long long>(row) * p.ldr + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 r = reinterpret_cast<const uint4*>(rrow)[j];
+                float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), cc = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
+                f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+                f[8 * j + 4] += cc.x; f[8 * j + 5] += cc.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+              }
+            } else {
+              for (int j = 0; j < 32 && col0 + j < p.N; ++j) f[j] += __bfloat162float(rrow[j]);
+            }
+          }
+          if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              reinterpret_cast<uint4*>(crow)[j] = o;
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __float2bfloat16_rn(f[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+}  // namespace
+
+// 2-D bf16 tensor map over a row-major [outer, inner] array with row stride ld (elements), 128B swizzle.
+bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                       uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int gemm_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+namespace {
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+cudaError_t launch(const GemmArgs& a, cudaStream_t s) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap tA, tB, tA2, tB2;
+  bool ok = true;
+  // K-major operand: global [rows, K], box {64 k, rows_per_tile}; MN-major: global [K, cols], box {64 cols, 64 k}
+  ok &= A_MN ? make_tmap_2d_bf16(&tA, a.A, a.M, a.K, a.lda, 64, 64) : make_tmap_2d_bf16(&tA, a.A, a.K, a.M, a.lda, 64, BM);
+  ok &= B_MN ? make_tmap_2d_bf16(&tB, a.B, a.N, a.K, a.ldb, 64, 64) : make_tmap_2d_bf16(&tB, a.B, a.K, a.N, a.ldb, 64, BN);
+  if (a.K2 > 0) {
+    ok &= A_MN ? make_tmap_2d_bf16(&tA2, a.A2, a.M, a.K2, a.lda2, 64, 64)
+               : make_tmap_2d_bf16(&tA2, a.A2, a.K2, a.M, a.lda2, 64, BM);
+    ok &= B_MN ? make_tmap_2d_bf16(&tB2, a.B2, a.N, a.K2, a.ldb2, 64, 64)
+               : make_tmap_2d_bf16(&tB2, a.B2, a.K2, a.N, a.ldb2, 64, BN);
+  } else {
+    tA2 = tA;
+    tB2 = tB;
+  }
+  if (!ok) return cudaErrorInvalidValue;
+
+  GemmKParams p;
+  p.M = a.M;
+  p.N = a.N;
+  p.kb1 = (a.K + BK - 1) / BK;
+  p.kb2 = (a.K2 + BK - 1) / BK;
+  p.split_k = a.split_k < 1 ? 1 : a.split_k;
+  int kb_total = p.kb1 + p.kb2;
+  if (p.split_k > kb_total) p.split_k = kb_total;
+  p.kb_per_split = (kb_total + p.split_k - 1) / p.split_k;
+  // every split must own at least one k-block (an empty split would publish a stale accumulator)
+  while (p.split_k > 1 && (p.split_k - 1) * p.kb_per_split >= kb_total) --p.split_k;
+  if (p.split_k != (a.split_k < 1 ? 1 : a.split_k)) return cudaErrorInvalidValue;
+  p.m_tiles = (a.M + BM - 1) / BM;
+  p.n_tiles = (a.N + BN - 1) / BN;
+  p.C = a.C;
+  p.ldc = a.ldc;
+  p.R = a.R;
+  p.ldr = a.ldr;
+  int total = p.m_tiles * p.n_tiles * p.split_k;
+  int grid = total < gemm_num_sms() ? total : gemm_num_sms();
+  if (grid <= 0) return cudaSuccess;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tA, tB, tA2, tB2, p);
+  return cudaGetLastError();
+}
+
+template <int BN, bool A_MN, bool B_MN>
+cudaError_t launch_epi(const GemmArgs& a, cudaStream_t s) {
+  switch (a.epilogue) {
+    case EPI_BF16: return launch<BN, A_MN, B_MN, EPI_BF16>(a, s);
+    case EPI_F32: return launch<BN, A_MN, B_MN, EPI_F32>(a, s);
+    case EPI_BF16_ADD: return launch<BN, A_MN, B_MN, EPI_BF16_ADD>(a, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <int BN>
+cudaError_t launch_major(const GemmArgs& a, cudaStream_t s) {
+  if (!a.a_mn_major && !a.b_mn_major) return launch_epi<BN, false, false>(a, s);
+  if (!a.a_mn_major && a.b_mn_major) return launch_epi<BN, false, true>(a, s);
+  if (a.a_mn_major && a.b_mn_major) return launch_epi<BN, true, true>(a, s);
+  return cudaErrorInvalidValue;  // (MN-major A, K-major B) is not used on the training path
+}
+
+}  // namespace
+
+cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaErrorInvalidValue;
+  if (a.split_k > 1 && a.epilogue != EPI_F32) return cudaErrorInvalidValue;
+  if (a.epilogue == EPI_BF16_ADD && a.R == nullptr) return cudaErrorInvalidValue;
+  // TMA needs 16-byte aligned bases and row strides
+  if ((a.lda & 7) || (a.ldb & 7) || (reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15))
+    return cudaErrorInvalidValue;
+  if (a.K2 > 0 && ((a.lda2 & 7) || (a.ldb2 & 7) || !a.A2 || !a.B2)) return cudaErrorInvalidValue;
+  int bn = a.block_n;
+  if (bn == 0) bn = (a.N <= 64) ? 64 : ((a.N <= 128) ? 128 : 256);
+  switch (bn) {
+    case 64: return launch_major<64>(a, s);
+    case 128: return launch_major<128>(a, s);
+    case 256: return launch_major<256>(a, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace dtx

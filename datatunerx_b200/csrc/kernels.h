@@ -1,0 +1,102 @@
+// Internal (C++) launch API of libdtxtune's sm_100a kernels.  The public surface is include/dtxtune.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace dtx {
+
+typedef __nv_bfloat16 bf16;
+
+enum GemmEpilogue {
+  EPI_BF16 = 0,      // C[bf16] = acc
+  EPI_F32 = 1,       // C[f32]  = acc            (logits, split-K partials)
+  EPI_BF16_ADD = 2,  // C[bf16] = acc + R[bf16]  (residual stream update)
+};
+
+// C[M,N] = A[M,K] * B[N,K]^T (+ A2[M,K2] * B2[N,K2]^T), bf16 operands, fp32 accumulation in TMEM.
+//   a_mn_major = 0: A is row-major [M, K]   (contraction dim contiguous)   lda = row stride (elements)
+//   a_mn_major = 1: A is row-major [K, M]   (M contiguous)                 lda = row stride
+//   b_mn_major = 0: B is row-major [N, K]                                   ldb = row stride
+//   b_mn_major = 1: B is row-major [K, N]                                   ldb = row stride
+// The optional second segment (A2,B2,K2) extends the contraction: it is how the LoRA up-projection
+// is accumulated into the same TMEM tile as the frozen base projection.
+struct GemmArgs {
+  const bf16* A = nullptr; int64_t lda = 0; int a_mn_major = 0;
+  const bf16* B = nullptr; int64_t ldb = 0; int b_mn_major = 0;
+  const bf16* A2 = nullptr; int64_t lda2 = 0;
+  const bf16* B2 = nullptr; int64_t ldb2 = 0;
+  int K2 = 0;
+  void* C = nullptr; int64_t ldc = 0;
+  const bf16* R = nullptr; int64_t ldr = 0;
+  int M = 0, N = 0, K = 0;
+  int epilogue = EPI_BF16;
+  int split_k = 1;  // >1 requires EPI_F32; C is [split_k][M][ldc] partial sums
+  int block_n = 0;  // 0 = auto (256 for wide N, 64 for N <= 64)
+};
+cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s);
+int gemm_num_sms();
+
+// ---------------------------------------------------------------------------------------------
+// flash attention (causal, head_dim 128), packed qkv layout [B*S, 3*H*128] (q | k | v per token)
+// ---------------------------------------------------------------------------------------------
+struct AttnArgs {
+  const bf16* qkv = nullptr;  // [B*S, 3*H*D]
+  bf16* out = nullptr;        // [B*S, H*D]
+  float* lse = nullptr;       // [B, H, S]  natural-log sum-exp of scaled scores
+  int B = 0, S = 0, H = 0;
+  float scale = 0.f;
+  // backward
+  const bf16* dout = nullptr;  // [B*S, H*D]
+  bf16* dqkv = nullptr;        // [B*S, 3*H*D]
+  float* delta = nullptr;      // [B, H, S] scratch: rowsum(dO * O)
+};
+cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s);
+cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// HBM-bound kernels
+// ---------------------------------------------------------------------------------------------
+cudaError_t embedding_fwd(const int32_t* ids, const bf16* table, bf16* out, int M, int d, int vocab, cudaStream_t s);
+// y = w * x * rsqrt(mean(x^2) + eps);  rstd saved for backward
+cudaError_t rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int M, int d, float eps, cudaStream_t s);
+// dx = rstd * (w*dy) - x * rstd^3 * mean(w*dy*x)  (+ dres if not null)
+cudaError_t rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx,
+                        int M, int d, cudaStream_t s);
+// half-split rotary embedding applied in place to the q and k thirds of packed qkv. inverse=1 applies R^T (backward)
+// cs = [S][D/2] float2(cos, sin) table built on the host in double precision
+cudaError_t rope_qk_inplace_table(bf16* qkv, const float2* cs, int B, int S, int H, int D, int inverse, cudaStream_t s);
+// gu = [gate | up] packed [M, 2F]; act[M,F] = silu(gate) * up
+cudaError_t swiglu_fwd(const bf16* gu, bf16* act, int M, int F, cudaStream_t s);
+// dgu[M,2F] from dact[M,F] and saved gu
+cudaError_t swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int M, int F, cudaStream_t s);
+// labels_shift[b,t] = labels[b,t+1] (last = -100); n_valid counted into *n_valid (int32)
+cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_valid, int B, int S, cudaStream_t s);
+// softmax cross-entropy over fp32 logits [M,V]; row_loss[M] (0 for ignored rows); dlogits bf16 = (p - onehot)/n_valid
+cudaError_t cross_entropy_fwd_bwd(const float* logits, int64_t ldl, const int32_t* labels, const int32_t* n_valid,
+                                  float* row_loss, bf16* dlogits, int64_t ldd, int M, int V, cudaStream_t s);
+// loss = sum(row_loss)/n_valid, fixed summation order
+cudaError_t loss_reduce(const float* row_loss, const int32_t* n_valid, float* loss, int M, cudaStream_t s);
+// out[i] = sum_s partial[s][i]  (fixed order)
+cudaError_t sum_partials(const float* partial, float* out, int64_t n, int splits, cudaStream_t s);
+// sumsq of a flat fp32 buffer, deterministic two-stage; result in *out (fp32)
+cudaError_t sumsq(const float* g, int64_t n, float* scratch, float* out, cudaStream_t s);
+
+struct AdamWArgs {
+  float* p; const float* g; float* m; float* v; int64_t n;
+  float lr, beta1, beta2, eps, weight_decay;
+  float bias1, bias2;          // 1 - beta^t
+  float grad_scale;            // 1/(world*grad_accum), applied before clipping
+  const float* sumsq;          // device: sum of squares of the *unscaled* flat grad
+  float max_grad_norm;         // <= 0 disables clipping
+  float* grad_norm_out;        // device: scaled norm (pre-clip), may be null
+};
+cudaError_t adamw_step(const AdamWArgs& a, cudaStream_t s);
+
+// fp32 -> bf16 with scale, strided 2-D (used to refresh the bf16 LoRA shadows)
+cudaError_t cast_f32_to_bf16_2d(const float* src, int64_t lds, bf16* dst, int64_t ldd, int rows, int cols, float scale,
+                                int transpose, cudaStream_t s);
+cudaError_t fill_normal_bf16(bf16* p, int64_t n, float std, uint64_t seed, cudaStream_t s);
+cudaError_t fill_const_bf16(bf16* p, int64_t n, float v, cudaStream_t s);
+
+}  // namespace dtx

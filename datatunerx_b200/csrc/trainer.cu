@@ -1,0 +1,899 @@
+// The training step of the DataTunerX fine-tuning worker, rebuilt for B200.
+//
+// Replaces, for the data-parallel LoRA-SFT path, what the reference reaches through
+//   cmd/tuning/train.py:299  trainer.train()  ->  HF Trainer.training_step / LlamaForCausalLM.forward /
+//   peft lora.Linear / DeepSpeed ZeRO-0 all-reduce / clip_grad_norm_ / torch.optim.AdamW / get_scheduler
+// (SURVEY §8a rows a7-a11).  One dtx_trainer = one GPU rank.  No PyTorch, no CPU fallback.
+//
+// HBM layout: frozen base weights bf16 with q|k|v and gate|up row-concatenated so that one
+// GEMM serves each pair; LoRA masters fp32 in one flat buffer (A^T[d,r] | B[d,r] per target per layer) with
+// m, v and the gradient in identically laid-out flat buffers (one NCCL all-reduce, one AdamW launch);
+// bf16 "shadows" of the adapters padded to a 64-wide rank block feed the tensor-core GEMMs.
+// Activations needed by backward are kept (no recompute: 180 GB HBM makes gradient checkpointing pointless
+// for 7B LoRA at 16K tokens/step).
+#include "kernels.h"
+#include "../../include/dtxtune.h"
+
+#include <cuda.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+namespace dtx {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that libdtxtune.so has no link-time dependency (N=1 runs never touch it)
+// ------------------------------------------------------------------------------------------------
+struct UidByValue {  // ncclUniqueId is passed by value
+  char internal[128];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, UidByValue, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (api.handle) {
+      api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(api.handle, "ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<int (*)(void**, int, UidByValue, int)>(dlsym(api.handle, "ncclCommInitRank"));
+      api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
+          dlsym(api.handle, "ncclAllReduce"));
+      api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.handle, "ncclCommDestroy"));
+      api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.handle, "ncclGetErrorString"));
+    }
+  }
+  if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) return nullptr;
+  return &api;
+}
+constexpr int kNcclFloat32 = 7;
+constexpr int kNcclSum = 0;
+
+thread_local std::string g_error;
+
+// ------------------------------------------------------------------------------------------------
+// LoRA-specific small kernels
+// ------------------------------------------------------------------------------------------------
+// dst[n*r + j] (+)= sum_s part[s*split_stride + (row0+n)*ld + col0 + j]   (fixed order)
+__global__ void lora_gather_kernel(const float* __restrict__ part, int splits, long long split_stride, int ld, int row0,
+                                   int col0, int rows, int r, float* __restrict__ dst, int accumulate) {
+  const long long total = static_cast<long long>(rows) * r;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / r), j = static_cast<int>(i % r);
+    const float* src = part + static_cast<long long>(row0 + n) * ld + col0 + j;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += src[k * split_stride];
+    dst[i] = accumulate ? dst[i] + s : s;
+  }
+}
+
+// refresh bf16 shadows of all adapters from the fp32 masters.
+//   a_cat[l][(ti*r + j)*d + c]              = A^T[c*r + j]
+//   b_ext[l][(row0[ti] + n)*RP + ti*r + j]  = scale * B[n*r + j]
+struct ShadowArgs {
+  const float* params;
+  bf16* a_cat;
+  bf16* b_ext;
+  int L, d, r, RP, nt;
+  int row0[3];
+  float scale;
+};
+__global__ void lora_shadow_kernel(ShadowArgs a) {
+  const long long per_t = 2LL * a.d * a.r;
+  const long long per_l = per_t * a.nt;
+  const long long total = per_l * a.L;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int l = static_cast<int>(i / per_l);
+    long long rem = i - l * per_l;
+    const int ti = static_cast<int>(rem / per_t);
+    rem -= ti * per_t;
+    const float v = a.params[i];
+    if (rem < static_cast<long long>(a.d) * a.r) {
+      const int c = static_cast<int>(rem / a.r), j = static_cast<int>(rem % a.r);
+      a.a_cat[(static_cast<long long>(l) * a.RP + ti * a.r + j) * a.d + c] = __float2bfloat16_rn(v);
+    } else {
+      rem -= static_cast<long long>(a.d) * a.r;
+      const int n = static_cast<int>(rem / a.r), j = static_cast<int>(rem % a.r);
+      a.b_ext[(static_cast<long long>(l) * 3 * a.d + a.row0[ti] + n) * a.RP + ti * a.r + j] = __float2bfloat16_rn(v * a.scale);
+    }
+  }
+}
+
+struct Layer {
+  bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr, *norm1 = nullptr, *norm2 = nullptr;
+  bf16 *a_cat = nullptr, *b_ext = nullptr;                                               // shadows
+  bf16 *h1 = nullptr, *t = nullptr, *qkv = nullptr, *attn = nullptr, *x_mid = nullptr, *gu = nullptr;  // saved
+  float *lse = nullptr, *rstd1 = nullptr, *rstd2 = nullptr;
+};
+
+}  // namespace
+}  // namespace dtx
+
+using namespace dtx;
+
+struct dtx_trainer {
+  dtx_model_cfg mc{};
+  dtx_train_cfg tc{};
+  int device = 0, rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void* nccl_comm = nullptr;
+  std::string err;
+  std::vector<void*> allocs;
+  size_t bytes_allocated = 0;
+
+  int M = 0, RP = 0, nt = 0;
+  int target_row0[3] = {0, 0, 0};
+  int64_t n_train = 0;
+
+  bf16 *embed = nullptr, *lm_head = nullptr, *normf = nullptr;
+  std::vector<Layer> layers;
+  std::vector<bf16*> xs;  // residual stream, L+1 entries
+  bf16 *a_cat_all = nullptr, *b_ext_all = nullptr;
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+
+  // transients
+  bf16 *h2 = nullptr, *act = nullptr, *dact = nullptr, *dgu = nullptr, *dx_a = nullptr, *dx_b = nullptr, *dh = nullptr,
+       *dattn = nullptr, *dqkv = nullptr, *dt = nullptr, *dlogits = nullptr;
+  float *logits = nullptr, *rstdf = nullptr, *row_loss = nullptr, *delta = nullptr, *part_b = nullptr, *part_a = nullptr;
+  float *d_loss = nullptr, *d_sumsq = nullptr, *d_gnorm = nullptr, *d_scratch = nullptr;
+  int32_t *d_ids = nullptr, *d_labels = nullptr, *d_shift = nullptr, *d_nvalid = nullptr;
+  float2* rope_cs = nullptr;
+  int split_b = 1, split_a = 1;
+
+  bool weights_loaded[8] = {false};
+  bool have_weights = false, have_lora = false;
+  int micro_idx = 0;
+  int opt_step = 0;
+  int64_t launches = 0;
+  float last_ms = 0.f;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  template <typename T>
+  bool alloc(T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) {
+      fail(DTX_ERR_CUDA, "cudaMalloc(%zu bytes) failed after %zu bytes: %s", n * sizeof(T), bytes_allocated,
+           cudaGetErrorString(e));
+      return false;
+    }
+    allocs.push_back(q);
+    bytes_allocated += n * sizeof(T);
+    *p = static_cast<T*>(q);
+    return true;
+  }
+};
+
+namespace {
+
+#define CK(expr, nlaunch)                                                                        \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    t->launches += (nlaunch);                                                                    \
+  } while (0)
+
+int pick_split(int m_tiles, int kb_total) {
+  int s = (2 * gemm_num_sms() + m_tiles - 1) / m_tiles;
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  if (s > kb_total) s = kb_total;
+  // every split must own at least one k-block
+  while (s > 1 && (s - 1) * ((kb_total + s - 1) / s) >= kb_total) --s;
+  return s;
+}
+
+int create_buffers(dtx_trainer* t) {
+  const dtx_model_cfg& mc = t->mc;
+  const dtx_train_cfg& tc = t->tc;
+  const size_t d = mc.hidden, F = mc.ffn, V = mc.vocab, L = mc.n_layers, M = t->M, RP = t->RP;
+  bool ok = true;
+  ok = ok && t->alloc(&t->embed, V * d) && t->alloc(&t->lm_head, V * d) && t->alloc(&t->normf, d);
+  ok = ok && t->alloc(&t->a_cat_all, L * RP * d) && t->alloc(&t->b_ext_all, L * 3 * d * RP);
+  if (!ok) return DTX_ERR_CUDA;
+  cudaMemset(t->a_cat_all, 0, L * RP * d * sizeof(bf16));
+  cudaMemset(t->b_ext_all, 0, L * 3 * d * RP * sizeof(bf16));
+  t->layers.resize(L);
+  t->xs.resize(L + 1);
+  for (size_t l = 0; l <= L; ++l) ok = ok && t->alloc(&t->xs[l], M * d);
+  for (size_t l = 0; l < L && ok; ++l) {
+    Layer& y = t->layers[l];
+    ok = ok && t->alloc(&y.wqkv, 3 * d * d) && t->alloc(&y.wo, d * d) && t->alloc(&y.wgu, 2 * F * d) &&
+         t->alloc(&y.wdown, d * F) && t->alloc(&y.norm1, d) && t->alloc(&y.norm2, d);
+    y.a_cat = t->a_cat_all + l * RP * d;
+    y.b_ext = t->b_ext_all + l * 3 * d * RP;
+    ok = ok && t->alloc(&y.h1, M * d) && t->alloc(&y.t, M * RP) && t->alloc(&y.qkv, M * 3 * d) &&
+         t->alloc(&y.attn, M * d) && t->alloc(&y.x_mid, M * d) && t->alloc(&y.gu, M * 2 * F);
+    ok = ok && t->alloc(&y.lse, static_cast<size_t>(tc.micro_batch) * mc.n_heads * tc.seq_len) && t->alloc(&y.rstd1, M) &&
+         t->alloc(&y.rstd2, M);
+  }
+  if (!ok) return DTX_ERR_CUDA;
+  ok = ok && t->alloc(&t->params, t->n_train) && t->alloc(&t->grads, t->n_train) && t->alloc(&t->adam_m, t->n_train) &&
+       t->alloc(&t->adam_v, t->n_train);
+  if (!ok) return DTX_ERR_CUDA;
+  cudaMemset(t->params, 0, t->n_train * sizeof(float));
+  cudaMemset(t->grads, 0, t->n_train * sizeof(float));
+  cudaMemset(t->adam_m, 0, t->n_train * sizeof(float));
+  cudaMemset(t->adam_v, 0, t->n_train * sizeof(float));
+  ok = ok && t->alloc(&t->h2, M * d) && t->alloc(&t->act, M * F) && t->alloc(&t->dact, M * F) && t->alloc(&t->dgu, M * 2 * F) &&
+       t->alloc(&t->dx_a, M * d) && t->alloc(&t->dx_b, M * d) && t->alloc(&t->dh, M * d) && t->alloc(&t->dattn, M * d) &&
+       t->alloc(&t->dqkv, M * 3 * d) && t->alloc(&t->dt, M * RP) && t->alloc(&t->dlogits, M * V) && t->alloc(&t->logits, M * V) &&
+       t->alloc(&t->rstdf, M) && t->alloc(&t->row_loss, M) &&
+       t->alloc(&t->delta, static_cast<size_t>(tc.micro_batch) * mc.n_heads * tc.seq_len);
+  const int kb_tok = (static_cast<int>(M) + 63) / 64;
+  t->split_b = pick_split((3 * static_cast<int>(d) + 127) / 128, kb_tok);
+  t->split_a = pick_split((static_cast<int>(d) + 127) / 128, kb_tok);
+  ok = ok && t->alloc(&t->part_b, static_cast<size_t>(t->split_b) * 3 * d * RP) &&
+       t->alloc(&t->part_a, static_cast<size_t>(t->split_a) * d * RP);
+  ok = ok && t->alloc(&t->d_loss, 4) && t->alloc(&t->d_sumsq, 4) && t->alloc(&t->d_gnorm, 4) && t->alloc(&t->d_scratch, 1024);
+  ok = ok && t->alloc(&t->d_ids, M) && t->alloc(&t->d_labels, M) && t->alloc(&t->d_shift, M) && t->alloc(&t->d_nvalid, 4);
+  ok = ok && t->alloc(&t->rope_cs, static_cast<size_t>(tc.seq_len) * (mc.head_dim / 2));
+  if (!ok) return DTX_ERR_CUDA;
+  // rotary table in double precision (HF LlamaRotaryEmbedding: inv_freq = theta^(-2i/D))
+  {
+    const int half = mc.head_dim / 2;
+    std::vector<float2> cs(static_cast<size_t>(tc.seq_len) * half);
+    for (int pos = 0; pos < tc.seq_len; ++pos)
+      for (int i = 0; i < half; ++i) {
+        // HF computes inv_freq and the angle in fp32; reproduce that rounding, then take cos/sin accurately
+        const float inv_freq = 1.0f / powf(mc.rope_theta, static_cast<float>(2 * i) / static_cast<float>(mc.head_dim));
+        const float ang = static_cast<float>(pos) * inv_freq;
+        cs[static_cast<size_t>(pos) * half + i] = make_float2(static_cast<float>(cos(static_cast<double>(ang))),
+                                                              static_cast<float>(sin(static_cast<double>(ang))));
+      }
+    cudaMemcpy(t->rope_cs, cs.data(), cs.size() * sizeof(float2), cudaMemcpyHostToDevice);
+  }
+  return DTX_OK;
+}
+
+int refresh_shadows(dtx_trainer* t) {
+  ShadowArgs a;
+  a.params = t->params;
+  a.a_cat = t->a_cat_all;
+  a.b_ext = t->b_ext_all;
+  a.L = t->mc.n_layers;
+  a.d = t->mc.hidden;
+  a.r = t->tc.lora_r;
+  a.RP = t->RP;
+  a.nt = t->nt;
+  for (int i = 0; i < 3; ++i) a.row0[i] = t->target_row0[i];
+  a.scale = t->tc.lora_alpha / static_cast<float>(t->tc.lora_r);
+  long long total = t->n_train;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  lora_shadow_kernel<<<grid, 256, 0, t->stream>>>(a);
+  CK(cudaGetLastError(), 1);
+  return DTX_OK;
+}
+
+// forward (+ backward) of one micro-batch whose ids/labels are already in t->d_ids / t->d_labels
+int fwd_bwd(dtx_trainer* t, bool backward) {
+  const dtx_model_cfg& mc = t->mc;
+  const dtx_train_cfg& tc = t->tc;
+  const int d = mc.hidden, F = mc.ffn, V = mc.vocab, L = mc.n_layers, M = t->M, RP = t->RP, H = mc.n_heads, D = mc.head_dim;
+  const int B = tc.micro_batch, S = tc.seq_len;
+  cudaStream_t s = t->stream;
+  const float att_scale = 1.0f / sqrtf(static_cast<float>(D));
+
+  CK(embedding_fwd(t->d_ids, t->embed, t->xs[0], M, d, V, s), 1);
+  for (int l = 0; l < L; ++l) {
+    Layer& y = t->layers[l];
+    CK(rmsnorm_fwd(t->xs[l], y.norm1, y.h1, y.rstd1, M, d, mc.rms_eps, s), 1);
+    {  // LoRA down-projection of all targets at once: t = h1 * A_cat^T   [M, RP]
+      GemmArgs g;
+      g.A = y.h1; g.lda = d; g.B = y.a_cat; g.ldb = d; g.C = y.t; g.ldc = RP;
+      g.M = M; g.N = RP; g.K = d; g.epilogue = EPI_BF16; g.block_n = 64;
+      CK(gemm_bf16(g, s), 1);
+    }
+    {  // qkv = h1 * Wqkv^T + t * B_ext^T : base projection and LoRA up-projection in one TMEM accumulator
+      GemmArgs g;
+      g.A = y.h1; g.lda = d; g.B = y.wqkv; g.ldb = d;
+      g.A2 = y.t; g.lda2 = RP; g.B2 = y.b_ext; g.ldb2 = RP; g.K2 = RP;
+      g.C = y.qkv; g.ldc = 3 * d; g.M = M; g.N = 3 * d; g.K = d; g.epilogue = EPI_BF16;
+      CK(gemm_bf16(g, s), 1);
+    }
+    CK(rope_qk_inplace_table(y.qkv, t->rope_cs, B, S, H, D, 0, s), 1);
+    {
+      AttnArgs a;
+      a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.scale = att_scale;
+      CK(attn_fwd(a, s), 1);
+    }
+    {  // x_mid = x + attn * Wo^T
+      GemmArgs g;
+      g.A = y.attn; g.lda = d; g.B = y.wo; g.ldb = d; g.C = y.x_mid; g.ldc = d; g.R = t->xs[l]; g.ldr = d;
+      g.M = M; g.N = d; g.K = d; g.epilogue = EPI_BF16_ADD;
+      CK(gemm_bf16(g, s), 1);
+    }
+    CK(rmsnorm_fwd(y.x_mid, y.norm2, t->h2, y.rstd2, M, d, mc.rms_eps, s), 1);
+    {  // [gate | up] = h2 * Wgu^T
+      GemmArgs g;
+      g.A = t->h2; g.lda = d; g.B = y.wgu; g.ldb = d; g.C = y.gu; g.ldc = 2 * F;
+      g.M = M; g.N = 2 * F; g.K = d; g.epilogue = EPI_BF16;
+      CK(gemm_bf16(g, s), 1);
+    }
+    CK(swiglu_fwd(y.gu, t->act, M, F, s), 1);
+    {  // x_next = x_mid + act * Wdown^T
+      GemmArgs g;
+      g.A = t->act; g.lda = F; g.B = y.wdown; g.ldb = F; g.C = t->xs[l + 1]; g.ldc = d; g.R = y.x_mid; g.ldr = d;
+      g.M = M; g.N = d; g.K = F; g.epilogue = EPI_BF16_ADD;
+      CK(gemm_bf16(g, s), 1);
+    }
+  }
+  CK(rmsnorm_fwd(t->xs[L], t->normf, t->h2, t->rstdf, M, d, mc.rms_eps, s), 1);
+  {  // fp32 logits (the reference patches lm_head to return fp32: cmd/tuning/train.py:256-264)
+    GemmArgs g;
+    g.A = t->h2; g.lda = d; g.B = t->lm_head; g.ldb = d; g.C = t->logits; g.ldc = V;
+    g.M = M; g.N = V; g.K = d; g.epilogue = EPI_F32;
+    CK(gemm_bf16(g, s), 1);
+  }
+  CK(shift_labels(t->d_labels, t->d_shift, t->d_nvalid, B, S, s), 1);
+  CK(cross_entropy_fwd_bwd(t->logits, V, t->d_shift, t->d_nvalid, t->row_loss, backward ? t->dlogits : nullptr, V, M, V, s), 1);
+  CK(loss_reduce(t->row_loss, t->d_nvalid, t->d_loss, M, s), 1);
+  if (!backward) return DTX_OK;
+
+  {  // d h_f = dlogits * W_lm
+    GemmArgs g;
+    g.A = t->dlogits; g.lda = V; g.B = t->lm_head; g.ldb = d; g.b_mn_major = 1; g.C = t->dh; g.ldc = d;
+    g.M = M; g.N = d; g.K = V; g.epilogue = EPI_BF16;
+    CK(gemm_bf16(g, s), 1);
+  }
+  CK(rmsnorm_bwd(t->dh, t->xs[L], t->normf, t->rstdf, nullptr, t->dx_a, M, d, s), 1);
+  bf16* cur = t->dx_a;
+  bf16* other = t->dx_b;
+  const int accumulate = t->micro_idx > 0 ? 1 : 0;
+  for (int l = L - 1; l >= 0; --l) {
+    Layer& y = t->layers[l];
+    {  // dact = dx * Wdown
+      GemmArgs g;
+      g.A = cur; g.lda = d; g.B = y.wdown; g.ldb = F; g.b_mn_major = 1; g.C = t->dact; g.ldc = F;
+      g.M = M; g.N = F; g.K = d; g.epilogue = EPI_BF16;
+      CK(gemm_bf16(g, s), 1);
+    }
+    CK(swiglu_bwd(t->dact, y.gu, t->dgu, M, F, s), 1);
+    {  // dh2 = [dgate | dup] * [Wg ; Wu]
+      GemmArgs g;
+      g.A = t->dgu; g.lda = 2 * F; g.B = y.wgu; g.ldb = d; g.b_mn_major = 1; g.C = t->dh; g.ldc = d;
+      g.M = M; g.N = d; g.K = 2 * F; g.epilogue = EPI_BF16;
+      CK(gemm_bf16(g, s), 1);
+    }
+    CK(rmsnorm_bwd(t->dh, y.x_mid, y.norm2, y.rstd2, cur, other, M, d, s), 1);  // other = d x_mid
+    {  // dattn = dx_mid * Wo
+      GemmArgs g;
+      g.A = other; g.lda = d; g.B = y.wo; g.ldb = d; g.b_mn_major = 1; g.C = t->dattn; g.ldc = d;
+      g.M = M; g.N = d; g.K = d; g.epilogue = EPI_BF16;
+      CK(gemm_bf16(g, s), 1);
+    }
+    {
+      AttnArgs a;
+      a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.scale = att_scale;
+      a.dout = t->dattn; a.dqkv = t->dqkv; a.delta = t->delta;
+      CK(attn_bwd(a, s), 3);
+    }
+    CK(rope_qk_inplace_table(t->dqkv, t->rope_cs, B, S, H, D, 1, s), 1);
+    {  // dt = dqkv * B_ext   [M, RP]
+      GemmArgs g;
+      g.A = t->dqkv; g.lda = 3 * d; g.B = y.b_ext; g.ldb = RP; g.b_mn_major = 1; g.C = t->dt; g.ldc = RP;
+      g.M = M; g.N = RP; g.K = 3 * d; g.epilogue = EPI_BF16; g.block_n = 64;
+      CK(gemm_bf16(g, s), 1);
+    }
+    {  // dh1 = dqkv * Wqkv + dt * A_cat
+      GemmArgs g;
+      g.A = t->dqkv; g.lda = 3 * d; g.B = y.wqkv; g.ldb = d; g.b_mn_major = 1;
+      g.A2 = t->dt; g.lda2 = RP; g.B2 = y.a_cat; g.ldb2 = d; g.K2 = RP;
+      g.C = t->dh; g.ldc = d; g.M = M; g.N = d; g.K = 3 * d; g.epilogue = EPI_BF16;
+      CK(gemm_bf16(g, s), 1);
+    }
+    {  // grad of B_ext (all rows): dqkv^T * t   [3d, RP], split over tokens
+      GemmArgs g;
+      g.A = t->dqkv; g.lda = 3 * d; g.a_mn_major = 1; g.B = y.t; g.ldb = RP; g.b_mn_major = 1;
+      g.C = t->part_b; g.ldc = RP; g.M = 3 * d; g.N = RP; g.K = M; g.epilogue = EPI_F32; g.split_k = t->split_b;
+      g.block_n = 64;
+      CK(gemm_bf16(g, s), 1);
+    }
+    {  // grad of A_cat^T: h1^T * dt   [d, RP]
+      GemmArgs g;
+      g.A = y.h1; g.lda = d; g.a_mn_major = 1; g.B = t->dt; g.ldb = RP; g.b_mn_major = 1;
+      g.C = t->part_a; g.ldc = RP; g.M = d; g.N = RP; g.K = M; g.epilogue = EPI_F32; g.split_k = t->split_a;
+      g.block_n = 64;
+      CK(gemm_bf16(g, s), 1);
+    }
+    const int r = tc.lora_r;
+    for (int ti = 0; ti < t->nt; ++ti) {
+      float* gl = t->grads + (static_cast<int64_t>(l) * t->nt + ti) * 2 * d * r;
+      const int grid = (d * r + 255) / 256;
+      lora_gather_kernel<<<grid, 256, 0, s>>>(t->part_a, t->split_a, static_cast<long long>(d) * RP, RP, 0, ti * r, d, r, gl,
+                                              accumulate);
+      lora_gather_kernel<<<grid, 256, 0, s>>>(t->part_b, t->split_b, 3LL * d * RP, RP, t->target_row0[ti], ti * r, d, r,
+                                              gl + static_cast<int64_t>(d) * r, accumulate);
+      CK(cudaGetLastError(), 2);
+    }
+    CK(rmsnorm_bwd(t->dh, t->xs[l], y.norm1, y.rstd1, other, cur, M, d, s), 1);  // cur = d x_in
+  }
+  return DTX_OK;
+}
+
+int optimizer_step(dtx_trainer* t, float* lr_used) {
+  const dtx_train_cfg& tc = t->tc;
+  cudaStream_t s = t->stream;
+  if (t->world > 1) {
+    NcclApi* api = nccl_api();
+    if (!api || !t->nccl_comm) return t->fail(DTX_ERR_NCCL, "NCCL communicator missing for world=%d", t->world);
+    int rc = api->AllReduce(t->grads, t->grads, static_cast<size_t>(t->n_train), kNcclFloat32, kNcclSum, t->nccl_comm, s);
+    if (rc != 0) return t->fail(DTX_ERR_NCCL, "ncclAllReduce failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
+    t->launches += 1;
+  }
+  CK(sumsq(t->grads, t->n_train, t->d_scratch, t->d_sumsq, s), 2);
+  const double lam = dtx_lr_lambda(tc.sched, t->opt_step, tc.warmup_steps, tc.total_steps);
+  const float lr = static_cast<float>(static_cast<double>(tc.lr) * lam);
+  const int step1 = t->opt_step + 1;
+  AdamWArgs a;
+  a.p = t->params; a.g = t->grads; a.m = t->adam_m; a.v = t->adam_v; a.n = t->n_train;
+  a.lr = lr; a.beta1 = tc.beta1; a.beta2 = tc.beta2; a.eps = tc.eps; a.weight_decay = tc.weight_decay;
+  a.bias1 = static_cast<float>(1.0 - pow(static_cast<double>(tc.beta1), step1));
+  a.bias2 = static_cast<float>(1.0 - pow(static_cast<double>(tc.beta2), step1));
+  a.grad_scale = 1.0f / static_cast<float>(t->world * (tc.grad_accum > 0 ? tc.grad_accum : 1));
+  a.sumsq = t->d_sumsq; a.max_grad_norm = tc.max_grad_norm; a.grad_norm_out = t->d_gnorm;
+  CK(adamw_step(a, s), 1);
+  int rc = refresh_shadows(t);
+  if (rc) return rc;
+  t->opt_step += 1;
+  if (lr_used) *lr_used = lr;
+  return DTX_OK;
+}
+
+int do_step(dtx_trainer* t, float* loss_out, float* gnorm_out, float* lr_out, int32_t* stepped_out) {
+  if (!t->have_weights) return t->fail(DTX_ERR_STATE, "base weights not loaded (dtx_load_tensor / dtx_init_random_weights)");
+  if (!t->have_lora) return t->fail(DTX_ERR_STATE, "LoRA adapters not initialised (dtx_init_lora / dtx_load_tensor)");
+  cudaEventRecord(t->ev0, t->stream);
+  int rc = fwd_bwd(t, true);
+  if (rc) return rc;
+  t->micro_idx += 1;
+  int stepped = 0;
+  float lr = 0.f;
+  const int accum = t->tc.grad_accum > 0 ? t->tc.grad_accum : 1;
+  if (t->micro_idx >= accum) {
+    rc = optimizer_step(t, &lr);
+    if (rc) return rc;
+    t->micro_idx = 0;
+    stepped = 1;
+  }
+  cudaEventRecord(t->ev1, t->stream);
+  float host[2] = {0.f, 0.f};
+  cudaMemcpyAsync(&host[0], t->d_loss, sizeof(float), cudaMemcpyDeviceToHost, t->stream);
+  if (stepped) cudaMemcpyAsync(&host[1], t->d_gnorm, sizeof(float), cudaMemcpyDeviceToHost, t->stream);
+  cudaError_t e = cudaStreamSynchronize(t->stream);
+  if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "step failed on device: %s", cudaGetErrorString(e));
+  cudaEventElapsedTime(&t->last_ms, t->ev0, t->ev1);
+  if (loss_out) *loss_out = host[0];
+  if (gnorm_out) *gnorm_out = host[1];
+  if (lr_out) *lr_out = lr;
+  if (stepped_out) *stepped_out = stepped;
+  return DTX_OK;
+}
+
+// --- HF tensor-name parsing -----------------------------------------------------------------------
+bool parse_layer(const char* name, int* layer, const char** rest) {
+  const char* p = strstr(name, "layers.");
+  if (!p) return false;
+  p += 7;
+  char* end = nullptr;
+  long v = strtol(p, &end, 10);
+  if (end == p || *end != '.') return false;
+  *layer = static_cast<int>(v);
+  *rest = end + 1;
+  return true;
+}
+
+void to_bf16_host(const void* src, int dtype, size_t n, std::vector<bf16>& out) {
+  out.resize(n);
+  if (dtype == DTX_BF16) {
+    memcpy(out.data(), src, n * 2);
+  } else if (dtype == DTX_F32) {
+    const float* f = static_cast<const float*>(src);
+    for (size_t i = 0; i < n; ++i) out[i] = __float2bfloat16_rn(f[i]);
+  } else {
+    const __half* h = static_cast<const __half*>(src);
+    for (size_t i = 0; i < n; ++i) out[i] = __float2bfloat16_rn(__half2float(h[i]));
+  }
+}
+void to_f32_host(const void* src, int dtype, size_t n, std::vector<float>& out) {
+  out.resize(n);
+  if (dtype == DTX_F32) {
+    memcpy(out.data(), src, n * 4);
+  } else if (dtype == DTX_BF16) {
+    const bf16* b = static_cast<const bf16*>(src);
+    for (size_t i = 0; i < n; ++i) out[i] = __bfloat162float(b[i]);
+  } else {
+    const __half* h = static_cast<const __half*>(src);
+    for (size_t i = 0; i < n; ++i) out[i] = __half2float(h[i]);
+  }
+}
+
+int target_index(const dtx_trainer* t, char which) {  // 'q','k','v' -> index among enabled targets or -1
+  int idx = 0;
+  const unsigned bits[3] = {DTX_TARGET_Q, DTX_TARGET_K, DTX_TARGET_V};
+  const char names[3] = {'q', 'k', 'v'};
+  for (int i = 0; i < 3; ++i) {
+    if (t->tc.target_mask & bits[i]) {
+      if (names[i] == which) return idx;
+      ++idx;
+    }
+  }
+  return -1;
+}
+
+}  // namespace
+
+// ==================================================================================================
+// C ABI
+// ==================================================================================================
+extern "C" {
+
+int32_t dtx_abi_version(void) { return DTX_ABI_VERSION; }
+const char* dtx_last_global_error(void) { return g_error.c_str(); }
+const char* dtx_last_error(const dtx_trainer* t) { return t ? t->err.c_str() : g_error.c_str(); }
+
+double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup, int32_t total) {
+  // transformers.optimization get_{linear,cosine,constant}_schedule_with_warmup lambdas
+  if (sched == DTX_SCHED_CONSTANT) return 1.0;
+  if (step < warmup) return static_cast<double>(step) / static_cast<double>(warmup > 1 ? warmup : 1);
+  if (sched == DTX_SCHED_CONSTANT_WITH_WARMUP) return 1.0;
+  if (sched == DTX_SCHED_LINEAR) {
+    const double v = static_cast<double>(total - step) / static_cast<double>((total - warmup) > 1 ? (total - warmup) : 1);
+    return v > 0.0 ? v : 0.0;
+  }
+  const double prog = static_cast<double>(step - warmup) / static_cast<double>((total - warmup) > 1 ? (total - warmup) : 1);
+  const double v = 0.5 * (1.0 + cos(M_PI * 2.0 * 0.5 * prog));
+  return v > 0.0 ? v : 0.0;
+}
+
+int32_t dtx_get_nccl_unique_id(void* out128) {
+  NcclApi* api = nccl_api();
+  if (!api) {
+    g_error = "libnccl.so.2 could not be loaded";
+    return DTX_ERR_NCCL;
+  }
+  int rc = api->GetUniqueId(out128);
+  if (rc != 0) {
+    g_error = std::string("ncclGetUniqueId failed: ") + (api->GetErrorString ? api->GetErrorString(rc) : "?");
+    return DTX_ERR_NCCL;
+  }
+  return DTX_OK;
+}
+
+int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int32_t device, int32_t rank, int32_t world,
+                           const void* nccl_unique_id, dtx_trainer** out) {
+  if (!mc || !tc || !out) {
+    g_error = "null argument";
+    return DTX_ERR_INVALID;
+  }
+  *out = nullptr;
+  auto bad = [&](const char* m) {
+    g_error = m;
+    return DTX_ERR_INVALID;
+  };
+  if (mc->head_dim != 128) return bad("only head_dim 128 is implemented (Llama-2 / Mistral family)");
+  if (mc->n_kv_heads != mc->n_heads) { g_error = "grouped-query attention (n_kv_heads != n_heads) is not implemented yet"; return DTX_ERR_UNSUPPORTED; }
+  if (mc->n_heads * mc->head_dim != mc->hidden) return bad("hidden != n_heads * head_dim");
+  if (mc->hidden % 64 || mc->ffn % 8 || mc->vocab % 8) return bad("hidden must be a multiple of 64, ffn and vocab multiples of 8");
+  if (tc->seq_len % 128 || tc->seq_len <= 0 || tc->micro_batch <= 0) return bad("seq_len must be a positive multiple of 128");
+  if (tc->seq_len > mc->max_seq) return bad("seq_len exceeds max_seq");
+  if (tc->lora_r <= 0 || tc->lora_r % 8) return bad("lora_r must be a positive multiple of 8");
+  if (tc->lora_dropout != 0.0f) { g_error = "lora_dropout != 0 is not implemented (parity config uses 0; SURVEY §8a quirk 7)"; return DTX_ERR_UNSUPPORTED; }
+  if ((tc->target_mask & ~(DTX_TARGET_Q | DTX_TARGET_K | DTX_TARGET_V)) || tc->target_mask == 0)
+    { g_error = "lora_target must be a non-empty subset of q_proj,k_proj,v_proj"; return DTX_ERR_UNSUPPORTED; }
+  if (world < 1 || rank < 0 || rank >= world) return bad("bad rank/world");
+  if (world > 1 && !nccl_unique_id) return bad("world > 1 needs an NCCL unique id");
+
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_error = std::string("cudaSetDevice failed (no CUDA device? there is no CPU fallback): ") + cudaGetErrorString(e);
+    return DTX_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess || prop.major != 10) {
+    g_error = "libdtxtune requires an sm_100 (Blackwell B200) device";
+    return DTX_ERR_CUDA;
+  }
+  dtx_trainer* t = new dtx_trainer();
+  t->mc = *mc;
+  t->tc = *tc;
+  t->device = device;
+  t->rank = rank;
+  t->world = world;
+  t->M = tc->micro_batch * tc->seq_len;
+  t->nt = 0;
+  {
+    const unsigned bits[3] = {DTX_TARGET_Q, DTX_TARGET_K, DTX_TARGET_V};
+    for (int i = 0; i < 3; ++i)
+      if (tc->target_mask & bits[i]) t->target_row0[t->nt++] = i * mc->hidden;
+  }
+  t->RP = ((t->nt * tc->lora_r + 63) / 64) * 64;
+  t->n_train = static_cast<int64_t>(mc->n_layers) * t->nt * 2 * mc->hidden * tc->lora_r;
+  cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&t->ev0);
+  cudaEventCreate(&t->ev1);
+  int rc = create_buffers(t);
+  if (rc) {
+    g_error = t->err;
+    dtx_trainer_destroy(t);
+    return rc;
+  }
+  if (world > 1) {
+    NcclApi* api = nccl_api();
+    if (!api) {
+      g_error = "libnccl.so.2 could not be loaded";
+      dtx_trainer_destroy(t);
+      return DTX_ERR_NCCL;
+    }
+    UidByValue uid;
+    memcpy(uid.internal, nccl_unique_id, 128);
+    int nrc = api->CommInitRank(&t->nccl_comm, world, uid, rank);
+    if (nrc != 0) {
+      g_error = std::string("ncclCommInitRank failed: ") + (api->GetErrorString ? api->GetErrorString(nrc) : "?");
+      dtx_trainer_destroy(t);
+      return DTX_ERR_NCCL;
+    }
+  }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    g_error = std::string("device error during create: ") + cudaGetErrorString(e);
+    dtx_trainer_destroy(t);
+    return DTX_ERR_CUDA;
+  }
+  *out = t;
+  return DTX_OK;
+}
+
+void dtx_trainer_destroy(dtx_trainer* t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  cudaDeviceSynchronize();
+  if (t->nccl_comm) {
+    NcclApi* api = nccl_api();
+    if (api) api->CommDestroy(t->nccl_comm);
+  }
+  for (void* p : t->allocs) cudaFree(p);
+  if (t->ev0) cudaEventDestroy(t->ev0);
+  if (t->ev1) cudaEventDestroy(t->ev1);
+  if (t->stream) cudaStreamDestroy(t->stream);
+  delete t;
+}
+
+int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int32_t dtype, const int64_t* shape, int32_t nd) {
+  if (!t || !name || !host || !shape || nd < 1 || nd > 2) return t ? t->fail(DTX_ERR_INVALID, "bad argument") : DTX_ERR_INVALID;
+  cudaSetDevice(t->device);
+  const int64_t d = t->mc.hidden, F = t->mc.ffn, V = t->mc.vocab, r = t->tc.lora_r;
+  const int64_t rows = shape[0], cols = nd == 2 ? shape[1] : 1;
+  auto expect = [&](int64_t er, int64_t ec) { return rows == er && cols == ec; };
+  auto upload = [&](bf16* dst, size_t n) -> int {
+    std::vector<bf16> tmp;
+    to_bf16_host(host, dtype, n, tmp);
+    cudaError_t e = cudaMemcpy(dst, tmp.data(), n * sizeof(bf16), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "upload %s: %s", name, cudaGetErrorString(e));
+    return DTX_OK;
+  };
+  if (strstr(name, "embed_tokens.weight")) {
+    if (!expect(V, d)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)V, (long long)d);
+    t->weights_loaded[0] = true;
+    return upload(t->embed, V * d);
+  }
+  if (strstr(name, "lm_head.weight")) {
+    if (!expect(V, d)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)V, (long long)d);
+    t->weights_loaded[1] = true;
+    return upload(t->lm_head, V * d);
+  }
+  int layer = -1;
+  const char* rest = nullptr;
+  if (!parse_layer(name, &layer, &rest)) {
+    if (strstr(name, "norm.weight")) {  // model.norm.weight
+      if (rows != d) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld]", name, (long long)d);
+      t->weights_loaded[2] = true;
+      return upload(t->normf, d);
+    }
+    return t->fail(DTX_ERR_INVALID, "unknown tensor name %s", name);
+  }
+  if (layer < 0 || layer >= t->mc.n_layers) return t->fail(DTX_ERR_INVALID, "%s: layer out of range", name);
+  Layer& y = t->layers[layer];
+  const bool is_lora_a = strstr(rest, "lora_A") != nullptr, is_lora_b = strstr(rest, "lora_B") != nullptr;
+  if (is_lora_a || is_lora_b) {
+    char which = 0;
+    if (strstr(rest, "q_proj")) which = 'q';
+    else if (strstr(rest, "k_proj")) which = 'k';
+    else if (strstr(rest, "v_proj")) which = 'v';
+    const int ti = which ? target_index(t, which) : -1;
+    if (ti < 0) return t->fail(DTX_ERR_INVALID, "%s: module is not a LoRA target", name);
+    float* base = t->params + (static_cast<int64_t>(layer) * t->nt + ti) * 2 * d * r;
+    std::vector<float> f;
+    if (is_lora_a) {  // [r, d] -> stored transposed [d, r]
+      if (!expect(r, d)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)r, (long long)d);
+      to_f32_host(host, dtype, r * d, f);
+      std::vector<float> tr(d * r);
+      for (int64_t j = 0; j < r; ++j)
+        for (int64_t c = 0; c < d; ++c) tr[c * r + j] = f[j * d + c];
+      cudaMemcpy(base, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice);
+    } else {
+      if (!expect(d, r)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)d, (long long)r);
+      to_f32_host(host, dtype, d * r, f);
+      cudaMemcpy(base + d * r, f.data(), f.size() * 4, cudaMemcpyHostToDevice);
+    }
+    t->have_lora = true;
+    int rc = refresh_shadows(t);
+    if (rc) return rc;
+    cudaStreamSynchronize(t->stream);
+    return DTX_OK;
+  }
+  struct Slot { const char* key; bf16* dst; int64_t r, c; };
+  const Slot slots[] = {
+      {"self_attn.q_proj.weight", y.wqkv, d, d},           {"self_attn.k_proj.weight", y.wqkv + d * d, d, d},
+      {"self_attn.v_proj.weight", y.wqkv + 2 * d * d, d, d}, {"self_attn.o_proj.weight", y.wo, d, d},
+      {"mlp.gate_proj.weight", y.wgu, F, d},               {"mlp.up_proj.weight", y.wgu + F * d, F, d},
+      {"mlp.down_proj.weight", y.wdown, d, F},             {"input_layernorm.weight", y.norm1, d, 1},
+      {"post_attention_layernorm.weight", y.norm2, d, 1},
+  };
+  for (const Slot& sl : slots) {
+    if (strstr(rest, sl.key)) {
+      if (!expect(sl.r, sl.c)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)sl.r, (long long)sl.c);
+      t->have_weights = true;  // completeness is the caller's contract (checked by the host loader)
+      return upload(sl.dst, sl.r * sl.c);
+    }
+  }
+  return t->fail(DTX_ERR_INVALID, "unknown tensor name %s", name);
+}
+
+int32_t dtx_init_random_weights(dtx_trainer* t, uint64_t seed) {
+  if (!t) return DTX_ERR_INVALID;
+  cudaSetDevice(t->device);
+  const int64_t d = t->mc.hidden, F = t->mc.ffn, V = t->mc.vocab;
+  cudaStream_t s = t->stream;
+  uint64_t k = seed * 1000003ull;
+  CK(fill_normal_bf16(t->embed, V * d, 0.02f, ++k, s), 1);
+  CK(fill_normal_bf16(t->lm_head, V * d, 0.02f, ++k, s), 1);
+  CK(fill_const_bf16(t->normf, d, 1.0f, s), 1);
+  for (Layer& y : t->layers) {
+    CK(fill_normal_bf16(y.wqkv, 3 * d * d, 0.02f, ++k, s), 1);
+    CK(fill_normal_bf16(y.wo, d * d, 0.02f, ++k, s), 1);
+    CK(fill_normal_bf16(y.wgu, 2 * F * d, 0.02f, ++k, s), 1);
+    CK(fill_normal_bf16(y.wdown, d * F, 0.02f, ++k, s), 1);
+    CK(fill_const_bf16(y.norm1, d, 1.0f, s), 1);
+    CK(fill_const_bf16(y.norm2, d, 1.0f, s), 1);
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "init_random_weights: %s", cudaGetErrorString(e));
+  t->have_weights = true;
+  return DTX_OK;
+}
+
+int32_t dtx_init_lora(dtx_trainer* t, uint64_t seed) {
+  if (!t) return DTX_ERR_INVALID;
+  cudaSetDevice(t->device);
+  const int64_t d = t->mc.hidden, r = t->tc.lora_r;
+  std::vector<float> host(t->n_train, 0.f);
+  // peft 0.5.0 LoraLayer.reset_lora_parameters: kaiming_uniform_(A, a=sqrt(5)) => U(-1/sqrt(fan_in), +1/sqrt(fan_in)); B = 0
+  const float bound = 1.0f / sqrtf(static_cast<float>(d));
+  uint64_t x = seed ? seed : 0x9E3779B97F4A7C15ull;
+  auto next = [&]() {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
+  };
+  for (int64_t l = 0; l < t->mc.n_layers; ++l)
+    for (int ti = 0; ti < t->nt; ++ti) {
+      float* a = host.data() + (l * t->nt + ti) * 2 * d * r;
+      for (int64_t i = 0; i < d * r; ++i) a[i] = (2.f * next() - 1.f) * bound;
+    }
+  cudaMemcpy(t->params, host.data(), host.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemsetAsync(t->adam_m, 0, t->n_train * 4, t->stream);
+  cudaMemsetAsync(t->adam_v, 0, t->n_train * 4, t->stream);
+  t->opt_step = 0;
+  t->micro_idx = 0;
+  int rc = refresh_shadows(t);
+  if (rc) return rc;
+  cudaStreamSynchronize(t->stream);
+  t->have_lora = true;
+  return DTX_OK;
+}
+
+int32_t dtx_step(dtx_trainer* t, const int32_t* ids, const int32_t* labels, float* loss, float* gnorm, float* lr,
+                 int32_t* stepped) {
+  if (!t || !ids || !labels) return t ? t->fail(DTX_ERR_INVALID, "null batch") : DTX_ERR_INVALID;
+  cudaSetDevice(t->device);
+  cudaMemcpyAsync(t->d_ids, ids, static_cast<size_t>(t->M) * 4, cudaMemcpyHostToDevice, t->stream);
+  cudaMemcpyAsync(t->d_labels, labels, static_cast<size_t>(t->M) * 4, cudaMemcpyHostToDevice, t->stream);
+  return do_step(t, loss, gnorm, lr, stepped);
+}
+
+int32_t dtx_step_device(dtx_trainer* t, const void* d_ids, const void* d_labels, float* loss, float* gnorm, float* lr,
+                        int32_t* stepped) {
+  if (!t || !d_ids || !d_labels) return t ? t->fail(DTX_ERR_INVALID, "null batch") : DTX_ERR_INVALID;
+  cudaSetDevice(t->device);
+  cudaMemcpyAsync(t->d_ids, d_ids, static_cast<size_t>(t->M) * 4, cudaMemcpyDeviceToDevice, t->stream);
+  cudaMemcpyAsync(t->d_labels, d_labels, static_cast<size_t>(t->M) * 4, cudaMemcpyDeviceToDevice, t->stream);
+  return do_step(t, loss, gnorm, lr, stepped);
+}
+
+int32_t dtx_eval_loss(dtx_trainer* t, const int32_t* ids, const int32_t* labels, float* loss_out) {
+  if (!t || !ids || !labels) return t ? t->fail(DTX_ERR_INVALID, "null batch") : DTX_ERR_INVALID;
+  if (!t->have_weights || !t->have_lora) return t->fail(DTX_ERR_STATE, "weights / adapters not initialised");
+  cudaSetDevice(t->device);
+  cudaMemcpyAsync(t->d_ids, ids, static_cast<size_t>(t->M) * 4, cudaMemcpyHostToDevice, t->stream);
+  cudaMemcpyAsync(t->d_labels, labels, static_cast<size_t>(t->M) * 4, cudaMemcpyHostToDevice, t->stream);
+  int rc = fwd_bwd(t, false);
+  if (rc) return rc;
+  float h = 0.f;
+  cudaMemcpyAsync(&h, t->d_loss, 4, cudaMemcpyDeviceToHost, t->stream);
+  cudaError_t e = cudaStreamSynchronize(t->stream);
+  if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "eval failed on device: %s", cudaGetErrorString(e));
+  if (loss_out) *loss_out = h;
+  return DTX_OK;
+}
+
+int32_t dtx_export_adapter(dtx_trainer* t, const char* name, void* host_out, int64_t nbytes) {
+  if (!t || !name || !host_out) return t ? t->fail(DTX_ERR_INVALID, "null argument") : DTX_ERR_INVALID;
+  cudaSetDevice(t->device);
+  const int64_t d = t->mc.hidden, r = t->tc.lora_r;
+  int layer = -1;
+  const char* rest = nullptr;
+  if (!parse_layer(name, &layer, &rest) || layer < 0 || layer >= t->mc.n_layers)
+    return t->fail(DTX_ERR_INVALID, "bad adapter tensor name %s", name);
+  char which = 0;
+  if (strstr(rest, "q_proj")) which = 'q';
+  else if (strstr(rest, "k_proj")) which = 'k';
+  else if (strstr(rest, "v_proj")) which = 'v';
+  const int ti = which ? target_index(t, which) : -1;
+  if (ti < 0) return t->fail(DTX_ERR_INVALID, "%s: module is not a LoRA target", name);
+  if (nbytes < d * r * 4) return t->fail(DTX_ERR_INVALID, "%s: output buffer too small", name);
+  const float* base = t->params + (static_cast<int64_t>(layer) * t->nt + ti) * 2 * d * r;
+  cudaStreamSynchronize(t->stream);
+  std::vector<float> tmp(d * r);
+  float* out = static_cast<float*>(host_out);
+  if (strstr(rest, "lora_A")) {
+    cudaMemcpy(tmp.data(), base, d * r * 4, cudaMemcpyDeviceToHost);
+    for (int64_t c = 0; c < d; ++c)
+      for (int64_t j = 0; j < r; ++j) out[j * d + c] = tmp[c * r + j];
+  } else if (strstr(rest, "lora_B")) {
+    cudaMemcpy(out, base + d * r, d * r * 4, cudaMemcpyDeviceToHost);
+  } else {
+    return t->fail(DTX_ERR_INVALID, "%s: expected lora_A or lora_B", name);
+  }
+  return DTX_OK;
+}
+
+int64_t dtx_num_trainable(const dtx_trainer* t) { return t ? t->n_train : 0; }
+int64_t dtx_launch_count(const dtx_trainer* t) { return t ? t->launches : 0; }
+float dtx_last_step_ms(const dtx_trainer* t) { return t ? t->last_ms : 0.f; }
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+/* libdtxtune — C ABI of the Blackwell-native DataTunerX fine-tuning worker.
+ *
+ * The reference (DataTunerX/datatunerx @ 508be30) has no in-process plugin API for this path: the
+ * Finetune controller launches `python /tuning/train.py <argv>` (internal/controller/finetune/
+ * finetune_controller.go:451-516) and everything below that command line is Python glue around
+ * third-party wheels (cmd/tuning/train.py:138-305).  This header is the boundary a replacement host
+ * (Go via cgo per BASELINE.json north_star; Python/ctypes in this repo because Go is not installed)
+ * binds instead.  Each entry point names the reference code it replaces.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative dtx_status;
+ * dtx_last_error() returns a NUL-terminated message owned by the library (valid until the next call
+ * on the same handle / thread).  The caller owns every host buffer it passes; the library owns all
+ * device memory.  One host thread per handle; handles on different GPUs may be driven concurrently.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with DTX_ERR_CUDA.
+ */
+#ifndef DTXTUNE_H_
+#define DTXTUNE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTX_ABI_VERSION 1
+#if defined(__GNUC__)
+#define DTX_API __attribute__((visibility("default")))
+#else
+#define DTX_API
+#endif
+
+typedef enum {
+  DTX_OK = 0,
+  DTX_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+  DTX_ERR_CUDA = -2,         /* CUDA runtime / driver error (message has details) */
+  DTX_ERR_NCCL = -3,         /* NCCL error or libnccl.so.2 not loadable */
+  DTX_ERR_STATE = -4,        /* call sequence error (e.g. step before weights are loaded) */
+  DTX_ERR_UNSUPPORTED = -5   /* accepted by the reference's CLI but not implemented natively yet */
+} dtx_status;
+
+typedef enum { DTX_F32 = 0, DTX_BF16 = 1, DTX_F16 = 2 } dtx_dtype;
+typedef enum { DTX_SCHED_LINEAR = 0, DTX_SCHED_COSINE = 1, DTX_SCHED_CONSTANT = 2,
+               DTX_SCHED_CONSTANT_WITH_WARMUP = 3 } dtx_sched;
+
+/* LoRA target bits, in HF module order (cmd/tuning/parser.py:211-213 `--lora_target`; the controller
+ * hard-codes "q_proj,v_proj": finetune_controller.go:482). */
+#define DTX_TARGET_Q 1u
+#define DTX_TARGET_K 2u
+#define DTX_TARGET_V 4u
+
+/* Architecture of the frozen base model: the fields of HF config.json that LlamaForCausalLM reads
+ * (loaded by AutoConfig at cmd/tuning/train.py:221). */
+typedef struct {
+  int32_t vocab, hidden, n_layers, n_heads, n_kv_heads, head_dim, ffn;
+  float rms_eps, rope_theta;
+  int32_t max_seq;
+} dtx_model_cfg;
+
+/* Everything of Seq2SeqTrainingArguments / FinetuningArguments that reaches the training step
+ * (cmd/tuning/train.py:196-217, 266-280; cmd/tuning/parser.py:138-149; HF defaults for the rest:
+ * beta1 .9, beta2 .999, eps 1e-8, max_grad_norm 1.0, warm-up 0). */
+typedef struct {
+  int32_t lora_r;
+  float lora_alpha, lora_dropout;
+  uint32_t target_mask;
+  float lr, weight_decay, beta1, beta2, eps, max_grad_norm;
+  int32_t sched;         /* dtx_sched */
+  int32_t warmup_steps;  /* the reference drops --warmup_ratio: effective value 0 (train.py:204) */
+  int32_t total_steps;   /* optimizer steps of the whole run (drives the LR schedule) */
+  int32_t grad_accum;
+  int32_t micro_batch, seq_len;
+  uint64_t seed;
+} dtx_train_cfg;
+
+typedef struct dtx_trainer dtx_trainer;
+
+/* ---- library ---- */
+DTX_API int32_t dtx_abi_version(void);
+/* message of the last failure on this thread when no handle is available (dtx_trainer_create) */
+DTX_API const char* dtx_last_global_error(void);
+DTX_API const char* dtx_last_error(const dtx_trainer* t);
+
+/* ---- lifecycle: replaces trainer_init_per_worker's model/LoRA/optimizer setup (train.py:138-296) ---- */
+/* nccl_unique_id: 128 bytes from dtx_get_nccl_unique_id on rank 0 (world > 1), else NULL. */
+DTX_API int32_t dtx_trainer_create(const dtx_model_cfg* model, const dtx_train_cfg* train, int32_t device, int32_t rank,
+                           int32_t world, const void* nccl_unique_id, dtx_trainer** out);
+DTX_API void dtx_trainer_destroy(dtx_trainer* t);
+DTX_API int32_t dtx_get_nccl_unique_id(void* out128);
+
+/* Upload one tensor by its HF checkpoint name (AutoModelForCausalLM.from_pretrained, train.py:236-242),
+ * e.g. "model.layers.3.self_attn.q_proj.weight" [out,in], "lm_head.weight", "model.norm.weight";
+ * LoRA init may be overridden with "...q_proj.lora_A.weight" [r,in] / "...lora_B.weight" [out,r]. */
+DTX_API int32_t dtx_load_tensor(dtx_trainer* t, const char* hf_name, const void* host, int32_t dtype, const int64_t* shape,
+                        int32_t ndim);
+/* Random-init base weights on the device: N(0, 0.02), norm weights 1 (HF _init_weights), seed-driven. */
+DTX_API int32_t dtx_init_random_weights(dtx_trainer* t, uint64_t seed);
+/* peft 0.5.0 LoRA init on the host RNG-free path: A ~ kaiming-uniform(a=sqrt 5) from `seed`, B = 0. */
+DTX_API int32_t dtx_init_lora(dtx_trainer* t, uint64_t seed);
+
+/* ---- the hot path: one micro-batch of HF Trainer.training_step + (at the accumulation boundary)
+ * all-reduce, clip, AdamW, scheduler (train.py:299; ds_config.json ZeRO-0).  input_ids / labels are
+ * host int32 [micro_batch, seq_len]; labels use -100 for ignored positions and are NOT pre-shifted.
+ * Outputs (host): mean token loss of this micro-batch, global grad-norm before clipping and the lr used
+ * (both only meaningful when *stepped_out == 1). */
+DTX_API int32_t dtx_step(dtx_trainer* t, const int32_t* input_ids, const int32_t* labels, float* loss_out,
+                 float* grad_norm_out, float* lr_out, int32_t* stepped_out);
+/* Same with the batch already resident on this trainer's device (int32 device pointers). */
+DTX_API int32_t dtx_step_device(dtx_trainer* t, const void* d_input_ids, const void* d_labels, float* loss_out,
+                        float* grad_norm_out, float* lr_out, int32_t* stepped_out);
+/* Forward only: SFTTrainer.evaluate's eval_loss (cmd/tuning/trainer.py:324-327). */
+DTX_API int32_t dtx_eval_loss(dtx_trainer* t, const int32_t* input_ids, const int32_t* labels, float* loss_out);
+
+/* ---- export: trainer.save_model writes the PEFT adapter (train.py:300).  hf_name as in
+ * dtx_load_tensor ("...lora_A.weight" / "...lora_B.weight"); fp32, row-major, caller-sized. */
+DTX_API int32_t dtx_export_adapter(dtx_trainer* t, const char* hf_name, void* host_out, int64_t nbytes);
+DTX_API int64_t dtx_num_trainable(const dtx_trainer* t);
+/* kernels launched by this trainer since creation (bench.py's gpu_launches) */
+DTX_API int64_t dtx_launch_count(const dtx_trainer* t);
+/* device time of the most recent dtx_step in ms (CUDA events on the trainer's stream) */
+DTX_API float dtx_last_step_ms(const dtx_trainer* t);
+/* HF get_scheduler value: lr multiplier after `step` optimizer steps (host arithmetic, no device). */
+DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, int32_t total_steps);
+
+/* ---- per-kernel entry points (raw device pointers, `stream` = cudaStream_t or NULL) for the parity
+ * tests and for ncu captures.  Shapes are documented in datatunerx_b200/csrc/kernels.h. ---- */
+DTX_API int32_t dtx_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
+                      const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int32_t K2, void* C, int64_t ldc,
+                      const void* R, int64_t ldr, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t split_k,
+                      int32_t block_n, void* stream);
+DTX_API int32_t dtx_embedding_fwd(const void* ids, const void* table, void* out, int32_t M, int32_t d, int32_t vocab, void* stream);
+DTX_API int32_t dtx_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd, int32_t M, int32_t d, float eps, void* stream);
+DTX_API int32_t dtx_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* rstd, const void* dres, void* dx,
+                        int32_t M, int32_t d, void* stream);
+DTX_API int32_t dtx_rope_table(void* cs_out_device, int32_t S, int32_t D, float theta, void* stream);
+DTX_API int32_t dtx_rope_qk(void* qkv, const void* cs_table, int32_t B, int32_t S, int32_t H, int32_t D, int32_t inverse,
+                    void* stream);
+DTX_API int32_t dtx_swiglu_fwd(const void* gu, void* act, int32_t M, int32_t F, void* stream);
+DTX_API int32_t dtx_swiglu_bwd(const void* dact, const void* gu, void* dgu, int32_t M, int32_t F, void* stream);
+DTX_API int32_t dtx_cross_entropy(const void* logits_f32, int64_t ldl, const void* labels_unshifted, void* shifted_scratch,
+                          void* n_valid_scratch, void* row_loss, void* dlogits_bf16, int64_t ldd, void* loss_out,
+                          int32_t B, int32_t S, int32_t V, void* stream);
+DTX_API int32_t dtx_sumsq(const void* g, int64_t n, void* scratch, void* out, void* stream);
+DTX_API int32_t dtx_adamw(void* p, const void* g, void* m, void* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int32_t step, float grad_scale, const void* sumsq, float max_grad_norm,
+                  void* grad_norm_out, void* stream);
+DTX_API int32_t dtx_attn_fwd(const void* qkv, void* out, void* lse2, int32_t B, int32_t S, int32_t H, float scale, void* stream);
+DTX_API int32_t dtx_attn_bwd(const void* qkv, const void* out, const void* dout, const void* lse2, void* delta_scratch,
+                     void* dqkv, int32_t B, int32_t S, int32_t H, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTXTUNE_H_ */
