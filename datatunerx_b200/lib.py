@@ -1,0 +1,283 @@
+"""ctypes binding of libdtxtune.so — the C ABI declared in include/dtxtune.h.
+
+This is the reference-side stub a maintainer would add (INTEGRATION.md shows the cgo twin).  It does
+no arithmetic: every call lands in the sm_100a kernels.  There is no CPU fallback — if the shared
+library is missing, or no CUDA device is visible, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Dict, Iterable, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdtxtune.so")
+
+DTX_F32, DTX_BF16, DTX_F16 = 0, 1, 2
+SCHED = {"linear": 0, "cosine": 1, "constant": 2, "constant_with_warmup": 3}
+TARGET_BITS = {"q_proj": 1, "k_proj": 2, "v_proj": 4}
+EPI_BF16, EPI_F32, EPI_BF16_ADD = 0, 1, 2
+
+
+class DtxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libdtxtune error {code}: {msg}")
+        self.code = code
+
+
+class ModelCfg(C.Structure):
+    _fields_ = [("vocab", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32), ("n_heads", C.c_int32),
+                ("n_kv_heads", C.c_int32), ("head_dim", C.c_int32), ("ffn", C.c_int32), ("rms_eps", C.c_float),
+                ("rope_theta", C.c_float), ("max_seq", C.c_int32)]
+
+
+class TrainCfg(C.Structure):
+    _fields_ = [("lora_r", C.c_int32), ("lora_alpha", C.c_float), ("lora_dropout", C.c_float),
+                ("target_mask", C.c_uint32), ("lr", C.c_float), ("weight_decay", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("eps", C.c_float), ("max_grad_norm", C.c_float), ("sched", C.c_int32),
+                ("warmup_steps", C.c_int32), ("total_steps", C.c_int32), ("grad_accum", C.c_int32),
+                ("micro_batch", C.c_int32), ("seq_len", C.c_int32), ("seed", C.c_uint64)]
+
+
+# every symbol include/dtxtune.h declares (tests/test_abi.py checks the .so exports all of them)
+ABI_SYMBOLS = [
+    "dtx_abi_version", "dtx_last_global_error", "dtx_last_error", "dtx_trainer_create", "dtx_trainer_destroy",
+    "dtx_get_nccl_unique_id", "dtx_load_tensor", "dtx_init_random_weights", "dtx_init_lora", "dtx_step",
+    "dtx_step_device", "dtx_eval_loss", "dtx_export_adapter", "dtx_num_trainable", "dtx_launch_count",
+    "dtx_last_step_ms", "dtx_lr_lambda", "dtx_gemm_bf16", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
+    "dtx_rope_table", "dtx_rope_qk", "dtx_swiglu_fwd", "dtx_swiglu_bwd", "dtx_cross_entropy", "dtx_sumsq", "dtx_adamw",
+    "dtx_attn_fwd", "dtx_attn_bwd",
+]
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """dlopen libdtxtune.so (built in-tree by datatunerx_b200/csrc/Makefile).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DtxError(-2, f"{LIB_PATH} not found: build it with `make -C datatunerx_b200/csrc` "
+                           "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.dtx_abi_version.restype = i32
+    lib.dtx_last_global_error.restype = C.c_char_p
+    lib.dtx_last_error.restype = C.c_char_p
+    lib.dtx_last_error.argtypes = [vp]
+    lib.dtx_trainer_create.argtypes = [C.POINTER(ModelCfg), C.POINTER(TrainCfg), i32, i32, i32, vp, C.POINTER(vp)]
+    lib.dtx_trainer_destroy.argtypes = [vp]
+    lib.dtx_trainer_destroy.restype = None
+    lib.dtx_get_nccl_unique_id.argtypes = [vp]
+    lib.dtx_load_tensor.argtypes = [vp, C.c_char_p, vp, i32, C.POINTER(i64), i32]
+    lib.dtx_init_random_weights.argtypes = [vp, C.c_uint64]
+    lib.dtx_init_lora.argtypes = [vp, C.c_uint64]
+    lib.dtx_step.argtypes = [vp, vp, vp, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
+    lib.dtx_step_device.argtypes = [vp, vp, vp, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
+    lib.dtx_eval_loss.argtypes = [vp, vp, vp, C.POINTER(f32)]
+    lib.dtx_export_adapter.argtypes = [vp, C.c_char_p, vp, i64]
+    lib.dtx_num_trainable.argtypes = [vp]
+    lib.dtx_num_trainable.restype = i64
+    lib.dtx_launch_count.argtypes = [vp]
+    lib.dtx_launch_count.restype = i64
+    lib.dtx_last_step_ms.argtypes = [vp]
+    lib.dtx_last_step_ms.restype = f32
+    lib.dtx_lr_lambda.argtypes = [i32, i32, i32, i32]
+    lib.dtx_lr_lambda.restype = C.c_double
+    lib.dtx_gemm_bf16.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, vp, i64, i32, vp, i64, vp, i64, i32, i32, i32, i32,
+                                  i32, i32, vp]
+    lib.dtx_embedding_fwd.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    lib.dtx_rmsnorm_fwd.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp]
+    lib.dtx_rmsnorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.dtx_rope_table.argtypes = [vp, i32, i32, f32, vp]
+    lib.dtx_rope_qk.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.dtx_swiglu_fwd.argtypes = [vp, vp, i32, i32, vp]
+    lib.dtx_swiglu_bwd.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.dtx_cross_entropy.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp]
+    lib.dtx_sumsq.argtypes = [vp, i64, vp, vp, vp]
+    lib.dtx_adamw.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, f32, vp, vp]
+    lib.dtx_attn_fwd.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp]
+    lib.dtx_attn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
+    for name in ABI_SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int:  # default: all status-returning entry points
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(code: int, handle=None) -> None:
+    if code != 0:
+        lib = load()
+        msg = lib.dtx_last_error(handle) if handle else lib.dtx_last_global_error()
+        raise DtxError(code, (msg or b"").decode("utf-8", "replace"))
+
+
+def lr_lambda(sched: str, step: int, warmup: int, total: int) -> float:
+    """HF get_scheduler multiplier — host arithmetic inside the library, usable without a GPU."""
+    return float(load().dtx_lr_lambda(SCHED[sched], step, warmup, total))
+
+
+@dataclass
+class ModelConfig:
+    vocab: int
+    hidden: int
+    n_layers: int
+    n_heads: int
+    ffn: int
+    n_kv_heads: Optional[int] = None
+    head_dim: int = 128
+    rms_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    max_seq: int = 4096
+
+    @staticmethod
+    def llama2_7b() -> "ModelConfig":
+        return ModelConfig(vocab=32000, hidden=4096, n_layers=32, n_heads=32, ffn=11008)
+
+    def to_c(self) -> ModelCfg:
+        return ModelCfg(self.vocab, self.hidden, self.n_layers, self.n_heads, self.n_kv_heads or self.n_heads,
+                        self.head_dim, self.ffn, self.rms_eps, self.rope_theta, self.max_seq)
+
+
+@dataclass
+class TrainConfig:
+    micro_batch: int
+    seq_len: int
+    total_steps: int
+    lora_r: int = 8                     # cmd/tuning/parser.py:138-141
+    lora_alpha: float = 32.0            # parser.py:142-145
+    lora_dropout: float = 0.1           # parser.py:146-149 (the native worker implements 0.0 only)
+    lora_target: Tuple[str, ...] = ("q_proj", "v_proj")  # finetune_controller.go:482
+    lr: float = 5e-5                    # HF TrainingArguments default
+    weight_decay: float = 0.0
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    max_grad_norm: float = 1.0
+    sched: str = "linear"
+    warmup_steps: int = 0               # --warmup_ratio is dropped by the reference (train.py:204)
+    grad_accum: int = 1
+    seed: int = 42
+
+    def to_c(self) -> TrainCfg:
+        mask = 0
+        for t in self.lora_target:
+            if t not in TARGET_BITS:
+                raise DtxError(-5, f"lora_target {t!r} is not implemented natively (q_proj,k_proj,v_proj are)")
+            mask |= TARGET_BITS[t]
+        return TrainCfg(self.lora_r, self.lora_alpha, self.lora_dropout, mask, self.lr, self.weight_decay, self.beta1,
+                        self.beta2, self.eps, self.max_grad_norm, SCHED[self.sched], self.warmup_steps, self.total_steps,
+                        self.grad_accum, self.micro_batch, self.seq_len, self.seed)
+
+
+_NP_DTYPES = {np.dtype(np.float32): DTX_F32, np.dtype(np.float16): DTX_F16}
+
+
+class Trainer:
+    """One GPU rank of the native fine-tuning worker (dtx_trainer handle)."""
+
+    def __init__(self, model: ModelConfig, train: TrainConfig, device: int = 0, rank: int = 0, world: int = 1,
+                 nccl_id: Optional[bytes] = None):
+        self.lib = load()
+        self.model, self.train = model, train
+        self._h = C.c_void_p()
+        mc, tc = model.to_c(), train.to_c()
+        idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        check(self.lib.dtx_trainer_create(C.byref(mc), C.byref(tc), device, rank, world, idbuf, C.byref(self._h)))
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.dtx_trainer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights ------------------------------------------------------------------------------
+    def load_tensor(self, name: str, arr: np.ndarray, bf16_bits: bool = False) -> None:
+        """arr: float32/float16 ndarray, or uint16 ndarray holding bf16 bit patterns (bf16_bits=True)."""
+        arr = np.ascontiguousarray(arr)
+        dt = DTX_BF16 if bf16_bits else _NP_DTYPES[arr.dtype]
+        shape = (C.c_int64 * arr.ndim)(*arr.shape)
+        check(self.lib.dtx_load_tensor(self._h, name.encode(), arr.ctypes.data_as(C.c_void_p), dt, shape, arr.ndim), self._h)
+
+    def load_state_dict(self, tensors: Dict[str, np.ndarray]) -> None:
+        for k, v in tensors.items():
+            self.load_tensor(k, v)
+
+    def init_random_weights(self, seed: int) -> None:
+        check(self.lib.dtx_init_random_weights(self._h, seed), self._h)
+
+    def init_lora(self, seed: int) -> None:
+        check(self.lib.dtx_init_lora(self._h, seed), self._h)
+
+    # -- the hot path -------------------------------------------------------------------------
+    def step(self, input_ids: np.ndarray, labels: np.ndarray) -> Tuple[float, float, float, bool]:
+        """One micro-batch.  Returns (loss, grad_norm, lr, stepped)."""
+        ids = np.ascontiguousarray(input_ids, dtype=np.int32)
+        lab = np.ascontiguousarray(labels, dtype=np.int32)
+        assert ids.shape == (self.train.micro_batch, self.train.seq_len) and lab.shape == ids.shape
+        loss, gn, lr, st = C.c_float(), C.c_float(), C.c_float(), C.c_int32()
+        check(self.lib.dtx_step(self._h, ids.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p), C.byref(loss),
+                                C.byref(gn), C.byref(lr), C.byref(st)), self._h)
+        return loss.value, gn.value, lr.value, bool(st.value)
+
+    def step_ptr(self, ids_ptr: int, labels_ptr: int, on_device: bool) -> Tuple[float, float, float, bool]:
+        """Same with raw pointers (pinned host memory, or device memory when on_device)."""
+        loss, gn, lr, st = C.c_float(), C.c_float(), C.c_float(), C.c_int32()
+        fn = self.lib.dtx_step_device if on_device else self.lib.dtx_step
+        check(fn(self._h, C.c_void_p(ids_ptr), C.c_void_p(labels_ptr), C.byref(loss), C.byref(gn), C.byref(lr),
+                 C.byref(st)), self._h)
+        return loss.value, gn.value, lr.value, bool(st.value)
+
+    def eval_loss(self, input_ids: np.ndarray, labels: np.ndarray) -> float:
+        ids = np.ascontiguousarray(input_ids, dtype=np.int32)
+        lab = np.ascontiguousarray(labels, dtype=np.int32)
+        out = C.c_float()
+        check(self.lib.dtx_eval_loss(self._h, ids.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p), C.byref(out)),
+              self._h)
+        return out.value
+
+    # -- export -------------------------------------------------------------------------------
+    def adapter_names(self) -> Iterable[str]:
+        for l in range(self.model.n_layers):
+            for t in self.train.lora_target:
+                for ab in ("lora_A", "lora_B"):
+                    yield f"base_model.model.model.layers.{l}.self_attn.{t}.{ab}.weight"
+
+    def export_adapter(self) -> Dict[str, np.ndarray]:
+        """PEFT state dict (fp32): lora_A [r, in], lora_B [out, r] per target module."""
+        out = {}
+        d, r = self.model.hidden, self.train.lora_r
+        for name in self.adapter_names():
+            shape = (r, d) if "lora_A" in name else (d, r)
+            buf = np.empty(shape, dtype=np.float32)
+            check(self.lib.dtx_export_adapter(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes), self._h)
+            out[name] = buf
+        return out
+
+    @property
+    def num_trainable(self) -> int:
+        return int(self.lib.dtx_num_trainable(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.dtx_launch_count(self._h))
+
+    @property
+    def last_step_ms(self) -> float:
+        return float(self.lib.dtx_last_step_ms(self._h))
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(load().dtx_get_nccl_unique_id(buf))
+    return buf.raw

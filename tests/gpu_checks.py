@@ -1,0 +1,433 @@
+"""Parity checks of the sm_100a kernels against plain torch fp32 references / the CPU oracle.
+
+Each check is a plain function (returns a dict of error metrics, raises AssertionError on mismatch) so that it
+can be driven both by pytest (tests/test_kernels_gpu.py, -m gpu) and by tools/gpu_diag.py, which runs every
+check in its own subprocess with a timeout (a trapped kernel poisons the CUDA context of its process only).
+All compute calls go through the C ABI (datatunerx_b200.lib -> libdtxtune.so).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+
+import numpy as np
+import torch
+
+from datatunerx_b200 import lib as L
+from oracle import llama_lora as O
+
+DEV = "cuda:0"
+
+
+def P(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def STREAM():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ok(code):
+    L.check(code)
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp(min=1e-12))
+
+
+def max_err(a, b) -> float:
+    return float((a.float() - b.float()).abs().max())
+
+
+def gemm(A, B, *, a_mn=False, b_mn=False, A2=None, B2=None, R=None, epi=L.EPI_BF16, split_k=1, block_n=0, M=None, N=None,
+         K=None):
+    lib = L.load()
+    if M is None:
+        M = A.shape[1] if a_mn else A.shape[0]
+    if K is None:
+        K = A.shape[0] if a_mn else A.shape[1]
+    if N is None:
+        N = B.shape[1] if b_mn else B.shape[0]
+    K2 = 0
+    if A2 is not None:
+        K2 = A2.shape[0] if a_mn else A2.shape[1]
+    out_dtype = torch.float32 if epi == L.EPI_F32 else torch.bfloat16
+    shape = (split_k, M, N) if split_k > 1 else (M, N)
+    Cm = torch.full(shape, float("nan"), dtype=out_dtype, device=A.device)
+    ok(lib.dtx_gemm_bf16(P(A), A.stride(0), int(a_mn), P(B), B.stride(0), int(b_mn), P(A2), A2.stride(0) if A2 is not None else 0,
+                         P(B2), B2.stride(0) if B2 is not None else 0, K2, P(Cm), N, P(R), R.stride(0) if R is not None else 0,
+                         M, N, K, epi, split_k, block_n, STREAM()))
+    torch.cuda.synchronize()
+    return Cm
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(DEV)
+
+
+def check_gemm_nt(M=256, N=512, K=320, block_n=0):
+    A, B = _rand(M, K, seed=1), _rand(N, K, seed=2)
+    ref = A.float() @ B.float().t()
+    out = gemm(A, B, block_n=block_n)
+    e = rel_err(out, ref)
+    assert e < 6e-3, f"NT bf16 rel_err {e}"
+    out32 = gemm(A, B, epi=L.EPI_F32, block_n=block_n)
+    e32 = rel_err(out32, ref)
+    assert e32 < 1e-5, f"NT f32 rel_err {e32}"
+    R = _rand(M, N, seed=3)
+    outr = gemm(A, B, R=R, epi=L.EPI_BF16_ADD, block_n=block_n)
+    er = rel_err(outr, ref + R.float())
+    assert er < 6e-3, f"NT +residual rel_err {er}"
+    return {"bf16": e, "f32": e32, "add": er}
+
+
+def check_gemm_nn(M=256, N=384, K=448, block_n=0):
+    A, B = _rand(M, K, seed=4), _rand(K, N, seed=5)
+    ref = A.float() @ B.float()
+    out32 = gemm(A, B, b_mn=True, epi=L.EPI_F32, block_n=block_n)
+    e = rel_err(out32, ref)
+    assert e < 1e-5, f"NN f32 rel_err {e}"
+    return {"f32": e}
+
+
+def check_gemm_tn(Mp=384, N=64, K=1024, split_k=4):
+    A, B = _rand(K, Mp, seed=6), _rand(K, N, seed=7)  # C[Mp,N] = A^T B
+    ref = A.float().t() @ B.float()
+    parts = gemm(A, B, a_mn=True, b_mn=True, epi=L.EPI_F32, split_k=split_k, block_n=64)
+    out = parts.sum(0) if split_k > 1 else parts
+    e = rel_err(out, ref)
+    assert e < 1e-5, f"TN split-K rel_err {e}"
+    return {"f32": e}
+
+
+def check_gemm_kext():
+    M, N, K, K2 = 256, 768, 256, 64
+    A, B, A2, B2 = _rand(M, K, seed=8), _rand(N, K, seed=9), _rand(M, K2, seed=10), _rand(N, K2, seed=11)
+    ref = A.float() @ B.float().t() + A2.float() @ B2.float().t()
+    e1 = rel_err(gemm(A, B, A2=A2, B2=B2, epi=L.EPI_F32), ref)
+    assert e1 < 1e-5, f"NT k-ext rel_err {e1}"
+    Bn, B2n = _rand(K, N, seed=12), _rand(K2, N, seed=13)
+    ref2 = A.float() @ Bn.float() + A2.float() @ B2n.float()
+    e2 = rel_err(gemm(A, Bn, b_mn=True, A2=A2, B2=B2n, epi=L.EPI_F32), ref2)
+    assert e2 < 1e-5, f"NN k-ext rel_err {e2}"
+    return {"nt": e1, "nn": e2}
+
+
+def check_gemm_ragged():
+    out = {}
+    for (M, N, K) in [(200, 200, 200), (130, 72, 136), (128, 2048, 64), (1000, 264, 520)]:
+        A, B = _rand(M, K, seed=M), _rand(N, K, seed=N + 1)
+        ref = A.float() @ B.float().t()
+        e = rel_err(gemm(A, B, epi=L.EPI_F32), ref)
+        assert e < 1e-5, f"ragged {M}x{N}x{K} rel_err {e}"
+        Bn = _rand(K, N, seed=K + 2)
+        e2 = rel_err(gemm(A, Bn, b_mn=True, epi=L.EPI_F32), A.float() @ Bn.float())
+        assert e2 < 1e-5, f"ragged NN {M}x{N}x{K} rel_err {e2}"
+        out[f"{M}x{N}x{K}"] = max(e, e2)
+    return out
+
+
+def check_gemm_large(M=4096, N=4096, K=4096, iters=10):
+    A, B = _rand(M, K, scale=0.05, seed=20), _rand(N, K, scale=0.05, seed=21)
+    out = gemm(A, B)
+    ref = (A @ B.t()).float()  # cuBLAS bf16 as the large-shape reference
+    e = rel_err(out, ref)
+    assert e < 1e-2, f"large NT rel_err {e}"
+    lib = L.load()
+    Cm = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        ok(lib.dtx_gemm_bf16(P(A), K, 0, P(B), K, 0, None, 0, None, 0, 0, P(Cm), N, None, 0, M, N, K, 0, 1, 0, STREAM()))
+    s.record()
+    for _ in range(iters):
+        ok(lib.dtx_gemm_bf16(P(A), K, 0, P(B), K, 0, None, 0, None, 0, 0, P(Cm), N, None, 0, M, N, K, 0, 1, 0, STREAM()))
+    t.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(t) / iters
+    s.record()
+    for _ in range(iters):
+        torch.matmul(A, B.t())
+    t.record()
+    torch.cuda.synchronize()
+    ms_ref = s.elapsed_time(t) / iters
+    return {"rel_err": e, "ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9, "cublas_ms": ms_ref,
+            "cublas_tflops": 2.0 * M * N * K / ms_ref / 1e9}
+
+
+def check_rmsnorm(M=300, d=4096):
+    lib = L.load()
+    x, w, dy, dres = _rand(M, d, seed=1), (_rand(d, seed=2) * 0.1 + 1).to(torch.bfloat16), _rand(M, d, seed=3), _rand(M, d, seed=4)
+    y = torch.empty_like(x)
+    rstd = torch.empty(M, dtype=torch.float32, device=DEV)
+    ok(lib.dtx_rmsnorm_fwd(P(x), P(w), P(y), P(rstd), M, d, 1e-5, STREAM()))
+    xf = x.float().requires_grad_(True)
+    ref = O.rmsnorm(xf, w.float(), 1e-5)
+    ref.backward(dy.float())
+    e_f = rel_err(y, ref)
+    assert e_f < 4e-3, f"rmsnorm fwd {e_f}"
+    dx = torch.empty_like(x)
+    ok(lib.dtx_rmsnorm_bwd(P(dy), P(x), P(w), P(rstd), P(dres), P(dx), M, d, STREAM()))
+    torch.cuda.synchronize()
+    e_b = rel_err(dx, xf.grad + dres.float())
+    assert e_b < 4e-3, f"rmsnorm bwd {e_b}"
+    return {"fwd": e_f, "bwd": e_b}
+
+
+def check_rope(B=2, S=256, H=2, D=128):
+    lib = L.load()
+    qkv = _rand(B * S, 3 * H * D, seed=5)
+    orig = qkv.clone()
+    cs = torch.empty(S, D // 2, 2, dtype=torch.float32, device=DEV)
+    ok(lib.dtx_rope_table(P(cs), S, D, 10000.0, STREAM()))
+    ok(lib.dtx_rope_qk(P(qkv), P(cs), B, S, H, D, 0, STREAM()))
+    torch.cuda.synchronize()
+    cos, sin = O.rope_cos_sin(S, D, 10000.0)
+    cos, sin = cos.to(DEV), sin.to(DEV)
+    x = orig.float().view(B, S, 3, H, D)
+    refq = O.apply_rope(x[:, :, 0].transpose(1, 2), cos, sin).transpose(1, 2)
+    refk = O.apply_rope(x[:, :, 1].transpose(1, 2), cos, sin).transpose(1, 2)
+    got = qkv.float().view(B, S, 3, H, D)
+    e = max(rel_err(got[:, :, 0], refq), rel_err(got[:, :, 1], refk))
+    assert e < 4e-3, f"rope {e}"
+    assert torch.equal(got[:, :, 2], x[:, :, 2]), "rope must not touch v"
+    ok(lib.dtx_rope_qk(P(qkv), P(cs), B, S, H, D, 1, STREAM()))
+    torch.cuda.synchronize()
+    e_inv = rel_err(qkv, orig)
+    assert e_inv < 8e-3, f"rope inverse round trip {e_inv}"
+    return {"fwd": e, "roundtrip": e_inv}
+
+
+def check_swiglu(M=257, F=768):
+    lib = L.load()
+    gu, dact = _rand(M, 2 * F, seed=6), _rand(M, F, seed=7)
+    act = torch.empty(M, F, dtype=torch.bfloat16, device=DEV)
+    dgu = torch.empty_like(gu)
+    ok(lib.dtx_swiglu_fwd(P(gu), P(act), M, F, STREAM()))
+    ok(lib.dtx_swiglu_bwd(P(dact), P(gu), P(dgu), M, F, STREAM()))
+    torch.cuda.synchronize()
+    g = gu.float().requires_grad_(True)
+    ref = torch.nn.functional.silu(g[:, :F]) * g[:, F:]
+    ref.backward(dact.float())
+    e_f, e_b = rel_err(act, ref), rel_err(dgu, g.grad)
+    assert e_f < 4e-3 and e_b < 4e-3, (e_f, e_b)
+    return {"fwd": e_f, "bwd": e_b}
+
+
+def check_embedding(M=500, d=256, V=1000):
+    lib = L.load()
+    table = _rand(V, d, seed=8)
+    ids = torch.randint(0, V, (M,), dtype=torch.int32, device=DEV)
+    out = torch.empty(M, d, dtype=torch.bfloat16, device=DEV)
+    ok(lib.dtx_embedding_fwd(P(ids), P(table), P(out), M, d, V, STREAM()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, table[ids.long()]), "embedding gather must be bit-exact"
+    return {"exact": True}
+
+
+def check_cross_entropy(B=3, S=128, V=2051):
+    lib = L.load()
+    M = B * S
+    Vp = (V + 3) // 4 * 4
+    logits = torch.randn(M, Vp, device=DEV) * 3
+    labels = torch.randint(0, V, (B, S), dtype=torch.int32, device=DEV)
+    labels[:, :20] = -100
+    shifted = torch.empty(M, dtype=torch.int32, device=DEV)
+    nvalid = torch.zeros(4, dtype=torch.int32, device=DEV)
+    row_loss = torch.empty(M, dtype=torch.float32, device=DEV)
+    dl = torch.empty(M, Vp, dtype=torch.bfloat16, device=DEV)
+    loss = torch.zeros(4, dtype=torch.float32, device=DEV)
+    ok(lib.dtx_cross_entropy(P(logits), Vp, P(labels), P(shifted), P(nvalid), P(row_loss), P(dl), Vp, P(loss), B, S, V, STREAM()))
+    torch.cuda.synchronize()
+    lg = logits[:, :V].view(B, S, V).clone().requires_grad_(True)
+    ref = O.causal_lm_loss(lg, labels.long())
+    ref.backward()
+    e_l = abs(float(loss[0]) - float(ref)) / float(ref)
+    assert e_l < 1e-5, f"CE loss {e_l}"
+    e_g = rel_err(dl[:, :V].view(B, S, V), lg.grad)
+    assert e_g < 4e-3, f"CE dlogits {e_g}"
+    assert int(nvalid[0]) == int((labels[:, 1:] >= 0).sum())
+    return {"loss": e_l, "dlogits": e_g}
+
+
+def check_adamw(n=100003 * 4):
+    lib = L.load()
+    g0 = torch.Generator().manual_seed(0)
+    p, m, v = torch.randn(n, generator=g0), torch.zeros(n), torch.zeros(n)
+    pd, md, vd = p.to(DEV), m.to(DEV), v.to(DEV)
+    sumsq = torch.zeros(4, device=DEV)
+    scratch = torch.zeros(1024, device=DEV)
+    gn = torch.zeros(4, device=DEV)
+    out = {}
+    for step in range(1, 4):
+        g = torch.randn(n, generator=g0) * (0.5 if step == 2 else 1e-3)
+        gd = g.to(DEV)
+        ok(lib.dtx_sumsq(P(gd), n, P(scratch), P(sumsq), STREAM()))
+        ok(lib.dtx_adamw(P(pd), P(gd), P(md), P(vd), n, 3e-4, 0.9, 0.999, 1e-8, 0.01, step, 0.5, P(sumsq), 1.0, P(gn), STREAM()))
+        torch.cuda.synchronize()
+        gs = g * 0.5
+        norm = float(gs.double().norm())
+        coef = O.clip_coef(norm, 1.0)
+        O.adamw_update(p, gs * coef, m, v, step, 3e-4, 0.9, 0.999, 1e-8, 0.01)
+        assert abs(float(gn[0]) - norm) / norm < 1e-5, (float(gn[0]), norm)
+        e = max_err(pd.cpu(), p)
+        assert e < 1e-6, f"adamw step {step} max err {e}"
+        out[f"step{step}"] = e
+    return out
+
+
+def _attn_ref(qkv, B, S, H, D):
+    x = qkv.float().view(B, S, 3, H, D)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    scores = q @ k.transpose(-1, -2) / math.sqrt(D)
+    mask = torch.full((S, S), float("-inf"), device=qkv.device).triu(1)
+    p = torch.softmax(scores + mask, dim=-1)
+    return (p @ v).transpose(1, 2).reshape(B * S, H * D), torch.logsumexp(scores + mask, dim=-1)
+
+
+def check_attn_fwd(B=2, S=256, H=2):
+    lib = L.load()
+    D = 128
+    qkv = _rand(B * S, 3 * H * D, seed=11)
+    out = torch.full((B * S, H * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lse2 = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
+    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, 1.0 / math.sqrt(D), STREAM()))
+    torch.cuda.synchronize()
+    ref, lse = _attn_ref(qkv, B, S, H, D)
+    e = rel_err(out, ref)
+    e_l = max_err(lse2 * math.log(2.0), lse)
+    assert e < 8e-3, f"attn fwd {e}"
+    assert e_l < 2e-3, f"attn lse {e_l}"
+    return {"out": e, "lse": e_l}
+
+
+def check_attn_bwd(B=2, S=256, H=2):
+    lib = L.load()
+    D = 128
+    qkv = _rand(B * S, 3 * H * D, seed=12)
+    dout = _rand(B * S, H * D, seed=13)
+    out = torch.empty(B * S, H * D, dtype=torch.bfloat16, device=DEV)
+    lse2 = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
+    delta = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
+    dqkv = torch.full((B * S, 3 * H * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    sc = 1.0 / math.sqrt(D)
+    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, sc, STREAM()))
+    ok(lib.dtx_attn_bwd(P(qkv), P(out), P(dout), P(lse2), P(delta), P(dqkv), B, S, H, sc, STREAM()))
+    torch.cuda.synchronize()
+    x = qkv.float().requires_grad_(True)
+    ref, _ = _attn_ref(x, B, S, H, D)
+    ref.backward(dout.float())
+    g = x.grad.view(B, S, 3, H, D)
+    got = dqkv.float().view(B, S, 3, H, D)
+    errs = {n: rel_err(got[:, :, i], g[:, :, i]) for i, n in enumerate(("dq", "dk", "dv"))}
+    for n, e in errs.items():
+        assert e < 1.5e-2, f"attn bwd {n} {e}"
+    return errs
+
+
+def tiny_configs(S=256, B=2, steps=20, L_layers=2, vocab=2048):
+    ocfg = O.OracleConfig(vocab=vocab, hidden=256, n_layers=L_layers, n_heads=2, ffn=768, lora_r=16, lora_alpha=32.0, lr=1e-3,
+                          total_steps=steps)
+    mc = L.ModelConfig(vocab=vocab, hidden=256, n_layers=L_layers, n_heads=2, ffn=768)
+    tc = L.TrainConfig(micro_batch=B, seq_len=S, total_steps=steps, lora_r=16, lora_alpha=32.0, lora_dropout=0.0, lr=1e-3)
+    return ocfg, mc, tc
+
+
+def make_tiny_pair(S=256, B=2, steps=20, L_layers=2, vocab=2048):
+    ocfg, mc, tc = tiny_configs(S, B, steps, L_layers, vocab)
+    w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
+    tr = L.Trainer(mc, tc)
+    tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+    tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+    return ocfg, O.OracleTrainer(ocfg, w, lora), tr
+
+
+def check_trainer_tiny(steps=10):
+    ocfg, orc, tr = make_tiny_pair(steps=steps)
+    S, B = tr.train.seq_len, tr.train.micro_batch
+    ids, labels = O.synthetic_batch(0, 0, B, S, ocfg.vocab)
+    e_eval = abs(tr.eval_loss(ids, labels) - orc.eval_loss(ids, labels)) / orc.eval_loss(ids, labels)
+    assert e_eval < 1e-3, f"forward loss mismatch {e_eval}"
+    worst_l = worst_g = 0.0
+    trace = []
+    for s in range(steps):
+        ids, labels = O.synthetic_batch(s, 0, B, S, ocfg.vocab)
+        ref = orc.step([(ids, labels)])
+        loss, gn, lr, stepped = tr.step(ids, labels)
+        assert stepped
+        assert abs(lr - ref.lr) <= 1e-9 + 1e-6 * ref.lr, (lr, ref.lr)
+        worst_l = max(worst_l, abs(loss - ref.loss) / ref.loss)
+        worst_g = max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
+        trace.append((loss, ref.loss, gn, ref.grad_norm))
+    assert worst_l < 1e-3, f"loss trace rel diff {worst_l}: {trace}"
+    assert worst_g < 3e-2, f"grad-norm trace rel diff {worst_g}: {trace}"
+    ad, ref_ad = tr.export_adapter(), orc.state_dict()
+    worst_a = 0.0
+    for k, v in ad.items():
+        r = ref_ad[k.replace("base_model.model.", "")]
+        worst_a = max(worst_a, float(np.linalg.norm(v - r) / max(np.linalg.norm(r), 1e-12)))
+    assert worst_a < 5e-2, f"adapter drift {worst_a}"
+    tr.close()
+    return {"eval": e_eval, "loss": worst_l, "gnorm": worst_g, "adapter": worst_a, "last": trace[-1]}
+
+
+def check_trainer_deterministic(steps=3):
+    runs = []
+    for _ in range(2):
+        ocfg, _, tr = make_tiny_pair(steps=steps)
+        out = []
+        for s in range(steps):
+            ids, labels = O.synthetic_batch(s, 0, tr.train.micro_batch, tr.train.seq_len, ocfg.vocab)
+            out.append(tr.step(ids, labels)[:2])
+        runs.append((out, {k: v.tobytes() for k, v in tr.export_adapter().items()}))
+        tr.close()
+    assert runs[0][0] == runs[1][0], "loss / grad-norm must be bitwise reproducible"
+    assert runs[0][1] == runs[1][1], "adapters must be bitwise reproducible"
+    return {"bitwise": True}
+
+
+def check_trainer_grad_accum():
+    """2 micro-batches with grad_accum=2 == oracle's mean over both (DeepSpeed ZeRO-0 / HF accumulation)."""
+    ocfg, mc, tc = tiny_configs(steps=4)
+    ocfg.grad_accum = 2
+    tc.grad_accum = 2
+    w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
+    tr = L.Trainer(mc, tc)
+    tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+    tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+    orc = O.OracleTrainer(ocfg, w, lora)
+    worst = 0.0
+    for s in range(3):
+        batches = [O.synthetic_batch(2 * s + i, 0, tc.micro_batch, tc.seq_len, ocfg.vocab) for i in range(2)]
+        ref = orc.step(batches)
+        l0, _, _, st0 = tr.step(*batches[0])
+        l1, gn, lr, st1 = tr.step(*batches[1])
+        assert not st0 and st1
+        worst = max(worst, abs(0.5 * (l0 + l1) - ref.loss) / ref.loss, abs(gn - ref.grad_norm) / ref.grad_norm / 30)
+    assert worst < 1e-3, worst
+    tr.close()
+    return {"worst": worst}
+
+
+ALL = {
+    "gemm_nt": check_gemm_nt, "gemm_nt_bn64": lambda: check_gemm_nt(N=64, block_n=64),
+    "gemm_nt_bn128": lambda: check_gemm_nt(N=384, block_n=128), "gemm_nn": check_gemm_nn,
+    "gemm_nn_bn64": lambda: check_gemm_nn(N=64, block_n=64), "gemm_tn": check_gemm_tn,
+    "gemm_tn_nosplit": lambda: check_gemm_tn(split_k=1), "gemm_kext": check_gemm_kext, "gemm_ragged": check_gemm_ragged,
+    "gemm_large": check_gemm_large, "rmsnorm": check_rmsnorm, "rmsnorm_small": lambda: check_rmsnorm(M=64, d=256),
+    "rope": check_rope, "swiglu": check_swiglu, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
+    "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
+    "attn_bwd": check_attn_bwd, "attn_bwd_long": lambda: check_attn_bwd(B=1, S=1024, H=1),
+    "trainer_tiny": check_trainer_tiny, "trainer_deterministic": check_trainer_deterministic,
+    "trainer_grad_accum": check_trainer_grad_accum,
+}
+
+if __name__ == "__main__":
+    import json
+    import sys
+    name = sys.argv[1]
+    t0 = time.time()
+    res = ALL[name]()
+    print("RESULT " + json.dumps({"name": name, "ok": True, "sec": round(time.time() - t0, 2), "metrics": res}, default=str))

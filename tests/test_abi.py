@@ -1,0 +1,44 @@
+"""The C-ABI library loads (no GPU needed for that) and exports every symbol include/dtxtune.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "dtxtune.h")).read()
+    return sorted(set(re.findall(r"DTX_API[^;(]*?\b(dtx_\w+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    from datatunerx_b200 import lib as L
+    assert sorted(L.ABI_SYMBOLS) == _declared()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert lib.dtx_abi_version() == 1
+
+
+def test_no_cpu_fallback_create_fails_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from datatunerx_b200 import lib as L
+    with pytest.raises(L.DtxError) as e:
+        L.Trainer(L.ModelConfig(vocab=256, hidden=256, n_layers=1, n_heads=2, ffn=256),
+                  L.TrainConfig(micro_batch=1, seq_len=128, total_steps=1, lora_dropout=0.0))
+    assert e.value.code == -2  # DTX_ERR_CUDA: the product path never computes on the CPU
+
+
+def test_unsupported_configs_are_rejected_loudly(lib):
+    from datatunerx_b200 import lib as L
+    with pytest.raises(L.DtxError):
+        L.Trainer(L.ModelConfig(vocab=256, hidden=256, n_layers=1, n_heads=2, ffn=256),
+                  L.TrainConfig(micro_batch=1, seq_len=128, total_steps=1, lora_dropout=0.1))
+    with pytest.raises(L.DtxError):
+        L.TrainConfig(micro_batch=1, seq_len=128, total_steps=1, lora_target=("o_proj",)).to_c()

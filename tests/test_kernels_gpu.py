@@ -1,0 +1,35 @@
+"""GPU parity tests proper (-m gpu): every sm_100a kernel and the whole training step, through the C ABI,
+against torch fp32 references / the CPU oracle.  The checks live in tests/gpu_checks.py."""
+import pytest
+
+from tests.conftest import has_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(name):
+    if not has_gpu():
+        pytest.skip("no GPU")
+    from tests import gpu_checks
+    return gpu_checks.ALL[name]()
+
+
+@pytest.mark.parametrize("name", ["gemm_nt", "gemm_nt_bn64", "gemm_nt_bn128", "gemm_nn", "gemm_nn_bn64", "gemm_tn",
+                                  "gemm_tn_nosplit", "gemm_kext", "gemm_ragged", "gemm_large"])
+def test_gemm(name):
+    _run(name)
+
+
+@pytest.mark.parametrize("name", ["rmsnorm", "rmsnorm_small", "rope", "swiglu", "embedding", "cross_entropy", "adamw"])
+def test_hbm_kernels(name):
+    _run(name)
+
+
+@pytest.mark.parametrize("name", ["attn_fwd", "attn_fwd_long", "attn_bwd", "attn_bwd_long"])
+def test_attention(name):
+    _run(name)
+
+
+@pytest.mark.parametrize("name", ["trainer_tiny", "trainer_deterministic", "trainer_grad_accum"])
+def test_training_step(name):
+    _run(name)
