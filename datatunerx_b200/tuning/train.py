@@ -1,0 +1,139 @@
+"""Native tuning worker — the process behind the controller's `python /tuning/train.py ...` (cmd/tuning/train.py).
+
+Flow (reference line in brackets):
+  parse argv [parser.get_train_args, train.py:313]  ->  block_size -> cutoff_len [323-325]  ->  tokenizer [337]
+  -> CSV + column rename [339-340] -> llama2 template + label masking [342, 58-135]
+  -> one rank per GPU (the reference: one Ray actor per worker, train.py:353-368) -> data-parallel LoRA-SFT steps on
+     libdtxtune (replaces trainer_init_per_worker + HF Trainer.train(), train.py:138-299)
+  -> log every 10 optimizer steps [198; callback.py:95-155] -> eval_loss / eval_perplexity [trainer.py:324-327]
+  -> PEFT adapter dir under storage_path [300-305] -> /home/ray/checkpoint_path without trailing newline [379-389]
+Exit status: 0 on success, non-zero on any error (the controller maps it to RayJob SUCCEEDED/FAILED).
+
+Multi-GPU: rank 0 creates the NCCL unique id and re-executes itself once per extra GPU with DTX_RANK/DTX_NCCL_ID in the
+environment (single node, one process per GPU, no torch.distributed needed).
+"""
+from __future__ import annotations
+
+import math
+import os
+import subprocess
+import sys
+import time
+from typing import List, Optional
+
+import numpy as np
+
+from .. import lib as L
+from . import data as D
+from . import model_io
+from .callback import LogCallback
+from .parser import TrainArgs, get_train_args
+
+CHECKPOINT_PATH_FILE = os.environ.get("DTX_CHECKPOINT_PATH_FILE", "/home/ray/checkpoint_path")
+
+
+def total_optimizer_steps(n_examples: int, world: int, batch: int, grad_accum: int, epochs: float, max_steps: int) -> int:
+    """HF Trainer: num_update_steps_per_epoch = max(len(dataloader) // grad_accum, 1); max_steps = ceil(epochs * that)."""
+    per_epoch = max(D.steps_per_epoch(n_examples, world, batch) // max(1, grad_accum), 1)
+    return max_steps if max_steps > 0 else int(math.ceil(epochs * per_epoch))
+
+
+def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], tokenizer=None) -> Optional[str]:
+    if a.quantization:
+        raise L.DtxError(-5, f"--quantization {a.quantization} (bitsandbytes path, train.py:224-234) is not implemented natively yet")
+    if tokenizer is None:
+        from transformers import AutoTokenizer  # host-side tokenisation only
+        tokenizer = AutoTokenizer.from_pretrained(a.model_name_or_path)
+    D.fix_tokenizer(tokenizer)
+    cutoff_len = a.block_size if a.block_size > 0 else 1024  # train.py:51,323-325
+    rows = D.read_csv_rows(a.train_path, a.columns_map())
+    dataset = D.build_dataset(rows, tokenizer, cutoff_len)
+    if not dataset:
+        raise RuntimeError("Empty dataset!")  # train.py:133
+    eval_set = dataset if a.evaluation_path else None  # the reference re-reads the TRAIN file for eval (train.py:347)
+
+    mc = model_io.load_model_config(a.model_name_or_path)
+    seq_len = D.static_seq_len(cutoff_len)
+    B, GA = a.per_device_train_batch_size, max(1, a.gradient_accumulation_steps)
+    total = total_optimizer_steps(len(dataset), world, B, GA, a.num_train_epochs, a.max_steps)
+    tc = L.TrainConfig(micro_batch=B, seq_len=seq_len, total_steps=total, lora_r=a.lora_rank, lora_alpha=a.lora_alpha,
+                       lora_dropout=a.lora_dropout, lora_target=tuple(a.lora_target), lr=a.learning_rate, weight_decay=a.weight_decay,
+                       beta1=a.adam_beta1, beta2=a.adam_beta2, eps=a.adam_epsilon, max_grad_norm=a.max_grad_norm,
+                       sched=a.lr_scheduler_type, warmup_steps=a.warmup_steps, grad_accum=GA, seed=a.seed)
+    device = int(os.environ.get("DTX_DEVICE", rank))
+    tr = L.Trainer(mc, tc, device=device, rank=rank, world=world, nccl_id=nccl_id)
+    model_io.load_weights_into(tr, a.model_name_or_path)
+    tr.init_lora(a.seed)
+    cb = LogCallback(a.output_dir, total, a.metrics_export_address, a.uid) if rank == 0 else None
+
+    pad_id = tokenizer.pad_token_id
+    step, window, t0 = 0, [], time.time()
+    per_epoch = max(D.steps_per_epoch(len(dataset), world, B) // GA, 1)
+    epoch = 0
+    while step < total:
+        micro_losses = []
+        for ids, labels in D.epoch_batches(dataset, rank, world, B, seq_len, pad_id, epoch, a.seed):
+            loss, gnorm, lr, stepped = tr.step(ids, labels)
+            micro_losses.append(loss)
+            if not stepped:
+                continue
+            step += 1
+            window.append(float(np.mean(micro_losses)))
+            micro_losses = []
+            if cb:
+                cb.on_step_end(step)
+                if step % a.logging_steps == 0:  # HF logs the mean loss since the last log and the *next* lr
+                    cb.on_log(float(np.mean(window)), a.learning_rate * L.lr_lambda(a.lr_scheduler_type, step, a.warmup_steps, total),
+                              step / per_epoch)
+                    window = []
+            if step >= total:
+                break
+        epoch += 1
+    if eval_set is not None:
+        losses = [tr.eval_loss(i, l) for i, l in D.epoch_batches(eval_set, rank, world, B, seq_len, pad_id, 0, a.seed)]
+        if cb and losses:
+            ev = float(np.mean(losses))
+            cb.on_eval(ev, math.exp(ev), step / per_epoch)  # eval_perplexity = exp(eval_loss), trainer.py:324-327
+    ckpt = None
+    if rank == 0:
+        name = f"TorchTrainer_{time.strftime('%Y-%m-%d_%H-%M-%S')}/checkpoint_000000"
+        ckpt = os.path.join(a.storage_path, name)
+        model_io.save_peft_adapter(ckpt, tr.export_adapter(), base_model=a.model_name_or_path, r=a.lora_rank, alpha=a.lora_alpha,
+                                   dropout=a.lora_dropout, target_modules=a.lora_target)
+        model_io.save_peft_adapter(a.output_dir, tr.export_adapter(), base_model=a.model_name_or_path, r=a.lora_rank,
+                                   alpha=a.lora_alpha, dropout=a.lora_dropout, target_modules=a.lora_target)
+        print(f"train_runtime {time.time() - t0:.1f}s, {step} optimizer steps")
+    tr.close()
+    return ckpt
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    a = get_train_args(argv)
+    rank = int(os.environ.get("DTX_RANK", "0"))
+    world = max(1, a.num_workers)
+    nccl_id = bytes.fromhex(os.environ["DTX_NCCL_ID"]) if "DTX_NCCL_ID" in os.environ else None
+    children = []
+    if world > 1 and rank == 0 and nccl_id is None:
+        nccl_id = L.nccl_unique_id()
+        for r in range(1, world):
+            env = dict(os.environ, DTX_RANK=str(r), DTX_NCCL_ID=nccl_id.hex())
+            children.append(subprocess.Popen([sys.executable, "-m", "datatunerx_b200.tuning.train"] + argv, env=env))
+    ckpt = run_rank(a, rank, world, nccl_id)
+    rc = 0
+    for c in children:
+        rc = rc or c.wait()
+    if rc:
+        return rc
+    if rank == 0 and ckpt:
+        print(f"result path {ckpt}")
+        d = os.path.dirname(CHECKPOINT_PATH_FILE)
+        if d and not os.path.exists(d):
+            os.makedirs(d)
+        with open(CHECKPOINT_PATH_FILE, "w", encoding="utf-8") as f:
+            f.write(ckpt)  # no trailing newline: the controller `cat`s it verbatim (finetune_controller.go:201-212)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
