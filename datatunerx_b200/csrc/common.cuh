@@ -61,19 +61,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin on an mbarrier phase.  With DTX_WATCHDOG the spin is bounded (~4 s) and traps instead of
+// Spin on an mbarrier phase.  With DTX_WATCHDOG the spin is bounded (~2 s of SM clock) and traps instead of
 // hanging the GPU: a hung kernel on the shared B200 pool costs a strike, a trap costs an error code.
+// (try_wait itself may suspend the thread for a hardware-defined interval, so the clock is polled often.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if DTX_WATCHDOG
-  long long t0 = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFFFu) == 0) {
-      long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 8000000000LL) {
-        printf("[dtx] mbarrier watchdog: block %d thread %d bar %p parity %u\n", (int)blockIdx.x,
-               (int)threadIdx.x, (void*)bar, parity);
+    if ((++spins & 0x3Fu) == 0) {
+      if (clock64() - t0 > 4000000000LL) {
+        printf("[dtx] mbarrier watchdog: block %d thread %d bar@%u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+               smem_u32(bar), parity);
         __trap();
       }
     }

@@ -72,9 +72,9 @@ thread_local std::string g_error;
 // ------------------------------------------------------------------------------------------------
 // LoRA-specific small kernels
 // ------------------------------------------------------------------------------------------------
-// dst[n*r + j] (+)= sum_s part[s*split_stride + (row0+n)*ld + col0 + j]   (fixed order)
+// dst[n*r + j] (+)= scale * sum_s part[s*split_stride + (row0+n)*ld + col0 + j]   (fixed order)
 __global__ void lora_gather_kernel(const float* __restrict__ part, int splits, long long split_stride, int ld, int row0,
-                                   int col0, int rows, int r, float* __restrict__ dst, int accumulate) {
+                                   int col0, int rows, int r, float* __restrict__ dst, int accumulate, float scale) {
   const long long total = static_cast<long long>(rows) * r;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -82,6 +82,7 @@ __global__ void lora_gather_kernel(const float* __restrict__ part, int splits, l
     const float* src = part + static_cast<long long>(row0 + n) * ld + col0 + j;
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += src[k * split_stride];
+    s *= scale;
     dst[i] = accumulate ? dst[i] + s : s;
   }
 }
@@ -430,10 +431,11 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
     for (int ti = 0; ti < t->nt; ++ti) {
       float* gl = t->grads + (static_cast<int64_t>(l) * t->nt + ti) * 2 * d * r;
       const int grid = (d * r + 255) / 256;
+      // dA^T = h1^T (dy * sB)  (the scale rides in B_ext);  dB = s * dy^T t  (t is unscaled, so the scale is applied here)
       lora_gather_kernel<<<grid, 256, 0, s>>>(t->part_a, t->split_a, static_cast<long long>(d) * RP, RP, 0, ti * r, d, r, gl,
-                                              accumulate);
+                                              accumulate, 1.0f);
       lora_gather_kernel<<<grid, 256, 0, s>>>(t->part_b, t->split_b, 3LL * d * RP, RP, t->target_row0[ti], ti * r, d, r,
-                                              gl + static_cast<int64_t>(d) * r, accumulate);
+                                              gl + static_cast<int64_t>(d) * r, accumulate, tc.lora_alpha / static_cast<float>(r));
       CK(cudaGetLastError(), 2);
     }
     CK(rmsnorm_bwd(t->dh, t->xs[l], y.norm1, y.rstd1, other, cur, M, d, s), 1);  // cur = d x_in

@@ -425,9 +425,25 @@ ALL = {
 }
 
 if __name__ == "__main__":
+    # usage: python -m tests.gpu_checks name [name ...]   — runs in order, one RESULT line per check; exits with
+    # code 3 right after a failure that may have poisoned the CUDA context so the driver can restart with the rest
     import json
     import sys
-    name = sys.argv[1]
-    t0 = time.time()
-    res = ALL[name]()
-    print("RESULT " + json.dumps({"name": name, "ok": True, "sec": round(time.time() - t0, 2), "metrics": res}, default=str))
+    import traceback
+    for name in sys.argv[1:]:
+        t0 = time.time()
+        try:
+            res = ALL[name]()
+            print("RESULT " + json.dumps({"name": name, "ok": True, "sec": round(time.time() - t0, 2), "metrics": res}, default=str),
+                  flush=True)
+        except AssertionError as e:
+            print("RESULT " + json.dumps({"name": name, "ok": False, "sec": round(time.time() - t0, 2), "error": str(e)[:1500]}),
+                  flush=True)
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                sys.exit(3)
+        except Exception as e:
+            print("RESULT " + json.dumps({"name": name, "ok": False, "sec": round(time.time() - t0, 2),
+                                          "error": (str(e) + " | " + traceback.format_exc())[-1500:]}), flush=True)
+            sys.exit(3)

@@ -1,7 +1,8 @@
-"""Run every GPU parity check in its own subprocess with a timeout; write gpurun_out/diag.json.
+"""Run the GPU parity checks (tests/gpu_checks.py) and write gpurun_out/diag.json.
 
-A kernel that traps (e.g. the mbarrier watchdog) poisons only its own process, so one bad kernel
-does not hide the state of the others.  Usage: python tools/gpu_diag.py [name ...]
+All checks run in one child process (one torch import); when a check kills the process (a trapped kernel poisons the
+CUDA context, a watchdog timeout...) the remaining checks continue in a fresh child.
+Usage: python tools/gpu_diag.py [name ...]
 """
 import json
 import os
@@ -11,33 +12,49 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+PER_CHECK_TIMEOUT = 180
 
 
 def main():
-    from tests import gpu_checks  # noqa: only for the list of names (imports torch once here)
-    names = sys.argv[1:] or list(gpu_checks.ALL)
+    import ast
+    src = open(os.path.join(ROOT, "tests", "gpu_checks.py")).read()
+    tree = ast.parse(src)
+    all_names = []
+    for n in tree.body:
+        if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "ALL":
+            all_names = [k.value for k in n.value.keys]
+    names = sys.argv[1:] or all_names
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    results = []
-    for n in names:
+    results, todo = [], list(names)
+    while todo:
         t0 = time.time()
+        p = subprocess.Popen([sys.executable, "-m", "tests.gpu_checks"] + todo, cwd=ROOT, stdout=subprocess.PIPE,
+                             stderr=subprocess.STDOUT, text=True)
+        done_here, tail = [], []
         try:
-            p = subprocess.run([sys.executable, "-m", "tests.gpu_checks", n], cwd=ROOT, capture_output=True, text=True,
-                               timeout=240)
-            out = p.stdout + p.stderr
-            line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
-            if p.returncode == 0 and line:
-                r = json.loads(line[-1][7:])
+            out, _ = p.communicate(timeout=PER_CHECK_TIMEOUT * max(1, len(todo)) // 2 + 120)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        for line in out.splitlines():
+            if line.startswith("RESULT "):
+                r = json.loads(line[7:])
+                results.append(r)
+                done_here.append(r["name"])
+                print(json.dumps(r)[:700], flush=True)
             else:
-                r = {"name": n, "ok": False, "rc": p.returncode, "tail": out[-1500:]}
-        except subprocess.TimeoutExpired as e:
-            r = {"name": n, "ok": False, "rc": "timeout", "tail": ((e.stdout or b"")[-800:]).decode("utf-8", "replace")
-                 if isinstance(e.stdout, bytes) else str(e.stdout)[-800:]}
-        r["wall"] = round(time.time() - t0, 1)
-        results.append(r)
-        print(json.dumps(r)[:600], flush=True)
+                tail.append(line)
+        remaining = [n for n in todo if n not in done_here]
+        if remaining and (p.returncode != 0 or not done_here):
+            if p.returncode != 3 or not done_here or results[-1].get("ok", False):
+                # the child died inside remaining[0] without reporting
+                bad = remaining.pop(0)
+                r = {"name": bad, "ok": False, "rc": p.returncode, "error": "\n".join(tail)[-1500:], "sec": round(time.time() - t0, 1)}
+                results.append(r)
+                print(json.dumps(r)[:900], flush=True)
+        todo = remaining
         json.dump(results, open(os.path.join(ROOT, "gpurun_out", "diag.json"), "w"), indent=1)
-    bad = [r["name"] for r in results if not r.get("ok")]
-    print("FAILED:", bad)
+    print("FAILED:", [r["name"] for r in results if not r.get("ok")])
 
 
 if __name__ == "__main__":
