@@ -169,11 +169,9 @@ def run_native(args, rank: int, local_rank: int, world: int):
     from datatunerx_b200 import lib as L
     from oracle.llama_lora import synthetic_batch  # input generator shared with the parity tests (not compute)
 
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        dist.init_process_group("gloo", rank=rank, world_size=world)
+    from datatunerx_b200.dist import Rendezvous
+    rv = Rendezvous()
+    dist = rv.dist
     torch.cuda.set_device(local_rank)
 
     if args.config == "7b":
@@ -184,11 +182,7 @@ def run_native(args, rank: int, local_rank: int, world: int):
         B, S = 2, 256
     total = args.warmup + 2 * args.steps + 2
     tc = L.TrainConfig(micro_batch=B, seq_len=S, total_steps=max(total, 100), lora_r=16, lora_alpha=32.0, lora_dropout=0.0, lr=1e-4)
-    nccl_id = None
-    if world > 1:
-        box = [L.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        nccl_id = box[0]
+    nccl_id = rv.broadcast_bytes(L.nccl_unique_id)
     tr = L.Trainer(mc, tc, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
     tr.init_random_weights(1234)
     tr.init_lora(4321)
@@ -201,15 +195,9 @@ def run_native(args, rank: int, local_rank: int, world: int):
 
     def barrier():
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+        rv.barrier()
 
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0])
+    max_over_ranks = rv.max_over_ranks
 
     losses = []
     for i in range(args.warmup):

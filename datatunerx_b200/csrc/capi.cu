@@ -3,6 +3,7 @@
 #include "../../include/dtxtune.h"
 
 #include <math.h>
+#include <string.h>
 #include <vector>
 
 using namespace dtx;
@@ -24,6 +25,15 @@ int32_t dtx_gemm_bf16(const void* A, int64_t lda, int32_t a_mn, const void* B, i
   g.C = C; g.ldc = ldc; g.R = static_cast<const bf16*>(R); g.ldr = ldr;
   g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.split_k = split_k; g.block_n = block_n;
   return rc(gemm_bf16(g, S(stream)));
+}
+
+int32_t dtx_set_option(const char* name, int32_t value) {
+  if (!name) return DTX_ERR_INVALID;
+  if (strcmp(name, "gemm_pair_kernel") == 0) {
+    gemm_set_pair_kernel(value);
+    return DTX_OK;
+  }
+  return DTX_ERR_INVALID;
 }
 
 int32_t dtx_embedding_fwd(const void* ids, const void* table, void* out, int32_t M, int32_t d, int32_t vocab, void* stream) {

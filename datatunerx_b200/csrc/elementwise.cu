@@ -51,39 +51,54 @@ __global__ void embedding_kernel(const int32_t* __restrict__ ids, const bf16* __
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: RMSNorm.  One warp per row, the row lives in registers between the reduce and the scale.
+// K2: RMSNorm.  One 128-thread block per row; the row lives in registers between the reduce and the scale
+// (NCH 16-byte chunks per thread), so each element is read from HBM exactly once.  Many small blocks per SM
+// (16 x 4 warps) keep enough loads in flight to saturate HBM; r01's one-warp-per-row version held 32 chunks per
+// thread in 150 registers, ran 8 warps/SM and reached only 31% of HBM bandwidth (profiles/r01_launches_bwd.txt).
 //   y = w * (x * rsqrt(mean(x^2) + eps)), all math fp32 (HF LlamaRMSNorm computes in fp32).
 // ------------------------------------------------------------------------------------------
-template <int MAXCH>
-__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
-                                                          bf16* __restrict__ y, float* __restrict__ rstd, int M, int d,
-                                                          float eps) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const int lane = threadIdx.x & 31;
+constexpr int RMS_THREADS = 128;
+
+__device__ __forceinline__ float block_sum_128(float v, float* sh4) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh4[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (sh4[0] + sh4[1]) + (sh4[2] + sh4[3]);  // fixed order
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(RMS_THREADS) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                  bf16* __restrict__ y, float* __restrict__ rstd, int d,
+                                                                  float eps) {
+  __shared__ float sh[4];
+  const int row = blockIdx.x;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d);
   const int nvec = d >> 3;
-  uint4 buf[MAXCH];
+  uint4 buf[NCH];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
-    const int v = i * 32 + lane;
+  for (int i = 0; i < NCH; ++i) {
+    const int v = i * RMS_THREADS + threadIdx.x;
+    if (v < nvec) buf[i] = ldg_stream(xr + v);
+  }
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int v = i * RMS_THREADS + threadIdx.x;
     if (v < nvec) {
-      buf[i] = ldg_stream(xr + v);
       float f[8];
       bf16x8_to_f32(buf[i], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
     }
   }
-  ss = warp_sum(ss);
+  ss = block_sum_128(ss, sh);
   const float r = rsqrtf(ss / static_cast<float>(d) + eps);
-  if (lane == 0 && rstd) rstd[row] = r;
+  if (threadIdx.x == 0 && rstd) rstd[row] = r;
   const uint4* wr = reinterpret_cast<const uint4*>(w);
   uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * d);
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
-    const int v = i * 32 + lane;
+  for (int i = 0; i < NCH; ++i) {
+    const int v = i * RMS_THREADS + threadIdx.x;
     if (v < nvec) {
       float f[8], g[8];
       bf16x8_to_f32(buf[i], f);
@@ -96,27 +111,33 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const bf16* __restrict
 }
 
 // dx = rstd * (w*dy) - x * rstd^3 * mean(w*dy*x) (+ dres).  Base weights are frozen: no dw.
-template <int MAXCH>
-__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                          const bf16* __restrict__ w, const float* __restrict__ rstd,
-                                                          const bf16* __restrict__ dres, bf16* __restrict__ dx, int M,
-                                                          int d) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const int lane = threadIdx.x & 31;
+template <int NCH>
+__global__ void __launch_bounds__(RMS_THREADS) rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                  const bf16* __restrict__ w, const float* __restrict__ rstd,
+                                                                  const bf16* __restrict__ dres, bf16* __restrict__ dx, int d) {
+  __shared__ float sh[4];
+  const int row = blockIdx.x;
   const size_t off = static_cast<size_t>(row) * d;
   const uint4* dyr = reinterpret_cast<const uint4*>(dy + off);
   const uint4* xr = reinterpret_cast<const uint4*>(x + off);
   const uint4* wr = reinterpret_cast<const uint4*>(w);
+  const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + off) : nullptr;
   const int nvec = d >> 3;
-  uint4 bx[MAXCH], bg[MAXCH];  // x and w*dy (as bf16-packed inputs; products recomputed in fp32)
-  float dot = 0.f;
+  uint4 bx[NCH], bg[NCH], br[NCH];
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
-    const int v = i * 32 + lane;
+  for (int i = 0; i < NCH; ++i) {
+    const int v = i * RMS_THREADS + threadIdx.x;
     if (v < nvec) {
       bx[i] = ldg_stream(xr + v);
       bg[i] = ldg_stream(dyr + v);
+      if (rr) br[i] = ldg_stream(rr + v);
+    }
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int v = i * RMS_THREADS + threadIdx.x;
+    if (v < nvec) {
       float fx[8], fg[8], fw[8];
       bf16x8_to_f32(bx[i], fx);
       bf16x8_to_f32(bg[i], fg);
@@ -125,14 +146,13 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict
       for (int j = 0; j < 8; ++j) dot += fg[j] * fw[j] * fx[j];
     }
   }
-  dot = warp_sum(dot);
+  dot = block_sum_128(dot, sh);
   const float r = rstd[row];
   const float c = dot * r * r * r / static_cast<float>(d);
   uint4* dxr = reinterpret_cast<uint4*>(dx + off);
-  const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + off) : nullptr;
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
-    const int v = i * 32 + lane;
+  for (int i = 0; i < NCH; ++i) {
+    const int v = i * RMS_THREADS + threadIdx.x;
     if (v < nvec) {
       float fx[8], fg[8], fw[8], o[8];
       bf16x8_to_f32(bx[i], fx);
@@ -142,7 +162,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict
       for (int j = 0; j < 8; ++j) o[j] = fg[j] * fw[j] * r - fx[j] * c;
       if (rr) {
         float fr[8];
-        bf16x8_to_f32(ldg_stream(rr + v), fr);
+        bf16x8_to_f32(br[i], fr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += fr[j];
       }
@@ -489,22 +509,22 @@ cudaError_t embedding_fwd(const int32_t* ids, const bf16* table, bf16* out, int 
 
 cudaError_t rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int M, int d, float eps, cudaStream_t s) {
   if (d % 8 || d > 8192) return cudaErrorInvalidValue;
-  const int rows_per_block = 8;
-  const int grid = (M + rows_per_block - 1) / rows_per_block;
-  if (d <= 1024) rmsnorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, w, y, rstd, M, d, eps);
-  else if (d <= 4096) rmsnorm_fwd_kernel<16><<<grid, 256, 0, s>>>(x, w, y, rstd, M, d, eps);
-  else rmsnorm_fwd_kernel<32><<<grid, 256, 0, s>>>(x, w, y, rstd, M, d, eps);
+  const int nch = (d / 8 + RMS_THREADS - 1) / RMS_THREADS;
+  if (nch <= 1) rmsnorm_fwd_kernel<1><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps);
+  else if (nch <= 2) rmsnorm_fwd_kernel<2><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps);
+  else if (nch <= 4) rmsnorm_fwd_kernel<4><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps);
+  else rmsnorm_fwd_kernel<8><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps);
   return cudaGetLastError();
 }
 
 cudaError_t rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx, int M,
                         int d, cudaStream_t s) {
   if (d % 8 || d > 8192) return cudaErrorInvalidValue;
-  const int rows_per_block = 8;
-  const int grid = (M + rows_per_block - 1) / rows_per_block;
-  if (d <= 1024) rmsnorm_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres, dx, M, d);
-  else if (d <= 4096) rmsnorm_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres, dx, M, d);
-  else rmsnorm_bwd_kernel<32><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres, dx, M, d);
+  const int nch = (d / 8 + RMS_THREADS - 1) / RMS_THREADS;
+  if (nch <= 1) rmsnorm_bwd_kernel<1><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d);
+  else if (nch <= 2) rmsnorm_bwd_kernel<2><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d);
+  else if (nch <= 4) rmsnorm_bwd_kernel<4><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d);
+  else rmsnorm_bwd_kernel<8><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d);
   return cudaGetLastError();
 }
 

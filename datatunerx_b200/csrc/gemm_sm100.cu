@@ -48,6 +48,55 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// store one 32-column chunk of an accumulator row (fp32 in registers) with the selected epilogue
+template <int EPI>
+__device__ __forceinline__ void epilogue_store_chunk(const GemmKParams& p, int row, int col0, int split, const uint32_t (&v)[32]) {
+  const bool full = (col0 + 32 <= p.N);
+  if (EPI == EPI_F32) {
+    float* crow = reinterpret_cast<float*>(p.C) + static_cast<long long>(split) * p.M * p.ldc +
+                  static_cast<long long>(row) * p.ldc + col0;
+    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<uint4*>(crow)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __uint_as_float(v[j]);
+    }
+  } else {
+    bf16* crow = reinterpret_cast<bf16*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (EPI == EPI_BF16_ADD) {
+      const bf16* rrow = p.R + static_cast<long long>(row) * p.ldr + col0;
+      if (full && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 r = reinterpret_cast<const uint4*>(rrow)[j];
+          float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), cc = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
+          f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+          f[8 * j + 4] += cc.x; f[8 * j + 5] += cc.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+        }
+      } else {
+        for (int j = 0; j < 32 && col0 + j < p.N; ++j) f[j] += __bfloat162float(rrow[j]);
+      }
+    }
+    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+        o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+        o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+        o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+        reinterpret_cast<uint4*>(crow)[j] = o;
+      }
+    } else {
+      for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __float2bfloat16_rn(f[j]);
+    }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -192,50 +241,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
         if (!row_ok) continue;
-        const bool full = (col0 + 32 <= p.N);
-        if (EPI == EPI_F32) {
-          float* crow = reinterpret_cast<float*>(p.C) + static_cast<long long>(split) * p.M * p.ldc +
-                        static_cast<long long>(row) * p.ldc + col0;
-          if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<uint4*>(crow)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __uint_as_float(v[j]);
-          }
-        } else {
-          bf16* crow = reinterpret_cast<bf16*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (EPI == EPI_BF16_ADD) {
-            const bf16* rrow = p.R + static_cast<long long>(row) * p.ldr + col0;
-            if (full && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 r = reinterpret_cast<const uint4*>(rrow)[j];
-                float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), cc = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
-                f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
-                f[8 * j + 4] += cc.x; f[8 * j + 5] += cc.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
-              }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < p.N; ++j) f[j] += __bfloat162float(rrow[j]);
-            }
-          }
-          if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              reinterpret_cast<uint4*>(crow)[j] = o;
-            }
-          } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __float2bfloat16_rn(f[j]);
-          }
-        }
+        epilogue_store_chunk<EPI>(p, row, col0, split, v);
       }
       tc_fence_before();
       __syncwarp();
@@ -251,6 +257,178 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ================================================================================================
+// CTA-pair kernel: 256 x 256 output tile per cluster of two CTAs (tcgen05 cta_group::2).
+//
+// The single-CTA kernel above tops out at ~67% tensor-pipe activity (ncu, profiles/r01_*): a 128x256x16 UMMA reads
+// 12 KB of operands from shared memory per 128 cycles (96 B/clk) while TMA writes another 96 B/clk, against a 128 B/clk
+// shared-memory port.  In pair mode each CTA stages only its half of B (128 rows) and the tensor cores exchange the
+// halves, so per-SM shared-memory traffic drops to 64 + 64 B/clk and L2->SM traffic per FLOP by a third.
+//   both CTAs : warp 0 = TMA producer (own A rows, own half of B; completion bytes land on the LEADER's barrier)
+//   leader    : warp 1 lane 0 issues tcgen05.mma.cta_group::2 (M = 256) and multicast-commits to both CTAs' barriers
+//   both CTAs : warps 2..5 drain their own 128 x 256 accumulator half from their own TMEM
+// ================================================================================================
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = 128 * BK * 2;
+constexpr int G2_B_BYTES = 128 * BK * 2;
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_TMEM_COLS = 512;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+constexpr int G2_GROUP_M = 8;  // in 256-row tiles
+
+template <bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* tfull_bar = empty_bar + G2_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB2);
+    for (int i = 0; i < G2_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's producer arrive.expect_tx (both CTAs' bytes)
+      mbar_init(&empty_bar[i], 1);  // one multicast tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);  // 4 epilogue warps of each CTA (only the leader's copy is waited on)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_ptr_smem, G2_TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int kb_total = p.kb1 + p.kb2;
+  const int total_tiles = p.m_tiles * p.n_tiles;  // m_tiles counts 256-row tiles here
+
+  auto decode = [&](int tile, int& m_blk, int& n_blk) {
+    const int per_group = G2_GROUP_M * p.n_tiles;
+    int group = tile / per_group;
+    int first_m = group * G2_GROUP_M;
+    int gsz = min(G2_GROUP_M, p.m_tiles - first_m);
+    int r = tile - group * per_group;
+    m_blk = first_m + (r % gsz);
+    n_blk = r / gsz;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        int m_blk, n_blk;
+        decode(tile, m_blk, n_blk);
+        const int m0 = m_blk * 256 + 128 * static_cast<int>(rank);
+        const int n0 = n_blk * 256 + 128 * static_cast<int>(rank);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          uint8_t* a_dst = smem + stage * G2_STAGE_BYTES;
+          uint8_t* b_dst = a_dst + G2_A_BYTES;
+          const bool seg2 = kb >= p.kb1;
+          const int kk = (seg2 ? kb - p.kb1 : kb) * BK;
+          const CUtensorMap* ma = seg2 ? &tmA2 : &tmA;
+          const CUtensorMap* mb = seg2 ? &tmB2 : &tmB;
+          tma_load_2d_pair(a_dst, ma, leader_full, kk, m0);
+          if (!B_MN) {
+            tma_load_2d_pair(b_dst, mb, leader_full, kk, n0);
+          } else {
+            tma_load_2d_pair(b_dst, mb, leader_full, n0, kk);
+            tma_load_2d_pair(b_dst + 8192, mb, leader_full, n0 + 64, kk);
+          }
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, 256, 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * G2_STAGE_BYTES);
+          const uint32_t b_base = a_base + G2_A_BYTES;
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) {
+            const uint64_t da = umma_desc_kmajor(a_base + k16 * 32);
+            const uint64_t db = B_MN ? umma_desc_mnmajor(b_base + k16 * 2048, 8192) : umma_desc_kmajor(b_base + k16 * 32);
+            umma_bf16_pair(d_tmem, da, db, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(&tfull_bar[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      int m_blk, n_blk;
+      decode(tile, m_blk, n_blk);
+      const int m0 = m_blk * 256 + 128 * static_cast<int>(rank);
+      const int n0 = n_blk * 256;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256);
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        epilogue_store_chunk<EPI>(p, row, col0, 0, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));  // the leader's MMA thread waits on it
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still signal / multicast into it
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, G2_TMEM_COLS);
   }
 }
 
@@ -364,6 +542,60 @@ cudaError_t launch_epi(const GemmArgs& a, cudaStream_t s) {
   return cudaErrorInvalidValue;
 }
 
+int g_use_pair_kernel = 1;
+
+template <bool B_MN, int EPI>
+cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
+  auto kern = gemm2_kernel<B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap tA, tB, tA2, tB2;
+  bool ok = true;
+  ok &= make_tmap_2d_bf16(&tA, a.A, a.K, a.M, a.lda, 64, 128);
+  ok &= B_MN ? make_tmap_2d_bf16(&tB, a.B, a.N, a.K, a.ldb, 64, 64) : make_tmap_2d_bf16(&tB, a.B, a.K, a.N, a.ldb, 64, 128);
+  if (a.K2 > 0) {
+    ok &= make_tmap_2d_bf16(&tA2, a.A2, a.K2, a.M, a.lda2, 64, 128);
+    ok &= B_MN ? make_tmap_2d_bf16(&tB2, a.B2, a.N, a.K2, a.ldb2, 64, 64) : make_tmap_2d_bf16(&tB2, a.B2, a.K2, a.N, a.ldb2, 64, 128);
+  } else {
+    tA2 = tA;
+    tB2 = tB;
+  }
+  if (!ok) return cudaErrorInvalidValue;
+  GemmKParams p;
+  p.M = a.M;
+  p.N = a.N;
+  p.kb1 = (a.K + BK - 1) / BK;
+  p.kb2 = (a.K2 + BK - 1) / BK;
+  p.split_k = 1;
+  p.kb_per_split = p.kb1 + p.kb2;
+  p.m_tiles = (a.M + 255) / 256;
+  p.n_tiles = (a.N + 255) / 256;
+  p.C = a.C;
+  p.ldc = a.ldc;
+  p.R = a.R;
+  p.ldr = a.ldr;
+  const int total = p.m_tiles * p.n_tiles;
+  int pairs = gemm_num_sms() / 2;
+  if (pairs > total) pairs = total;
+  if (pairs <= 0) return cudaSuccess;
+  kern<<<2 * pairs, GEMM_THREADS, G2_SMEM_BYTES, s>>>(tA, tB, tA2, tB2, p);
+  return cudaGetLastError();
+}
+
+template <bool B_MN>
+cudaError_t launch2_epi(const GemmArgs& a, cudaStream_t s) {
+  switch (a.epilogue) {
+    case EPI_BF16: return launch2<B_MN, EPI_BF16>(a, s);
+    case EPI_F32: return launch2<B_MN, EPI_F32>(a, s);
+    case EPI_BF16_ADD: return launch2<B_MN, EPI_BF16_ADD>(a, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
 template <int BN>
 cudaError_t launch_major(const GemmArgs& a, cudaStream_t s) {
   if (!a.a_mn_major && !a.b_mn_major) return launch_epi<BN, false, false>(a, s);
@@ -373,6 +605,8 @@ cudaError_t launch_major(const GemmArgs& a, cudaStream_t s) {
 }
 
 }  // namespace
+
+void gemm_set_pair_kernel(int on) { g_use_pair_kernel = on; }
 
 cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaErrorInvalidValue;
@@ -384,6 +618,8 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s) {
   if (a.K2 > 0 && ((a.lda2 & 7) || (a.ldb2 & 7) || !a.A2 || !a.B2)) return cudaErrorInvalidValue;
   int bn = a.block_n;
   if (bn == 0) bn = (a.N <= 64) ? 64 : ((a.N <= 128) ? 128 : 256);
+  if (bn == 256 && !a.a_mn_major && a.split_k <= 1 && g_use_pair_kernel && a.M > 128)
+    return a.b_mn_major ? launch2_epi<true>(a, s) : launch2_epi<false>(a, s);
   switch (bn) {
     case 64: return launch_major<64>(a, s);
     case 128: return launch_major<128>(a, s);

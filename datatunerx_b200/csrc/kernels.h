@@ -36,6 +36,8 @@ struct GemmArgs {
 };
 cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s);
 int gemm_num_sms();
+// 1 (default): wide GEMMs use the CTA-pair (cta_group::2) kernel; 0: single-CTA kernel everywhere (A/B measurements)
+void gemm_set_pair_kernel(int on);
 
 // ---------------------------------------------------------------------------------------------
 // flash attention (causal, head_dim 128), packed qkv layout [B*S, 3*H*128] (q | k | v per token)

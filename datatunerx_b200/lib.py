@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "dtx_abi_version", "dtx_last_global_error", "dtx_last_error", "dtx_trainer_create", "dtx_trainer_destroy",
     "dtx_get_nccl_unique_id", "dtx_load_tensor", "dtx_init_random_weights", "dtx_init_lora", "dtx_step",
     "dtx_step_device", "dtx_eval_loss", "dtx_export_adapter", "dtx_num_trainable", "dtx_launch_count",
-    "dtx_last_step_ms", "dtx_lr_lambda", "dtx_gemm_bf16", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
+    "dtx_last_step_ms", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
     "dtx_rope_table", "dtx_rope_qk", "dtx_swiglu_fwd", "dtx_swiglu_bwd", "dtx_cross_entropy", "dtx_sumsq", "dtx_adamw",
     "dtx_attn_fwd", "dtx_attn_bwd",
 ]
@@ -88,6 +88,7 @@ def load() -> C.CDLL:
     lib.dtx_last_step_ms.restype = f32
     lib.dtx_lr_lambda.argtypes = [i32, i32, i32, i32]
     lib.dtx_lr_lambda.restype = C.c_double
+    lib.dtx_set_option.argtypes = [C.c_char_p, i32]
     lib.dtx_gemm_bf16.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, vp, i64, i32, vp, i64, vp, i64, i32, i32, i32, i32,
                                   i32, i32, vp]
     lib.dtx_embedding_fwd.argtypes = [vp, vp, vp, i32, i32, i32, vp]
@@ -115,6 +116,10 @@ def check(code: int, handle=None) -> None:
         lib = load()
         msg = lib.dtx_last_error(handle) if handle else lib.dtx_last_global_error()
         raise DtxError(code, (msg or b"").decode("utf-8", "replace"))
+
+
+def set_option(name: str, value: int) -> None:
+    check(load().dtx_set_option(name.encode(), value))
 
 
 def lr_lambda(sched: str, step: int, warmup: int, total: int) -> float:

@@ -121,6 +121,10 @@ DTX_API float dtx_last_step_ms(const dtx_trainer* t);
 /* HF get_scheduler value: lr multiplier after `step` optimizer steps (host arithmetic, no device). */
 DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, int32_t total_steps);
 
+/* Tuning / diagnostics switches.  "gemm_pair_kernel" = 1 (default): wide GEMMs run the cta_group::2 CTA-pair kernel;
+ * 0: the single-CTA kernel everywhere (used for A/B measurements in profiles/). */
+DTX_API int32_t dtx_set_option(const char* name, int32_t value);
+
 /* ---- per-kernel entry points (raw device pointers, `stream` = cudaStream_t or NULL) for the parity
  * tests and for ncu captures.  Shapes are documented in datatunerx_b200/csrc/kernels.h. ---- */
 DTX_API int32_t dtx_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,

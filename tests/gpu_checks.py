@@ -411,12 +411,49 @@ def check_trainer_grad_accum():
     return {"worst": worst}
 
 
+def check_gemm_single_cta():
+    """The single-CTA kernel stays covered when the CTA-pair kernel is the default for wide GEMMs."""
+    L.set_option("gemm_pair_kernel", 0)
+    try:
+        out = {"nt": check_gemm_nt(), "nn": check_gemm_nn(), "kext": check_gemm_kext(), "ragged": check_gemm_ragged()}
+    finally:
+        L.set_option("gemm_pair_kernel", 1)
+    return out
+
+
+def check_gemm_pair_vs_single(M=8192, N=8192, K=4096):
+    """Bitwise agreement of the two kernels (same fp32 accumulation order along K) + timing of both."""
+    A, B = _rand(M, K, scale=0.05, seed=30), _rand(N, K, scale=0.05, seed=31)
+    lib = L.load()
+    res = {}
+    outs = []
+    for name, flag in (("pair", 1), ("single", 0)):
+        L.set_option("gemm_pair_kernel", flag)
+        Cm = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            ok(lib.dtx_gemm_bf16(P(A), K, 0, P(B), K, 0, None, 0, None, 0, 0, P(Cm), N, None, 0, M, N, K, 0, 1, 0, STREAM()))
+        s.record()
+        for _ in range(10):
+            ok(lib.dtx_gemm_bf16(P(A), K, 0, P(B), K, 0, None, 0, None, 0, 0, P(Cm), N, None, 0, M, N, K, 0, 1, 0, STREAM()))
+        t.record()
+        torch.cuda.synchronize()
+        res[name + "_tflops"] = 2.0 * M * N * K / (s.elapsed_time(t) / 10) / 1e9
+        outs.append(Cm)
+    L.set_option("gemm_pair_kernel", 1)
+    assert torch.equal(outs[0], outs[1]), "pair and single-CTA kernels must agree bitwise"
+    ref = (A @ B.t())
+    res["rel_err_vs_cublas"] = rel_err(outs[0], ref)
+    assert res["rel_err_vs_cublas"] < 1e-2
+    return res
+
+
 ALL = {
     "gemm_nt": check_gemm_nt, "gemm_nt_bn64": lambda: check_gemm_nt(N=64, block_n=64),
     "gemm_nt_bn128": lambda: check_gemm_nt(N=384, block_n=128), "gemm_nn": check_gemm_nn,
     "gemm_nn_bn64": lambda: check_gemm_nn(N=64, block_n=64), "gemm_tn": check_gemm_tn,
     "gemm_tn_nosplit": lambda: check_gemm_tn(split_k=1), "gemm_kext": check_gemm_kext, "gemm_ragged": check_gemm_ragged,
-    "gemm_large": check_gemm_large, "rmsnorm": check_rmsnorm, "rmsnorm_small": lambda: check_rmsnorm(M=64, d=256),
+    "gemm_large": check_gemm_large, "gemm_single_cta": check_gemm_single_cta, "gemm_pair_vs_single": check_gemm_pair_vs_single, "rmsnorm": check_rmsnorm, "rmsnorm_small": lambda: check_rmsnorm(M=64, d=256),
     "rope": check_rope, "swiglu": check_swiglu, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
     "attn_bwd": check_attn_bwd, "attn_bwd_long": lambda: check_attn_bwd(B=1, S=1024, H=1),
