@@ -7,12 +7,18 @@
 // Data layout: packed qkv [B*S, 3*H*128] (per token: q heads | k heads | v heads), out [B*S, H*128],
 // lse2 [B,H,S] = log2-domain log-sum-exp of the scaled scores (m + log2 l).
 //
-// Kernels (128 threads = 4 warps; thread r owns TMEM lane r = one row of the score tile):
+// Kernels (one CTA per SM; 4 compute warps where thread r owns TMEM lane r = one row of the score tile, plus a 5th
+// warp whose lane 0 issues every TMA load and every tcgen05.mma, so no compute warp ever executes serial issue code):
 //   attn_fwd_kernel   : CTA = 128 query rows, loops over 64-row KV blocks.  S = Q K^T (UMMA 128x64x16, K-major x K-major),
 //                       online softmax in registers, P -> smem (K-major A operand), O_blk = P V (V is the MN-major B operand).
 //   attn_dq_kernel    : CTA = 128 query rows.  S, dP = dO V^T, dS = P o (dP - delta) * scale, dQ += dS K (K as MN-major B),
 //                       dQ accumulates in TMEM over the whole KV loop.
 //   attn_dkv_kernel   : CTA = 128 KV rows, loops over 64-row Q blocks.  S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q.
+// All three are software-pipelined inside the CTA (r01 v2; v1 ran its phases back to back and left the tensor pipe 18-30%
+// busy, profiles/r01_ncu_full_baseline.txt): the streamed operand blocks sit in a 3-deep TMA ring, the score MMAs of block
+// j+1 are issued into a second TMEM buffer BEFORE the threads start the exp / dS arithmetic of block j, and the
+// accumulating MMAs of block j run under the TMEM loads of block j+1.  mbarriers carry every hand-off (bar_kv/bar_q: TMA
+// landed; bar_s: scores ready; bar_p: the 128 compute threads have written P / dS to smem; bar_o: accumulate MMA done).
 // Two backward kernels instead of one with fp32 atomics on dQ: every reduction has a fixed order, so the
 // step is bitwise reproducible (needed for the N-rank == 1-rank parity tests).
 #include "common.cuh"
@@ -26,7 +32,8 @@ bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint6
 namespace {
 
 constexpr int HD = 128;      // head dim
-constexpr int ATT_THREADS = 128;
+constexpr int BWD_THREADS = 288;  // backward kernels: 8 compute warps (two per score row quadrant, splitting the columns) + issuer warp
+constexpr int ATT_THREADS = 160;  // 4 compute warps (one TMEM lane / score row per thread) + 1 issuer warp (TMA + MMA)
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnKParams {
@@ -45,38 +52,45 @@ __device__ __forceinline__ uint32_t kmaj_addr(uint32_t base, int k16, uint32_t s
   return base + (k16 >> 2) * subtile_bytes + (k16 & 3) * 32;
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ================================================================================================
 // forward
 // ================================================================================================
-constexpr int FWD_SQ = 0;                 // 2 x [128 x 128B]
-constexpr int FWD_SK = 32768;             // 2 x [64 x 128B]
-constexpr int FWD_SV = FWD_SK + 16384;    // 2 x [64 x 128B]
-constexpr int FWD_SP = FWD_SV + 16384;    // [128 x 128B]
-constexpr int FWD_BAR = FWD_SP + 16384;   // barriers
-constexpr int FWD_SMEM = FWD_BAR + 128 + 1024;
+constexpr int FWD_SQ = 0;                    // 2 x [128 x 128B]
+constexpr int FWD_SK = 32768;                // 3 x (2 x [64 x 128B])
+constexpr int FWD_SV = FWD_SK + 3 * 16384;   // 3 x (2 x [64 x 128B])
+constexpr int FWD_SP = FWD_SV + 3 * 16384;   // [128 x 128B]
+constexpr int FWD_BAR = FWD_SP + 16384;
+constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
-  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_o = bars + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[3]*/, *bar_s = bars + 4 /*[2]*/, *bar_o = bars + 6, *bar_p = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int nqb = p.S / 128;
   const int qb = nqb - 1 - (blockIdx.x % nqb);  // heavy (late) query blocks first
   const int bh = blockIdx.x / nqb;
   const int h = bh % p.H, b = bh / p.H;
   const int q0 = qb * 128;
-  const int row_base = b * p.S;  // token row of position 0
-  const int n_kv = (q0 + 128) / 64;
+  const int row_base = b * p.S;
+  const int n = (q0 + 128) / 64;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int colQ = h * HD, colK = p.H * HD + h * HD, colV = 2 * p.H * HD + h * HD;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_p, 128);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr, 256);
@@ -84,130 +98,151 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const uint32_t T_S = 0, T_O = 64;
+  const uint32_t T_S = 0 /* +64*buf */, T_O = 128;
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, 32768);
-    tma_load_2d(smem + FWD_SQ, &tmQ, bar_q, colQ, row_base + q0);
-    tma_load_2d(smem + FWD_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
-    mbar_arrive_expect_tx(bar_k, 16384);
-    tma_load_2d(smem + FWD_SK, &tmKV, bar_k, colK, row_base);
-    tma_load_2d(smem + FWD_SK + 8192, &tmKV, bar_k, colK + 64, row_base);
-    mbar_arrive_expect_tx(bar_v, 16384);
-    tma_load_2d(smem + FWD_SV, &tmKV, bar_v, colV, row_base);
-    tma_load_2d(smem + FWD_SV + 8192, &tmKV, bar_v, colV + 64, row_base);
-  }
-
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 0, 1);
-  const uint32_t sQ = smem_u32(smem + FWD_SQ), sK = smem_u32(smem + FWD_SK), sV = smem_u32(smem + FWD_SV),
-                 sP = smem_u32(smem + FWD_SP);
-
-  float m_run = -INFINITY, l_run = 0.f;
-  float o[HD];
-#pragma unroll
-  for (int i = 0; i < HD; ++i) o[i] = 0.f;
-  const int qrow = q0 + tid;
-
-  for (int j = 0; j < n_kv; ++j) {
-    const uint32_t ph = j & 1;
-    const int kv0 = j * 64;
-    if (tid == 0) {
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int k16 = 0; k16 < 8; ++k16)
-        umma_bf16(tmem + T_S, umma_desc_kmajor(kmaj_addr(sQ, k16, 16384)), umma_desc_kmajor(kmaj_addr(sK, k16, 8192)),
-                  idesc_s, k16 > 0 ? 1u : 0u);
-      umma_commit(bar_s);
-    }
-    mbar_wait(bar_s, ph);
-    tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {  // K buffer is free: prefetch next K block
-      mbar_arrive_expect_tx(bar_k, 16384);
-      tma_load_2d(smem + FWD_SK, &tmKV, bar_k, colK, row_base + kv0 + 64);
-      tma_load_2d(smem + FWD_SK + 8192, &tmKV, bar_k, colK + 64, row_base + kv0 + 64);
-    }
-    uint32_t sv[64];
+  if (warp == 4) {
+    // ------------------------------------------ issuer ------------------------------------------
     {
-      uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
-      uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
-      tmem_ld32(t_lane + T_S, lo);
-      tmem_ld32(t_lane + T_S + 32, hi);
-      tmem_ld_wait();
-    }
-    const bool need_mask = (kv0 + 63 > q0);
-    float mx = -INFINITY;
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 0, 1);
+      const uint32_t sQ = smem_u32(smem + FWD_SQ), sK = smem_u32(smem + FWD_SK), sV = smem_u32(smem + FWD_SV),
+                     sP = smem_u32(smem + FWD_SP);
+      auto load_kv = [&](int j) {  // KV block j -> ring slot j % 3
+        const int slot = j % 3;
+        if (!leader) return;
+        mbar_arrive_expect_tx(&bar_kv[slot], 32768);
+        tma_load_2d(smem + FWD_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
+        tma_load_2d(smem + FWD_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
+        tma_load_2d(smem + FWD_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
+        tma_load_2d(smem + FWD_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
+      };
+      auto issue_s = [&](int j) {  // S(j) = Q K(j)^T into score buffer j & 1
+        const int slot = j % 3;
+        mbar_wait_backoff(&bar_kv[slot], (j / 3) & 1);
+        tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      float t = __uint_as_float(sv[c]) * p.scale_log2;
-      if (need_mask && (kv0 + c > qrow)) t = -INFINITY;
-      sv[c] = __float_as_uint(t);
-      mx = fmaxf(mx, t);
-    }
-    const float m_new = fmaxf(m_run, mx);
-    const float alpha = exp2f(m_run - m_new);
-    float rs = 0.f;
-    uint8_t* prow = smem + FWD_SP;
-#pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-      float pv[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        pv[e] = exp2f(__uint_as_float(sv[c8 * 8 + e]) - m_new);
-        rs += pv[e];
+        for (int k16 = 0; k16 < 8; ++k16)
+          if (leader) umma_bf16(tmem + T_S + (j & 1) * 64, umma_desc_kmajor(kmaj_addr(sQ, k16, 16384)),
+                    umma_desc_kmajor(kmaj_addr(sK + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+        if (leader) umma_commit(&bar_s[j & 1]);
+      };
+      if (leader) {
+        mbar_arrive_expect_tx(bar_q, 32768);
+        tma_load_2d(smem + FWD_SQ, &tmQ, bar_q, colQ, row_base + q0);
+        tma_load_2d(smem + FWD_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
       }
-      uint4 u;
-      u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
-      u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
-      *reinterpret_cast<uint4*>(prow + sw128_offset(tid, c8)) = u;
-    }
-    l_run = l_run * alpha + rs;
-    m_run = m_new;
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(bar_v, ph);
+      for (int j = 0; j < 3 && j < n; ++j) load_kv(j);
+      mbar_wait_backoff(bar_q, 0);
+      issue_s(0);
+      if (n > 1) issue_s(1);
+      for (int j = 0; j < n; ++j) {
+        mbar_wait_backoff(bar_p, j & 1);  // P(j) is in smem; score buffer j&1 and the O tile have been consumed
+        tc_fence_after();
+        const uint32_t vb = sV + (j % 3) * 16384;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16(tmem + T_O, umma_desc_kmajor(sP + kk * 32), umma_desc_mnmajor(sV + kk * 2048, 8192), idesc_o,
-                  kk > 0 ? 1u : 0u);
-      umma_commit(bar_o);
+        for (int kk = 0; kk < 4; ++kk)
+          if (leader) umma_bf16(tmem + T_O, umma_desc_kmajor(sP + kk * 32), umma_desc_mnmajor(vb + kk * 2048, 8192), idesc_o, kk > 0 ? 1u : 0u);
+        if (leader) umma_commit(bar_o);
+        if (j + 2 < n) issue_s(j + 2);
+        if (j + 3 < n) {
+          mbar_wait_backoff(bar_o, j & 1);  // P V(j) done: ring slot j % 3 is free
+          load_kv(j + 3);
+        }
+      }
     }
-    mbar_wait(bar_o, ph);
+  } else {
+    // ------------------------------------------ softmax warps ------------------------------------------
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    const int qrow = q0 + tid;
+
+    for (int j = 0; j < n; ++j) {
+      const int kv0 = j * 64;
+      mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[64];
+      {
+        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
+        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
+        tmem_ld32(t_lane + T_S + (j & 1) * 64, lo);
+        tmem_ld32(t_lane + T_S + (j & 1) * 64 + 32, hi);
+        tmem_ld_wait();
+      }
+      if (kv0 + 63 > q0) {  // diagonal blocks: causal mask
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (kv0 + c > qrow) sv[c] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;  // scale > 0: max commutes with the scaling
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = fast_exp2(m_run - m_new);
+      uint32_t pk[32];
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; c += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), p.scale_log2, -m_new));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), p.scale_log2, -m_new));
+        rs0 += p0;
+        rs1 += p1;
+        pk[c >> 1] = pack_bf16x2(p0, p1);
+      }
+      l_run = l_run * alpha + (rs0 + rs1);
+      m_run = m_new;
+      if (j > 0) {  // fold the previous block's P V (finished under the work above) into the running output
+        mbar_wait(bar_o, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + T_O + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[c * 32 + e] = fmaf(o[c * 32 + e], alpha_prev, __uint_as_float(v[e]));
+        }
+      }
+      alpha_prev = alpha;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8)
+        *reinterpret_cast<uint4*>(smem + FWD_SP + sw128_offset(tid, c8)) =
+            make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    mbar_wait(bar_o, (n - 1) & 1);
     tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {  // V buffer is free
-      mbar_arrive_expect_tx(bar_v, 16384);
-      tma_load_2d(smem + FWD_SV, &tmKV, bar_v, colV, row_base + kv0 + 64);
-      tma_load_2d(smem + FWD_SV + 8192, &tmKV, bar_v, colV + 64, row_base + kv0 + 64);
-    }
+    const float inv_l = 1.f / l_run;
+    bf16* orow = p.out + static_cast<size_t>(row_base + qrow) * (p.H * HD) + h * HD;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
       tmem_ld32(t_lane + T_O + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) o[c * 32 + e] = o[c * 32 + e] * alpha + __uint_as_float(v[e]);
-    }
-    tc_fence_before();
-  }
-
-  const float inv_l = 1.f / l_run;
-  bf16* orow = p.out + static_cast<size_t>(row_base + qrow) * (p.H * HD) + h * HD;
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float f[8];
 #pragma unroll
-  for (int c8 = 0; c8 < 16; ++c8) {
-    uint4 u;
-    u.x = pack_bf16x2(o[c8 * 8 + 0] * inv_l, o[c8 * 8 + 1] * inv_l);
-    u.y = pack_bf16x2(o[c8 * 8 + 2] * inv_l, o[c8 * 8 + 3] * inv_l);
-    u.z = pack_bf16x2(o[c8 * 8 + 4] * inv_l, o[c8 * 8 + 5] * inv_l);
-    u.w = pack_bf16x2(o[c8 * 8 + 6] * inv_l, o[c8 * 8 + 7] * inv_l);
-    reinterpret_cast<uint4*>(orow)[c8] = u;
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(o[c * 32 + c8 * 8 + e], alpha_prev, __uint_as_float(v[c8 * 8 + e])) * inv_l;
+        uint4 u;
+        u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+        u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+        reinterpret_cast<uint4*>(orow)[c * 4 + c8] = u;
+      }
+    }
+    if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = m_run + log2f(l_run);
   }
-  if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = m_run + log2f(l_run);
 
   tc_fence_before();
   __syncthreads();
@@ -244,21 +279,22 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
 // ================================================================================================
 // backward: dQ
 // ================================================================================================
-constexpr int DQ_SQ = 0;                  // 2 x [128 x 128B]
-constexpr int DQ_SDO = 32768;             // 2 x [128 x 128B]
-constexpr int DQ_SK = 65536;              // 2 x [64 x 128B]
-constexpr int DQ_SV = DQ_SK + 16384;      // 2 x [64 x 128B], reused for dS [128 x 128B]
-constexpr int DQ_BAR = DQ_SV + 16384;
-constexpr int DQ_SMEM = DQ_BAR + 128 + 1024;
+constexpr int DQ_SQ = 0;                    // 2 x [128 x 128B]
+constexpr int DQ_SDO = 32768;               // 2 x [128 x 128B]
+constexpr int DQ_SK = 65536;                // 3 x (2 x [64 x 128B])
+constexpr int DQ_SV = DQ_SK + 3 * 16384;    // 3 x (2 x [64 x 128B])
+constexpr int DQ_SDS = DQ_SV + 3 * 16384;   // [128 x 128B]
+constexpr int DQ_BAR = DQ_SDS + 16384;
+constexpr int DQ_SMEM = DQ_BAR + 256 + 1024;
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                const __grid_constant__ CUtensorMap tmDO, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
-  uint64_t *bar_q = bars, *bar_kv = bars + 1, *bar_s = bars + 2, *bar_o = bars + 3;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[3]*/, *bar_s = bars + 4 /*[2]*/, *bar_o = bars + 6, *bar_p = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int nqb = p.S / 128;
   const int qb = nqb - 1 - (blockIdx.x % nqb);
@@ -266,7 +302,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int h = bh % p.H, b = bh / p.H;
   const int q0 = qb * 128;
   const int row_base = b * p.S;
-  const int n_kv = (q0 + 128) / 64;
+  const int n = (q0 + 128) / 64;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int colQ = h * HD, colK = p.H * HD + h * HD, colV = 2 * p.H * HD + h * HD;
 
@@ -274,164 +310,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmDO);
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_ptr, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const uint32_t T_S = 0, T_DP = 64, T_DQ = 128;
-
-  auto load_kv = [&](int kv0) {
-    mbar_arrive_expect_tx(bar_kv, 32768);
-    tma_load_2d(smem + DQ_SK, &tmKV, bar_kv, colK, row_base + kv0);
-    tma_load_2d(smem + DQ_SK + 8192, &tmKV, bar_kv, colK + 64, row_base + kv0);
-    tma_load_2d(smem + DQ_SV, &tmKV, bar_kv, colV, row_base + kv0);
-    tma_load_2d(smem + DQ_SV + 8192, &tmKV, bar_kv, colV + 64, row_base + kv0);
-  };
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, 65536);
-    tma_load_2d(smem + DQ_SQ, &tmQ, bar_q, colQ, row_base + q0);
-    tma_load_2d(smem + DQ_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
-    tma_load_2d(smem + DQ_SDO, &tmDO, bar_q, h * HD, row_base + q0);
-    tma_load_2d(smem + DQ_SDO + 16384, &tmDO, bar_q, h * HD + 64, row_base + q0);
-    load_kv(0);
-  }
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-  constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);
-  const uint32_t sQ = smem_u32(smem + DQ_SQ), sDO = smem_u32(smem + DQ_SDO), sK = smem_u32(smem + DQ_SK),
-                 sV = smem_u32(smem + DQ_SV);
-  const int qrow = q0 + tid;
-  const size_t stat_idx = (static_cast<size_t>(b) * p.H + h) * p.S + qrow;
-  const float lse2 = p.lse2[stat_idx];
-  const float delta = p.delta[stat_idx];
-
-  for (int j = 0; j < n_kv; ++j) {
-    const uint32_t ph = j & 1;
-    const int kv0 = j * 64;
-    if (tid == 0) {
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int k16 = 0; k16 < 8; ++k16)
-        umma_bf16(tmem + T_S, umma_desc_kmajor(kmaj_addr(sQ, k16, 16384)), umma_desc_kmajor(kmaj_addr(sK, k16, 8192)),
-                  idesc_s, k16 > 0 ? 1u : 0u);
-#pragma unroll
-      for (int k16 = 0; k16 < 8; ++k16)
-        umma_bf16(tmem + T_DP, umma_desc_kmajor(kmaj_addr(sDO, k16, 16384)), umma_desc_kmajor(kmaj_addr(sV, k16, 8192)),
-                  idesc_s, k16 > 0 ? 1u : 0u);
-      umma_commit(bar_s);
-    }
-    mbar_wait(bar_s, ph);
-    tc_fence_after();
-    const bool need_mask = (kv0 + 63 > q0);
-    uint8_t* dsrow = smem + DQ_SV;  // V is dead once dP is complete
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t sv[32], dv[32];
-      tmem_ld32(t_lane + T_S + half * 32, sv);
-      tmem_ld32(t_lane + T_DP + half * 32, dv);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        float ds[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = half * 32 + c8 * 8 + e;
-          float pr = exp2f(__uint_as_float(sv[c8 * 8 + e]) * p.scale_log2 - lse2);
-          if (need_mask && (kv0 + c > qrow)) pr = 0.f;
-          ds[e] = pr * (__uint_as_float(dv[c8 * 8 + e]) - delta) * p.scale;
-        }
-        uint4 u;
-        u.x = pack_bf16x2(ds[0], ds[1]); u.y = pack_bf16x2(ds[2], ds[3]);
-        u.z = pack_bf16x2(ds[4], ds[5]); u.w = pack_bf16x2(ds[6], ds[7]);
-        *reinterpret_cast<uint4*>(dsrow + sw128_offset(tid, half * 4 + c8)) = u;
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16(tmem + T_DQ, umma_desc_kmajor(sV + kk * 32), umma_desc_mnmajor(sK + kk * 2048, 8192), idesc_dq,
-                  (j > 0 || kk > 0) ? 1u : 0u);
-      umma_commit(bar_o);
-      mbar_wait(bar_o, ph);  // K and V/dS buffers free again
-      if (j + 1 < n_kv) load_kv(kv0 + 64);
-    }
-  }
-  // all threads: wait for the last dQ MMA
-  mbar_wait(bar_o, (n_kv - 1) & 1);
-  tc_fence_after();
-  bf16* drow = p.dqkv + static_cast<size_t>(row_base + qrow) * (3 * p.H * HD) + colQ;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    tmem_ld32(t_lane + T_DQ + c * 32, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int c8 = 0; c8 < 4; ++c8) {
-      uint4 u;
-      u.x = pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
-      u.y = pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
-      u.z = pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5]));
-      u.w = pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7]));
-      reinterpret_cast<uint4*>(drow)[c * 4 + c8] = u;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 256);
-  }
-}
-
-// ================================================================================================
-// backward: dK, dV
-// ================================================================================================
-constexpr int DKV_SK = 0;                   // 2 x [128 x 128B]
-constexpr int DKV_SV = 32768;               // 2 x [128 x 128B]
-constexpr int DKV_SQ = 65536;               // 2 x [64 x 128B]
-constexpr int DKV_SDO = DKV_SQ + 16384;     // 2 x [64 x 128B]
-constexpr int DKV_SPT = DKV_SDO + 16384;    // [128 x 128B]  P^T
-constexpr int DKV_SDST = DKV_SPT + 16384;   // [128 x 128B]  dS^T
-constexpr int DKV_STAT = DKV_SDST + 16384;  // lse2[64], delta[64]
-constexpr int DKV_BAR = DKV_STAT + 512;
-constexpr int DKV_SMEM = DKV_BAR + 128 + 1024;
-
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmQ64,
-                const __grid_constant__ CUtensorMap tmDO64, const AttnKParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_BAR);
-  uint64_t *bar_kv = bars, *bar_q = bars + 1, *bar_s = bars + 2, *bar_o = bars + 3;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
-  float* s_lse = reinterpret_cast<float*>(smem + DKV_STAT);
-  float* s_delta = s_lse + 64;
-
-  const int nkb = p.S / 128;
-  const int kb = blockIdx.x % nkb;  // early KV blocks see the most query blocks: they come first
-  const int bh = blockIdx.x / nkb;
-  const int h = bh % p.H, b = bh / p.H;
-  const int kv0 = kb * 128;
-  const int row_base = b * p.S;
-  const int i0 = kv0 / 64, n_q = p.S / 64;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int colQ = h * HD, colK = p.H * HD + h * HD, colV = 2 * p.H * HD + h * HD;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmKV128);
-    tma_prefetch_desc(&tmQ64);
-    tma_prefetch_desc(&tmDO64);
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_p, 256);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr, 512);
@@ -439,111 +319,300 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const uint32_t T_ST = 0, T_DPT = 64, T_DV = 128, T_DK = 256;
+  const uint32_t T_S = 0 /* +64*buf */, T_DP = 128 /* +64*buf */, T_DQ = 256;
 
-  auto load_q = [&](int qs) {
-    mbar_arrive_expect_tx(bar_q, 32768);
-    tma_load_2d(smem + DKV_SQ, &tmQ64, bar_q, colQ, row_base + qs);
-    tma_load_2d(smem + DKV_SQ + 8192, &tmQ64, bar_q, colQ + 64, row_base + qs);
-    tma_load_2d(smem + DKV_SDO, &tmDO64, bar_q, h * HD, row_base + qs);
-    tma_load_2d(smem + DKV_SDO + 8192, &tmDO64, bar_q, h * HD + 64, row_base + qs);
-  };
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_kv, 65536);
-    tma_load_2d(smem + DKV_SK, &tmKV128, bar_kv, colK, row_base + kv0);
-    tma_load_2d(smem + DKV_SK + 16384, &tmKV128, bar_kv, colK + 64, row_base + kv0);
-    tma_load_2d(smem + DKV_SV, &tmKV128, bar_kv, colV, row_base + kv0);
-    tma_load_2d(smem + DKV_SV + 16384, &tmKV128, bar_kv, colV + 64, row_base + kv0);
-    load_q(i0 * 64);
-  }
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-  constexpr uint32_t idesc_g = umma_idesc_bf16(128, 128, 0, 1);
-  const uint32_t sK = smem_u32(smem + DKV_SK), sV = smem_u32(smem + DKV_SV), sQ = smem_u32(smem + DKV_SQ),
-                 sDO = smem_u32(smem + DKV_SDO), sPT = smem_u32(smem + DKV_SPT), sDST = smem_u32(smem + DKV_SDST);
-  const int kvrow = kv0 + tid;
-  const float* g_lse = p.lse2 + (static_cast<size_t>(b) * p.H + h) * p.S;
-  const float* g_delta = p.delta + (static_cast<size_t>(b) * p.H + h) * p.S;
-
-  for (int i = i0; i < n_q; ++i) {
-    const uint32_t ph = (i - i0) & 1;
-    const int qs = i * 64;
-    if (tid < 64) {
-      s_lse[tid] = g_lse[qs + tid];
-      s_delta[tid] = g_delta[qs + tid];
+  if (warp == 8) {
+    {
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);
+      const uint32_t sQ = smem_u32(smem + DQ_SQ), sDO = smem_u32(smem + DQ_SDO), sK = smem_u32(smem + DQ_SK),
+                     sV = smem_u32(smem + DQ_SV), sDS = smem_u32(smem + DQ_SDS);
+      auto load_kv = [&](int j) {
+        const int slot = j % 3;
+        if (!leader) return;
+        mbar_arrive_expect_tx(&bar_kv[slot], 32768);
+        tma_load_2d(smem + DQ_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
+        tma_load_2d(smem + DQ_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
+        tma_load_2d(smem + DQ_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
+        tma_load_2d(smem + DQ_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
+      };
+      auto issue_s = [&](int j) {  // S(j) = Q K(j)^T and dP(j) = dO V(j)^T into buffer j & 1
+        const int slot = j % 3;
+        mbar_wait_backoff(&bar_kv[slot], (j / 3) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16)
+          if (leader) umma_bf16(tmem + T_S + (j & 1) * 64, umma_desc_kmajor(kmaj_addr(sQ, k16, 16384)),
+                    umma_desc_kmajor(kmaj_addr(sK + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16)
+          if (leader) umma_bf16(tmem + T_DP + (j & 1) * 64, umma_desc_kmajor(kmaj_addr(sDO, k16, 16384)),
+                    umma_desc_kmajor(kmaj_addr(sV + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+        if (leader) umma_commit(&bar_s[j & 1]);
+      };
+      if (leader) {
+        mbar_arrive_expect_tx(bar_q, 65536);
+        tma_load_2d(smem + DQ_SQ, &tmQ, bar_q, colQ, row_base + q0);
+        tma_load_2d(smem + DQ_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
+        tma_load_2d(smem + DQ_SDO, &tmDO, bar_q, h * HD, row_base + q0);
+        tma_load_2d(smem + DQ_SDO + 16384, &tmDO, bar_q, h * HD + 64, row_base + q0);
+      }
+      for (int j = 0; j < 3 && j < n; ++j) load_kv(j);
+      mbar_wait_backoff(bar_q, 0);
+      issue_s(0);
+      if (n > 1) issue_s(1);
+      for (int j = 0; j < n; ++j) {
+        mbar_wait_backoff(bar_p, j & 1);  // dS(j) is in smem; score buffers j&1 have been consumed
+        tc_fence_after();
+        const uint32_t kb = sK + (j % 3) * 16384;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          if (leader) umma_bf16(tmem + T_DQ, umma_desc_kmajor(sDS + kk * 32), umma_desc_mnmajor(kb + kk * 2048, 8192), idesc_dq,
+                    (j > 0 || kk > 0) ? 1u : 0u);
+        if (leader) umma_commit(bar_o);
+        if (j + 2 < n) issue_s(j + 2);
+        if (j + 3 < n) {
+          mbar_wait_backoff(bar_o, j & 1);  // dQ MMA(j) done: ring slot j % 3 is free
+          load_kv(j + 3);
+        }
+      }
     }
-    if (tid == 0) {
-      if (i == i0) mbar_wait(bar_kv, 0);
-      mbar_wait(bar_q, ph);
+  } else {
+    // 8 compute warps: warps w and w+4 share the TMEM lanes (score rows) 32*(w&3)..+31 and split the 64 columns
+    const int rw = warp & 3, half = warp >> 2;
+    const int r = rw * 32 + (tid & 31);
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(rw * 32) << 16);
+    const int qrow = q0 + r;
+    const size_t stat_idx = (static_cast<size_t>(b) * p.H + h) * p.S + qrow;
+    const float lse2 = p.lse2[stat_idx];
+    const float delta = p.delta[stat_idx];
+
+    for (int j = 0; j < n; ++j) {
+      const int kv0 = j * 64;
+      mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      uint32_t sv[32], dv[32], pk[16];
+      tmem_ld32(t_lane + T_S + (j & 1) * 64 + half * 32, sv);
+      tmem_ld32(t_lane + T_DP + (j & 1) * 64 + half * 32, dv);
+      tmem_ld_wait();
+      if (kv0 + 63 > q0) {  // diagonal blocks
 #pragma unroll
-      for (int k16 = 0; k16 < 8; ++k16)
-        umma_bf16(tmem + T_ST, umma_desc_kmajor(kmaj_addr(sK, k16, 16384)), umma_desc_kmajor(kmaj_addr(sQ, k16, 8192)),
-                  idesc_s, k16 > 0 ? 1u : 0u);
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse2));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse2));
+          if (kv0 + half * 32 + e > qrow) p0 = 0.f;
+          if (kv0 + half * 32 + e + 1 > qrow) p1 = 0.f;
+          pk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta) * p.scale, p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale);
+        }
+      } else {
 #pragma unroll
-      for (int k16 = 0; k16 < 8; ++k16)
-        umma_bf16(tmem + T_DPT, umma_desc_kmajor(kmaj_addr(sV, k16, 16384)), umma_desc_kmajor(kmaj_addr(sDO, k16, 8192)),
-                  idesc_s, k16 > 0 ? 1u : 0u);
-      umma_commit(bar_s);
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse2));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse2));
+          pk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta) * p.scale, p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale);
+        }
+      }
+      if (j > 0) mbar_wait(bar_o, (j - 1) & 1);  // dQ MMA of block j-1 done: the dS buffer is free
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8)
+        *reinterpret_cast<uint4*>(smem + DQ_SDS + sw128_offset(r, half * 4 + c8)) =
+            make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
     }
-    __syncthreads();  // s_lse / s_delta visible
-    mbar_wait(bar_s, ph);
+    mbar_wait(bar_o, (n - 1) & 1);
     tc_fence_after();
-    const bool need_mask = (qs < kv0 + 127);
+    bf16* drow = p.dqkv + static_cast<size_t>(row_base + qrow) * (3 * p.H * HD) + colQ + half * 64;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t sv[32], dv[32];
-      tmem_ld32(t_lane + T_ST + half * 32, sv);
-      tmem_ld32(t_lane + T_DPT + half * 32, dv);
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + T_DQ + half * 64 + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
-        float pt[8], ds[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = half * 32 + c8 * 8 + e;  // query column
-          float pr = exp2f(__uint_as_float(sv[c8 * 8 + e]) * p.scale_log2 - s_lse[c]);
-          if (need_mask && (kvrow > qs + c)) pr = 0.f;
-          pt[e] = pr;
-          ds[e] = pr * (__uint_as_float(dv[c8 * 8 + e]) - s_delta[c]) * p.scale;
-        }
-        uint4 u, w;
-        u.x = pack_bf16x2(pt[0], pt[1]); u.y = pack_bf16x2(pt[2], pt[3]);
-        u.z = pack_bf16x2(pt[4], pt[5]); u.w = pack_bf16x2(pt[6], pt[7]);
-        w.x = pack_bf16x2(ds[0], ds[1]); w.y = pack_bf16x2(ds[2], ds[3]);
-        w.z = pack_bf16x2(ds[4], ds[5]); w.w = pack_bf16x2(ds[6], ds[7]);
-        const uint32_t off = sw128_offset(tid, half * 4 + c8);
-        *reinterpret_cast<uint4*>(smem + DKV_SPT + off) = u;
-        *reinterpret_cast<uint4*>(smem + DKV_SDST + off) = w;
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
+        u.y = pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
+        u.z = pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5]));
+        u.w = pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7]));
+        reinterpret_cast<uint4*>(drow)[c * 4 + c8] = u;
       }
     }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t first = (i == i0) ? 0u : 1u;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16(tmem + T_DV, umma_desc_kmajor(sPT + kk * 32), umma_desc_mnmajor(sDO + kk * 2048, 8192), idesc_g,
-                  (first || kk > 0) ? 1u : 0u);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16(tmem + T_DK, umma_desc_kmajor(sDST + kk * 32), umma_desc_mnmajor(sQ + kk * 2048, 8192), idesc_g,
-                  (first || kk > 0) ? 1u : 0u);
-      umma_commit(bar_o);
-      mbar_wait(bar_o, ph);  // Q/dO/P^T/dS^T buffers free again
-      if (i + 1 < n_q) load_q(qs + 64);
-    }
   }
-  mbar_wait(bar_o, (n_q - 1 - i0) & 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ================================================================================================
+// backward: dK, dV
+// ================================================================================================
+constexpr int DKV_SK = 0;                      // 2 x [128 x 128B]
+constexpr int DKV_SV = 32768;                  // 2 x [128 x 128B]
+constexpr int DKV_SQ = 65536;                  // 3 x (2 x [64 x 128B])
+constexpr int DKV_SDO = DKV_SQ + 3 * 16384;    // 3 x (2 x [64 x 128B])
+constexpr int DKV_SPT = DKV_SDO + 3 * 16384;   // [128 x 128B]  P^T
+constexpr int DKV_SDST = DKV_SPT + 16384;      // [128 x 128B]  dS^T
+constexpr int DKV_STAT = DKV_SDST + 16384;     // 3 x (lse2[64], delta[64]) fp32, filled by bulk copies with the Q ring
+constexpr int DKV_BAR = DKV_STAT + 3 * 512;
+constexpr int DKV_SMEM = DKV_BAR + 256 + 1024;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmQ64,
+                const __grid_constant__ CUtensorMap tmDO64, const AttnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_BAR);
+  uint64_t *bar_kv = bars, *bar_q = bars + 1 /*[3]*/, *bar_s = bars + 4 /*[2]*/, *bar_o = bars + 6, *bar_p = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int nkb = p.S / 128;
+  const int kb = blockIdx.x % nkb;  // early KV blocks see the most query blocks: they come first
+  const int bh = blockIdx.x / nkb;
+  const int h = bh % p.H, b = bh / p.H;
+  const int kv0 = kb * 128;
+  const int row_base = b * p.S;
+  const int i0 = kv0 / 64;
+  const int n = p.S / 64 - i0;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int colQ = h * HD, colK = p.H * HD + h * HD, colV = 2 * p.H * HD + h * HD;
+  const float* g_lse = p.lse2 + (static_cast<size_t>(b) * p.H + h) * p.S;
+  const float* g_delta = p.delta + (static_cast<size_t>(b) * p.H + h) * p.S;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmKV128);
+    tma_prefetch_desc(&tmQ64);
+    tma_prefetch_desc(&tmDO64);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_p, 256);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
   tc_fence_after();
-  bf16* dkrow = p.dqkv + static_cast<size_t>(row_base + kvrow) * (3 * p.H * HD) + colK;
-  bf16* dvrow = p.dqkv + static_cast<size_t>(row_base + kvrow) * (3 * p.H * HD) + colV;
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t T_ST = 0 /* +64*buf */, T_DPT = 128 /* +64*buf */, T_DV = 256, T_DK = 384;
+
+  if (warp == 8) {
+    {
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, 128, 0, 1);
+      const uint32_t sK = smem_u32(smem + DKV_SK), sV = smem_u32(smem + DKV_SV), sQ = smem_u32(smem + DKV_SQ),
+                     sDO = smem_u32(smem + DKV_SDO), sPT = smem_u32(smem + DKV_SPT), sDST = smem_u32(smem + DKV_SDST);
+      auto load_q = [&](int ii) {  // query block i0+ii (Q, dO, lse2, delta) -> ring slot ii % 3
+        const int slot = ii % 3, qs = (i0 + ii) * 64;
+        if (!leader) return;
+        mbar_arrive_expect_tx(&bar_q[slot], 32768 + 512);
+        tma_load_2d(smem + DKV_SQ + slot * 16384, &tmQ64, &bar_q[slot], colQ, row_base + qs);
+        tma_load_2d(smem + DKV_SQ + slot * 16384 + 8192, &tmQ64, &bar_q[slot], colQ + 64, row_base + qs);
+        tma_load_2d(smem + DKV_SDO + slot * 16384, &tmDO64, &bar_q[slot], h * HD, row_base + qs);
+        tma_load_2d(smem + DKV_SDO + slot * 16384 + 8192, &tmDO64, &bar_q[slot], h * HD + 64, row_base + qs);
+        tma_load_1d(smem + DKV_STAT + slot * 512, g_lse + qs, 256, &bar_q[slot]);
+        tma_load_1d(smem + DKV_STAT + slot * 512 + 256, g_delta + qs, 256, &bar_q[slot]);
+      };
+      auto issue_s = [&](int ii) {  // S^T = K Q^T, dP^T = V dO^T into buffer ii & 1
+        const int slot = ii % 3;
+        mbar_wait_backoff(&bar_q[slot], (ii / 3) & 1);
+        tc_fence_after();
 #pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    bf16* drow = which ? dkrow : dvrow;
-    const uint32_t tcol = which ? T_DK : T_DV;
+        for (int k16 = 0; k16 < 8; ++k16)
+          if (leader) umma_bf16(tmem + T_ST + (ii & 1) * 64, umma_desc_kmajor(kmaj_addr(sK, k16, 16384)),
+                    umma_desc_kmajor(kmaj_addr(sQ + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16)
+          if (leader) umma_bf16(tmem + T_DPT + (ii & 1) * 64, umma_desc_kmajor(kmaj_addr(sV, k16, 16384)),
+                    umma_desc_kmajor(kmaj_addr(sDO + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+        if (leader) umma_commit(&bar_s[ii & 1]);
+      };
+      if (leader) {
+        mbar_arrive_expect_tx(bar_kv, 65536);
+        tma_load_2d(smem + DKV_SK, &tmKV128, bar_kv, colK, row_base + kv0);
+        tma_load_2d(smem + DKV_SK + 16384, &tmKV128, bar_kv, colK + 64, row_base + kv0);
+        tma_load_2d(smem + DKV_SV, &tmKV128, bar_kv, colV, row_base + kv0);
+        tma_load_2d(smem + DKV_SV + 16384, &tmKV128, bar_kv, colV + 64, row_base + kv0);
+      }
+      for (int ii = 0; ii < 3 && ii < n; ++ii) load_q(ii);
+      mbar_wait_backoff(bar_kv, 0);
+      issue_s(0);
+      if (n > 1) issue_s(1);
+      for (int ii = 0; ii < n; ++ii) {
+        mbar_wait_backoff(bar_p, ii & 1);  // P^T / dS^T of block ii are in smem; score buffers ii&1 consumed
+        tc_fence_after();
+        const uint32_t first = (ii == 0) ? 0u : 1u;
+        const uint32_t qb_ = sQ + (ii % 3) * 16384, dob = sDO + (ii % 3) * 16384;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          if (leader) umma_bf16(tmem + T_DV, umma_desc_kmajor(sPT + kk * 32), umma_desc_mnmajor(dob + kk * 2048, 8192), idesc_g,
+                    (first || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          if (leader) umma_bf16(tmem + T_DK, umma_desc_kmajor(sDST + kk * 32), umma_desc_mnmajor(qb_ + kk * 2048, 8192), idesc_g,
+                    (first || kk > 0) ? 1u : 0u);
+        if (leader) umma_commit(bar_o);
+        if (ii + 2 < n) issue_s(ii + 2);
+        if (ii + 3 < n) {
+          mbar_wait_backoff(bar_o, ii & 1);  // dV/dK MMAs(ii) done: ring slot ii % 3 is free
+          load_q(ii + 3);
+        }
+      }
+    }
+  } else {
+    // 8 compute warps: warps w and w+4 share the TMEM lanes (kv rows) 32*(w&3)..+31 and split the 64 query columns
+    const int rw = warp & 3, half = warp >> 2;
+    const int r = rw * 32 + (tid & 31);
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(rw * 32) << 16);
+    const int kvrow = kv0 + r;
+    for (int ii = 0; ii < n; ++ii) {
+      const int qs = (i0 + ii) * 64;
+      mbar_wait(&bar_q[ii % 3], (ii / 3) & 1);  // acquire the TMA-written row statistics of this ring slot
+      mbar_wait(&bar_s[ii & 1], (ii >> 1) & 1);
+      tc_fence_after();
+      const float* st = reinterpret_cast<const float*>(smem + DKV_STAT + (ii % 3) * 512) + half * 32;
+      uint32_t sv[32], dv[32], ppk[16], dpk[16];
+      tmem_ld32(t_lane + T_ST + (ii & 1) * 64 + half * 32, sv);
+      tmem_ld32(t_lane + T_DPT + (ii & 1) * 64 + half * 32, dv);
+      tmem_ld_wait();
+      const bool need_mask = (qs < kv0 + 127);
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(st + e);
+        const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + e);
+        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds4[4] = {d4.x, d4.y, d4.z, d4.w};
+        float pr[4], dsv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          pr[u] = fast_exp2(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, -ls[u]));
+          if (need_mask && (kvrow > qs + half * 32 + e + u)) pr[u] = 0.f;
+          dsv[u] = pr[u] * (__uint_as_float(dv[e + u]) - ds4[u]) * p.scale;
+        }
+        ppk[e >> 1] = pack_bf16x2(pr[0], pr[1]);
+        ppk[(e >> 1) + 1] = pack_bf16x2(pr[2], pr[3]);
+        dpk[e >> 1] = pack_bf16x2(dsv[0], dsv[1]);
+        dpk[(e >> 1) + 1] = pack_bf16x2(dsv[2], dsv[3]);
+      }
+      if (ii > 0) mbar_wait(bar_o, (ii - 1) & 1);  // dV/dK MMAs of block ii-1 done: P^T/dS^T buffers are free
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        const uint32_t off = sw128_offset(r, half * 4 + c8);
+        *reinterpret_cast<uint4*>(smem + DKV_SPT + off) = make_uint4(ppk[4 * c8], ppk[4 * c8 + 1], ppk[4 * c8 + 2], ppk[4 * c8 + 3]);
+        *reinterpret_cast<uint4*>(smem + DKV_SDST + off) = make_uint4(dpk[4 * c8], dpk[4 * c8 + 1], dpk[4 * c8 + 2], dpk[4 * c8 + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    mbar_wait(bar_o, (n - 1) & 1);
+    tc_fence_after();
+    // warps 0-3 write dV, warps 4-7 write dK (each thread one full 128-wide row)
+    bf16* drow = p.dqkv + static_cast<size_t>(row_base + kvrow) * (3 * p.H * HD) + (half ? colK : colV);
+    const uint32_t tcol = half ? T_DK : T_DV;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
@@ -627,8 +696,8 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
     const long long grid = (warps * 32 + block - 1) / block;
     attn_delta_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(a.out, a.dout, a.delta, a.B, a.S, a.H);
   }
-  attn_dq_kernel<<<a.B * a.H * (a.S / 128), ATT_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, p);
-  attn_dkv_kernel<<<a.B * a.H * (a.S / 128), ATT_THREADS, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, p);
+  attn_dq_kernel<<<a.B * a.H * (a.S / 128), BWD_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, p);
+  attn_dkv_kernel<<<a.B * a.H * (a.S / 128), BWD_THREADS, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, p);
   return cudaGetLastError();
 }
 

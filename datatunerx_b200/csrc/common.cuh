@@ -28,6 +28,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+// One lane of a converged warp.  Issuer warps run their loops warp-uniformly and predicate only the TMA / MMA / commit
+// instructions on this: descriptor and address arithmetic then stays in the uniform datapath instead of being computed in
+// vector registers and moved (R2UR) one operand at a time in front of every tcgen05.mma.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier
@@ -83,6 +97,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// Wait used by single-thread issuer roles that share an SM sub-partition with a compute warp: back off between polls
+// so the spinning lane does not take issue slots from the warp doing arithmetic.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+#if DTX_WATCHDOG
+  const long long t0 = clock64();
+#endif
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+#if DTX_WATCHDOG
+    if (clock64() - t0 > 4000000000LL) {
+      printf("[dtx] mbarrier watchdog (issuer): block %d bar@%u parity %u\n", (int)blockIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+#endif
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
@@ -101,6 +133,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
       : "memory");
+}
+// 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16), completes `bytes` on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

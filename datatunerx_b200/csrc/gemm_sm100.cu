@@ -154,7 +154,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -163,24 +164,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int m0 = m_blk * BM, n0 = n_blk * BN;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
           const bool seg2 = kb >= p.kb1;
           const int kk = (seg2 ? kb - p.kb1 : kb) * BK;
           const CUtensorMap* ma = seg2 ? &tmA2 : &tmA;
           const CUtensorMap* mb = seg2 ? &tmB2 : &tmB;
-          if (!A_MN) {
-            tma_load_2d(a_dst, ma, &full_bar[stage], kk, m0);
-          } else {
+          if (leader) {
+            if (!A_MN) {
+              tma_load_2d(a_dst, ma, &full_bar[stage], kk, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, ma, &full_bar[stage], m0 + 64 * j, kk);
-          }
-          if (!B_MN) {
-            tma_load_2d(b_dst, mb, &full_bar[stage], kk, n0);
-          } else {
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, ma, &full_bar[stage], m0 + 64 * j, kk);
+            }
+            if (!B_MN) {
+              tma_load_2d(b_dst, mb, &full_bar[stage], kk, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, mb, &full_bar[stage], n0 + 64 * j, kk);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, mb, &full_bar[stage], n0 + 64 * j, kk);
+            }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -188,7 +191,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -209,12 +213,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k16 = 0; k16 < BK / 16; ++k16) {
             const uint64_t da = A_MN ? umma_desc_mnmajor(a_base + k16 * 2048, 8192) : umma_desc_kmajor(a_base + k16 * 32);
             const uint64_t db = B_MN ? umma_desc_mnmajor(b_base + k16 * 2048, 8192) : umma_desc_kmajor(b_base + k16 * 32);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb_begin || k16 > 0) ? 1u : 0u);
+            if (leader) umma_bf16(d_tmem, da, db, idesc, (kb > kb_begin || k16 > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (leader) umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (leader) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -332,7 +336,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
@@ -342,7 +347,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n0 = n_blk * 256 + 128 * static_cast<int>(rank);
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+          if (leader && rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
           const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
           uint8_t* a_dst = smem + stage * G2_STAGE_BYTES;
           uint8_t* b_dst = a_dst + G2_A_BYTES;
@@ -350,19 +355,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int kk = (seg2 ? kb - p.kb1 : kb) * BK;
           const CUtensorMap* ma = seg2 ? &tmA2 : &tmA;
           const CUtensorMap* mb = seg2 ? &tmB2 : &tmB;
-          tma_load_2d_pair(a_dst, ma, leader_full, kk, m0);
-          if (!B_MN) {
-            tma_load_2d_pair(b_dst, mb, leader_full, kk, n0);
-          } else {
-            tma_load_2d_pair(b_dst, mb, leader_full, n0, kk);
-            tma_load_2d_pair(b_dst + 8192, mb, leader_full, n0 + 64, kk);
+          if (leader) {
+            tma_load_2d_pair(a_dst, ma, leader_full, kk, m0);
+            if (!B_MN) {
+              tma_load_2d_pair(b_dst, mb, leader_full, kk, n0);
+            } else {
+              tma_load_2d_pair(b_dst, mb, leader_full, n0, kk);
+              tma_load_2d_pair(b_dst + 8192, mb, leader_full, n0 + 64, kk);
+            }
           }
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(256, 256, 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -381,12 +389,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int k16 = 0; k16 < BK / 16; ++k16) {
             const uint64_t da = umma_desc_kmajor(a_base + k16 * 32);
             const uint64_t db = B_MN ? umma_desc_mnmajor(b_base + k16 * 2048, 8192) : umma_desc_kmajor(b_base + k16 * 32);
-            umma_bf16_pair(d_tmem, da, db, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+            if (leader) umma_bf16_pair(d_tmem, da, db, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
           }
-          umma_commit_pair(&empty_bar[stage], 3);
+          if (leader) umma_commit_pair(&empty_bar[stage], 3);
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_pair(&tfull_bar[acc], 3);
+        if (leader) umma_commit_pair(&tfull_bar[acc], 3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
