@@ -154,6 +154,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else {
     // ------------------------------------------ softmax warps ------------------------------------------
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t sP_addr = smem_u32(smem + FWD_SP);
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
     float o[HD];
 #pragma unroll
@@ -215,8 +216,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       alpha_prev = alpha;
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8)
-        *reinterpret_cast<uint4*>(smem + FWD_SP + sw128_offset(tid, c8)) =
-            make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+        sts128(sP_addr + sw128_offset(tid, c8), pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
@@ -384,6 +384,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int r = rw * 32 + (tid & 31);
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(rw * 32) << 16);
     const int qrow = q0 + r;
+    const uint32_t sDS_addr = smem_u32(smem + DQ_SDS);
     const size_t stat_idx = (static_cast<size_t>(b) * p.H + h) * p.S + qrow;
     const float lse2 = p.lse2[stat_idx];
     const float delta = p.delta[stat_idx];
@@ -416,8 +417,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (j > 0) mbar_wait(bar_o, (j - 1) & 1);  // dQ MMA of block j-1 done: the dS buffer is free
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8)
-        *reinterpret_cast<uint4*>(smem + DQ_SDS + sw128_offset(r, half * 4 + c8)) =
-            make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+        sts128(sDS_addr + sw128_offset(r, half * 4 + c8), pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
@@ -569,12 +569,13 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     const int r = rw * 32 + (tid & 31);
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(rw * 32) << 16);
     const int kvrow = kv0 + r;
+    const uint32_t sPT_addr = smem_u32(smem + DKV_SPT), sDST_addr = smem_u32(smem + DKV_SDST);
     for (int ii = 0; ii < n; ++ii) {
       const int qs = (i0 + ii) * 64;
       mbar_wait(&bar_q[ii % 3], (ii / 3) & 1);  // acquire the TMA-written row statistics of this ring slot
       mbar_wait(&bar_s[ii & 1], (ii >> 1) & 1);
       tc_fence_after();
-      const float* st = reinterpret_cast<const float*>(smem + DKV_STAT + (ii % 3) * 512) + half * 32;
+      const uint32_t st = smem_u32(smem + DKV_STAT + (ii % 3) * 512) + half * 128;
       uint32_t sv[32], dv[32], ppk[16], dpk[16];
       tmem_ld32(t_lane + T_ST + (ii & 1) * 64 + half * 32, sv);
       tmem_ld32(t_lane + T_DPT + (ii & 1) * 64 + half * 32, dv);
@@ -582,8 +583,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
       const bool need_mask = (qs < kv0 + 127);
 #pragma unroll
       for (int e = 0; e < 32; e += 4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(st + e);
-        const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + e);
+        const float4 l4 = lds128f(st + e * 4);
+        const float4 d4 = lds128f(st + 256 + e * 4);
         const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds4[4] = {d4.x, d4.y, d4.z, d4.w};
         float pr[4], dsv[4];
 #pragma unroll
@@ -601,8 +602,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         const uint32_t off = sw128_offset(r, half * 4 + c8);
-        *reinterpret_cast<uint4*>(smem + DKV_SPT + off) = make_uint4(ppk[4 * c8], ppk[4 * c8 + 1], ppk[4 * c8 + 2], ppk[4 * c8 + 3]);
-        *reinterpret_cast<uint4*>(smem + DKV_SDST + off) = make_uint4(dpk[4 * c8], dpk[4 * c8 + 1], dpk[4 * c8 + 2], dpk[4 * c8 + 3]);
+        sts128(sPT_addr + off, ppk[4 * c8], ppk[4 * c8 + 1], ppk[4 * c8 + 2], ppk[4 * c8 + 3]);
+        sts128(sDST_addr + off, dpk[4 * c8], dpk[4 * c8 + 1], dpk[4 * c8 + 2], dpk[4 * c8 + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();

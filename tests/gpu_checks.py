@@ -450,6 +450,97 @@ def check_gemm_pair_vs_single(M=8192, N=8192, K=4096):
     return res
 
 
+def check_trainer_100_steps():
+    """north_star: training loss within 1e-3 relative of the reference CPU path after 100 steps (tiny-Llama config).
+    Compared with the live fp32 oracle and with the committed oracle trace tests/golden/tiny_trace_100.json."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tiny_trace_100.json")))
+    ocfg, orc, tr = make_tiny_pair(steps=100)
+    S, B = tr.train.seq_len, tr.train.micro_batch
+    worst = worst_gold = 0.0
+    native, ref = [], []
+    for s in range(100):
+        ids, labels = O.synthetic_batch(s, 0, B, S, ocfg.vocab)
+        r = orc.step([(ids, labels)])
+        loss, gn, lr, _ = tr.step(ids, labels)
+        native.append(loss)
+        ref.append(r.loss)
+        worst = max(worst, abs(loss - r.loss) / r.loss)
+        g = gold["trace_loss_gradnorm_lr"][s]
+        worst_gold = max(worst_gold, abs(r.loss - g[0]) / g[0])
+        assert abs(lr - g[2]) <= 1e-6 * g[2] + 1e-12
+    tr.close()
+    w_nat, w_ref = float(np.mean(native[90:])), float(np.mean(ref[90:]))  # the value HF logs at step 100 (window mean)
+    res = {"worst_step_rel": worst, "step100_rel": abs(native[99] - ref[99]) / ref[99], "window_91_100_rel": abs(w_nat - w_ref) / w_ref,
+           "oracle_vs_golden_rel": worst_gold, "loss_step1": native[0], "loss_step100": native[99], "oracle_step100": ref[99]}
+    assert worst_gold < 1e-5, f"oracle drifted from its committed trace: {worst_gold}"
+    assert res["step100_rel"] < 1e-3 and res["window_91_100_rel"] < 1e-3 and worst < 1e-3, res
+    assert native[99] < native[0] - 0.01, "loss must go down"
+    return res
+
+
+def check_worker_end_to_end():
+    """The whole worker behind the controller's command line on a tiny HF-format model directory: argv -> CSV -> llama2
+    template -> native training -> PEFT adapter + checkpoint-path file + trainer_log.jsonl (cmd/tuning/train.py:308-389)."""
+    import json
+    import os
+    import shlex
+    import shutil
+    import tempfile
+    from datatunerx_b200.tuning import model_io, parser as TP
+    tmp = tempfile.mkdtemp(prefix="dtx_e2e_")
+    try:
+        mdir, out, store = os.path.join(tmp, "model"), os.path.join(tmp, "result"), os.path.join(tmp, "storage")
+        os.makedirs(mdir)
+        gold = os.path.join(os.path.dirname(__file__), "golden")
+        shutil.copy(os.path.join(gold, "tiny_tokenizer.json"), os.path.join(mdir, "tokenizer.json"))
+        json.dump({"tokenizer_class": "PreTrainedTokenizerFast", "bos_token": "<s>", "eos_token": "</s>", "unk_token": "<unk>"},
+                  open(os.path.join(mdir, "tokenizer_config.json"), "w"))
+        ocfg = O.OracleConfig(vocab=400, hidden=256, n_layers=2, n_heads=2, ffn=768)
+        json.dump({"architectures": ["LlamaForCausalLM"], "vocab_size": 400, "hidden_size": 256, "intermediate_size": 768,
+                   "num_hidden_layers": 2, "num_attention_heads": 2, "num_key_value_heads": 2, "rms_norm_eps": 1e-5, "rope_theta": 10000.0,
+                   "max_position_embeddings": 4096, "model_type": "llama"}, open(os.path.join(mdir, "config.json"), "w"))
+        model_io.write_safetensors(os.path.join(mdir, "model.safetensors"), {k: v.numpy() for k, v in O.init_base_weights(ocfg, 7).items()})
+        csv_path = os.path.join(tmp, "train.csv")
+        with open(csv_path, "w") as f:
+            f.write("q,a\n")
+            for i in range(48):
+                f.write(f"What is {i} plus {i}?,The answer is {2 * i}.\n")
+        ckpt_file = os.path.join(tmp, "checkpoint_path")
+        os.environ["DTX_CHECKPOINT_PATH_FILE"] = ckpt_file
+        import importlib
+        from datatunerx_b200.tuning import train as TT
+        importlib.reload(TT)
+        entry = TP.controller_entrypoint(mdir, csv_path, validate_file=csv_path, columns='{"instruction":"q","response":"a"}',
+                                         scheduler="linear", optimizer="adamw_hf", lora_r="16", lora_alpha="32", lora_dropout="0.0",
+                                         learning_rate="1e-3", epochs=2, block_size=256, batch_size=4, grad_acc_steps=1,
+                                         num_workers=1, storage_path=store, uid="e2e")
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            rc = TT.main(shlex.split(entry)[2:])
+        finally:
+            os.chdir(cwd)
+        assert rc == 0, f"worker exit status {rc}"
+        ckpt = open(ckpt_file).read()
+        assert not ckpt.endswith("\n") and ckpt.startswith(store) and os.path.isdir(ckpt), f"checkpoint path file: {ckpt!r}"
+        cfg = json.load(open(os.path.join(ckpt, "adapter_config.json")))
+        assert cfg["r"] == 16 and cfg["target_modules"] == ["q_proj", "v_proj"] and cfg["peft_type"] == "LORA", cfg
+        ad = {k: np.array(a) for k, a, _ in model_io.iter_safetensors(os.path.join(ckpt, "adapter_model.safetensors"))}
+        assert len(ad) == 8 and all(np.isfinite(v).all() for v in ad.values()), sorted(ad)
+        assert any(np.abs(v).max() > 0 for k, v in ad.items() if "lora_B" in k), "B adapters must have moved"
+        logs = [json.loads(l) for l in open(os.path.join(tmp, "result", "watch", "trainer_log.jsonl"))]
+        assert len(logs) == 2 and logs[0]["current_steps"] == 10 and logs[0]["total_steps"] == 24, logs
+        assert logs[1]["loss"] < logs[0]["loss"], f"loss did not go down: {logs}"
+        ev = [json.loads(l) for l in open(os.path.join(tmp, "result", "watch", "eval_log.jsonl"))]
+        assert abs(ev[0]["eval_perplexity"] - math.exp(ev[0]["eval_loss"])) < 1e-9, ev
+        return {"first_log_loss": logs[0]["loss"], "last_log_loss": logs[1]["loss"], "eval_loss": ev[0]["eval_loss"], "ckpt": os.path.basename(ckpt)}
+    finally:
+        os.environ.pop("DTX_CHECKPOINT_PATH_FILE", None)
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 ALL = {
     "gemm_nt": check_gemm_nt, "gemm_nt_bn64": lambda: check_gemm_nt(N=64, block_n=64),
     "gemm_nt_bn128": lambda: check_gemm_nt(N=384, block_n=128), "gemm_nn": check_gemm_nn,
@@ -460,7 +551,8 @@ ALL = {
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
     "attn_bwd": check_attn_bwd, "attn_bwd_long": lambda: check_attn_bwd(B=1, S=1024, H=1),
     "trainer_tiny": check_trainer_tiny, "trainer_deterministic": check_trainer_deterministic,
-    "trainer_grad_accum": check_trainer_grad_accum,
+    "trainer_grad_accum": check_trainer_grad_accum, "trainer_100_steps": check_trainer_100_steps,
+    "worker_end_to_end": check_worker_end_to_end,
 }
 
 if __name__ == "__main__":
