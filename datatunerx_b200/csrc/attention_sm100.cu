@@ -44,6 +44,7 @@ struct AttnKParams {
   bf16* out;
   const float* delta;
   bf16* dqkv;
+  const float2* rope_cs;  // [S][64] (cos, sin) or null
 };
 
 // issue `n16` UMMAs (K=16 each) walking both operands.  a/b step = byte advance per k16.
@@ -424,20 +425,36 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     mbar_wait(bar_o, (n - 1) & 1);
     tc_fence_after();
-    bf16* drow = p.dqkv + static_cast<size_t>(row_base + qrow) * (3 * p.H * HD) + colQ + half * 64;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(t_lane + T_DQ + half * 64 + c * 32, v);
+    // each thread stores columns [32*half, +32) and [64 + 32*half, +32): the rotary pair (i, i+64) stays in one thread
+    bf16* drow = p.dqkv + static_cast<size_t>(row_base + qrow) * (3 * p.H * HD) + colQ;
+    {
+      uint32_t lo[32], hi[32];
+      tmem_ld32(t_lane + T_DQ + half * 32, lo);
+      tmem_ld32(t_lane + T_DQ + 64 + half * 32, hi);
       tmem_ld_wait();
+      if (p.rope_cs) {  // dq of the pre-rotary projection: apply R^T (inverse rotation)
+        const float2* cs = p.rope_cs + static_cast<size_t>(qrow) * 64 + half * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 t = __ldg(cs + j);
+          const float x0 = __uint_as_float(lo[j]), x1 = __uint_as_float(hi[j]);
+          lo[j] = __float_as_uint(x0 * t.x + x1 * t.y);
+          hi[j] = __float_as_uint(x1 * t.x - x0 * t.y);
+        }
+      }
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
-        u.y = pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
-        u.z = pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5]));
-        u.w = pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7]));
-        reinterpret_cast<uint4*>(drow)[c * 4 + c8] = u;
+        uint4 u, w;
+        u.x = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 0]), __uint_as_float(lo[c8 * 8 + 1]));
+        u.y = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 2]), __uint_as_float(lo[c8 * 8 + 3]));
+        u.z = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 4]), __uint_as_float(lo[c8 * 8 + 5]));
+        u.w = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 6]), __uint_as_float(lo[c8 * 8 + 7]));
+        w.x = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 0]), __uint_as_float(hi[c8 * 8 + 1]));
+        w.y = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 2]), __uint_as_float(hi[c8 * 8 + 3]));
+        w.z = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 4]), __uint_as_float(hi[c8 * 8 + 5]));
+        w.w = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 6]), __uint_as_float(hi[c8 * 8 + 7]));
+        reinterpret_cast<uint4*>(drow + half * 32)[c8] = u;
+        reinterpret_cast<uint4*>(drow + 64 + half * 32)[c8] = w;
       }
     }
   }
@@ -614,19 +631,36 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     // warps 0-3 write dV, warps 4-7 write dK (each thread one full 128-wide row)
     bf16* drow = p.dqkv + static_cast<size_t>(row_base + kvrow) * (3 * p.H * HD) + (half ? colK : colV);
     const uint32_t tcol = half ? T_DK : T_DV;
+    const bool rot = half && p.rope_cs;  // dK is the gradient of the post-rotary key: rotate back (R^T)
+    const float2* cs = p.rope_cs + static_cast<size_t>(kvrow) * 64;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld32(t_lane + tcol + c * 32, v);
+    for (int c = 0; c < 2; ++c) {
+      uint32_t lo[32], hi[32];
+      tmem_ld32(t_lane + tcol + c * 32, lo);
+      tmem_ld32(t_lane + tcol + 64 + c * 32, hi);
       tmem_ld_wait();
+      if (rot) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 t = __ldg(cs + c * 32 + j);
+          const float x0 = __uint_as_float(lo[j]), x1 = __uint_as_float(hi[j]);
+          lo[j] = __float_as_uint(x0 * t.x + x1 * t.y);
+          hi[j] = __float_as_uint(x1 * t.x - x0 * t.y);
+        }
+      }
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
-        u.y = pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
-        u.z = pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5]));
-        u.w = pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7]));
-        reinterpret_cast<uint4*>(drow)[c * 4 + c8] = u;
+        uint4 u, w;
+        u.x = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 0]), __uint_as_float(lo[c8 * 8 + 1]));
+        u.y = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 2]), __uint_as_float(lo[c8 * 8 + 3]));
+        u.z = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 4]), __uint_as_float(lo[c8 * 8 + 5]));
+        u.w = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 6]), __uint_as_float(lo[c8 * 8 + 7]));
+        w.x = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 0]), __uint_as_float(hi[c8 * 8 + 1]));
+        w.y = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 2]), __uint_as_float(hi[c8 * 8 + 3]));
+        w.z = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 4]), __uint_as_float(hi[c8 * 8 + 5]));
+        w.w = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 6]), __uint_as_float(hi[c8 * 8 + 7]));
+        reinterpret_cast<uint4*>(drow + c * 32)[c8] = u;
+        reinterpret_cast<uint4*>(drow + 64 + c * 32)[c8] = w;
       }
     }
   }
@@ -691,6 +725,7 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   p.out = a.out;
   p.delta = a.delta;
   p.dqkv = a.dqkv;
+  p.rope_cs = a.rope_cs;
   {
     const long long warps = static_cast<long long>(a.B) * a.S * a.H;
     const int block = 256;

@@ -33,6 +33,10 @@ int32_t dtx_set_option(const char* name, int32_t value) {
     gemm_set_pair_kernel(value);
     return DTX_OK;
   }
+  if (strcmp(name, "fused_epilogues") == 0) {
+    trainer_set_fused_epilogues(value);
+    return DTX_OK;
+  }
   return DTX_ERR_INVALID;
 }
 
@@ -67,10 +71,10 @@ int32_t dtx_rope_qk(void* qkv, const void* cs, int32_t B, int32_t Sq, int32_t H,
   return rc(rope_qk_inplace_table(static_cast<bf16*>(qkv), static_cast<const float2*>(cs), B, Sq, H, D, inverse, S(stream)));
 }
 int32_t dtx_swiglu_fwd(const void* gu, void* act, int32_t M, int32_t F, void* stream) {
-  return rc(swiglu_fwd(static_cast<const bf16*>(gu), static_cast<bf16*>(act), M, F, S(stream)));
+  return rc(swiglu_fwd(static_cast<const bf16*>(gu), static_cast<bf16*>(act), M, F, 0, S(stream)));
 }
 int32_t dtx_swiglu_bwd(const void* dact, const void* gu, void* dgu, int32_t M, int32_t F, void* stream) {
-  return rc(swiglu_bwd(static_cast<const bf16*>(dact), static_cast<const bf16*>(gu), static_cast<bf16*>(dgu), M, F, S(stream)));
+  return rc(swiglu_bwd(static_cast<const bf16*>(dact), static_cast<const bf16*>(gu), static_cast<bf16*>(dgu), M, F, 0, S(stream)));
 }
 int32_t dtx_cross_entropy(const void* logits, int64_t ldl, const void* labels, void* shifted, void* n_valid, void* row_loss,
                           void* dlogits, int64_t ldd, void* loss_out, int32_t B, int32_t Sq, int32_t V, void* stream) {

@@ -213,15 +213,18 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, const float2* __restrict__ c
 // ------------------------------------------------------------------------------------------
 // SwiGLU elementwise (HF LlamaMLP: down(silu(gate(x)) * up(x))) on packed [gate | up].
 // ------------------------------------------------------------------------------------------
-__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int M, int F) {
+__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int M, int F, int il) {
   const int vecF = F >> 3;
   const long long total = static_cast<long long>(M) * vecF;
   for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
        t += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long m = t / vecF;
     const int v = static_cast<int>(t % vecF);
-    const uint4* g = reinterpret_cast<const uint4*>(gu + m * 2LL * F) + v;
-    const uint4* u = reinterpret_cast<const uint4*>(gu + m * 2LL * F + F) + v;
+    // il: GU-interleaved layout, feature f -> gate at (f/128)*256 + f%128, up 128 further; else [gate F | up F]
+    const int f = v << 3;
+    const long long gpos = il ? (static_cast<long long>(f >> 7) * 256 + (f & 127)) : f;
+    const uint4* g = reinterpret_cast<const uint4*>(gu + m * 2LL * F + gpos);
+    const uint4* u = reinterpret_cast<const uint4*>(gu + m * 2LL * F + gpos + (il ? 128 : F));
     float fg[8], fu[8];
     bf16x8_to_f32(ldg_stream(g), fg);
     bf16x8_to_f32(ldg_stream(u), fu);
@@ -234,7 +237,7 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
   }
 }
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __restrict__ gu, bf16* __restrict__ dgu,
-                                  int M, int F) {
+                                  int M, int F, int il) {
   const int vecF = F >> 3;
   const long long total = static_cast<long long>(M) * vecF;
   for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
@@ -242,8 +245,11 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
     const long long m = t / vecF;
     const int v = static_cast<int>(t % vecF);
     float fg[8], fu[8], fd[8], og[8], ou[8];
-    bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(gu + m * 2LL * F) + v), fg);
-    bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(gu + m * 2LL * F + F) + v), fu);
+    const int f = v << 3;
+    const long long gpos = il ? (static_cast<long long>(f >> 7) * 256 + (f & 127)) : f;
+    const long long upos = gpos + (il ? 128 : F);
+    bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(gu + m * 2LL * F + gpos)), fg);
+    bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(gu + m * 2LL * F + upos)), fu);
     bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(dact + m * static_cast<long long>(F)) + v), fd);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -252,8 +258,8 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
       ou[j] = fd[j] * silu;
       og[j] = fd[j] * fu[j] * (s + silu * (1.f - s));  // d/dg [g*sigmoid(g)] = s + g*s*(1-s)
     }
-    reinterpret_cast<uint4*>(dgu + m * 2LL * F)[v] = f32_to_bf16x8(og);
-    reinterpret_cast<uint4*>(dgu + m * 2LL * F + F)[v] = f32_to_bf16x8(ou);
+    *reinterpret_cast<uint4*>(dgu + m * 2LL * F + gpos) = f32_to_bf16x8(og);
+    *reinterpret_cast<uint4*>(dgu + m * 2LL * F + upos) = f32_to_bf16x8(ou);
   }
 }
 
@@ -320,7 +326,8 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logit
   for (int o = 16; o > 0; o >>= 1) {
     const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sm, o);
     const float nm = fmaxf(mx, om);
-    sm = sm * __expf(mx - nm) + os * __expf(om - nm);
+    // a lane with no elements (V < 4 * blockDim) holds (-inf, 0): (-inf) - (-inf) would be NaN
+    sm = (mx == -INFINITY ? 0.f : sm * __expf(mx - nm)) + (om == -INFINITY ? 0.f : os * __expf(om - nm));
     mx = nm;
   }
   if ((threadIdx.x & 31) == 0) { shm[threadIdx.x >> 5] = mx; shs[threadIdx.x >> 5] = sm; }
@@ -329,7 +336,7 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logit
     float M0 = shm[0], S0 = shs[0];
     for (int i = 1; i < (blockDim.x >> 5); ++i) {
       const float nm = fmaxf(M0, shm[i]);
-      S0 = S0 * __expf(M0 - nm) + shs[i] * __expf(shm[i] - nm);
+      S0 = (M0 == -INFINITY ? 0.f : S0 * __expf(M0 - nm)) + (shm[i] == -INFINITY ? 0.f : shs[i] * __expf(shm[i] - nm));
       M0 = nm;
     }
     s_max = M0;
@@ -535,14 +542,14 @@ cudaError_t rope_qk_inplace_table(bf16* qkv, const float2* cs, int B, int S, int
   return cudaGetLastError();
 }
 
-cudaError_t swiglu_fwd(const bf16* gu, bf16* act, int M, int F, cudaStream_t s) {
-  if (F % 8) return cudaErrorInvalidValue;
-  swiglu_fwd_kernel<<<grid_for(static_cast<long long>(M) * (F / 8), 256), 256, 0, s>>>(gu, act, M, F);
+cudaError_t swiglu_fwd(const bf16* gu, bf16* act, int M, int F, int interleaved, cudaStream_t s) {
+  if (F % 8 || (interleaved && F % 128)) return cudaErrorInvalidValue;
+  swiglu_fwd_kernel<<<grid_for(static_cast<long long>(M) * (F / 8), 256), 256, 0, s>>>(gu, act, M, F, interleaved);
   return cudaGetLastError();
 }
-cudaError_t swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int M, int F, cudaStream_t s) {
-  if (F % 8) return cudaErrorInvalidValue;
-  swiglu_bwd_kernel<<<grid_for(static_cast<long long>(M) * (F / 8), 256), 256, 0, s>>>(dact, gu, dgu, M, F);
+cudaError_t swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int M, int F, int interleaved, cudaStream_t s) {
+  if (F % 8 || (interleaved && F % 128)) return cudaErrorInvalidValue;
+  swiglu_bwd_kernel<<<grid_for(static_cast<long long>(M) * (F / 8), 256), 256, 0, s>>>(dact, gu, dgu, M, F, interleaved);
   return cudaGetLastError();
 }
 

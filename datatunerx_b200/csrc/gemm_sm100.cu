@@ -36,6 +36,10 @@ struct GemmKParams {
   long long ldc;
   const bf16* R;
   long long ldr;
+  void* aux;
+  long long ld_aux;
+  const float2* rope_cs;
+  int rope_S, rope_cols, rope_inverse;
 };
 
 template <int BN>
@@ -60,7 +64,9 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmKParams& p, int r
       for (int j = 0; j < 8; ++j)
         reinterpret_cast<uint4*>(crow)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     } else {
-      for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __uint_as_float(v[j]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)  // statically indexed (a dynamic index would push the whole fragment to local memory)
+        if (col0 + j < p.N) crow[j] = __uint_as_float(v[j]);
     }
   } else {
     bf16* crow = reinterpret_cast<bf16*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
@@ -78,7 +84,9 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmKParams& p, int r
           f[8 * j + 4] += cc.x; f[8 * j + 5] += cc.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
         }
       } else {
-        for (int j = 0; j < 32 && col0 + j < p.N; ++j) f[j] += __bfloat162float(rrow[j]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) f[j] += __bfloat162float(rrow[j]);
       }
     }
     if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
@@ -92,7 +100,9 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmKParams& p, int r
         reinterpret_cast<uint4*>(crow)[j] = o;
       }
     } else {
-      for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __float2bfloat16_rn(f[j]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) crow[j] = __float2bfloat16_rn(f[j]);
     }
   }
 }
@@ -413,15 +423,121 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256);
+      if (EPI == EPI_ROPE) {
+        // two heads per tile (chunks 0-3 / 4-7); rotary pairs column i with i+64: chunk c with chunk c+2
+        const bool rot = n0 < p.rope_cols;
+        const float2* cs = p.rope_cs + static_cast<long long>(row_ok ? (row % p.rope_S) : 0) * 64;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;
-        uint32_t v[32];
-        tmem_ld32(t_row + c * 32, v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        epilogue_store_chunk<EPI>(p, row, col0, 0, v);
+        for (int hc = 0; hc < 4; ++hc) {
+          const int c = (hc >> 1) * 4 + (hc & 1);
+          if (n0 + c * 32 >= p.N) break;
+          uint32_t lo[32], hi[32];
+          tmem_ld32(t_row + c * 32, lo);
+          tmem_ld32(t_row + (c + 2) * 32, hi);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          if (rot) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float2 t = __ldg(cs + (hc & 1) * 32 + j);
+              const float sn = p.rope_inverse ? -t.y : t.y;
+              const float x0 = __uint_as_float(lo[j]), x1 = __uint_as_float(hi[j]);
+              lo[j] = __float_as_uint(x0 * t.x - x1 * sn);
+              hi[j] = __float_as_uint(x1 * t.x + x0 * sn);
+            }
+          }
+          epilogue_store_chunk<EPI_BF16>(p, row, n0 + c * 32, 0, lo);
+          epilogue_store_chunk<EPI_BF16>(p, row, n0 + (c + 2) * 32, 0, hi);
+        }
+      } else if (EPI == EPI_SWIGLU_FWD) {
+        // tile = [gate 128 | up 128] of the same 128 features: chunk c (gate) pairs with chunk c+4 (up)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t g[32], u[32];
+          tmem_ld32(t_row + c * 32, g);
+          tmem_ld32(t_row + (c + 4) * 32, u);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          epilogue_store_chunk<EPI_BF16>(p, row, n0 + c * 32, 0, g);
+          epilogue_store_chunk<EPI_BF16>(p, row, n0 + (c + 4) * 32, 0, u);
+          bf16* arow = reinterpret_cast<bf16*>(p.aux) + static_cast<long long>(row) * p.ld_aux + (n0 >> 1) + c * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              // match the unfused path bit for bit: gate/up are rounded to bf16 before the activation
+              const float gg = __bfloat162float(__float2bfloat16_rn(__uint_as_float(g[8 * j + e])));
+              const float uu = __bfloat162float(__float2bfloat16_rn(__uint_as_float(u[8 * j + e])));
+              a[e] = gg * (1.f / (1.f + __expf(-gg))) * uu;
+            }
+            uint4 o;
+            o.x = pack_bf16x2(a[0], a[1]); o.y = pack_bf16x2(a[2], a[3]);
+            o.z = pack_bf16x2(a[4], a[5]); o.w = pack_bf16x2(a[6], a[7]);
+            reinterpret_cast<uint4*>(arow)[j] = o;
+          }
+        }
+      } else if (EPI == EPI_SWIGLU_BWD) {
+        // acc = d(act) for features n0 + 32c + j; gate/up of feature f live at (f/128)*256 + f%128 (+128) of gu / d(gu).
+        // The gate/up fragments of chunk c+1 are requested before chunk c is processed: the epilogue is latency-bound
+        // on these HBM reads otherwise (r01: +420 us on the 1.0 ms GEMM without the prefetch).
+        const bf16* gbase = reinterpret_cast<const bf16*>(p.aux) + static_cast<long long>(row_ok ? row : 0) * p.ld_aux;
+        bf16* dbase = reinterpret_cast<bf16*>(p.C) + static_cast<long long>(row_ok ? row : 0) * p.ldc;
+        auto gcol_of = [&](int c) { const int f0 = n0 + c * 32; return static_cast<long long>(f0 >> 7) * 256 + (f0 & 127); };
+        uint4 gq[4], uq[4], gn[4], un[4];
+        if (row_ok && n0 < p.N) {
+          const bf16* g0 = gbase + gcol_of(0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { gq[j] = reinterpret_cast<const uint4*>(g0)[j]; uq[j] = reinterpret_cast<const uint4*>(g0 + 128)[j]; }
+        }
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          const int f0 = n0 + c * 32;
+          if (f0 >= p.N) break;
+          const bool has_next = (c + 1 < 8) && (f0 + 32 < p.N);
+          if (row_ok && has_next) {
+            const bf16* g1 = gbase + gcol_of(c + 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { gn[j] = reinterpret_cast<const uint4*>(g1)[j]; un[j] = reinterpret_cast<const uint4*>(g1 + 128)[j]; }
+          }
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            bf16* drow = dbase + gcol_of(c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t gw[4] = {gq[j].x, gq[j].y, gq[j].z, gq[j].w}, uw[4] = {uq[j].x, uq[j].y, uq[j].z, uq[j].w};
+              uint32_t og[4], ou[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 g2 = unpack_bf16x2(gw[e]), u2 = unpack_bf16x2(uw[e]);
+                // d(act) is rounded to bf16 first, exactly like the unfused path that stores it
+                const float d0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[8 * j + 2 * e])));
+                const float d1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[8 * j + 2 * e + 1])));
+                const float s0 = 1.f / (1.f + __expf(-g2.x)), s1 = 1.f / (1.f + __expf(-g2.y));
+                const float si0 = g2.x * s0, si1 = g2.y * s1;
+                og[e] = pack_bf16x2(d0 * u2.x * (s0 + si0 * (1.f - s0)), d1 * u2.y * (s1 + si1 * (1.f - s1)));
+                ou[e] = pack_bf16x2(d0 * si0, d1 * si1);
+              }
+              reinterpret_cast<uint4*>(drow)[j] = make_uint4(og[0], og[1], og[2], og[3]);
+              reinterpret_cast<uint4*>(drow + 128)[j] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { gq[j] = gn[j]; uq[j] = un[j]; }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          epilogue_store_chunk<EPI>(p, row, col0, 0, v);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -533,6 +649,10 @@ cudaError_t launch(const GemmArgs& a, cudaStream_t s) {
   p.ldc = a.ldc;
   p.R = a.R;
   p.ldr = a.ldr;
+  p.aux = nullptr;
+  p.ld_aux = 0;
+  p.rope_cs = nullptr;
+  p.rope_S = p.rope_cols = p.rope_inverse = 0;
   int total = p.m_tiles * p.n_tiles * p.split_k;
   int grid = total < gemm_num_sms() ? total : gemm_num_sms();
   if (grid <= 0) return cudaSuccess;
@@ -586,6 +706,12 @@ cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
   p.ldc = a.ldc;
   p.R = a.R;
   p.ldr = a.ldr;
+  p.aux = a.aux;
+  p.ld_aux = a.ld_aux;
+  p.rope_cs = a.rope_cs;
+  p.rope_S = a.rope_S;
+  p.rope_cols = a.rope_cols;
+  p.rope_inverse = a.rope_inverse;
   const int total = p.m_tiles * p.n_tiles;
   int pairs = gemm_num_sms() / 2;
   if (pairs > total) pairs = total;
@@ -600,6 +726,9 @@ cudaError_t launch2_epi(const GemmArgs& a, cudaStream_t s) {
     case EPI_BF16: return launch2<B_MN, EPI_BF16>(a, s);
     case EPI_F32: return launch2<B_MN, EPI_F32>(a, s);
     case EPI_BF16_ADD: return launch2<B_MN, EPI_BF16_ADD>(a, s);
+    case EPI_ROPE: return launch2<B_MN, EPI_ROPE>(a, s);
+    case EPI_SWIGLU_FWD: return launch2<B_MN, EPI_SWIGLU_FWD>(a, s);
+    case EPI_SWIGLU_BWD: return launch2<B_MN, EPI_SWIGLU_BWD>(a, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -620,6 +749,13 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaErrorInvalidValue;
   if (a.split_k > 1 && a.epilogue != EPI_F32) return cudaErrorInvalidValue;
   if (a.epilogue == EPI_BF16_ADD && a.R == nullptr) return cudaErrorInvalidValue;
+  if (a.epilogue >= EPI_ROPE) {  // fused epilogues exist only in the CTA-pair kernel and need whole 256-column tiles
+    if (a.a_mn_major || a.split_k > 1 || a.M <= 128 || !g_use_pair_kernel) return cudaErrorInvalidValue;
+    if (a.epilogue == EPI_ROPE && (!a.rope_cs || a.rope_S <= 0 || (a.rope_cols & 255) || (a.N & 255))) return cudaErrorInvalidValue;
+    if (a.epilogue == EPI_SWIGLU_FWD && (!a.aux || (a.N & 255))) return cudaErrorInvalidValue;
+    if (a.epilogue == EPI_SWIGLU_BWD && (!a.aux || (a.N & 127))) return cudaErrorInvalidValue;
+    return a.b_mn_major ? launch2_epi<true>(a, s) : launch2_epi<false>(a, s);
+  }
   // TMA needs 16-byte aligned bases and row strides
   if ((a.lda & 7) || (a.ldb & 7) || (reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15))
     return cudaErrorInvalidValue;

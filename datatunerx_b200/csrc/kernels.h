@@ -12,6 +12,10 @@ enum GemmEpilogue {
   EPI_BF16 = 0,      // C[bf16] = acc
   EPI_F32 = 1,       // C[f32]  = acc            (logits, split-K partials)
   EPI_BF16_ADD = 2,  // C[bf16] = acc + R[bf16]  (residual stream update)
+  // fused epilogues of the CTA-pair kernel (256-wide N tiles; M > 128):
+  EPI_ROPE = 3,        // C[bf16] = rotary(acc) on columns < rope_cols (head_dim 128, half-split), plain store beyond
+  EPI_SWIGLU_FWD = 4,  // N tiles hold [gate 128 | up 128] (GU-interleaved layout): C[bf16] = acc, aux[M, N/2] = silu(gate)*up
+  EPI_SWIGLU_BWD = 5,  // acc = d(act) [M, F]; reads gu = aux_in[M, 2F] (interleaved), writes d(gu) to C[M, 2F]; d(act) never stored
 };
 
 // C[M,N] = A[M,K] * B[N,K]^T (+ A2[M,K2] * B2[N,K2]^T), bf16 operands, fp32 accumulation in TMEM.
@@ -29,6 +33,8 @@ struct GemmArgs {
   int K2 = 0;
   void* C = nullptr; int64_t ldc = 0;
   const bf16* R = nullptr; int64_t ldr = 0;
+  void* aux = nullptr; int64_t ld_aux = 0;             // EPI_SWIGLU_FWD: act out; EPI_SWIGLU_BWD: gu in (ld = 2F)
+  const float2* rope_cs = nullptr; int rope_S = 0, rope_cols = 0, rope_inverse = 0;  // EPI_ROPE
   int M = 0, N = 0, K = 0;
   int epilogue = EPI_BF16;
   int split_k = 1;  // >1 requires EPI_F32; C is [split_k][M][ldc] partial sums
@@ -38,6 +44,8 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s);
 int gemm_num_sms();
 // 1 (default): wide GEMMs use the CTA-pair (cta_group::2) kernel; 0: single-CTA kernel everywhere (A/B measurements)
 void gemm_set_pair_kernel(int on);
+// 1 (default): RoPE / SwiGLU run inside GEMM and attention epilogues; 0: separate HBM-bound kernels (A/B, tiny M)
+void trainer_set_fused_epilogues(int on);
 
 // ---------------------------------------------------------------------------------------------
 // flash attention (causal, head_dim 128), packed qkv layout [B*S, 3*H*128] (q | k | v per token)
@@ -49,6 +57,7 @@ struct AttnArgs {
   int B = 0, S = 0, H = 0;
   float scale = 0.f;
   // backward
+  const float2* rope_cs = nullptr;  // backward only: if set, dq and dk get the inverse rotary applied before the store
   const bf16* dout = nullptr;  // [B*S, H*D]
   bf16* dqkv = nullptr;        // [B*S, 3*H*D]
   float* delta = nullptr;      // [B, H, S] scratch: rowsum(dO * O)
@@ -68,10 +77,11 @@ cudaError_t rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const floa
 // half-split rotary embedding applied in place to the q and k thirds of packed qkv. inverse=1 applies R^T (backward)
 // cs = [S][D/2] float2(cos, sin) table built on the host in double precision
 cudaError_t rope_qk_inplace_table(bf16* qkv, const float2* cs, int B, int S, int H, int D, int inverse, cudaStream_t s);
-// gu = [gate | up] packed [M, 2F]; act[M,F] = silu(gate) * up
-cudaError_t swiglu_fwd(const bf16* gu, bf16* act, int M, int F, cudaStream_t s);
+// gu [M, 2F]: [gate F | up F] (interleaved = 0) or the GU-interleaved layout the trainer uses (interleaved = 1: feature f
+// has its gate at column (f/128)*256 + f%128 and its up 128 columns further); act[M,F] = silu(gate) * up
+cudaError_t swiglu_fwd(const bf16* gu, bf16* act, int M, int F, int interleaved, cudaStream_t s);
 // dgu[M,2F] from dact[M,F] and saved gu
-cudaError_t swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int M, int F, cudaStream_t s);
+cudaError_t swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int M, int F, int interleaved, cudaStream_t s);
 // labels_shift[b,t] = labels[b,t+1] (last = -100); n_valid counted into *n_valid (int32)
 cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_valid, int B, int S, cudaStream_t s);
 // softmax cross-entropy over fp32 logits [M,V]; row_loss[M] (0 for ignored rows); dlogits bf16 = (p - onehot)/n_valid

@@ -68,6 +68,7 @@ constexpr int kNcclFloat32 = 7;
 constexpr int kNcclSum = 0;
 
 thread_local std::string g_error;
+int g_fused_epilogues = 1;  // RoPE / SwiGLU fused into the GEMM and attention epilogues (needs M > 128: CTA-pair GEMM)
 
 // ------------------------------------------------------------------------------------------------
 // LoRA-specific small kernels
@@ -121,6 +122,7 @@ __global__ void lora_shadow_kernel(ShadowArgs a) {
 }
 
 struct Layer {
+  // wgu: [2F, d] in the GU-interleaved layout (128 gate rows | 128 up rows per 128 features)
   bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr, *norm1 = nullptr, *norm2 = nullptr;
   bf16 *a_cat = nullptr, *b_ext = nullptr;                                               // shadows
   bf16 *h1 = nullptr, *t = nullptr, *qkv = nullptr, *attn = nullptr, *x_mid = nullptr, *gu = nullptr;  // saved
@@ -128,6 +130,7 @@ struct Layer {
 };
 
 }  // namespace
+void trainer_set_fused_epilogues(int on) { g_fused_epilogues = on; }
 }  // namespace dtx
 
 using namespace dtx;
@@ -304,6 +307,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   const int B = tc.micro_batch, S = tc.seq_len;
   cudaStream_t s = t->stream;
   const float att_scale = 1.0f / sqrtf(static_cast<float>(D));
+  const bool fused = g_fused_epilogues && M > 128 && (d % 128 == 0);
 
   CK(embedding_fwd(t->d_ids, t->embed, t->xs[0], M, d, V, s), 1);
   for (int l = 0; l < L; ++l) {
@@ -320,9 +324,12 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       g.A = y.h1; g.lda = d; g.B = y.wqkv; g.ldb = d;
       g.A2 = y.t; g.lda2 = RP; g.B2 = y.b_ext; g.ldb2 = RP; g.K2 = RP;
       g.C = y.qkv; g.ldc = 3 * d; g.M = M; g.N = 3 * d; g.K = d; g.epilogue = EPI_BF16;
+      if (fused) {  // rotary embedding of q and k applied to the fp32 accumulator in the epilogue
+        g.epilogue = EPI_ROPE; g.rope_cs = t->rope_cs; g.rope_S = S; g.rope_cols = 2 * d;
+      }
       CK(gemm_bf16(g, s), 1);
     }
-    CK(rope_qk_inplace_table(y.qkv, t->rope_cs, B, S, H, D, 0, s), 1);
+    if (!fused) CK(rope_qk_inplace_table(y.qkv, t->rope_cs, B, S, H, D, 0, s), 1);
     {
       AttnArgs a;
       a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.scale = att_scale;
@@ -339,9 +346,12 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       GemmArgs g;
       g.A = t->h2; g.lda = d; g.B = y.wgu; g.ldb = d; g.C = y.gu; g.ldc = 2 * F;
       g.M = M; g.N = 2 * F; g.K = d; g.epilogue = EPI_BF16;
+      if (fused) {  // silu(gate) * up computed from the accumulator tile ([gate 128 | up 128] interleaved layout)
+        g.epilogue = EPI_SWIGLU_FWD; g.aux = t->act; g.ld_aux = F;
+      }
       CK(gemm_bf16(g, s), 1);
     }
-    CK(swiglu_fwd(y.gu, t->act, M, F, s), 1);
+    if (!fused) CK(swiglu_fwd(y.gu, t->act, M, F, 1, s), 1);
     {  // x_next = x_mid + act * Wdown^T
       GemmArgs g;
       g.A = t->act; g.lda = F; g.B = y.wdown; g.ldb = F; g.C = t->xs[l + 1]; g.ldc = d; g.R = y.x_mid; g.ldr = d;
@@ -373,13 +383,16 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   const int accumulate = t->micro_idx > 0 ? 1 : 0;
   for (int l = L - 1; l >= 0; --l) {
     Layer& y = t->layers[l];
-    {  // dact = dx * Wdown
+    {  // dact = dx * Wdown ; fused: d[gate|up] straight from the accumulator, dact never touches HBM
       GemmArgs g;
       g.A = cur; g.lda = d; g.B = y.wdown; g.ldb = F; g.b_mn_major = 1; g.C = t->dact; g.ldc = F;
       g.M = M; g.N = F; g.K = d; g.epilogue = EPI_BF16;
+      if (fused) {
+        g.epilogue = EPI_SWIGLU_BWD; g.C = t->dgu; g.ldc = 2 * F; g.aux = y.gu; g.ld_aux = 2 * F;
+      }
       CK(gemm_bf16(g, s), 1);
     }
-    CK(swiglu_bwd(t->dact, y.gu, t->dgu, M, F, s), 1);
+    if (!fused) CK(swiglu_bwd(t->dact, y.gu, t->dgu, M, F, 1, s), 1);
     {  // dh2 = [dgate | dup] * [Wg ; Wu]
       GemmArgs g;
       g.A = t->dgu; g.lda = 2 * F; g.B = y.wgu; g.ldb = d; g.b_mn_major = 1; g.C = t->dh; g.ldc = d;
@@ -397,6 +410,9 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       AttnArgs a;
       a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.scale = att_scale;
       a.dout = t->dattn; a.dqkv = t->dqkv; a.delta = t->delta;
+      // the kernels can apply the inverse rotary in their store epilogues (a.rope_cs), but the per-row table reads
+      // at the very end of each CTA are exposed latency: measured +270 us/layer vs 47 us for the separate kernel
+      a.rope_cs = nullptr;
       CK(attn_bwd(a, s), 3);
     }
     CK(rope_qk_inplace_table(t->dqkv, t->rope_cs, B, S, H, D, 1, s), 1);
@@ -606,7 +622,8 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
   if (mc->head_dim != 128) return bad("only head_dim 128 is implemented (Llama-2 / Mistral family)");
   if (mc->n_kv_heads != mc->n_heads) { g_error = "grouped-query attention (n_kv_heads != n_heads) is not implemented yet"; return DTX_ERR_UNSUPPORTED; }
   if (mc->n_heads * mc->head_dim != mc->hidden) return bad("hidden != n_heads * head_dim");
-  if (mc->hidden % 64 || mc->ffn % 8 || mc->vocab % 8) return bad("hidden must be a multiple of 64, ffn and vocab multiples of 8");
+  if (mc->hidden % 64 || mc->ffn % 128 || mc->vocab % 8)
+    return bad("hidden must be a multiple of 64, ffn a multiple of 128 (GU-interleaved layout), vocab a multiple of 8");
   if (tc->seq_len % 128 || tc->seq_len <= 0 || tc->micro_batch <= 0) return bad("seq_len must be a positive multiple of 128");
   if (tc->seq_len > mc->max_seq) return bad("seq_len exceeds max_seq");
   if (tc->lora_r <= 0 || tc->lora_r % 8) return bad("lora_r must be a positive multiple of 8");
@@ -755,11 +772,24 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
     cudaStreamSynchronize(t->stream);
     return DTX_OK;
   }
+  // gate/up rows go to the GU-interleaved layout: 128 gate rows, then the 128 up rows of the same features, ...
+  for (int which = 0; which < 2; ++which) {
+    if (!strstr(rest, which ? "mlp.up_proj.weight" : "mlp.gate_proj.weight")) continue;
+    if (!expect(F, d)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)F, (long long)d);
+    std::vector<bf16> tmp;
+    to_bf16_host(host, dtype, static_cast<size_t>(F) * d, tmp);
+    for (int64_t b = 0; b < F / 128; ++b) {
+      cudaError_t e = cudaMemcpy(y.wgu + (b * 256 + which * 128) * d, tmp.data() + b * 128 * d, 128 * d * sizeof(bf16),
+                                 cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "upload %s: %s", name, cudaGetErrorString(e));
+    }
+    t->have_weights = true;
+    return DTX_OK;
+  }
   struct Slot { const char* key; bf16* dst; int64_t r, c; };
   const Slot slots[] = {
       {"self_attn.q_proj.weight", y.wqkv, d, d},           {"self_attn.k_proj.weight", y.wqkv + d * d, d, d},
       {"self_attn.v_proj.weight", y.wqkv + 2 * d * d, d, d}, {"self_attn.o_proj.weight", y.wo, d, d},
-      {"mlp.gate_proj.weight", y.wgu, F, d},               {"mlp.up_proj.weight", y.wgu + F * d, F, d},
       {"mlp.down_proj.weight", y.wdown, d, F},             {"input_layernorm.weight", y.norm1, d, 1},
       {"post_attention_layernorm.weight", y.norm2, d, 1},
   };

@@ -30,7 +30,7 @@ def test_attention(name):
     _run(name)
 
 
-@pytest.mark.parametrize("name", ["trainer_tiny", "trainer_deterministic", "trainer_grad_accum", "trainer_100_steps",
+@pytest.mark.parametrize("name", ["trainer_tiny", "trainer_unfused", "trainer_deterministic", "trainer_grad_accum", "trainer_100_steps",
                                   "worker_end_to_end"])
 def test_training_step(name):
     _run(name)
