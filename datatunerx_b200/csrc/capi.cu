@@ -33,6 +33,10 @@ int32_t dtx_set_option(const char* name, int32_t value) {
     gemm_set_pair_kernel(value);
     return DTX_OK;
   }
+  if (strcmp(name, "gemm_group_m") == 0) {
+    gemm_set_pair_group_m(value);
+    return DTX_OK;
+  }
   if (strcmp(name, "fused_epilogues") == 0) {
     trainer_set_fused_epilogues(value);
     return DTX_OK;

@@ -36,6 +36,7 @@ struct GemmKParams {
   long long ldc;
   const bf16* R;
   long long ldr;
+  int group_m;  // pair kernel: 256-row tiles per rasterisation group
   void* aux;
   long long ld_aux;
   const float2* rope_cs;
@@ -291,7 +292,7 @@ constexpr int G2_B_BYTES = 128 * BK * 2;
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_TMEM_COLS = 512;
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
-constexpr int G2_GROUP_M = 8;  // in 256-row tiles
+constexpr int G2_GROUP_M = 16;  // in 256-row tiles (swept in tools/sweep_group_m.py: 16 >= 8 on every step shape)
 
 template <bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -336,10 +337,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int total_tiles = p.m_tiles * p.n_tiles;  // m_tiles counts 256-row tiles here
 
   auto decode = [&](int tile, int& m_blk, int& n_blk) {
-    const int per_group = G2_GROUP_M * p.n_tiles;
+    const int per_group = p.group_m * p.n_tiles;
     int group = tile / per_group;
-    int first_m = group * G2_GROUP_M;
-    int gsz = min(G2_GROUP_M, p.m_tiles - first_m);
+    int first_m = group * p.group_m;
+    int gsz = min(p.group_m, p.m_tiles - first_m);
     int r = tile - group * per_group;
     m_blk = first_m + (r % gsz);
     n_blk = r / gsz;
@@ -649,6 +650,7 @@ cudaError_t launch(const GemmArgs& a, cudaStream_t s) {
   p.ldc = a.ldc;
   p.R = a.R;
   p.ldr = a.ldr;
+  p.group_m = 0;
   p.aux = nullptr;
   p.ld_aux = 0;
   p.rope_cs = nullptr;
@@ -671,6 +673,7 @@ cudaError_t launch_epi(const GemmArgs& a, cudaStream_t s) {
 }
 
 int g_use_pair_kernel = 1;
+int g_pair_group_m = G2_GROUP_M;
 
 template <bool B_MN, int EPI>
 cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
@@ -706,6 +709,7 @@ cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
   p.ldc = a.ldc;
   p.R = a.R;
   p.ldr = a.ldr;
+  p.group_m = g_pair_group_m;
   p.aux = a.aux;
   p.ld_aux = a.ld_aux;
   p.rope_cs = a.rope_cs;
@@ -744,6 +748,7 @@ cudaError_t launch_major(const GemmArgs& a, cudaStream_t s) {
 }  // namespace
 
 void gemm_set_pair_kernel(int on) { g_use_pair_kernel = on; }
+void gemm_set_pair_group_m(int g) { g_pair_group_m = g > 0 ? g : G2_GROUP_M; }
 
 cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaErrorInvalidValue;
