@@ -4,7 +4,8 @@
 // reached from cmd/tuning/train.py:299) and its autograd backward (K10).  The [B,H,S,S] score tensor
 // never exists: scores live in TMEM, probabilities go TMEM -> registers -> swizzled smem -> tensor core.
 //
-// Data layout: packed qkv [B*S, 3*H*128] (per token: q heads | k heads | v heads), out [B*S, H*128],
+// Data layout: packed qkv [B*S, (H + 2*Hkv)*128] (per token: q heads | k heads | v heads; Hkv <= H for grouped-query
+// attention), out [B*S, H*128],
 // lse2 [B,H,S] = log2-domain log-sum-exp of the scaled scores (m + log2 l).
 //
 // Kernels (one CTA per SM; 4 compute warps where thread r owns TMEM lane r = one row of the score tile, plus a 5th
@@ -38,6 +39,8 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnKParams {
   int B, S, H;
+  int Hkv, W;        // kv heads (grouped-query attention: q head h reads kv head h / (H / Hkv)); W = row stride of qkv
+  int colK0, colV0;  // first column of the k / v sections inside a qkv row
   float scale_log2;  // softmax scale * log2(e)
   float scale;
   float* lse2;
@@ -85,7 +88,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int row_base = b * p.S;
   const int n = (q0 + 128) / 64;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int colQ = h * HD, colK = p.H * HD + h * HD, colV = 2 * p.H * HD + h * HD;
+  const int hk = h / (p.H / p.Hkv);
+  const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ);
@@ -305,7 +309,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int row_base = b * p.S;
   const int n = (q0 + 128) / 64;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int colQ = h * HD, colK = p.H * HD + h * HD, colV = 2 * p.H * HD + h * HD;
+  const int hk = h / (p.H / p.Hkv);
+  const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ);
@@ -426,7 +431,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_wait(bar_o, (n - 1) & 1);
     tc_fence_after();
     // each thread stores columns [32*half, +32) and [64 + 32*half, +32): the rotary pair (i, i+64) stays in one thread
-    bf16* drow = p.dqkv + static_cast<size_t>(row_base + qrow) * (3 * p.H * HD) + colQ;
+    bf16* drow = p.dqkv + static_cast<size_t>(row_base + qrow) * p.W + colQ;
     {
       uint32_t lo[32], hi[32];
       tmem_ld32(t_lane + T_DQ + half * 32, lo);
@@ -491,15 +496,17 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
   const int nkb = p.S / 128;
   const int kb = blockIdx.x % nkb;  // early KV blocks see the most query blocks: they come first
   const int bh = blockIdx.x / nkb;
-  const int h = bh % p.H, b = bh / p.H;
+  const int hk = bh % p.Hkv, b = bh / p.Hkv;  // one CTA per (batch, KV head, 128-row KV block)
+  const int grp = p.H / p.Hkv;                // query heads sharing this KV head (1 = multi-head attention)
   const int kv0 = kb * 128;
   const int row_base = b * p.S;
   const int i0 = kv0 / 64;
-  const int n = p.S / 64 - i0;
+  const int nq = p.S / 64 - i0;               // query blocks per query head that see this KV block
+  const int n = nq * grp;                     // streamed (head, query block) pairs; it -> head it / nq, block it % nq
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int colQ = h * HD, colK = p.H * HD + h * HD, colV = 2 * p.H * HD + h * HD;
-  const float* g_lse = p.lse2 + (static_cast<size_t>(b) * p.H + h) * p.S;
-  const float* g_delta = p.delta + (static_cast<size_t>(b) * p.H + h) * p.S;
+  const int colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
+  const float* g_lse = p.lse2 + (static_cast<size_t>(b) * p.H + hk * grp) * p.S;
+  const float* g_delta = p.delta + (static_cast<size_t>(b) * p.H + hk * grp) * p.S;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmKV128);
@@ -523,16 +530,17 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, 128, 0, 1);
       const uint32_t sK = smem_u32(smem + DKV_SK), sV = smem_u32(smem + DKV_SV), sQ = smem_u32(smem + DKV_SQ),
                      sDO = smem_u32(smem + DKV_SDO), sPT = smem_u32(smem + DKV_SPT), sDST = smem_u32(smem + DKV_SDST);
-      auto load_q = [&](int ii) {  // query block i0+ii (Q, dO, lse2, delta) -> ring slot ii % 3
-        const int slot = ii % 3, qs = (i0 + ii) * 64;
+      auto load_q = [&](int ii) {  // (head, query block) pair ii: Q, dO, lse2, delta -> ring slot ii % 3
+        const int slot = ii % 3, hq = ii / nq, qs = (i0 + ii % nq) * 64;
+        const int colQ = (hk * grp + hq) * HD;
         if (!leader) return;
         mbar_arrive_expect_tx(&bar_q[slot], 32768 + 512);
         tma_load_2d(smem + DKV_SQ + slot * 16384, &tmQ64, &bar_q[slot], colQ, row_base + qs);
         tma_load_2d(smem + DKV_SQ + slot * 16384 + 8192, &tmQ64, &bar_q[slot], colQ + 64, row_base + qs);
-        tma_load_2d(smem + DKV_SDO + slot * 16384, &tmDO64, &bar_q[slot], h * HD, row_base + qs);
-        tma_load_2d(smem + DKV_SDO + slot * 16384 + 8192, &tmDO64, &bar_q[slot], h * HD + 64, row_base + qs);
-        tma_load_1d(smem + DKV_STAT + slot * 512, g_lse + qs, 256, &bar_q[slot]);
-        tma_load_1d(smem + DKV_STAT + slot * 512 + 256, g_delta + qs, 256, &bar_q[slot]);
+        tma_load_2d(smem + DKV_SDO + slot * 16384, &tmDO64, &bar_q[slot], colQ, row_base + qs);
+        tma_load_2d(smem + DKV_SDO + slot * 16384 + 8192, &tmDO64, &bar_q[slot], colQ + 64, row_base + qs);
+        tma_load_1d(smem + DKV_STAT + slot * 512, g_lse + static_cast<size_t>(hq) * p.S + qs, 256, &bar_q[slot]);
+        tma_load_1d(smem + DKV_STAT + slot * 512 + 256, g_delta + static_cast<size_t>(hq) * p.S + qs, 256, &bar_q[slot]);
       };
       auto issue_s = [&](int ii) {  // S^T = K Q^T, dP^T = V dO^T into buffer ii & 1
         const int slot = ii % 3;
@@ -588,7 +596,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     const int kvrow = kv0 + r;
     const uint32_t sPT_addr = smem_u32(smem + DKV_SPT), sDST_addr = smem_u32(smem + DKV_SDST);
     for (int ii = 0; ii < n; ++ii) {
-      const int qs = (i0 + ii) * 64;
+      const int qs = (i0 + ii % nq) * 64;
       mbar_wait(&bar_q[ii % 3], (ii / 3) & 1);  // acquire the TMA-written row statistics of this ring slot
       mbar_wait(&bar_s[ii & 1], (ii >> 1) & 1);
       tc_fence_after();
@@ -629,7 +637,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     mbar_wait(bar_o, (n - 1) & 1);
     tc_fence_after();
     // warps 0-3 write dV, warps 4-7 write dK (each thread one full 128-wide row)
-    bf16* drow = p.dqkv + static_cast<size_t>(row_base + kvrow) * (3 * p.H * HD) + (half ? colK : colV);
+    bf16* drow = p.dqkv + static_cast<size_t>(row_base + kvrow) * p.W + (half ? colK : colV);
     const uint32_t tcol = half ? T_DK : T_DV;
     const bool rot = half && p.rope_cs;  // dK is the gradient of the post-rotary key: rotate back (R^T)
     const float2* cs = p.rope_cs + static_cast<size_t>(kvrow) * 64;
@@ -686,12 +694,15 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     init = true;
   }
-  const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = 3ull * a.H * HD;
+  const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
+  if (a.H % Hkv) return cudaErrorInvalidValue;
+  const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD;
   CUtensorMap tmQ, tmKV;
   if (!make_tmap_2d_bf16(&tmQ, a.qkv, W, M, W, 64, 128) || !make_tmap_2d_bf16(&tmKV, a.qkv, W, M, W, 64, 64))
     return cudaErrorInvalidValue;
   AttnKParams p{};
   p.B = a.B; p.S = a.S; p.H = a.H;
+  p.Hkv = Hkv; p.W = static_cast<int>(W); p.colK0 = a.H * HD; p.colV0 = (a.H + Hkv) * HD;
   p.scale = a.scale;
   p.scale_log2 = a.scale * LOG2E;
   p.lse2 = a.lse;
@@ -710,7 +721,10 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     init = true;
   }
-  const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = 3ull * a.H * HD, WO = static_cast<uint64_t>(a.H) * HD;
+  const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
+  if (a.H % Hkv) return cudaErrorInvalidValue;
+  const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD,
+                 WO = static_cast<uint64_t>(a.H) * HD;
   CUtensorMap tmQ128, tmKV64, tmDO128, tmKV128, tmQ64, tmDO64;
   bool ok = make_tmap_2d_bf16(&tmQ128, a.qkv, W, M, W, 64, 128) && make_tmap_2d_bf16(&tmKV64, a.qkv, W, M, W, 64, 64) &&
             make_tmap_2d_bf16(&tmDO128, a.dout, WO, M, WO, 64, 128) && make_tmap_2d_bf16(&tmDO64, a.dout, WO, M, WO, 64, 64);
@@ -719,6 +733,7 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (!ok) return cudaErrorInvalidValue;
   AttnKParams p{};
   p.B = a.B; p.S = a.S; p.H = a.H;
+  p.Hkv = Hkv; p.W = static_cast<int>(W); p.colK0 = a.H * HD; p.colV0 = (a.H + Hkv) * HD;
   p.scale = a.scale;
   p.scale_log2 = a.scale * LOG2E;
   p.lse2 = a.lse;
@@ -733,7 +748,7 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
     attn_delta_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(a.out, a.dout, a.delta, a.B, a.S, a.H);
   }
   attn_dq_kernel<<<a.B * a.H * (a.S / 128), BWD_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, p);
-  attn_dkv_kernel<<<a.B * a.H * (a.S / 128), BWD_THREADS, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, p);
+  attn_dkv_kernel<<<a.B * Hkv * (a.S / 128), BWD_THREADS, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, p);
   return cudaGetLastError();
 }
 

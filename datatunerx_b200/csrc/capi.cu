@@ -71,14 +71,22 @@ int32_t dtx_rope_table(void* cs_out_device, int32_t Sq, int32_t D, float theta, 
   if (e == cudaSuccess) e = cudaStreamSynchronize(S(stream));
   return rc(e);
 }
-int32_t dtx_rope_qk(void* qkv, const void* cs, int32_t B, int32_t Sq, int32_t H, int32_t D, int32_t inverse, void* stream) {
-  return rc(rope_qk_inplace_table(static_cast<bf16*>(qkv), static_cast<const float2*>(cs), B, Sq, H, D, inverse, S(stream)));
+int32_t dtx_rope_qk(void* qkv, const void* cs, int32_t B, int32_t Sq, int32_t H, int32_t Hkv, int32_t D, int32_t inverse,
+                    void* stream) {
+  return rc(rope_qk_inplace_table(static_cast<bf16*>(qkv), static_cast<const float2*>(cs), B, Sq, H + Hkv, (H + 2 * Hkv) * D, D, inverse,
+                                  S(stream)));
 }
 int32_t dtx_swiglu_fwd(const void* gu, void* act, int32_t M, int32_t F, void* stream) {
   return rc(swiglu_fwd(static_cast<const bf16*>(gu), static_cast<bf16*>(act), M, F, 0, S(stream)));
 }
 int32_t dtx_swiglu_bwd(const void* dact, const void* gu, void* dgu, int32_t M, int32_t F, void* stream) {
   return rc(swiglu_bwd(static_cast<const bf16*>(dact), static_cast<const bf16*>(gu), static_cast<bf16*>(dgu), M, F, 0, S(stream)));
+}
+int32_t dtx_lora_dropout_fwd(const void* h, void* hd, int32_t M, int32_t d, int32_t nt, float p, uint64_t key, void* stream) {
+  return rc(lora_dropout_fwd(static_cast<const bf16*>(h), static_cast<bf16*>(hd), M, d, nt, p, key, S(stream)));
+}
+int32_t dtx_lora_dropout_bwd_add(void* dh, const void* g, int32_t M, int32_t d, int32_t nt, float p, uint64_t key, void* stream) {
+  return rc(lora_dropout_bwd_add(static_cast<bf16*>(dh), static_cast<const bf16*>(g), M, d, nt, p, key, S(stream)));
 }
 int32_t dtx_cross_entropy(const void* logits, int64_t ldl, const void* labels, void* shifted, void* n_valid, void* row_loss,
                           void* dlogits, int64_t ldd, void* loss_out, int32_t B, int32_t Sq, int32_t V, void* stream) {
@@ -107,15 +115,18 @@ int32_t dtx_adamw(void* p, const void* g, void* m, void* v, int64_t n, float lr,
   a.grad_norm_out = static_cast<float*>(grad_norm_out);
   return rc(adamw_step(a, S(stream)));
 }
-int32_t dtx_attn_fwd(const void* qkv, void* out, void* lse2, int32_t B, int32_t Sq, int32_t H, float scale, void* stream) {
+int32_t dtx_attn_fwd(const void* qkv, void* out, void* lse2, int32_t B, int32_t Sq, int32_t H, int32_t Hkv, float scale,
+                     void* stream) {
   AttnArgs a;
+  a.Hkv = Hkv;
   a.qkv = static_cast<const bf16*>(qkv); a.out = static_cast<bf16*>(out); a.lse = static_cast<float*>(lse2);
   a.B = B; a.S = Sq; a.H = H; a.scale = scale;
   return rc(attn_fwd(a, S(stream)));
 }
 int32_t dtx_attn_bwd(const void* qkv, const void* out, const void* dout, const void* lse2, void* delta, void* dqkv, int32_t B,
-                     int32_t Sq, int32_t H, float scale, void* stream) {
+                     int32_t Sq, int32_t H, int32_t Hkv, float scale, void* stream) {
   AttnArgs a;
+  a.Hkv = Hkv;
   a.qkv = static_cast<const bf16*>(qkv); a.out = const_cast<bf16*>(static_cast<const bf16*>(out));
   a.lse = const_cast<float*>(static_cast<const float*>(lse2)); a.dout = static_cast<const bf16*>(dout);
   a.delta = static_cast<float*>(delta); a.dqkv = static_cast<bf16*>(dqkv);

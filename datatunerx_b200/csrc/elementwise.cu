@@ -176,21 +176,19 @@ __global__ void __launch_bounds__(RMS_THREADS) rmsnorm_bwd_kernel(const bf16* __
 //   out[i] = x[i] cos - x[i+D/2] sin ; out[i+D/2] = x[i+D/2] cos + x[i] sin ; inverse flips sin.
 // cs table: [S][D/2] float2(cos, sin), built in double precision on the host.
 // ------------------------------------------------------------------------------------------
-__global__ void rope_kernel(bf16* __restrict__ qkv, const float2* __restrict__ cs, int S, int H, int D, int inverse,
+__global__ void rope_kernel(bf16* __restrict__ qkv, const float2* __restrict__ cs, int S, int NH, int W, int D, int inverse,
                             long long total_vec) {
-  // one thread handles 8 consecutive i (one uint4 from each half) of one (token, q|k, head)
+  // one thread handles 8 consecutive i (one uint4 from each half) of one (token, head); heads 0..NH-1 = q heads then k heads
   const int half = D >> 1;
   const int vec_per_head = half >> 3;
   for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total_vec;
        t += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int iv = static_cast<int>(t % vec_per_head);
     long long r = t / vec_per_head;
-    const int h = static_cast<int>(r % H);
-    r /= H;
-    const int which = static_cast<int>(r % 2);  // 0 = q, 1 = k
-    const long long m = r / 2;
+    const int h = static_cast<int>(r % NH);
+    const long long m = r / NH;
     const int pos = static_cast<int>(m % S);
-    bf16* base = qkv + m * (3LL * H * D) + static_cast<long long>(which) * H * D + static_cast<long long>(h) * D + iv * 8;
+    bf16* base = qkv + m * static_cast<long long>(W) + static_cast<long long>(h) * D + iv * 8;
     uint4 lo = *reinterpret_cast<uint4*>(base);
     uint4 hi = *reinterpret_cast<uint4*>(base + half);
     float a[8], b[8];
@@ -461,6 +459,59 @@ __global__ void adamw_kernel(AdamWArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// LoRA dropout (peft lora.Linear: lora_A(lora_dropout(x)), one nn.Dropout per wrapped module).  Counter-based masks:
+// keep(m, c, target) = splitmix64(key + target * G + m * d + c) >> 40 >= p * 2^24 ; kept values are scaled by 1/(1-p).
+// The backward kernel regenerates the same decisions instead of storing masks.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool drop_keep(uint64_t key, int target, long long idx, uint32_t thresh) {
+  uint64_t x = key + static_cast<uint64_t>(target) * 0x9E3779B97F4A7C15ull + static_cast<uint64_t>(idx);
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return static_cast<uint32_t>(x >> 40) >= thresh;
+}
+__global__ void lora_dropout_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ hd, long long M, int d, int nt,
+                                        uint32_t thresh, float inv_keep, uint64_t key) {
+  const int vec = d >> 3;
+  const long long total = M * vec;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = t / vec;
+    const int c0 = static_cast<int>(t % vec) << 3;
+    float f[8];
+    bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(h + m * d + c0)), f);
+    for (int ti = 0; ti < nt; ++ti) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = drop_keep(key, ti, m * d + c0 + j, thresh) ? f[j] * inv_keep : 0.f;
+      *reinterpret_cast<uint4*>(hd + m * static_cast<long long>(nt) * d + static_cast<long long>(ti) * d + c0) = f32_to_bf16x8(o);
+    }
+  }
+}
+__global__ void lora_dropout_bwd_kernel(bf16* __restrict__ dh, const bf16* __restrict__ g, long long M, int d, int nt,
+                                        uint32_t thresh, float inv_keep, uint64_t key) {
+  const int vec = d >> 3;
+  const long long total = M * vec;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = t / vec;
+    const int c0 = static_cast<int>(t % vec) << 3;
+    float acc[8];
+    uint4* dst = reinterpret_cast<uint4*>(dh + m * d + c0);
+    bf16x8_to_f32(*dst, acc);
+    for (int ti = 0; ti < nt; ++ti) {
+      float gv[8];
+      bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(g + m * static_cast<long long>(nt) * d + static_cast<long long>(ti) * d + c0)), gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (drop_keep(key, ti, m * d + c0 + j, thresh)) acc[j] += gv[j] * inv_keep;
+    }
+    *dst = f32_to_bf16x8(acc);
+  }
+}
+
 __global__ void cast2d_kernel(const float* __restrict__ src, long long lds, bf16* __restrict__ dst, long long ldd, int rows,
                               int cols, float scale, int transpose) {
   const long long total = static_cast<long long>(rows) * cols;
@@ -535,10 +586,11 @@ cudaError_t rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const floa
   return cudaGetLastError();
 }
 
-cudaError_t rope_qk_inplace_table(bf16* qkv, const float2* cs, int B, int S, int H, int D, int inverse, cudaStream_t s) {
+cudaError_t rope_qk_inplace_table(bf16* qkv, const float2* cs, int B, int S, int n_rot_heads, int W, int D, int inverse,
+                                  cudaStream_t s) {
   if (D % 16) return cudaErrorInvalidValue;
-  const long long total = static_cast<long long>(B) * S * 2 * H * (D / 16);
-  rope_kernel<<<grid_for(total, 256), 256, 0, s>>>(qkv, cs, S, H, D, inverse, total);
+  const long long total = static_cast<long long>(B) * S * n_rot_heads * (D / 16);
+  rope_kernel<<<grid_for(total, 256), 256, 0, s>>>(qkv, cs, S, n_rot_heads, W, D, inverse, total);
   return cudaGetLastError();
 }
 
@@ -586,6 +638,25 @@ cudaError_t adamw_step(const AdamWArgs& a, cudaStream_t s) {
        reinterpret_cast<uintptr_t>(a.v)) & 15)
     return cudaErrorInvalidValue;
   adamw_kernel<<<grid_for(a.n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+static uint32_t drop_thresh(float p) {
+  double v = static_cast<double>(p) * 16777216.0;
+  if (v < 0) v = 0;
+  if (v > 16777215.0) v = 16777215.0;
+  return static_cast<uint32_t>(v);
+}
+cudaError_t lora_dropout_fwd(const bf16* h, bf16* hd, int M, int d, int nt, float p, uint64_t key, cudaStream_t s) {
+  if (d % 8) return cudaErrorInvalidValue;
+  lora_dropout_fwd_kernel<<<grid_for(static_cast<long long>(M) * (d / 8), 256), 256, 0, s>>>(h, hd, M, d, nt, drop_thresh(p),
+                                                                                          1.0f / (1.0f - p), key);
+  return cudaGetLastError();
+}
+cudaError_t lora_dropout_bwd_add(bf16* dh, const bf16* g, int M, int d, int nt, float p, uint64_t key, cudaStream_t s) {
+  if (d % 8) return cudaErrorInvalidValue;
+  lora_dropout_bwd_kernel<<<grid_for(static_cast<long long>(M) * (d / 8), 256), 256, 0, s>>>(dh, g, M, d, nt, drop_thresh(p),
+                                                                                          1.0f / (1.0f - p), key);
   return cudaGetLastError();
 }
 

@@ -49,18 +49,19 @@ void gemm_set_pair_group_m(int tiles);  // rasterisation group height of the pai
 void trainer_set_fused_epilogues(int on);
 
 // ---------------------------------------------------------------------------------------------
-// flash attention (causal, head_dim 128), packed qkv layout [B*S, 3*H*128] (q | k | v per token)
+// flash attention (causal, head_dim 128), packed qkv layout [B*S, (H + 2*Hkv)*128] (q heads | k heads | v heads per token)
 // ---------------------------------------------------------------------------------------------
 struct AttnArgs {
-  const bf16* qkv = nullptr;  // [B*S, 3*H*D]
+  const bf16* qkv = nullptr;  // [B*S, (H + 2*Hkv)*D]
   bf16* out = nullptr;        // [B*S, H*D]
   float* lse = nullptr;       // [B, H, S]  natural-log sum-exp of scaled scores
   int B = 0, S = 0, H = 0;
+  int Hkv = 0;                // kv heads; 0 = H (multi-head attention)
   float scale = 0.f;
   // backward
   const float2* rope_cs = nullptr;  // backward only: if set, dq and dk get the inverse rotary applied before the store
   const bf16* dout = nullptr;  // [B*S, H*D]
-  bf16* dqkv = nullptr;        // [B*S, 3*H*D]
+  bf16* dqkv = nullptr;        // [B*S, (H + 2*Hkv)*D]
   float* delta = nullptr;      // [B, H, S] scratch: rowsum(dO * O)
 };
 cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s);
@@ -75,9 +76,10 @@ cudaError_t rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int 
 // dx = rstd * (w*dy) - x * rstd^3 * mean(w*dy*x)  (+ dres if not null)
 cudaError_t rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx,
                         int M, int d, cudaStream_t s);
-// half-split rotary embedding applied in place to the q and k thirds of packed qkv. inverse=1 applies R^T (backward)
-// cs = [S][D/2] float2(cos, sin) table built on the host in double precision
-cudaError_t rope_qk_inplace_table(bf16* qkv, const float2* cs, int B, int S, int H, int D, int inverse, cudaStream_t s);
+// half-split rotary embedding applied in place to the first n_rot_heads heads (q heads then k heads) of every row of
+// packed qkv (row stride W elements). inverse=1 applies R^T (backward).  cs = [S][D/2] float2(cos, sin) table
+cudaError_t rope_qk_inplace_table(bf16* qkv, const float2* cs, int B, int S, int n_rot_heads, int W, int D, int inverse,
+                                  cudaStream_t s);
 // gu [M, 2F]: [gate F | up F] (interleaved = 0) or the GU-interleaved layout the trainer uses (interleaved = 1: feature f
 // has its gate at column (f/128)*256 + f%128 and its up 128 columns further); act[M,F] = silu(gate) * up
 cudaError_t swiglu_fwd(const bf16* gu, bf16* act, int M, int F, int interleaved, cudaStream_t s);
@@ -106,6 +108,10 @@ struct AdamWArgs {
 };
 cudaError_t adamw_step(const AdamWArgs& a, cudaStream_t s);
 
+// LoRA dropout with counter-based masks (see elementwise.cu): hd[M, nt*d] = per-target dropped copies of h[M, d];
+// dh[M, d] += sum_t mask_t o g[:, t*d:(t+1)*d] / (1-p)
+cudaError_t lora_dropout_fwd(const bf16* h, bf16* hd, int M, int d, int nt, float p, uint64_t key, cudaStream_t s);
+cudaError_t lora_dropout_bwd_add(bf16* dh, const bf16* g, int M, int d, int nt, float p, uint64_t key, cudaStream_t s);
 // fp32 -> bf16 with scale, strided 2-D (used to refresh the bf16 LoRA shadows)
 cudaError_t cast_f32_to_bf16_2d(const float* src, int64_t lds, bf16* dst, int64_t ldd, int rows, int cols, float scale,
                                 int transpose, cudaStream_t s);

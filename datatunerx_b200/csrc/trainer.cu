@@ -88,35 +88,42 @@ __global__ void lora_gather_kernel(const float* __restrict__ part, int splits, l
   }
 }
 
+// Per-target geometry of the LoRA adapters inside one layer's block of the flat parameter buffer.
+struct TargetInfo {
+  int row0;        // first row of the target's output features inside wqkv / b_ext
+  int d_out;       // output features (n_heads*128 for q, n_kv_heads*128 for k, v)
+  long long off;   // offset of this target's [A^T (d x r) | B (d_out x r)] inside the layer block
+};
+
 // refresh bf16 shadows of all adapters from the fp32 masters.
-//   a_cat[l][(ti*r + j)*d + c]              = A^T[c*r + j]
-//   b_ext[l][(row0[ti] + n)*RP + ti*r + j]  = scale * B[n*r + j]
+//   a_cat[l][(ti*r + j)*KA + a_col0(ti) + c]  = A^T[c*r + j]      (KA = d, a_col0 = 0; with LoRA dropout KA = nt*d, a_col0 = ti*d)
+//   b_ext[l][(row0[ti] + n)*RP + ti*r + j]    = scale * B[n*r + j]
 struct ShadowArgs {
   const float* params;
   bf16* a_cat;
   bf16* b_ext;
-  int L, d, r, RP, nt;
-  int row0[3];
+  int L, d, r, RP, nt, KA, W, a_split;
+  long long per_layer;
+  TargetInfo tg[3];
   float scale;
 };
 __global__ void lora_shadow_kernel(ShadowArgs a) {
-  const long long per_t = 2LL * a.d * a.r;
-  const long long per_l = per_t * a.nt;
-  const long long total = per_l * a.L;
+  const long long total = a.per_layer * a.L;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int l = static_cast<int>(i / per_l);
-    long long rem = i - l * per_l;
-    const int ti = static_cast<int>(rem / per_t);
-    rem -= ti * per_t;
+    const int l = static_cast<int>(i / a.per_layer);
+    long long rem = i - l * a.per_layer;
+    int ti = 0;
+    while (ti + 1 < a.nt && rem >= a.tg[ti + 1].off) ++ti;
+    rem -= a.tg[ti].off;
     const float v = a.params[i];
     if (rem < static_cast<long long>(a.d) * a.r) {
       const int c = static_cast<int>(rem / a.r), j = static_cast<int>(rem % a.r);
-      a.a_cat[(static_cast<long long>(l) * a.RP + ti * a.r + j) * a.d + c] = __float2bfloat16_rn(v);
+      a.a_cat[(static_cast<long long>(l) * a.RP + ti * a.r + j) * a.KA + (a.a_split ? ti * a.d : 0) + c] = __float2bfloat16_rn(v);
     } else {
       rem -= static_cast<long long>(a.d) * a.r;
       const int n = static_cast<int>(rem / a.r), j = static_cast<int>(rem % a.r);
-      a.b_ext[(static_cast<long long>(l) * 3 * a.d + a.row0[ti] + n) * a.RP + ti * a.r + j] = __float2bfloat16_rn(v * a.scale);
+      a.b_ext[(static_cast<long long>(l) * a.W + a.tg[ti].row0 + n) * a.RP + ti * a.r + j] = __float2bfloat16_rn(v * a.scale);
     }
   }
 }
@@ -126,6 +133,7 @@ struct Layer {
   bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr, *norm1 = nullptr, *norm2 = nullptr;
   bf16 *a_cat = nullptr, *b_ext = nullptr;                                               // shadows
   bf16 *h1 = nullptr, *t = nullptr, *qkv = nullptr, *attn = nullptr, *x_mid = nullptr, *gu = nullptr;  // saved
+  bf16* hd = nullptr;  // LoRA dropout only: [M, nt*d] dropped copies of h1, one per target (peft: one nn.Dropout per module)
   float *lse = nullptr, *rstd1 = nullptr, *rstd2 = nullptr;
 };
 
@@ -147,8 +155,13 @@ struct dtx_trainer {
   size_t bytes_allocated = 0;
 
   int M = 0, RP = 0, nt = 0;
-  int target_row0[3] = {0, 0, 0};
-  int64_t n_train = 0;
+  int dq = 0, dkv = 0, W = 0;  // q width (= hidden), k/v width (n_kv_heads*128), packed qkv row width
+  int KA = 0;                  // contraction length of the LoRA down-projection: d, or nt*d with dropout
+  bool dropout = false;
+  TargetInfo tg[3];
+  char tg_name[3] = {0, 0, 0};
+  int64_t per_layer = 0, n_train = 0;
+  uint64_t fwd_count = 0;      // forward passes so far: seeds the dropout masks
 
   bf16 *embed = nullptr, *lm_head = nullptr, *normf = nullptr;
   std::vector<Layer> layers;
@@ -158,7 +171,7 @@ struct dtx_trainer {
 
   // transients
   bf16 *h2 = nullptr, *act = nullptr, *dact = nullptr, *dgu = nullptr, *dx_a = nullptr, *dx_b = nullptr, *dh = nullptr,
-       *dattn = nullptr, *dqkv = nullptr, *dt = nullptr, *dlogits = nullptr;
+       *dattn = nullptr, *dqkv = nullptr, *dt = nullptr, *dlogits = nullptr, *glora = nullptr;
   float *logits = nullptr, *rstdf = nullptr, *row_loss = nullptr, *delta = nullptr, *part_b = nullptr, *part_a = nullptr;
   float *d_loss = nullptr, *d_sumsq = nullptr, *d_gnorm = nullptr, *d_scratch = nullptr;
   int32_t *d_ids = nullptr, *d_labels = nullptr, *d_shift = nullptr, *d_nvalid = nullptr;
@@ -206,6 +219,17 @@ namespace {
     t->launches += (nlaunch);                                                                    \
   } while (0)
 
+// key of the dropout masks of one (forward pass, layer): the per-element keep decision is
+// splitmix64(key + target * 0x9E3779B97F4A7C15 + m * d + c) >> 40 >= p * 2^24  (restated in oracle/llama_lora.py)
+uint64_t dropout_key(const dtx_trainer* t, int layer) {
+  uint64_t x = t->tc.seed * 0xD1B54A32D192ED03ull + t->fwd_count * 0x100000001B3ull + static_cast<uint64_t>(layer) * 0x9E3779B1ull +
+               static_cast<uint64_t>(t->rank) * 0xC2B2AE3D27D4EB4Full;
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
 int pick_split(int m_tiles, int kb_total) {
   int s = (2 * gemm_num_sms() + m_tiles - 1) / m_tiles;
   if (s < 1) s = 1;
@@ -219,24 +243,25 @@ int pick_split(int m_tiles, int kb_total) {
 int create_buffers(dtx_trainer* t) {
   const dtx_model_cfg& mc = t->mc;
   const dtx_train_cfg& tc = t->tc;
-  const size_t d = mc.hidden, F = mc.ffn, V = mc.vocab, L = mc.n_layers, M = t->M, RP = t->RP;
+  const size_t d = mc.hidden, F = mc.ffn, V = mc.vocab, L = mc.n_layers, M = t->M, RP = t->RP, W = t->W, KA = t->KA;
   bool ok = true;
   ok = ok && t->alloc(&t->embed, V * d) && t->alloc(&t->lm_head, V * d) && t->alloc(&t->normf, d);
-  ok = ok && t->alloc(&t->a_cat_all, L * RP * d) && t->alloc(&t->b_ext_all, L * 3 * d * RP);
+  ok = ok && t->alloc(&t->a_cat_all, L * RP * KA) && t->alloc(&t->b_ext_all, L * W * RP);
   if (!ok) return DTX_ERR_CUDA;
-  cudaMemset(t->a_cat_all, 0, L * RP * d * sizeof(bf16));
-  cudaMemset(t->b_ext_all, 0, L * 3 * d * RP * sizeof(bf16));
+  cudaMemset(t->a_cat_all, 0, L * RP * KA * sizeof(bf16));
+  cudaMemset(t->b_ext_all, 0, L * W * RP * sizeof(bf16));
   t->layers.resize(L);
   t->xs.resize(L + 1);
   for (size_t l = 0; l <= L; ++l) ok = ok && t->alloc(&t->xs[l], M * d);
   for (size_t l = 0; l < L && ok; ++l) {
     Layer& y = t->layers[l];
-    ok = ok && t->alloc(&y.wqkv, 3 * d * d) && t->alloc(&y.wo, d * d) && t->alloc(&y.wgu, 2 * F * d) &&
+    ok = ok && t->alloc(&y.wqkv, W * d) && t->alloc(&y.wo, d * d) && t->alloc(&y.wgu, 2 * F * d) &&
          t->alloc(&y.wdown, d * F) && t->alloc(&y.norm1, d) && t->alloc(&y.norm2, d);
-    y.a_cat = t->a_cat_all + l * RP * d;
-    y.b_ext = t->b_ext_all + l * 3 * d * RP;
-    ok = ok && t->alloc(&y.h1, M * d) && t->alloc(&y.t, M * RP) && t->alloc(&y.qkv, M * 3 * d) &&
+    y.a_cat = t->a_cat_all + l * RP * KA;
+    y.b_ext = t->b_ext_all + l * W * RP;
+    ok = ok && t->alloc(&y.h1, M * d) && t->alloc(&y.t, M * RP) && t->alloc(&y.qkv, M * W) &&
          t->alloc(&y.attn, M * d) && t->alloc(&y.x_mid, M * d) && t->alloc(&y.gu, M * 2 * F);
+    if (t->dropout) ok = ok && t->alloc(&y.hd, M * KA);
     ok = ok && t->alloc(&y.lse, static_cast<size_t>(tc.micro_batch) * mc.n_heads * tc.seq_len) && t->alloc(&y.rstd1, M) &&
          t->alloc(&y.rstd2, M);
   }
@@ -250,14 +275,15 @@ int create_buffers(dtx_trainer* t) {
   cudaMemset(t->adam_v, 0, t->n_train * sizeof(float));
   ok = ok && t->alloc(&t->h2, M * d) && t->alloc(&t->act, M * F) && t->alloc(&t->dact, M * F) && t->alloc(&t->dgu, M * 2 * F) &&
        t->alloc(&t->dx_a, M * d) && t->alloc(&t->dx_b, M * d) && t->alloc(&t->dh, M * d) && t->alloc(&t->dattn, M * d) &&
-       t->alloc(&t->dqkv, M * 3 * d) && t->alloc(&t->dt, M * RP) && t->alloc(&t->dlogits, M * V) && t->alloc(&t->logits, M * V) &&
+       t->alloc(&t->dqkv, M * W) && t->alloc(&t->dt, M * RP) && t->alloc(&t->dlogits, M * V) && t->alloc(&t->logits, M * V) &&
        t->alloc(&t->rstdf, M) && t->alloc(&t->row_loss, M) &&
        t->alloc(&t->delta, static_cast<size_t>(tc.micro_batch) * mc.n_heads * tc.seq_len);
   const int kb_tok = (static_cast<int>(M) + 63) / 64;
-  t->split_b = pick_split((3 * static_cast<int>(d) + 127) / 128, kb_tok);
-  t->split_a = pick_split((static_cast<int>(d) + 127) / 128, kb_tok);
-  ok = ok && t->alloc(&t->part_b, static_cast<size_t>(t->split_b) * 3 * d * RP) &&
-       t->alloc(&t->part_a, static_cast<size_t>(t->split_a) * d * RP);
+  t->split_b = pick_split((static_cast<int>(W) + 127) / 128, kb_tok);
+  t->split_a = pick_split((static_cast<int>(KA) + 127) / 128, kb_tok);
+  ok = ok && t->alloc(&t->part_b, static_cast<size_t>(t->split_b) * W * RP) &&
+       t->alloc(&t->part_a, static_cast<size_t>(t->split_a) * KA * RP);
+  if (t->dropout) ok = ok && t->alloc(&t->glora, M * KA);
   ok = ok && t->alloc(&t->d_loss, 4) && t->alloc(&t->d_sumsq, 4) && t->alloc(&t->d_gnorm, 4) && t->alloc(&t->d_scratch, 1024);
   ok = ok && t->alloc(&t->d_ids, M) && t->alloc(&t->d_labels, M) && t->alloc(&t->d_shift, M) && t->alloc(&t->d_nvalid, 4);
   ok = ok && t->alloc(&t->rope_cs, static_cast<size_t>(tc.seq_len) * (mc.head_dim / 2));
@@ -289,7 +315,11 @@ int refresh_shadows(dtx_trainer* t) {
   a.r = t->tc.lora_r;
   a.RP = t->RP;
   a.nt = t->nt;
-  for (int i = 0; i < 3; ++i) a.row0[i] = t->target_row0[i];
+  a.KA = t->KA;
+  a.W = t->W;
+  a.a_split = t->dropout ? 1 : 0;
+  a.per_layer = t->per_layer;
+  for (int i = 0; i < 3; ++i) a.tg[i] = t->tg[i];
   a.scale = t->tc.lora_alpha / static_cast<float>(t->tc.lora_r);
   long long total = t->n_train;
   int grid = static_cast<int>((total + 255) / 256);
@@ -304,35 +334,44 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   const dtx_model_cfg& mc = t->mc;
   const dtx_train_cfg& tc = t->tc;
   const int d = mc.hidden, F = mc.ffn, V = mc.vocab, L = mc.n_layers, M = t->M, RP = t->RP, H = mc.n_heads, D = mc.head_dim;
+  const int Hkv = mc.n_kv_heads, W = t->W;
   const int B = tc.micro_batch, S = tc.seq_len;
   cudaStream_t s = t->stream;
   const float att_scale = 1.0f / sqrtf(static_cast<float>(D));
-  const bool fused = g_fused_epilogues && M > 128 && (d % 128 == 0);
+  const bool fused = g_fused_epilogues && M > 128 && ((t->dq + t->dkv) % 256 == 0);
+  const bool drop = t->dropout;  // adapters laid out for per-target dropped inputs (KA = nt*d)
+  const float p_drop = backward ? tc.lora_dropout : 0.f;  // eval (model.eval()) runs the same path with p = 0
+  t->fwd_count += 1;
 
   CK(embedding_fwd(t->d_ids, t->embed, t->xs[0], M, d, V, s), 1);
   for (int l = 0; l < L; ++l) {
     Layer& y = t->layers[l];
     CK(rmsnorm_fwd(t->xs[l], y.norm1, y.h1, y.rstd1, M, d, mc.rms_eps, s), 1);
-    {  // LoRA down-projection of all targets at once: t = h1 * A_cat^T   [M, RP]
+    const bf16* lora_in = y.h1;
+    if (drop) {  // peft: lora_A(lora_dropout(x)) with one nn.Dropout per wrapped module -> one dropped copy per target
+      CK(lora_dropout_fwd(y.h1, y.hd, M, d, t->nt, p_drop, dropout_key(t, l), s), 1);
+      lora_in = y.hd;
+    }
+    {  // LoRA down-projection of all targets at once: t = lora_in * A_cat^T   [M, RP]
       GemmArgs g;
-      g.A = y.h1; g.lda = d; g.B = y.a_cat; g.ldb = d; g.C = y.t; g.ldc = RP;
-      g.M = M; g.N = RP; g.K = d; g.epilogue = EPI_BF16; g.block_n = 64;
+      g.A = lora_in; g.lda = t->KA; g.B = y.a_cat; g.ldb = t->KA; g.C = y.t; g.ldc = RP;
+      g.M = M; g.N = RP; g.K = t->KA; g.epilogue = EPI_BF16; g.block_n = 64;
       CK(gemm_bf16(g, s), 1);
     }
     {  // qkv = h1 * Wqkv^T + t * B_ext^T : base projection and LoRA up-projection in one TMEM accumulator
       GemmArgs g;
       g.A = y.h1; g.lda = d; g.B = y.wqkv; g.ldb = d;
       g.A2 = y.t; g.lda2 = RP; g.B2 = y.b_ext; g.ldb2 = RP; g.K2 = RP;
-      g.C = y.qkv; g.ldc = 3 * d; g.M = M; g.N = 3 * d; g.K = d; g.epilogue = EPI_BF16;
+      g.C = y.qkv; g.ldc = W; g.M = M; g.N = W; g.K = d; g.epilogue = EPI_BF16;
       if (fused) {  // rotary embedding of q and k applied to the fp32 accumulator in the epilogue
-        g.epilogue = EPI_ROPE; g.rope_cs = t->rope_cs; g.rope_S = S; g.rope_cols = 2 * d;
+        g.epilogue = EPI_ROPE; g.rope_cs = t->rope_cs; g.rope_S = S; g.rope_cols = t->dq + t->dkv;
       }
       CK(gemm_bf16(g, s), 1);
     }
-    if (!fused) CK(rope_qk_inplace_table(y.qkv, t->rope_cs, B, S, H, D, 0, s), 1);
+    if (!fused) CK(rope_qk_inplace_table(y.qkv, t->rope_cs, B, S, H + Hkv, W, D, 0, s), 1);
     {
       AttnArgs a;
-      a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.scale = att_scale;
+      a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.Hkv = Hkv; a.scale = att_scale;
       CK(attn_fwd(a, s), 1);
     }
     {  // x_mid = x + attn * Wo^T
@@ -408,50 +447,58 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
     }
     {
       AttnArgs a;
-      a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.scale = att_scale;
+      a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.Hkv = Hkv; a.scale = att_scale;
       a.dout = t->dattn; a.dqkv = t->dqkv; a.delta = t->delta;
       // the kernels can apply the inverse rotary in their store epilogues (a.rope_cs), but the per-row table reads
       // at the very end of each CTA are exposed latency: measured +270 us/layer vs 47 us for the separate kernel
       a.rope_cs = nullptr;
       CK(attn_bwd(a, s), 3);
     }
-    CK(rope_qk_inplace_table(t->dqkv, t->rope_cs, B, S, H, D, 1, s), 1);
+    CK(rope_qk_inplace_table(t->dqkv, t->rope_cs, B, S, H + Hkv, W, D, 1, s), 1);
     {  // dt = dqkv * B_ext   [M, RP]
       GemmArgs g;
-      g.A = t->dqkv; g.lda = 3 * d; g.B = y.b_ext; g.ldb = RP; g.b_mn_major = 1; g.C = t->dt; g.ldc = RP;
-      g.M = M; g.N = RP; g.K = 3 * d; g.epilogue = EPI_BF16; g.block_n = 64;
+      g.A = t->dqkv; g.lda = W; g.B = y.b_ext; g.ldb = RP; g.b_mn_major = 1; g.C = t->dt; g.ldc = RP;
+      g.M = M; g.N = RP; g.K = W; g.epilogue = EPI_BF16; g.block_n = 64;
       CK(gemm_bf16(g, s), 1);
     }
-    {  // dh1 = dqkv * Wqkv + dt * A_cat
+    {  // dh1 = dqkv * Wqkv (+ dt * A_cat in the same accumulator when there is no dropout between h1 and A)
       GemmArgs g;
-      g.A = t->dqkv; g.lda = 3 * d; g.B = y.wqkv; g.ldb = d; g.b_mn_major = 1;
-      g.A2 = t->dt; g.lda2 = RP; g.B2 = y.a_cat; g.ldb2 = d; g.K2 = RP;
-      g.C = t->dh; g.ldc = d; g.M = M; g.N = d; g.K = 3 * d; g.epilogue = EPI_BF16;
+      g.A = t->dqkv; g.lda = W; g.B = y.wqkv; g.ldb = d; g.b_mn_major = 1;
+      if (!drop) { g.A2 = t->dt; g.lda2 = RP; g.B2 = y.a_cat; g.ldb2 = t->KA; g.K2 = RP; }
+      g.C = t->dh; g.ldc = d; g.M = M; g.N = d; g.K = W; g.epilogue = EPI_BF16;
       CK(gemm_bf16(g, s), 1);
     }
-    {  // grad of B_ext (all rows): dqkv^T * t   [3d, RP], split over tokens
+    if (drop) {  // dh1 += sum_t mask_t o (dt_t * A_t) / (1 - p): the masks are regenerated from the counter-based RNG
       GemmArgs g;
-      g.A = t->dqkv; g.lda = 3 * d; g.a_mn_major = 1; g.B = y.t; g.ldb = RP; g.b_mn_major = 1;
-      g.C = t->part_b; g.ldc = RP; g.M = 3 * d; g.N = RP; g.K = M; g.epilogue = EPI_F32; g.split_k = t->split_b;
+      g.A = t->dt; g.lda = RP; g.B = y.a_cat; g.ldb = t->KA; g.b_mn_major = 1; g.C = t->glora; g.ldc = t->KA;
+      g.M = M; g.N = t->KA; g.K = RP; g.epilogue = EPI_BF16;
+      CK(gemm_bf16(g, s), 1);
+      CK(lora_dropout_bwd_add(t->dh, t->glora, M, d, t->nt, p_drop, dropout_key(t, l), s), 1);
+    }
+    {  // grad of B_ext (all rows): dqkv^T * t   [W, RP], split over tokens
+      GemmArgs g;
+      g.A = t->dqkv; g.lda = W; g.a_mn_major = 1; g.B = y.t; g.ldb = RP; g.b_mn_major = 1;
+      g.C = t->part_b; g.ldc = RP; g.M = W; g.N = RP; g.K = M; g.epilogue = EPI_F32; g.split_k = t->split_b;
       g.block_n = 64;
       CK(gemm_bf16(g, s), 1);
     }
-    {  // grad of A_cat^T: h1^T * dt   [d, RP]
+    {  // grad of A_cat^T: lora_in^T * dt   [KA, RP]
       GemmArgs g;
-      g.A = y.h1; g.lda = d; g.a_mn_major = 1; g.B = t->dt; g.ldb = RP; g.b_mn_major = 1;
-      g.C = t->part_a; g.ldc = RP; g.M = d; g.N = RP; g.K = M; g.epilogue = EPI_F32; g.split_k = t->split_a;
+      g.A = drop ? y.hd : y.h1; g.lda = t->KA; g.a_mn_major = 1; g.B = t->dt; g.ldb = RP; g.b_mn_major = 1;
+      g.C = t->part_a; g.ldc = RP; g.M = t->KA; g.N = RP; g.K = M; g.epilogue = EPI_F32; g.split_k = t->split_a;
       g.block_n = 64;
       CK(gemm_bf16(g, s), 1);
     }
     const int r = tc.lora_r;
     for (int ti = 0; ti < t->nt; ++ti) {
-      float* gl = t->grads + (static_cast<int64_t>(l) * t->nt + ti) * 2 * d * r;
-      const int grid = (d * r + 255) / 256;
-      // dA^T = h1^T (dy * sB)  (the scale rides in B_ext);  dB = s * dy^T t  (t is unscaled, so the scale is applied here)
-      lora_gather_kernel<<<grid, 256, 0, s>>>(t->part_a, t->split_a, static_cast<long long>(d) * RP, RP, 0, ti * r, d, r, gl,
-                                              accumulate, 1.0f);
-      lora_gather_kernel<<<grid, 256, 0, s>>>(t->part_b, t->split_b, 3LL * d * RP, RP, t->target_row0[ti], ti * r, d, r,
-                                              gl + static_cast<int64_t>(d) * r, accumulate, tc.lora_alpha / static_cast<float>(r));
+      float* gl = t->grads + static_cast<int64_t>(l) * t->per_layer + t->tg[ti].off;
+      const int d_out = t->tg[ti].d_out;
+      // dA^T = lora_in^T (dy * sB)  (the scale rides in B_ext);  dB = s * dy^T t  (t is unscaled, so the scale is applied here)
+      lora_gather_kernel<<<(d * r + 255) / 256, 256, 0, s>>>(t->part_a, t->split_a, static_cast<long long>(t->KA) * RP, RP,
+                                                            drop ? ti * d : 0, ti * r, d, r, gl, accumulate, 1.0f);
+      lora_gather_kernel<<<(d_out * r + 255) / 256, 256, 0, s>>>(t->part_b, t->split_b, static_cast<long long>(W) * RP, RP,
+                                                                t->tg[ti].row0, ti * r, d_out, r, gl + static_cast<int64_t>(d) * r,
+                                                                accumulate, tc.lora_alpha / static_cast<float>(r));
       CK(cudaGetLastError(), 2);
     }
     CK(rmsnorm_bwd(t->dh, t->xs[l], y.norm1, y.rstd1, other, cur, M, d, s), 1);  // cur = d x_in
@@ -557,15 +604,8 @@ void to_f32_host(const void* src, int dtype, size_t n, std::vector<float>& out) 
 }
 
 int target_index(const dtx_trainer* t, char which) {  // 'q','k','v' -> index among enabled targets or -1
-  int idx = 0;
-  const unsigned bits[3] = {DTX_TARGET_Q, DTX_TARGET_K, DTX_TARGET_V};
-  const char names[3] = {'q', 'k', 'v'};
-  for (int i = 0; i < 3; ++i) {
-    if (t->tc.target_mask & bits[i]) {
-      if (names[i] == which) return idx;
-      ++idx;
-    }
-  }
+  for (int i = 0; i < t->nt; ++i)
+    if (t->tg_name[i] == which) return i;
   return -1;
 }
 
@@ -620,14 +660,14 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
     return DTX_ERR_INVALID;
   };
   if (mc->head_dim != 128) return bad("only head_dim 128 is implemented (Llama-2 / Mistral family)");
-  if (mc->n_kv_heads != mc->n_heads) { g_error = "grouped-query attention (n_kv_heads != n_heads) is not implemented yet"; return DTX_ERR_UNSUPPORTED; }
+  if (mc->n_kv_heads <= 0 || mc->n_heads % mc->n_kv_heads) return bad("n_heads must be a multiple of n_kv_heads");
   if (mc->n_heads * mc->head_dim != mc->hidden) return bad("hidden != n_heads * head_dim");
   if (mc->hidden % 64 || mc->ffn % 128 || mc->vocab % 8)
     return bad("hidden must be a multiple of 64, ffn a multiple of 128 (GU-interleaved layout), vocab a multiple of 8");
   if (tc->seq_len % 128 || tc->seq_len <= 0 || tc->micro_batch <= 0) return bad("seq_len must be a positive multiple of 128");
   if (tc->seq_len > mc->max_seq) return bad("seq_len exceeds max_seq");
   if (tc->lora_r <= 0 || tc->lora_r % 8) return bad("lora_r must be a positive multiple of 8");
-  if (tc->lora_dropout != 0.0f) { g_error = "lora_dropout != 0 is not implemented (parity config uses 0; SURVEY §8a quirk 7)"; return DTX_ERR_UNSUPPORTED; }
+  if (tc->lora_dropout < 0.0f || tc->lora_dropout >= 1.0f) return bad("lora_dropout must be in [0, 1)");
   if ((tc->target_mask & ~(DTX_TARGET_Q | DTX_TARGET_K | DTX_TARGET_V)) || tc->target_mask == 0)
     { g_error = "lora_target must be a non-empty subset of q_proj,k_proj,v_proj"; return DTX_ERR_UNSUPPORTED; }
   if (world < 1 || rank < 0 || rank >= world) return bad("bad rank/world");
@@ -651,14 +691,30 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
   t->rank = rank;
   t->world = world;
   t->M = tc->micro_batch * tc->seq_len;
+  t->dq = mc->n_heads * mc->head_dim;
+  t->dkv = mc->n_kv_heads * mc->head_dim;
+  t->W = t->dq + 2 * t->dkv;
+  t->dropout = tc->lora_dropout > 0.0f;
   t->nt = 0;
+  t->per_layer = 0;
   {
     const unsigned bits[3] = {DTX_TARGET_Q, DTX_TARGET_K, DTX_TARGET_V};
+    const char names[3] = {'q', 'k', 'v'};
+    const int row0[3] = {0, t->dq, t->dq + t->dkv};
+    const int dout[3] = {t->dq, t->dkv, t->dkv};
     for (int i = 0; i < 3; ++i)
-      if (tc->target_mask & bits[i]) t->target_row0[t->nt++] = i * mc->hidden;
+      if (tc->target_mask & bits[i]) {
+        t->tg[t->nt].row0 = row0[i];
+        t->tg[t->nt].d_out = dout[i];
+        t->tg[t->nt].off = t->per_layer;
+        t->tg_name[t->nt] = names[i];
+        t->per_layer += static_cast<int64_t>(mc->hidden + dout[i]) * tc->lora_r;
+        ++t->nt;
+      }
   }
   t->RP = ((t->nt * tc->lora_r + 63) / 64) * 64;
-  t->n_train = static_cast<int64_t>(mc->n_layers) * t->nt * 2 * mc->hidden * tc->lora_r;
+  t->KA = t->dropout ? t->nt * mc->hidden : mc->hidden;
+  t->n_train = static_cast<int64_t>(mc->n_layers) * t->per_layer;
   cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
   cudaEventCreate(&t->ev0);
   cudaEventCreate(&t->ev1);
@@ -712,7 +768,7 @@ void dtx_trainer_destroy(dtx_trainer* t) {
 int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int32_t dtype, const int64_t* shape, int32_t nd) {
   if (!t || !name || !host || !shape || nd < 1 || nd > 2) return t ? t->fail(DTX_ERR_INVALID, "bad argument") : DTX_ERR_INVALID;
   cudaSetDevice(t->device);
-  const int64_t d = t->mc.hidden, F = t->mc.ffn, V = t->mc.vocab, r = t->tc.lora_r;
+  const int64_t d = t->mc.hidden, F = t->mc.ffn, V = t->mc.vocab, r = t->tc.lora_r, dq = t->dq, dkv = t->dkv;
   const int64_t rows = shape[0], cols = nd == 2 ? shape[1] : 1;
   auto expect = [&](int64_t er, int64_t ec) { return rows == er && cols == ec; };
   auto upload = [&](bf16* dst, size_t n) -> int {
@@ -752,7 +808,8 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
     else if (strstr(rest, "v_proj")) which = 'v';
     const int ti = which ? target_index(t, which) : -1;
     if (ti < 0) return t->fail(DTX_ERR_INVALID, "%s: module is not a LoRA target", name);
-    float* base = t->params + (static_cast<int64_t>(layer) * t->nt + ti) * 2 * d * r;
+    float* base = t->params + static_cast<int64_t>(layer) * t->per_layer + t->tg[ti].off;
+    const int64_t d_out = t->tg[ti].d_out;
     std::vector<float> f;
     if (is_lora_a) {  // [r, d] -> stored transposed [d, r]
       if (!expect(r, d)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)r, (long long)d);
@@ -762,8 +819,8 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
         for (int64_t c = 0; c < d; ++c) tr[c * r + j] = f[j * d + c];
       cudaMemcpy(base, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice);
     } else {
-      if (!expect(d, r)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)d, (long long)r);
-      to_f32_host(host, dtype, d * r, f);
+      if (!expect(d_out, r)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)d_out, (long long)r);
+      to_f32_host(host, dtype, d_out * r, f);
       cudaMemcpy(base + d * r, f.data(), f.size() * 4, cudaMemcpyHostToDevice);
     }
     t->have_lora = true;
@@ -788,8 +845,8 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
   }
   struct Slot { const char* key; bf16* dst; int64_t r, c; };
   const Slot slots[] = {
-      {"self_attn.q_proj.weight", y.wqkv, d, d},           {"self_attn.k_proj.weight", y.wqkv + d * d, d, d},
-      {"self_attn.v_proj.weight", y.wqkv + 2 * d * d, d, d}, {"self_attn.o_proj.weight", y.wo, d, d},
+      {"self_attn.q_proj.weight", y.wqkv, dq, d},                  {"self_attn.k_proj.weight", y.wqkv + dq * d, dkv, d},
+      {"self_attn.v_proj.weight", y.wqkv + (dq + dkv) * d, dkv, d}, {"self_attn.o_proj.weight", y.wo, d, dq},
       {"mlp.down_proj.weight", y.wdown, d, F},             {"input_layernorm.weight", y.norm1, d, 1},
       {"post_attention_layernorm.weight", y.norm2, d, 1},
   };
@@ -813,7 +870,7 @@ int32_t dtx_init_random_weights(dtx_trainer* t, uint64_t seed) {
   CK(fill_normal_bf16(t->lm_head, V * d, 0.02f, ++k, s), 1);
   CK(fill_const_bf16(t->normf, d, 1.0f, s), 1);
   for (Layer& y : t->layers) {
-    CK(fill_normal_bf16(y.wqkv, 3 * d * d, 0.02f, ++k, s), 1);
+    CK(fill_normal_bf16(y.wqkv, static_cast<int64_t>(t->W) * d, 0.02f, ++k, s), 1);
     CK(fill_normal_bf16(y.wo, d * d, 0.02f, ++k, s), 1);
     CK(fill_normal_bf16(y.wgu, 2 * F * d, 0.02f, ++k, s), 1);
     CK(fill_normal_bf16(y.wdown, d * F, 0.02f, ++k, s), 1);
@@ -844,7 +901,7 @@ int32_t dtx_init_lora(dtx_trainer* t, uint64_t seed) {
   };
   for (int64_t l = 0; l < t->mc.n_layers; ++l)
     for (int ti = 0; ti < t->nt; ++ti) {
-      float* a = host.data() + (l * t->nt + ti) * 2 * d * r;
+      float* a = host.data() + l * t->per_layer + t->tg[ti].off;
       for (int64_t i = 0; i < d * r; ++i) a[i] = (2.f * next() - 1.f) * bound;
     }
   cudaMemcpy(t->params, host.data(), host.size() * 4, cudaMemcpyHostToDevice);
@@ -907,8 +964,10 @@ int32_t dtx_export_adapter(dtx_trainer* t, const char* name, void* host_out, int
   else if (strstr(rest, "v_proj")) which = 'v';
   const int ti = which ? target_index(t, which) : -1;
   if (ti < 0) return t->fail(DTX_ERR_INVALID, "%s: module is not a LoRA target", name);
-  if (nbytes < d * r * 4) return t->fail(DTX_ERR_INVALID, "%s: output buffer too small", name);
-  const float* base = t->params + (static_cast<int64_t>(layer) * t->nt + ti) * 2 * d * r;
+  const int64_t d_out = t->tg[ti].d_out;
+  const bool is_a = strstr(rest, "lora_A") != nullptr;
+  if (nbytes < (is_a ? d : d_out) * r * 4) return t->fail(DTX_ERR_INVALID, "%s: output buffer too small", name);
+  const float* base = t->params + static_cast<int64_t>(layer) * t->per_layer + t->tg[ti].off;
   cudaStreamSynchronize(t->stream);
   std::vector<float> tmp(d * r);
   float* out = static_cast<float*>(host_out);
@@ -917,7 +976,7 @@ int32_t dtx_export_adapter(dtx_trainer* t, const char* name, void* host_out, int
     for (int64_t c = 0; c < d; ++c)
       for (int64_t j = 0; j < r; ++j) out[j * d + c] = tmp[c * r + j];
   } else if (strstr(rest, "lora_B")) {
-    cudaMemcpy(out, base + d * r, d * r * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, base + d * r, d_out * r * 4, cudaMemcpyDeviceToHost);
   } else {
     return t->fail(DTX_ERR_INVALID, "%s: expected lora_A or lora_B", name);
   }

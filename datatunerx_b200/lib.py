@@ -48,7 +48,8 @@ ABI_SYMBOLS = [
     "dtx_get_nccl_unique_id", "dtx_load_tensor", "dtx_init_random_weights", "dtx_init_lora", "dtx_step",
     "dtx_step_device", "dtx_eval_loss", "dtx_export_adapter", "dtx_num_trainable", "dtx_launch_count",
     "dtx_last_step_ms", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
-    "dtx_rope_table", "dtx_rope_qk", "dtx_swiglu_fwd", "dtx_swiglu_bwd", "dtx_cross_entropy", "dtx_sumsq", "dtx_adamw",
+    "dtx_rope_table", "dtx_rope_qk", "dtx_swiglu_fwd", "dtx_swiglu_bwd", "dtx_lora_dropout_fwd", "dtx_lora_dropout_bwd_add",
+    "dtx_cross_entropy", "dtx_sumsq", "dtx_adamw",
     "dtx_attn_fwd", "dtx_attn_bwd",
 ]
 
@@ -95,14 +96,16 @@ def load() -> C.CDLL:
     lib.dtx_rmsnorm_fwd.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp]
     lib.dtx_rmsnorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.dtx_rope_table.argtypes = [vp, i32, i32, f32, vp]
-    lib.dtx_rope_qk.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.dtx_rope_qk.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.dtx_swiglu_fwd.argtypes = [vp, vp, i32, i32, vp]
     lib.dtx_swiglu_bwd.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.dtx_lora_dropout_fwd.argtypes = [vp, vp, i32, i32, i32, f32, C.c_uint64, vp]
+    lib.dtx_lora_dropout_bwd_add.argtypes = [vp, vp, i32, i32, i32, f32, C.c_uint64, vp]
     lib.dtx_cross_entropy.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp]
     lib.dtx_sumsq.argtypes = [vp, i64, vp, vp, vp]
     lib.dtx_adamw.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, f32, vp, vp]
-    lib.dtx_attn_fwd.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp]
-    lib.dtx_attn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
+    lib.dtx_attn_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, vp]
+    lib.dtx_attn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:  # default: all status-returning entry points
@@ -156,7 +159,7 @@ class TrainConfig:
     total_steps: int
     lora_r: int = 8                     # cmd/tuning/parser.py:138-141
     lora_alpha: float = 32.0            # parser.py:142-145
-    lora_dropout: float = 0.1           # parser.py:146-149 (the native worker implements 0.0 only)
+    lora_dropout: float = 0.1           # parser.py:146-149
     lora_target: Tuple[str, ...] = ("q_proj", "v_proj")  # finetune_controller.go:482
     lr: float = 5e-5                    # HF TrainingArguments default
     weight_decay: float = 0.0
@@ -262,8 +265,10 @@ class Trainer:
         """PEFT state dict (fp32): lora_A [r, in], lora_B [out, r] per target module."""
         out = {}
         d, r = self.model.hidden, self.train.lora_r
+        dkv = (self.model.n_kv_heads or self.model.n_heads) * self.model.head_dim
         for name in self.adapter_names():
-            shape = (r, d) if "lora_A" in name else (d, r)
+            d_out = d if ".q_proj." in name else dkv
+            shape = (r, d) if "lora_A" in name else (d_out, r)
             buf = np.empty(shape, dtype=np.float32)
             check(self.lib.dtx_export_adapter(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes), self._h)
             out[name] = buf

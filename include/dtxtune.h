@@ -137,10 +137,15 @@ DTX_API int32_t dtx_rmsnorm_fwd(const void* x, const void* w, void* y, void* rst
 DTX_API int32_t dtx_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* rstd, const void* dres, void* dx,
                         int32_t M, int32_t d, void* stream);
 DTX_API int32_t dtx_rope_table(void* cs_out_device, int32_t S, int32_t D, float theta, void* stream);
-DTX_API int32_t dtx_rope_qk(void* qkv, const void* cs_table, int32_t B, int32_t S, int32_t H, int32_t D, int32_t inverse,
-                    void* stream);
+DTX_API int32_t dtx_rope_qk(void* qkv, const void* cs_table, int32_t B, int32_t S, int32_t H, int32_t Hkv, int32_t D,
+                    int32_t inverse, void* stream);
 DTX_API int32_t dtx_swiglu_fwd(const void* gu, void* act, int32_t M, int32_t F, void* stream);
 DTX_API int32_t dtx_swiglu_bwd(const void* dact, const void* gu, void* dgu, int32_t M, int32_t F, void* stream);
+/* LoRA dropout with counter-based masks: hd[M, nt*d] = per-target dropped copies of h[M, d] (peft: lora_A(lora_dropout(x)),
+ * one nn.Dropout per wrapped module); dh[M, d] += sum_t mask_t o g[:, t*d:(t+1)*d] / (1 - p) regenerates the same masks. */
+DTX_API int32_t dtx_lora_dropout_fwd(const void* h, void* hd, int32_t M, int32_t d, int32_t nt, float p, uint64_t key, void* stream);
+DTX_API int32_t dtx_lora_dropout_bwd_add(void* dh, const void* g, int32_t M, int32_t d, int32_t nt, float p, uint64_t key,
+                                 void* stream);
 DTX_API int32_t dtx_cross_entropy(const void* logits_f32, int64_t ldl, const void* labels_unshifted, void* shifted_scratch,
                           void* n_valid_scratch, void* row_loss, void* dlogits_bf16, int64_t ldd, void* loss_out,
                           int32_t B, int32_t S, int32_t V, void* stream);
@@ -148,9 +153,11 @@ DTX_API int32_t dtx_sumsq(const void* g, int64_t n, void* scratch, void* out, vo
 DTX_API int32_t dtx_adamw(void* p, const void* g, void* m, void* v, int64_t n, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int32_t step, float grad_scale, const void* sumsq, float max_grad_norm,
                   void* grad_norm_out, void* stream);
-DTX_API int32_t dtx_attn_fwd(const void* qkv, void* out, void* lse2, int32_t B, int32_t S, int32_t H, float scale, void* stream);
+/* attention: packed qkv [B*S, (H + 2*Hkv)*128]; Hkv < H = grouped-query attention (Mistral / Llama-2-70B) */
+DTX_API int32_t dtx_attn_fwd(const void* qkv, void* out, void* lse2, int32_t B, int32_t S, int32_t H, int32_t Hkv, float scale,
+                     void* stream);
 DTX_API int32_t dtx_attn_bwd(const void* qkv, const void* out, const void* dout, const void* lse2, void* delta_scratch,
-                     void* dqkv, int32_t B, int32_t S, int32_t H, float scale, void* stream);
+                     void* dqkv, int32_t B, int32_t S, int32_t H, int32_t Hkv, float scale, void* stream);
 
 #ifdef __cplusplus
 }

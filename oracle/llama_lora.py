@@ -45,12 +45,15 @@ class OracleConfig:
     n_layers: int = 2
     n_heads: int = 2
     ffn: int = 768
+    n_kv_heads: Optional[int] = None   # grouped-query attention when < n_heads (Mistral, Llama-2-70B)
     head_dim: int = 128
     rms_eps: float = 1e-5
     rope_theta: float = 10000.0
     # training (defaults = what the reference worker ends up with)
     lora_r: int = 16
     lora_alpha: float = 32.0
+    lora_dropout: float = 0.0          # reference default 0.1 (cmd/tuning/parser.py:146-149); parity config uses 0
+    seed: int = 42
     lora_target: Tuple[str, ...] = ("q_proj", "v_proj")
     lr: float = 1e-4
     weight_decay: float = 0.0
@@ -77,6 +80,7 @@ def init_base_weights(cfg: OracleConfig, seed: int = 1234, dtype=torch.float32) 
     """HF _init_weights for Llama: Linear/Embedding ~ N(0, 0.02), RMSNorm weight = 1 (bf16-representable values)."""
     g = torch.Generator().manual_seed(seed)
     d, F, V = cfg.hidden, cfg.ffn, cfg.vocab
+    dkv = (cfg.n_kv_heads or cfg.n_heads) * cfg.head_dim
 
     def n(*shape):
         return bf16_round(torch.randn(*shape, generator=g) * 0.02).to(dtype)
@@ -85,8 +89,8 @@ def init_base_weights(cfg: OracleConfig, seed: int = 1234, dtype=torch.float32) 
     for l in range(cfg.n_layers):
         p = f"model.layers.{l}."
         w[p + "self_attn.q_proj.weight"] = n(d, d)
-        w[p + "self_attn.k_proj.weight"] = n(d, d)
-        w[p + "self_attn.v_proj.weight"] = n(d, d)
+        w[p + "self_attn.k_proj.weight"] = n(dkv, d)
+        w[p + "self_attn.v_proj.weight"] = n(dkv, d)
         w[p + "self_attn.o_proj.weight"] = n(d, d)
         w[p + "mlp.gate_proj.weight"] = n(F, d)
         w[p + "mlp.up_proj.weight"] = n(F, d)
@@ -103,12 +107,13 @@ def init_lora(cfg: OracleConfig, seed: int = 4321) -> Dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)
     out = {}
     d, r = cfg.hidden, cfg.lora_r
+    dkv = (cfg.n_kv_heads or cfg.n_heads) * cfg.head_dim
     bound = 1.0 / math.sqrt(d)  # gain sqrt(2/(1+5)) * sqrt(3/fan_in) = 1/sqrt(fan_in)
     for l in range(cfg.n_layers):
         for t in cfg.lora_target:
             p = f"model.layers.{l}.self_attn.{t}."
             out[p + "lora_A.weight"] = (torch.rand(r, d, generator=g) * 2 - 1) * bound
-            out[p + "lora_B.weight"] = torch.zeros(d, r)
+            out[p + "lora_B.weight"] = torch.zeros(d if t == "q_proj" else dkv, r)
     return out
 
 
@@ -164,17 +169,51 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor
     return p @ v
 
 
-def lora_linear(x: torch.Tensor, w: torch.Tensor, a: Optional[torch.Tensor], b: Optional[torch.Tensor], scale: float):
-    # peft 0.5.0 lora.Linear.forward (dropout p=0): result = F.linear(x, W) + lora_B(lora_A(x)) * scaling
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def dropout_key(seed: int, fwd_count: int, layer: int, rank: int = 0) -> int:
+    """Key of the LoRA-dropout masks of one (forward pass, layer) — the same integer arithmetic as dropout_key() in
+    datatunerx_b200/csrc/trainer.cu (torch's own Philox stream cannot be reproduced on the device; what the reference fixes
+    is the distribution: independent Bernoulli(1-p) keep masks per wrapped module, kept values scaled by 1/(1-p))."""
+    x = (seed * 0xD1B54A32D192ED03 + fwd_count * 0x100000001B3 + layer * 0x9E3779B1 + rank * 0xC2B2AE3D27D4EB4F) & _M64
+    with np.errstate(over="ignore"):
+        return int(_splitmix64(np.array([x], dtype=np.uint64))[0])
+
+
+def dropout_mask(key: int, target: int, n_rows: int, d: int, p: float) -> torch.Tensor:
+    """keep[m, c] = splitmix64(key + target*G + m*d + c) >> 40 >= p * 2^24   (elementwise.cu drop_keep)."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(n_rows * d, dtype=np.uint64) + np.uint64((key + target * 0x9E3779B97F4A7C15) & _M64)
+        u = (_splitmix64(idx) >> np.uint64(40)).astype(np.int64)
+    thresh = min(int(p * 16777216.0), 16777215)
+    return torch.from_numpy((u >= thresh).astype(np.float32)).view(n_rows, d)
+
+
+def lora_linear(x: torch.Tensor, w: torch.Tensor, a: Optional[torch.Tensor], b: Optional[torch.Tensor], scale: float,
+                mask: Optional[torch.Tensor] = None, p: float = 0.0):
+    # peft 0.5.0 lora.Linear.forward: result = F.linear(x, W) + lora_B(lora_A(lora_dropout(x))) * scaling
     y = x @ w.t()
     if a is not None:
-        y = y + (x @ a.t()) @ b.t() * scale
+        xd = x if mask is None else x * mask.view(x.shape) / (1.0 - p)
+        y = y + (xd @ a.t()) @ b.t() * scale
     return y
 
 
-def forward_logits(cfg: OracleConfig, w: Dict[str, torch.Tensor], lora: Dict[str, torch.Tensor], ids: torch.Tensor):
+def forward_logits(cfg: OracleConfig, w: Dict[str, torch.Tensor], lora: Dict[str, torch.Tensor], ids: torch.Tensor,
+                   drop_ctx: Optional[Tuple[int, int]] = None):
+    """drop_ctx = (fwd_count, rank) enables LoRA dropout with the counter-based masks; None = eval mode / p = 0."""
     B, S = ids.shape
     H, D = cfg.n_heads, cfg.head_dim
+    Hkv = cfg.n_kv_heads or H
+    targets = [t for t in ("q_proj", "k_proj", "v_proj") if t in cfg.lora_target]
     scale = cfg.lora_alpha / cfg.lora_r
     cos, sin = rope_cos_sin(S, D, cfg.rope_theta)
     x = w["model.embed_tokens.weight"][ids.long()]
@@ -185,12 +224,19 @@ def forward_logits(cfg: OracleConfig, w: Dict[str, torch.Tensor], lora: Dict[str
         def proj(name):
             a = lora.get(p + f"self_attn.{name}.lora_A.weight")
             b = lora.get(p + f"self_attn.{name}.lora_B.weight")
-            return lora_linear(h, w[p + f"self_attn.{name}.weight"], a, b, scale)
+            mask = None
+            if a is not None and drop_ctx is not None and cfg.lora_dropout > 0:
+                key = dropout_key(cfg.seed, drop_ctx[0], l, drop_ctx[1])
+                mask = dropout_mask(key, targets.index(name), B * S, cfg.hidden, cfg.lora_dropout)
+            return lora_linear(h, w[p + f"self_attn.{name}.weight"], a, b, scale, mask, cfg.lora_dropout)
 
         q = proj("q_proj").view(B, S, H, D).transpose(1, 2)
-        k = proj("k_proj").view(B, S, H, D).transpose(1, 2)
-        v = proj("v_proj").view(B, S, H, D).transpose(1, 2)
+        k = proj("k_proj").view(B, S, Hkv, D).transpose(1, 2)
+        v = proj("v_proj").view(B, S, Hkv, D).transpose(1, 2)
         q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
+        if Hkv != H:  # HF repeat_kv: kv head i serves query heads i*g .. (i+1)*g-1
+            k = k.repeat_interleave(H // Hkv, dim=1)
+            v = v.repeat_interleave(H // Hkv, dim=1)
         o = attention(q, k, v).transpose(1, 2).reshape(B, S, H * D)
         x = x + o @ w[p + "self_attn.o_proj.weight"].t()
         h = rmsnorm(x, w[p + "post_attention_layernorm.weight"], cfg.rms_eps)
@@ -263,17 +309,24 @@ class OracleTrainer:
         self.v = {k: torch.zeros_like(v) for k, v in self.lora.items()}
         self.opt_step = 0
         self.micro = 0
+        self.fwd_count = 0  # mirrors dtx_trainer::fwd_count (every forward pass, training or eval, advances it)
+        self.rank_of_next = 0
         self._acc: Dict[str, torch.Tensor] = {}
 
-    def loss_and_grads(self, ids: np.ndarray, labels: np.ndarray) -> Tuple[float, Dict[str, torch.Tensor]]:
+    def loss_and_grads(self, ids: np.ndarray, labels: np.ndarray, rank: int = 0,
+                       fwd_count: Optional[int] = None) -> Tuple[float, Dict[str, torch.Tensor]]:
         for p in self.lora.values():
             p.grad = None
-        logits = forward_logits(self.cfg, self.w, self.lora, torch.from_numpy(np.asarray(ids)).long())
+        if fwd_count is None:
+            self.fwd_count += 1
+            fwd_count = self.fwd_count
+        logits = forward_logits(self.cfg, self.w, self.lora, torch.from_numpy(np.asarray(ids)).long(), (fwd_count, rank))
         loss = causal_lm_loss(logits, torch.from_numpy(np.asarray(labels)).long())
         loss.backward()
         return float(loss.detach()), {k: p.grad.detach().clone() for k, p in self.lora.items()}
 
     def eval_loss(self, ids: np.ndarray, labels: np.ndarray) -> float:
+        self.fwd_count += 1
         with torch.no_grad():
             logits = forward_logits(self.cfg, self.w, self.lora, torch.from_numpy(np.asarray(ids)).long())
             return float(causal_lm_loss(logits, torch.from_numpy(np.asarray(labels)).long()))
@@ -286,11 +339,13 @@ class OracleTrainer:
         assert len(batches) == self.world * cfg.grad_accum
         acc = {k: torch.zeros_like(v) for k, v in self.lora.items()}
         losses = []
-        for ids, labels in batches:
-            loss, g = self.loss_and_grads(ids, labels)
+        base = self.fwd_count
+        for i, (ids, labels) in enumerate(batches):  # rank-major: rank i // grad_accum, its (i % grad_accum)-th forward pass
+            loss, g = self.loss_and_grads(ids, labels, rank=i // cfg.grad_accum, fwd_count=base + (i % cfg.grad_accum) + 1)
             losses.append(loss)
             for k in acc:
                 acc[k] += g[k]
+        self.fwd_count = base + cfg.grad_accum
         for k in acc:
             acc[k] /= len(batches)
         total_norm = math.sqrt(sum(float((g.double() ** 2).sum()) for g in acc.values()))

@@ -182,7 +182,7 @@ def check_rope(B=2, S=256, H=2, D=128):
     orig = qkv.clone()
     cs = torch.empty(S, D // 2, 2, dtype=torch.float32, device=DEV)
     ok(lib.dtx_rope_table(P(cs), S, D, 10000.0, STREAM()))
-    ok(lib.dtx_rope_qk(P(qkv), P(cs), B, S, H, D, 0, STREAM()))
+    ok(lib.dtx_rope_qk(P(qkv), P(cs), B, S, H, H, D, 0, STREAM()))
     torch.cuda.synchronize()
     cos, sin = O.rope_cos_sin(S, D, 10000.0)
     cos, sin = cos.to(DEV), sin.to(DEV)
@@ -193,7 +193,7 @@ def check_rope(B=2, S=256, H=2, D=128):
     e = max(rel_err(got[:, :, 0], refq), rel_err(got[:, :, 1], refk))
     assert e < 4e-3, f"rope {e}"
     assert torch.equal(got[:, :, 2], x[:, :, 2]), "rope must not touch v"
-    ok(lib.dtx_rope_qk(P(qkv), P(cs), B, S, H, D, 1, STREAM()))
+    ok(lib.dtx_rope_qk(P(qkv), P(cs), B, S, H, H, D, 1, STREAM()))
     torch.cuda.synchronize()
     e_inv = rel_err(qkv, orig)
     assert e_inv < 8e-3, f"rope inverse round trip {e_inv}"
@@ -214,6 +214,30 @@ def check_swiglu(M=257, F=768):
     e_f, e_b = rel_err(act, ref), rel_err(dgu, g.grad)
     assert e_f < 4e-3 and e_b < 4e-3, (e_f, e_b)
     return {"fwd": e_f, "bwd": e_b}
+
+
+def check_lora_dropout(M=300, d=256, nt=2, p=0.1):
+    """Counter-based dropout masks: the device kernels and the oracle's numpy restatement agree element for element."""
+    lib = L.load()
+    key = O.dropout_key(42, 5, 3, 0)
+    h = _rand(M, d, seed=21)
+    hd = torch.empty(M, nt * d, dtype=torch.bfloat16, device=DEV)
+    ok(lib.dtx_lora_dropout_fwd(P(h), P(hd), M, d, nt, p, C.c_uint64(key), STREAM()))
+    g = _rand(M, nt * d, seed=22)
+    dh0 = _rand(M, d, seed=23)
+    dh = dh0.clone()
+    ok(lib.dtx_lora_dropout_bwd_add(P(dh), P(g), M, d, nt, p, C.c_uint64(key), STREAM()))
+    torch.cuda.synchronize()
+    ref_add = torch.zeros(M, d, device=DEV)
+    for ti in range(nt):
+        mask = O.dropout_mask(key, ti, M, d, p).to(DEV)
+        got = hd[:, ti * d:(ti + 1) * d].float()
+        assert torch.equal(got != 0, (mask != 0) & (h.float() != 0)), f"keep pattern of target {ti} differs from the oracle"
+        assert rel_err(got, h.float() * mask / (1 - p)) < 4e-3
+        ref_add += g[:, ti * d:(ti + 1) * d].float() * mask / (1 - p)
+    e = rel_err(dh, dh0.float() + ref_add)
+    assert e < 4e-3, f"dropout backward {e}"
+    return {"keep_rate": float((hd != 0).float().mean()), "bwd": e}
 
 
 def check_embedding(M=500, d=256, V=1000):
@@ -278,24 +302,28 @@ def check_adamw(n=100003 * 4):
     return out
 
 
-def _attn_ref(qkv, B, S, H, D):
-    x = qkv.float().view(B, S, 3, H, D)
-    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+def _attn_ref(qkv, B, S, H, D, Hkv=None):
+    Hkv = Hkv or H
+    x = qkv.float().view(B, S, H + 2 * Hkv, D)
+    q = x[:, :, :H].transpose(1, 2)
+    k = x[:, :, H:H + Hkv].transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
+    v = x[:, :, H + Hkv:].transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
     scores = q @ k.transpose(-1, -2) / math.sqrt(D)
     mask = torch.full((S, S), float("-inf"), device=qkv.device).triu(1)
     p = torch.softmax(scores + mask, dim=-1)
     return (p @ v).transpose(1, 2).reshape(B * S, H * D), torch.logsumexp(scores + mask, dim=-1)
 
 
-def check_attn_fwd(B=2, S=256, H=2):
+def check_attn_fwd(B=2, S=256, H=2, Hkv=None):
     lib = L.load()
     D = 128
-    qkv = _rand(B * S, 3 * H * D, seed=11)
+    Hkv = Hkv or H
+    qkv = _rand(B * S, (H + 2 * Hkv) * D, seed=11)
     out = torch.full((B * S, H * D), float("nan"), dtype=torch.bfloat16, device=DEV)
     lse2 = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
-    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, 1.0 / math.sqrt(D), STREAM()))
+    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, 1.0 / math.sqrt(D), STREAM()))
     torch.cuda.synchronize()
-    ref, lse = _attn_ref(qkv, B, S, H, D)
+    ref, lse = _attn_ref(qkv, B, S, H, D, Hkv)
     e = rel_err(out, ref)
     e_l = max_err(lse2 * math.log(2.0), lse)
     assert e < 8e-3, f"attn fwd {e}"
@@ -303,40 +331,43 @@ def check_attn_fwd(B=2, S=256, H=2):
     return {"out": e, "lse": e_l}
 
 
-def check_attn_bwd(B=2, S=256, H=2):
+def check_attn_bwd(B=2, S=256, H=2, Hkv=None):
     lib = L.load()
     D = 128
-    qkv = _rand(B * S, 3 * H * D, seed=12)
+    Hkv = Hkv or H
+    qkv = _rand(B * S, (H + 2 * Hkv) * D, seed=12)
     dout = _rand(B * S, H * D, seed=13)
     out = torch.empty(B * S, H * D, dtype=torch.bfloat16, device=DEV)
     lse2 = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
     delta = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
-    dqkv = torch.full((B * S, 3 * H * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dqkv = torch.full((B * S, (H + 2 * Hkv) * D), float("nan"), dtype=torch.bfloat16, device=DEV)
     sc = 1.0 / math.sqrt(D)
-    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, sc, STREAM()))
-    ok(lib.dtx_attn_bwd(P(qkv), P(out), P(dout), P(lse2), P(delta), P(dqkv), B, S, H, sc, STREAM()))
+    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, sc, STREAM()))
+    ok(lib.dtx_attn_bwd(P(qkv), P(out), P(dout), P(lse2), P(delta), P(dqkv), B, S, H, Hkv, sc, STREAM()))
     torch.cuda.synchronize()
     x = qkv.float().requires_grad_(True)
-    ref, _ = _attn_ref(x, B, S, H, D)
+    ref, _ = _attn_ref(x, B, S, H, D, Hkv)
     ref.backward(dout.float())
-    g = x.grad.view(B, S, 3, H, D)
-    got = dqkv.float().view(B, S, 3, H, D)
-    errs = {n: rel_err(got[:, :, i], g[:, :, i]) for i, n in enumerate(("dq", "dk", "dv"))}
+    g = x.grad.view(B, S, H + 2 * Hkv, D)
+    got = dqkv.float().view(B, S, H + 2 * Hkv, D)
+    sl = {"dq": slice(0, H), "dk": slice(H, H + Hkv), "dv": slice(H + Hkv, H + 2 * Hkv)}
+    errs = {n: rel_err(got[:, :, s_], g[:, :, s_]) for n, s_ in sl.items()}
     for n, e in errs.items():
         assert e < 1.5e-2, f"attn bwd {n} {e}"
     return errs
 
 
-def tiny_configs(S=256, B=2, steps=20, L_layers=2, vocab=2048):
-    ocfg = O.OracleConfig(vocab=vocab, hidden=256, n_layers=L_layers, n_heads=2, ffn=768, lora_r=16, lora_alpha=32.0, lr=1e-3,
-                          total_steps=steps)
-    mc = L.ModelConfig(vocab=vocab, hidden=256, n_layers=L_layers, n_heads=2, ffn=768)
-    tc = L.TrainConfig(micro_batch=B, seq_len=S, total_steps=steps, lora_r=16, lora_alpha=32.0, lora_dropout=0.0, lr=1e-3)
+def tiny_configs(S=256, B=2, steps=20, L_layers=2, vocab=2048, heads=2, kv_heads=None, dropout=0.0, targets=("q_proj", "v_proj")):
+    ocfg = O.OracleConfig(vocab=vocab, hidden=128 * heads, n_layers=L_layers, n_heads=heads, n_kv_heads=kv_heads, ffn=768, lora_r=16,
+                          lora_alpha=32.0, lr=1e-3, total_steps=steps, lora_dropout=dropout, lora_target=tuple(targets))
+    mc = L.ModelConfig(vocab=vocab, hidden=128 * heads, n_layers=L_layers, n_heads=heads, n_kv_heads=kv_heads, ffn=768)
+    tc = L.TrainConfig(micro_batch=B, seq_len=S, total_steps=steps, lora_r=16, lora_alpha=32.0, lora_dropout=dropout, lr=1e-3,
+                       lora_target=tuple(targets))
     return ocfg, mc, tc
 
 
-def make_tiny_pair(S=256, B=2, steps=20, L_layers=2, vocab=2048):
-    ocfg, mc, tc = tiny_configs(S, B, steps, L_layers, vocab)
+def make_tiny_pair(S=256, B=2, steps=20, L_layers=2, vocab=2048, **kw):
+    ocfg, mc, tc = tiny_configs(S, B, steps, L_layers, vocab, **kw)
     w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
     tr = L.Trainer(mc, tc)
     tr.load_state_dict({k: v.numpy() for k, v in w.items()})
@@ -344,11 +375,12 @@ def make_tiny_pair(S=256, B=2, steps=20, L_layers=2, vocab=2048):
     return ocfg, O.OracleTrainer(ocfg, w, lora), tr
 
 
-def check_trainer_tiny(steps=10):
-    ocfg, orc, tr = make_tiny_pair(steps=steps)
+def check_trainer_tiny(steps=10, **kw):
+    ocfg, orc, tr = make_tiny_pair(steps=steps, **kw)
     S, B = tr.train.seq_len, tr.train.micro_batch
     ids, labels = O.synthetic_batch(0, 0, B, S, ocfg.vocab)
-    e_eval = abs(tr.eval_loss(ids, labels) - orc.eval_loss(ids, labels)) / orc.eval_loss(ids, labels)
+    ref_eval = orc.eval_loss(ids, labels)  # exactly one forward pass on each side (forward passes key the dropout masks)
+    e_eval = abs(tr.eval_loss(ids, labels) - ref_eval) / ref_eval
     assert e_eval < 1e-3, f"forward loss mismatch {e_eval}"
     worst_l = worst_g = 0.0
     trace = []
@@ -558,9 +590,12 @@ ALL = {
     "gemm_nn_bn64": lambda: check_gemm_nn(N=64, block_n=64), "gemm_tn": check_gemm_tn,
     "gemm_tn_nosplit": lambda: check_gemm_tn(split_k=1), "gemm_kext": check_gemm_kext, "gemm_ragged": check_gemm_ragged,
     "gemm_large": check_gemm_large, "gemm_single_cta": check_gemm_single_cta, "gemm_pair_vs_single": check_gemm_pair_vs_single, "rmsnorm": check_rmsnorm, "rmsnorm_small": lambda: check_rmsnorm(M=64, d=256),
-    "rope": check_rope, "swiglu": check_swiglu, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
+    "rope": check_rope, "swiglu": check_swiglu, "lora_dropout": check_lora_dropout, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
     "attn_bwd": check_attn_bwd, "attn_bwd_long": lambda: check_attn_bwd(B=1, S=1024, H=1),
+    "attn_gqa": lambda: {"fwd": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "bwd": check_attn_bwd(B=2, S=384, H=4, Hkv=1)},
+    "trainer_gqa": lambda: check_trainer_tiny(heads=4, kv_heads=2, targets=("q_proj", "k_proj", "v_proj")),
+    "trainer_dropout": lambda: check_trainer_tiny(dropout=0.1),
     "trainer_tiny": check_trainer_tiny, "trainer_unfused": check_trainer_unfused, "trainer_deterministic": check_trainer_deterministic,
     "trainer_grad_accum": check_trainer_grad_accum, "trainer_100_steps": check_trainer_100_steps,
     "worker_end_to_end": check_worker_end_to_end,

@@ -37,8 +37,8 @@ def test_no_cpu_fallback_create_fails_without_gpu(lib):
 
 def test_unsupported_configs_are_rejected_loudly(lib):
     from datatunerx_b200 import lib as L
-    with pytest.raises(L.DtxError):
-        L.Trainer(L.ModelConfig(vocab=256, hidden=256, n_layers=1, n_heads=2, ffn=256),
-                  L.TrainConfig(micro_batch=1, seq_len=128, total_steps=1, lora_dropout=0.1))
+    with pytest.raises(L.DtxError):  # head_dim != 128 is not implemented: rejected before any device work
+        L.Trainer(L.ModelConfig(vocab=256, hidden=256, n_layers=1, n_heads=4, head_dim=64, ffn=256),
+                  L.TrainConfig(micro_batch=1, seq_len=128, total_steps=1, lora_dropout=0.0))
     with pytest.raises(L.DtxError):
         L.TrainConfig(micro_batch=1, seq_len=128, total_steps=1, lora_target=("o_proj",)).to_c()

@@ -13,7 +13,8 @@ from oracle import llama_lora as O
 def _hf_model(cfg: O.OracleConfig, weights):
     from transformers import LlamaConfig, LlamaForCausalLM
     hc = LlamaConfig(vocab_size=cfg.vocab, hidden_size=cfg.hidden, intermediate_size=cfg.ffn,
-                     num_hidden_layers=cfg.n_layers, num_attention_heads=cfg.n_heads, num_key_value_heads=cfg.n_heads,
+                     num_hidden_layers=cfg.n_layers, num_attention_heads=cfg.n_heads,
+                     num_key_value_heads=cfg.n_kv_heads or cfg.n_heads,
                      max_position_embeddings=4096, rms_norm_eps=cfg.rms_eps, rope_theta=cfg.rope_theta,
                      tie_word_embeddings=False, attn_implementation="eager")
     m = LlamaForCausalLM(hc).float()
@@ -70,6 +71,30 @@ def test_oracle_matches_hf_llama_logits_loss_and_lora_grads():
     for key, mod in wrapped.items():
         assert torch.allclose(grads[key + "lora_A.weight"], mod.lora_A.grad, atol=1e-6, rtol=1e-4)
         assert torch.allclose(grads[key + "lora_B.weight"], mod.lora_B.grad, atol=1e-6, rtol=1e-4)
+
+
+def test_oracle_gqa_matches_hf_llama():
+    """grouped-query attention (n_kv_heads < n_heads: Mistral-7B, Llama-2-70B) against the installed HF model."""
+    cfg = O.OracleConfig(vocab=512, hidden=512, n_layers=1, n_heads=4, n_kv_heads=2, ffn=384, lora_r=8, lora_alpha=16.0)
+    w = O.init_base_weights(cfg, seed=17)
+    ids, labels = O.synthetic_batch(step=1, rank=0, batch=2, seq_len=48, vocab=cfg.vocab)
+    m = _hf_model(cfg, w)
+    t_ids, t_lab = torch.from_numpy(ids).long(), torch.from_numpy(labels).long()
+    with torch.no_grad():
+        out = m(input_ids=t_ids, labels=t_lab)
+        logits = O.forward_logits(cfg, w, {}, t_ids)
+    assert torch.allclose(logits, out.logits.float(), atol=2e-5, rtol=1e-4)
+    assert abs(float(O.causal_lm_loss(logits, t_lab)) - float(out.loss)) < 1e-5
+
+
+def test_dropout_masks_are_bernoulli_and_independent_per_module():
+    key = O.dropout_key(42, 3, 1, 0)
+    m0 = O.dropout_mask(key, 0, 512, 256, 0.1)
+    m1 = O.dropout_mask(key, 1, 512, 256, 0.1)
+    assert abs(float(m0.mean()) - 0.9) < 5e-3 and abs(float(m1.mean()) - 0.9) < 5e-3
+    assert abs(float((m0 * m1).mean()) - 0.81) < 5e-3                      # independent masks for q_proj and v_proj
+    assert not torch.equal(m0, O.dropout_mask(O.dropout_key(42, 4, 1, 0), 0, 512, 256, 0.1))  # fresh mask every forward pass
+    assert torch.equal(O.dropout_mask(key, 0, 512, 256, 0.0), torch.ones(512, 256))
 
 
 def test_adamw_clip_match_torch():
