@@ -88,6 +88,9 @@ int32_t dtx_lora_dropout_fwd(const void* h, void* hd, int32_t M, int32_t d, int3
 int32_t dtx_lora_dropout_bwd_add(void* dh, const void* g, int32_t M, int32_t d, int32_t nt, float p, uint64_t key, void* stream) {
   return rc(lora_dropout_bwd_add(static_cast<bf16*>(dh), static_cast<const bf16*>(g), M, d, nt, p, key, S(stream)));
 }
+int32_t dtx_nf4_roundtrip(void* w_bf16, int64_t n, void* stream) {
+  return rc(nf4_roundtrip_bf16(static_cast<bf16*>(w_bf16), n, S(stream)));
+}
 int32_t dtx_cross_entropy(const void* logits, int64_t ldl, const void* labels, void* shifted, void* n_valid, void* row_loss,
                           void* dlogits, int64_t ldd, void* loss_out, int32_t B, int32_t Sq, int32_t V, void* stream) {
   cudaError_t e = shift_labels(static_cast<const int32_t*>(labels), static_cast<int32_t*>(shifted), static_cast<int32_t*>(n_valid), B,

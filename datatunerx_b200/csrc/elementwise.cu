@@ -524,6 +524,64 @@ __global__ void cast2d_kernel(const float* __restrict__ src, long long lds, bf16
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// QLoRA base weights (cmd/tuning/train.py:224-230: BitsAndBytesConfig(load_in_4bit, nf4, no double quant), bitsandbytes
+// 0.41.3).  On a 180 GB B200 there is no reason to keep 7-13B frozen weights packed: the weights are replaced ONCE at load
+// time by dequant(quant(W)) — exactly the values bitsandbytes' 4-bit matmul multiplies with — and every GEMM keeps
+// running on resident bf16.  Block-wise: 64 consecutive elements share one fp32 absmax; codes are the 16 NF4 levels.
+// ------------------------------------------------------------------------------------------
+__constant__ float kNF4[16] = {-1.0f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f,
+                               -0.28444138169288635f, -0.18477343022823334f, -0.09105003625154495f, 0.0f,
+                               0.07958029955625534f, 0.16093020141124725f, 0.24611230194568634f, 0.33791524171829224f,
+                               0.44070982933044434f, 0.5626170039176941f, 0.7229568362236023f, 1.0f};
+__device__ __forceinline__ int nf4_code(float x) {  // nearest level (bitsandbytes dQuantizeNF4 decision tree = midpoints)
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < 15; ++i) c += (x > 0.5f * (kNF4[i] + kNF4[i + 1])) ? 1 : 0;
+  return c;
+}
+__global__ void nf4_roundtrip_kernel(bf16* __restrict__ w, long long nblocks) {
+  for (long long b = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; b < nblocks;
+       b += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4* p = reinterpret_cast<uint4*>(w + b * 64);
+    float v[64];
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float f[8];
+      bf16x8_to_f32(p[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i * 8 + j] = f[j];
+        amax = fmaxf(amax, fabsf(f[j]));
+      }
+    }
+    const float inv = amax > 0.f ? 1.0f / amax : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = kNF4[nf4_code(v[i * 8 + j] * inv)] * amax;
+      p[i] = f32_to_bf16x8(f);
+    }
+  }
+}
+// row-wise absmax int8 (the weight side of LLM.int8; the reference's runtime outlier decomposition is NOT reproduced)
+__global__ void int8_rowwise_roundtrip_kernel(bf16* __restrict__ w, int rows, int cols) {
+  const int row = blockIdx.x;
+  __shared__ float sh[32];
+  bf16* r = w + static_cast<long long>(row) * cols;
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) amax = fmaxf(amax, fabsf(__bfloat162float(r[i])));
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  amax = sh[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) amax = fmaxf(amax, sh[i]);
+  const float sc = amax > 0.f ? 127.0f / amax : 0.f, isc = amax / 127.0f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) r[i] = __float2bfloat16_rn(rintf(__bfloat162float(r[i]) * sc) * isc);
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -638,6 +696,16 @@ cudaError_t adamw_step(const AdamWArgs& a, cudaStream_t s) {
        reinterpret_cast<uintptr_t>(a.v)) & 15)
     return cudaErrorInvalidValue;
   adamw_kernel<<<grid_for(a.n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t nf4_roundtrip_bf16(bf16* w, int64_t n, cudaStream_t s) {
+  if (n % 64) return cudaErrorInvalidValue;
+  nf4_roundtrip_kernel<<<grid_for(n / 64, 128), 128, 0, s>>>(w, n / 64);
+  return cudaGetLastError();
+}
+cudaError_t int8_rowwise_roundtrip_bf16(bf16* w, int rows, int cols, cudaStream_t s) {
+  int8_rowwise_roundtrip_kernel<<<rows, 256, 0, s>>>(w, rows, cols);
   return cudaGetLastError();
 }
 

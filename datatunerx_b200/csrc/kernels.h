@@ -115,6 +115,9 @@ cudaError_t lora_dropout_bwd_add(bf16* dh, const bf16* g, int M, int d, int nt, 
 // fp32 -> bf16 with scale, strided 2-D (used to refresh the bf16 LoRA shadows)
 cudaError_t cast_f32_to_bf16_2d(const float* src, int64_t lds, bf16* dst, int64_t ldd, int rows, int cols, float scale,
                                 int transpose, cudaStream_t s);
+// w <- dequant(quant(w)) in place: NF4 with 64-element absmax blocks (bitsandbytes 4-bit, no double quantisation) / row-wise int8
+cudaError_t nf4_roundtrip_bf16(bf16* w, int64_t n, cudaStream_t s);
+cudaError_t int8_rowwise_roundtrip_bf16(bf16* w, int rows, int cols, cudaStream_t s);
 cudaError_t fill_normal_bf16(bf16* p, int64_t n, float std, uint64_t seed, cudaStream_t s);
 cudaError_t fill_const_bf16(bf16* p, int64_t n, float v, cudaStream_t s);
 

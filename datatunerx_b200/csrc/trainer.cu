@@ -883,6 +883,27 @@ int32_t dtx_init_random_weights(dtx_trainer* t, uint64_t seed) {
   return DTX_OK;
 }
 
+int32_t dtx_quantize_base(dtx_trainer* t, int32_t mode) {
+  // mode 4: NF4 (--quantization int4), mode 8: row-wise int8 (--quantization int8).  Applies to the decoder-layer Linear
+  // weights (bitsandbytes skips lm_head; embeddings and norms are never quantised).
+  if (!t) return DTX_ERR_INVALID;
+  if (!t->have_weights) return t->fail(DTX_ERR_STATE, "quantize_base: load the base weights first");
+  if (mode != 4 && mode != 8) return t->fail(DTX_ERR_INVALID, "quantize_base: mode must be 4 (nf4) or 8 (int8)");
+  cudaSetDevice(t->device);
+  const int64_t d = t->mc.hidden, F = t->mc.ffn, W = t->W;
+  cudaStream_t s = t->stream;
+  for (Layer& y : t->layers) {
+    struct { bf16* p; int64_t rows, cols; } m[4] = {{y.wqkv, W, d}, {y.wo, d, d}, {y.wgu, 2 * F, d}, {y.wdown, d, F}};
+    for (auto& w : m) {
+      if (mode == 4) CK(nf4_roundtrip_bf16(w.p, w.rows * w.cols, s), 1);
+      else CK(int8_rowwise_roundtrip_bf16(w.p, static_cast<int>(w.rows), static_cast<int>(w.cols), s), 1);
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "quantize_base: %s", cudaGetErrorString(e));
+  return DTX_OK;
+}
+
 int32_t dtx_init_lora(dtx_trainer* t, uint64_t seed) {
   if (!t) return DTX_ERR_INVALID;
   cudaSetDevice(t->device);

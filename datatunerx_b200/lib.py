@@ -45,11 +45,11 @@ class TrainCfg(C.Structure):
 # every symbol include/dtxtune.h declares (tests/test_abi.py checks the .so exports all of them)
 ABI_SYMBOLS = [
     "dtx_abi_version", "dtx_last_global_error", "dtx_last_error", "dtx_trainer_create", "dtx_trainer_destroy",
-    "dtx_get_nccl_unique_id", "dtx_load_tensor", "dtx_init_random_weights", "dtx_init_lora", "dtx_step",
+    "dtx_get_nccl_unique_id", "dtx_load_tensor", "dtx_init_random_weights", "dtx_init_lora", "dtx_quantize_base", "dtx_step",
     "dtx_step_device", "dtx_eval_loss", "dtx_export_adapter", "dtx_num_trainable", "dtx_launch_count",
     "dtx_last_step_ms", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
     "dtx_rope_table", "dtx_rope_qk", "dtx_swiglu_fwd", "dtx_swiglu_bwd", "dtx_lora_dropout_fwd", "dtx_lora_dropout_bwd_add",
-    "dtx_cross_entropy", "dtx_sumsq", "dtx_adamw",
+    "dtx_nf4_roundtrip", "dtx_cross_entropy", "dtx_sumsq", "dtx_adamw",
     "dtx_attn_fwd", "dtx_attn_bwd",
 ]
 
@@ -77,6 +77,8 @@ def load() -> C.CDLL:
     lib.dtx_load_tensor.argtypes = [vp, C.c_char_p, vp, i32, C.POINTER(i64), i32]
     lib.dtx_init_random_weights.argtypes = [vp, C.c_uint64]
     lib.dtx_init_lora.argtypes = [vp, C.c_uint64]
+    lib.dtx_quantize_base.argtypes = [vp, i32]
+    lib.dtx_nf4_roundtrip.argtypes = [vp, i64, vp]
     lib.dtx_step.argtypes = [vp, vp, vp, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
     lib.dtx_step_device.argtypes = [vp, vp, vp, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
     lib.dtx_eval_loss.argtypes = [vp, vp, vp, C.POINTER(f32)]
@@ -223,6 +225,10 @@ class Trainer:
 
     def init_random_weights(self, seed: int) -> None:
         check(self.lib.dtx_init_random_weights(self._h, seed), self._h)
+
+    def quantize_base(self, mode: str) -> None:
+        """`--quantization int4|int8`: W <- dequant(quant(W)) on the device (nf4 / row-wise int8), once."""
+        check(self.lib.dtx_quantize_base(self._h, {"int4": 4, "nf4": 4, "int8": 8}[mode]), self._h)
 
     def init_lora(self, seed: int) -> None:
         check(self.lib.dtx_init_lora(self._h, seed), self._h)

@@ -33,6 +33,15 @@ def load_model_config(model_dir: str) -> ModelConfig:
                        max_seq=cfg.get("max_position_embeddings", 4096))
 
 
+def check_attention_window(model_dir: str, seq_len: int) -> None:
+    """Mistral-style sliding-window attention equals plain causal attention while seq_len <= sliding_window (4096 for
+    Mistral-7B); longer sequences would need the windowed mask, which the native kernels do not implement."""
+    cfg = json.load(open(os.path.join(model_dir, "config.json")))
+    win = cfg.get("sliding_window")
+    if win is not None and seq_len > int(win):
+        raise ValueError(f"seq_len {seq_len} exceeds the model's sliding_window {win}: windowed attention is not implemented")
+
+
 def iter_safetensors(path: str) -> Iterator[Tuple[str, np.ndarray, bool]]:
     """Yields (name, array, is_bf16_bits).  bf16 tensors come back as uint16 bit patterns."""
     with open(path, "rb") as f:

@@ -39,8 +39,8 @@ def total_optimizer_steps(n_examples: int, world: int, batch: int, grad_accum: i
 
 
 def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], tokenizer=None) -> Optional[str]:
-    if a.quantization:
-        raise L.DtxError(-5, f"--quantization {a.quantization} (bitsandbytes path, train.py:224-234) is not implemented natively yet")
+    if a.quantization and a.quantization not in ("int4", "int8"):
+        raise L.DtxError(-1, f"--quantization {a.quantization}: expected int4 or int8 (cmd/tuning/train.py:224-234)")
     if tokenizer is None:
         from transformers import AutoTokenizer  # host-side tokenisation only
         tokenizer = AutoTokenizer.from_pretrained(a.model_name_or_path)
@@ -54,6 +54,7 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
 
     mc = model_io.load_model_config(a.model_name_or_path)
     seq_len = D.static_seq_len(cutoff_len)
+    model_io.check_attention_window(a.model_name_or_path, seq_len)
     B, GA = a.per_device_train_batch_size, max(1, a.gradient_accumulation_steps)
     total = total_optimizer_steps(len(dataset), world, B, GA, a.num_train_epochs, a.max_steps)
     tc = L.TrainConfig(micro_batch=B, seq_len=seq_len, total_steps=total, lora_r=a.lora_rank, lora_alpha=a.lora_alpha,
@@ -63,6 +64,8 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
     device = int(os.environ.get("DTX_DEVICE", rank))
     tr = L.Trainer(mc, tc, device=device, rank=rank, world=world, nccl_id=nccl_id)
     model_io.load_weights_into(tr, a.model_name_or_path)
+    if a.quantization:  # QLoRA: the frozen base sees nf4 / int8 round-tripped weights (train.py:224-234)
+        tr.quantize_base(a.quantization)
     tr.init_lora(a.seed)
     cb = LogCallback(a.output_dir, total, a.metrics_export_address, a.uid) if rank == 0 else None
 

@@ -97,6 +97,12 @@ DTX_API int32_t dtx_init_random_weights(dtx_trainer* t, uint64_t seed);
 /* peft 0.5.0 LoRA init on the host RNG-free path: A ~ kaiming-uniform(a=sqrt 5) from `seed`, B = 0. */
 DTX_API int32_t dtx_init_lora(dtx_trainer* t, uint64_t seed);
 
+/* `--quantization int4|int8` (cmd/tuning/train.py:224-234, bitsandbytes): replaces the decoder-layer Linear weights by
+ * dequant(quant(W)) once, on the device; mode 4 = NF4 with 64-element fp32 absmax blocks (no double quantisation: the exact
+ * values the reference's 4-bit matmul multiplies with), mode 8 = row-wise absmax int8 (weight side of LLM.int8 only).
+ * Call after the base weights are loaded.  The GEMMs keep running on resident bf16: 180 GB of HBM make packed storage moot. */
+DTX_API int32_t dtx_quantize_base(dtx_trainer* t, int32_t mode);
+
 /* ---- the hot path: one micro-batch of HF Trainer.training_step + (at the accumulation boundary)
  * all-reduce, clip, AdamW, scheduler (train.py:299; ds_config.json ZeRO-0).  input_ids / labels are
  * host int32 [micro_batch, seq_len]; labels use -100 for ignored positions and are NOT pre-shifted.
@@ -146,6 +152,7 @@ DTX_API int32_t dtx_swiglu_bwd(const void* dact, const void* gu, void* dgu, int3
 DTX_API int32_t dtx_lora_dropout_fwd(const void* h, void* hd, int32_t M, int32_t d, int32_t nt, float p, uint64_t key, void* stream);
 DTX_API int32_t dtx_lora_dropout_bwd_add(void* dh, const void* g, int32_t M, int32_t d, int32_t nt, float p, uint64_t key,
                                  void* stream);
+DTX_API int32_t dtx_nf4_roundtrip(void* w_bf16, int64_t n, void* stream);
 DTX_API int32_t dtx_cross_entropy(const void* logits_f32, int64_t ldl, const void* labels_unshifted, void* shifted_scratch,
                           void* n_valid_scratch, void* row_loss, void* dlogits_bf16, int64_t ldd, void* loss_out,
                           int32_t B, int32_t S, int32_t V, void* stream);

@@ -71,6 +71,35 @@ class OracleConfig:
         return OracleConfig(vocab=32000, hidden=4096, n_layers=32, n_heads=32, ffn=11008, **kw)
 
 
+NF4_LEVELS = np.array([-1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453, -0.28444138169288635,
+                       -0.18477343022823334, -0.09105003625154495, 0.0, 0.07958029955625534, 0.16093020141124725,
+                       0.24611230194568634, 0.33791524171829224, 0.44070982933044434, 0.5626170039176941, 0.7229568362236023,
+                       1.0], dtype=np.float32)
+
+
+def nf4_roundtrip(w: torch.Tensor, blocksize: int = 64) -> torch.Tensor:
+    """dequantize(quantize(w)) of bitsandbytes 0.41 `quantize_4bit(quant_type="nf4", blocksize=64)` without double
+    quantisation (cmd/tuning/train.py:224-230): per block of 64 consecutive elements absmax in fp32, x/absmax mapped to the
+    nearest of the 16 NF4 levels (the library's decision tree uses the midpoints), value = level * absmax.  The levels are the
+    published table of the QLoRA paper / bitsandbytes `create_normal_map`.  Result rounded to bf16 like the device copy."""
+    x = w.detach().float().numpy().reshape(-1, blocksize)
+    amax = np.abs(x).max(axis=1, keepdims=True).astype(np.float32)
+    inv = np.where(amax > 0, np.float32(1.0) / np.where(amax > 0, amax, 1), 0).astype(np.float32)
+    mids = (np.float32(0.5) * (NF4_LEVELS[:-1] + NF4_LEVELS[1:])).astype(np.float32)
+    code = (((x * inv)[..., None] > mids).sum(-1)).astype(np.int64)
+    out = NF4_LEVELS[code] * amax
+    return bf16_round(torch.from_numpy(out.astype(np.float32)).view(w.shape))
+
+
+QUANTIZED_SUFFIXES = ("q_proj.weight", "k_proj.weight", "v_proj.weight", "o_proj.weight", "gate_proj.weight", "up_proj.weight",
+                      "down_proj.weight")
+
+
+def quantize_base_nf4(weights: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """bitsandbytes load_in_4bit replaces every decoder nn.Linear (lm_head is skipped, embeddings/norms untouched)."""
+    return {k: (nf4_roundtrip(v) if k.endswith(QUANTIZED_SUFFIXES) else v) for k, v in weights.items()}
+
+
 def bf16_round(t: torch.Tensor) -> torch.Tensor:
     """Round to bf16 and back: both sides of a parity test start from bit-identical bf16 weights."""
     return t.to(torch.bfloat16).to(torch.float32)

@@ -240,6 +240,41 @@ def check_lora_dropout(M=300, d=256, nt=2, p=0.1):
     return {"keep_rate": float((hd != 0).float().mean()), "bwd": e}
 
 
+def check_nf4(n=64 * 5000):
+    """NF4 block quantise-dequantise on the device == the oracle's restatement of bitsandbytes' algorithm, bit for bit."""
+    lib = L.load()
+    w = _rand(n, scale=0.02, seed=31)
+    w[64:128] = 0  # an all-zero block
+    ref = O.nf4_roundtrip(w.float().cpu().view(-1, 64)).view(-1)
+    got = w.clone()
+    ok(lib.dtx_nf4_roundtrip(P(got), n, STREAM()))
+    torch.cuda.synchronize()
+    assert torch.equal(got.float().cpu(), ref), f"nf4 mismatch: {int((got.float().cpu() != ref).sum())} of {n}"
+    return {"distinct_levels": int(torch.unique((got.float() / got.float().view(-1, 64).abs().amax(1, keepdim=True).clamp(min=1e-30)).view(-1)).numel()),
+            "rel_quant_err": rel_err(got, w)}
+
+
+def check_trainer_qlora(steps=6):
+    """--quantization int4: native trainer with device-side NF4 round trip == oracle trained on nf4_roundtrip'ed weights."""
+    ocfg, mc, tc = tiny_configs(steps=steps)
+    w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
+    tr = L.Trainer(mc, tc)
+    tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+    tr.quantize_base("int4")
+    tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+    orc = O.OracleTrainer(ocfg, O.quantize_base_nf4(w), lora)
+    worst_l = worst_g = 0.0
+    for s_ in range(steps):
+        ids, labels = O.synthetic_batch(s_, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)
+        ref = orc.step([(ids, labels)])
+        loss, gn, _, _ = tr.step(ids, labels)
+        worst_l, worst_g = max(worst_l, abs(loss - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
+    tr.close()
+    plain = O.OracleTrainer(ocfg, w, lora).step([O.synthetic_batch(0, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)]).loss
+    assert worst_l < 1e-3 and worst_g < 3e-2, (worst_l, worst_g)
+    return {"loss": worst_l, "gnorm": worst_g, "loss_shift_vs_unquantized": abs(plain - ref.loss)}
+
+
 def check_embedding(M=500, d=256, V=1000):
     lib = L.load()
     table = _rand(V, d, seed=8)
@@ -590,7 +625,7 @@ ALL = {
     "gemm_nn_bn64": lambda: check_gemm_nn(N=64, block_n=64), "gemm_tn": check_gemm_tn,
     "gemm_tn_nosplit": lambda: check_gemm_tn(split_k=1), "gemm_kext": check_gemm_kext, "gemm_ragged": check_gemm_ragged,
     "gemm_large": check_gemm_large, "gemm_single_cta": check_gemm_single_cta, "gemm_pair_vs_single": check_gemm_pair_vs_single, "rmsnorm": check_rmsnorm, "rmsnorm_small": lambda: check_rmsnorm(M=64, d=256),
-    "rope": check_rope, "swiglu": check_swiglu, "lora_dropout": check_lora_dropout, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
+    "rope": check_rope, "swiglu": check_swiglu, "lora_dropout": check_lora_dropout, "nf4": check_nf4, "trainer_qlora": check_trainer_qlora, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
     "attn_bwd": check_attn_bwd, "attn_bwd_long": lambda: check_attn_bwd(B=1, S=1024, H=1),
     "attn_gqa": lambda: {"fwd": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "bwd": check_attn_bwd(B=2, S=384, H=4, Hkv=1)},

@@ -20,7 +20,7 @@ def test_gemm(name):
     _run(name)
 
 
-@pytest.mark.parametrize("name", ["rmsnorm", "rmsnorm_small", "rope", "swiglu", "lora_dropout", "embedding", "cross_entropy", "adamw"])
+@pytest.mark.parametrize("name", ["rmsnorm", "rmsnorm_small", "rope", "swiglu", "lora_dropout", "nf4", "embedding", "cross_entropy", "adamw"])
 def test_hbm_kernels(name):
     _run(name)
 
@@ -30,7 +30,7 @@ def test_attention(name):
     _run(name)
 
 
-@pytest.mark.parametrize("name", ["trainer_tiny", "trainer_gqa", "trainer_dropout", "trainer_unfused", "trainer_deterministic", "trainer_grad_accum", "trainer_100_steps",
+@pytest.mark.parametrize("name", ["trainer_tiny", "trainer_gqa", "trainer_dropout", "trainer_qlora", "trainer_unfused", "trainer_deterministic", "trainer_grad_accum", "trainer_100_steps",
                                   "worker_end_to_end"])
 def test_training_step(name):
     _run(name)
