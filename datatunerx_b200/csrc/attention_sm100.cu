@@ -282,14 +282,17 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
 }
 
 // ================================================================================================
-// backward: dQ
+// backward: dQ — two 128-row query tiles per CTA (groups) ping-ponging on one tensor pipe
 // ================================================================================================
-constexpr int DQ_SQ = 0;                    // 2 x [128 x 128B]
-constexpr int DQ_SDO = 32768;               // 2 x [128 x 128B]
-constexpr int DQ_SK = 65536;                // 3 x (2 x [64 x 128B])
-constexpr int DQ_SV = DQ_SK + 3 * 16384;    // 3 x (2 x [64 x 128B])
-constexpr int DQ_SDS = DQ_SV + 3 * 16384;   // [128 x 128B]
-constexpr int DQ_BAR = DQ_SDS + 16384;
+// Group g owns query rows [256*pair + 128*g, +128): while its four warps turn (S, dP) into dS, the tensor core works for the
+// other group (dQ accumulate, next S / dP).  Both groups read the same K/V ring, so each K/V block is staged once per 256
+// query rows.  The single-tile version of this kernel left the tensor pipe 25% busy (profiles/r01_*attn*).
+constexpr int DQ_SQ = 0;                    // 2 groups x (2 x [128 x 128B])
+constexpr int DQ_SDO = 65536;               // 2 groups x (2 x [128 x 128B])
+constexpr int DQ_SK = 131072;               // 2 slots x (2 x [64 x 128B])
+constexpr int DQ_SV = DQ_SK + 2 * 16384;    // 2 slots x (2 x [64 x 128B])
+constexpr int DQ_SDS = DQ_SV + 2 * 16384;   // 2 groups x [128 x 128B]
+constexpr int DQ_BAR = DQ_SDS + 2 * 16384;
 constexpr int DQ_SMEM = DQ_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -298,26 +301,29 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
-  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[3]*/, *bar_s = bars + 4 /*[2]*/, *bar_o = bars + 6, *bar_p = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[2]*/, *bar_s = bars + 3 /*[g]*/, *bar_o = bars + 5 /*[g]*/, *bar_p = bars + 7 /*[g]*/;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
 
-  const int nqb = p.S / 128;
-  const int qb = nqb - 1 - (blockIdx.x % nqb);
-  const int bh = blockIdx.x / nqb;
+  const int npair = (p.S + 255) / 256;
+  const int qp = npair - 1 - (blockIdx.x % npair);
+  const int bh = blockIdx.x / npair;
   const int h = bh % p.H, b = bh / p.H;
-  const int q0 = qb * 128;
   const int row_base = b * p.S;
-  const int n = (q0 + 128) / 64;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int hk = h / (p.H / p.Hkv);
   const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
+  const int q00 = qp * 256, q01 = qp * 256 + 128;
+  const int ng0 = (q00 + 128) / 64, ng1 = q01 < p.S ? (q01 + 128) / 64 : 0;  // KV blocks each group needs
+  const int n = max(ng0, ng1);
+  auto ngf = [&](int g) { return g ? ng1 : ng0; };
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmDO);
     for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
-    mbar_init(bar_p, 256);
+    mbar_init(&bar_p[0], 128);
+    mbar_init(&bar_p[1], 128);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr, 512);
@@ -325,141 +331,149 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t T_S = 0 /* +64*buf */, T_DP = 128 /* +64*buf */, T_DQ = 256;
+  // TMEM columns of group g: S 256g, dP 256g + 64, dQ 256g + 128
 
   if (warp == 8) {
-    {
-      const bool leader = elect_one();
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);
-      const uint32_t sQ = smem_u32(smem + DQ_SQ), sDO = smem_u32(smem + DQ_SDO), sK = smem_u32(smem + DQ_SK),
-                     sV = smem_u32(smem + DQ_SV), sDS = smem_u32(smem + DQ_SDS);
-      auto load_kv = [&](int j) {
-        const int slot = j % 3;
-        if (!leader) return;
-        mbar_arrive_expect_tx(&bar_kv[slot], 32768);
-        tma_load_2d(smem + DQ_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
-        tma_load_2d(smem + DQ_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
-        tma_load_2d(smem + DQ_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
-        tma_load_2d(smem + DQ_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
-      };
-      auto issue_s = [&](int j) {  // S(j) = Q K(j)^T and dP(j) = dO V(j)^T into buffer j & 1
-        const int slot = j % 3;
-        mbar_wait_backoff(&bar_kv[slot], (j / 3) & 1);
-        tc_fence_after();
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);
+    const uint32_t sQ = smem_u32(smem + DQ_SQ), sDO = smem_u32(smem + DQ_SDO), sK = smem_u32(smem + DQ_SK),
+                   sV = smem_u32(smem + DQ_SV), sDS = smem_u32(smem + DQ_SDS);
+    auto load_kv = [&](int j) {
+      const int slot = j & 1;
+      if (!leader) return;
+      mbar_arrive_expect_tx(&bar_kv[slot], 32768);
+      tma_load_2d(smem + DQ_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
+      tma_load_2d(smem + DQ_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
+      tma_load_2d(smem + DQ_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
+      tma_load_2d(smem + DQ_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
+    };
+    auto issue_s = [&](int g, int j) {  // S_g(j) = Q_g K(j)^T and dP_g(j) = dO_g V(j)^T
+      const int slot = j & 1;
+      mbar_wait_backoff(&bar_kv[slot], (j >> 1) & 1);
+      tc_fence_after();
 #pragma unroll
-        for (int k16 = 0; k16 < 8; ++k16)
-          if (leader) umma_bf16(tmem + T_S + (j & 1) * 64, umma_desc_kmajor(kmaj_addr(sQ, k16, 16384)),
-                    umma_desc_kmajor(kmaj_addr(sK + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+      for (int k16 = 0; k16 < 8; ++k16)
+        if (leader) umma_bf16(tmem + g * 256, umma_desc_kmajor(kmaj_addr(sQ + g * 32768, k16, 16384)),
+                              umma_desc_kmajor(kmaj_addr(sK + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k16 = 0; k16 < 8; ++k16)
-          if (leader) umma_bf16(tmem + T_DP + (j & 1) * 64, umma_desc_kmajor(kmaj_addr(sDO, k16, 16384)),
-                    umma_desc_kmajor(kmaj_addr(sV + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
-        if (leader) umma_commit(&bar_s[j & 1]);
-      };
-      if (leader) {
-        mbar_arrive_expect_tx(bar_q, 65536);
-        tma_load_2d(smem + DQ_SQ, &tmQ, bar_q, colQ, row_base + q0);
-        tma_load_2d(smem + DQ_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
-        tma_load_2d(smem + DQ_SDO, &tmDO, bar_q, h * HD, row_base + q0);
-        tma_load_2d(smem + DQ_SDO + 16384, &tmDO, bar_q, h * HD + 64, row_base + q0);
+      for (int k16 = 0; k16 < 8; ++k16)
+        if (leader) umma_bf16(tmem + g * 256 + 64, umma_desc_kmajor(kmaj_addr(sDO + g * 32768, k16, 16384)),
+                              umma_desc_kmajor(kmaj_addr(sV + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+      if (leader) umma_commit(&bar_s[g]);
+    };
+    if (leader) {
+      mbar_arrive_expect_tx(bar_q, ng1 > 0 ? 131072 : 65536);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (ngf(g) == 0) continue;
+        const int q0 = g ? q01 : q00;
+        tma_load_2d(smem + DQ_SQ + g * 32768, &tmQ, bar_q, colQ, row_base + q0);
+        tma_load_2d(smem + DQ_SQ + g * 32768 + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
+        tma_load_2d(smem + DQ_SDO + g * 32768, &tmDO, bar_q, h * HD, row_base + q0);
+        tma_load_2d(smem + DQ_SDO + g * 32768 + 16384, &tmDO, bar_q, h * HD + 64, row_base + q0);
       }
-      for (int j = 0; j < 3 && j < n; ++j) load_kv(j);
-      mbar_wait_backoff(bar_q, 0);
-      issue_s(0);
-      if (n > 1) issue_s(1);
-      for (int j = 0; j < n; ++j) {
-        mbar_wait_backoff(bar_p, j & 1);  // dS(j) is in smem; score buffers j&1 have been consumed
+    }
+    load_kv(0);
+    if (n > 1) load_kv(1);
+    mbar_wait_backoff(bar_q, 0);
+    issue_s(0, 0);
+    if (ng1 > 0) issue_s(1, 0);
+    for (int j = 0; j < n; ++j) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (j >= ngf(g)) continue;
+        mbar_wait_backoff(&bar_p[g], j & 1);  // dS_g(j) is in smem; group g's S / dP tiles have been consumed
         tc_fence_after();
-        const uint32_t kb = sK + (j % 3) * 16384;
+        const uint32_t kb = sK + (j & 1) * 16384;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          if (leader) umma_bf16(tmem + T_DQ, umma_desc_kmajor(sDS + kk * 32), umma_desc_mnmajor(kb + kk * 2048, 8192), idesc_dq,
-                    (j > 0 || kk > 0) ? 1u : 0u);
-        if (leader) umma_commit(bar_o);
-        if (j + 2 < n) issue_s(j + 2);
-        if (j + 3 < n) {
-          mbar_wait_backoff(bar_o, j & 1);  // dQ MMA(j) done: ring slot j % 3 is free
-          load_kv(j + 3);
-        }
+          if (leader) umma_bf16(tmem + g * 256 + 128, umma_desc_kmajor(sDS + g * 16384 + kk * 32), umma_desc_mnmajor(kb + kk * 2048, 8192),
+                                idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
+        if (leader) umma_commit(&bar_o[g]);
+        if (j + 1 < ngf(g)) issue_s(g, j + 1);
+      }
+      if (j + 2 < n) {  // ring slot j & 1 is free once both groups' dQ MMAs of block j have completed
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (j < ngf(g)) mbar_wait_backoff(&bar_o[g], j & 1);
+        load_kv(j + 2);
       }
     }
   } else {
-    // 8 compute warps: warps w and w+4 share the TMEM lanes (score rows) 32*(w&3)..+31 and split the 64 columns
-    const int rw = warp & 3, half = warp >> 2;
-    const int r = rw * 32 + (tid & 31);
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(rw * 32) << 16);
+    const int g = warp >> 2, w = warp & 3;
+    const int r = w * 32 + (tid & 31);
+    const int n_mine = ngf(g);
+    const int q0 = g ? q01 : q00;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(w * 32) << 16) + g * 256;
+    const uint32_t T_S = 0, T_DP = 64, T_DQ = 128;
     const int qrow = q0 + r;
-    const uint32_t sDS_addr = smem_u32(smem + DQ_SDS);
-    const size_t stat_idx = (static_cast<size_t>(b) * p.H + h) * p.S + qrow;
-    const float lse2 = p.lse2[stat_idx];
-    const float delta = p.delta[stat_idx];
-
-    for (int j = 0; j < n; ++j) {
+    const uint32_t sDS_addr = smem_u32(smem + DQ_SDS + g * 16384);
+    uint64_t *my_s = bar_s + g, *my_o = bar_o + g, *my_p = bar_p + g;
+    float lse2 = 0.f, delta = 0.f;
+    if (n_mine > 0) {
+      const size_t stat_idx = (static_cast<size_t>(b) * p.H + h) * p.S + qrow;
+      lse2 = p.lse2[stat_idx];
+      delta = p.delta[stat_idx];
+    }
+    for (int j = 0; j < n_mine; ++j) {
       const int kv0 = j * 64;
-      mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
+      mbar_wait(my_s, j & 1);
       tc_fence_after();
-      uint32_t sv[32], dv[32], pk[16];
-      tmem_ld32(t_lane + T_S + (j & 1) * 64 + half * 32, sv);
-      tmem_ld32(t_lane + T_DP + (j & 1) * 64 + half * 32, dv);
-      tmem_ld_wait();
-      if (kv0 + 63 > q0) {  // diagonal blocks
+      const bool need_mask = (kv0 + 63 > q0);
+      uint32_t pk[32];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse2));
-          float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse2));
-          if (kv0 + half * 32 + e > qrow) p0 = 0.f;
-          if (kv0 + half * 32 + e + 1 > qrow) p1 = 0.f;
-          pk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta) * p.scale, p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale);
-        }
-      } else {
+      for (int half = 0; half < 2; ++half) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(t_lane + T_S + half * 32, sv);
+        tmem_ld32(t_lane + T_DP + half * 32, dv);
+        tmem_ld_wait();
+        if (need_mask) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse2));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse2));
-          pk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta) * p.scale, p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale);
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse2));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse2));
+            if (kv0 + half * 32 + e > qrow) p0 = 0.f;
+            if (kv0 + half * 32 + e + 1 > qrow) p1 = 0.f;
+            pk[half * 16 + (e >> 1)] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta) * p.scale,
+                                                   p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse2));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse2));
+            pk[half * 16 + (e >> 1)] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta) * p.scale,
+                                                   p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale);
+          }
         }
       }
-      if (j > 0) mbar_wait(bar_o, (j - 1) & 1);  // dQ MMA of block j-1 done: the dS buffer is free
+      if (j > 0) mbar_wait(my_o, (j - 1) & 1);  // dQ MMA of block j-1 done: the dS buffer is free
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8)
-        sts128(sDS_addr + sw128_offset(r, half * 4 + c8), pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+      for (int c8 = 0; c8 < 8; ++c8)
+        sts128(sDS_addr + sw128_offset(r, c8), pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive(my_p);
     }
-    mbar_wait(bar_o, (n - 1) & 1);
-    tc_fence_after();
-    // each thread stores columns [32*half, +32) and [64 + 32*half, +32): the rotary pair (i, i+64) stays in one thread
-    bf16* drow = p.dqkv + static_cast<size_t>(row_base + qrow) * p.W + colQ;
-    {
-      uint32_t lo[32], hi[32];
-      tmem_ld32(t_lane + T_DQ + half * 32, lo);
-      tmem_ld32(t_lane + T_DQ + 64 + half * 32, hi);
-      tmem_ld_wait();
-      if (p.rope_cs) {  // dq of the pre-rotary projection: apply R^T (inverse rotation)
-        const float2* cs = p.rope_cs + static_cast<size_t>(qrow) * 64 + half * 32;
+    if (n_mine > 0) {
+      mbar_wait(my_o, (n_mine - 1) & 1);
+      tc_fence_after();
+      bf16* drow = p.dqkv + static_cast<size_t>(row_base + qrow) * p.W + colQ;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float2 t = __ldg(cs + j);
-          const float x0 = __uint_as_float(lo[j]), x1 = __uint_as_float(hi[j]);
-          lo[j] = __float_as_uint(x0 * t.x + x1 * t.y);
-          hi[j] = __float_as_uint(x1 * t.x - x0 * t.y);
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + T_DQ + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
+          u.y = pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
+          u.z = pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5]));
+          u.w = pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7]));
+          reinterpret_cast<uint4*>(drow)[c * 4 + c8] = u;
         }
-      }
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        uint4 u, w;
-        u.x = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 0]), __uint_as_float(lo[c8 * 8 + 1]));
-        u.y = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 2]), __uint_as_float(lo[c8 * 8 + 3]));
-        u.z = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 4]), __uint_as_float(lo[c8 * 8 + 5]));
-        u.w = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 6]), __uint_as_float(lo[c8 * 8 + 7]));
-        w.x = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 0]), __uint_as_float(hi[c8 * 8 + 1]));
-        w.y = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 2]), __uint_as_float(hi[c8 * 8 + 3]));
-        w.z = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 4]), __uint_as_float(hi[c8 * 8 + 5]));
-        w.w = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 6]), __uint_as_float(hi[c8 * 8 + 7]));
-        reinterpret_cast<uint4*>(drow + half * 32)[c8] = u;
-        reinterpret_cast<uint4*>(drow + 64 + half * 32)[c8] = w;
       }
     }
   }
@@ -639,8 +653,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     // warps 0-3 write dV, warps 4-7 write dK (each thread one full 128-wide row)
     bf16* drow = p.dqkv + static_cast<size_t>(row_base + kvrow) * p.W + (half ? colK : colV);
     const uint32_t tcol = half ? T_DK : T_DV;
-    const bool rot = half && p.rope_cs;  // dK is the gradient of the post-rotary key: rotate back (R^T)
-    const float2* cs = p.rope_cs + static_cast<size_t>(kvrow) * 64;
+    const bool rot = false;  // (inverse rotary of dK here was measured slower than the separate HBM-bound kernel)
+    const float2* cs = nullptr;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t lo[32], hi[32];
@@ -713,6 +727,7 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
 
 cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (a.S % 128 || a.B <= 0 || a.H <= 0 || !a.delta || !a.lse || !a.dout || !a.dqkv) return cudaErrorInvalidValue;
+  if (a.rope_cs) return cudaErrorInvalidValue;  // inverse rotary in the store epilogues was measured slower than the separate kernel
   static bool init = false;
   if (!init) {
     cudaError_t e = set_smem(reinterpret_cast<const void*>(attn_dq_kernel), DQ_SMEM);
@@ -747,7 +762,7 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
     const long long grid = (warps * 32 + block - 1) / block;
     attn_delta_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(a.out, a.dout, a.delta, a.B, a.S, a.H);
   }
-  attn_dq_kernel<<<a.B * a.H * (a.S / 128), BWD_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, p);
+  attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), BWD_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, p);
   attn_dkv_kernel<<<a.B * Hkv * (a.S / 128), BWD_THREADS, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, p);
   return cudaGetLastError();
 }
