@@ -167,7 +167,7 @@ def time_dominant_gemm(torch, L):
 def run_native(args, rank: int, local_rank: int, world: int):
     import torch  # device memory for the resident batches, gloo rendezvous and the clock; no torch compute
     from datatunerx_b200 import lib as L
-    from oracle.llama_lora import synthetic_batch  # input generator shared with the parity tests (not compute)
+    from datatunerx_b200.tuning.synthetic import synthetic_batch
 
     from datatunerx_b200.dist import Rendezvous
     rv = Rendezvous()
