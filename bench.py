@@ -135,6 +135,11 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant GEMM at the bench shape, from the
+# ncu --set full capture summarised in profiles/r01_ncu_dominant_gemm_final.txt (1.371 GB read + 0.706 GB write).
+DOMINANT_GEMM_DRAM_BYTES = 2.0769e9
+
+
 def time_dominant_gemm(torch, L):
     """CUDA-event timing of the tcgen05 GEMM at the largest per-layer shape (gate|up projection)."""
     import ctypes as C
@@ -273,7 +278,7 @@ def run_native(args, rank: int, local_rank: int, world: int):
     }
     if gemm:
         line["roofline"] = {"bound": "tensor", "achieved": gemm["tflops"], "peak": peaks["burst"], "unit": "TFLOP/s",
-                            "frac": gemm["tflops"] / peaks["burst"], "traffic": None, "kernel": "gemm_kernel<256,NT,bf16>",
+                            "frac": gemm["tflops"] / peaks["burst"], "traffic": DOMINANT_GEMM_DRAM_BYTES, "traffic_src": "profiles/r01_ncu_dominant_gemm_final.txt (ncu --set full, dram read+write per launch; algorithmic 1.036e9)", "kernel": "gemm2_kernel<NT,bf16> (CTA-pair 256x256x64, cta_group::2)",
                             "shape_mnk": gemm["shape"], "ms": gemm["ms"], "peak_src": peaks["src"] + " bf16_tflops (burst)"}
     if args.cpu_baseline and args.config == "7b":
         threads = os.cpu_count() or 1
