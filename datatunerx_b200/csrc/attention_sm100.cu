@@ -33,8 +33,8 @@ bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint6
 namespace {
 
 constexpr int HD = 128;      // head dim
-constexpr int BWD_THREADS = 288;  // backward kernels: 8 compute warps (two per score row quadrant, splitting the columns) + issuer warp
-constexpr int ATT_THREADS = 160;  // 4 compute warps (one TMEM lane / score row per thread) + 1 issuer warp (TMA + MMA)
+constexpr int DKV_THREADS = 320;  // backward kernels: 8 compute warps + MMA issuer warp (8) + TMA loader warp (9)
+constexpr int ATT_THREADS = 192;  // 4 compute warps (one TMEM lane / score row per thread) + MMA issuer warp (4) + TMA loader warp (5)
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnKParams {
@@ -50,10 +50,9 @@ struct AttnKParams {
   const float2* rope_cs;  // [S][64] (cos, sin) or null
 };
 
-// issue `n16` UMMAs (K=16 each) walking both operands.  a/b step = byte advance per k16.
-// K-major operands made of 64-wide subtiles: k16 -> subtile (k16/4) + 32 B * (k16%4).
-__device__ __forceinline__ uint32_t kmaj_addr(uint32_t base, int k16, uint32_t subtile_bytes) {
-  return base + (k16 >> 2) * subtile_bytes + (k16 & 3) * 32;
+// descriptor low-word advance of the k16-th K=16 slice of a K-major operand made of 64-wide subtiles
+__device__ __forceinline__ constexpr uint32_t kmaj_lo(int k16, uint32_t subtile_bytes) {
+  return static_cast<uint32_t>(k16 >> 2) * (subtile_bytes >> 4) + static_cast<uint32_t>(k16 & 3) * 2u;
 }
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -65,11 +64,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // ================================================================================================
 // forward
 // ================================================================================================
+constexpr int FWD_NS = 4;                    // K/V ring depth: loads run FWD_NS - 2 blocks ahead of the score MMA
 constexpr int FWD_SQ = 0;                    // 2 x [128 x 128B]
-constexpr int FWD_SK = 32768;                // 3 x (2 x [64 x 128B])
-constexpr int FWD_SV = FWD_SK + 3 * 16384;   // 3 x (2 x [64 x 128B])
-constexpr int FWD_SP = FWD_SV + 3 * 16384;   // [128 x 128B]
-constexpr int FWD_BAR = FWD_SP + 16384;
+constexpr int FWD_SK = 32768;                // FWD_NS x (2 x [64 x 128B])
+constexpr int FWD_SV = FWD_SK + FWD_NS * 16384;   // FWD_NS x (2 x [64 x 128B])
+constexpr int FWD_BAR = FWD_SV + FWD_NS * 16384;
 constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -77,8 +76,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
-  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[3]*/, *bar_s = bars + 4 /*[2]*/, *bar_o = bars + 6, *bar_p = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[FWD_NS]*/, *bar_s = bars + 1 + FWD_NS /*[2]*/, *bar_o = bars + 3 + FWD_NS,
+           *bar_free = bars + 4 + FWD_NS /*[FWD_NS]*/, *bar_p = bars + 4 + 2 * FWD_NS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5 + 2 * FWD_NS);
+  static_assert(FWD_NS == 4, "the issue loop is unrolled over a 4-slot ring");
 
   const int nqb = p.S / 128;
   const int qb = nqb - 1 - (blockIdx.x % nqb);  // heavy (late) query blocks first
@@ -94,7 +95,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (tid == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 4 + 2 * FWD_NS; ++i) mbar_init(&bars[i], 1);
     mbar_init(bar_p, 128);
     fence_barrier_init();
   }
@@ -105,61 +106,65 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem = *tmem_ptr;
   const uint32_t T_S = 0 /* +64*buf */, T_O = 128;
 
-  if (warp == 4) {
-    // ------------------------------------------ issuer ------------------------------------------
-    {
-      const bool leader = elect_one();
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 0, 1);
-      const uint32_t sQ = smem_u32(smem + FWD_SQ), sK = smem_u32(smem + FWD_SK), sV = smem_u32(smem + FWD_SV),
-                     sP = smem_u32(smem + FWD_SP);
-      auto load_kv = [&](int j) {  // KV block j -> ring slot j % 3
-        const int slot = j % 3;
-        if (!leader) return;
+  if (warp == 5) {
+    // ------------------------------------------ TMA loader ------------------------------------------
+    if ((tid & 31) == 0) {
+      mbar_arrive_expect_tx(bar_q, 32768);
+      tma_load_2d(smem + FWD_SQ, &tmQ, bar_q, colQ, row_base + q0);
+      tma_load_2d(smem + FWD_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
+      for (int j = 0; j < n; ++j) {
+        const int slot = j & (FWD_NS - 1);
+        if (j >= FWD_NS) mbar_wait_backoff(&bar_free[slot], ((j >> 2) - 1) & 1);  // P V(j - 4) has read the slot
         mbar_arrive_expect_tx(&bar_kv[slot], 32768);
         tma_load_2d(smem + FWD_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
         tma_load_2d(smem + FWD_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
         tma_load_2d(smem + FWD_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
         tma_load_2d(smem + FWD_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
-      };
-      auto issue_s = [&](int j) {  // S(j) = Q K(j)^T into score buffer j & 1
-        const int slot = j % 3;
-        mbar_wait_backoff(&bar_kv[slot], (j / 3) & 1);
-        tc_fence_after();
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------ MMA issuer (lean: see attn_dkv_kernel) ------------------------------------------
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 0, 1);
+    const uint32_t loQ = umma_desc_lo(smem_u32(smem + FWD_SQ), 16), loK = umma_desc_lo(smem_u32(smem + FWD_SK), 16),
+                   loVm = umma_desc_lo(smem_u32(smem + FWD_SV), 8192);
+    auto issue_s = [&](const int slot, const int buf, const uint32_t parity) {  // S = Q K^T into score buffer buf
+      mbar_wait_backoff(&bar_kv[slot], parity);
+      tc_fence_after();
+      if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < 8; ++k16)
-          if (leader) umma_bf16(tmem + T_S + (j & 1) * 64, umma_desc_kmajor(kmaj_addr(sQ, k16, 16384)),
-                    umma_desc_kmajor(kmaj_addr(sK + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
-        if (leader) umma_commit(&bar_s[j & 1]);
-      };
-      if (leader) {
-        mbar_arrive_expect_tx(bar_q, 32768);
-        tma_load_2d(smem + FWD_SQ, &tmQ, bar_q, colQ, row_base + q0);
-        tma_load_2d(smem + FWD_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
+          umma_bf16(tmem + T_S + buf * 64, umma_desc_pack(loQ + kmaj_lo(k16, 16384)),
+                    umma_desc_pack(loK + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+        umma_commit(&bar_s[buf]);
       }
-      for (int j = 0; j < 3 && j < n; ++j) load_kv(j);
-      mbar_wait_backoff(bar_q, 0);
-      issue_s(0);
-      if (n > 1) issue_s(1);
-      for (int j = 0; j < n; ++j) {
-        mbar_wait_backoff(bar_p, j & 1);  // P(j) is in smem; score buffer j&1 and the O tile have been consumed
-        tc_fence_after();
-        const uint32_t vb = sV + (j % 3) * 16384;
+    };
+    mbar_wait_backoff(bar_q, 0);
+    issue_s(0, 0, 0);
+    if (n > 1) issue_s(1, 1, 0);
+    for (int base = 0; base < n; base += FWD_NS) {
+      const uint32_t rp = (base >> 2) & 1;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          if (leader) umma_bf16(tmem + T_O, umma_desc_kmajor(sP + kk * 32), umma_desc_mnmajor(vb + kk * 2048, 8192), idesc_o, kk > 0 ? 1u : 0u);
-        if (leader) umma_commit(bar_o);
-        if (j + 2 < n) issue_s(j + 2);
-        if (j + 3 < n) {
-          mbar_wait_backoff(bar_o, j & 1);  // P V(j) done: ring slot j % 3 is free
-          load_kv(j + 3);
+      for (int u = 0; u < FWD_NS; ++u) {
+        const int j = base + u;
+        if (j < n) {
+          mbar_wait_backoff(bar_p, u & 1);  // P(j) sits (bf16-packed) in the first 32 columns of score buffer j&1; the O tile has been consumed
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ts(tmem + T_O, tmem + T_S + (u & 1) * 64 + kk * 8, umma_desc_pack(loVm + u * 1024 + kk * 128), idesc_o, kk > 0 ? 1u : 0u);
+            umma_commit(bar_o);
+            umma_commit(&bar_free[u]);
+          }
+          if (j + 2 < n) issue_s((u + 2) & (FWD_NS - 1), u & 1, (u + 2 >= FWD_NS) ? (rp ^ 1u) : rp);
         }
       }
     }
   } else {
     // ------------------------------------------ softmax warps ------------------------------------------
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    const uint32_t sP_addr = smem_u32(smem + FWD_SP);
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
     float o[HD];
 #pragma unroll
@@ -219,10 +224,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       alpha_prev = alpha;
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8)
-        sts128(sP_addr + sw128_offset(tid, c8), pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
-      fence_proxy_async_smem();
+      tmem_st32(t_lane + T_S + (j & 1) * 64, pk);  // A operand of the P V MMA, read straight from tensor memory
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_p);
     }
@@ -289,20 +292,21 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
 // query rows.  The single-tile version of this kernel left the tensor pipe 25% busy (profiles/r01_*attn*).
 constexpr int DQ_SQ = 0;                    // 2 groups x (2 x [128 x 128B])
 constexpr int DQ_SDO = 65536;               // 2 groups x (2 x [128 x 128B])
-constexpr int DQ_SK = 131072;               // 2 slots x (2 x [64 x 128B])
-constexpr int DQ_SV = DQ_SK + 2 * 16384;    // 2 slots x (2 x [64 x 128B])
-constexpr int DQ_SDS = DQ_SV + 2 * 16384;   // 2 groups x [128 x 128B]
-constexpr int DQ_BAR = DQ_SDS + 2 * 16384;
+constexpr int DQ_NS = 3;                    // K/V ring depth
+constexpr int DQ_SK = 131072;               // DQ_NS slots x (2 x [64 x 128B])
+constexpr int DQ_SV = DQ_SK + DQ_NS * 16384;    // DQ_NS slots x (2 x [64 x 128B])
+constexpr int DQ_BAR = DQ_SV + DQ_NS * 16384;
 constexpr int DQ_SMEM = DQ_BAR + 256 + 1024;
 
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+__global__ void __launch_bounds__(DKV_THREADS, 1)
 attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                const __grid_constant__ CUtensorMap tmDO, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
-  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[2]*/, *bar_s = bars + 3 /*[g]*/, *bar_o = bars + 5 /*[g]*/, *bar_p = bars + 7 /*[g]*/;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[DQ_NS]*/, *bar_s = bars + 1 + DQ_NS /*[g]*/, *bar_o = bars + 3 + DQ_NS /*[g]*/,
+           *bar_free = bars + 5 + DQ_NS /*[DQ_NS]*/, *bar_p = bars + 5 + 2 * DQ_NS /*[g]*/;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8 + 2 * DQ_NS);
 
   const int npair = (p.S + 255) / 256;
   const int qp = npair - 1 - (blockIdx.x % npair);
@@ -321,7 +325,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmDO);
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5 + 2 * DQ_NS; ++i) mbar_init(&bars[i], 1);
     mbar_init(&bar_p[0], 128);
     mbar_init(&bar_p[1], 128);
     fence_barrier_init();
@@ -333,36 +337,9 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem = *tmem_ptr;
   // TMEM columns of group g: S 256g, dP 256g + 64, dQ 256g + 128
 
-  if (warp == 8) {
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);
-    const uint32_t sQ = smem_u32(smem + DQ_SQ), sDO = smem_u32(smem + DQ_SDO), sK = smem_u32(smem + DQ_SK),
-                   sV = smem_u32(smem + DQ_SV), sDS = smem_u32(smem + DQ_SDS);
-    auto load_kv = [&](int j) {
-      const int slot = j & 1;
-      if (!leader) return;
-      mbar_arrive_expect_tx(&bar_kv[slot], 32768);
-      tma_load_2d(smem + DQ_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
-      tma_load_2d(smem + DQ_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
-      tma_load_2d(smem + DQ_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
-      tma_load_2d(smem + DQ_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
-    };
-    auto issue_s = [&](int g, int j) {  // S_g(j) = Q_g K(j)^T and dP_g(j) = dO_g V(j)^T
-      const int slot = j & 1;
-      mbar_wait_backoff(&bar_kv[slot], (j >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int k16 = 0; k16 < 8; ++k16)
-        if (leader) umma_bf16(tmem + g * 256, umma_desc_kmajor(kmaj_addr(sQ + g * 32768, k16, 16384)),
-                              umma_desc_kmajor(kmaj_addr(sK + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
-#pragma unroll
-      for (int k16 = 0; k16 < 8; ++k16)
-        if (leader) umma_bf16(tmem + g * 256 + 64, umma_desc_kmajor(kmaj_addr(sDO + g * 32768, k16, 16384)),
-                              umma_desc_kmajor(kmaj_addr(sV + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
-      if (leader) umma_commit(&bar_s[g]);
-    };
-    if (leader) {
+  if (warp == 9) {
+    // ------------------------------------------ TMA loader ------------------------------------------
+    if ((tid & 31) == 0) {
       mbar_arrive_expect_tx(bar_q, ng1 > 0 ? 131072 : 65536);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -373,32 +350,70 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tma_load_2d(smem + DQ_SDO + g * 32768, &tmDO, bar_q, h * HD, row_base + q0);
         tma_load_2d(smem + DQ_SDO + g * 32768 + 16384, &tmDO, bar_q, h * HD + 64, row_base + q0);
       }
+      int slot = 0;
+      uint32_t par = 1;  // parity of the PREVIOUS ring round (first round: nothing to wait for)
+      for (int j = 0; j < n; ++j) {
+        if (j >= DQ_NS) mbar_wait_backoff(&bar_free[slot], par);  // both groups' MMAs of block j - DQ_NS have read the slot
+        mbar_arrive_expect_tx(&bar_kv[slot], 32768);
+        tma_load_2d(smem + DQ_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
+        tma_load_2d(smem + DQ_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
+        tma_load_2d(smem + DQ_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
+        tma_load_2d(smem + DQ_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
+        if (++slot == DQ_NS) { slot = 0; par ^= 1u; }
+      }
     }
-    load_kv(0);
-    if (n > 1) load_kv(1);
+  } else if (warp == 8) {
+    // ------------------------------------------ MMA issuer (lean: see attn_dkv_kernel) ------------------------------------------
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);
+    const uint32_t loQ = umma_desc_lo(smem_u32(smem + DQ_SQ), 16), loDO = umma_desc_lo(smem_u32(smem + DQ_SDO), 16),
+                   loK = umma_desc_lo(smem_u32(smem + DQ_SK), 16), loV = umma_desc_lo(smem_u32(smem + DQ_SV), 16),
+                   loKm = umma_desc_lo(smem_u32(smem + DQ_SK), 8192);
+    auto issue_s = [&](const int g, const int slot, const uint32_t parity) {  // S_g = Q_g K^T and dP_g = dO_g V^T for the block in `slot`
+      mbar_wait_backoff(&bar_kv[slot], parity);
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16)
+          umma_bf16(tmem + g * 256, umma_desc_pack(loQ + g * 2048 + kmaj_lo(k16, 16384)),
+                    umma_desc_pack(loK + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16)
+          umma_bf16(tmem + g * 256 + 64, umma_desc_pack(loDO + g * 2048 + kmaj_lo(k16, 16384)),
+                    umma_desc_pack(loV + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+        umma_commit(&bar_s[g]);
+      }
+    };
     mbar_wait_backoff(bar_q, 0);
-    issue_s(0, 0);
-    if (ng1 > 0) issue_s(1, 0);
-    for (int j = 0; j < n; ++j) {
+    issue_s(0, 0, 0);
+    if (ng1 > 0) issue_s(1, 0, 0);
+    uint32_t rp = 0;  // ring round parity of block `base`
+    for (int base = 0; base < n; base += DQ_NS) {
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (j >= ngf(g)) continue;
-        mbar_wait_backoff(&bar_p[g], j & 1);  // dS_g(j) is in smem; group g's S / dP tiles have been consumed
-        tc_fence_after();
-        const uint32_t kb = sK + (j & 1) * 16384;
+      for (int u = 0; u < DQ_NS; ++u) {
+        const int j = base + u;
+        if (j < n) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          if (leader) umma_bf16(tmem + g * 256 + 128, umma_desc_kmajor(sDS + g * 16384 + kk * 32), umma_desc_mnmajor(kb + kk * 2048, 8192),
-                                idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
-        if (leader) umma_commit(&bar_o[g]);
-        if (j + 1 < ngf(g)) issue_s(g, j + 1);
+          for (int g = 0; g < 2; ++g) {
+            if (j < ngf(g)) {
+              mbar_wait_backoff(&bar_p[g], j & 1);  // dS_g(j) sits bf16-packed in the first 32 columns of group g's S tile; dP consumed
+              tc_fence_after();
+              if (leader) {
+                const uint32_t acc0 = j > 0 ? 1u : 0u;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16_ts(tmem + g * 256 + 128, tmem + g * 256 + kk * 8, umma_desc_pack(loKm + u * 1024 + kk * 128), idesc_dq,
+                               kk > 0 ? 1u : acc0);
+                umma_commit(&bar_o[g]);
+              }
+              if (j + 1 < ngf(g)) issue_s(g, (u + 1) % DQ_NS, (u + 1 >= DQ_NS) ? (rp ^ 1u) : rp);
+            }
+          }
+          if (leader) umma_commit(&bar_free[u]);  // every MMA that reads ring slot u has been issued
+        }
       }
-      if (j + 2 < n) {  // ring slot j & 1 is free once both groups' dQ MMAs of block j have completed
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-          if (j < ngf(g)) mbar_wait_backoff(&bar_o[g], j & 1);
-        load_kv(j + 2);
-      }
+      rp ^= 1u;
     }
   } else {
     const int g = warp >> 2, w = warp & 3;
@@ -408,7 +423,6 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(w * 32) << 16) + g * 256;
     const uint32_t T_S = 0, T_DP = 64, T_DQ = 128;
     const int qrow = q0 + r;
-    const uint32_t sDS_addr = smem_u32(smem + DQ_SDS + g * 16384);
     uint64_t *my_s = bar_s + g, *my_o = bar_o + g, *my_p = bar_p + g;
     float lse2 = 0.f, delta = 0.f;
     if (n_mine > 0) {
@@ -448,11 +462,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
       }
-      if (j > 0) mbar_wait(my_o, (j - 1) & 1);  // dQ MMA of block j-1 done: the dS buffer is free
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8)
-        sts128(sDS_addr + sw128_offset(r, c8), pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
-      fence_proxy_async_smem();
+      tmem_st32(t_lane + T_S, pk);  // A operand of the dQ MMA, read straight from tensor memory
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(my_p);
     }
@@ -488,24 +499,25 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // ================================================================================================
 // backward: dK, dV
 // ================================================================================================
+constexpr int DKV_NS = 4;                      // Q / dO ring depth
 constexpr int DKV_SK = 0;                      // 2 x [128 x 128B]
 constexpr int DKV_SV = 32768;                  // 2 x [128 x 128B]
-constexpr int DKV_SQ = 65536;                  // 3 x (2 x [64 x 128B])
-constexpr int DKV_SDO = DKV_SQ + 3 * 16384;    // 3 x (2 x [64 x 128B])
-constexpr int DKV_SPT = DKV_SDO + 3 * 16384;   // [128 x 128B]  P^T
-constexpr int DKV_SDST = DKV_SPT + 16384;      // [128 x 128B]  dS^T
-constexpr int DKV_STAT = DKV_SDST + 16384;     // 3 x (lse2[64], delta[64]) fp32, filled by bulk copies with the Q ring
-constexpr int DKV_BAR = DKV_STAT + 3 * 512;
+constexpr int DKV_SQ = 65536;                  // DKV_NS x (2 x [64 x 128B])
+constexpr int DKV_SDO = DKV_SQ + DKV_NS * 16384;    // DKV_NS x (2 x [64 x 128B])
+constexpr int DKV_STAT = DKV_SDO + DKV_NS * 16384;  // DKV_NS x (lse2[64], delta[64]) fp32, filled by bulk copies with the Q ring
+constexpr int DKV_BAR = DKV_STAT + DKV_NS * 512;
 constexpr int DKV_SMEM = DKV_BAR + 256 + 1024;
 
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+__global__ void __launch_bounds__(DKV_THREADS, 1)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmQ64,
                 const __grid_constant__ CUtensorMap tmDO64, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_BAR);
-  uint64_t *bar_kv = bars, *bar_q = bars + 1 /*[3]*/, *bar_s = bars + 4 /*[2]*/, *bar_o = bars + 6, *bar_p = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t *bar_kv = bars, *bar_q = bars + 1 /*[DKV_NS]*/, *bar_s = bars + 1 + DKV_NS /*[2]*/, *bar_free = bars + 3 + DKV_NS /*[DKV_NS]*/,
+           *bar_p = bars + 3 + 2 * DKV_NS, *bar_fin = bars + 4 + 2 * DKV_NS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5 + 2 * DKV_NS);
+  static_assert(DKV_NS == 4, "the issue loop is unrolled over a 4-slot ring (slot and buffer indices are compile-time)");
 
   const int nkb = p.S / 128;
   const int kb = blockIdx.x % nkb;  // early KV blocks see the most query blocks: they come first
@@ -526,8 +538,9 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     tma_prefetch_desc(&tmKV128);
     tma_prefetch_desc(&tmQ64);
     tma_prefetch_desc(&tmDO64);
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 3 + 2 * DKV_NS; ++i) mbar_init(&bars[i], 1);
     mbar_init(bar_p, 256);
+    mbar_init(bar_fin, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr, 512);
@@ -537,17 +550,19 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
   const uint32_t tmem = *tmem_ptr;
   const uint32_t T_ST = 0 /* +64*buf */, T_DPT = 128 /* +64*buf */, T_DV = 256, T_DK = 384;
 
-  if (warp == 8) {
-    {
-      const bool leader = elect_one();
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_g = umma_idesc_bf16(128, 128, 0, 1);
-      const uint32_t sK = smem_u32(smem + DKV_SK), sV = smem_u32(smem + DKV_SV), sQ = smem_u32(smem + DKV_SQ),
-                     sDO = smem_u32(smem + DKV_SDO), sPT = smem_u32(smem + DKV_SPT), sDST = smem_u32(smem + DKV_SDST);
-      auto load_q = [&](int ii) {  // (head, query block) pair ii: Q, dO, lse2, delta -> ring slot ii % 3
-        const int slot = ii % 3, hq = ii / nq, qs = (i0 + ii % nq) * 64;
-        const int colQ = (hk * grp + hq) * HD;
-        if (!leader) return;
+  if (warp == 9) {
+    // ------------------------------------------ TMA loader ------------------------------------------
+    if ((tid & 31) == 0) {
+      mbar_arrive_expect_tx(bar_kv, 65536);
+      tma_load_2d(smem + DKV_SK, &tmKV128, bar_kv, colK, row_base + kv0);
+      tma_load_2d(smem + DKV_SK + 16384, &tmKV128, bar_kv, colK + 64, row_base + kv0);
+      tma_load_2d(smem + DKV_SV, &tmKV128, bar_kv, colV, row_base + kv0);
+      tma_load_2d(smem + DKV_SV + 16384, &tmKV128, bar_kv, colV + 64, row_base + kv0);
+      int hq = 0, qi = 0;  // (query head of the group, query block) of pair ii
+      for (int ii = 0; ii < n; ++ii) {
+        const int slot = ii & (DKV_NS - 1);
+        if (ii >= DKV_NS) mbar_wait_backoff(&bar_free[slot], ((ii >> 2) - 1) & 1);  // dV/dK MMAs of pair ii - 4 have read the slot
+        const int qs = (i0 + qi) * 64, colQ = (hk * grp + hq) * HD;
         mbar_arrive_expect_tx(&bar_q[slot], 32768 + 512);
         tma_load_2d(smem + DKV_SQ + slot * 16384, &tmQ64, &bar_q[slot], colQ, row_base + qs);
         tma_load_2d(smem + DKV_SQ + slot * 16384 + 8192, &tmQ64, &bar_q[slot], colQ + 64, row_base + qs);
@@ -555,66 +570,83 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
         tma_load_2d(smem + DKV_SDO + slot * 16384 + 8192, &tmDO64, &bar_q[slot], colQ + 64, row_base + qs);
         tma_load_1d(smem + DKV_STAT + slot * 512, g_lse + static_cast<size_t>(hq) * p.S + qs, 256, &bar_q[slot]);
         tma_load_1d(smem + DKV_STAT + slot * 512 + 256, g_delta + static_cast<size_t>(hq) * p.S + qs, 256, &bar_q[slot]);
-      };
-      auto issue_s = [&](int ii) {  // S^T = K Q^T, dP^T = V dO^T into buffer ii & 1
-        const int slot = ii % 3;
-        mbar_wait_backoff(&bar_q[slot], (ii / 3) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k16 = 0; k16 < 8; ++k16)
-          if (leader) umma_bf16(tmem + T_ST + (ii & 1) * 64, umma_desc_kmajor(kmaj_addr(sK, k16, 16384)),
-                    umma_desc_kmajor(kmaj_addr(sQ + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k16 = 0; k16 < 8; ++k16)
-          if (leader) umma_bf16(tmem + T_DPT + (ii & 1) * 64, umma_desc_kmajor(kmaj_addr(sV, k16, 16384)),
-                    umma_desc_kmajor(kmaj_addr(sDO + slot * 16384, k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
-        if (leader) umma_commit(&bar_s[ii & 1]);
-      };
-      if (leader) {
-        mbar_arrive_expect_tx(bar_kv, 65536);
-        tma_load_2d(smem + DKV_SK, &tmKV128, bar_kv, colK, row_base + kv0);
-        tma_load_2d(smem + DKV_SK + 16384, &tmKV128, bar_kv, colK + 64, row_base + kv0);
-        tma_load_2d(smem + DKV_SV, &tmKV128, bar_kv, colV, row_base + kv0);
-        tma_load_2d(smem + DKV_SV + 16384, &tmKV128, bar_kv, colV + 64, row_base + kv0);
+        if (++qi == nq) { qi = 0; ++hq; }
       }
-      for (int ii = 0; ii < 3 && ii < n; ++ii) load_q(ii);
-      mbar_wait_backoff(bar_kv, 0);
-      issue_s(0);
-      if (n > 1) issue_s(1);
-      for (int ii = 0; ii < n; ++ii) {
-        mbar_wait_backoff(bar_p, ii & 1);  // P^T / dS^T of block ii are in smem; score buffers ii&1 consumed
-        tc_fence_after();
-        const uint32_t first = (ii == 0) ? 0u : 1u;
-        const uint32_t qb_ = sQ + (ii % 3) * 16384, dob = sDO + (ii % 3) * 16384;
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------ MMA issuer ------------------------------------------
+    // Everything here is on the critical path of the tensor pipe (24 MMAs of 32-64 cycles per pair): the loop is unrolled
+    // over the ring so that slot / buffer / parity are immediates, and operand descriptors are one add off precomputed
+    // low words.  (r01: the first version rebuilt every 64-bit descriptor and ran ~490 instructions per pair on this single
+    // warp - the tensor pipe idled 2/3 of the time waiting for it, profiles/r01_ncu_attn_issue_bound.txt.)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_g = umma_idesc_bf16(128, 128, 0, 1);
+    const uint32_t loK = umma_desc_lo(smem_u32(smem + DKV_SK), 16), loV = umma_desc_lo(smem_u32(smem + DKV_SV), 16),
+                   loQ = umma_desc_lo(smem_u32(smem + DKV_SQ), 16), loDO = umma_desc_lo(smem_u32(smem + DKV_SDO), 16),
+                   loQm = umma_desc_lo(smem_u32(smem + DKV_SQ), 8192), loDOm = umma_desc_lo(smem_u32(smem + DKV_SDO), 8192);
+    auto issue_s = [&](const int slot, const int buf, const uint32_t parity) {  // S^T = K Q^T, dP^T = V dO^T into buffer buf
+      mbar_wait_backoff(&bar_q[slot], parity);
+      tc_fence_after();
+      if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          if (leader) umma_bf16(tmem + T_DV, umma_desc_kmajor(sPT + kk * 32), umma_desc_mnmajor(dob + kk * 2048, 8192), idesc_g,
-                    (first || kk > 0) ? 1u : 0u);
+        for (int k16 = 0; k16 < 8; ++k16)
+          umma_bf16(tmem + T_ST + buf * 64, umma_desc_pack(loK + kmaj_lo(k16, 16384)),
+                    umma_desc_pack(loQ + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          if (leader) umma_bf16(tmem + T_DK, umma_desc_kmajor(sDST + kk * 32), umma_desc_mnmajor(qb_ + kk * 2048, 8192), idesc_g,
-                    (first || kk > 0) ? 1u : 0u);
-        if (leader) umma_commit(bar_o);
-        if (ii + 2 < n) issue_s(ii + 2);
-        if (ii + 3 < n) {
-          mbar_wait_backoff(bar_o, ii & 1);  // dV/dK MMAs(ii) done: ring slot ii % 3 is free
-          load_q(ii + 3);
+        for (int k16 = 0; k16 < 8; ++k16)
+          umma_bf16(tmem + T_DPT + buf * 64, umma_desc_pack(loV + kmaj_lo(k16, 16384)),
+                    umma_desc_pack(loDO + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+        umma_commit(&bar_s[buf]);
+      }
+    };
+    mbar_wait_backoff(bar_kv, 0);
+    issue_s(0, 0, 0);
+    if (n > 1) issue_s(1, 1, 0);
+    for (int base = 0; base < n; base += DKV_NS) {
+      const uint32_t rp = (base >> 2) & 1;  // ring round parity of this group of four pairs
+#pragma unroll
+      for (int u = 0; u < DKV_NS; ++u) {
+        const int ii = base + u;
+        if (ii < n) {
+          // P^T / dS^T of pair ii sit bf16-packed in the score buffers u&1 themselves (query columns 0-31 -> TMEM columns
+          // 0-15, 32-63 -> 32-47): the A operands of the accumulating MMAs come straight from tensor memory.
+          mbar_wait_backoff(bar_p, u & 1);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t acc0 = ii > 0 ? 1u : 0u;
+            const uint32_t aP = tmem + T_ST + (u & 1) * 64, aDS = tmem + T_DPT + (u & 1) * 64;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ts(tmem + T_DV, aP + (kk >> 1) * 32 + (kk & 1) * 8, umma_desc_pack(loDOm + u * 1024 + kk * 128), idesc_g,
+                           kk > 0 ? 1u : acc0);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ts(tmem + T_DK, aDS + (kk >> 1) * 32 + (kk & 1) * 8, umma_desc_pack(loQm + u * 1024 + kk * 128), idesc_g,
+                           kk > 0 ? 1u : acc0);
+            umma_commit(&bar_free[u]);  // ring slot u may be refilled once these have read it
+          }
+          if (ii + 2 < n) issue_s((u + 2) & (DKV_NS - 1), u & 1, (u + 2 >= DKV_NS) ? (rp ^ 1u) : rp);
         }
       }
     }
+    // the compute warps do not follow the MMA completions phase by phase (parity waits are only safe one phase behind):
+    // a dedicated single-phase barrier reports that every MMA of this CTA has completed
+    if (leader) umma_commit(bar_fin);
   } else {
     // 8 compute warps: warps w and w+4 share the TMEM lanes (kv rows) 32*(w&3)..+31 and split the 64 query columns
     const int rw = warp & 3, half = warp >> 2;
     const int r = rw * 32 + (tid & 31);
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(rw * 32) << 16);
     const int kvrow = kv0 + r;
-    const uint32_t sPT_addr = smem_u32(smem + DKV_SPT), sDST_addr = smem_u32(smem + DKV_SDST);
+    int qi = 0;
     for (int ii = 0; ii < n; ++ii) {
-      const int qs = (i0 + ii % nq) * 64;
-      mbar_wait(&bar_q[ii % 3], (ii / 3) & 1);  // acquire the TMA-written row statistics of this ring slot
+      const int qs = (i0 + qi) * 64;
+      if (++qi == nq) qi = 0;
+      mbar_wait(&bar_q[ii % DKV_NS], (ii / DKV_NS) & 1);  // acquire the TMA-written row statistics of this ring slot
       mbar_wait(&bar_s[ii & 1], (ii >> 1) & 1);
       tc_fence_after();
-      const uint32_t st = smem_u32(smem + DKV_STAT + (ii % 3) * 512) + half * 128;
+      const uint32_t st = smem_u32(smem + DKV_STAT + (ii % DKV_NS) * 512) + half * 128;
       uint32_t sv[32], dv[32], ppk[16], dpk[16];
       tmem_ld32(t_lane + T_ST + (ii & 1) * 64 + half * 32, sv);
       tmem_ld32(t_lane + T_DPT + (ii & 1) * 64 + half * 32, dv);
@@ -637,18 +669,14 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
         dpk[e >> 1] = pack_bf16x2(dsv[0], dsv[1]);
         dpk[(e >> 1) + 1] = pack_bf16x2(dsv[2], dsv[3]);
       }
-      if (ii > 0) mbar_wait(bar_o, (ii - 1) & 1);  // dV/dK MMAs of block ii-1 done: P^T/dS^T buffers are free
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        const uint32_t off = sw128_offset(r, half * 4 + c8);
-        sts128(sPT_addr + off, ppk[4 * c8], ppk[4 * c8 + 1], ppk[4 * c8 + 2], ppk[4 * c8 + 3]);
-        sts128(sDST_addr + off, dpk[4 * c8], dpk[4 * c8 + 1], dpk[4 * c8 + 2], dpk[4 * c8 + 3]);
-      }
-      fence_proxy_async_smem();
+      // overwrite this thread's own (already loaded) score columns with the packed operands
+      tmem_st16(t_lane + T_ST + (ii & 1) * 64 + half * 32, ppk);
+      tmem_st16(t_lane + T_DPT + (ii & 1) * 64 + half * 32, dpk);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_p);
     }
-    mbar_wait(bar_o, (n - 1) & 1);
+    mbar_wait(bar_fin, 0);
     tc_fence_after();
     // warps 0-3 write dV, warps 4-7 write dK (each thread one full 128-wide row)
     bf16* drow = p.dqkv + static_cast<size_t>(row_base + kvrow) * p.W + (half ? colK : colV);
@@ -762,8 +790,8 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
     const long long grid = (warps * 32 + block - 1) / block;
     attn_delta_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(a.out, a.dout, a.delta, a.B, a.S, a.H);
   }
-  attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), BWD_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, p);
-  attn_dkv_kernel<<<a.B * Hkv * (a.S / 128), BWD_THREADS, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, p);
+  attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), DKV_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, p);
+  attn_dkv_kernel<<<a.B * Hkv * (a.S / 128), DKV_THREADS, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, p);
   return cudaGetLastError();
 }
 
