@@ -72,7 +72,8 @@ constexpr int FWD_BAR = FWD_SV + FWD_NS * 16384;
 constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnKParams p) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
@@ -232,7 +233,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(bar_o, (n - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l_run;
-    bf16* orow = p.out + static_cast<size_t>(row_base + qrow) * (p.H * HD) + h * HD;
+    // output tile -> bf16 -> 128B-swizzled staging tile (the Q buffer: its last reader, the final S MMA, has completed) -> TMA store
+    const uint32_t stage_addr = smem_u32(smem + FWD_SQ);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
@@ -243,11 +245,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = fmaf(o[c * 32 + c8 * 8 + e], alpha_prev, __uint_as_float(v[c8 * 8 + e])) * inv_l;
-        uint4 u;
-        u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-        u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
-        reinterpret_cast<uint4*>(orow)[c * 4 + c8] = u;
+        sts128(stage_addr + (c >> 1) * 16384 + sw128_offset(tid, (c & 1) * 4 + c8), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+               pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
       }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (tid == 0) {
+      tma_store_2d(&tmOut, smem + FWD_SQ, h * HD, row_base + q0);
+      tma_store_2d(&tmOut, smem + FWD_SQ + 16384, h * HD + 64, row_base + q0);
+      tma_store_commit();
+      tma_store_wait_read0();
     }
     if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = m_run + log2f(l_run);
   }
@@ -300,7 +308,7 @@ constexpr int DQ_SMEM = DQ_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(DKV_THREADS, 1)
 attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-               const __grid_constant__ CUtensorMap tmDO, const AttnKParams p) {
+               const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
@@ -470,21 +478,29 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (n_mine > 0) {
       mbar_wait(my_o, (n_mine - 1) & 1);
       tc_fence_after();
-      bf16* drow = p.dqkv + static_cast<size_t>(row_base + qrow) * p.W + colQ;
+      // dQ tile -> bf16 -> 128B-swizzled staging tile (this group's Q buffer: every MMA that read it has completed) -> TMA store
+      uint8_t* stage = smem + DQ_SQ + g * 32768;
+      const uint32_t stage_addr = smem_u32(stage);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld32(t_lane + T_DQ + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
-          u.y = pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
-          u.z = pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5]));
-          u.w = pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7]));
-          reinterpret_cast<uint4*>(drow)[c * 4 + c8] = u;
-        }
+        for (int c8 = 0; c8 < 4; ++c8)
+          sts128(stage_addr + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + c8),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1])),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3])),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5])),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7])));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + g, 128);
+      if (r == 0) {
+        tma_store_2d(&tmOut, stage, colQ, row_base + q0);
+        tma_store_2d(&tmOut, stage + 16384, colQ + 64, row_base + q0);
+        tma_store_commit();
+        tma_store_wait_read0();
       }
     }
   }
@@ -510,7 +526,7 @@ constexpr int DKV_SMEM = DKV_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(DKV_THREADS, 1)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmQ64,
-                const __grid_constant__ CUtensorMap tmDO64, const AttnKParams p) {
+                const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_BAR);
@@ -538,6 +554,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     tma_prefetch_desc(&tmKV128);
     tma_prefetch_desc(&tmQ64);
     tma_prefetch_desc(&tmDO64);
+    tma_prefetch_desc(&tmOut);
     for (int i = 0; i < 3 + 2 * DKV_NS; ++i) mbar_init(&bars[i], 1);
     mbar_init(bar_p, 256);
     mbar_init(bar_fin, 1);
@@ -678,40 +695,33 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     }
     mbar_wait(bar_fin, 0);
     tc_fence_after();
-    // warps 0-3 write dV, warps 4-7 write dK (each thread one full 128-wide row)
-    bf16* drow = p.dqkv + static_cast<size_t>(row_base + kvrow) * p.W + (half ? colK : colV);
+    // warps 0-3 hand dV, warps 4-7 dK to the TMA: each thread converts its 128-wide row to bf16 into a 128B-swizzled staging
+    // tile (the Q/dO ring is free now), one thread per matrix issues two bulk tensor stores.  (Direct 16-byte stores of one
+    // row per thread touch 32 different 128-byte lines per instruction: 16 % of the compute warps' time, lg_throttle.)
+    uint8_t* stage = smem + DKV_SQ + half * 32768;
+    const uint32_t stage_addr = smem_u32(stage);
     const uint32_t tcol = half ? T_DK : T_DV;
-    const bool rot = false;  // (inverse rotary of dK here was measured slower than the separate HBM-bound kernel)
-    const float2* cs = nullptr;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t lo[32], hi[32];
-      tmem_ld32(t_lane + tcol + c * 32, lo);
-      tmem_ld32(t_lane + tcol + 64 + c * 32, hi);
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + tcol + c * 32, v);
       tmem_ld_wait();
-      if (rot) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float2 t = __ldg(cs + c * 32 + j);
-          const float x0 = __uint_as_float(lo[j]), x1 = __uint_as_float(hi[j]);
-          lo[j] = __float_as_uint(x0 * t.x + x1 * t.y);
-          hi[j] = __float_as_uint(x1 * t.x - x0 * t.y);
-        }
-      }
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        uint4 u, w;
-        u.x = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 0]), __uint_as_float(lo[c8 * 8 + 1]));
-        u.y = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 2]), __uint_as_float(lo[c8 * 8 + 3]));
-        u.z = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 4]), __uint_as_float(lo[c8 * 8 + 5]));
-        u.w = pack_bf16x2(__uint_as_float(lo[c8 * 8 + 6]), __uint_as_float(lo[c8 * 8 + 7]));
-        w.x = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 0]), __uint_as_float(hi[c8 * 8 + 1]));
-        w.y = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 2]), __uint_as_float(hi[c8 * 8 + 3]));
-        w.z = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 4]), __uint_as_float(hi[c8 * 8 + 5]));
-        w.w = pack_bf16x2(__uint_as_float(hi[c8 * 8 + 6]), __uint_as_float(hi[c8 * 8 + 7]));
-        reinterpret_cast<uint4*>(drow + c * 32)[c8] = u;
-        reinterpret_cast<uint4*>(drow + 64 + c * 32)[c8] = w;
-      }
+      for (int c8 = 0; c8 < 4; ++c8)
+        sts128(stage_addr + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + c8),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1])),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3])),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5])),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7])));
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1 + half, 128);
+    if (r == 0) {
+      const int col = half ? colK : colV;
+      tma_store_2d(&tmOut, stage, col, row_base + kv0);
+      tma_store_2d(&tmOut, stage + 16384, col + 64, row_base + kv0);
+      tma_store_commit();
+      tma_store_wait_read0();  // the CTA's shared memory must stay valid until the bulk stores have read it
     }
   }
   tc_fence_before();
@@ -739,8 +749,10 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
   if (a.H % Hkv) return cudaErrorInvalidValue;
   const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD;
-  CUtensorMap tmQ, tmKV;
-  if (!make_tmap_2d_bf16(&tmQ, a.qkv, W, M, W, 64, 128) || !make_tmap_2d_bf16(&tmKV, a.qkv, W, M, W, 64, 64))
+  CUtensorMap tmQ, tmKV, tmOut;
+  const uint64_t WO = static_cast<uint64_t>(a.H) * HD;
+  if (!make_tmap_2d_bf16(&tmQ, a.qkv, W, M, W, 64, 128) || !make_tmap_2d_bf16(&tmKV, a.qkv, W, M, W, 64, 64) ||
+      !make_tmap_2d_bf16(&tmOut, a.out, WO, M, WO, 64, 128))
     return cudaErrorInvalidValue;
   AttnKParams p{};
   p.B = a.B; p.S = a.S; p.H = a.H;
@@ -749,7 +761,7 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   p.scale_log2 = a.scale * LOG2E;
   p.lse2 = a.lse;
   p.out = a.out;
-  attn_fwd_kernel<<<a.B * a.H * (a.S / 128), ATT_THREADS, FWD_SMEM, s>>>(tmQ, tmKV, p);
+  attn_fwd_kernel<<<a.B * a.H * (a.S / 128), ATT_THREADS, FWD_SMEM, s>>>(tmQ, tmKV, tmOut, p);
   return cudaGetLastError();
 }
 
@@ -768,8 +780,9 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (a.H % Hkv) return cudaErrorInvalidValue;
   const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD,
                  WO = static_cast<uint64_t>(a.H) * HD;
-  CUtensorMap tmQ128, tmKV64, tmDO128, tmKV128, tmQ64, tmDO64;
+  CUtensorMap tmQ128, tmKV64, tmDO128, tmKV128, tmQ64, tmDO64, tmDqkv;
   bool ok = make_tmap_2d_bf16(&tmQ128, a.qkv, W, M, W, 64, 128) && make_tmap_2d_bf16(&tmKV64, a.qkv, W, M, W, 64, 64) &&
+            make_tmap_2d_bf16(&tmDqkv, a.dqkv, W, M, W, 64, 128) &&
             make_tmap_2d_bf16(&tmDO128, a.dout, WO, M, WO, 64, 128) && make_tmap_2d_bf16(&tmDO64, a.dout, WO, M, WO, 64, 64);
   tmKV128 = tmQ128;
   tmQ64 = tmKV64;
@@ -790,8 +803,8 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
     const long long grid = (warps * 32 + block - 1) / block;
     attn_delta_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(a.out, a.dout, a.delta, a.B, a.S, a.H);
   }
-  attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), DKV_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, p);
-  attn_dkv_kernel<<<a.B * Hkv * (a.S / 128), DKV_THREADS, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, p);
+  attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), DKV_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmDqkv, p);
+  attn_dkv_kernel<<<a.B * Hkv * (a.S / 128), DKV_THREADS, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
   return cudaGetLastError();
 }
 
