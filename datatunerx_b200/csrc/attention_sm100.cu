@@ -78,8 +78,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
   uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[FWD_NS]*/, *bar_s = bars + 1 + FWD_NS /*[2]*/, *bar_o = bars + 3 + FWD_NS,
-           *bar_free = bars + 4 + FWD_NS /*[FWD_NS]*/, *bar_p = bars + 4 + 2 * FWD_NS;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5 + 2 * FWD_NS);
+           *bar_free = bars + 4 + FWD_NS /*[FWD_NS]*/, *bar_p = bars + 4 + 2 * FWD_NS /*[2]*/;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6 + 2 * FWD_NS);
   static_assert(FWD_NS == 4, "the issue loop is unrolled over a 4-slot ring");
 
   const int nqb = p.S / 128;
@@ -97,7 +97,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     for (int i = 0; i < 4 + 2 * FWD_NS; ++i) mbar_init(&bars[i], 1);
-    mbar_init(bar_p, 128);
+    mbar_init(&bar_p[0], 128);
+    mbar_init(&bar_p[1], 128);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr, 256);
@@ -150,7 +151,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int u = 0; u < FWD_NS; ++u) {
         const int j = base + u;
         if (j < n) {
-          mbar_wait_backoff(bar_p, u & 1);  // P(j) sits (bf16-packed) in the first 32 columns of score buffer j&1; the O tile has been consumed
+          mbar_wait_backoff(&bar_p[u & 1], (j >> 1) & 1);  // P(j) sits (bf16-packed) in the first 32 columns of score buffer j&1; the O tile has been consumed
           tc_fence_after();
           if (leader) {
 #pragma unroll
@@ -228,7 +229,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_st32(t_lane + T_S + (j & 1) * 64, pk);  // A operand of the P V MMA, read straight from tensor memory
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive(&bar_p[j & 1]);
     }
     mbar_wait(bar_o, (n - 1) & 1);
     tc_fence_after();
@@ -265,6 +266,257 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
+  }
+}
+
+// ================================================================================================
+// forward, two query tiles per CTA
+// ================================================================================================
+// Tiles t = 0, 1 own query rows [256*pair + 128*t, +128) and share one K/V ring; while the four softmax warps of one tile
+// work on a score block the tensor core serves the other tile, and every scheduler has two softmax warps to interleave.
+// The running output lives in TENSOR MEMORY (P V accumulates there) instead of 128 registers per thread: the row maximum
+// used as the exponent reference is only moved when the true maximum has grown by more than 2^8 ("lazy rescale"), and
+// only then is the output tile read back, scaled and rewritten.  exp2(s - m_ref) <= 256 keeps P and the row sum exact
+// enough in bf16 / fp32, and out = O / l, lse = m_ref + log2 l do not depend on which reference was used.
+// (r01: the one-tile kernel kept O in registers (255 registers, spills) and folded 128 FMAs per row per block - it was
+// bound by its one softmax warp per scheduler, tensor pipe 25 % busy; a two-tile version of THAT design spilled and was
+// 2.8x slower.)
+constexpr int FW2_THREADS = 320;             // 8 softmax warps (4 per tile) + MMA issuer warp (8) + TMA loader warp (9)
+constexpr int FW2_NS = 4;
+constexpr int FW2_SQ = 0;                    // 2 tiles x (2 x [128 x 128B])
+constexpr int FW2_SK = 65536;                // FW2_NS x (2 x [64 x 128B])
+constexpr int FW2_SV = FW2_SK + FW2_NS * 16384;
+constexpr int FW2_BAR = FW2_SV + FW2_NS * 16384;
+constexpr int FW2_SMEM = FW2_BAR + 256 + 1024;
+constexpr float FW2_RESCALE_T = 8.f;         // log2 of the factor the row maximum may outgrow the reference by
+
+__global__ void __launch_bounds__(FW2_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FW2_BAR);
+  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[4]*/, *bar_free = bars + 5 /*[4]*/, *bar_s = bars + 9 /*[t][2]*/, *bar_o = bars + 13 /*[t]*/,
+           *bar_fin = bars + 15 /*[t]*/, *bar_p = bars + 17 /*[t][2]*/;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 21);
+  static_assert(FW2_NS == 4, "the issue loop is unrolled over a 4-slot ring");
+
+  const int npair = (p.S + 255) / 256;
+  const int qp = npair - 1 - (blockIdx.x % npair);  // heavy (late) query pairs first
+  const int bh = blockIdx.x / npair;
+  const int h = bh % p.H, b = bh / p.H;
+  const int row_base = b * p.S;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int hk = h / (p.H / p.Hkv);
+  const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
+  const int q00 = qp * 256, q01 = qp * 256 + 128;
+  const int n0 = (q00 + 128) / 64, n1 = q01 < p.S ? (q01 + 128) / 64 : 0;  // KV blocks each tile needs
+  const int n = max(n0, n1);
+  auto nt = [&](int t) { return t ? n1 : n0; };
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmOut);
+    for (int i = 0; i < 17; ++i) mbar_init(&bars[i], 1);
+    // "P_t(j) is in tensor memory": one barrier per score buffer, like bar_s.  With a single barrier per tile a tile whose
+    // next score block is already there (double buffering) can complete TWO phases while the issuer is still serving the
+    // other tile, and a parity wait that misses a phase never returns.
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_p[i], 128);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  // TMEM columns of tile t: score buffers 256t, 256t + 64; output 256t + 128
+
+  if (warp == 9) {
+    // ------------------------------------------ TMA loader ------------------------------------------
+    if ((tid & 31) == 0) {
+      mbar_arrive_expect_tx(bar_q, n1 > 0 ? 65536 : 32768);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (nt(t) == 0) continue;
+        const int q0 = t ? q01 : q00;
+        tma_load_2d(smem + FW2_SQ + t * 32768, &tmQ, bar_q, colQ, row_base + q0);
+        tma_load_2d(smem + FW2_SQ + t * 32768 + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
+      }
+      for (int j = 0; j < n; ++j) {
+        const int slot = j & 3;
+        if (j >= FW2_NS) mbar_wait_backoff(&bar_free[slot], ((j >> 2) - 1) & 1);  // both tiles' P V(j - 4) have read the slot
+        mbar_arrive_expect_tx(&bar_kv[slot], 32768);
+        tma_load_2d(smem + FW2_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
+        tma_load_2d(smem + FW2_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
+        tma_load_2d(smem + FW2_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
+        tma_load_2d(smem + FW2_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------ MMA issuer (lean: see attn_dkv_kernel) ------------------------------------------
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 0, 1);
+    const uint32_t loQ = umma_desc_lo(smem_u32(smem + FW2_SQ), 16), loK = umma_desc_lo(smem_u32(smem + FW2_SK), 16),
+                   loVm = umma_desc_lo(smem_u32(smem + FW2_SV), 8192);
+    auto issue_s = [&](const int t, const int slot, const int buf, const uint32_t parity) {  // S_t = Q_t K^T into buffer buf
+      mbar_wait_backoff(&bar_kv[slot], parity);
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16)
+          umma_bf16(tmem + t * 256 + buf * 64, umma_desc_pack(loQ + t * 2048 + kmaj_lo(k16, 16384)),
+                    umma_desc_pack(loK + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
+        umma_commit(&bar_s[t * 2 + buf]);
+      }
+    };
+    mbar_wait_backoff(bar_q, 0);
+    issue_s(0, 0, 0, 0);
+    if (n1 > 0) issue_s(1, 0, 0, 0);
+    if (n0 > 1) issue_s(0, 1, 1, 0);
+    if (n1 > 1) issue_s(1, 1, 1, 0);
+    for (int base = 0; base < n; base += FW2_NS) {
+      const uint32_t rp = (base >> 2) & 1;
+#pragma unroll
+      for (int u = 0; u < FW2_NS; ++u) {
+        const int j = base + u;
+        if (j < n) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (j < nt(t)) {
+              mbar_wait_backoff(&bar_p[t * 2 + (u & 1)], (j >> 1) & 1);  // P_t(j) sits bf16-packed in the first 32 columns of score buffer j&1
+              tc_fence_after();
+              if (leader) {
+                const uint32_t acc0 = j > 0 ? 1u : 0u;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16_ts(tmem + t * 256 + 128, tmem + t * 256 + (u & 1) * 64 + kk * 8, umma_desc_pack(loVm + u * 1024 + kk * 128),
+                               idesc_o, kk > 0 ? 1u : acc0);
+                umma_commit(&bar_o[t]);
+                if (j == nt(t) - 1) umma_commit(&bar_fin[t]);
+              }
+              if (j + 2 < nt(t)) issue_s(t, (u + 2) & 3, u & 1, (u + 2 >= FW2_NS) ? (rp ^ 1u) : rp);
+            }
+          }
+          if (leader) umma_commit(&bar_free[u]);  // every MMA that reads ring slot u has been issued
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------ softmax warps ------------------------------------------
+    const int t = warp >> 2, w = warp & 3;
+    const int r = w * 32 + (tid & 31);
+    const int n_mine = nt(t);
+    const int q0 = t ? q01 : q00;
+    const int qrow = q0 + r;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(w * 32) << 16) + t * 256;
+    const uint32_t T_O = 128;
+    uint64_t *my_s = bar_s + t * 2, *my_o = bar_o + t, *my_p = bar_p + t * 2;
+    float m_ref = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < n_mine; ++j) {
+      const int kv0 = j * 64;
+      mbar_wait(&my_s[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[64];
+      {
+        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
+        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
+        tmem_ld32(t_lane + (j & 1) * 64, lo);
+        tmem_ld32(t_lane + (j & 1) * 64 + 32, hi);
+        tmem_ld_wait();
+      }
+      if (kv0 + 63 > q0) {  // diagonal blocks: causal mask
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (kv0 + c > qrow) sv[c] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;  // scale > 0: max commutes with the scaling
+      if (j == 0) {
+        m_ref = mx;  // block 0 always holds column 0 <= qrow: finite
+      } else {
+        const bool grow = mx > m_ref + FW2_RESCALE_T;
+        if (__any_sync(0xffffffffu, grow)) {  // rare: move the reference of the rows that need it and rescale their output
+          const float m_new = grow ? mx : m_ref;
+          const float alpha = fast_exp2(m_ref - m_new);
+          mbar_wait(my_o, (j - 1) & 1);  // P V(j-1) (and every earlier one) has landed in the output tile
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_lane + T_O + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st32(t_lane + T_O + c * 32, v);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_ref = m_new;
+        }
+      }
+      uint32_t pk[32];
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; c += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), p.scale_log2, -m_ref));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), p.scale_log2, -m_ref));
+        rs0 += p0;
+        rs1 += p1;
+        pk[c >> 1] = pack_bf16x2(p0, p1);
+      }
+      l_run += rs0 + rs1;
+      tmem_st32(t_lane + (j & 1) * 64, pk);  // A operand of the P V MMA, read straight from tensor memory
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&my_p[j & 1]);
+    }
+    if (n_mine > 0) {
+      mbar_wait(&bar_fin[t], 0);
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+      // output tile -> bf16 -> 128B-swizzled staging tile (this tile's Q buffer: every S MMA has completed) -> TMA store
+      uint8_t* stage = smem + FW2_SQ + t * 32768;
+      const uint32_t stage_addr = smem_u32(stage);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + T_O + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8)
+          sts128(stage_addr + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + c8),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]) * inv_l, __uint_as_float(v[c8 * 8 + 1]) * inv_l),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]) * inv_l, __uint_as_float(v[c8 * 8 + 3]) * inv_l),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]) * inv_l, __uint_as_float(v[c8 * 8 + 5]) * inv_l),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]) * inv_l, __uint_as_float(v[c8 * 8 + 7]) * inv_l));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + t, 128);
+      if (r == 0) {
+        tma_store_2d(&tmOut, stage, h * HD, row_base + q0);
+        tma_store_2d(&tmOut, stage + 16384, h * HD + 64, row_base + q0);
+        tma_store_commit();
+        tma_store_wait_read0();
+      }
+      if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = m_ref + log2f(l_run);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -531,8 +783,9 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_BAR);
   uint64_t *bar_kv = bars, *bar_q = bars + 1 /*[DKV_NS]*/, *bar_s = bars + 1 + DKV_NS /*[2]*/, *bar_free = bars + 3 + DKV_NS /*[DKV_NS]*/,
-           *bar_p = bars + 3 + 2 * DKV_NS, *bar_fin = bars + 4 + 2 * DKV_NS;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5 + 2 * DKV_NS);
+           *bar_p = bars + 3 + 2 * DKV_NS /*[2]: one per score buffer, so that no waiter can fall two phases behind*/,
+           *bar_fin = bars + 5 + 2 * DKV_NS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6 + 2 * DKV_NS);
   static_assert(DKV_NS == 4, "the issue loop is unrolled over a 4-slot ring (slot and buffer indices are compile-time)");
 
   const int nkb = p.S / 128;
@@ -556,7 +809,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     tma_prefetch_desc(&tmDO64);
     tma_prefetch_desc(&tmOut);
     for (int i = 0; i < 3 + 2 * DKV_NS; ++i) mbar_init(&bars[i], 1);
-    mbar_init(bar_p, 256);
+    mbar_init(&bar_p[0], 256);
+    mbar_init(&bar_p[1], 256);
     mbar_init(bar_fin, 1);
     fence_barrier_init();
   }
@@ -628,7 +882,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
         if (ii < n) {
           // P^T / dS^T of pair ii sit bf16-packed in the score buffers u&1 themselves (query columns 0-31 -> TMEM columns
           // 0-15, 32-63 -> 32-47): the A operands of the accumulating MMAs come straight from tensor memory.
-          mbar_wait_backoff(bar_p, u & 1);
+          mbar_wait_backoff(&bar_p[u & 1], (ii >> 1) & 1);
           tc_fence_after();
           if (leader) {
             const uint32_t acc0 = ii > 0 ? 1u : 0u;
@@ -691,7 +945,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
       tmem_st16(t_lane + T_DPT + (ii & 1) * 64 + half * 32, dpk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive(&bar_p[ii & 1]);
     }
     mbar_wait(bar_fin, 0);
     tc_fence_after();
@@ -738,11 +992,16 @@ cudaError_t set_smem(const void* fn, int bytes) {
 
 }  // namespace
 
+bool g_attn_fwd_two_tiles = true;
+void attn_set_fwd_two_tiles(bool on) { g_attn_fwd_two_tiles = on; }
+
 cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   if (a.S % 128 || a.B <= 0 || a.H <= 0) return cudaErrorInvalidValue;
   static bool init = false;
   if (!init) {
     cudaError_t e = set_smem(reinterpret_cast<const void*>(attn_fwd_kernel), FWD_SMEM);
+    if (e != cudaSuccess) return e;
+    e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel), FW2_SMEM);
     if (e != cudaSuccess) return e;
     init = true;
   }
@@ -761,7 +1020,10 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   p.scale_log2 = a.scale * LOG2E;
   p.lse2 = a.lse;
   p.out = a.out;
-  attn_fwd_kernel<<<a.B * a.H * (a.S / 128), ATT_THREADS, FWD_SMEM, s>>>(tmQ, tmKV, tmOut, p);
+  if (g_attn_fwd_two_tiles)
+    attn_fwd2_kernel<<<a.B * a.H * ((a.S + 255) / 256), FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p);
+  else
+    attn_fwd_kernel<<<a.B * a.H * (a.S / 128), ATT_THREADS, FWD_SMEM, s>>>(tmQ, tmKV, tmOut, p);
   return cudaGetLastError();
 }
 

@@ -129,7 +129,8 @@ DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, 
 
 /* Tuning / diagnostics switches.  "gemm_pair_kernel" = 1 (default): wide GEMMs run the cta_group::2 CTA-pair kernel;
  * 0: the single-CTA kernel everywhere (used for A/B measurements in profiles/).  "fused_epilogues" = 1 (default): RoPE and
- * SwiGLU run inside the GEMM / attention epilogues; 0: separate HBM-bound kernels. */
+ * SwiGLU run inside the GEMM / attention epilogues; 0: separate HBM-bound kernels.  "attn_fwd_two_tiles" = 1 (default):
+ * forward attention runs two query tiles per CTA with the output accumulated in tensor memory; 0: one-tile kernel. */
 DTX_API int32_t dtx_set_option(const char* name, int32_t value);
 
 /* ---- per-kernel entry points (raw device pointers, `stream` = cudaStream_t or NULL) for the parity

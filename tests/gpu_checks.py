@@ -349,11 +349,22 @@ def _attn_ref(qkv, B, S, H, D, Hkv=None):
     return (p @ v).transpose(1, 2).reshape(B * S, H * D), torch.logsumexp(scores + mask, dim=-1)
 
 
-def check_attn_fwd(B=2, S=256, H=2, Hkv=None):
+def _growing_scores_qkv(B, S, H, Hkv, D):
+    """q.k grows by ~16 (log2 units) per 64 keys: every KV block moves the softmax reference (lazy-rescale path)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    u = torch.ones(D) / math.sqrt(D)
+    x = torch.randn(B, S, H + 2 * Hkv, D, generator=g) * 0.1
+    pos = torch.arange(S, dtype=torch.float32).view(1, S, 1, 1)
+    x[:, :, :H] += 4.0 * u
+    x[:, :, H:H + Hkv] += 0.5 * pos * u
+    return x.reshape(B * S, (H + 2 * Hkv) * D).to(torch.bfloat16).to(DEV)
+
+
+def check_attn_fwd(B=2, S=256, H=2, Hkv=None, growing=False):
     lib = L.load()
     D = 128
     Hkv = Hkv or H
-    qkv = _rand(B * S, (H + 2 * Hkv) * D, seed=11)
+    qkv = _growing_scores_qkv(B, S, H, Hkv, D) if growing else _rand(B * S, (H + 2 * Hkv) * D, seed=11)
     out = torch.full((B * S, H * D), float("nan"), dtype=torch.bfloat16, device=DEV)
     lse2 = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
     ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, 1.0 / math.sqrt(D), STREAM()))
@@ -364,6 +375,15 @@ def check_attn_fwd(B=2, S=256, H=2, Hkv=None):
     assert e < 8e-3, f"attn fwd {e}"
     assert e_l < 2e-3, f"attn lse {e_l}"
     return {"out": e, "lse": e_l}
+
+
+def check_attn_fwd_one_tile():
+    """The one-tile forward kernel (output in registers) stays available behind an option: same parity bar."""
+    L.set_option("attn_fwd_two_tiles", 0)
+    try:
+        return {"s384": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "s1024": check_attn_fwd(B=1, S=1024, H=1)}
+    finally:
+        L.set_option("attn_fwd_two_tiles", 1)
 
 
 def check_attn_bwd(B=2, S=256, H=2, Hkv=None):
@@ -627,6 +647,8 @@ ALL = {
     "gemm_large": check_gemm_large, "gemm_single_cta": check_gemm_single_cta, "gemm_pair_vs_single": check_gemm_pair_vs_single, "rmsnorm": check_rmsnorm, "rmsnorm_small": lambda: check_rmsnorm(M=64, d=256),
     "rope": check_rope, "swiglu": check_swiglu, "lora_dropout": check_lora_dropout, "nf4": check_nf4, "trainer_qlora": check_trainer_qlora, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
+    "attn_fwd_rescale": lambda: check_attn_fwd(B=1, S=1024, H=2, growing=True), "attn_fwd_one_tile": check_attn_fwd_one_tile,
+    "attn_fwd_odd_tiles": lambda: check_attn_fwd(B=1, S=640, H=2),
     "attn_bwd": check_attn_bwd, "attn_bwd_long": lambda: check_attn_bwd(B=1, S=1024, H=1),
     "attn_gqa": lambda: {"fwd": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "bwd": check_attn_bwd(B=2, S=384, H=4, Hkv=1)},
     "trainer_gqa": lambda: check_trainer_tiny(heads=4, kv_heads=2, targets=("q_proj", "k_proj", "v_proj")),
