@@ -32,6 +32,16 @@ bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint6
 
 namespace {
 
+// How the MMA issuer warps wait on mbarriers: their wake-up latency is on the critical path of the tensor pipe.
+#ifndef DTX_ATTN_ISSUER_SPIN
+#define DTX_ATTN_ISSUER_SPIN 1
+#endif
+#if DTX_ATTN_ISSUER_SPIN
+#define ISSUER_WAIT(bar, parity) mbar_wait(bar, parity)
+#else
+#define ISSUER_WAIT(bar, parity) mbar_wait_backoff(bar, parity)
+#endif
+
 constexpr int HD = 128;      // head dim
 constexpr int DKV_THREADS = 320;  // backward kernels: 8 compute warps + MMA issuer warp (8) + TMA loader warp (9)
 constexpr int ATT_THREADS = 192;  // 4 compute warps (one TMEM lane / score row per thread) + MMA issuer warp (4) + TMA loader warp (5)
@@ -132,7 +142,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t loQ = umma_desc_lo(smem_u32(smem + FWD_SQ), 16), loK = umma_desc_lo(smem_u32(smem + FWD_SK), 16),
                    loVm = umma_desc_lo(smem_u32(smem + FWD_SV), 8192);
     auto issue_s = [&](const int slot, const int buf, const uint32_t parity) {  // S = Q K^T into score buffer buf
-      mbar_wait_backoff(&bar_kv[slot], parity);
+      ISSUER_WAIT(&bar_kv[slot], parity);
       tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -142,7 +152,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(&bar_s[buf]);
       }
     };
-    mbar_wait_backoff(bar_q, 0);
+    ISSUER_WAIT(bar_q, 0);
     issue_s(0, 0, 0);
     if (n > 1) issue_s(1, 1, 0);
     for (int base = 0; base < n; base += FWD_NS) {
@@ -151,7 +161,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int u = 0; u < FWD_NS; ++u) {
         const int j = base + u;
         if (j < n) {
-          mbar_wait_backoff(&bar_p[u & 1], (j >> 1) & 1);  // P(j) sits (bf16-packed) in the first 32 columns of score buffer j&1; the O tile has been consumed
+          ISSUER_WAIT(&bar_p[u & 1], (j >> 1) & 1);  // P(j) sits (bf16-packed) in the first 32 columns of score buffer j&1; the O tile has been consumed
           tc_fence_after();
           if (leader) {
 #pragma unroll
@@ -361,7 +371,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t loQ = umma_desc_lo(smem_u32(smem + FW2_SQ), 16), loK = umma_desc_lo(smem_u32(smem + FW2_SK), 16),
                    loVm = umma_desc_lo(smem_u32(smem + FW2_SV), 8192);
     auto issue_s = [&](const int t, const int slot, const int buf, const uint32_t parity) {  // S_t = Q_t K^T into buffer buf
-      mbar_wait_backoff(&bar_kv[slot], parity);
+      ISSUER_WAIT(&bar_kv[slot], parity);
       tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -371,7 +381,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         umma_commit(&bar_s[t * 2 + buf]);
       }
     };
-    mbar_wait_backoff(bar_q, 0);
+    ISSUER_WAIT(bar_q, 0);
     issue_s(0, 0, 0, 0);
     if (n1 > 0) issue_s(1, 0, 0, 0);
     if (n0 > 1) issue_s(0, 1, 1, 0);
@@ -385,7 +395,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (j < nt(t)) {
-              mbar_wait_backoff(&bar_p[t * 2 + (u & 1)], (j >> 1) & 1);  // P_t(j) sits bf16-packed in the first 32 columns of score buffer j&1
+              ISSUER_WAIT(&bar_p[t * 2 + (u & 1)], (j >> 1) & 1);  // P_t(j) sits bf16-packed in the first 32 columns of score buffer j&1
               tc_fence_after();
               if (leader) {
                 const uint32_t acc0 = j > 0 ? 1u : 0u;
@@ -631,7 +641,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                    loK = umma_desc_lo(smem_u32(smem + DQ_SK), 16), loV = umma_desc_lo(smem_u32(smem + DQ_SV), 16),
                    loKm = umma_desc_lo(smem_u32(smem + DQ_SK), 8192);
     auto issue_s = [&](const int g, const int slot, const uint32_t parity) {  // S_g = Q_g K^T and dP_g = dO_g V^T for the block in `slot`
-      mbar_wait_backoff(&bar_kv[slot], parity);
+      ISSUER_WAIT(&bar_kv[slot], parity);
       tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -645,7 +655,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         umma_commit(&bar_s[g]);
       }
     };
-    mbar_wait_backoff(bar_q, 0);
+    ISSUER_WAIT(bar_q, 0);
     issue_s(0, 0, 0);
     if (ng1 > 0) issue_s(1, 0, 0);
     uint32_t rp = 0;  // ring round parity of block `base`
@@ -657,7 +667,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             if (j < ngf(g)) {
-              mbar_wait_backoff(&bar_p[g], j & 1);  // dS_g(j) sits bf16-packed in the first 32 columns of group g's S tile; dP consumed
+              ISSUER_WAIT(&bar_p[g], j & 1);  // dS_g(j) sits bf16-packed in the first 32 columns of group g's S tile; dP consumed
               tc_fence_after();
               if (leader) {
                 const uint32_t acc0 = j > 0 ? 1u : 0u;
@@ -776,7 +786,11 @@ constexpr int DKV_STAT = DKV_SDO + DKV_NS * 16384;  // DKV_NS x (lse2[64], delta
 constexpr int DKV_BAR = DKV_STAT + DKV_NS * 512;
 constexpr int DKV_SMEM = DKV_BAR + 256 + 1024;
 
-__global__ void __launch_bounds__(DKV_THREADS, 1)
+// NCW compute warps (8 or 16): warp w owns TMEM lanes (kv rows) 32*(w&3)..+31 and the query columns of column group w>>2
+// (64 / (NCW/4) columns per thread).  16 warps halve the latency of the exp / dS phase of a block (four warps per scheduler
+// to interleave instead of two) - it sits on the critical path between the score MMAs and the accumulating MMAs.
+template <int NCW>
+__global__ void __launch_bounds__((NCW + 2) * 32, 1)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmQ64,
                 const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -809,8 +823,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     tma_prefetch_desc(&tmDO64);
     tma_prefetch_desc(&tmOut);
     for (int i = 0; i < 3 + 2 * DKV_NS; ++i) mbar_init(&bars[i], 1);
-    mbar_init(&bar_p[0], 256);
-    mbar_init(&bar_p[1], 256);
+    mbar_init(&bar_p[0], NCW * 32);
+    mbar_init(&bar_p[1], NCW * 32);
     mbar_init(bar_fin, 1);
     fence_barrier_init();
   }
@@ -821,7 +835,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
   const uint32_t tmem = *tmem_ptr;
   const uint32_t T_ST = 0 /* +64*buf */, T_DPT = 128 /* +64*buf */, T_DV = 256, T_DK = 384;
 
-  if (warp == 9) {
+  constexpr int CPT = 64 / (NCW / 4);  // query columns per compute thread
+  if (warp == NCW + 1) {
     // ------------------------------------------ TMA loader ------------------------------------------
     if ((tid & 31) == 0) {
       mbar_arrive_expect_tx(bar_kv, 65536);
@@ -844,7 +859,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
         if (++qi == nq) { qi = 0; ++hq; }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == NCW) {
     // ------------------------------------------ MMA issuer ------------------------------------------
     // Everything here is on the critical path of the tensor pipe (24 MMAs of 32-64 cycles per pair): the loop is unrolled
     // over the ring so that slot / buffer / parity are immediates, and operand descriptors are one add off precomputed
@@ -857,7 +872,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
                    loQ = umma_desc_lo(smem_u32(smem + DKV_SQ), 16), loDO = umma_desc_lo(smem_u32(smem + DKV_SDO), 16),
                    loQm = umma_desc_lo(smem_u32(smem + DKV_SQ), 8192), loDOm = umma_desc_lo(smem_u32(smem + DKV_SDO), 8192);
     auto issue_s = [&](const int slot, const int buf, const uint32_t parity) {  // S^T = K Q^T, dP^T = V dO^T into buffer buf
-      mbar_wait_backoff(&bar_q[slot], parity);
+      ISSUER_WAIT(&bar_q[slot], parity);
       tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -871,7 +886,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
         umma_commit(&bar_s[buf]);
       }
     };
-    mbar_wait_backoff(bar_kv, 0);
+    ISSUER_WAIT(bar_kv, 0);
     issue_s(0, 0, 0);
     if (n > 1) issue_s(1, 1, 0);
     for (int base = 0; base < n; base += DKV_NS) {
@@ -880,21 +895,21 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
       for (int u = 0; u < DKV_NS; ++u) {
         const int ii = base + u;
         if (ii < n) {
-          // P^T / dS^T of pair ii sit bf16-packed in the score buffers u&1 themselves (query columns 0-31 -> TMEM columns
-          // 0-15, 32-63 -> 32-47): the A operands of the accumulating MMAs come straight from tensor memory.
-          mbar_wait_backoff(&bar_p[u & 1], (ii >> 1) & 1);
+          // P^T / dS^T of pair ii sit bf16-packed in the score buffers u&1 themselves (the CPT query columns of column group c
+          // -> TMEM columns CPT*c .. CPT*c + CPT/2 - 1): the A operands of the accumulating MMAs come straight from tensor memory.
+          ISSUER_WAIT(&bar_p[u & 1], (ii >> 1) & 1);
           tc_fence_after();
           if (leader) {
             const uint32_t acc0 = ii > 0 ? 1u : 0u;
             const uint32_t aP = tmem + T_ST + (u & 1) * 64, aDS = tmem + T_DPT + (u & 1) * 64;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_bf16_ts(tmem + T_DV, aP + (kk >> 1) * 32 + (kk & 1) * 8, umma_desc_pack(loDOm + u * 1024 + kk * 128), idesc_g,
-                           kk > 0 ? 1u : acc0);
+              umma_bf16_ts(tmem + T_DV, aP + ((16 * kk) / CPT) * CPT + ((16 * kk) % CPT) / 2, umma_desc_pack(loDOm + u * 1024 + kk * 128),
+                           idesc_g, kk > 0 ? 1u : acc0);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_bf16_ts(tmem + T_DK, aDS + (kk >> 1) * 32 + (kk & 1) * 8, umma_desc_pack(loQm + u * 1024 + kk * 128), idesc_g,
-                           kk > 0 ? 1u : acc0);
+              umma_bf16_ts(tmem + T_DK, aDS + ((16 * kk) / CPT) * CPT + ((16 * kk) % CPT) / 2, umma_desc_pack(loQm + u * 1024 + kk * 128),
+                           idesc_g, kk > 0 ? 1u : acc0);
             umma_commit(&bar_free[u]);  // ring slot u may be refilled once these have read it
           }
           if (ii + 2 < n) issue_s((u + 2) & (DKV_NS - 1), u & 1, (u + 2 >= DKV_NS) ? (rp ^ 1u) : rp);
@@ -905,8 +920,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     // a dedicated single-phase barrier reports that every MMA of this CTA has completed
     if (leader) umma_commit(bar_fin);
   } else {
-    // 8 compute warps: warps w and w+4 share the TMEM lanes (kv rows) 32*(w&3)..+31 and split the 64 query columns
-    const int rw = warp & 3, half = warp >> 2;
+    const int rw = warp & 3, cq = warp >> 2;
     const int r = rw * 32 + (tid & 31);
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(rw * 32) << 16);
     const int kvrow = kv0 + r;
@@ -917,14 +931,19 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
       mbar_wait(&bar_q[ii % DKV_NS], (ii / DKV_NS) & 1);  // acquire the TMA-written row statistics of this ring slot
       mbar_wait(&bar_s[ii & 1], (ii >> 1) & 1);
       tc_fence_after();
-      const uint32_t st = smem_u32(smem + DKV_STAT + (ii % DKV_NS) * 512) + half * 128;
-      uint32_t sv[32], dv[32], ppk[16], dpk[16];
-      tmem_ld32(t_lane + T_ST + (ii & 1) * 64 + half * 32, sv);
-      tmem_ld32(t_lane + T_DPT + (ii & 1) * 64 + half * 32, dv);
+      const uint32_t st = smem_u32(smem + DKV_STAT + (ii % DKV_NS) * 512) + cq * (CPT * 4);
+      uint32_t sv[CPT], dv[CPT], ppk[CPT / 2], dpk[CPT / 2];
+      if constexpr (CPT == 32) {
+        tmem_ld32(t_lane + T_ST + (ii & 1) * 64 + cq * CPT, sv);
+        tmem_ld32(t_lane + T_DPT + (ii & 1) * 64 + cq * CPT, dv);
+      } else {
+        tmem_ld16(t_lane + T_ST + (ii & 1) * 64 + cq * CPT, sv);
+        tmem_ld16(t_lane + T_DPT + (ii & 1) * 64 + cq * CPT, dv);
+      }
       tmem_ld_wait();
       const bool need_mask = (qs < kv0 + 127);
 #pragma unroll
-      for (int e = 0; e < 32; e += 4) {
+      for (int e = 0; e < CPT; e += 4) {
         const float4 l4 = lds128f(st + e * 4);
         const float4 d4 = lds128f(st + 256 + e * 4);
         const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds4[4] = {d4.x, d4.y, d4.z, d4.w};
@@ -932,7 +951,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           pr[u] = fast_exp2(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, -ls[u]));
-          if (need_mask && (kvrow > qs + half * 32 + e + u)) pr[u] = 0.f;
+          if (need_mask && (kvrow > qs + cq * CPT + e + u)) pr[u] = 0.f;
           dsv[u] = pr[u] * (__uint_as_float(dv[e + u]) - ds4[u]) * p.scale;
         }
         ppk[e >> 1] = pack_bf16x2(pr[0], pr[1]);
@@ -941,24 +960,32 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
         dpk[(e >> 1) + 1] = pack_bf16x2(dsv[2], dsv[3]);
       }
       // overwrite this thread's own (already loaded) score columns with the packed operands
-      tmem_st16(t_lane + T_ST + (ii & 1) * 64 + half * 32, ppk);
-      tmem_st16(t_lane + T_DPT + (ii & 1) * 64 + half * 32, dpk);
+      if constexpr (CPT == 32) {
+        tmem_st16(t_lane + T_ST + (ii & 1) * 64 + cq * CPT, ppk);
+        tmem_st16(t_lane + T_DPT + (ii & 1) * 64 + cq * CPT, dpk);
+      } else {
+        tmem_st8(t_lane + T_ST + (ii & 1) * 64 + cq * CPT, ppk);
+        tmem_st8(t_lane + T_DPT + (ii & 1) * 64 + cq * CPT, dpk);
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_p[ii & 1]);
     }
     mbar_wait(bar_fin, 0);
     tc_fence_after();
-    // warps 0-3 hand dV, warps 4-7 dK to the TMA: each thread converts its 128-wide row to bf16 into a 128B-swizzled staging
-    // tile (the Q/dO ring is free now), one thread per matrix issues two bulk tensor stores.  (Direct 16-byte stores of one
-    // row per thread touch 32 different 128-byte lines per instruction: 16 % of the compute warps' time, lg_throttle.)
-    uint8_t* stage = smem + DKV_SQ + half * 32768;
+    // Hand dV and dK to the TMA: the eight 32-column chunks (dV 0-3, dK 4-7) are dealt to the column groups; each thread
+    // converts its part of row r to bf16 into a 128B-swizzled staging tile (the Q/dO ring is free now), one thread per matrix
+    // issues two bulk tensor stores.  (Direct 16-byte stores of one row per thread touch 32 different 128-byte lines per
+    // instruction: 16 % of the compute warps' time, lg_throttle.)
+    constexpr int CHUNKS = 8 / (NCW / 4);
+    const int gc0 = cq * CHUNKS, m = gc0 >> 2;
+    uint8_t* stage = smem + DKV_SQ + m * 32768;
     const uint32_t stage_addr = smem_u32(stage);
-    const uint32_t tcol = half ? T_DK : T_DV;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c = (gc0 + i) & 3;
       uint32_t v[32];
-      tmem_ld32(t_lane + tcol + c * 32, v);
+      tmem_ld32(t_lane + (m ? T_DK : T_DV) + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8)
@@ -969,9 +996,9 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
                pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7])));
     }
     fence_proxy_async_smem();
-    named_bar_sync(1 + half, 128);
-    if (r == 0) {
-      const int col = half ? colK : colV;
+    named_bar_sync(1 + m, NCW * 16);
+    if (r == 0 && (gc0 & 3) == 0) {
+      const int col = m ? colK : colV;
       tma_store_2d(&tmOut, stage, col, row_base + kv0);
       tma_store_2d(&tmOut, stage + 16384, col + 64, row_base + kv0);
       tma_store_commit();
@@ -994,6 +1021,8 @@ cudaError_t set_smem(const void* fn, int bytes) {
 
 bool g_attn_fwd_two_tiles = true;
 void attn_set_fwd_two_tiles(bool on) { g_attn_fwd_two_tiles = on; }
+bool g_attn_bwd_warps16 = false;  // measured: 16 warps are 1 % slower than 8 (tools/attn_bwd_ab.py): the exp / dS phase is not the limiter
+void attn_set_bwd_warps16(bool on) { g_attn_bwd_warps16 = on; }
 
 cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   if (a.S % 128 || a.B <= 0 || a.H <= 0) return cudaErrorInvalidValue;
@@ -1034,7 +1063,9 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (!init) {
     cudaError_t e = set_smem(reinterpret_cast<const void*>(attn_dq_kernel), DQ_SMEM);
     if (e != cudaSuccess) return e;
-    e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel), DKV_SMEM);
+    e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<8>), DKV_SMEM);
+    if (e != cudaSuccess) return e;
+    e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<16>), DKV_SMEM);
     if (e != cudaSuccess) return e;
     init = true;
   }
@@ -1066,7 +1097,10 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
     attn_delta_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(a.out, a.dout, a.delta, a.B, a.S, a.H);
   }
   attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), DKV_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmDqkv, p);
-  attn_dkv_kernel<<<a.B * Hkv * (a.S / 128), DKV_THREADS, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
+  if (g_attn_bwd_warps16)
+    attn_dkv_kernel<16><<<a.B * Hkv * (a.S / 128), 18 * 32, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
+  else
+    attn_dkv_kernel<8><<<a.B * Hkv * (a.S / 128), 10 * 32, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
   return cudaGetLastError();
 }
 
