@@ -2,24 +2,30 @@
 //
 // Replaces HF 4.34 eager LlamaAttention (matmul -> mask add -> fp32 softmax -> matmul, SURVEY §2.3 K6,
 // reached from cmd/tuning/train.py:299) and its autograd backward (K10).  The [B,H,S,S] score tensor
-// never exists: scores live in TMEM, probabilities go TMEM -> registers -> swizzled smem -> tensor core.
+// never exists: scores live in TMEM, probabilities go TMEM -> registers -> TMEM (bf16) -> tensor core.
 //
 // Data layout: packed qkv [B*S, (H + 2*Hkv)*128] (per token: q heads | k heads | v heads; Hkv <= H for grouped-query
 // attention), out [B*S, H*128],
 // lse2 [B,H,S] = log2-domain log-sum-exp of the scaled scores (m + log2 l).
 //
-// Kernels (one CTA per SM; 4 compute warps where thread r owns TMEM lane r = one row of the score tile, plus a 5th
-// warp whose lane 0 issues every TMA load and every tcgen05.mma, so no compute warp ever executes serial issue code):
-//   attn_fwd_kernel   : CTA = 128 query rows, loops over 64-row KV blocks.  S = Q K^T (UMMA 128x64x16, K-major x K-major),
-//                       online softmax in registers, P -> smem (K-major A operand), O_blk = P V (V is the MN-major B operand).
-//   attn_dq_kernel    : CTA = 128 query rows.  S, dP = dO V^T, dS = P o (dP - delta) * scale, dQ += dS K (K as MN-major B),
-//                       dQ accumulates in TMEM over the whole KV loop.
-//   attn_dkv_kernel   : CTA = 128 KV rows, loops over 64-row Q blocks.  S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q.
-// All three are software-pipelined inside the CTA (r01 v2; v1 ran its phases back to back and left the tensor pipe 18-30%
-// busy, profiles/r01_ncu_full_baseline.txt): the streamed operand blocks sit in a 3-deep TMA ring, the score MMAs of block
-// j+1 are issued into a second TMEM buffer BEFORE the threads start the exp / dS arithmetic of block j, and the
-// accumulating MMAs of block j run under the TMEM loads of block j+1.  mbarriers carry every hand-off (bar_kv/bar_q: TMA
-// landed; bar_s: scores ready; bar_p: the 128 compute threads have written P / dS to smem; bar_o: accumulate MMA done).
+// Kernels (one CTA per SM).  Roles are warp-specialised: compute warps where thread r owns TMEM lane r = one row of a score
+// tile, ONE MMA issuer warp (warp-uniform code, an elected lane issues every tcgen05.mma) and ONE TMA loader warp:
+//   attn_fwd2_kernel  : CTA = two 128-row query tiles sharing one K/V ring of 64-row blocks.  S = Q K^T (UMMA 128x64x16) in two
+//                       score buffers per tile, softmax in registers, P is written bf16-packed over the score columns it came
+//                       from and is the TENSOR-MEMORY A operand of O += P V; O accumulates in tensor memory (lazy rescale).
+//                       (attn_fwd_kernel: the one-tile / output-in-registers variant, kept behind an option for A/B runs.)
+//   attn_dq_kernel    : CTA = two 128-row query tiles (groups).  S, dP = dO V^T, dS = P o (dP - delta) * scale -> TMEM operand,
+//                       dQ += dS K (K as MN-major B) accumulates in TMEM over the whole KV loop.
+//   attn_dkv_kernel   : CTA = 128 KV rows, loops over 64-row Q blocks of every query head of its KV group.  S^T = K Q^T,
+//                       dP^T = V dO^T (double-buffered), P^T / dS^T -> TMEM operands, dV += P^T dO, dK += dS^T Q.
+// What shaped them (profiles/r01_ncu_attn_issue_bound.txt, r01_ubench_mma_latency.txt):
+//   * a single warp can feed the tensor pipe only if its loop is tiny: the issuers are unrolled over the ring (slot, buffer,
+//     parity are immediates) and add constants to precomputed descriptor low words; loads live in a separate warp;
+//   * P / dS never touch shared memory (tcgen05.mma with A in TMEM): no st.shared + proxy fence, no operand re-read, and the
+//     freed smem deepens the TMA rings;
+//   * output tiles leave through a swizzled staging tile and TMA stores (row-per-thread 16-byte stores are LSU-bound);
+//   * every hand-off is an mbarrier; a waiter may never fall two phases behind a parity wait, hence one P barrier per score
+//     buffer and dedicated single-phase "all MMAs done" barriers.
 // Two backward kernels instead of one with fp32 atomics on dQ: every reduction has a fixed order, so the
 // step is bitwise reproducible (needed for the N-rank == 1-rank parity tests).
 #include "common.cuh"

@@ -292,15 +292,21 @@ constexpr int G2_B_BYTES = 128 * BK * 2;
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_TMEM_COLS = 512;
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+// Epilogues that write more than they can afford to store row-by-row stage their output tile in shared memory and hand it to
+// the TMA (SwiGLU backward: 1 KB read + 1 KB written per row and tile; one 16-byte access per thread touches 32 different
+// 128-byte lines per instruction, and ~16 K such wavefronts per tile outlast the 16 K-cycle main loop of the next tile).
+__host__ __device__ constexpr int g2_out_stage_bytes(int epi) { return epi == EPI_SWIGLU_BWD ? 32768 : 0; }
 constexpr int G2_GROUP_M = 16;  // in 256-row tiles (swept in tools/sweep_group_m.py: 16 >= 8 on every step shape)
 
 template <bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmKParams p) {
+             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+             const __grid_constant__ CUtensorMap tmC, const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  uint8_t* out_stage = smem + G2_STAGES * G2_STAGE_BYTES;  // g2_out_stage_bytes(EPI) bytes, 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES + g2_out_stage_bytes(EPI));
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* tfull_bar = empty_bar + G2_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -317,6 +323,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB2);
+    if (g2_out_stage_bytes(EPI)) tma_prefetch_desc(&tmC);
     for (int i = 0; i < G2_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);   // leader's producer arrive.expect_tx (both CTAs' bytes)
       mbar_init(&empty_bar[i], 1);  // one multicast tcgen05.commit
@@ -435,6 +442,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int i = 0; i < 8; ++i) prefetch_l2(gr + i * 64);
         }
       }
+      // SwiGLU backward: the gate|up fragments of the first two 32-feature chunks are requested before the wait for the
+      // accumulator, later ones two chunks ahead of their use (profiles/r01_ncu_swiglu_bwd_gemm_staged.txt: with a one-chunk
+      // lookahead issued after the wait, 31 % of the epilogue's samples sat on the first use of these loads).
+      uint4 gq[4], uq[4], gn[4], un[4], gm[4], um[4];
+      if (EPI == EPI_SWIGLU_BWD && row_ok) {
+        const bf16* gbase0 = reinterpret_cast<const bf16*>(p.aux) + static_cast<long long>(row) * p.ld_aux;
+        const long long c0 = static_cast<long long>(n0 >> 7) * 256 + (n0 & 127);
+        if (n0 < p.N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { gq[j] = reinterpret_cast<const uint4*>(gbase0 + c0)[j]; uq[j] = reinterpret_cast<const uint4*>(gbase0 + c0 + 128)[j]; }
+        }
+        if (n0 + 32 < p.N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { gn[j] = reinterpret_cast<const uint4*>(gbase0 + c0 + 32)[j]; un[j] = reinterpret_cast<const uint4*>(gbase0 + c0 + 160)[j]; }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256);
@@ -496,50 +519,59 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // acc = d(act) for features n0 + 32c + j; gate/up of feature f live at (f/128)*256 + f%128 (+128) of gu / d(gu).
         // The gate/up fragments of chunk c+1 are requested before chunk c is processed: the epilogue is latency-bound
         // on these HBM reads otherwise (r01: +420 us on the 1.0 ms GEMM without the prefetch).
+        // Output goes through a staging tile [d gate 128 x 64 | d up 128 x 64] (128B-swizzled) and two TMA stores per 64 features.
         const bf16* gbase = reinterpret_cast<const bf16*>(p.aux) + static_cast<long long>(row_ok ? row : 0) * p.ld_aux;
-        bf16* dbase = reinterpret_cast<bf16*>(p.C) + static_cast<long long>(row_ok ? row : 0) * p.ldc;
+        const uint32_t stg = smem_u32(out_stage);
+        const int r = q * 32 + lane;
+        const bool store_thread = (warp == 2 && lane == 0);
         auto gcol_of = [&](int c) { const int f0 = n0 + c * 32; return static_cast<long long>(f0 >> 7) * 256 + (f0 & 127); };
-        uint4 gq[4], uq[4], gn[4], un[4];
-        if (row_ok && n0 < p.N) {
-          const bf16* g0 = gbase + gcol_of(0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { gq[j] = reinterpret_cast<const uint4*>(g0)[j]; uq[j] = reinterpret_cast<const uint4*>(g0 + 128)[j]; }
-        }
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
           const int f0 = n0 + c * 32;
           if (f0 >= p.N) break;
-          const bool has_next = (c + 1 < 8) && (f0 + 32 < p.N);
-          if (row_ok && has_next) {
-            const bf16* g1 = gbase + gcol_of(c + 1);
+          const bool has_next2 = (c + 2 < 8) && (f0 + 64 < p.N);
+          if (row_ok && has_next2) {
+            const bf16* g2 = gbase + gcol_of(c + 2);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { gn[j] = reinterpret_cast<const uint4*>(g1)[j]; un[j] = reinterpret_cast<const uint4*>(g1 + 128)[j]; }
+            for (int j = 0; j < 4; ++j) { gm[j] = reinterpret_cast<const uint4*>(g2)[j]; um[j] = reinterpret_cast<const uint4*>(g2 + 128)[j]; }
           }
           uint32_t v[32];
           tmem_ld32(t_row + c * 32, v);
           tmem_ld_wait();
-          if (row_ok) {
-            bf16* drow = dbase + gcol_of(c);
+          if ((c & 1) == 0) {  // the staging tile is free once the previous pair's bulk stores have read it
+            if (store_thread) tma_store_wait_read0();
+            named_bar_sync(1, 128);
+          }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t gw[4] = {gq[j].x, gq[j].y, gq[j].z, gq[j].w}, uw[4] = {uq[j].x, uq[j].y, uq[j].z, uq[j].w};
-              uint32_t og[4], ou[4];
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t gw[4] = {gq[j].x, gq[j].y, gq[j].z, gq[j].w}, uw[4] = {uq[j].x, uq[j].y, uq[j].z, uq[j].w};
+            uint32_t og[4], ou[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 g2 = unpack_bf16x2(gw[e]), u2 = unpack_bf16x2(uw[e]);
-                // d(act) is rounded to bf16 first, exactly like the unfused path that stores it
-                const float d0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[8 * j + 2 * e])));
-                const float d1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[8 * j + 2 * e + 1])));
-                const float s0 = __fdividef(1.f, 1.f + __expf(-g2.x)), s1 = __fdividef(1.f, 1.f + __expf(-g2.y));
-                const float si0 = g2.x * s0, si1 = g2.y * s1;
-                og[e] = pack_bf16x2(d0 * u2.x * (s0 + si0 * (1.f - s0)), d1 * u2.y * (s1 + si1 * (1.f - s1)));
-                ou[e] = pack_bf16x2(d0 * si0, d1 * si1);
-              }
-              reinterpret_cast<uint4*>(drow)[j] = make_uint4(og[0], og[1], og[2], og[3]);
-              reinterpret_cast<uint4*>(drow + 128)[j] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+            for (int e = 0; e < 4; ++e) {
+              const float2 g2 = unpack_bf16x2(gw[e]), u2 = unpack_bf16x2(uw[e]);
+              // d(act) is rounded to bf16 first, exactly like the unfused path that stores it
+              const float d0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[8 * j + 2 * e])));
+              const float d1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[8 * j + 2 * e + 1])));
+              const float s0 = __fdividef(1.f, 1.f + __expf(-g2.x)), s1 = __fdividef(1.f, 1.f + __expf(-g2.y));
+              const float si0 = g2.x * s0, si1 = g2.y * s1;
+              og[e] = pack_bf16x2(d0 * u2.x * (s0 + si0 * (1.f - s0)), d1 * u2.y * (s1 + si1 * (1.f - s1)));
+              ou[e] = pack_bf16x2(d0 * si0, d1 * si1);
             }
+            const uint32_t off = sw128_offset(r, (c & 1) * 4 + j);
+            sts128(stg + off, og[0], og[1], og[2], og[3]);
+            sts128(stg + 16384 + off, ou[0], ou[1], ou[2], ou[3]);
+          }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { gq[j] = gn[j]; uq[j] = un[j]; }
+          for (int j = 0; j < 4; ++j) { gq[j] = gn[j]; uq[j] = un[j]; gn[j] = gm[j]; un[j] = um[j]; }
+          if ((c & 1) == 1) {  // 64 features staged: rows beyond M are clipped by the tensor map
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (store_thread) {
+              const int gc = static_cast<int>(gcol_of(c - 1));
+              tma_store_2d(&tmC, out_stage, gc, m0);
+              tma_store_2d(&tmC, out_stage + 16384, gc + 128, m0);
+              tma_store_commit();
+            }
           }
         }
       } else {
@@ -562,6 +594,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
 
+  if (g2_out_stage_bytes(EPI) && warp == 2 && lane == 0) tma_store_wait_read0();  // staging tile must outlive the bulk stores' reads
   tc_fence_before();
   cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still signal / multicast into it
   if (warp == 1) {
@@ -694,12 +727,14 @@ cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
   auto kern = gemm2_kernel<B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES + g2_out_stage_bytes(EPI));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  CUtensorMap tA, tB, tA2, tB2;
+  CUtensorMap tA, tB, tA2, tB2, tC;
   bool ok = true;
+  if (EPI == EPI_SWIGLU_BWD)  // d(gate|up) [M, 2N] bf16, stored in [128 x 64] boxes
+    ok &= make_tmap_2d_bf16(&tC, a.C, 2ull * static_cast<uint64_t>(a.N), a.M, a.ldc, 64, 128);
   ok &= make_tmap_2d_bf16(&tA, a.A, a.K, a.M, a.lda, 64, 128);
   ok &= B_MN ? make_tmap_2d_bf16(&tB, a.B, a.N, a.K, a.ldb, 64, 64) : make_tmap_2d_bf16(&tB, a.B, a.K, a.N, a.ldb, 64, 128);
   if (a.K2 > 0) {
@@ -734,7 +769,8 @@ cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
   int pairs = gemm_num_sms() / 2;
   if (pairs > total) pairs = total;
   if (pairs <= 0) return cudaSuccess;
-  kern<<<2 * pairs, GEMM_THREADS, G2_SMEM_BYTES, s>>>(tA, tB, tA2, tB2, p);
+  if (EPI != EPI_SWIGLU_BWD) tC = tA;
+  kern<<<2 * pairs, GEMM_THREADS, G2_SMEM_BYTES + g2_out_stage_bytes(EPI), s>>>(tA, tB, tA2, tB2, tC, p);
   return cudaGetLastError();
 }
 
