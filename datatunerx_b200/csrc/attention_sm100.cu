@@ -541,20 +541,28 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // ================================================================================================
 __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta,
                                   int B, int S, int H) {
-  // one warp per (token, head): 128 elements -> 4 per lane
-  const long long gw = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  // 16 lanes per (token, head): 128 elements -> 8 per lane (one 16-byte load from each tensor), 4 shuffle steps
+  const long long gt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long item = gt >> 4;
   const long long total = static_cast<long long>(B) * S * H;
-  if (gw >= total) return;
-  const int lane = threadIdx.x & 31;
-  const int h = static_cast<int>(gw % H);
-  const long long tok = gw / H;
-  const size_t off = static_cast<size_t>(tok) * H * HD + static_cast<size_t>(h) * HD + lane * 4;
-  const uint2 a = *reinterpret_cast<const uint2*>(out + off);
-  const uint2 d = *reinterpret_cast<const uint2*>(dout + off);
-  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y);
-  float s = a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y;
-  s = warp_sum(s);
-  if (lane == 0) {
+  if (item >= total) return;  // S*H is a multiple of 2: both halves of a warp are either in or out
+  const int sub = threadIdx.x & 15;
+  const int h = static_cast<int>(item % H);
+  const long long tok = item / H;
+  const size_t off = static_cast<size_t>(tok) * H * HD + static_cast<size_t>(h) * HD + sub * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(out + off);
+  const uint4 d = *reinterpret_cast<const uint4*>(dout + off);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 x = unpack_bf16x2(aw[i]), y = unpack_bf16x2(dw[i]);
+    s = fmaf(x.x, y.x, s);
+    s = fmaf(x.y, y.y, s);
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (sub == 0) {
     const int b = static_cast<int>(tok / S), pos = static_cast<int>(tok % S);
     delta[(static_cast<size_t>(b) * H + h) * S + pos] = s;
   }
@@ -1097,9 +1105,9 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   p.dqkv = a.dqkv;
   p.rope_cs = a.rope_cs;
   {
-    const long long warps = static_cast<long long>(a.B) * a.S * a.H;
+    const long long items = static_cast<long long>(a.B) * a.S * a.H;
     const int block = 256;
-    const long long grid = (warps * 32 + block - 1) / block;
+    const long long grid = (items * 16 + block - 1) / block;
     attn_delta_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(a.out, a.dout, a.delta, a.B, a.S, a.H);
   }
   attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), DKV_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmDqkv, p);
