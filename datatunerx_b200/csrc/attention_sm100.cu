@@ -13,7 +13,8 @@
 //   attn_fwd2_kernel  : CTA = two 128-row query tiles sharing one K/V ring of 64-row blocks.  S = Q K^T (UMMA 128x64x16) in two
 //                       score buffers per tile, softmax in registers, P is written bf16-packed over the score columns it came
 //                       from and is the TENSOR-MEMORY A operand of O += P V; O accumulates in tensor memory (lazy rescale).
-//                       (attn_fwd_kernel: the one-tile / output-in-registers variant, kept behind an option for A/B runs.)
+//                       (attn_fwd_kernel: one tile per CTA, two CTAs per SM, separate K and V rings - same arithmetic, same speed,
+//                       bitwise the same result; behind the "attn_fwd_two_tiles" = 0 option.)
 //   attn_dq_kernel    : CTA = two 128-row query tiles (groups).  S, dP = dO V^T, dS = P o (dP - delta) * scale -> TMEM operand,
 //                       dQ += dS K (K as MN-major B) accumulates in TMEM over the whole KV loop.
 //   attn_dkv_kernel   : CTA = 128 KV rows, loops over 64-row Q blocks of every query head of its KV group.  S^T = K Q^T,
@@ -52,6 +53,7 @@ constexpr int HD = 128;      // head dim
 constexpr int DKV_THREADS = 320;  // backward kernels: 8 compute warps + MMA issuer warp (8) + TMA loader warp (9)
 constexpr int ATT_THREADS = 192;  // 4 compute warps (one TMEM lane / score row per thread) + MMA issuer warp (4) + TMA loader warp (5)
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float FW2_RESCALE_T = 8.f;  // forward: log2 of the factor a row maximum may outgrow its exponent reference by before O is rescaled
 
 struct AttnKParams {
   int B, S, H;
@@ -80,23 +82,26 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // ================================================================================================
 // forward
 // ================================================================================================
-constexpr int FWD_NS = 4;                    // K/V ring depth: loads run FWD_NS - 2 blocks ahead of the score MMA
+// One 128-row query tile per CTA, sized so that TWO CTAs share an SM (97 KB of shared memory, 256 TMEM columns, 192 threads):
+// the hardware then overlaps one tile's prologue / epilogue with the other tile's steady state, which a single resident CTA
+// cannot do.  Same arithmetic as attn_fwd2_kernel (P through tensor memory, O accumulated in tensor memory, lazy rescale).
+// K and V have separate 2-slot rings: a K block is dead as soon as its score MMA has completed - long before the P V MMA
+// that releases the V block - so two slots each already give a two-block load lookahead.
 constexpr int FWD_SQ = 0;                    // 2 x [128 x 128B]
-constexpr int FWD_SK = 32768;                // FWD_NS x (2 x [64 x 128B])
-constexpr int FWD_SV = FWD_SK + FWD_NS * 16384;   // FWD_NS x (2 x [64 x 128B])
-constexpr int FWD_BAR = FWD_SV + FWD_NS * 16384;
+constexpr int FWD_SK = 32768;                // 2 slots x (2 x [64 x 128B])
+constexpr int FWD_SV = FWD_SK + 2 * 16384;   // 2 slots x (2 x [64 x 128B])
+constexpr int FWD_BAR = FWD_SV + 2 * 16384;
 constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
-  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[FWD_NS]*/, *bar_s = bars + 1 + FWD_NS /*[2]*/, *bar_o = bars + 3 + FWD_NS,
-           *bar_free = bars + 4 + FWD_NS /*[FWD_NS]*/, *bar_p = bars + 4 + 2 * FWD_NS /*[2]*/;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6 + 2 * FWD_NS);
-  static_assert(FWD_NS == 4, "the issue loop is unrolled over a 4-slot ring");
+  uint64_t *bar_q = bars, *bar_k = bars + 1 /*[2]*/, *bar_v = bars + 3 /*[2]*/, *bar_kfree = bars + 5 /*[2]*/, *bar_vfree = bars + 7 /*[2]*/,
+           *bar_s = bars + 9 /*[2]*/, *bar_o = bars + 11, *bar_fin = bars + 12, *bar_p = bars + 13 /*[2]*/;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int nqb = p.S / 128;
   const int qb = nqb - 1 - (blockIdx.x % nqb);  // heavy (late) query blocks first
@@ -112,7 +117,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (tid == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    for (int i = 0; i < 4 + 2 * FWD_NS; ++i) mbar_init(&bars[i], 1);
+    tma_prefetch_desc(&tmOut);
+    for (int i = 0; i < 13; ++i) mbar_init(&bars[i], 1);
     mbar_init(&bar_p[0], 128);
     mbar_init(&bar_p[1], 128);
     fence_barrier_init();
@@ -131,13 +137,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_load_2d(smem + FWD_SQ, &tmQ, bar_q, colQ, row_base + q0);
       tma_load_2d(smem + FWD_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
       for (int j = 0; j < n; ++j) {
-        const int slot = j & (FWD_NS - 1);
-        if (j >= FWD_NS) mbar_wait_backoff(&bar_free[slot], ((j >> 2) - 1) & 1);  // P V(j - 4) has read the slot
-        mbar_arrive_expect_tx(&bar_kv[slot], 32768);
-        tma_load_2d(smem + FWD_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
-        tma_load_2d(smem + FWD_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
-        tma_load_2d(smem + FWD_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
-        tma_load_2d(smem + FWD_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
+        const int slot = j & 1;
+        const uint32_t prev = ((j >> 1) - 1) & 1;
+        if (j >= 2) mbar_wait_backoff(&bar_kfree[slot], prev);  // S(j - 2) has read the K slot
+        mbar_arrive_expect_tx(&bar_k[slot], 16384);
+        tma_load_2d(smem + FWD_SK + slot * 16384, &tmKV, &bar_k[slot], colK, row_base + j * 64);
+        tma_load_2d(smem + FWD_SK + slot * 16384 + 8192, &tmKV, &bar_k[slot], colK + 64, row_base + j * 64);
+        if (j >= 2) mbar_wait_backoff(&bar_vfree[slot], prev);  // P V(j - 2) has read the V slot
+        mbar_arrive_expect_tx(&bar_v[slot], 16384);
+        tma_load_2d(smem + FWD_SV + slot * 16384, &tmKV, &bar_v[slot], colV, row_base + j * 64);
+        tma_load_2d(smem + FWD_SV + slot * 16384 + 8192, &tmKV, &bar_v[slot], colV + 64, row_base + j * 64);
       }
     }
   } else if (warp == 4) {
@@ -147,47 +156,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 0, 1);
     const uint32_t loQ = umma_desc_lo(smem_u32(smem + FWD_SQ), 16), loK = umma_desc_lo(smem_u32(smem + FWD_SK), 16),
                    loVm = umma_desc_lo(smem_u32(smem + FWD_SV), 8192);
-    auto issue_s = [&](const int slot, const int buf, const uint32_t parity) {  // S = Q K^T into score buffer buf
-      ISSUER_WAIT(&bar_kv[slot], parity);
+    auto issue_s = [&](const int u, const uint32_t parity) {  // S = Q K^T for the block in K slot u, into score buffer u
+      ISSUER_WAIT(&bar_k[u], parity);
       tc_fence_after();
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < 8; ++k16)
-          umma_bf16(tmem + T_S + buf * 64, umma_desc_pack(loQ + kmaj_lo(k16, 16384)),
-                    umma_desc_pack(loK + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
-        umma_commit(&bar_s[buf]);
+          umma_bf16(tmem + T_S + u * 64, umma_desc_pack(loQ + kmaj_lo(k16, 16384)), umma_desc_pack(loK + u * 1024 + kmaj_lo(k16, 8192)),
+                    idesc_s, k16 > 0 ? 1u : 0u);
+        umma_commit(&bar_s[u]);
+        umma_commit(&bar_kfree[u]);
       }
     };
     ISSUER_WAIT(bar_q, 0);
-    issue_s(0, 0, 0);
-    if (n > 1) issue_s(1, 1, 0);
-    for (int base = 0; base < n; base += FWD_NS) {
-      const uint32_t rp = (base >> 2) & 1;
+    issue_s(0, 0);
+    if (n > 1) issue_s(1, 0);
+    for (int base = 0; base < n; base += 2) {
+      const uint32_t rp = (base >> 1) & 1;
 #pragma unroll
-      for (int u = 0; u < FWD_NS; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int j = base + u;
         if (j < n) {
-          ISSUER_WAIT(&bar_p[u & 1], (j >> 1) & 1);  // P(j) sits (bf16-packed) in the first 32 columns of score buffer j&1; the O tile has been consumed
+          ISSUER_WAIT(&bar_p[u], rp);  // P(j) sits bf16-packed in the first 32 columns of score buffer u
+          ISSUER_WAIT(&bar_v[u], rp);  // V(j) has landed
           tc_fence_after();
           if (leader) {
+            const uint32_t acc0 = j > 0 ? 1u : 0u;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_bf16_ts(tmem + T_O, tmem + T_S + (u & 1) * 64 + kk * 8, umma_desc_pack(loVm + u * 1024 + kk * 128), idesc_o, kk > 0 ? 1u : 0u);
+              umma_bf16_ts(tmem + T_O, tmem + T_S + u * 64 + kk * 8, umma_desc_pack(loVm + u * 1024 + kk * 128), idesc_o, kk > 0 ? 1u : acc0);
             umma_commit(bar_o);
-            umma_commit(&bar_free[u]);
+            umma_commit(&bar_vfree[u]);
+            if (j == n - 1) umma_commit(bar_fin);
           }
-          if (j + 2 < n) issue_s((u + 2) & (FWD_NS - 1), u & 1, (u + 2 >= FWD_NS) ? (rp ^ 1u) : rp);
+          if (j + 2 < n) issue_s(u, rp ^ 1u);
         }
       }
     }
   } else {
     // ------------------------------------------ softmax warps ------------------------------------------
+    const int r = tid;
+    const int qrow = q0 + r;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    const int qrow = q0 + tid;
+    float m_ref = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < n; ++j) {
       const int kv0 = j * 64;
@@ -215,42 +226,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;  // scale > 0: max commutes with the scaling
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = fast_exp2(m_run - m_new);
+      if (j == 0) {
+        m_ref = mx;  // block 0 always holds column 0 <= qrow: finite
+      } else {
+        const bool grow = mx > m_ref + FW2_RESCALE_T;
+        if (__any_sync(0xffffffffu, grow)) {  // rare: move the reference of the rows that need it and rescale their output
+          const float m_new = grow ? mx : m_ref;
+          const float alpha = fast_exp2(m_ref - m_new);
+          mbar_wait(bar_o, (j - 1) & 1);  // P V(j-1) (and every earlier one) has landed in the output tile
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_lane + T_O + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st32(t_lane + T_O + c * 32, v);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_ref = m_new;
+        }
+      }
       uint32_t pk[32];
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), p.scale_log2, -m_new));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), p.scale_log2, -m_new));
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), p.scale_log2, -m_ref));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), p.scale_log2, -m_ref));
         rs0 += p0;
         rs1 += p1;
         pk[c >> 1] = pack_bf16x2(p0, p1);
       }
-      l_run = l_run * alpha + (rs0 + rs1);
-      m_run = m_new;
-      if (j > 0) {  // fold the previous block's P V (finished under the work above) into the running output
-        mbar_wait(bar_o, (j - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_lane + T_O + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[c * 32 + e] = fmaf(o[c * 32 + e], alpha_prev, __uint_as_float(v[e]));
-        }
-      }
-      alpha_prev = alpha;
+      l_run += rs0 + rs1;
       tmem_st32(t_lane + T_S + (j & 1) * 64, pk);  // A operand of the P V MMA, read straight from tensor memory
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_p[j & 1]);
     }
-    mbar_wait(bar_o, (n - 1) & 1);
+    mbar_wait(bar_fin, 0);
     tc_fence_after();
     const float inv_l = 1.f / l_run;
-    // output tile -> bf16 -> 128B-swizzled staging tile (the Q buffer: its last reader, the final S MMA, has completed) -> TMA store
+    // output tile -> bf16 -> 128B-swizzled staging tile (the Q buffer: every S MMA has completed) -> TMA store
     const uint32_t stage_addr = smem_u32(smem + FWD_SQ);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -258,13 +276,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32(t_lane + T_O + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaf(o[c * 32 + c8 * 8 + e], alpha_prev, __uint_as_float(v[c8 * 8 + e])) * inv_l;
-        sts128(stage_addr + (c >> 1) * 16384 + sw128_offset(tid, (c & 1) * 4 + c8), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-               pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      }
+      for (int c8 = 0; c8 < 4; ++c8)
+        sts128(stage_addr + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + c8),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]) * inv_l, __uint_as_float(v[c8 * 8 + 1]) * inv_l),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]) * inv_l, __uint_as_float(v[c8 * 8 + 3]) * inv_l),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]) * inv_l, __uint_as_float(v[c8 * 8 + 5]) * inv_l),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]) * inv_l, __uint_as_float(v[c8 * 8 + 7]) * inv_l));
     }
     fence_proxy_async_smem();
     named_bar_sync(1, 128);
@@ -274,7 +291,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_store_commit();
       tma_store_wait_read0();
     }
-    if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = m_run + log2f(l_run);
+    if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = m_ref + log2f(l_run);
   }
 
   tc_fence_before();
@@ -304,7 +321,6 @@ constexpr int FW2_SK = 65536;                // FW2_NS x (2 x [64 x 128B])
 constexpr int FW2_SV = FW2_SK + FW2_NS * 16384;
 constexpr int FW2_BAR = FW2_SV + FW2_NS * 16384;
 constexpr int FW2_SMEM = FW2_BAR + 256 + 1024;
-constexpr float FW2_RESCALE_T = 8.f;         // log2 of the factor the row maximum may outgrow the reference by
 
 __global__ void __launch_bounds__(FW2_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
