@@ -648,7 +648,8 @@ ALL = {
     "rope": check_rope, "swiglu": check_swiglu, "lora_dropout": check_lora_dropout, "nf4": check_nf4, "trainer_qlora": check_trainer_qlora, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
     "attn_fwd_rescale": lambda: check_attn_fwd(B=1, S=1024, H=2, growing=True), "attn_fwd_one_tile": check_attn_fwd_one_tile,
-    "attn_fwd_odd_tiles": lambda: check_attn_fwd(B=1, S=640, H=2),
+    "attn_fwd_odd_tiles": lambda: {"s640": check_attn_fwd(B=1, S=640, H=2), "s128": check_attn_fwd(B=3, S=128, H=2)},
+    "attn_bwd_single_tile": lambda: check_attn_bwd(B=3, S=128, H=2),
     "attn_bwd": check_attn_bwd, "attn_bwd_long": lambda: check_attn_bwd(B=1, S=1024, H=1),
     "attn_gqa": lambda: {"fwd": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "bwd": check_attn_bwd(B=2, S=384, H=4, Hkv=1)},
     "trainer_gqa": lambda: check_trainer_tiny(heads=4, kv_heads=2, targets=("q_proj", "k_proj", "v_proj")),
