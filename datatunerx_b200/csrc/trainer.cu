@@ -461,14 +461,16 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       g.M = M; g.N = RP; g.K = W; g.epilogue = EPI_BF16; g.block_n = 64;
       CK(gemm_bf16(g, s), 1);
     }
-    {  // dh1 = dqkv * Wqkv (+ dt * A_cat in the same accumulator when there is no dropout between h1 and A)
+    // Layer 0's input gradient has no consumer (the embedding is frozen): its dh1 GEMM, the dropout-branch
+    // gradient and the norm-1 backward are skipped.
+    if (l > 0) {  // dh1 = dqkv * Wqkv (+ dt * A_cat in the same accumulator when there is no dropout between h1 and A)
       GemmArgs g;
       g.A = t->dqkv; g.lda = W; g.B = y.wqkv; g.ldb = d; g.b_mn_major = 1;
       if (!drop) { g.A2 = t->dt; g.lda2 = RP; g.B2 = y.a_cat; g.ldb2 = t->KA; g.K2 = RP; }
       g.C = t->dh; g.ldc = d; g.M = M; g.N = d; g.K = W; g.epilogue = EPI_BF16;
       CK(gemm_bf16(g, s), 1);
     }
-    if (drop) {  // dh1 += sum_t mask_t o (dt_t * A_t) / (1 - p): the masks are regenerated from the counter-based RNG
+    if (drop && l > 0) {  // dh1 += sum_t mask_t o (dt_t * A_t) / (1 - p): the masks are regenerated from the counter-based RNG
       GemmArgs g;
       g.A = t->dt; g.lda = RP; g.B = y.a_cat; g.ldb = t->KA; g.b_mn_major = 1; g.C = t->glora; g.ldc = t->KA;
       g.M = M; g.N = t->KA; g.K = RP; g.epilogue = EPI_BF16;
@@ -501,7 +503,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
                                                                 accumulate, tc.lora_alpha / static_cast<float>(r));
       CK(cudaGetLastError(), 2);
     }
-    CK(rmsnorm_bwd(t->dh, t->xs[l], y.norm1, y.rstd1, other, cur, M, d, s), 1);  // cur = d x_in
+    if (l > 0) CK(rmsnorm_bwd(t->dh, t->xs[l], y.norm1, y.rstd1, other, cur, M, d, s), 1);  // cur = d x_in
   }
   return DTX_OK;
 }
