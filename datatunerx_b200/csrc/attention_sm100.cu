@@ -79,6 +79,33 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x for a pair of values on the FMA pipe (no MUFU): round-to-nearest split x = n + f via the 1.5 * 2^23 trick, cubic
+// minimax for 2^f on [-0.5, 0.5] (max. relative error 7.5e-5, far below bf16 resolution), 2^n added into the exponent field.
+// x is clamped to >= -125 (the polynomial's value can sit just below 1, i.e. in exponent 126, and the exponent field must
+// stay positive after adding n; 2^-125 ~ 0); callers guarantee x <= ~16.
+// MEASURED AND SWITCHED OFF (exp2_pair's default FMA_EVERY = 0): the exp / dS phase of a block spends 512 of its ~670 cycles
+// per scheduler on the ex2 unit (32 ex2 per thread), but moving every other pair here made the phase 780 cycles - the FMA
+// pipe becomes the limiter (profiles/r01_attn_phase_timing.txt).  Kept for a cheaper-polynomial / smaller-fraction retry.
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 q = __ffma2_rn(make_float2(0.055171649903059006f, 0.055171649903059006f), f, make_float2(0.2426111251115799f, 0.2426111251115799f));
+  q = __ffma2_rn(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  q = __ffma2_rn(q, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  q.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return q;
+}
+// exponentials of pair number `pair_idx` of a row: every FMA_EVERY-th pair on the FMA pipe (0 = none), the rest on the MUFU
+template <int FMA_EVERY = 0>
+__device__ __forceinline__ float2 exp2_pair(float2 x, int pair_idx) {
+  if (FMA_EVERY > 0 && (pair_idx % FMA_EVERY) == FMA_EVERY - 1) return exp2_fma2(x);
+  return make_float2(fast_exp2(x.x), fast_exp2(x.y));
+}
+
 // ================================================================================================
 // forward
 // ================================================================================================
@@ -250,16 +277,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       uint32_t pk[32];
-      float rs0 = 0.f, rs1 = 0.f;
+      float2 rs = make_float2(0.f, 0.f);
+      const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
 #pragma unroll
-      for (int c = 0; c < 64; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), p.scale_log2, -m_ref));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), p.scale_log2, -m_ref));
-        rs0 += p0;
-        rs1 += p1;
-        pk[c >> 1] = pack_bf16x2(p0, p1);
+      for (int c = 0; c < 64; c += 2) {  // packed fp32 pairs; every other pair of exponentials on the FMA pipe (exp2_fma2)
+        const float2 pr = exp2_pair(__ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), c >> 1);
+        rs = __fadd2_rn(rs, pr);
+        pk[c >> 1] = pack_bf16x2(pr.x, pr.y);
       }
-      l_run += rs0 + rs1;
+      l_run += rs.x + rs.y;
       tmem_st32(t_lane + T_S + (j & 1) * 64, pk);  // A operand of the P V MMA, read straight from tensor memory
       tmem_st_wait();
       tc_fence_before();
@@ -497,16 +523,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       uint32_t pk[32];
-      float rs0 = 0.f, rs1 = 0.f;
+      float2 rs = make_float2(0.f, 0.f);
+      const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
 #pragma unroll
-      for (int c = 0; c < 64; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c]), p.scale_log2, -m_ref));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + 1]), p.scale_log2, -m_ref));
-        rs0 += p0;
-        rs1 += p1;
-        pk[c >> 1] = pack_bf16x2(p0, p1);
+      for (int c = 0; c < 64; c += 2) {  // packed fp32 pairs; every other pair of exponentials on the FMA pipe (exp2_fma2)
+        const float2 pr = exp2_pair(__ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), c >> 1);
+        rs = __fadd2_rn(rs, pr);
+        pk[c >> 1] = pack_bf16x2(pr.x, pr.y);
       }
-      l_run += rs0 + rs1;
+      l_run += rs.x + rs.y;
       tmem_st32(t_lane + (j & 1) * 64, pk);  // A operand of the P V MMA, read straight from tensor memory
       tmem_st_wait();
       tc_fence_before();
@@ -805,6 +830,272 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 // ================================================================================================
+// backward: dQ, one query tile per CTA with Q and dO RESIDENT IN TENSOR MEMORY
+// ================================================================================================
+// The score MMAs of the two-group kernel read their 128-row A operand (Q / dO, 4 KB per 128x64x16 instruction) from shared
+// memory for every 64-row K/V block: 48 cycles per instruction instead of 32 (profiles/r01_ubench_mma_latency.txt).  Here the
+// tile's Q and dO rows are copied once into tensor memory (bf16-packed, 64 columns each) and every MMA of the kernel takes
+// its A operand from there; shared memory only streams K and V.  TMEM: S 2x64 | dP 2x64 | dQ 128 | Q 64 | dO 64 = 512.
+// Structure = attn_dkv_kernel: double-buffered scores, 8 compute warps (lane quadrant x column half), issuer + loader warps.
+constexpr int DQ1_NS = 4;
+constexpr int DQ1_SQ = 0;                       // 2 x [128 x 128B]  (TMA landing zone, later the dQ staging tile)
+constexpr int DQ1_SDO = 32768;                  // 2 x [128 x 128B]
+constexpr int DQ1_SK = 65536;                   // DQ1_NS x (2 x [64 x 128B])
+constexpr int DQ1_SV = DQ1_SK + DQ1_NS * 16384;
+constexpr int DQ1_BAR = DQ1_SV + DQ1_NS * 16384;
+constexpr int DQ1_SMEM = DQ1_BAR + 256 + 1024;
+
+__global__ void __launch_bounds__(DKV_THREADS, 1)
+attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ1_BAR);
+  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[4]*/, *bar_free = bars + 5 /*[4]*/, *bar_s = bars + 9 /*[2]*/, *bar_fin = bars + 11,
+           *bar_qt = bars + 12, *bar_p = bars + 13 /*[2]*/;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  static_assert(DQ1_NS == 4, "the issue loop is unrolled over a 4-slot ring");
+
+  const int nqb = p.S / 128;
+  const int qb = nqb - 1 - (blockIdx.x % nqb);  // heavy (late) query tiles first
+  const int bh = blockIdx.x / nqb;
+  const int h = bh % p.H, b = bh / p.H;
+  const int q0 = qb * 128;
+  const int row_base = b * p.S;
+  const int n = (q0 + 128) / 64;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int hk = h / (p.H / p.Hkv);
+  const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmOut);
+    for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_qt, 256);
+    mbar_init(&bar_p[0], 256);
+    mbar_init(&bar_p[1], 256);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t T_S = 0 /* +64*buf */, T_DP = 128 /* +64*buf */, T_DQ = 256, T_QT = 384, T_DOT = 448;
+
+  if (warp == 9) {
+    // ------------------------------------------ TMA loader ------------------------------------------
+    if ((tid & 31) == 0) {
+      mbar_arrive_expect_tx(bar_q, 65536);
+      tma_load_2d(smem + DQ1_SQ, &tmQ, bar_q, colQ, row_base + q0);
+      tma_load_2d(smem + DQ1_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
+      tma_load_2d(smem + DQ1_SDO, &tmDO, bar_q, h * HD, row_base + q0);
+      tma_load_2d(smem + DQ1_SDO + 16384, &tmDO, bar_q, h * HD + 64, row_base + q0);
+      for (int j = 0; j < n; ++j) {
+        const int slot = j & 3;
+        if (j >= DQ1_NS) mbar_wait_backoff(&bar_free[slot], ((j >> 2) - 1) & 1);  // dQ MMA of block j - 4 has read the slot
+        mbar_arrive_expect_tx(&bar_kv[slot], 32768);
+        tma_load_2d(smem + DQ1_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
+        tma_load_2d(smem + DQ1_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
+        tma_load_2d(smem + DQ1_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
+        tma_load_2d(smem + DQ1_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------ MMA issuer (lean: see attn_dkv_kernel) ------------------------------------------
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);
+    const uint32_t loK = umma_desc_lo(smem_u32(smem + DQ1_SK), 16), loV = umma_desc_lo(smem_u32(smem + DQ1_SV), 16),
+                   loKm = umma_desc_lo(smem_u32(smem + DQ1_SK), 8192);
+#ifdef DTX_ATTN_TIMING
+    long long ti_kv = 0, ti_mma = 0;
+#endif
+    auto issue_s = [&](const int slot, const int buf, const uint32_t parity) {  // S = Q K^T, dP = dO V^T (A operands from TMEM)
+#ifdef DTX_ATTN_TIMING
+      const long long tk0 = clock64();
+#endif
+      ISSUER_WAIT(&bar_kv[slot], parity);
+      tc_fence_after();
+#ifdef DTX_ATTN_TIMING
+      const long long tk1 = clock64();
+      ti_kv += tk1 - tk0;
+#endif
+      if (leader) {
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16)
+          umma_bf16_ts(tmem + T_S + buf * 64, tmem + T_QT + k16 * 8, umma_desc_pack(loK + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s,
+                       k16 > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16)
+          umma_bf16_ts(tmem + T_DP + buf * 64, tmem + T_DOT + k16 * 8, umma_desc_pack(loV + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s,
+                       k16 > 0 ? 1u : 0u);
+        umma_commit(&bar_s[buf]);
+      }
+#ifdef DTX_ATTN_TIMING
+      ti_mma += clock64() - tk1;
+#endif
+    };
+#ifdef DTX_ATTN_TIMING
+    long long ti_p = 0, ti_t0 = clock64();
+#endif
+    ISSUER_WAIT(bar_qt, 0);  // the compute warps have moved Q and dO into tensor memory
+    tc_fence_after();
+#ifdef DTX_ATTN_TIMING
+    const long long ti_qt = clock64() - ti_t0;
+#endif
+    issue_s(0, 0, 0);
+    if (n > 1) issue_s(1, 1, 0);
+    for (int base = 0; base < n; base += DQ1_NS) {
+      const uint32_t rp = (base >> 2) & 1;
+#pragma unroll
+      for (int u = 0; u < DQ1_NS; ++u) {
+        const int j = base + u;
+        if (j < n) {
+#ifdef DTX_ATTN_TIMING
+          const long long tw0 = clock64();
+#endif
+          ISSUER_WAIT(&bar_p[u & 1], (j >> 1) & 1);  // dS(j) sits bf16-packed in score buffer u&1 (columns 0-15 and 32-47)
+          tc_fence_after();
+#ifdef DTX_ATTN_TIMING
+          ti_p += clock64() - tw0;
+#endif
+          if (leader) {
+            const uint32_t acc0 = j > 0 ? 1u : 0u;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ts(tmem + T_DQ, tmem + T_S + (u & 1) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
+                           umma_desc_pack(loKm + u * 1024 + kk * 128), idesc_dq, kk > 0 ? 1u : acc0);
+            umma_commit(&bar_free[u]);
+            if (j == n - 1) umma_commit(bar_fin);
+          }
+          if (j + 2 < n) issue_s((u + 2) & 3, u & 1, (u + 2 >= DQ1_NS) ? (rp ^ 1u) : rp);
+        }
+      }
+    }
+#ifdef DTX_ATTN_TIMING
+    if (leader && (blockIdx.x == 3 || blockIdx.x == 1500))
+      printf("[dq1 issuer] block %d n %d total %lld wait_qt %lld per block: wait_p %lld wait_kv %lld issue_s %lld\n", (int)blockIdx.x, n,
+             clock64() - ti_t0, ti_qt, ti_p / n, ti_kv / n, ti_mma / n);
+#endif
+  } else {
+    // ------------------------------------------ 8 compute warps ------------------------------------------
+    const int rw = warp & 3, half = warp >> 2;
+    const int r = rw * 32 + (tid & 31);
+    const int qrow = q0 + r;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(rw * 32) << 16);
+    const size_t stat_idx = (static_cast<size_t>(b) * p.H + h) * p.S + qrow;
+    const float lse2 = p.lse2[stat_idx], delta = p.delta[stat_idx];
+    {  // Q / dO rows: swizzled smem -> registers -> tensor memory (thread (r, half) moves the 64 head-dim columns of its half)
+      mbar_wait(bar_q, 0);
+      const uint32_t sq = smem_u32(smem + DQ1_SQ) + half * 16384, sdo = smem_u32(smem + DQ1_SDO) + half * 16384;
+      uint32_t v[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 x = lds128u(sq + sw128_offset(r, c));
+        v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+      }
+      tmem_st32(t_lane + T_QT + half * 32, v);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 x = lds128u(sdo + sw128_offset(r, c));
+        v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+      }
+      tmem_st32(t_lane + T_DOT + half * 32, v);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_qt);
+    }
+#ifdef DTX_ATTN_TIMING
+    long long tc_wait = 0, tc_ld = 0, tc_math = 0, tc_st = 0;
+    const long long tc_t0 = clock64();
+#endif
+    for (int j = 0; j < n; ++j) {
+      const int kv0 = j * 64;
+#ifdef DTX_ATTN_TIMING
+      const long long t_a = clock64();
+#endif
+      mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+#ifdef DTX_ATTN_TIMING
+      const long long t_b = clock64();
+#endif
+      uint32_t sv[32], dv[32], pk[16];
+      tmem_ld32(t_lane + T_S + (j & 1) * 64 + half * 32, sv);
+      tmem_ld32(t_lane + T_DP + (j & 1) * 64 + half * 32, dv);
+      tmem_ld_wait();
+#ifdef DTX_ATTN_TIMING
+      const long long t_c = clock64();
+#endif
+      const bool need_mask = (kv0 + 63 > q0);
+      // packed fp32 pairs (FFMA2 / FMUL2): dS = P o (dP * scale - delta * scale), P = 2^(S * scale_log2 - lse2)
+      const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nl2 = make_float2(-lse2, -lse2), sc2 = make_float2(p.scale, p.scale),
+                   nd2 = make_float2(-delta * p.scale, -delta * p.scale);
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2, nl2);
+        float2 pr = exp2_pair(x, e >> 1);
+        if (need_mask) {
+          if (kv0 + half * 32 + e > qrow) pr.x = 0.f;
+          if (kv0 + half * 32 + e + 1 > qrow) pr.y = 0.f;
+        }
+        const float2 dd = __ffma2_rn(make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sc2, nd2);
+        const float2 ds = __fmul2_rn(pr, dd);
+        pk[e >> 1] = pack_bf16x2(ds.x, ds.y);
+      }
+#ifdef DTX_ATTN_TIMING
+      const long long t_d = clock64();
+#endif
+      tmem_st16(t_lane + T_S + (j & 1) * 64 + half * 32, pk);  // over this thread's own (already loaded) score columns
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_p[j & 1]);
+#ifdef DTX_ATTN_TIMING
+      tc_wait += t_b - t_a; tc_ld += t_c - t_b; tc_math += t_d - t_c; tc_st += clock64() - t_d;
+#endif
+    }
+#ifdef DTX_ATTN_TIMING
+    if ((tid == 0 || tid == 128) && (blockIdx.x == 3 || blockIdx.x == 1500))
+      printf("[dq1 compute] block %d tid %d n %d loop %lld per block: wait_s %lld ld %lld math %lld st+arrive %lld\n", (int)blockIdx.x, tid, n,
+             clock64() - tc_t0, tc_wait / n, tc_ld / n, tc_math / n, tc_st / n);
+#endif
+    mbar_wait(bar_fin, 0);
+    tc_fence_after();
+    // dQ tile -> bf16 -> 128B-swizzled staging tile (the Q landing zone: its contents live in tensor memory) -> TMA store
+    const uint32_t stage_addr = smem_u32(smem + DQ1_SQ) + half * 16384;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + T_DQ + half * 64 + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8)
+        sts128(stage_addr + sw128_offset(r, c * 4 + c8),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1])),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3])),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5])),
+               pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7])));
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 256);
+    if (tid == 0) {
+      tma_store_2d(&tmOut, smem + DQ1_SQ, colQ, row_base + q0);
+      tma_store_2d(&tmOut, smem + DQ1_SQ + 16384, colQ + 64, row_base + q0);
+      tma_store_commit();
+      tma_store_wait_read0();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ================================================================================================
 // backward: dK, dV
 // ================================================================================================
 constexpr int DKV_NS = 4;                      // Q / dO ring depth
@@ -972,22 +1263,27 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
       }
       tmem_ld_wait();
       const bool need_mask = (qs < kv0 + 127);
+      // packed fp32 pairs (FFMA2 / FMUL2); every other pair of exponentials on the FMA pipe (exp2_fma2)
+      const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale), nsc2 = make_float2(-p.scale, -p.scale);
 #pragma unroll
       for (int e = 0; e < CPT; e += 4) {
         const float4 l4 = lds128f(st + e * 4);
         const float4 d4 = lds128f(st + 256 + e * 4);
-        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds4[4] = {d4.x, d4.y, d4.z, d4.w};
-        float pr[4], dsv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          pr[u] = fast_exp2(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, -ls[u]));
-          if (need_mask && (kvrow > qs + cq * CPT + e + u)) pr[u] = 0.f;
-          dsv[u] = pr[u] * (__uint_as_float(dv[e + u]) - ds4[u]) * p.scale;
+        for (int u = 0; u < 4; u += 2) {
+          const float2 nl = u ? make_float2(-l4.z, -l4.w) : make_float2(-l4.x, -l4.y);
+          const float2 dl = u ? make_float2(d4.z, d4.w) : make_float2(d4.x, d4.y);
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[e + u]), __uint_as_float(sv[e + u + 1])), sl2, nl);
+          float2 pr = exp2_pair(x, (e + u) >> 1);
+          if (need_mask) {
+            if (kvrow > qs + cq * CPT + e + u) pr.x = 0.f;
+            if (kvrow > qs + cq * CPT + e + u + 1) pr.y = 0.f;
+          }
+          const float2 dd = __ffma2_rn(make_float2(__uint_as_float(dv[e + u]), __uint_as_float(dv[e + u + 1])), sc2, __fmul2_rn(dl, nsc2));
+          const float2 ds = __fmul2_rn(pr, dd);
+          ppk[(e + u) >> 1] = pack_bf16x2(pr.x, pr.y);
+          dpk[(e + u) >> 1] = pack_bf16x2(ds.x, ds.y);
         }
-        ppk[e >> 1] = pack_bf16x2(pr[0], pr[1]);
-        ppk[(e >> 1) + 1] = pack_bf16x2(pr[2], pr[3]);
-        dpk[e >> 1] = pack_bf16x2(dsv[0], dsv[1]);
-        dpk[(e >> 1) + 1] = pack_bf16x2(dsv[2], dsv[3]);
       }
       // overwrite this thread's own (already loaded) score columns with the packed operands
       if constexpr (CPT == 32) {
@@ -1051,6 +1347,8 @@ cudaError_t set_smem(const void* fn, int bytes) {
 
 bool g_attn_fwd_two_tiles = true;
 void attn_set_fwd_two_tiles(bool on) { g_attn_fwd_two_tiles = on; }
+bool g_attn_dq_tmem_operands = true;
+void attn_set_dq_tmem_operands(bool on) { g_attn_dq_tmem_operands = on; }
 bool g_attn_bwd_warps16 = false;  // measured: 16 warps are 1 % slower than 8 (tools/attn_bwd_ab.py): the exp / dS phase is not the limiter
 void attn_set_bwd_warps16(bool on) { g_attn_bwd_warps16 = on; }
 
@@ -1093,6 +1391,8 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (!init) {
     cudaError_t e = set_smem(reinterpret_cast<const void*>(attn_dq_kernel), DQ_SMEM);
     if (e != cudaSuccess) return e;
+    e = set_smem(reinterpret_cast<const void*>(attn_dq1_kernel), DQ1_SMEM);
+    if (e != cudaSuccess) return e;
     e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<8>), DKV_SMEM);
     if (e != cudaSuccess) return e;
     e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<16>), DKV_SMEM);
@@ -1126,7 +1426,10 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
     const long long grid = (items * 16 + block - 1) / block;
     attn_delta_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(a.out, a.dout, a.delta, a.B, a.S, a.H);
   }
-  attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), DKV_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmDqkv, p);
+  if (g_attn_dq_tmem_operands)
+    attn_dq1_kernel<<<a.B * a.H * (a.S / 128), DKV_THREADS, DQ1_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmDqkv, p);
+  else
+    attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), DKV_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmDqkv, p);
   if (g_attn_bwd_warps16)
     attn_dkv_kernel<16><<<a.B * Hkv * (a.S / 128), 18 * 32, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
   else

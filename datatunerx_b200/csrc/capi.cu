@@ -41,6 +41,10 @@ int32_t dtx_set_option(const char* name, int32_t value) {
     trainer_set_fused_epilogues(value);
     return DTX_OK;
   }
+  if (strcmp(name, "attn_dq_tmem_operands") == 0) {
+    attn_set_dq_tmem_operands(value != 0);
+    return DTX_OK;
+  }
   if (strcmp(name, "attn_bwd_warps16") == 0) {
     attn_set_bwd_warps16(value != 0);
     return DTX_OK;

@@ -386,6 +386,11 @@ __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
 // Byte offset of (row, 16-byte chunk) inside a 128B-swizzled tile with 128-byte rows.
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {
   return row * 128u + ((chunk16 ^ (row & 7u)) << 4);

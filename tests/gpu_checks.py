@@ -386,6 +386,19 @@ def check_attn_fwd_one_tile():
         L.set_option("attn_fwd_two_tiles", 1)
 
 
+def check_attn_bwd_variants():
+    """The alternative backward kernels kept behind options (two-group dQ kernel, 16-warp dK/dV kernel): same parity bar."""
+    out = {}
+    for opt, val in (("attn_dq_tmem_operands", 0), ("attn_bwd_warps16", 1)):
+        default = 1 - val
+        L.set_option(opt, val)
+        try:
+            out[f"{opt}={val}"] = {"s384": check_attn_bwd(B=2, S=384, H=4, Hkv=2), "s1024": check_attn_bwd(B=1, S=1024, H=1)}
+        finally:
+            L.set_option(opt, default)
+    return out
+
+
 def check_attn_bwd(B=2, S=256, H=2, Hkv=None):
     lib = L.load()
     D = 128
@@ -649,6 +662,7 @@ ALL = {
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
     "attn_fwd_rescale": lambda: check_attn_fwd(B=1, S=1024, H=2, growing=True), "attn_fwd_one_tile": check_attn_fwd_one_tile,
     "attn_fwd_odd_tiles": lambda: {"s640": check_attn_fwd(B=1, S=640, H=2), "s128": check_attn_fwd(B=3, S=128, H=2)},
+    "attn_bwd_variants": check_attn_bwd_variants,
     "attn_bwd_single_tile": lambda: check_attn_bwd(B=3, S=128, H=2),
     "attn_bwd": check_attn_bwd, "attn_bwd_long": lambda: check_attn_bwd(B=1, S=1024, H=1),
     "attn_gqa": lambda: {"fwd": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "bwd": check_attn_bwd(B=2, S=384, H=4, Hkv=1)},

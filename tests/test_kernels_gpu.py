@@ -25,7 +25,7 @@ def test_hbm_kernels(name):
     _run(name)
 
 
-@pytest.mark.parametrize("name", ["attn_fwd", "attn_fwd_long", "attn_fwd_rescale", "attn_fwd_one_tile", "attn_fwd_odd_tiles", "attn_bwd_single_tile", "attn_bwd", "attn_bwd_long",
+@pytest.mark.parametrize("name", ["attn_fwd", "attn_fwd_long", "attn_fwd_rescale", "attn_fwd_one_tile", "attn_fwd_odd_tiles", "attn_bwd_single_tile", "attn_bwd_variants", "attn_bwd", "attn_bwd_long",
                                   "attn_gqa"])
 def test_attention(name):
     _run(name)

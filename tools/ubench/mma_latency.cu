@@ -1,5 +1,6 @@
 // Microbenchmark: latency of the hand-offs the attention kernels are built from (sm_100a).
 //   A: issuer-only chain   MMA x nmma -> commit -> wait                      (MMA issue-to-complete latency)
+//   C: issuer-only chain with the A operand in tensor memory (mode 2)
 //   B: ping-pong           MMA x nmma -> commit -> 128 threads: wait, tcgen05.ld x32, tcgen05.st x32, arrive -> issuer wait
 // Operands are whatever is in shared memory; only the timing matters.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../datatunerx_b200/csrc mma_latency.cu -o mma_latency
@@ -32,10 +33,14 @@ __global__ void __launch_bounds__(160, 1) k(int mode, int nmma, int n_cols, int 
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       if (leader) {
-        for (int i = 0; i < nmma; ++i) umma_bf16(tmem, umma_desc_pack(loA + i * 2), umma_desc_pack(loB + i * 2), idesc, i > 0);
+        if (mode == 2) {  // A operand from tensor memory (columns 256..), B from shared memory
+          for (int i = 0; i < nmma; ++i) umma_bf16_ts(tmem, tmem + 256 + (i & 7) * 8, umma_desc_pack(loB + i * 2), idesc, i > 0);
+        } else {
+          for (int i = 0; i < nmma; ++i) umma_bf16(tmem, umma_desc_pack(loA + i * 2), umma_desc_pack(loB + i * 2), idesc, i > 0);
+        }
         umma_commit(&bars[0]);
       }
-      if (mode == 0) {
+      if (mode == 0 || mode == 2) {
         mbar_wait(&bars[0], it & 1);
         tc_fence_after();
       } else {
@@ -74,14 +79,14 @@ int main() {
   cudaMalloc(&d, 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
   const int iters = 2000;
-  for (int mode = 0; mode < 2; ++mode)
+  for (int mode = 0; mode < 3; ++mode)
     for (int n_cols : {64, 128})
-      for (int nmma : {1, 8, 16}) {
+      for (int nmma : {1, 8, 16, 64}) {
         k<<<1, 160, 70000>>>(mode, nmma, n_cols, iters, d);
         cudaError_t e = cudaDeviceSynchronize();
         long long h = 0;
         cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-        printf("mode %d (%s) N=%d nmma=%2d: %.1f cycles / iteration (MMA floor %d)%s\n", mode, mode ? "ping-pong" : "issuer chain", n_cols, nmma,
+        printf("mode %d (%s) N=%d nmma=%2d: %.1f cycles / iteration (MMA floor %d)%s\n", mode, mode == 1 ? "ping-pong" : (mode == 2 ? "issuer chain, A in TMEM" : "issuer chain"), n_cols, nmma,
                double(h) / iters, nmma * n_cols / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
       }
   return 0;
