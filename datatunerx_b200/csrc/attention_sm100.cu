@@ -102,7 +102,9 @@ __device__ __forceinline__ float2 exp2_fma2(float2 x) {
 // exponentials of pair number `pair_idx` of a row: every FMA_EVERY-th pair on the FMA pipe (0 = none), the rest on the MUFU
 template <int FMA_EVERY = 0>
 __device__ __forceinline__ float2 exp2_pair(float2 x, int pair_idx) {
-  if (FMA_EVERY > 0 && (pair_idx % FMA_EVERY) == FMA_EVERY - 1) return exp2_fma2(x);
+  if constexpr (FMA_EVERY > 0) {
+    if ((pair_idx % FMA_EVERY) == FMA_EVERY - 1) return exp2_fma2(x);
+  }
   return make_float2(fast_exp2(x.x), fast_exp2(x.y));
 }
 
