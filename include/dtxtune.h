@@ -130,7 +130,10 @@ DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, 
 /* Tuning / diagnostics switches.  "gemm_pair_kernel" = 1 (default): wide GEMMs run the cta_group::2 CTA-pair kernel;
  * 0: the single-CTA kernel everywhere (used for A/B measurements in profiles/).  "fused_epilogues" = 1 (default): RoPE and
  * SwiGLU run inside the GEMM / attention epilogues; 0: separate HBM-bound kernels.  "attn_fwd_two_tiles" = 1 (default):
- * forward attention runs two query tiles per CTA with the output accumulated in tensor memory; 0: one-tile kernel. */
+ * forward attention runs two query tiles per CTA with the output accumulated in tensor memory; 0: one-tile kernel (two CTAs
+ * per SM).  "attn_dq_tmem_operands" = 1 (default): dQ kernel with Q / dO resident in tensor memory; 0: two-group kernel.
+ * "attn_bwd_warps16" = 0 (default): 8 compute warps in the dK/dV kernel; 1: 16.  "gemm_group_m": rasterisation group of the
+ * CTA-pair GEMM in 256-row tiles (default 16).  Unknown names return DTX_ERR_INVALID. */
 DTX_API int32_t dtx_set_option(const char* name, int32_t value);
 
 /* ---- per-kernel entry points (raw device pointers, `stream` = cudaStream_t or NULL) for the parity

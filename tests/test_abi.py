@@ -42,3 +42,14 @@ def test_unsupported_configs_are_rejected_loudly(lib):
                   L.TrainConfig(micro_batch=1, seq_len=128, total_steps=1, lora_dropout=0.0))
     with pytest.raises(L.DtxError):
         L.TrainConfig(micro_batch=1, seq_len=128, total_steps=1, lora_target=("o_proj",)).to_c()
+
+
+def test_option_switches_are_known_and_unknown_names_rejected(lib):
+    """Every A/B switch documented in include/dtxtune.h / kernels.h is accepted (host-side flags, no device needed)."""
+    from datatunerx_b200 import lib as L
+    defaults = {"gemm_pair_kernel": 1, "gemm_group_m": 16, "fused_epilogues": 1, "attn_fwd_two_tiles": 1, "attn_dq_tmem_operands": 1,
+                "attn_bwd_warps16": 0}
+    for name, value in defaults.items():
+        L.set_option(name, value)  # restores the default: raises DtxError on an unknown name
+    with pytest.raises(L.DtxError):
+        L.set_option("no_such_option", 1)
