@@ -99,6 +99,10 @@ __device__ __forceinline__ float2 exp2_fma2(float2 x) {
   q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
   return q;
 }
+#ifndef DTX_FWD_EXP_FMA_EVERY
+#define DTX_FWD_EXP_FMA_EVERY 4
+#endif
+constexpr int FWD_EXP_FMA_EVERY = DTX_FWD_EXP_FMA_EVERY;  // forward softmax: every 4th pair of exponentials on the FMA pipe (0 = none)
 // exponentials of pair number `pair_idx` of a row: every FMA_EVERY-th pair on the FMA pipe (0 = none), the rest on the MUFU
 template <int FMA_EVERY = 0>
 __device__ __forceinline__ float2 exp2_pair(float2 x, int pair_idx) {
@@ -283,7 +287,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {  // packed fp32 pairs; every other pair of exponentials on the FMA pipe (exp2_fma2)
-        const float2 pr = exp2_pair(__ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), c >> 1);
+        const float2 pr = exp2_pair<FWD_EXP_FMA_EVERY>(__ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), c >> 1);
         rs = __fadd2_rn(rs, pr);
         pk[c >> 1] = pack_bf16x2(pr.x, pr.y);
       }
@@ -529,7 +533,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {  // packed fp32 pairs; every other pair of exponentials on the FMA pipe (exp2_fma2)
-        const float2 pr = exp2_pair(__ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), c >> 1);
+        const float2 pr = exp2_pair<FWD_EXP_FMA_EVERY>(__ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), c >> 1);
         rs = __fadd2_rn(rs, pr);
         pk[c >> 1] = pack_bf16x2(pr.x, pr.y);
       }
