@@ -64,6 +64,7 @@ struct AttnKParams {
   float* lse2;
   bf16* out;
   const float* delta;
+  float* delta_w;    // attn_dq1_kernel writes delta here (same buffer the dK/dV kernel then reads)
   bf16* dqkv;
   const float2* rope_cs;  // [S][64] (cos, sin) or null
 };
@@ -846,14 +847,17 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 constexpr int DQ1_NS = 4;
 constexpr int DQ1_SQ = 0;                       // 2 x [128 x 128B]  (TMA landing zone, later the dQ staging tile)
 constexpr int DQ1_SDO = 32768;                  // 2 x [128 x 128B]
-constexpr int DQ1_SK = 65536;                   // DQ1_NS x (2 x [64 x 128B])
+constexpr int DQ1_SO = 65536;                   // 2 x [128 x 128B]  forward output tile, only for delta = rowsum(dO o O)
+constexpr int DQ1_SK = 98304;                   // DQ1_NS x (2 x [64 x 128B])
 constexpr int DQ1_SV = DQ1_SK + DQ1_NS * 16384;
 constexpr int DQ1_BAR = DQ1_SV + DQ1_NS * 16384;
-constexpr int DQ1_SMEM = DQ1_BAR + 256 + 1024;
+constexpr int DQ1_XD = DQ1_BAR + 256;           // [2 halves][128] partial delta sums
+constexpr int DQ1_SMEM = DQ1_XD + 1024 + 1024;
 
 __global__ void __launch_bounds__(DKV_THREADS, 1)
 attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
+                const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ1_BAR);
@@ -877,6 +881,7 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmO);
     tma_prefetch_desc(&tmOut);
     for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1);
     mbar_init(bar_qt, 256);
@@ -894,11 +899,13 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 9) {
     // ------------------------------------------ TMA loader ------------------------------------------
     if ((tid & 31) == 0) {
-      mbar_arrive_expect_tx(bar_q, 65536);
+      mbar_arrive_expect_tx(bar_q, 98304);
       tma_load_2d(smem + DQ1_SQ, &tmQ, bar_q, colQ, row_base + q0);
       tma_load_2d(smem + DQ1_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
       tma_load_2d(smem + DQ1_SDO, &tmDO, bar_q, h * HD, row_base + q0);
       tma_load_2d(smem + DQ1_SDO + 16384, &tmDO, bar_q, h * HD + 64, row_base + q0);
+      tma_load_2d(smem + DQ1_SO, &tmO, bar_q, h * HD, row_base + q0);
+      tma_load_2d(smem + DQ1_SO + 16384, &tmO, bar_q, h * HD + 64, row_base + q0);
       for (int j = 0; j < n; ++j) {
         const int slot = j & 3;
         if (j >= DQ1_NS) mbar_wait_backoff(&bar_free[slot], ((j >> 2) - 1) & 1);  // dQ MMA of block j - 4 has read the slot
@@ -993,10 +1000,13 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int qrow = q0 + r;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(rw * 32) << 16);
     const size_t stat_idx = (static_cast<size_t>(b) * p.H + h) * p.S + qrow;
-    const float lse2 = p.lse2[stat_idx], delta = p.delta[stat_idx];
-    {  // Q / dO rows: swizzled smem -> registers -> tensor memory (thread (r, half) moves the 64 head-dim columns of its half)
+    const float lse2 = p.lse2[stat_idx];
+    float delta;
+    {  // Q / dO rows: swizzled smem -> registers -> tensor memory (thread (r, half) moves the 64 head-dim columns of its half);
+       // delta = rowsum(dO o O) falls out of the same pass (the dO words are in registers) and is published for the dK/dV kernel
       mbar_wait(bar_q, 0);
-      const uint32_t sq = smem_u32(smem + DQ1_SQ) + half * 16384, sdo = smem_u32(smem + DQ1_SDO) + half * 16384;
+      const uint32_t sq = smem_u32(smem + DQ1_SQ) + half * 16384, sdo = smem_u32(smem + DQ1_SDO) + half * 16384,
+                     so = smem_u32(smem + DQ1_SO) + half * 16384;
       uint32_t v[32];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -1010,9 +1020,26 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
       }
       tmem_st32(t_lane + T_DOT + half * 32, v);
+      float part = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 x = lds128u(so + sw128_offset(r, c));
+        const uint32_t ow[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 o2 = unpack_bf16x2(ow[i]), d2 = unpack_bf16x2(v[4 * c + i]);
+          part = fmaf(o2.x, d2.x, part);
+          part = fmaf(o2.y, d2.y, part);
+        }
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_qt);
+      float* xd = reinterpret_cast<float*>(smem + DQ1_XD);
+      xd[half * 128 + r] = part;
+      named_bar_sync(2, 256);
+      delta = part + xd[(1 - half) * 128 + r];
+      if (half == 0) p.delta_w[stat_idx] = delta;
     }
 #ifdef DTX_ATTN_TIMING
     long long tc_wait = 0, tc_ld = 0, tc_math = 0, tc_st = 0;
@@ -1355,6 +1382,7 @@ bool g_attn_fwd_two_tiles = true;
 void attn_set_fwd_two_tiles(bool on) { g_attn_fwd_two_tiles = on; }
 bool g_attn_dq_tmem_operands = true;
 void attn_set_dq_tmem_operands(bool on) { g_attn_dq_tmem_operands = on; }
+int attn_bwd_launches() { return g_attn_dq_tmem_operands ? 2 : 3; }
 bool g_attn_bwd_warps16 = false;  // measured: 16 warps are 1 % slower than 8 (tools/attn_bwd_ab.py): the exp / dS phase is not the limiter
 void attn_set_bwd_warps16(bool on) { g_attn_bwd_warps16 = on; }
 
@@ -1409,7 +1437,9 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (a.H % Hkv) return cudaErrorInvalidValue;
   const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD,
                  WO = static_cast<uint64_t>(a.H) * HD;
-  CUtensorMap tmQ128, tmKV64, tmDO128, tmKV128, tmQ64, tmDO64, tmDqkv;
+  CUtensorMap tmQ128, tmKV64, tmDO128, tmKV128, tmQ64, tmDO64, tmDqkv, tmO128;
+  if (!make_tmap_2d_bf16(&tmO128, a.out, static_cast<uint64_t>(a.H) * HD, static_cast<uint64_t>(a.B) * a.S, static_cast<uint64_t>(a.H) * HD, 64, 128))
+    return cudaErrorInvalidValue;
   bool ok = make_tmap_2d_bf16(&tmQ128, a.qkv, W, M, W, 64, 128) && make_tmap_2d_bf16(&tmKV64, a.qkv, W, M, W, 64, 64) &&
             make_tmap_2d_bf16(&tmDqkv, a.dqkv, W, M, W, 64, 128) &&
             make_tmap_2d_bf16(&tmDO128, a.dout, WO, M, WO, 64, 128) && make_tmap_2d_bf16(&tmDO64, a.dout, WO, M, WO, 64, 64);
@@ -1424,16 +1454,17 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   p.lse2 = a.lse;
   p.out = a.out;
   p.delta = a.delta;
+  p.delta_w = a.delta;
   p.dqkv = a.dqkv;
   p.rope_cs = a.rope_cs;
-  {
+  if (!g_attn_dq_tmem_operands) {  // the one-tile dQ kernel computes delta itself
     const long long items = static_cast<long long>(a.B) * a.S * a.H;
     const int block = 256;
     const long long grid = (items * 16 + block - 1) / block;
     attn_delta_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(a.out, a.dout, a.delta, a.B, a.S, a.H);
   }
   if (g_attn_dq_tmem_operands)
-    attn_dq1_kernel<<<a.B * a.H * (a.S / 128), DKV_THREADS, DQ1_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmDqkv, p);
+    attn_dq1_kernel<<<a.B * a.H * (a.S / 128), DKV_THREADS, DQ1_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmO128, tmDqkv, p);
   else
     attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), DKV_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmDqkv, p);
   if (g_attn_bwd_warps16)

@@ -44,6 +44,7 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s);
 int gemm_num_sms();
 // 1 (default): wide GEMMs use the CTA-pair (cta_group::2) kernel; 0: single-CTA kernel everywhere (A/B measurements)
 void gemm_set_pair_kernel(int on);
+int attn_bwd_launches();  // kernels one attn_bwd() call launches (2 with the one-tile dQ kernel, which also produces delta; else 3)
 void attn_set_dq_tmem_operands(bool on);  // 1 (default): one-tile dQ kernel with Q / dO resident in tensor memory; 0: two-group kernel
 void attn_set_bwd_warps16(bool on);     // 1: 16 compute warps in the dK/dV kernel; 0 (default): 8
 void attn_set_fwd_two_tiles(bool on);  // 1 (default): two query tiles per CTA, output accumulated in tensor memory

@@ -452,7 +452,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       // the kernels can apply the inverse rotary in their store epilogues (a.rope_cs), but the per-row table reads
       // at the very end of each CTA are exposed latency: measured +270 us/layer vs 47 us for the separate kernel
       a.rope_cs = nullptr;
-      CK(attn_bwd(a, s), 3);
+      CK(attn_bwd(a, s), attn_bwd_launches());
     }
     CK(rope_qk_inplace_table(t->dqkv, t->rope_cs, B, S, H + Hkv, W, D, 1, s), 1);
     {  // dt = dqkv * B_ext   [M, RP]
