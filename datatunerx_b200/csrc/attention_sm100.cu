@@ -66,7 +66,7 @@ struct AttnKParams {
   const float* delta;
   float* delta_w;    // attn_dq1_kernel writes delta here (same buffer the dK/dV kernel then reads)
   bf16* dqkv;
-  const float2* rope_cs;  // [S][64] (cos, sin) or null
+  const float2* rope_cs;  // backward: transposed rotary table [64][S] (cos, sin), or null
 };
 
 // descriptor low-word advance of the k16-th K=16 slice of a K-major operand made of 64-wide subtiles
@@ -1096,20 +1096,37 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #endif
     mbar_wait(bar_fin, 0);
     tc_fence_after();
-    // dQ tile -> bf16 -> 128B-swizzled staging tile (the Q landing zone: its contents live in tensor memory) -> TMA store
-    const uint32_t stage_addr = smem_u32(smem + DQ1_SQ) + half * 16384;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(t_lane + T_DQ + half * 64 + c * 32, v);
+    // dQ tile -> (inverse rotary) -> bf16 -> 128B-swizzled staging tile (the Q landing zone: its contents live in tensor
+    // memory) -> TMA store.  Thread (r, half) owns the 32-column chunks `half` and `half + 2`: rotary partners i, i + 64.
+    {
+      uint32_t lo[32], hi[32];
+      tmem_ld32(t_lane + T_DQ + half * 32, lo);
+      tmem_ld32(t_lane + T_DQ + 64 + half * 32, hi);
       tmem_ld_wait();
+      if (p.rope_cs) {
+        const float2* cs = p.rope_cs + static_cast<size_t>(half * 32) * p.S + qrow;
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8)
-        sts128(stage_addr + sw128_offset(r, c * 4 + c8),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1])),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3])),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5])),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7])));
+        for (int jj = 0; jj < 32; ++jj) {
+          const float2 tcs = __ldg(cs + static_cast<size_t>(jj) * p.S);
+          const float x0 = __uint_as_float(lo[jj]), x1 = __uint_as_float(hi[jj]);
+          lo[jj] = __float_as_uint(x0 * tcs.x + x1 * tcs.y);
+          hi[jj] = __float_as_uint(x1 * tcs.x - x0 * tcs.y);
+        }
+      }
+      const uint32_t stage_addr = smem_u32(smem + DQ1_SQ);
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        sts128(stage_addr + sw128_offset(r, half * 4 + c8),
+               pack_bf16x2(__uint_as_float(lo[c8 * 8 + 0]), __uint_as_float(lo[c8 * 8 + 1])),
+               pack_bf16x2(__uint_as_float(lo[c8 * 8 + 2]), __uint_as_float(lo[c8 * 8 + 3])),
+               pack_bf16x2(__uint_as_float(lo[c8 * 8 + 4]), __uint_as_float(lo[c8 * 8 + 5])),
+               pack_bf16x2(__uint_as_float(lo[c8 * 8 + 6]), __uint_as_float(lo[c8 * 8 + 7])));
+        sts128(stage_addr + 16384 + sw128_offset(r, half * 4 + c8),
+               pack_bf16x2(__uint_as_float(hi[c8 * 8 + 0]), __uint_as_float(hi[c8 * 8 + 1])),
+               pack_bf16x2(__uint_as_float(hi[c8 * 8 + 2]), __uint_as_float(hi[c8 * 8 + 3])),
+               pack_bf16x2(__uint_as_float(hi[c8 * 8 + 4]), __uint_as_float(hi[c8 * 8 + 5])),
+               pack_bf16x2(__uint_as_float(hi[c8 * 8 + 6]), __uint_as_float(hi[c8 * 8 + 7])));
+      }
     }
     fence_proxy_async_smem();
     named_bar_sync(1, 256);
@@ -1340,19 +1357,51 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     const int gc0 = cq * CHUNKS, m = gc0 >> 2;
     uint8_t* stage = smem + DKV_SQ + m * 32768;
     const uint32_t stage_addr = smem_u32(stage);
+    if (NCW == 8 && m == 1 && p.rope_cs) {
+      // dK with the inverse rotary: this thread holds the whole row; rotary partners are chunks c and c + 2
 #pragma unroll
-    for (int i = 0; i < CHUNKS; ++i) {
-      const int c = (gc0 + i) & 3;
-      uint32_t v[32];
-      tmem_ld32(t_lane + (m ? T_DK : T_DV) + c * 32, v);
-      tmem_ld_wait();
+      for (int c = 0; c < 2; ++c) {
+        uint32_t lo[32], hi[32];
+        tmem_ld32(t_lane + T_DK + c * 32, lo);
+        tmem_ld32(t_lane + T_DK + 64 + c * 32, hi);
+        tmem_ld_wait();
+        const float2* cs = p.rope_cs + static_cast<size_t>(c * 32) * p.S + kvrow;
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8)
-        sts128(stage_addr + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + c8),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1])),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3])),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5])),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7])));
+        for (int jj = 0; jj < 32; ++jj) {
+          const float2 tcs = __ldg(cs + static_cast<size_t>(jj) * p.S);
+          const float x0 = __uint_as_float(lo[jj]), x1 = __uint_as_float(hi[jj]);
+          lo[jj] = __float_as_uint(x0 * tcs.x + x1 * tcs.y);
+          hi[jj] = __float_as_uint(x1 * tcs.x - x0 * tcs.y);
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          sts128(stage_addr + sw128_offset(r, c * 4 + c8),
+                 pack_bf16x2(__uint_as_float(lo[c8 * 8 + 0]), __uint_as_float(lo[c8 * 8 + 1])),
+                 pack_bf16x2(__uint_as_float(lo[c8 * 8 + 2]), __uint_as_float(lo[c8 * 8 + 3])),
+                 pack_bf16x2(__uint_as_float(lo[c8 * 8 + 4]), __uint_as_float(lo[c8 * 8 + 5])),
+                 pack_bf16x2(__uint_as_float(lo[c8 * 8 + 6]), __uint_as_float(lo[c8 * 8 + 7])));
+          sts128(stage_addr + 16384 + sw128_offset(r, c * 4 + c8),
+                 pack_bf16x2(__uint_as_float(hi[c8 * 8 + 0]), __uint_as_float(hi[c8 * 8 + 1])),
+                 pack_bf16x2(__uint_as_float(hi[c8 * 8 + 2]), __uint_as_float(hi[c8 * 8 + 3])),
+                 pack_bf16x2(__uint_as_float(hi[c8 * 8 + 4]), __uint_as_float(hi[c8 * 8 + 5])),
+                 pack_bf16x2(__uint_as_float(hi[c8 * 8 + 6]), __uint_as_float(hi[c8 * 8 + 7])));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        const int c = (gc0 + i) & 3;
+        uint32_t v[32];
+        tmem_ld32(t_lane + (m ? T_DK : T_DV) + c * 32, v);
+        tmem_ld_wait();
+  #pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8)
+          sts128(stage_addr + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + c8),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1])),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3])),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5])),
+                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7])));
+      }
     }
     fence_proxy_async_smem();
     named_bar_sync(1 + m, NCW * 16);
@@ -1385,6 +1434,7 @@ void attn_set_dq_tmem_operands(bool on) { g_attn_dq_tmem_operands = on; }
 int attn_bwd_launches() { return g_attn_dq_tmem_operands ? 2 : 3; }
 bool g_attn_bwd_warps16 = false;  // measured: 16 warps are 1 % slower than 8 (tools/attn_bwd_ab.py): the exp / dS phase is not the limiter
 void attn_set_bwd_warps16(bool on) { g_attn_bwd_warps16 = on; }
+bool attn_bwd_can_rope() { return g_attn_dq_tmem_operands && !g_attn_bwd_warps16; }
 
 cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   if (a.S % 128 || a.B <= 0 || a.H <= 0) return cudaErrorInvalidValue;
@@ -1420,7 +1470,7 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
 
 cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (a.S % 128 || a.B <= 0 || a.H <= 0 || !a.delta || !a.lse || !a.dout || !a.dqkv) return cudaErrorInvalidValue;
-  if (a.rope_cs) return cudaErrorInvalidValue;  // inverse rotary in the store epilogues was measured slower than the separate kernel
+  if (a.rope_cs && !attn_bwd_can_rope()) return cudaErrorInvalidValue;  // only the one-tile dQ kernel and the 8-warp dK/dV kernel rotate
   static bool init = false;
   if (!init) {
     cudaError_t e = set_smem(reinterpret_cast<const void*>(attn_dq_kernel), DQ_SMEM);

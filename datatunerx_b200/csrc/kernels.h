@@ -44,6 +44,7 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s);
 int gemm_num_sms();
 // 1 (default): wide GEMMs use the CTA-pair (cta_group::2) kernel; 0: single-CTA kernel everywhere (A/B measurements)
 void gemm_set_pair_kernel(int on);
+bool attn_bwd_can_rope();  // the selected backward kernels can apply the inverse rotary themselves
 int attn_bwd_launches();  // kernels one attn_bwd() call launches (2 with the one-tile dQ kernel, which also produces delta; else 3)
 void attn_set_dq_tmem_operands(bool on);  // 1 (default): one-tile dQ kernel with Q / dO resident in tensor memory; 0: two-group kernel
 void attn_set_bwd_warps16(bool on);     // 1: 16 compute warps in the dK/dV kernel; 0 (default): 8
@@ -63,7 +64,7 @@ struct AttnArgs {
   int Hkv = 0;                // kv heads; 0 = H (multi-head attention)
   float scale = 0.f;
   // backward
-  const float2* rope_cs = nullptr;  // backward only: if set, dq and dk get the inverse rotary applied before the store
+  const float2* rope_cs = nullptr;  // backward only: TRANSPOSED table [64][S] (cos, sin); if set, dq and dk get the inverse rotary applied before the store
   const bf16* dout = nullptr;  // [B*S, H*D]
   bf16* dqkv = nullptr;        // [B*S, (H + 2*Hkv)*D]
   float* delta = nullptr;      // [B, H, S] scratch: rowsum(dO * O)

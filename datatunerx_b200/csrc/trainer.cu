@@ -176,6 +176,7 @@ struct dtx_trainer {
   float *d_loss = nullptr, *d_sumsq = nullptr, *d_gnorm = nullptr, *d_scratch = nullptr;
   int32_t *d_ids = nullptr, *d_labels = nullptr, *d_shift = nullptr, *d_nvalid = nullptr;
   float2* rope_cs = nullptr;
+  float2* rope_cs_t = nullptr;  // the same table transposed to [D/2][S]: coalesced when thread r needs position q0 + r (attention backward epilogues)
   int split_b = 1, split_a = 1;
 
   bool weights_loaded[8] = {false};
@@ -287,6 +288,7 @@ int create_buffers(dtx_trainer* t) {
   ok = ok && t->alloc(&t->d_loss, 4) && t->alloc(&t->d_sumsq, 4) && t->alloc(&t->d_gnorm, 4) && t->alloc(&t->d_scratch, 1024);
   ok = ok && t->alloc(&t->d_ids, M) && t->alloc(&t->d_labels, M) && t->alloc(&t->d_shift, M) && t->alloc(&t->d_nvalid, 4);
   ok = ok && t->alloc(&t->rope_cs, static_cast<size_t>(tc.seq_len) * (mc.head_dim / 2));
+  ok = ok && t->alloc(&t->rope_cs_t, static_cast<size_t>(tc.seq_len) * (mc.head_dim / 2));
   if (!ok) return DTX_ERR_CUDA;
   // rotary table in double precision (HF LlamaRotaryEmbedding: inv_freq = theta^(-2i/D))
   {
@@ -301,6 +303,10 @@ int create_buffers(dtx_trainer* t) {
                                                               static_cast<float>(sin(static_cast<double>(ang))));
       }
     cudaMemcpy(t->rope_cs, cs.data(), cs.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    std::vector<float2> cst(cs.size());
+    for (int pos = 0; pos < tc.seq_len; ++pos)
+      for (int i = 0; i < half; ++i) cst[static_cast<size_t>(i) * tc.seq_len + pos] = cs[static_cast<size_t>(pos) * half + i];
+    cudaMemcpy(t->rope_cs_t, cst.data(), cst.size() * sizeof(float2), cudaMemcpyHostToDevice);
   }
   return DTX_OK;
 }
@@ -449,12 +455,14 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       AttnArgs a;
       a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.Hkv = Hkv; a.scale = att_scale;
       a.dout = t->dattn; a.dqkv = t->dqkv; a.delta = t->delta;
-      // the kernels can apply the inverse rotary in their store epilogues (a.rope_cs), but the per-row table reads
-      // at the very end of each CTA are exposed latency: measured +270 us/layer vs 47 us for the separate kernel
-      a.rope_cs = nullptr;
+      // The dQ / dK kernels apply the inverse rotary in their store epilogues from the TRANSPOSED table (thread r of a tile
+      // reads position q0 + r: one coalesced 256-byte line per frequency and warp).  A first attempt with the [S][64] table
+      // (32 uncoalesced 8-byte reads per thread) cost +270 us/layer, the standalone HBM-bound kernel 92 us.
+      const bool rope_in_attn = fused && attn_bwd_can_rope();
+      a.rope_cs = rope_in_attn ? t->rope_cs_t : nullptr;
       CK(attn_bwd(a, s), attn_bwd_launches());
+      if (!rope_in_attn) CK(rope_qk_inplace_table(t->dqkv, t->rope_cs, B, S, H + Hkv, W, D, 1, s), 1);
     }
-    CK(rope_qk_inplace_table(t->dqkv, t->rope_cs, B, S, H + Hkv, W, D, 1, s), 1);
     {  // dt = dqkv * B_ext   [M, RP]
       GemmArgs g;
       g.A = t->dqkv; g.lda = W; g.B = y.b_ext; g.ldb = RP; g.b_mn_major = 1; g.C = t->dt; g.ldc = RP;
