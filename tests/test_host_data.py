@@ -85,3 +85,31 @@ def test_unknown_flag_and_missing_required_fail_like_hf_argparser():
         P.get_train_args(base[:-2])
     with pytest.raises(SystemExit):
         P.get_train_args(["--model_name_or_path", "m", "--output_dir", "o", "--storage_path", "s"])
+
+
+def test_empty_ragged_and_oversized_inputs(tmp_path):
+    """Edge cases of the integer path: skipped rows, an empty shard, ragged batches, rows longer than the static length,
+    a batch whose labels are all masked, CSV column renaming."""
+    tok = _tokenizer()
+    D.fix_tokenizer(tok)
+    # rows with an empty / missing side are skipped exactly like train.py:83-84 (no exception)
+    rows = [{"instruction": "", "response": "x"}, {"instruction": "hello", "response": ""}, {"instruction": None, "response": "y"},
+            {"instruction": "hello there", "response": "general kenobi"}]
+    ds = D.build_dataset(rows, tok, 64)
+    assert len(ds) == 1 and len(ds[0][0]) == len(ds[0][1]) <= 64
+    assert D.build_dataset([], tok, 64) == []
+    # an empty shard yields no batches; fewer examples than one global batch yields none either (drop-last semantics)
+    assert list(D.epoch_batches([], 0, 2, 4, 128, tok.eos_token_id, seed=0, epoch=0)) == []
+    assert D.steps_per_epoch(3, 2, 4) == 0
+    # ragged lengths collate to one static shape; an example longer than the static length is cut, never overflows
+    long_ids = list(range(3, 3 + 300))
+    ids, lab = D.collate([(long_ids, long_ids), ([1, 2], [-100, 2])], 128, pad_id=0)
+    assert ids.shape == (2, 128) and ids[0].tolist() == long_ids[:128] and lab[0].tolist() == long_ids[:128]
+    assert ids[1, :2].tolist() == [1, 2] and (ids[1, 2:] == 0).all() and (lab[1, 2:] == D.IGNORE_INDEX).all()
+    # a fully masked example stays fully masked (the step then sees n_valid = 0 for it)
+    _, lab2 = D.collate([([1, 5, 6], [-100, -100, -100])], 128, pad_id=0)
+    assert (lab2 == D.IGNORE_INDEX).all()
+    # --columns renaming: CSV header names -> instruction / response
+    p = tmp_path / "d.csv"
+    p.write_text("q,a\n\"what, exactly?\",\"this\"\n")
+    assert D.read_csv_rows(str(p), {"q": "instruction", "a": "response"}) == [{"instruction": "what, exactly?", "response": "this"}]
