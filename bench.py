@@ -71,6 +71,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def pick_cpu_threads(max_threads: int) -> int:
+    """Thread count at which torch's fp32 GEMM is fastest on this host (<= max_threads).  On the 128-thread GPU boxes the full
+    thread count is several times SLOWER than a moderate one for the step's matrix shapes; the CPU arm should be the best the
+    host cores can do, so the count is calibrated in ~2 s on the MLP GEMM shape of one sequence."""
+    import torch
+    cands = sorted({t for t in (8, 16, 24, 32, 48, 64, 96, 128, max_threads) if 1 <= t <= max_threads})
+    a, b = torch.randn(2048, 4096), torch.randn(4096, 11008)
+    best, best_t = cands[-1], float("inf")
+    for t in cands:
+        torch.set_num_threads(t)
+        torch.mm(a, b)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            torch.mm(a, b)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = t, dt
+    return best
+
+
 def cpu_reference_sample(layers_sample: int, threads: int, steps: int = 1, warmup: int = 0):
     """Time the oracle (CPU restatement of the reference step) on a bounded sample of the 7B workload:
     one 2048-token sequence through `layers_sample` of the 32 identical Llama-2-7B decoder layers plus embedding,
@@ -117,7 +137,7 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     import torch
-    threads = os.cpu_count() or 1
+    threads = pick_cpu_threads(os.cpu_count() or 1)
     t0 = time.perf_counter()
     r = cpu_reference_sample(layers_sample=3, threads=threads, steps=max(1, min(args.steps, 2)), warmup=0)
     wall = time.perf_counter() - t0
@@ -281,7 +301,7 @@ def run_native(args, rank: int, local_rank: int, world: int):
                             "frac": gemm["tflops"] / peaks["burst"], "traffic": DOMINANT_GEMM_DRAM_BYTES, "traffic_src": "profiles/r01_ncu_dominant_gemm_final.txt (ncu --set full, dram read+write per launch; algorithmic 1.036e9)", "kernel": "gemm2_kernel<NT,bf16> (CTA-pair 256x256x64, cta_group::2)",
                             "shape_mnk": gemm["shape"], "ms": gemm["ms"], "peak_src": peaks["src"] + " bf16_tflops (burst)"}
     if args.cpu_baseline and args.config == "7b":
-        threads = os.cpu_count() or 1
+        threads = pick_cpu_threads(os.cpu_count() or 1)
         r = cpu_reference_sample(layers_sample=3, threads=threads, steps=1)
         line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": threads, "kind": "port",
                                 "sample": "oracle fp32: 1 x 2048-token sequence fwd+bwd+AdamW through 1 and 3 Llama-2-7B layers + "
