@@ -32,6 +32,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <mutex>
+
 namespace dtx {
 
 bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
@@ -51,7 +53,6 @@ namespace {
 
 constexpr int HD = 128;      // head dim
 constexpr int DKV_THREADS = 320;  // backward kernels: 8 compute warps + MMA issuer warp (8) + TMA loader warp (9)
-constexpr int ATT_THREADS = 192;  // 4 compute warps (one TMEM lane / score row per thread) + MMA issuer warp (4) + TMA loader warp (5)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float FW2_RESCALE_T = 8.f;  // forward: log2 of the factor a row maximum may outgrow its exponent reference by before O is rescaled
 
@@ -66,8 +67,21 @@ struct AttnKParams {
   const float* delta;
   float* delta_w;    // attn_dq1_kernel writes delta here (same buffer the dK/dV kernel then reads)
   bf16* dqkv;
-  const float2* rope_cs;  // backward: transposed rotary table [64][S] (cos, sin), or null
+  const float2* rope_cs;  // backward: transposed rotary table [64][rope_stride] (cos, sin), or null
+  int rope_stride;
+  const int32_t* seq_lens;  // [B] true row lengths (right padding beyond), or null = S
 };
+
+// true length of batch row b (tiles that start at or beyond it hold only padding)
+__device__ __forceinline__ int row_len(const AttnKParams& p, int b) {
+  return p.seq_lens ? min(max(p.seq_lens[b], 0), p.S) : p.S;
+}
+// zero a [128 x 128] bf16 tile of a row-major matrix (skipped padding tiles: downstream GEMMs contract over tokens, so the
+// rows must hold finite values - and the gradient of a padded token is exactly zero)
+__device__ __forceinline__ void zero_tile_128(bf16* base, long long ld, long long row0, int col0, int tid, int nthreads) {
+  for (int i = tid; i < 128 * 16; i += nthreads)
+    *reinterpret_cast<uint4*>(base + (row0 + (i >> 4)) * ld + col0 + (i & 15) * 8) = make_uint4(0u, 0u, 0u, 0u);
+}
 
 // descriptor low-word advance of the k16-th K=16 slice of a K-major operand made of 64-wide subtiles
 __device__ __forceinline__ constexpr uint32_t kmaj_lo(int k16, uint32_t subtile_bytes) {
@@ -114,228 +128,6 @@ __device__ __forceinline__ float2 exp2_pair(float2 x, int pair_idx) {
 }
 
 // ================================================================================================
-// forward
-// ================================================================================================
-// One 128-row query tile per CTA, sized so that TWO CTAs share an SM (97 KB of shared memory, 256 TMEM columns, 192 threads):
-// the hardware then overlaps one tile's prologue / epilogue with the other tile's steady state, which a single resident CTA
-// cannot do.  Same arithmetic as attn_fwd2_kernel (P through tensor memory, O accumulated in tensor memory, lazy rescale).
-// K and V have separate 2-slot rings: a K block is dead as soon as its score MMA has completed - long before the P V MMA
-// that releases the V block - so two slots each already give a two-block load lookahead.
-constexpr int FWD_SQ = 0;                    // 2 x [128 x 128B]
-constexpr int FWD_SK = 32768;                // 2 slots x (2 x [64 x 128B])
-constexpr int FWD_SV = FWD_SK + 2 * 16384;   // 2 slots x (2 x [64 x 128B])
-constexpr int FWD_BAR = FWD_SV + 2 * 16384;
-constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
-
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
-  uint64_t *bar_q = bars, *bar_k = bars + 1 /*[2]*/, *bar_v = bars + 3 /*[2]*/, *bar_kfree = bars + 5 /*[2]*/, *bar_vfree = bars + 7 /*[2]*/,
-           *bar_s = bars + 9 /*[2]*/, *bar_o = bars + 11, *bar_fin = bars + 12, *bar_p = bars + 13 /*[2]*/;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
-
-  const int nqb = p.S / 128;
-  const int qb = nqb - 1 - (blockIdx.x % nqb);  // heavy (late) query blocks first
-  const int bh = blockIdx.x / nqb;
-  const int h = bh % p.H, b = bh / p.H;
-  const int q0 = qb * 128;
-  const int row_base = b * p.S;
-  const int n = (q0 + 128) / 64;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int hk = h / (p.H / p.Hkv);
-  const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmKV);
-    tma_prefetch_desc(&tmOut);
-    for (int i = 0; i < 13; ++i) mbar_init(&bars[i], 1);
-    mbar_init(&bar_p[0], 128);
-    mbar_init(&bar_p[1], 128);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_ptr, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  const uint32_t T_S = 0 /* +64*buf */, T_O = 128;
-
-  if (warp == 5) {
-    // ------------------------------------------ TMA loader ------------------------------------------
-    if ((tid & 31) == 0) {
-      mbar_arrive_expect_tx(bar_q, 32768);
-      tma_load_2d(smem + FWD_SQ, &tmQ, bar_q, colQ, row_base + q0);
-      tma_load_2d(smem + FWD_SQ + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
-      for (int j = 0; j < n; ++j) {
-        const int slot = j & 1;
-        const uint32_t prev = ((j >> 1) - 1) & 1;
-        if (j >= 2) mbar_wait_backoff(&bar_kfree[slot], prev);  // S(j - 2) has read the K slot
-        mbar_arrive_expect_tx(&bar_k[slot], 16384);
-        tma_load_2d(smem + FWD_SK + slot * 16384, &tmKV, &bar_k[slot], colK, row_base + j * 64);
-        tma_load_2d(smem + FWD_SK + slot * 16384 + 8192, &tmKV, &bar_k[slot], colK + 64, row_base + j * 64);
-        if (j >= 2) mbar_wait_backoff(&bar_vfree[slot], prev);  // P V(j - 2) has read the V slot
-        mbar_arrive_expect_tx(&bar_v[slot], 16384);
-        tma_load_2d(smem + FWD_SV + slot * 16384, &tmKV, &bar_v[slot], colV, row_base + j * 64);
-        tma_load_2d(smem + FWD_SV + slot * 16384 + 8192, &tmKV, &bar_v[slot], colV + 64, row_base + j * 64);
-      }
-    }
-  } else if (warp == 4) {
-    // ------------------------------------------ MMA issuer (lean: see attn_dkv_kernel) ------------------------------------------
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 0, 1);
-    const uint32_t loQ = umma_desc_lo(smem_u32(smem + FWD_SQ), 16), loK = umma_desc_lo(smem_u32(smem + FWD_SK), 16),
-                   loVm = umma_desc_lo(smem_u32(smem + FWD_SV), 8192);
-    auto issue_s = [&](const int u, const uint32_t parity) {  // S = Q K^T for the block in K slot u, into score buffer u
-      ISSUER_WAIT(&bar_k[u], parity);
-      tc_fence_after();
-      if (leader) {
-#pragma unroll
-        for (int k16 = 0; k16 < 8; ++k16)
-          umma_bf16(tmem + T_S + u * 64, umma_desc_pack(loQ + kmaj_lo(k16, 16384)), umma_desc_pack(loK + u * 1024 + kmaj_lo(k16, 8192)),
-                    idesc_s, k16 > 0 ? 1u : 0u);
-        umma_commit(&bar_s[u]);
-        umma_commit(&bar_kfree[u]);
-      }
-    };
-    ISSUER_WAIT(bar_q, 0);
-    issue_s(0, 0);
-    if (n > 1) issue_s(1, 0);
-    for (int base = 0; base < n; base += 2) {
-      const uint32_t rp = (base >> 1) & 1;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int j = base + u;
-        if (j < n) {
-          ISSUER_WAIT(&bar_p[u], rp);  // P(j) sits bf16-packed in the first 32 columns of score buffer u
-          ISSUER_WAIT(&bar_v[u], rp);  // V(j) has landed
-          tc_fence_after();
-          if (leader) {
-            const uint32_t acc0 = j > 0 ? 1u : 0u;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16_ts(tmem + T_O, tmem + T_S + u * 64 + kk * 8, umma_desc_pack(loVm + u * 1024 + kk * 128), idesc_o, kk > 0 ? 1u : acc0);
-            umma_commit(bar_o);
-            umma_commit(&bar_vfree[u]);
-            if (j == n - 1) umma_commit(bar_fin);
-          }
-          if (j + 2 < n) issue_s(u, rp ^ 1u);
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------ softmax warps ------------------------------------------
-    const int r = tid;
-    const int qrow = q0 + r;
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    float m_ref = -INFINITY, l_run = 0.f;
-
-    for (int j = 0; j < n; ++j) {
-      const int kv0 = j * 64;
-      mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t sv[64];
-      {
-        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
-        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
-        tmem_ld32(t_lane + T_S + (j & 1) * 64, lo);
-        tmem_ld32(t_lane + T_S + (j & 1) * 64 + 32, hi);
-        tmem_ld_wait();
-      }
-      if (kv0 + 63 > q0) {  // diagonal blocks: causal mask
-#pragma unroll
-        for (int c = 0; c < 64; ++c)
-          if (kv0 + c > qrow) sv[c] = 0xff800000u;  // -inf
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 64; c += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sv[c]));
-        mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;  // scale > 0: max commutes with the scaling
-      if (j == 0) {
-        m_ref = mx;  // block 0 always holds column 0 <= qrow: finite
-      } else {
-        const bool grow = mx > m_ref + FW2_RESCALE_T;
-        if (__any_sync(0xffffffffu, grow)) {  // rare: move the reference of the rows that need it and rescale their output
-          const float m_new = grow ? mx : m_ref;
-          const float alpha = fast_exp2(m_ref - m_new);
-          mbar_wait(bar_o, (j - 1) & 1);  // P V(j-1) (and every earlier one) has landed in the output tile
-          tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(t_lane + T_O + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-            tmem_st32(t_lane + T_O + c * 32, v);
-          }
-          tmem_st_wait();
-          l_run *= alpha;
-          m_ref = m_new;
-        }
-      }
-      uint32_t pk[32];
-      float2 rs = make_float2(0.f, 0.f);
-      const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
-#pragma unroll
-      for (int c = 0; c < 64; c += 2) {  // packed fp32 pairs; every other pair of exponentials on the FMA pipe (exp2_fma2)
-        const float2 pr = exp2_pair<FWD_EXP_FMA_EVERY>(__ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), c >> 1);
-        rs = __fadd2_rn(rs, pr);
-        pk[c >> 1] = pack_bf16x2(pr.x, pr.y);
-      }
-      l_run += rs.x + rs.y;
-      tmem_st32(t_lane + T_S + (j & 1) * 64, pk);  // A operand of the P V MMA, read straight from tensor memory
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&bar_p[j & 1]);
-    }
-    mbar_wait(bar_fin, 0);
-    tc_fence_after();
-    const float inv_l = 1.f / l_run;
-    // output tile -> bf16 -> 128B-swizzled staging tile (the Q buffer: every S MMA has completed) -> TMA store
-    const uint32_t stage_addr = smem_u32(smem + FWD_SQ);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld32(t_lane + T_O + c * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8)
-        sts128(stage_addr + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + c8),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]) * inv_l, __uint_as_float(v[c8 * 8 + 1]) * inv_l),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]) * inv_l, __uint_as_float(v[c8 * 8 + 3]) * inv_l),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]) * inv_l, __uint_as_float(v[c8 * 8 + 5]) * inv_l),
-               pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]) * inv_l, __uint_as_float(v[c8 * 8 + 7]) * inv_l));
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1, 128);
-    if (tid == 0) {
-      tma_store_2d(&tmOut, smem + FWD_SQ, h * HD, row_base + q0);
-      tma_store_2d(&tmOut, smem + FWD_SQ + 16384, h * HD + 64, row_base + q0);
-      tma_store_commit();
-      tma_store_wait_read0();
-    }
-    if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = m_ref + log2f(l_run);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 256);
-  }
-}
-
-// ================================================================================================
 // forward, two query tiles per CTA
 // ================================================================================================
 // Tiles t = 0, 1 own query rows [256*pair + 128*t, +128) and share one K/V ring; while the four softmax warps of one tile
@@ -375,9 +167,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int hk = h / (p.H / p.Hkv);
   const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
   const int q00 = qp * 256, q01 = qp * 256 + 128;
-  const int n0 = (q00 + 128) / 64, n1 = q01 < p.S ? (q01 + 128) / 64 : 0;  // KV blocks each tile needs
+  const int len = row_len(p, b);
+  const int n0 = q00 < len ? (q00 + 128) / 64 : 0, n1 = q01 < len ? (q01 + 128) / 64 : 0;  // KV blocks each tile needs (0: padding only)
   const int n = max(n0, n1);
   auto nt = [&](int t) { return t ? n1 : n0; };
+  if (n0 == 0) {  // both tiles lie in this row's padding (n1 > 0 implies n0 > 0)
+    zero_tile_128(p.out, static_cast<long long>(p.H) * HD, row_base + q00, h * HD, tid, FW2_THREADS);
+    if (q01 < p.S) zero_tile_128(p.out, static_cast<long long>(p.H) * HD, row_base + q01, h * HD, tid, FW2_THREADS);
+    if (p.lse2 && tid < 256 && q00 + tid < p.S) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + q00 + tid] = 0.f;
+    return;
+  }
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ);
@@ -573,261 +372,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_store_wait_read0();
       }
       if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = m_ref + log2f(l_run);
+    } else if (q0 < p.S) {  // this tile holds only padding: zeros (see zero_tile_128)
+      zero_tile_128(p.out, static_cast<long long>(p.H) * HD, row_base + q0, h * HD, r, 128);
+      if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = 0.f;
     }
   }
 
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
-// ================================================================================================
-// backward: delta = rowsum(dO * O)
-// ================================================================================================
-__global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta,
-                                  int B, int S, int H) {
-  // 16 lanes per (token, head): 128 elements -> 8 per lane (one 16-byte load from each tensor), 4 shuffle steps
-  const long long gt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long item = gt >> 4;
-  const long long total = static_cast<long long>(B) * S * H;
-  if (item >= total) return;  // S*H is a multiple of 2: both halves of a warp are either in or out
-  const int sub = threadIdx.x & 15;
-  const int h = static_cast<int>(item % H);
-  const long long tok = item / H;
-  const size_t off = static_cast<size_t>(tok) * H * HD + static_cast<size_t>(h) * HD + sub * 8;
-  const uint4 a = *reinterpret_cast<const uint4*>(out + off);
-  const uint4 d = *reinterpret_cast<const uint4*>(dout + off);
-  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 x = unpack_bf16x2(aw[i]), y = unpack_bf16x2(dw[i]);
-    s = fmaf(x.x, y.x, s);
-    s = fmaf(x.y, y.y, s);
-  }
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (sub == 0) {
-    const int b = static_cast<int>(tok / S), pos = static_cast<int>(tok % S);
-    delta[(static_cast<size_t>(b) * H + h) * S + pos] = s;
-  }
-}
-
-// ================================================================================================
-// backward: dQ — two 128-row query tiles per CTA (groups) ping-ponging on one tensor pipe
-// ================================================================================================
-// Group g owns query rows [256*pair + 128*g, +128): while its four warps turn (S, dP) into dS, the tensor core works for the
-// other group (dQ accumulate, next S / dP).  Both groups read the same K/V ring, so each K/V block is staged once per 256
-// query rows.  The single-tile version of this kernel left the tensor pipe 25% busy (profiles/r01_*attn*).
-constexpr int DQ_SQ = 0;                    // 2 groups x (2 x [128 x 128B])
-constexpr int DQ_SDO = 65536;               // 2 groups x (2 x [128 x 128B])
-constexpr int DQ_NS = 3;                    // K/V ring depth
-constexpr int DQ_SK = 131072;               // DQ_NS slots x (2 x [64 x 128B])
-constexpr int DQ_SV = DQ_SK + DQ_NS * 16384;    // DQ_NS slots x (2 x [64 x 128B])
-constexpr int DQ_BAR = DQ_SV + DQ_NS * 16384;
-constexpr int DQ_SMEM = DQ_BAR + 256 + 1024;
-
-__global__ void __launch_bounds__(DKV_THREADS, 1)
-attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-               const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
-  uint64_t *bar_q = bars, *bar_kv = bars + 1 /*[DQ_NS]*/, *bar_s = bars + 1 + DQ_NS /*[g]*/, *bar_o = bars + 3 + DQ_NS /*[g]*/,
-           *bar_free = bars + 5 + DQ_NS /*[DQ_NS]*/, *bar_p = bars + 5 + 2 * DQ_NS /*[g]*/;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8 + 2 * DQ_NS);
-
-  const int npair = (p.S + 255) / 256;
-  const int qp = npair - 1 - (blockIdx.x % npair);
-  const int bh = blockIdx.x / npair;
-  const int h = bh % p.H, b = bh / p.H;
-  const int row_base = b * p.S;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int hk = h / (p.H / p.Hkv);
-  const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
-  const int q00 = qp * 256, q01 = qp * 256 + 128;
-  const int ng0 = (q00 + 128) / 64, ng1 = q01 < p.S ? (q01 + 128) / 64 : 0;  // KV blocks each group needs
-  const int n = max(ng0, ng1);
-  auto ngf = [&](int g) { return g ? ng1 : ng0; };
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmKV);
-    tma_prefetch_desc(&tmDO);
-    for (int i = 0; i < 5 + 2 * DQ_NS; ++i) mbar_init(&bars[i], 1);
-    mbar_init(&bar_p[0], 128);
-    mbar_init(&bar_p[1], 128);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_ptr, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  // TMEM columns of group g: S 256g, dP 256g + 64, dQ 256g + 128
-
-  if (warp == 9) {
-    // ------------------------------------------ TMA loader ------------------------------------------
-    if ((tid & 31) == 0) {
-      mbar_arrive_expect_tx(bar_q, ng1 > 0 ? 131072 : 65536);
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (ngf(g) == 0) continue;
-        const int q0 = g ? q01 : q00;
-        tma_load_2d(smem + DQ_SQ + g * 32768, &tmQ, bar_q, colQ, row_base + q0);
-        tma_load_2d(smem + DQ_SQ + g * 32768 + 16384, &tmQ, bar_q, colQ + 64, row_base + q0);
-        tma_load_2d(smem + DQ_SDO + g * 32768, &tmDO, bar_q, h * HD, row_base + q0);
-        tma_load_2d(smem + DQ_SDO + g * 32768 + 16384, &tmDO, bar_q, h * HD + 64, row_base + q0);
-      }
-      int slot = 0;
-      uint32_t par = 1;  // parity of the PREVIOUS ring round (first round: nothing to wait for)
-      for (int j = 0; j < n; ++j) {
-        if (j >= DQ_NS) mbar_wait_backoff(&bar_free[slot], par);  // both groups' MMAs of block j - DQ_NS have read the slot
-        mbar_arrive_expect_tx(&bar_kv[slot], 32768);
-        tma_load_2d(smem + DQ_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
-        tma_load_2d(smem + DQ_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
-        tma_load_2d(smem + DQ_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
-        tma_load_2d(smem + DQ_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
-        if (++slot == DQ_NS) { slot = 0; par ^= 1u; }
-      }
-    }
-  } else if (warp == 8) {
-    // ------------------------------------------ MMA issuer (lean: see attn_dkv_kernel) ------------------------------------------
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);
-    const uint32_t loQ = umma_desc_lo(smem_u32(smem + DQ_SQ), 16), loDO = umma_desc_lo(smem_u32(smem + DQ_SDO), 16),
-                   loK = umma_desc_lo(smem_u32(smem + DQ_SK), 16), loV = umma_desc_lo(smem_u32(smem + DQ_SV), 16),
-                   loKm = umma_desc_lo(smem_u32(smem + DQ_SK), 8192);
-    auto issue_s = [&](const int g, const int slot, const uint32_t parity) {  // S_g = Q_g K^T and dP_g = dO_g V^T for the block in `slot`
-      ISSUER_WAIT(&bar_kv[slot], parity);
-      tc_fence_after();
-      if (leader) {
-#pragma unroll
-        for (int k16 = 0; k16 < 8; ++k16)
-          umma_bf16(tmem + g * 256, umma_desc_pack(loQ + g * 2048 + kmaj_lo(k16, 16384)),
-                    umma_desc_pack(loK + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k16 = 0; k16 < 8; ++k16)
-          umma_bf16(tmem + g * 256 + 64, umma_desc_pack(loDO + g * 2048 + kmaj_lo(k16, 16384)),
-                    umma_desc_pack(loV + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
-        umma_commit(&bar_s[g]);
-      }
-    };
-    ISSUER_WAIT(bar_q, 0);
-    issue_s(0, 0, 0);
-    if (ng1 > 0) issue_s(1, 0, 0);
-    uint32_t rp = 0;  // ring round parity of block `base`
-    for (int base = 0; base < n; base += DQ_NS) {
-#pragma unroll
-      for (int u = 0; u < DQ_NS; ++u) {
-        const int j = base + u;
-        if (j < n) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (j < ngf(g)) {
-              ISSUER_WAIT(&bar_p[g], j & 1);  // dS_g(j) sits bf16-packed in the first 32 columns of group g's S tile; dP consumed
-              tc_fence_after();
-              if (leader) {
-                const uint32_t acc0 = j > 0 ? 1u : 0u;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma_bf16_ts(tmem + g * 256 + 128, tmem + g * 256 + kk * 8, umma_desc_pack(loKm + u * 1024 + kk * 128), idesc_dq,
-                               kk > 0 ? 1u : acc0);
-                umma_commit(&bar_o[g]);
-              }
-              if (j + 1 < ngf(g)) issue_s(g, (u + 1) % DQ_NS, (u + 1 >= DQ_NS) ? (rp ^ 1u) : rp);
-            }
-          }
-          if (leader) umma_commit(&bar_free[u]);  // every MMA that reads ring slot u has been issued
-        }
-      }
-      rp ^= 1u;
-    }
-  } else {
-    const int g = warp >> 2, w = warp & 3;
-    const int r = w * 32 + (tid & 31);
-    const int n_mine = ngf(g);
-    const int q0 = g ? q01 : q00;
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(w * 32) << 16) + g * 256;
-    const uint32_t T_S = 0, T_DP = 64, T_DQ = 128;
-    const int qrow = q0 + r;
-    uint64_t *my_s = bar_s + g, *my_o = bar_o + g, *my_p = bar_p + g;
-    float lse2 = 0.f, delta = 0.f;
-    if (n_mine > 0) {
-      const size_t stat_idx = (static_cast<size_t>(b) * p.H + h) * p.S + qrow;
-      lse2 = p.lse2[stat_idx];
-      delta = p.delta[stat_idx];
-    }
-    for (int j = 0; j < n_mine; ++j) {
-      const int kv0 = j * 64;
-      mbar_wait(my_s, j & 1);
-      tc_fence_after();
-      const bool need_mask = (kv0 + 63 > q0);
-      uint32_t pk[32];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(t_lane + T_S + half * 32, sv);
-        tmem_ld32(t_lane + T_DP + half * 32, dv);
-        tmem_ld_wait();
-        if (need_mask) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse2));
-            float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse2));
-            if (kv0 + half * 32 + e > qrow) p0 = 0.f;
-            if (kv0 + half * 32 + e + 1 > qrow) p1 = 0.f;
-            pk[half * 16 + (e >> 1)] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta) * p.scale,
-                                                   p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse2));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse2));
-            pk[half * 16 + (e >> 1)] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta) * p.scale,
-                                                   p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale);
-          }
-        }
-      }
-      tmem_st32(t_lane + T_S, pk);  // A operand of the dQ MMA, read straight from tensor memory
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(my_p);
-    }
-    if (n_mine > 0) {
-      mbar_wait(my_o, (n_mine - 1) & 1);
-      tc_fence_after();
-      // dQ tile -> bf16 -> 128B-swizzled staging tile (this group's Q buffer: every MMA that read it has completed) -> TMA store
-      uint8_t* stage = smem + DQ_SQ + g * 32768;
-      const uint32_t stage_addr = smem_u32(stage);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_lane + T_DQ + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8)
-          sts128(stage_addr + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + c8),
-                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1])),
-                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3])),
-                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5])),
-                 pack_bf16x2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7])));
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1 + g, 128);
-      if (r == 0) {
-        tma_store_2d(&tmOut, stage, colQ, row_base + q0);
-        tma_store_2d(&tmOut, stage + 16384, colQ + 64, row_base + q0);
-        tma_store_commit();
-        tma_store_wait_read0();
-      }
-    }
-  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -876,6 +426,11 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5;
   const int hk = h / (p.H / p.Hkv);
   const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
+  if (q0 >= row_len(p, b)) {  // the tile holds only padding: dQ = 0, delta = 0
+    zero_tile_128(p.dqkv, p.W, row_base + q0, colQ, tid, DKV_THREADS);
+    if (tid < 128) p.delta_w[(static_cast<size_t>(b) * p.H + h) * p.S + q0 + tid] = 0.f;
+    return;
+  }
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ);
@@ -1104,10 +659,10 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32(t_lane + T_DQ + 64 + half * 32, hi);
       tmem_ld_wait();
       if (p.rope_cs) {
-        const float2* cs = p.rope_cs + static_cast<size_t>(half * 32) * p.S + qrow;
+        const float2* cs = p.rope_cs + static_cast<size_t>(half * 32) * p.rope_stride + qrow;
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-          const float2 tcs = __ldg(cs + static_cast<size_t>(jj) * p.S);
+          const float2 tcs = __ldg(cs + static_cast<size_t>(jj) * p.rope_stride);
           const float x0 = __uint_as_float(lo[jj]), x1 = __uint_as_float(hi[jj]);
           lo[jj] = __float_as_uint(x0 * tcs.x + x1 * tcs.y);
           hi[jj] = __float_as_uint(x1 * tcs.x - x0 * tcs.y);
@@ -1181,12 +736,18 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
   const int kv0 = kb * 128;
   const int row_base = b * p.S;
   const int i0 = kv0 / 64;
-  const int nq = p.S / 64 - i0;               // query blocks per query head that see this KV block
+  const int len = row_len(p, b);
+  const int nq = (len + 63) / 64 - i0;        // query blocks per query head that see this KV block and hold a real token
   const int n = nq * grp;                     // streamed (head, query block) pairs; it -> head it / nq, block it % nq
   const int tid = threadIdx.x, warp = tid >> 5;
   const int colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
   const float* g_lse = p.lse2 + (static_cast<size_t>(b) * p.H + hk * grp) * p.S;
   const float* g_delta = p.delta + (static_cast<size_t>(b) * p.H + hk * grp) * p.S;
+  if (kv0 >= len) {  // the KV tile holds only padding: dK = dV = 0
+    zero_tile_128(p.dqkv, p.W, row_base + kv0, colK, tid, (NCW + 2) * 32);
+    zero_tile_128(p.dqkv, p.W, row_base + kv0, colV, tid, (NCW + 2) * 32);
+    return;
+  }
 
   if (tid == 0) {
     tma_prefetch_desc(&tmKV128);
@@ -1365,10 +926,10 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
         tmem_ld32(t_lane + T_DK + c * 32, lo);
         tmem_ld32(t_lane + T_DK + 64 + c * 32, hi);
         tmem_ld_wait();
-        const float2* cs = p.rope_cs + static_cast<size_t>(c * 32) * p.S + kvrow;
+        const float2* cs = p.rope_cs + static_cast<size_t>(c * 32) * p.rope_stride + kvrow;
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-          const float2 tcs = __ldg(cs + static_cast<size_t>(jj) * p.S);
+          const float2 tcs = __ldg(cs + static_cast<size_t>(jj) * p.rope_stride);
           const float x0 = __uint_as_float(lo[jj]), x1 = __uint_as_float(hi[jj]);
           lo[jj] = __float_as_uint(x0 * tcs.x + x1 * tcs.y);
           hi[jj] = __float_as_uint(x1 * tcs.x - x0 * tcs.y);
@@ -1427,25 +988,32 @@ cudaError_t set_smem(const void* fn, int bytes) {
 
 }  // namespace
 
-bool g_attn_fwd_two_tiles = true;
-void attn_set_fwd_two_tiles(bool on) { g_attn_fwd_two_tiles = on; }
-bool g_attn_dq_tmem_operands = true;
-void attn_set_dq_tmem_operands(bool on) { g_attn_dq_tmem_operands = on; }
-int attn_bwd_launches() { return g_attn_dq_tmem_operands ? 2 : 3; }
-bool g_attn_bwd_warps16 = false;  // measured: 16 warps are 1 % slower than 8 (tools/attn_bwd_ab.py): the exp / dS phase is not the limiter
-void attn_set_bwd_warps16(bool on) { g_attn_bwd_warps16 = on; }
-bool attn_bwd_can_rope() { return g_attn_dq_tmem_operands && !g_attn_bwd_warps16; }
+int attn_bwd_launches() { return 2; }
+bool attn_bwd_can_rope() { return true; }
+
+namespace {
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a function: set it once per device
+cudaError_t attn_init_device() {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  if ((e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel), FW2_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(reinterpret_cast<const void*>(attn_dq1_kernel), DQ1_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<8>), DKV_SMEM)) != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return cudaSuccess;
+}
+}  // namespace
 
 cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   if (a.S % 128 || a.B <= 0 || a.H <= 0) return cudaErrorInvalidValue;
-  static bool init = false;
-  if (!init) {
-    cudaError_t e = set_smem(reinterpret_cast<const void*>(attn_fwd_kernel), FWD_SMEM);
-    if (e != cudaSuccess) return e;
-    e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel), FW2_SMEM);
-    if (e != cudaSuccess) return e;
-    init = true;
-  }
+  if (a.window != 0) return cudaErrorInvalidValue;  // sliding-window masks are not implemented (the host refuses seq_len > window)
+  cudaError_t e = attn_init_device();
+  if (e != cudaSuccess) return e;
   const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
   if (a.H % Hkv) return cudaErrorInvalidValue;
   const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD;
@@ -1461,35 +1029,22 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   p.scale_log2 = a.scale * LOG2E;
   p.lse2 = a.lse;
   p.out = a.out;
-  if (g_attn_fwd_two_tiles)
-    attn_fwd2_kernel<<<a.B * a.H * ((a.S + 255) / 256), FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p);
-  else
-    attn_fwd_kernel<<<a.B * a.H * (a.S / 128), ATT_THREADS, FWD_SMEM, s>>>(tmQ, tmKV, tmOut, p);
+  p.seq_lens = a.seq_lens;
+  attn_fwd2_kernel<<<a.B * a.H * ((a.S + 255) / 256), FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p);
   return cudaGetLastError();
 }
 
 cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (a.S % 128 || a.B <= 0 || a.H <= 0 || !a.delta || !a.lse || !a.dout || !a.dqkv) return cudaErrorInvalidValue;
-  if (a.rope_cs && !attn_bwd_can_rope()) return cudaErrorInvalidValue;  // only the one-tile dQ kernel and the 8-warp dK/dV kernel rotate
-  static bool init = false;
-  if (!init) {
-    cudaError_t e = set_smem(reinterpret_cast<const void*>(attn_dq_kernel), DQ_SMEM);
-    if (e != cudaSuccess) return e;
-    e = set_smem(reinterpret_cast<const void*>(attn_dq1_kernel), DQ1_SMEM);
-    if (e != cudaSuccess) return e;
-    e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<8>), DKV_SMEM);
-    if (e != cudaSuccess) return e;
-    e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<16>), DKV_SMEM);
-    if (e != cudaSuccess) return e;
-    init = true;
-  }
+  if (a.window != 0) return cudaErrorInvalidValue;
+  cudaError_t e = attn_init_device();
+  if (e != cudaSuccess) return e;
   const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
   if (a.H % Hkv) return cudaErrorInvalidValue;
   const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD,
                  WO = static_cast<uint64_t>(a.H) * HD;
   CUtensorMap tmQ128, tmKV64, tmDO128, tmKV128, tmQ64, tmDO64, tmDqkv, tmO128;
-  if (!make_tmap_2d_bf16(&tmO128, a.out, static_cast<uint64_t>(a.H) * HD, static_cast<uint64_t>(a.B) * a.S, static_cast<uint64_t>(a.H) * HD, 64, 128))
-    return cudaErrorInvalidValue;
+  if (!make_tmap_2d_bf16(&tmO128, a.out, WO, M, WO, 64, 128)) return cudaErrorInvalidValue;
   bool ok = make_tmap_2d_bf16(&tmQ128, a.qkv, W, M, W, 64, 128) && make_tmap_2d_bf16(&tmKV64, a.qkv, W, M, W, 64, 64) &&
             make_tmap_2d_bf16(&tmDqkv, a.dqkv, W, M, W, 64, 128) &&
             make_tmap_2d_bf16(&tmDO128, a.dout, WO, M, WO, 64, 128) && make_tmap_2d_bf16(&tmDO64, a.dout, WO, M, WO, 64, 64);
@@ -1507,20 +1062,10 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   p.delta_w = a.delta;
   p.dqkv = a.dqkv;
   p.rope_cs = a.rope_cs;
-  if (!g_attn_dq_tmem_operands) {  // the one-tile dQ kernel computes delta itself
-    const long long items = static_cast<long long>(a.B) * a.S * a.H;
-    const int block = 256;
-    const long long grid = (items * 16 + block - 1) / block;
-    attn_delta_kernel<<<static_cast<unsigned>(grid), block, 0, s>>>(a.out, a.dout, a.delta, a.B, a.S, a.H);
-  }
-  if (g_attn_dq_tmem_operands)
-    attn_dq1_kernel<<<a.B * a.H * (a.S / 128), DKV_THREADS, DQ1_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmO128, tmDqkv, p);
-  else
-    attn_dq_kernel<<<a.B * a.H * ((a.S + 255) / 256), DKV_THREADS, DQ_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmDqkv, p);
-  if (g_attn_bwd_warps16)
-    attn_dkv_kernel<16><<<a.B * Hkv * (a.S / 128), 18 * 32, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
-  else
-    attn_dkv_kernel<8><<<a.B * Hkv * (a.S / 128), 10 * 32, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
+  p.rope_stride = a.rope_stride > 0 ? a.rope_stride : a.S;
+  p.seq_lens = a.seq_lens;
+  attn_dq1_kernel<<<a.B * a.H * (a.S / 128), DKV_THREADS, DQ1_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmO128, tmDqkv, p);
+  attn_dkv_kernel<8><<<a.B * Hkv * (a.S / 128), 10 * 32, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
   return cudaGetLastError();
 }
 

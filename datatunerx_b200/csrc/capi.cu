@@ -27,6 +27,20 @@ int32_t dtx_gemm_bf16(const void* A, int64_t lda, int32_t a_mn, const void* B, i
   return rc(gemm_bf16(g, S(stream)));
 }
 
+int32_t dtx_gemm_fused(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t b_mn, const void* A2, int64_t lda2,
+                       const void* B2, int64_t ldb2, int32_t K2, void* C, int64_t ldc, void* aux, int64_t ld_aux, const void* rope_cs,
+                       int32_t rope_S, int32_t rope_cols, int32_t M, int32_t N, int32_t K, int32_t epilogue, void* stream) {
+  if (epilogue < EPI_ROPE || epilogue > EPI_SWIGLU_BWD) return DTX_ERR_INVALID;
+  GemmArgs g;
+  g.A = static_cast<const bf16*>(A); g.lda = lda;
+  g.B = static_cast<const bf16*>(B); g.ldb = ldb; g.b_mn_major = b_mn;
+  g.A2 = static_cast<const bf16*>(A2); g.lda2 = lda2; g.B2 = static_cast<const bf16*>(B2); g.ldb2 = ldb2; g.K2 = K2;
+  g.C = C; g.ldc = ldc; g.aux = aux; g.ld_aux = ld_aux;
+  g.rope_cs = static_cast<const float2*>(rope_cs); g.rope_S = rope_S; g.rope_cols = rope_cols;
+  g.M = M; g.N = N; g.K = K; g.epilogue = epilogue;
+  return rc(gemm_bf16(g, S(stream)));
+}
+
 int32_t dtx_set_option(const char* name, int32_t value) {
   if (!name) return DTX_ERR_INVALID;
   if (strcmp(name, "gemm_pair_kernel") == 0) {
@@ -39,18 +53,6 @@ int32_t dtx_set_option(const char* name, int32_t value) {
   }
   if (strcmp(name, "fused_epilogues") == 0) {
     trainer_set_fused_epilogues(value);
-    return DTX_OK;
-  }
-  if (strcmp(name, "attn_dq_tmem_operands") == 0) {
-    attn_set_dq_tmem_operands(value != 0);
-    return DTX_OK;
-  }
-  if (strcmp(name, "attn_bwd_warps16") == 0) {
-    attn_set_bwd_warps16(value != 0);
-    return DTX_OK;
-  }
-  if (strcmp(name, "attn_fwd_two_tiles") == 0) {
-    attn_set_fwd_two_tiles(value != 0);
     return DTX_OK;
   }
   return DTX_ERR_INVALID;
@@ -103,6 +105,12 @@ int32_t dtx_lora_dropout_bwd_add(void* dh, const void* g, int32_t M, int32_t d, 
 int32_t dtx_nf4_roundtrip(void* w_bf16, int64_t n, void* stream) {
   return rc(nf4_roundtrip_bf16(static_cast<bf16*>(w_bf16), n, S(stream)));
 }
+int32_t dtx_nf4_pack(const void* w_bf16, void* packed, void* absmax, int64_t n, void* stream) {
+  return rc(nf4_quantize_pack(static_cast<const bf16*>(w_bf16), static_cast<uint8_t*>(packed), static_cast<float*>(absmax), n, S(stream)));
+}
+int32_t dtx_nf4_dequant(const void* packed, const void* absmax, void* w_bf16, int64_t n, void* stream) {
+  return rc(nf4_dequant_bf16(static_cast<const uint8_t*>(packed), static_cast<const float*>(absmax), static_cast<bf16*>(w_bf16), n, S(stream)));
+}
 int32_t dtx_cross_entropy(const void* logits, int64_t ldl, const void* labels, void* shifted, void* n_valid, void* row_loss,
                           void* dlogits, int64_t ldd, void* loss_out, int32_t B, int32_t Sq, int32_t V, void* stream) {
   cudaError_t e = shift_labels(static_cast<const int32_t*>(labels), static_cast<int32_t*>(shifted), static_cast<int32_t*>(n_valid), B,
@@ -131,21 +139,25 @@ int32_t dtx_adamw(void* p, const void* g, void* m, void* v, int64_t n, float lr,
   return rc(adamw_step(a, S(stream)));
 }
 int32_t dtx_attn_fwd(const void* qkv, void* out, void* lse2, int32_t B, int32_t Sq, int32_t H, int32_t Hkv, float scale,
-                     void* stream) {
+                     const void* seq_lens, int32_t window, void* stream) {
   AttnArgs a;
   a.Hkv = Hkv;
   a.qkv = static_cast<const bf16*>(qkv); a.out = static_cast<bf16*>(out); a.lse = static_cast<float*>(lse2);
   a.B = B; a.S = Sq; a.H = H; a.scale = scale;
+  a.seq_lens = static_cast<const int32_t*>(seq_lens); a.window = window;
   return rc(attn_fwd(a, S(stream)));
 }
 int32_t dtx_attn_bwd(const void* qkv, const void* out, const void* dout, const void* lse2, void* delta, void* dqkv, int32_t B,
-                     int32_t Sq, int32_t H, int32_t Hkv, float scale, void* stream) {
+                     int32_t Sq, int32_t H, int32_t Hkv, float scale, const void* seq_lens, int32_t window, const void* rope_cs_t,
+                     int32_t rope_stride, void* stream) {
   AttnArgs a;
   a.Hkv = Hkv;
   a.qkv = static_cast<const bf16*>(qkv); a.out = const_cast<bf16*>(static_cast<const bf16*>(out));
   a.lse = const_cast<float*>(static_cast<const float*>(lse2)); a.dout = static_cast<const bf16*>(dout);
   a.delta = static_cast<float*>(delta); a.dqkv = static_cast<bf16*>(dqkv);
   a.B = B; a.S = Sq; a.H = H; a.scale = scale;
+  a.seq_lens = static_cast<const int32_t*>(seq_lens); a.window = window;
+  a.rope_cs = static_cast<const float2*>(rope_cs_t); a.rope_stride = rope_stride;
   return rc(attn_bwd(a, S(stream)));
 }
 

@@ -526,9 +526,10 @@ __global__ void cast2d_kernel(const float* __restrict__ src, long long lds, bf16
 
 // ------------------------------------------------------------------------------------------
 // QLoRA base weights (cmd/tuning/train.py:224-230: BitsAndBytesConfig(load_in_4bit, nf4, no double quant), bitsandbytes
-// 0.41.3).  On a 180 GB B200 there is no reason to keep 7-13B frozen weights packed: the weights are replaced ONCE at load
-// time by dequant(quant(W)) — exactly the values bitsandbytes' 4-bit matmul multiplies with — and every GEMM keeps
-// running on resident bf16.  Block-wise: 64 consecutive elements share one fp32 absmax; codes are the 16 NF4 levels.
+// 0.41.3).  Block-wise: 64 consecutive elements share one fp32 absmax; codes are the 16 NF4 levels.  The trainer keeps the
+// decoder weights PACKED (nf4_pack_kernel: 0.5625 B per weight) and expands a matrix into a bf16 scratch right before the
+// GEMM that needs it (nf4_dequant_kernel); nf4_roundtrip_kernel (quantise + dequantise in place) is the same arithmetic in
+// one kernel, kept for the per-kernel parity test.
 // ------------------------------------------------------------------------------------------
 __constant__ float kNF4[16] = {-1.0f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f,
                                -0.28444138169288635f, -0.18477343022823334f, -0.09105003625154495f, 0.0f,
@@ -566,20 +567,94 @@ __global__ void nf4_roundtrip_kernel(bf16* __restrict__ w, long long nblocks) {
     }
   }
 }
-// row-wise absmax int8 (the weight side of LLM.int8; the reference's runtime outlier decomposition is NOT reproduced)
-__global__ void int8_rowwise_roundtrip_kernel(bf16* __restrict__ w, int rows, int cols) {
-  const int row = blockIdx.x;
-  __shared__ float sh[32];
-  bf16* r = w + static_cast<long long>(row) * cols;
-  float amax = 0.f;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) amax = fmaxf(amax, fabsf(__bfloat162float(r[i])));
-  amax = warp_max(amax);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = amax;
+// Packed storage: one thread per 64-element block.  Byte layout as bitsandbytes kQuantizeBlockwise<..., NF4>: the first
+// element of a pair sits in the high nibble.
+__global__ void nf4_pack_kernel(const bf16* __restrict__ w, uint8_t* __restrict__ q, float* __restrict__ absmax, long long nblocks) {
+  for (long long b = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; b < nblocks;
+       b += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4* p = reinterpret_cast<const uint4*>(w + b * 64);
+    float v[64];
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float f[8];
+      bf16x8_to_f32(p[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i * 8 + j] = f[j];
+        amax = fmaxf(amax, fabsf(f[j]));
+      }
+    }
+    const float inv = amax > 0.f ? 1.0f / amax : 0.f;
+    absmax[b] = amax;
+    uint32_t words[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t wd = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t byte = (static_cast<uint32_t>(nf4_code(v[i * 8 + 2 * j] * inv)) << 4) |
+                              static_cast<uint32_t>(nf4_code(v[i * 8 + 2 * j + 1] * inv));
+        wd |= byte << (8 * j);
+      }
+      words[i] = wd;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(q + b * 32);
+    dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
+    dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
+  }
+}
+// Expansion: one thread per 16 packed bytes (32 weights, half a block): 16 B + 4 B read, 64 B written; the 16 levels
+// live in shared memory as bf16-rounded-on-store fp32 products (level * absmax, rounded to bf16 = what bitsandbytes'
+// dequantize_4bit yields after the cast to the compute dtype).
+__global__ void __launch_bounds__(256) nf4_dequant_kernel(const uint8_t* __restrict__ q, const float* __restrict__ absmax,
+                                                          bf16* __restrict__ w, long long nhalf) {
+  __shared__ float lv[16];
+  if (threadIdx.x < 16) lv[threadIdx.x] = kNF4[threadIdx.x];
   __syncthreads();
-  amax = sh[0];
-  for (int i = 1; i < (blockDim.x >> 5); ++i) amax = fmaxf(amax, sh[i]);
-  const float sc = amax > 0.f ? 127.0f / amax : 0.f, isc = amax / 127.0f;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) r[i] = __float2bfloat16_rn(rintf(__bfloat162float(r[i]) * sc) * isc);
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < nhalf;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 pk = ldg_stream(reinterpret_cast<const uint4*>(q) + t);
+    const float am = __ldg(absmax + (t >> 1));
+    const uint32_t words[4] = {pk.x, pk.y, pk.z, pk.w};
+    uint4* dst = reinterpret_cast<uint4*>(w + t * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t byte = (words[i] >> (8 * j)) & 0xFFu;
+        f[2 * j] = lv[byte >> 4] * am;
+        f[2 * j + 1] = lv[byte & 15u] * am;
+      }
+      dst[i] = f32_to_bf16x8(f);
+    }
+  }
+}
+
+// per-sequence loss sum / valid-token count (evaluation: lets the host form HF's eval batches of any size)
+__global__ void row_loss_stats_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ labels, int S,
+                                      float* __restrict__ row_sum, int32_t* __restrict__ row_valid) {
+  __shared__ float sh[32];
+  __shared__ int shc[32];
+  const int b = blockIdx.x;
+  double acc = 0.0;
+  int cnt = 0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    acc += static_cast<double>(row_loss[static_cast<size_t>(b) * S + i]);
+    cnt += labels[static_cast<size_t>(b) * S + i] >= 0 ? 1 : 0;
+  }
+  float v = block_sum(static_cast<float>(acc), sh);
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) shc[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) c += shc[i];
+    row_sum[b] = v;
+    row_valid[b] = c;
+  }
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -704,8 +779,19 @@ cudaError_t nf4_roundtrip_bf16(bf16* w, int64_t n, cudaStream_t s) {
   nf4_roundtrip_kernel<<<grid_for(n / 64, 128), 128, 0, s>>>(w, n / 64);
   return cudaGetLastError();
 }
-cudaError_t int8_rowwise_roundtrip_bf16(bf16* w, int rows, int cols, cudaStream_t s) {
-  int8_rowwise_roundtrip_kernel<<<rows, 256, 0, s>>>(w, rows, cols);
+cudaError_t nf4_quantize_pack(const bf16* w, uint8_t* q, float* absmax, int64_t n, cudaStream_t s) {
+  if (n % 64) return cudaErrorInvalidValue;
+  nf4_pack_kernel<<<grid_for(n / 64, 128), 128, 0, s>>>(w, q, absmax, n / 64);
+  return cudaGetLastError();
+}
+cudaError_t nf4_dequant_bf16(const uint8_t* q, const float* absmax, bf16* w, int64_t n, cudaStream_t s) {
+  if (n % 64) return cudaErrorInvalidValue;
+  nf4_dequant_kernel<<<grid_for(n / 32, 256), 256, 0, s>>>(q, absmax, w, n / 32);
+  return cudaGetLastError();
+}
+cudaError_t row_loss_stats(const float* row_loss, const int32_t* shifted_labels, int B, int S, float* row_sum, int32_t* row_valid,
+                           cudaStream_t s) {
+  row_loss_stats_kernel<<<B, 256, 0, s>>>(row_loss, shifted_labels, S, row_sum, row_valid);
   return cudaGetLastError();
 }
 

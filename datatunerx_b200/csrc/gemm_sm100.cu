@@ -653,16 +653,31 @@ int gemm_num_sms() {
 
 namespace {
 
+// runs `fn` once per CUDA device (thread-safe): function attributes are per-device state
+struct DeviceOnce {
+  std::mutex mu;
+  bool done[64] = {false};
+  template <typename F>
+  cudaError_t run(F fn) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = fn();
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+  }
+};
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 cudaError_t launch(const GemmArgs& a, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static DeviceOnce attr;  // the attribute is per device: a second trainer on another GPU of the same process needs it too
+  if (cudaError_t e = attr.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
+      e != cudaSuccess)
+    return e;
   CUtensorMap tA, tB, tA2, tB2;
   bool ok = true;
   // K-major operand: global [rows, K], box {64 k, rows_per_tile}; MN-major: global [K, cols], box {64 cols, 64 k}
@@ -725,12 +740,12 @@ int g_pair_group_m = G2_GROUP_M;
 template <bool B_MN, int EPI>
 cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
   auto kern = gemm2_kernel<B_MN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES + g2_out_stage_bytes(EPI));
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static DeviceOnce attr;
+  if (cudaError_t e = attr.run([&] {
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES + g2_out_stage_bytes(EPI));
+      });
+      e != cudaSuccess)
+    return e;
   CUtensorMap tA, tB, tA2, tB2, tC;
   bool ok = true;
   if (EPI == EPI_SWIGLU_BWD)  // d(gate|up) [M, 2N] bf16, stored in [128 x 64] boxes

@@ -44,11 +44,8 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s);
 int gemm_num_sms();
 // 1 (default): wide GEMMs use the CTA-pair (cta_group::2) kernel; 0: single-CTA kernel everywhere (A/B measurements)
 void gemm_set_pair_kernel(int on);
-bool attn_bwd_can_rope();  // the selected backward kernels can apply the inverse rotary themselves
-int attn_bwd_launches();  // kernels one attn_bwd() call launches (2 with the one-tile dQ kernel, which also produces delta; else 3)
-void attn_set_dq_tmem_operands(bool on);  // 1 (default): one-tile dQ kernel with Q / dO resident in tensor memory; 0: two-group kernel
-void attn_set_bwd_warps16(bool on);     // 1: 16 compute warps in the dK/dV kernel; 0 (default): 8
-void attn_set_fwd_two_tiles(bool on);  // 1 (default): two query tiles per CTA, output accumulated in tensor memory
+bool attn_bwd_can_rope();  // the backward kernels apply the inverse rotary themselves when AttnArgs::rope_cs is set
+int attn_bwd_launches();   // kernels one attn_bwd() call launches (dQ (+ delta) and dK/dV)
 void gemm_set_pair_group_m(int tiles);  // rasterisation group height of the pair kernel, in 256-row tiles
 // 1 (default): RoPE / SwiGLU run inside GEMM and attention epilogues; 0: separate HBM-bound kernels (A/B, tiny M)
 void trainer_set_fused_epilogues(int on);
@@ -63,7 +60,15 @@ struct AttnArgs {
   int B = 0, S = 0, H = 0;
   int Hkv = 0;                // kv heads; 0 = H (multi-head attention)
   float scale = 0.f;
+  // Optional true row lengths (device int32 [B]): rows are right-padded beyond them.  Query / KV tiles that lie entirely in a
+  // row's padding are skipped and their outputs (out, dq, dk, dv) written as zeros, the dK/dV kernel stops at the last query
+  // block that holds a real token.  nullptr = every row is S long.
+  const int32_t* seq_lens = nullptr;
+  // Sliding-window attention (Mistral): query i sees keys j with i - window <= j <= i  (transformers 4.34.0
+  // _make_sliding_window_causal_mask: triu(diagonal=-sliding_window)); 0 = plain causal.
+  int window = 0;
   // backward
+  int rope_stride = 0;              // row stride (positions) of the transposed rope table; 0 = S
   const float2* rope_cs = nullptr;  // backward only: TRANSPOSED table [64][S] (cos, sin); if set, dq and dk get the inverse rotary applied before the store
   const bf16* dout = nullptr;  // [B*S, H*D]
   bf16* dqkv = nullptr;        // [B*S, (H + 2*Hkv)*D]
@@ -120,9 +125,14 @@ cudaError_t lora_dropout_bwd_add(bf16* dh, const bf16* g, int M, int d, int nt, 
 // fp32 -> bf16 with scale, strided 2-D (used to refresh the bf16 LoRA shadows)
 cudaError_t cast_f32_to_bf16_2d(const float* src, int64_t lds, bf16* dst, int64_t ldd, int rows, int cols, float scale,
                                 int transpose, cudaStream_t s);
-// w <- dequant(quant(w)) in place: NF4 with 64-element absmax blocks (bitsandbytes 4-bit, no double quantisation) / row-wise int8
+// w <- dequant(quant(w)) in place: NF4 with 64-element absmax blocks (bitsandbytes 4-bit, no double quantisation)
 cudaError_t nf4_roundtrip_bf16(bf16* w, int64_t n, cudaStream_t s);
-cudaError_t int8_rowwise_roundtrip_bf16(bf16* w, int rows, int cols, cudaStream_t s);
+// packed NF4 storage (bitsandbytes quantize_4bit layout): q[i] = code(w[2i]) << 4 | code(w[2i+1]), absmax[b] = max |w| of block b
+cudaError_t nf4_quantize_pack(const bf16* w, uint8_t* q, float* absmax, int64_t n, cudaStream_t s);
+cudaError_t nf4_dequant_bf16(const uint8_t* q, const float* absmax, bf16* w, int64_t n, cudaStream_t s);
+// per sequence: row_sum[b] = sum of row_loss over the S tokens of sequence b, row_valid[b] = tokens with a label >= 0
+cudaError_t row_loss_stats(const float* row_loss, const int32_t* shifted_labels, int B, int S, float* row_sum, int32_t* row_valid,
+                           cudaStream_t s);
 cudaError_t fill_normal_bf16(bf16* p, int64_t n, float std, uint64_t seed, cudaStream_t s);
 cudaError_t fill_const_bf16(bf16* p, int64_t n, float v, cudaStream_t s);
 

@@ -21,6 +21,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -65,6 +66,7 @@ NcclApi* nccl_api() {
   return &api;
 }
 constexpr int kNcclFloat32 = 7;
+constexpr int kNcclFloat64 = 8;
 constexpr int kNcclSum = 0;
 
 thread_local std::string g_error;
@@ -135,7 +137,12 @@ struct Layer {
   bf16 *h1 = nullptr, *t = nullptr, *qkv = nullptr, *attn = nullptr, *x_mid = nullptr, *gu = nullptr;  // saved
   bf16* hd = nullptr;  // LoRA dropout only: [M, nt*d] dropped copies of h1, one per target (peft: one nn.Dropout per module)
   float *lse = nullptr, *rstd1 = nullptr, *rstd2 = nullptr;
+  // --quantization int4: packed NF4 codes (two per byte) + one fp32 absmax per 64 elements; the bf16 pointers above are then
+  // null and the GEMMs read a per-trainer scratch that dequantize() fills right before each launch
+  uint8_t* q4[4] = {nullptr, nullptr, nullptr, nullptr};   // wqkv, wo, wgu, wdown
+  float* absmax[4] = {nullptr, nullptr, nullptr, nullptr};
 };
+enum { W_QKV = 0, W_O = 1, W_GU = 2, W_DOWN = 3 };
 
 }  // namespace
 void trainer_set_fused_epilogues(int on) { g_fused_epilogues = on; }
@@ -154,7 +161,9 @@ struct dtx_trainer {
   std::vector<void*> allocs;
   size_t bytes_allocated = 0;
 
-  int M = 0, RP = 0, nt = 0;
+  int M = 0, RP = 0, nt = 0;    // M = micro_batch * seq_len: the largest batch this trainer was created for
+  int cur_S = 0, cur_M = 0;     // padded length / token count of the batch being processed (<= seq_len / M)
+  bool use_seq_lens = false;    // d_seq_lens holds this batch's true row lengths
   int dq = 0, dkv = 0, W = 0;  // q width (= hidden), k/v width (n_kv_heads*128), packed qkv row width
   int KA = 0;                  // contraction length of the LoRA down-projection: d, or nt*d with dropout
   bool dropout = false;
@@ -174,13 +183,26 @@ struct dtx_trainer {
        *dattn = nullptr, *dqkv = nullptr, *dt = nullptr, *dlogits = nullptr, *glora = nullptr;
   float *logits = nullptr, *rstdf = nullptr, *row_loss = nullptr, *delta = nullptr, *part_b = nullptr, *part_a = nullptr;
   float *d_loss = nullptr, *d_sumsq = nullptr, *d_gnorm = nullptr, *d_scratch = nullptr;
-  int32_t *d_ids = nullptr, *d_labels = nullptr, *d_shift = nullptr, *d_nvalid = nullptr;
+  int32_t *d_ids = nullptr, *d_labels = nullptr, *d_shift = nullptr, *d_nvalid = nullptr, *d_seq_lens = nullptr;
+  float* d_row_sum = nullptr;     // [micro_batch] per-row summed token loss (evaluation)
+  int32_t* d_row_valid = nullptr; // [micro_batch] per-row valid-token count
+  double* d_host_red = nullptr;   // staging for dtx_allreduce_host
+  int window = 0;                 // sliding-window attention span (0 = plain causal)
+  bool quant4 = false;
+  bf16* scratch_w[4] = {nullptr, nullptr, nullptr, nullptr};  // dequantised wqkv / wo / wgu / wdown of the layer in flight
+  int64_t base_bytes = 0;
   float2* rope_cs = nullptr;
   float2* rope_cs_t = nullptr;  // the same table transposed to [D/2][S]: coalesced when thread r needs position q0 + r (attention backward epilogues)
   int split_b = 1, split_a = 1;
 
-  bool weights_loaded[8] = {false};
-  bool have_weights = false, have_lora = false;
+  // which base tensors have been uploaded: [0] embed, [1] lm_head, [2] final norm, then 9 per layer
+  // (q, k, v, o, gate, up, down, norm1, norm2); a step with a hole in this map would train on uninitialised memory
+  std::vector<uint8_t> loaded;
+  bool all_random = false;
+  bool have_lora = false;
+  cudaEvent_t ev_fb = nullptr, ev_ar = nullptr;
+  float seg_ms[4] = {0.f, 0.f, 0.f, 0.f};
+  cudaStream_t copy_stream = nullptr;
   int micro_idx = 0;
   int opt_step = 0;
   int64_t launches = 0;
@@ -209,6 +231,31 @@ struct dtx_trainer {
     *p = static_cast<T*>(q);
     return true;
   }
+  void release(void* p, size_t bytes) {
+    if (!p) return;
+    for (size_t i = 0; i < allocs.size(); ++i)
+      if (allocs[i] == p) {
+        allocs[i] = allocs.back();
+        allocs.pop_back();
+        break;
+      }
+    cudaFree(p);
+    bytes_allocated -= bytes;
+  }
+  // first base tensor that has not been loaded, or nullptr when the model is complete
+  const char* missing_weight(char* buf, size_t n) const {
+    if (all_random) return nullptr;
+    static const char* top[3] = {"model.embed_tokens.weight", "lm_head.weight", "model.norm.weight"};
+    static const char* per[9] = {"self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj", "mlp.gate_proj",
+                                 "mlp.up_proj", "mlp.down_proj", "input_layernorm", "post_attention_layernorm"};
+    for (size_t i = 0; i < loaded.size(); ++i)
+      if (!loaded[i]) {
+        if (i < 3) snprintf(buf, n, "%s", top[i]);
+        else snprintf(buf, n, "model.layers.%zu.%s.weight", (i - 3) / 9, per[(i - 3) % 9]);
+        return buf;
+      }
+    return nullptr;
+  }
 };
 
 namespace {
@@ -218,6 +265,13 @@ namespace {
     cudaError_t _e = (expr);                                                                     \
     if (_e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
     t->launches += (nlaunch);                                                                    \
+  } while (0)
+
+// checked copies / fills outside the hot loop (no launch counted)
+#define CKM(expr)                                                                                \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
 // key of the dropout masks of one (forward pass, layer): the per-element keep decision is
@@ -249,8 +303,10 @@ int create_buffers(dtx_trainer* t) {
   ok = ok && t->alloc(&t->embed, V * d) && t->alloc(&t->lm_head, V * d) && t->alloc(&t->normf, d);
   ok = ok && t->alloc(&t->a_cat_all, L * RP * KA) && t->alloc(&t->b_ext_all, L * W * RP);
   if (!ok) return DTX_ERR_CUDA;
-  cudaMemset(t->a_cat_all, 0, L * RP * KA * sizeof(bf16));
-  cudaMemset(t->b_ext_all, 0, L * W * RP * sizeof(bf16));
+  CKM(cudaMemset(t->a_cat_all, 0, L * RP * KA * sizeof(bf16)));
+  CKM(cudaMemset(t->b_ext_all, 0, L * W * RP * sizeof(bf16)));
+  t->base_bytes = static_cast<int64_t>((2 * V * d + d) * sizeof(bf16));
+  t->loaded.assign(3 + 9 * L, 0);
   t->layers.resize(L);
   t->xs.resize(L + 1);
   for (size_t l = 0; l <= L; ++l) ok = ok && t->alloc(&t->xs[l], M * d);
@@ -258,6 +314,7 @@ int create_buffers(dtx_trainer* t) {
     Layer& y = t->layers[l];
     ok = ok && t->alloc(&y.wqkv, W * d) && t->alloc(&y.wo, d * d) && t->alloc(&y.wgu, 2 * F * d) &&
          t->alloc(&y.wdown, d * F) && t->alloc(&y.norm1, d) && t->alloc(&y.norm2, d);
+    t->base_bytes += static_cast<int64_t>((W * d + d * d + 3 * F * d + 2 * d) * sizeof(bf16));
     y.a_cat = t->a_cat_all + l * RP * KA;
     y.b_ext = t->b_ext_all + l * W * RP;
     ok = ok && t->alloc(&y.h1, M * d) && t->alloc(&y.t, M * RP) && t->alloc(&y.qkv, M * W) &&
@@ -270,10 +327,10 @@ int create_buffers(dtx_trainer* t) {
   ok = ok && t->alloc(&t->params, t->n_train) && t->alloc(&t->grads, t->n_train) && t->alloc(&t->adam_m, t->n_train) &&
        t->alloc(&t->adam_v, t->n_train);
   if (!ok) return DTX_ERR_CUDA;
-  cudaMemset(t->params, 0, t->n_train * sizeof(float));
-  cudaMemset(t->grads, 0, t->n_train * sizeof(float));
-  cudaMemset(t->adam_m, 0, t->n_train * sizeof(float));
-  cudaMemset(t->adam_v, 0, t->n_train * sizeof(float));
+  CKM(cudaMemset(t->params, 0, t->n_train * sizeof(float)));
+  CKM(cudaMemset(t->grads, 0, t->n_train * sizeof(float)));
+  CKM(cudaMemset(t->adam_m, 0, t->n_train * sizeof(float)));
+  CKM(cudaMemset(t->adam_v, 0, t->n_train * sizeof(float)));
   ok = ok && t->alloc(&t->h2, M * d) && t->alloc(&t->act, M * F) && t->alloc(&t->dact, M * F) && t->alloc(&t->dgu, M * 2 * F) &&
        t->alloc(&t->dx_a, M * d) && t->alloc(&t->dx_b, M * d) && t->alloc(&t->dh, M * d) && t->alloc(&t->dattn, M * d) &&
        t->alloc(&t->dqkv, M * W) && t->alloc(&t->dt, M * RP) && t->alloc(&t->dlogits, M * V) && t->alloc(&t->logits, M * V) &&
@@ -287,6 +344,8 @@ int create_buffers(dtx_trainer* t) {
   if (t->dropout) ok = ok && t->alloc(&t->glora, M * KA);
   ok = ok && t->alloc(&t->d_loss, 4) && t->alloc(&t->d_sumsq, 4) && t->alloc(&t->d_gnorm, 4) && t->alloc(&t->d_scratch, 1024);
   ok = ok && t->alloc(&t->d_ids, M) && t->alloc(&t->d_labels, M) && t->alloc(&t->d_shift, M) && t->alloc(&t->d_nvalid, 4);
+  ok = ok && t->alloc(&t->d_seq_lens, static_cast<size_t>(tc.micro_batch)) && t->alloc(&t->d_row_sum, static_cast<size_t>(tc.micro_batch)) &&
+       t->alloc(&t->d_row_valid, static_cast<size_t>(tc.micro_batch)) && t->alloc(&t->d_host_red, 64);
   ok = ok && t->alloc(&t->rope_cs, static_cast<size_t>(tc.seq_len) * (mc.head_dim / 2));
   ok = ok && t->alloc(&t->rope_cs_t, static_cast<size_t>(tc.seq_len) * (mc.head_dim / 2));
   if (!ok) return DTX_ERR_CUDA;
@@ -302,11 +361,11 @@ int create_buffers(dtx_trainer* t) {
         cs[static_cast<size_t>(pos) * half + i] = make_float2(static_cast<float>(cos(static_cast<double>(ang))),
                                                               static_cast<float>(sin(static_cast<double>(ang))));
       }
-    cudaMemcpy(t->rope_cs, cs.data(), cs.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    CKM(cudaMemcpy(t->rope_cs, cs.data(), cs.size() * sizeof(float2), cudaMemcpyHostToDevice));
     std::vector<float2> cst(cs.size());
     for (int pos = 0; pos < tc.seq_len; ++pos)
       for (int i = 0; i < half; ++i) cst[static_cast<size_t>(i) * tc.seq_len + pos] = cs[static_cast<size_t>(pos) * half + i];
-    cudaMemcpy(t->rope_cs_t, cst.data(), cst.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    CKM(cudaMemcpy(t->rope_cs_t, cst.data(), cst.size() * sizeof(float2), cudaMemcpyHostToDevice));
   }
   return DTX_OK;
 }
@@ -335,16 +394,45 @@ int refresh_shadows(dtx_trainer* t) {
   return DTX_OK;
 }
 
-// forward (+ backward) of one micro-batch whose ids/labels are already in t->d_ids / t->d_labels
+// Frozen base weight `which` of layer y for the next GEMM.  bf16-resident: the pointer.  --quantization int4: the packed NF4
+// codes are expanded into the per-trainer scratch first (HBM-bound: 0.56 B read + 2 B written per weight, ~85 us per layer
+// of a 7B model and direction) - the values are exactly bitsandbytes' dequantize_4bit output, so the GEMM sees what the
+// reference's 4-bit matmul multiplies with.
+int base_weight(dtx_trainer* t, Layer& y, int which, const bf16** out) {
+  bf16* res[4] = {y.wqkv, y.wo, y.wgu, y.wdown};
+  if (!t->quant4) {
+    *out = res[which];
+    return DTX_OK;
+  }
+  const int64_t d = t->mc.hidden, F = t->mc.ffn;
+  const int64_t n[4] = {static_cast<int64_t>(t->W) * d, d * d, 2 * F * d, d * F};
+  CK(nf4_dequant_bf16(y.q4[which], y.absmax[which], t->scratch_w[which], n[which], t->stream), 1);
+  *out = t->scratch_w[which];
+  return DTX_OK;
+}
+#define BASEW(which, ptr)                           \
+  const bf16* ptr = nullptr;                        \
+  do {                                              \
+    int _rc = base_weight(t, y, which, &ptr);       \
+    if (_rc) return _rc;                            \
+  } while (0)
+
+// forward (+ backward) of one micro-batch whose ids / labels (/ row lengths) are already in t->d_ids / t->d_labels (/ t->d_seq_lens).
+// The batch is [micro_batch, cur_S]: cur_S <= seq_len is this batch's own padded length (DataCollatorForSeq2Seq pads to the
+// longest row of the batch, cmd/tuning/train.py:282-286); every buffer was sized for seq_len.
 int fwd_bwd(dtx_trainer* t, bool backward) {
   const dtx_model_cfg& mc = t->mc;
   const dtx_train_cfg& tc = t->tc;
-  const int d = mc.hidden, F = mc.ffn, V = mc.vocab, L = mc.n_layers, M = t->M, RP = t->RP, H = mc.n_heads, D = mc.head_dim;
+  const int d = mc.hidden, F = mc.ffn, V = mc.vocab, L = mc.n_layers, M = t->cur_M, RP = t->RP, H = mc.n_heads, D = mc.head_dim;
   const int Hkv = mc.n_kv_heads, W = t->W;
-  const int B = tc.micro_batch, S = tc.seq_len;
+  const int B = tc.micro_batch, S = t->cur_S;
+  const int32_t* seq_lens = t->use_seq_lens ? t->d_seq_lens : nullptr;
+  const int kb_tok = (M + 63) / 64;
+  const int split_b = std::min(t->split_b, pick_split((W + 127) / 128, kb_tok));
+  const int split_a = std::min(t->split_a, pick_split((t->KA + 127) / 128, kb_tok));
   cudaStream_t s = t->stream;
   const float att_scale = 1.0f / sqrtf(static_cast<float>(D));
-  const bool fused = g_fused_epilogues && M > 128 && ((t->dq + t->dkv) % 256 == 0);
+  const bool fused = g_fused_epilogues && M > 128 && ((t->dq + t->dkv) % 256 == 0) && (W % 256 == 0);  // whole 256-column tiles
   const bool drop = t->dropout;  // adapters laid out for per-target dropped inputs (KA = nt*d)
   const float p_drop = backward ? tc.lora_dropout : 0.f;  // eval (model.eval()) runs the same path with p = 0
   t->fwd_count += 1;
@@ -365,8 +453,9 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       CK(gemm_bf16(g, s), 1);
     }
     {  // qkv = h1 * Wqkv^T + t * B_ext^T : base projection and LoRA up-projection in one TMEM accumulator
+      BASEW(W_QKV, wqkv);
       GemmArgs g;
-      g.A = y.h1; g.lda = d; g.B = y.wqkv; g.ldb = d;
+      g.A = y.h1; g.lda = d; g.B = wqkv; g.ldb = d;
       g.A2 = y.t; g.lda2 = RP; g.B2 = y.b_ext; g.ldb2 = RP; g.K2 = RP;
       g.C = y.qkv; g.ldc = W; g.M = M; g.N = W; g.K = d; g.epilogue = EPI_BF16;
       if (fused) {  // rotary embedding of q and k applied to the fp32 accumulator in the epilogue
@@ -378,18 +467,21 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
     {
       AttnArgs a;
       a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.Hkv = Hkv; a.scale = att_scale;
+      a.seq_lens = seq_lens; a.window = t->window;
       CK(attn_fwd(a, s), 1);
     }
     {  // x_mid = x + attn * Wo^T
+      BASEW(W_O, wo);
       GemmArgs g;
-      g.A = y.attn; g.lda = d; g.B = y.wo; g.ldb = d; g.C = y.x_mid; g.ldc = d; g.R = t->xs[l]; g.ldr = d;
+      g.A = y.attn; g.lda = d; g.B = wo; g.ldb = d; g.C = y.x_mid; g.ldc = d; g.R = t->xs[l]; g.ldr = d;
       g.M = M; g.N = d; g.K = d; g.epilogue = EPI_BF16_ADD;
       CK(gemm_bf16(g, s), 1);
     }
     CK(rmsnorm_fwd(y.x_mid, y.norm2, t->h2, y.rstd2, M, d, mc.rms_eps, s), 1);
     {  // [gate | up] = h2 * Wgu^T
+      BASEW(W_GU, wgu);
       GemmArgs g;
-      g.A = t->h2; g.lda = d; g.B = y.wgu; g.ldb = d; g.C = y.gu; g.ldc = 2 * F;
+      g.A = t->h2; g.lda = d; g.B = wgu; g.ldb = d; g.C = y.gu; g.ldc = 2 * F;
       g.M = M; g.N = 2 * F; g.K = d; g.epilogue = EPI_BF16;
       if (fused) {  // silu(gate) * up computed from the accumulator tile ([gate 128 | up 128] interleaved layout)
         g.epilogue = EPI_SWIGLU_FWD; g.aux = t->act; g.ld_aux = F;
@@ -398,8 +490,9 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
     }
     if (!fused) CK(swiglu_fwd(y.gu, t->act, M, F, 1, s), 1);
     {  // x_next = x_mid + act * Wdown^T
+      BASEW(W_DOWN, wdown);
       GemmArgs g;
-      g.A = t->act; g.lda = F; g.B = y.wdown; g.ldb = F; g.C = t->xs[l + 1]; g.ldc = d; g.R = y.x_mid; g.ldr = d;
+      g.A = t->act; g.lda = F; g.B = wdown; g.ldb = F; g.C = t->xs[l + 1]; g.ldc = d; g.R = y.x_mid; g.ldr = d;
       g.M = M; g.N = d; g.K = F; g.epilogue = EPI_BF16_ADD;
       CK(gemm_bf16(g, s), 1);
     }
@@ -429,8 +522,9 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   for (int l = L - 1; l >= 0; --l) {
     Layer& y = t->layers[l];
     {  // dact = dx * Wdown ; fused: d[gate|up] straight from the accumulator, dact never touches HBM
+      BASEW(W_DOWN, wdown);
       GemmArgs g;
-      g.A = cur; g.lda = d; g.B = y.wdown; g.ldb = F; g.b_mn_major = 1; g.C = t->dact; g.ldc = F;
+      g.A = cur; g.lda = d; g.B = wdown; g.ldb = F; g.b_mn_major = 1; g.C = t->dact; g.ldc = F;
       g.M = M; g.N = F; g.K = d; g.epilogue = EPI_BF16;
       if (fused) {
         g.epilogue = EPI_SWIGLU_BWD; g.C = t->dgu; g.ldc = 2 * F; g.aux = y.gu; g.ld_aux = 2 * F;
@@ -439,15 +533,17 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
     }
     if (!fused) CK(swiglu_bwd(t->dact, y.gu, t->dgu, M, F, 1, s), 1);
     {  // dh2 = [dgate | dup] * [Wg ; Wu]
+      BASEW(W_GU, wgu);
       GemmArgs g;
-      g.A = t->dgu; g.lda = 2 * F; g.B = y.wgu; g.ldb = d; g.b_mn_major = 1; g.C = t->dh; g.ldc = d;
+      g.A = t->dgu; g.lda = 2 * F; g.B = wgu; g.ldb = d; g.b_mn_major = 1; g.C = t->dh; g.ldc = d;
       g.M = M; g.N = d; g.K = 2 * F; g.epilogue = EPI_BF16;
       CK(gemm_bf16(g, s), 1);
     }
     CK(rmsnorm_bwd(t->dh, y.x_mid, y.norm2, y.rstd2, cur, other, M, d, s), 1);  // other = d x_mid
     {  // dattn = dx_mid * Wo
+      BASEW(W_O, wo);
       GemmArgs g;
-      g.A = other; g.lda = d; g.B = y.wo; g.ldb = d; g.b_mn_major = 1; g.C = t->dattn; g.ldc = d;
+      g.A = other; g.lda = d; g.B = wo; g.ldb = d; g.b_mn_major = 1; g.C = t->dattn; g.ldc = d;
       g.M = M; g.N = d; g.K = d; g.epilogue = EPI_BF16;
       CK(gemm_bf16(g, s), 1);
     }
@@ -455,6 +551,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       AttnArgs a;
       a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.Hkv = Hkv; a.scale = att_scale;
       a.dout = t->dattn; a.dqkv = t->dqkv; a.delta = t->delta;
+      a.seq_lens = seq_lens; a.window = t->window; a.rope_stride = tc.seq_len;
       // The dQ / dK kernels apply the inverse rotary in their store epilogues from the TRANSPOSED table (thread r of a tile
       // reads position q0 + r: one coalesced 256-byte line per frequency and warp).  A first attempt with the [S][64] table
       // (32 uncoalesced 8-byte reads per thread) cost +270 us/layer, the standalone HBM-bound kernel 92 us.
@@ -472,8 +569,9 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
     // Layer 0's input gradient has no consumer (the embedding is frozen): its dh1 GEMM, the dropout-branch
     // gradient and the norm-1 backward are skipped.
     if (l > 0) {  // dh1 = dqkv * Wqkv (+ dt * A_cat in the same accumulator when there is no dropout between h1 and A)
+      BASEW(W_QKV, wqkv);
       GemmArgs g;
-      g.A = t->dqkv; g.lda = W; g.B = y.wqkv; g.ldb = d; g.b_mn_major = 1;
+      g.A = t->dqkv; g.lda = W; g.B = wqkv; g.ldb = d; g.b_mn_major = 1;
       if (!drop) { g.A2 = t->dt; g.lda2 = RP; g.B2 = y.a_cat; g.ldb2 = t->KA; g.K2 = RP; }
       g.C = t->dh; g.ldc = d; g.M = M; g.N = d; g.K = W; g.epilogue = EPI_BF16;
       CK(gemm_bf16(g, s), 1);
@@ -488,14 +586,14 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
     {  // grad of B_ext (all rows): dqkv^T * t   [W, RP], split over tokens
       GemmArgs g;
       g.A = t->dqkv; g.lda = W; g.a_mn_major = 1; g.B = y.t; g.ldb = RP; g.b_mn_major = 1;
-      g.C = t->part_b; g.ldc = RP; g.M = W; g.N = RP; g.K = M; g.epilogue = EPI_F32; g.split_k = t->split_b;
+      g.C = t->part_b; g.ldc = RP; g.M = W; g.N = RP; g.K = M; g.epilogue = EPI_F32; g.split_k = split_b;
       g.block_n = 64;
       CK(gemm_bf16(g, s), 1);
     }
     {  // grad of A_cat^T: lora_in^T * dt   [KA, RP]
       GemmArgs g;
       g.A = drop ? y.hd : y.h1; g.lda = t->KA; g.a_mn_major = 1; g.B = t->dt; g.ldb = RP; g.b_mn_major = 1;
-      g.C = t->part_a; g.ldc = RP; g.M = t->KA; g.N = RP; g.K = M; g.epilogue = EPI_F32; g.split_k = t->split_a;
+      g.C = t->part_a; g.ldc = RP; g.M = t->KA; g.N = RP; g.K = M; g.epilogue = EPI_F32; g.split_k = split_a;
       g.block_n = 64;
       CK(gemm_bf16(g, s), 1);
     }
@@ -504,9 +602,9 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       float* gl = t->grads + static_cast<int64_t>(l) * t->per_layer + t->tg[ti].off;
       const int d_out = t->tg[ti].d_out;
       // dA^T = lora_in^T (dy * sB)  (the scale rides in B_ext);  dB = s * dy^T t  (t is unscaled, so the scale is applied here)
-      lora_gather_kernel<<<(d * r + 255) / 256, 256, 0, s>>>(t->part_a, t->split_a, static_cast<long long>(t->KA) * RP, RP,
+      lora_gather_kernel<<<(d * r + 255) / 256, 256, 0, s>>>(t->part_a, split_a, static_cast<long long>(t->KA) * RP, RP,
                                                             drop ? ti * d : 0, ti * r, d, r, gl, accumulate, 1.0f);
-      lora_gather_kernel<<<(d_out * r + 255) / 256, 256, 0, s>>>(t->part_b, t->split_b, static_cast<long long>(W) * RP, RP,
+      lora_gather_kernel<<<(d_out * r + 255) / 256, 256, 0, s>>>(t->part_b, split_b, static_cast<long long>(W) * RP, RP,
                                                                 t->tg[ti].row0, ti * r, d_out, r, gl + static_cast<int64_t>(d) * r,
                                                                 accumulate, tc.lora_alpha / static_cast<float>(r));
       CK(cudaGetLastError(), 2);
@@ -526,6 +624,7 @@ int optimizer_step(dtx_trainer* t, float* lr_used) {
     if (rc != 0) return t->fail(DTX_ERR_NCCL, "ncclAllReduce failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
     t->launches += 1;
   }
+  cudaEventRecord(t->ev_ar, s);
   CK(sumsq(t->grads, t->n_train, t->d_scratch, t->d_sumsq, s), 2);
   const double lam = dtx_lr_lambda(tc.sched, t->opt_step, tc.warmup_steps, tc.total_steps);
   const float lr = static_cast<float>(static_cast<double>(tc.lr) * lam);
@@ -535,6 +634,7 @@ int optimizer_step(dtx_trainer* t, float* lr_used) {
   a.lr = lr; a.beta1 = tc.beta1; a.beta2 = tc.beta2; a.eps = tc.eps; a.weight_decay = tc.weight_decay;
   a.bias1 = static_cast<float>(1.0 - pow(static_cast<double>(tc.beta1), step1));
   a.bias2 = static_cast<float>(1.0 - pow(static_cast<double>(tc.beta2), step1));
+  // HF scales every micro-batch loss by 1/grad_accum whatever the number actually accumulated (forced end-of-epoch step)
   a.grad_scale = 1.0f / static_cast<float>(t->world * (tc.grad_accum > 0 ? tc.grad_accum : 1));
   a.sumsq = t->d_sumsq; a.max_grad_norm = tc.max_grad_norm; a.grad_norm_out = t->d_gnorm;
   CK(adamw_step(a, s), 1);
@@ -545,17 +645,35 @@ int optimizer_step(dtx_trainer* t, float* lr_used) {
   return DTX_OK;
 }
 
-int do_step(dtx_trainer* t, float* loss_out, float* gnorm_out, float* lr_out, int32_t* stepped_out) {
-  if (!t->have_weights) return t->fail(DTX_ERR_STATE, "base weights not loaded (dtx_load_tensor / dtx_init_random_weights)");
+// validate and record the shape of the batch about to be processed
+int set_batch_shape(dtx_trainer* t, int32_t seq_len_batch, bool have_lens) {
+  const int S = seq_len_batch > 0 ? seq_len_batch : t->tc.seq_len;
+  if (S % 128 || S > t->tc.seq_len)
+    return t->fail(DTX_ERR_INVALID, "seq_len_batch %d must be a multiple of 128 and <= seq_len %d", S, t->tc.seq_len);
+  t->cur_S = S;
+  t->cur_M = S * t->tc.micro_batch;
+  t->use_seq_lens = have_lens;
+  return DTX_OK;
+}
+
+int check_ready(dtx_trainer* t) {
+  char buf[160];
+  if (const char* m = t->missing_weight(buf, sizeof(buf)))
+    return t->fail(DTX_ERR_STATE, "base weight %s was never loaded (dtx_load_tensor / dtx_init_random_weights)", m);
   if (!t->have_lora) return t->fail(DTX_ERR_STATE, "LoRA adapters not initialised (dtx_init_lora / dtx_load_tensor)");
+  return DTX_OK;
+}
+
+int do_step(dtx_trainer* t, int32_t flags, float* loss_out, float* gnorm_out, float* lr_out, int32_t* stepped_out) {
   cudaEventRecord(t->ev0, t->stream);
   int rc = fwd_bwd(t, true);
   if (rc) return rc;
+  cudaEventRecord(t->ev_fb, t->stream);
   t->micro_idx += 1;
   int stepped = 0;
   float lr = 0.f;
   const int accum = t->tc.grad_accum > 0 ? t->tc.grad_accum : 1;
-  if (t->micro_idx >= accum) {
+  if (t->micro_idx >= accum || (flags & DTX_STEP_FORCE)) {
     rc = optimizer_step(t, &lr);
     if (rc) return rc;
     t->micro_idx = 0;
@@ -568,6 +686,13 @@ int do_step(dtx_trainer* t, float* loss_out, float* gnorm_out, float* lr_out, in
   cudaError_t e = cudaStreamSynchronize(t->stream);
   if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "step failed on device: %s", cudaGetErrorString(e));
   cudaEventElapsedTime(&t->last_ms, t->ev0, t->ev1);
+  t->seg_ms[0] = t->last_ms;
+  cudaEventElapsedTime(&t->seg_ms[1], t->ev0, t->ev_fb);
+  t->seg_ms[2] = t->seg_ms[3] = 0.f;
+  if (stepped) {
+    cudaEventElapsedTime(&t->seg_ms[2], t->ev_fb, t->ev_ar);
+    cudaEventElapsedTime(&t->seg_ms[3], t->ev_ar, t->ev1);
+  }
   if (loss_out) *loss_out = host[0];
   if (gnorm_out) *gnorm_out = host[1];
   if (lr_out) *lr_out = lr;
@@ -725,9 +850,15 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
   t->RP = ((t->nt * tc->lora_r + 63) / 64) * 64;
   t->KA = t->dropout ? t->nt * mc->hidden : mc->hidden;
   t->n_train = static_cast<int64_t>(mc->n_layers) * t->per_layer;
+  t->cur_S = tc->seq_len;
+  t->cur_M = t->M;
+  // Mistral-style sliding window: only a different mask once the sequence is longer than the window
+  t->window = (mc->sliding_window > 0 && mc->sliding_window < tc->seq_len) ? mc->sliding_window : 0;
   cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
   cudaEventCreate(&t->ev0);
   cudaEventCreate(&t->ev1);
+  cudaEventCreate(&t->ev_fb);
+  cudaEventCreate(&t->ev_ar);
   int rc = create_buffers(t);
   if (rc) {
     g_error = t->err;
@@ -771,6 +902,8 @@ void dtx_trainer_destroy(dtx_trainer* t) {
   for (void* p : t->allocs) cudaFree(p);
   if (t->ev0) cudaEventDestroy(t->ev0);
   if (t->ev1) cudaEventDestroy(t->ev1);
+  if (t->ev_fb) cudaEventDestroy(t->ev_fb);
+  if (t->ev_ar) cudaEventDestroy(t->ev_ar);
   if (t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
@@ -790,12 +923,12 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
   };
   if (strstr(name, "embed_tokens.weight")) {
     if (!expect(V, d)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)V, (long long)d);
-    t->weights_loaded[0] = true;
+    t->loaded[0] = 1;
     return upload(t->embed, V * d);
   }
   if (strstr(name, "lm_head.weight")) {
     if (!expect(V, d)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)V, (long long)d);
-    t->weights_loaded[1] = true;
+    t->loaded[1] = 1;
     return upload(t->lm_head, V * d);
   }
   int layer = -1;
@@ -803,13 +936,14 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
   if (!parse_layer(name, &layer, &rest)) {
     if (strstr(name, "norm.weight")) {  // model.norm.weight
       if (rows != d) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld]", name, (long long)d);
-      t->weights_loaded[2] = true;
+      t->loaded[2] = 1;
       return upload(t->normf, d);
     }
     return t->fail(DTX_ERR_INVALID, "unknown tensor name %s", name);
   }
   if (layer < 0 || layer >= t->mc.n_layers) return t->fail(DTX_ERR_INVALID, "%s: layer out of range", name);
   Layer& y = t->layers[layer];
+  uint8_t* lmap = t->loaded.data() + 3 + 9 * static_cast<size_t>(layer);
   const bool is_lora_a = strstr(rest, "lora_A") != nullptr, is_lora_b = strstr(rest, "lora_B") != nullptr;
   if (is_lora_a || is_lora_b) {
     char which = 0;
@@ -827,18 +961,20 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
       std::vector<float> tr(d * r);
       for (int64_t j = 0; j < r; ++j)
         for (int64_t c = 0; c < d; ++c) tr[c * r + j] = f[j * d + c];
-      cudaMemcpy(base, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice);
+      CKM(cudaMemcpy(base, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice));
     } else {
       if (!expect(d_out, r)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)d_out, (long long)r);
       to_f32_host(host, dtype, d_out * r, f);
-      cudaMemcpy(base + d * r, f.data(), f.size() * 4, cudaMemcpyHostToDevice);
+      CKM(cudaMemcpy(base + d * r, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
     }
     t->have_lora = true;
     int rc = refresh_shadows(t);
     if (rc) return rc;
-    cudaStreamSynchronize(t->stream);
+    CKM(cudaStreamSynchronize(t->stream));
     return DTX_OK;
   }
+  if (t->quant4 && !strstr(rest, "layernorm"))
+    return t->fail(DTX_ERR_STATE, "%s: the base weights are already NF4-packed; load tensors before dtx_quantize_base", name);
   // gate/up rows go to the GU-interleaved layout: 128 gate rows, then the 128 up rows of the same features, ...
   for (int which = 0; which < 2; ++which) {
     if (!strstr(rest, which ? "mlp.up_proj.weight" : "mlp.gate_proj.weight")) continue;
@@ -850,21 +986,22 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
                                  cudaMemcpyHostToDevice);
       if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "upload %s: %s", name, cudaGetErrorString(e));
     }
-    t->have_weights = true;
+    lmap[4 + which] = 1;
     return DTX_OK;
   }
-  struct Slot { const char* key; bf16* dst; int64_t r, c; };
+  struct Slot { const char* key; bf16* dst; int64_t r, c; int bit; };
   const Slot slots[] = {
-      {"self_attn.q_proj.weight", y.wqkv, dq, d},                  {"self_attn.k_proj.weight", y.wqkv + dq * d, dkv, d},
-      {"self_attn.v_proj.weight", y.wqkv + (dq + dkv) * d, dkv, d}, {"self_attn.o_proj.weight", y.wo, d, dq},
-      {"mlp.down_proj.weight", y.wdown, d, F},             {"input_layernorm.weight", y.norm1, d, 1},
-      {"post_attention_layernorm.weight", y.norm2, d, 1},
+      {"self_attn.q_proj.weight", y.wqkv, dq, d, 0},                  {"self_attn.k_proj.weight", y.wqkv + dq * d, dkv, d, 1},
+      {"self_attn.v_proj.weight", y.wqkv + (dq + dkv) * d, dkv, d, 2}, {"self_attn.o_proj.weight", y.wo, d, dq, 3},
+      {"mlp.down_proj.weight", y.wdown, d, F, 6},             {"input_layernorm.weight", y.norm1, d, 1, 7},
+      {"post_attention_layernorm.weight", y.norm2, d, 1, 8},
   };
   for (const Slot& sl : slots) {
     if (strstr(rest, sl.key)) {
       if (!expect(sl.r, sl.c)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)sl.r, (long long)sl.c);
-      t->have_weights = true;  // completeness is the caller's contract (checked by the host loader)
-      return upload(sl.dst, sl.r * sl.c);
+      int rc = upload(sl.dst, sl.r * sl.c);
+      if (rc == DTX_OK) lmap[sl.bit] = 1;  // a step with a hole in this map is refused (check_ready)
+      return rc;
     }
   }
   return t->fail(DTX_ERR_INVALID, "unknown tensor name %s", name);
@@ -872,6 +1009,7 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
 
 int32_t dtx_init_random_weights(dtx_trainer* t, uint64_t seed) {
   if (!t) return DTX_ERR_INVALID;
+  if (t->quant4) return t->fail(DTX_ERR_STATE, "init_random_weights: the base weights are already NF4-packed");
   cudaSetDevice(t->device);
   const int64_t d = t->mc.hidden, F = t->mc.ffn, V = t->mc.vocab;
   cudaStream_t s = t->stream;
@@ -889,30 +1027,50 @@ int32_t dtx_init_random_weights(dtx_trainer* t, uint64_t seed) {
   }
   cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "init_random_weights: %s", cudaGetErrorString(e));
-  t->have_weights = true;
+  std::fill(t->loaded.begin(), t->loaded.end(), 1);
   return DTX_OK;
 }
 
 int32_t dtx_quantize_base(dtx_trainer* t, int32_t mode) {
-  // mode 4: NF4 (--quantization int4), mode 8: row-wise int8 (--quantization int8).  Applies to the decoder-layer Linear
-  // weights (bitsandbytes skips lm_head; embeddings and norms are never quantised).
+  // mode 4: NF4 (--quantization int4).  Applies to the decoder-layer Linear weights (bitsandbytes skips lm_head; embeddings
+  // and norms are never quantised).  The bf16 copies are replaced by packed codes + absmax and freed.
   if (!t) return DTX_ERR_INVALID;
-  if (!t->have_weights) return t->fail(DTX_ERR_STATE, "quantize_base: load the base weights first");
-  if (mode != 4 && mode != 8) return t->fail(DTX_ERR_INVALID, "quantize_base: mode must be 4 (nf4) or 8 (int8)");
+  if (mode == 8)
+    return t->fail(DTX_ERR_UNSUPPORTED, "--quantization int8 (bitsandbytes LLM.int8 with runtime outlier decomposition, "
+                                         "cmd/tuning/train.py:231-232) is not implemented natively; use int4 or no quantization");
+  if (mode != 4) return t->fail(DTX_ERR_INVALID, "quantize_base: mode must be 4 (nf4)");
+  if (t->quant4) return t->fail(DTX_ERR_STATE, "quantize_base: already quantised");
+  {
+    char buf[160];
+    if (const char* m = t->missing_weight(buf, sizeof(buf)))
+      return t->fail(DTX_ERR_STATE, "quantize_base: base weight %s is not loaded yet", m);
+  }
   cudaSetDevice(t->device);
   const int64_t d = t->mc.hidden, F = t->mc.ffn, W = t->W;
+  const int64_t n[4] = {W * d, d * d, 2 * F * d, d * F};
+  for (int i = 0; i < 4; ++i)
+    if (n[i] % 64) return t->fail(DTX_ERR_INVALID, "quantize_base: matrix sizes must be multiples of the 64-element NF4 block");
   cudaStream_t s = t->stream;
   for (Layer& y : t->layers) {
-    struct { bf16* p; int64_t rows, cols; } m[4] = {{y.wqkv, W, d}, {y.wo, d, d}, {y.wgu, 2 * F, d}, {y.wdown, d, F}};
-    for (auto& w : m) {
-      if (mode == 4) CK(nf4_roundtrip_bf16(w.p, w.rows * w.cols, s), 1);
-      else CK(int8_rowwise_roundtrip_bf16(w.p, static_cast<int>(w.rows), static_cast<int>(w.cols), s), 1);
+    bf16** w[4] = {&y.wqkv, &y.wo, &y.wgu, &y.wdown};
+    for (int i = 0; i < 4; ++i) {
+      if (!t->alloc(&y.q4[i], static_cast<size_t>(n[i] / 2)) || !t->alloc(&y.absmax[i], static_cast<size_t>(n[i] / 64))) return DTX_ERR_CUDA;
+      CK(nf4_quantize_pack(*w[i], y.q4[i], y.absmax[i], n[i], s), 1);
+    }
+    CKM(cudaStreamSynchronize(s));
+    for (int i = 0; i < 4; ++i) {
+      t->release(*w[i], static_cast<size_t>(n[i]) * sizeof(bf16));
+      *w[i] = nullptr;
+      t->base_bytes += n[i] / 2 + (n[i] / 64) * 4 - n[i] * static_cast<int64_t>(sizeof(bf16));
     }
   }
-  cudaError_t e = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "quantize_base: %s", cudaGetErrorString(e));
+  for (int i = 0; i < 4; ++i)
+    if (!t->alloc(&t->scratch_w[i], static_cast<size_t>(n[i]))) return DTX_ERR_CUDA;
+  t->quant4 = true;
   return DTX_OK;
 }
+
+int64_t dtx_base_weight_bytes(const dtx_trainer* t) { return t ? t->base_bytes : 0; }
 
 int32_t dtx_init_lora(dtx_trainer* t, uint64_t seed) {
   if (!t) return DTX_ERR_INVALID;
@@ -935,49 +1093,81 @@ int32_t dtx_init_lora(dtx_trainer* t, uint64_t seed) {
       float* a = host.data() + l * t->per_layer + t->tg[ti].off;
       for (int64_t i = 0; i < d * r; ++i) a[i] = (2.f * next() - 1.f) * bound;
     }
-  cudaMemcpy(t->params, host.data(), host.size() * 4, cudaMemcpyHostToDevice);
-  cudaMemsetAsync(t->adam_m, 0, t->n_train * 4, t->stream);
-  cudaMemsetAsync(t->adam_v, 0, t->n_train * 4, t->stream);
+  CKM(cudaMemcpy(t->params, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+  CKM(cudaMemsetAsync(t->adam_m, 0, t->n_train * 4, t->stream));
+  CKM(cudaMemsetAsync(t->adam_v, 0, t->n_train * 4, t->stream));
   t->opt_step = 0;
   t->micro_idx = 0;
   int rc = refresh_shadows(t);
   if (rc) return rc;
-  cudaStreamSynchronize(t->stream);
+  CKM(cudaStreamSynchronize(t->stream));
   t->have_lora = true;
   return DTX_OK;
 }
 
-int32_t dtx_step(dtx_trainer* t, const int32_t* ids, const int32_t* labels, float* loss, float* gnorm, float* lr,
-                 int32_t* stepped) {
+int32_t dtx_step(dtx_trainer* t, const int32_t* ids, const int32_t* labels, const int32_t* seq_lens, int32_t seq_len_batch,
+                 int32_t flags, float* loss, float* gnorm, float* lr, int32_t* stepped) {
   if (!t || !ids || !labels) return t ? t->fail(DTX_ERR_INVALID, "null batch") : DTX_ERR_INVALID;
   cudaSetDevice(t->device);
-  cudaMemcpyAsync(t->d_ids, ids, static_cast<size_t>(t->M) * 4, cudaMemcpyHostToDevice, t->stream);
-  cudaMemcpyAsync(t->d_labels, labels, static_cast<size_t>(t->M) * 4, cudaMemcpyHostToDevice, t->stream);
-  return do_step(t, loss, gnorm, lr, stepped);
+  int rc = check_ready(t);
+  if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, seq_lens != nullptr);
+  if (rc) return rc;
+  CKM(cudaMemcpyAsync(t->d_ids, ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+  CKM(cudaMemcpyAsync(t->d_labels, labels, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+  if (seq_lens) CKM(cudaMemcpyAsync(t->d_seq_lens, seq_lens, static_cast<size_t>(t->tc.micro_batch) * 4, cudaMemcpyHostToDevice, t->stream));
+  return do_step(t, flags, loss, gnorm, lr, stepped);
 }
 
-int32_t dtx_step_device(dtx_trainer* t, const void* d_ids, const void* d_labels, float* loss, float* gnorm, float* lr,
-                        int32_t* stepped) {
+int32_t dtx_step_device(dtx_trainer* t, const void* d_ids, const void* d_labels, const void* d_seq_lens, int32_t seq_len_batch,
+                        int32_t flags, float* loss, float* gnorm, float* lr, int32_t* stepped) {
   if (!t || !d_ids || !d_labels) return t ? t->fail(DTX_ERR_INVALID, "null batch") : DTX_ERR_INVALID;
   cudaSetDevice(t->device);
-  cudaMemcpyAsync(t->d_ids, d_ids, static_cast<size_t>(t->M) * 4, cudaMemcpyDeviceToDevice, t->stream);
-  cudaMemcpyAsync(t->d_labels, d_labels, static_cast<size_t>(t->M) * 4, cudaMemcpyDeviceToDevice, t->stream);
-  return do_step(t, loss, gnorm, lr, stepped);
+  int rc = check_ready(t);
+  if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, d_seq_lens != nullptr);
+  if (rc) return rc;
+  CKM(cudaMemcpyAsync(t->d_ids, d_ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyDeviceToDevice, t->stream));
+  CKM(cudaMemcpyAsync(t->d_labels, d_labels, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyDeviceToDevice, t->stream));
+  if (d_seq_lens) CKM(cudaMemcpyAsync(t->d_seq_lens, d_seq_lens, static_cast<size_t>(t->tc.micro_batch) * 4, cudaMemcpyDeviceToDevice, t->stream));
+  return do_step(t, flags, loss, gnorm, lr, stepped);
 }
 
-int32_t dtx_eval_loss(dtx_trainer* t, const int32_t* ids, const int32_t* labels, float* loss_out) {
+int32_t dtx_eval_loss(dtx_trainer* t, const int32_t* ids, const int32_t* labels, const int32_t* seq_lens, int32_t seq_len_batch,
+                      float* loss_out, float* row_sum_out, int32_t* row_valid_out) {
   if (!t || !ids || !labels) return t ? t->fail(DTX_ERR_INVALID, "null batch") : DTX_ERR_INVALID;
-  if (!t->have_weights || !t->have_lora) return t->fail(DTX_ERR_STATE, "weights / adapters not initialised");
   cudaSetDevice(t->device);
-  cudaMemcpyAsync(t->d_ids, ids, static_cast<size_t>(t->M) * 4, cudaMemcpyHostToDevice, t->stream);
-  cudaMemcpyAsync(t->d_labels, labels, static_cast<size_t>(t->M) * 4, cudaMemcpyHostToDevice, t->stream);
-  int rc = fwd_bwd(t, false);
+  int rc = check_ready(t);
+  if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, seq_lens != nullptr);
+  if (rc) return rc;
+  const int B = t->tc.micro_batch;
+  CKM(cudaMemcpyAsync(t->d_ids, ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+  CKM(cudaMemcpyAsync(t->d_labels, labels, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+  if (seq_lens) CKM(cudaMemcpyAsync(t->d_seq_lens, seq_lens, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, t->stream));
+  rc = fwd_bwd(t, false);
   if (rc) return rc;
   float h = 0.f;
-  cudaMemcpyAsync(&h, t->d_loss, 4, cudaMemcpyDeviceToHost, t->stream);
+  CKM(cudaMemcpyAsync(&h, t->d_loss, 4, cudaMemcpyDeviceToHost, t->stream));
+  if (row_sum_out || row_valid_out) {
+    CK(row_loss_stats(t->row_loss, t->d_shift, B, t->cur_S, t->d_row_sum, t->d_row_valid, t->stream), 1);
+    if (row_sum_out) CKM(cudaMemcpyAsync(row_sum_out, t->d_row_sum, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, t->stream));
+    if (row_valid_out) CKM(cudaMemcpyAsync(row_valid_out, t->d_row_valid, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, t->stream));
+  }
   cudaError_t e = cudaStreamSynchronize(t->stream);
   if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "eval failed on device: %s", cudaGetErrorString(e));
   if (loss_out) *loss_out = h;
+  return DTX_OK;
+}
+
+int32_t dtx_allreduce_host(dtx_trainer* t, double* inout, int32_t n) {
+  if (!t || !inout || n < 0 || n > 64) return t ? t->fail(DTX_ERR_INVALID, "allreduce_host: n must be in [0, 64]") : DTX_ERR_INVALID;
+  if (t->world == 1 || n == 0) return DTX_OK;
+  cudaSetDevice(t->device);
+  NcclApi* api = nccl_api();
+  if (!api || !t->nccl_comm) return t->fail(DTX_ERR_NCCL, "NCCL communicator missing for world=%d", t->world);
+  CKM(cudaMemcpyAsync(t->d_host_red, inout, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, t->stream));
+  int rc = api->AllReduce(t->d_host_red, t->d_host_red, static_cast<size_t>(n), kNcclFloat64, kNcclSum, t->nccl_comm, t->stream);
+  if (rc != 0) return t->fail(DTX_ERR_NCCL, "ncclAllReduce failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
+  CKM(cudaMemcpyAsync(inout, t->d_host_red, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, t->stream));
+  CKM(cudaStreamSynchronize(t->stream));
   return DTX_OK;
 }
 
@@ -1003,11 +1193,11 @@ int32_t dtx_export_adapter(dtx_trainer* t, const char* name, void* host_out, int
   std::vector<float> tmp(d * r);
   float* out = static_cast<float*>(host_out);
   if (strstr(rest, "lora_A")) {
-    cudaMemcpy(tmp.data(), base, d * r * 4, cudaMemcpyDeviceToHost);
+    CKM(cudaMemcpy(tmp.data(), base, d * r * 4, cudaMemcpyDeviceToHost));
     for (int64_t c = 0; c < d; ++c)
       for (int64_t j = 0; j < r; ++j) out[j * d + c] = tmp[c * r + j];
   } else if (strstr(rest, "lora_B")) {
-    cudaMemcpy(out, base + d * r, d_out * r * 4, cudaMemcpyDeviceToHost);
+    CKM(cudaMemcpy(out, base + d * r, d_out * r * 4, cudaMemcpyDeviceToHost));
   } else {
     return t->fail(DTX_ERR_INVALID, "%s: expected lora_A or lora_B", name);
   }
@@ -1017,5 +1207,10 @@ int32_t dtx_export_adapter(dtx_trainer* t, const char* name, void* host_out, int
 int64_t dtx_num_trainable(const dtx_trainer* t) { return t ? t->n_train : 0; }
 int64_t dtx_launch_count(const dtx_trainer* t) { return t ? t->launches : 0; }
 float dtx_last_step_ms(const dtx_trainer* t) { return t ? t->last_ms : 0.f; }
+int32_t dtx_last_step_timings(const dtx_trainer* t, float* out4) {
+  if (!t || !out4) return DTX_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) out4[i] = t->seg_ms[i];
+  return DTX_OK;
+}
 
 }  // extern "C"

@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(_HERE, "libdtxtune.so")
 DTX_F32, DTX_BF16, DTX_F16 = 0, 1, 2
 SCHED = {"linear": 0, "cosine": 1, "constant": 2, "constant_with_warmup": 3}
 TARGET_BITS = {"q_proj": 1, "k_proj": 2, "v_proj": 4}
-EPI_BF16, EPI_F32, EPI_BF16_ADD = 0, 1, 2
+EPI_BF16, EPI_F32, EPI_BF16_ADD, EPI_ROPE, EPI_SWIGLU_FWD, EPI_SWIGLU_BWD = 0, 1, 2, 3, 4, 5
+STEP_FORCE = 1
 
 
 class DtxError(RuntimeError):
@@ -31,7 +32,7 @@ class DtxError(RuntimeError):
 class ModelCfg(C.Structure):
     _fields_ = [("vocab", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32), ("n_heads", C.c_int32),
                 ("n_kv_heads", C.c_int32), ("head_dim", C.c_int32), ("ffn", C.c_int32), ("rms_eps", C.c_float),
-                ("rope_theta", C.c_float), ("max_seq", C.c_int32)]
+                ("rope_theta", C.c_float), ("max_seq", C.c_int32), ("sliding_window", C.c_int32)]
 
 
 class TrainCfg(C.Structure):
@@ -46,10 +47,11 @@ class TrainCfg(C.Structure):
 ABI_SYMBOLS = [
     "dtx_abi_version", "dtx_last_global_error", "dtx_last_error", "dtx_trainer_create", "dtx_trainer_destroy",
     "dtx_get_nccl_unique_id", "dtx_load_tensor", "dtx_init_random_weights", "dtx_init_lora", "dtx_quantize_base", "dtx_step",
-    "dtx_step_device", "dtx_eval_loss", "dtx_export_adapter", "dtx_num_trainable", "dtx_launch_count",
-    "dtx_last_step_ms", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
+    "dtx_step_device", "dtx_eval_loss", "dtx_allreduce_host", "dtx_export_adapter", "dtx_num_trainable", "dtx_launch_count",
+    "dtx_base_weight_bytes", "dtx_last_step_ms", "dtx_last_step_timings", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16",
+    "dtx_gemm_fused", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
     "dtx_rope_table", "dtx_rope_qk", "dtx_swiglu_fwd", "dtx_swiglu_bwd", "dtx_lora_dropout_fwd", "dtx_lora_dropout_bwd_add",
-    "dtx_nf4_roundtrip", "dtx_cross_entropy", "dtx_sumsq", "dtx_adamw",
+    "dtx_nf4_roundtrip", "dtx_nf4_pack", "dtx_nf4_dequant", "dtx_cross_entropy", "dtx_sumsq", "dtx_adamw",
     "dtx_attn_fwd", "dtx_attn_bwd",
 ]
 
@@ -79,9 +81,17 @@ def load() -> C.CDLL:
     lib.dtx_init_lora.argtypes = [vp, C.c_uint64]
     lib.dtx_quantize_base.argtypes = [vp, i32]
     lib.dtx_nf4_roundtrip.argtypes = [vp, i64, vp]
-    lib.dtx_step.argtypes = [vp, vp, vp, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
-    lib.dtx_step_device.argtypes = [vp, vp, vp, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
-    lib.dtx_eval_loss.argtypes = [vp, vp, vp, C.POINTER(f32)]
+    lib.dtx_nf4_pack.argtypes = [vp, vp, vp, i64, vp]
+    lib.dtx_nf4_dequant.argtypes = [vp, vp, vp, i64, vp]
+    lib.dtx_step.argtypes = [vp, vp, vp, vp, i32, i32, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
+    lib.dtx_step_device.argtypes = [vp, vp, vp, vp, i32, i32, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
+    lib.dtx_eval_loss.argtypes = [vp, vp, vp, vp, i32, C.POINTER(f32), vp, vp]
+    lib.dtx_allreduce_host.argtypes = [vp, vp, i32]
+    lib.dtx_base_weight_bytes.argtypes = [vp]
+    lib.dtx_base_weight_bytes.restype = i64
+    lib.dtx_last_step_timings.argtypes = [vp, vp]
+    lib.dtx_gemm_fused.argtypes = [vp, i64, vp, i64, i32, vp, i64, vp, i64, i32, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32,
+                                   i32, vp]
     lib.dtx_export_adapter.argtypes = [vp, C.c_char_p, vp, i64]
     lib.dtx_num_trainable.argtypes = [vp]
     lib.dtx_num_trainable.restype = i64
@@ -106,8 +116,8 @@ def load() -> C.CDLL:
     lib.dtx_cross_entropy.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp]
     lib.dtx_sumsq.argtypes = [vp, i64, vp, vp, vp]
     lib.dtx_adamw.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, f32, vp, vp]
-    lib.dtx_attn_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, vp]
-    lib.dtx_attn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
+    lib.dtx_attn_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, vp, i32, vp]
+    lib.dtx_attn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, i32, vp, i32, vp]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:  # default: all status-returning entry points
@@ -144,6 +154,7 @@ class ModelConfig:
     rms_eps: float = 1e-5
     rope_theta: float = 10000.0
     max_seq: int = 4096
+    sliding_window: int = 0            # Mistral config.json `sliding_window`; 0 = none
 
     @staticmethod
     def llama2_7b() -> "ModelConfig":
@@ -151,7 +162,7 @@ class ModelConfig:
 
     def to_c(self) -> ModelCfg:
         return ModelCfg(self.vocab, self.hidden, self.n_layers, self.n_heads, self.n_kv_heads or self.n_heads,
-                        self.head_dim, self.ffn, self.rms_eps, self.rope_theta, self.max_seq)
+                        self.head_dim, self.ffn, self.rms_eps, self.rope_theta, self.max_seq, int(self.sliding_window or 0))
 
 
 @dataclass
@@ -227,38 +238,69 @@ class Trainer:
         check(self.lib.dtx_init_random_weights(self._h, seed), self._h)
 
     def quantize_base(self, mode: str) -> None:
-        """`--quantization int4|int8`: W <- dequant(quant(W)) on the device (nf4 / row-wise int8), once."""
+        """`--quantization int4`: the decoder weights are re-stored as packed NF4 (+ fp32 absmax per 64) on the device and
+        expanded per GEMM; `int8` raises DtxError (DTX_ERR_UNSUPPORTED)."""
         check(self.lib.dtx_quantize_base(self._h, {"int4": 4, "nf4": 4, "int8": 8}[mode]), self._h)
 
     def init_lora(self, seed: int) -> None:
         check(self.lib.dtx_init_lora(self._h, seed), self._h)
 
     # -- the hot path -------------------------------------------------------------------------
-    def step(self, input_ids: np.ndarray, labels: np.ndarray) -> Tuple[float, float, float, bool]:
-        """One micro-batch.  Returns (loss, grad_norm, lr, stepped)."""
+    def _batch_args(self, input_ids, labels, seq_lens):
         ids = np.ascontiguousarray(input_ids, dtype=np.int32)
         lab = np.ascontiguousarray(labels, dtype=np.int32)
-        assert ids.shape == (self.train.micro_batch, self.train.seq_len) and lab.shape == ids.shape
+        assert ids.ndim == 2 and ids.shape[0] == self.train.micro_batch and lab.shape == ids.shape, (ids.shape, lab.shape)
+        S = ids.shape[1]
+        assert S % 128 == 0 and S <= self.train.seq_len, f"batch length {S}: a multiple of 128 and <= {self.train.seq_len} expected"
+        lens = None if seq_lens is None else np.ascontiguousarray(seq_lens, dtype=np.int32)
+        assert lens is None or lens.shape == (self.train.micro_batch,)
+        return ids, lab, lens, S
+
+    def step(self, input_ids: np.ndarray, labels: np.ndarray, seq_lens: Optional[np.ndarray] = None,
+             force_step: bool = False) -> Tuple[float, float, float, bool]:
+        """One micro-batch [micro_batch, S] (S = this batch's padded length, a multiple of 128, <= seq_len); seq_lens = true
+        row lengths (None: all rows full).  Returns (loss, grad_norm, lr, stepped)."""
+        ids, lab, lens, S = self._batch_args(input_ids, labels, seq_lens)
         loss, gn, lr, st = C.c_float(), C.c_float(), C.c_float(), C.c_int32()
-        check(self.lib.dtx_step(self._h, ids.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p), C.byref(loss),
-                                C.byref(gn), C.byref(lr), C.byref(st)), self._h)
+        check(self.lib.dtx_step(self._h, ids.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p),
+                                lens.ctypes.data_as(C.c_void_p) if lens is not None else None, S, STEP_FORCE if force_step else 0,
+                                C.byref(loss), C.byref(gn), C.byref(lr), C.byref(st)), self._h)
         return loss.value, gn.value, lr.value, bool(st.value)
 
-    def step_ptr(self, ids_ptr: int, labels_ptr: int, on_device: bool) -> Tuple[float, float, float, bool]:
+    def step_ptr(self, ids_ptr: int, labels_ptr: int, on_device: bool, seq_lens_ptr: int = 0,
+                 seq_len_batch: int = 0) -> Tuple[float, float, float, bool]:
         """Same with raw pointers (pinned host memory, or device memory when on_device)."""
         loss, gn, lr, st = C.c_float(), C.c_float(), C.c_float(), C.c_int32()
         fn = self.lib.dtx_step_device if on_device else self.lib.dtx_step
-        check(fn(self._h, C.c_void_p(ids_ptr), C.c_void_p(labels_ptr), C.byref(loss), C.byref(gn), C.byref(lr),
-                 C.byref(st)), self._h)
+        check(fn(self._h, C.c_void_p(ids_ptr), C.c_void_p(labels_ptr), C.c_void_p(seq_lens_ptr) if seq_lens_ptr else None,
+                 seq_len_batch, 0, C.byref(loss), C.byref(gn), C.byref(lr), C.byref(st)), self._h)
         return loss.value, gn.value, lr.value, bool(st.value)
 
-    def eval_loss(self, input_ids: np.ndarray, labels: np.ndarray) -> float:
-        ids = np.ascontiguousarray(input_ids, dtype=np.int32)
-        lab = np.ascontiguousarray(labels, dtype=np.int32)
+    def eval_loss(self, input_ids: np.ndarray, labels: np.ndarray, seq_lens: Optional[np.ndarray] = None) -> float:
+        ids, lab, lens, S = self._batch_args(input_ids, labels, seq_lens)
         out = C.c_float()
-        check(self.lib.dtx_eval_loss(self._h, ids.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p), C.byref(out)),
+        check(self.lib.dtx_eval_loss(self._h, ids.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p),
+                                     lens.ctypes.data_as(C.c_void_p) if lens is not None else None, S, C.byref(out), None, None),
               self._h)
         return out.value
+
+    def eval_rows(self, input_ids: np.ndarray, labels: np.ndarray,
+                  seq_lens: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """Forward only; returns per row (summed token loss, number of valid tokens)."""
+        ids, lab, lens, S = self._batch_args(input_ids, labels, seq_lens)
+        out = C.c_float()
+        sums = np.zeros(self.train.micro_batch, dtype=np.float32)
+        cnts = np.zeros(self.train.micro_batch, dtype=np.int32)
+        check(self.lib.dtx_eval_loss(self._h, ids.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p),
+                                     lens.ctypes.data_as(C.c_void_p) if lens is not None else None, S, C.byref(out),
+                                     sums.ctypes.data_as(C.c_void_p), cnts.ctypes.data_as(C.c_void_p)), self._h)
+        return sums, cnts
+
+    def allreduce_host(self, values) -> np.ndarray:
+        """Sum a small float64 vector over the ranks of this trainer's communicator."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        check(self.lib.dtx_allreduce_host(self._h, v.ctypes.data_as(C.c_void_p), int(v.size)), self._h)
+        return v
 
     # -- export -------------------------------------------------------------------------------
     def adapter_names(self) -> Iterable[str]:
@@ -291,6 +333,17 @@ class Trainer:
     @property
     def last_step_ms(self) -> float:
         return float(self.lib.dtx_last_step_ms(self._h))
+
+    @property
+    def last_step_timings(self) -> Dict[str, float]:
+        """Event-timed segments of the last step in ms."""
+        out = (C.c_float * 4)()
+        check(self.lib.dtx_last_step_timings(self._h, out), self._h)
+        return {"step": out[0], "fwd_bwd": out[1], "allreduce": out[2], "optimizer": out[3]}
+
+    @property
+    def base_weight_bytes(self) -> int:
+        return int(self.lib.dtx_base_weight_bytes(self._h))
 
 
 def nccl_unique_id() -> bytes:

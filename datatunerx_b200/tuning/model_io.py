@@ -1,7 +1,8 @@
 """Model / adapter file IO of the worker, numpy only (no torch, no safetensors package needed at run time).
 
   * load_model_config  : HF config.json -> ModelConfig  (AutoConfig.from_pretrained, cmd/tuning/train.py:221)
-  * iter_safetensors   : stream tensors of *.safetensors shards (AutoModelForCausalLM.from_pretrained, train.py:236-242)
+  * iter_safetensors   : stream tensors of *.safetensors shards (AutoModelForCausalLM.from_pretrained, train.py:236-242);
+                         iter_torch_bin does the same for pytorch_model*.bin shards
   * save_peft_adapter  : adapter_config.json + adapter_model.safetensors (+ adapter_model.bin when torch is importable)
                          in the layout peft 0.5.0 `save_pretrained` writes and the inference image loads
                          (train.py:300; pkg/util/generate/generate.go:287-294 CHECKPOINT_DIR)
@@ -30,7 +31,7 @@ def load_model_config(model_dir: str) -> ModelConfig:
     return ModelConfig(vocab=cfg["vocab_size"], hidden=cfg["hidden_size"], n_layers=cfg["num_hidden_layers"], n_heads=heads,
                        n_kv_heads=cfg.get("num_key_value_heads", heads), head_dim=cfg.get("head_dim") or cfg["hidden_size"] // heads,
                        ffn=cfg["intermediate_size"], rms_eps=cfg.get("rms_norm_eps", 1e-5), rope_theta=cfg.get("rope_theta", 10000.0),
-                       max_seq=cfg.get("max_position_embeddings", 4096))
+                       max_seq=cfg.get("max_position_embeddings", 4096), sliding_window=int(cfg.get("sliding_window") or 0))
 
 
 def check_attention_window(model_dir: str, seq_len: int) -> None:
@@ -60,17 +61,45 @@ def iter_safetensors(path: str) -> Iterator[Tuple[str, np.ndarray, bool]]:
             yield name, arr, bits
 
 
+def iter_torch_bin(path: str) -> Iterator[Tuple[str, np.ndarray, bool]]:
+    """pytorch_model*.bin shards (torch pickles, the pre-safetensors HF format AutoModelForCausalLM.from_pretrained also
+    accepts, cmd/tuning/train.py:236-242).  Unpickling needs torch on the host - file plumbing only, no torch compute."""
+    import torch
+    sd = torch.load(path, map_location="cpu", weights_only=True, mmap=True)
+    for name, t in sd.items():
+        if t.dtype == torch.bfloat16:
+            yield name, t.contiguous().view(torch.uint16).numpy(), True
+        elif t.dtype in (torch.float16, torch.float32):
+            yield name, t.contiguous().numpy(), False
+        else:
+            yield name, t.float().contiguous().numpy(), False
+
+
 def load_weights_into(trainer, model_dir: str) -> int:
+    """Stream every checkpoint tensor into the trainer.  The library refuses to step while a base tensor is missing, so a
+    partial checkpoint fails loudly instead of training on uninitialised memory."""
     files = sorted(glob.glob(os.path.join(model_dir, "*.safetensors")))
+    readers = [(f, iter_safetensors) for f in files]
     if not files:
-        raise FileNotFoundError(f"no *.safetensors under {model_dir} (pytorch_model.bin checkpoints need conversion)")
-    n = 0
-    for fpath in files:
-        for name, arr, bits in iter_safetensors(fpath):
+        bins = sorted(glob.glob(os.path.join(model_dir, "pytorch_model*.bin")))
+        if not bins:
+            raise FileNotFoundError(f"no *.safetensors or pytorch_model*.bin under {model_dir}")
+        readers = [(f, iter_torch_bin) for f in bins]
+    cfg = json.load(open(os.path.join(model_dir, "config.json")))
+    n, embed, have_head = 0, None, False
+    for fpath, reader in readers:
+        for name, arr, bits in reader(fpath):
             if "rotary_emb.inv_freq" in name:
                 continue
-            trainer.load_tensor(name, np.ascontiguousarray(arr), bf16_bits=bits)
+            arr = np.ascontiguousarray(arr)
+            trainer.load_tensor(name, arr, bf16_bits=bits)
+            if name.endswith("embed_tokens.weight"):
+                embed = (arr, bits)
+            have_head = have_head or name.endswith("lm_head.weight")
             n += 1
+    if not have_head and cfg.get("tie_word_embeddings") and embed is not None:
+        trainer.load_tensor("lm_head.weight", embed[0], bf16_bits=embed[1])  # tied output embedding: no separate tensor on disk
+        n += 1
     return n
 
 

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DTX_ABI_VERSION 1
+#define DTX_ABI_VERSION 2
 #if defined(__GNUC__)
 #define DTX_API __attribute__((visibility("default")))
 #else
@@ -54,6 +54,7 @@ typedef struct {
   int32_t vocab, hidden, n_layers, n_heads, n_kv_heads, head_dim, ffn;
   float rms_eps, rope_theta;
   int32_t max_seq;
+  int32_t sliding_window;  /* Mistral `sliding_window` (0 = none); only changes the mask when train.seq_len exceeds it */
 } dtx_model_cfg;
 
 /* Everything of Seq2SeqTrainingArguments / FinetuningArguments that reaches the training step
@@ -97,24 +98,43 @@ DTX_API int32_t dtx_init_random_weights(dtx_trainer* t, uint64_t seed);
 /* peft 0.5.0 LoRA init on the host RNG-free path: A ~ kaiming-uniform(a=sqrt 5) from `seed`, B = 0. */
 DTX_API int32_t dtx_init_lora(dtx_trainer* t, uint64_t seed);
 
-/* `--quantization int4|int8` (cmd/tuning/train.py:224-234, bitsandbytes): replaces the decoder-layer Linear weights by
- * dequant(quant(W)) once, on the device; mode 4 = NF4 with 64-element fp32 absmax blocks (no double quantisation: the exact
- * values the reference's 4-bit matmul multiplies with), mode 8 = row-wise absmax int8 (weight side of LLM.int8 only).
- * Call after the base weights are loaded.  The GEMMs keep running on resident bf16: 180 GB of HBM make packed storage moot. */
+/* `--quantization int4` (cmd/tuning/train.py:224-230, bitsandbytes BitsAndBytesConfig(load_in_4bit, nf4, fp16 compute, no
+ * double quantisation)): mode 4 re-stores the decoder-layer Linear weights PACKED - two 4-bit NF4 codes per byte plus one fp32
+ * absmax per 64 consecutive elements (0.5625 bytes / weight instead of 2) - and frees the bf16 copies.  Each GEMM that needs a
+ * weight expands it on the fly into a per-trainer bf16 scratch right before the launch (one HBM-bound kernel, bit-identical to
+ * bitsandbytes' dequantize_4bit values).  Call after the base weights are loaded.
+ * mode 8 (`--quantization int8`, LLM.int8 with runtime outlier decomposition) is NOT implemented: DTX_ERR_UNSUPPORTED. */
 DTX_API int32_t dtx_quantize_base(dtx_trainer* t, int32_t mode);
+/* bytes of device memory currently held by the frozen base weights (bf16 or packed NF4 + absmax), for reporting */
+DTX_API int64_t dtx_base_weight_bytes(const dtx_trainer* t);
 
 /* ---- the hot path: one micro-batch of HF Trainer.training_step + (at the accumulation boundary)
- * all-reduce, clip, AdamW, scheduler (train.py:299; ds_config.json ZeRO-0).  input_ids / labels are
- * host int32 [micro_batch, seq_len]; labels use -100 for ignored positions and are NOT pre-shifted.
+ * all-reduce, clip, AdamW, scheduler (train.py:299; ds_config.json ZeRO-0).
+ *   input_ids / labels : host int32 [micro_batch, seq_len_batch]; labels use -100 for ignored positions and are NOT pre-shifted.
+ *   seq_len_batch      : this batch's padded length - a multiple of 128, <= train.seq_len; 0 = train.seq_len.  The reference's
+ *                        DataCollatorForSeq2Seq pads every batch to its own longest row (train.py:282-286): so does the host here.
+ *   seq_lens           : host int32 [micro_batch] true row lengths (right padding beyond them), or NULL = every row is full.
+ *                        Attention tiles that lie entirely in a row's padding are skipped (their outputs are written as zeros).
+ *   flags              : DTX_STEP_FORCE = run the optimizer step after this micro-batch even if fewer than grad_accum have been
+ *                        accumulated (HF Trainer's end-of-epoch step when an epoch holds fewer batches than grad_accum).
  * Outputs (host): mean token loss of this micro-batch, global grad-norm before clipping and the lr used
  * (both only meaningful when *stepped_out == 1). */
-DTX_API int32_t dtx_step(dtx_trainer* t, const int32_t* input_ids, const int32_t* labels, float* loss_out,
-                 float* grad_norm_out, float* lr_out, int32_t* stepped_out);
-/* Same with the batch already resident on this trainer's device (int32 device pointers). */
-DTX_API int32_t dtx_step_device(dtx_trainer* t, const void* d_input_ids, const void* d_labels, float* loss_out,
-                        float* grad_norm_out, float* lr_out, int32_t* stepped_out);
-/* Forward only: SFTTrainer.evaluate's eval_loss (cmd/tuning/trainer.py:324-327). */
-DTX_API int32_t dtx_eval_loss(dtx_trainer* t, const int32_t* input_ids, const int32_t* labels, float* loss_out);
+#define DTX_STEP_FORCE 1
+DTX_API int32_t dtx_step(dtx_trainer* t, const int32_t* input_ids, const int32_t* labels, const int32_t* seq_lens,
+                 int32_t seq_len_batch, int32_t flags, float* loss_out, float* grad_norm_out, float* lr_out,
+                 int32_t* stepped_out);
+/* Same with the batch already resident on this trainer's device (int32 device pointers; d_seq_lens may be NULL). */
+DTX_API int32_t dtx_step_device(dtx_trainer* t, const void* d_input_ids, const void* d_labels, const void* d_seq_lens,
+                        int32_t seq_len_batch, int32_t flags, float* loss_out, float* grad_norm_out, float* lr_out,
+                        int32_t* stepped_out);
+/* Forward only: SFTTrainer.evaluate's eval_loss (cmd/tuning/trainer.py:324-327).  row_loss_sum_out / row_valid_out (host,
+ * [micro_batch], may be NULL) receive each row's summed token loss and number of valid tokens so that the host can form HF's
+ * per_device_eval_batch_size batches whatever the native micro-batch is. */
+DTX_API int32_t dtx_eval_loss(dtx_trainer* t, const int32_t* input_ids, const int32_t* labels, const int32_t* seq_lens,
+                      int32_t seq_len_batch, float* loss_out, float* row_loss_sum_out, int32_t* row_valid_out);
+/* Sum a small host array over all ranks of this trainer's communicator (NCCL; a no-op when world == 1).  Used for the
+ * evaluation mean across ranks (HF gathers the eval losses of all processes). */
+DTX_API int32_t dtx_allreduce_host(dtx_trainer* t, double* inout, int32_t n);
 
 /* ---- export: trainer.save_model writes the PEFT adapter (train.py:300).  hf_name as in
  * dtx_load_tensor ("...lora_A.weight" / "...lora_B.weight"); fp32, row-major, caller-sized. */
@@ -124,15 +144,15 @@ DTX_API int64_t dtx_num_trainable(const dtx_trainer* t);
 DTX_API int64_t dtx_launch_count(const dtx_trainer* t);
 /* device time of the most recent dtx_step in ms (CUDA events on the trainer's stream) */
 DTX_API float dtx_last_step_ms(const dtx_trainer* t);
+/* event-timed segments of the most recent dtx_step in ms: out[0] whole step, out[1] forward + backward, out[2] gradient
+ * all-reduce (0 when world == 1 or no optimizer step ran), out[3] grad-norm + clip + AdamW + adapter refresh */
+DTX_API int32_t dtx_last_step_timings(const dtx_trainer* t, float* out4);
 /* HF get_scheduler value: lr multiplier after `step` optimizer steps (host arithmetic, no device). */
 DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, int32_t total_steps);
 
 /* Tuning / diagnostics switches.  "gemm_pair_kernel" = 1 (default): wide GEMMs run the cta_group::2 CTA-pair kernel;
  * 0: the single-CTA kernel everywhere (used for A/B measurements in profiles/).  "fused_epilogues" = 1 (default): RoPE and
- * SwiGLU run inside the GEMM / attention epilogues; 0: separate HBM-bound kernels.  "attn_fwd_two_tiles" = 1 (default):
- * forward attention runs two query tiles per CTA with the output accumulated in tensor memory; 0: one-tile kernel (two CTAs
- * per SM).  "attn_dq_tmem_operands" = 1 (default): dQ kernel with Q / dO resident in tensor memory; 0: two-group kernel.
- * "attn_bwd_warps16" = 0 (default): 8 compute warps in the dK/dV kernel; 1: 16.  "gemm_group_m": rasterisation group of the
+ * SwiGLU run inside the GEMM / attention epilogues; 0: separate HBM-bound kernels.  "gemm_group_m": rasterisation group of the
  * CTA-pair GEMM in 256-row tiles (default 16).  Unknown names return DTX_ERR_INVALID. */
 DTX_API int32_t dtx_set_option(const char* name, int32_t value);
 
@@ -142,6 +162,17 @@ DTX_API int32_t dtx_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, co
                       const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int32_t K2, void* C, int64_t ldc,
                       const void* R, int64_t ldr, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t split_k,
                       int32_t block_n, void* stream);
+/* The fused epilogues of the CTA-pair GEMM as the training step runs them (M > 128, B operand K-major or MN-major):
+ *   epilogue 3 (RoPE)        : C[M,N] bf16 = rotary(acc) on columns < rope_cols (head_dim 128, half-split pairs i / i+64, position =
+ *                              row % rope_S), plain beyond; rope_cs = device [rope_S][64] float2 (cos, sin) from dtx_rope_table
+ *   epilogue 4 (SwiGLU fwd)  : B rows in the GU-interleaved layout (128 gate rows | 128 up rows per 128 features): C[M,N] = acc
+ *                              (the interleaved gate|up activations), aux[M, N/2] = silu(gate) * up
+ *   epilogue 5 (SwiGLU bwd)  : acc = d(act) [M, N=F]; aux = saved gate|up [M, 2F] (interleaved, ld_aux = 2F); C[M, 2F] = d(gate|up)
+ * A2/B2/K2 extend the contraction as in dtx_gemm_bf16. */
+DTX_API int32_t dtx_gemm_fused(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t b_mn_major, const void* A2,
+                       int64_t lda2, const void* B2, int64_t ldb2, int32_t K2, void* C, int64_t ldc, void* aux, int64_t ld_aux,
+                       const void* rope_cs, int32_t rope_S, int32_t rope_cols, int32_t M, int32_t N, int32_t K,
+                       int32_t epilogue, void* stream);
 DTX_API int32_t dtx_embedding_fwd(const void* ids, const void* table, void* out, int32_t M, int32_t d, int32_t vocab, void* stream);
 DTX_API int32_t dtx_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd, int32_t M, int32_t d, float eps, void* stream);
 DTX_API int32_t dtx_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* rstd, const void* dres, void* dx,
@@ -157,6 +188,9 @@ DTX_API int32_t dtx_lora_dropout_fwd(const void* h, void* hd, int32_t M, int32_t
 DTX_API int32_t dtx_lora_dropout_bwd_add(void* dh, const void* g, int32_t M, int32_t d, int32_t nt, float p, uint64_t key,
                                  void* stream);
 DTX_API int32_t dtx_nf4_roundtrip(void* w_bf16, int64_t n, void* stream);
+/* packed NF4 storage (bitsandbytes quantize_4bit layout: first element of a pair in the high nibble; one fp32 absmax per 64) */
+DTX_API int32_t dtx_nf4_pack(const void* w_bf16, void* packed_u8, void* absmax_f32, int64_t n, void* stream);
+DTX_API int32_t dtx_nf4_dequant(const void* packed_u8, const void* absmax_f32, void* w_bf16, int64_t n, void* stream);
 DTX_API int32_t dtx_cross_entropy(const void* logits_f32, int64_t ldl, const void* labels_unshifted, void* shifted_scratch,
                           void* n_valid_scratch, void* row_loss, void* dlogits_bf16, int64_t ldd, void* loss_out,
                           int32_t B, int32_t S, int32_t V, void* stream);
@@ -164,11 +198,17 @@ DTX_API int32_t dtx_sumsq(const void* g, int64_t n, void* scratch, void* out, vo
 DTX_API int32_t dtx_adamw(void* p, const void* g, void* m, void* v, int64_t n, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int32_t step, float grad_scale, const void* sumsq, float max_grad_norm,
                   void* grad_norm_out, void* stream);
-/* attention: packed qkv [B*S, (H + 2*Hkv)*128]; Hkv < H = grouped-query attention (Mistral / Llama-2-70B) */
+/* attention: packed qkv [B*S, (H + 2*Hkv)*128]; Hkv < H = grouped-query attention (Mistral / Llama-2-70B).
+ *   seq_lens : optional device int32 [B] true row lengths (right padding beyond): tiles entirely in the padding are skipped and
+ *              their outputs written as zeros; NULL = all rows full.
+ *   window   : sliding-window span (query i sees keys i - window .. i), 0 = plain causal.
+ *   rope_cs_t (backward): optional TRANSPOSED rotary table [64][rope_stride] float2 - when given, dq and dk leave the kernel
+ *              with the inverse rotary applied (what the training step does instead of a separate RoPE-backward kernel). */
 DTX_API int32_t dtx_attn_fwd(const void* qkv, void* out, void* lse2, int32_t B, int32_t S, int32_t H, int32_t Hkv, float scale,
-                     void* stream);
+                     const void* seq_lens, int32_t window, void* stream);
 DTX_API int32_t dtx_attn_bwd(const void* qkv, const void* out, const void* dout, const void* lse2, void* delta_scratch,
-                     void* dqkv, int32_t B, int32_t S, int32_t H, int32_t Hkv, float scale, void* stream);
+                     void* dqkv, int32_t B, int32_t S, int32_t H, int32_t Hkv, float scale, const void* seq_lens,
+                     int32_t window, const void* rope_cs_t, int32_t rope_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ def test_header_and_binding_agree():
 def test_library_exports_every_declared_symbol(lib):
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.dtx_abi_version() == 1
+    assert lib.dtx_abi_version() == 2
 
 
 def test_no_cpu_fallback_create_fails_without_gpu(lib):
@@ -44,11 +44,25 @@ def test_unsupported_configs_are_rejected_loudly(lib):
         L.TrainConfig(micro_batch=1, seq_len=128, total_steps=1, lora_target=("o_proj",)).to_c()
 
 
+def test_struct_layouts_match_the_header(lib):
+    """ctypes mirrors of dtx_model_cfg / dtx_train_cfg: field order and count as declared in include/dtxtune.h."""
+    from datatunerx_b200 import lib as L
+    src = open(os.path.join(ROOT, "include", "dtxtune.h")).read()
+    for cname, cls in (("dtx_model_cfg", L.ModelCfg), ("dtx_train_cfg", L.TrainCfg)):
+        body = re.search(r"typedef struct \{([^}]*)\} " + cname + ";", src).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
+        assert names == [f[0] for f in cls._fields_], (cname, names)
+
+
 def test_option_switches_are_known_and_unknown_names_rejected(lib):
     """Every A/B switch documented in include/dtxtune.h / kernels.h is accepted (host-side flags, no device needed)."""
     from datatunerx_b200 import lib as L
-    defaults = {"gemm_pair_kernel": 1, "gemm_group_m": 16, "fused_epilogues": 1, "attn_fwd_two_tiles": 1, "attn_dq_tmem_operands": 1,
-                "attn_bwd_warps16": 0}
+    defaults = {"gemm_pair_kernel": 1, "gemm_group_m": 16, "fused_epilogues": 1}
     for name, value in defaults.items():
         L.set_option(name, value)  # restores the default: raises DtxError on an unknown name
     with pytest.raises(L.DtxError):

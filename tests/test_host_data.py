@@ -57,6 +57,31 @@ def test_epoch_batches_same_permutation_on_every_rank():
     assert sorted(seen) == sorted(set(seen)) and len(seen) == 20
 
 
+def test_last_partial_batch_is_kept_and_step_counts_follow_hf():
+    """HF Trainer keeps the last partial batch (dataloader_drop_last=False) and the reference computes ceil(len / batch)
+    (cmd/tuning/train.py:192-193): 11 examples on one rank at batch 4 -> 3 batches, the third with one filler row."""
+    from datatunerx_b200.tuning.train import total_optimizer_steps
+    ds = [([5 + i] * (3 + i), [-100] + [5 + i] * (2 + i)) for i in range(11)]
+    batches = list(D.epoch_batches(ds, 0, 1, 4, 256, 0, epoch=0, seed=1, varlen=True))
+    assert len(batches) == D.steps_per_epoch(11, 1, 4) == 3
+    ids, lab, lens = batches[-1]
+    assert ids.shape == (4, 128) and lens.tolist()[3] == 0 and (lab[3] == D.IGNORE_INDEX).all() and (lens[:3] > 0).all()
+    assert sorted(int(x[0]) for b in batches for x, n in zip(b[0], b[2]) if n > 0) == [5 + i for i in range(11)]
+    # every batch is padded to its own longest row rounded up to the 128-row tile, never beyond the static length
+    assert all(b[0].shape[1] == 128 for b in batches)
+    long_ds = [(list(range(3, 3 + 300)), list(range(3, 3 + 300))), ([1, 2], [-100, 2])]
+    (i2, l2, n2), = list(D.epoch_batches(long_ds, 0, 1, 2, 512, 0, epoch=0, seed=0, varlen=True))
+    assert i2.shape == (2, 384) and sorted(n2.tolist()) == [2, 300]
+    assert D.batch_seq_len([5000], 2048) == 2048 and D.batch_seq_len([1], 2048) == 128 and D.batch_seq_len([129, 7], 2048) == 256
+    # two ranks: Ray's equal split drops the odd example, each rank then has ceil(5 / 4) = 2 batches
+    assert D.steps_per_epoch(11, 2, 4) == 2 and len(list(D.epoch_batches(ds, 1, 2, 4, 256, 0, epoch=0, seed=1))) == 2
+    # HF: num_update_steps_per_epoch = max(len(dataloader) // GA, 1); max_steps = ceil(epochs * that)
+    assert total_optimizer_steps(11, 1, 4, 1, 2, -1) == 6 and total_optimizer_steps(11, 1, 4, 2, 3, -1) == 3
+    assert total_optimizer_steps(3, 1, 4, 4, 2, -1) == 2 and total_optimizer_steps(1000, 8, 8, 1, 1, 7) == 7
+    # the reference's own known answer: 84 total steps in cmd/tuning/prometheus/metrics.py:117-124 style runs (ceil semantics)
+    assert total_optimizer_steps(84 * 8 - 3, 1, 8, 1, 1, -1) == 84
+
+
 def test_controller_entrypoint_is_accepted_verbatim():
     # the exact string getRayJobEntrypoint builds (finetune_controller.go:451-516), including the double space
     s = P.controller_entrypoint("/tmp/llama2-7b/", "/data/train.csv", validate_file="/data/val.csv",
@@ -98,9 +123,12 @@ def test_empty_ragged_and_oversized_inputs(tmp_path):
     ds = D.build_dataset(rows, tok, 64)
     assert len(ds) == 1 and len(ds[0][0]) == len(ds[0][1]) <= 64
     assert D.build_dataset([], tok, 64) == []
-    # an empty shard yields no batches; fewer examples than one global batch yields none either (drop-last semantics)
+    # an empty shard yields no batches (the worker refuses to start on it); fewer examples than one batch yield ONE batch
+    # filled up with fully masked rows (HF keeps the last partial batch)
     assert list(D.epoch_batches([], 0, 2, 4, 128, tok.eos_token_id, seed=0, epoch=0)) == []
-    assert D.steps_per_epoch(3, 2, 4) == 0
+    assert D.steps_per_epoch(3, 2, 4) == 1 and D.steps_per_epoch(1, 2, 4) == 0
+    (ids_t, lab_t), = list(D.epoch_batches(ds * 3, 0, 2, 4, 128, tok.eos_token_id, seed=0, epoch=0))
+    assert ids_t.shape == (4, 128) and (lab_t[1:] == D.IGNORE_INDEX).all() and (lab_t[0] != D.IGNORE_INDEX).any()
     # ragged lengths collate to one static shape; an example longer than the static length is cut, never overflows
     long_ids = list(range(3, 3 + 300))
     ids, lab = D.collate([(long_ids, long_ids), ([1, 2], [-100, 2])], 128, pad_id=0)
