@@ -1171,7 +1171,7 @@ int32_t dtx_allreduce_host(dtx_trainer* t, double* inout, int32_t n) {
   return DTX_OK;
 }
 
-int32_t dtx_export_adapter(dtx_trainer* t, const char* name, void* host_out, int64_t nbytes) {
+static int32_t export_lora_tensor(dtx_trainer* t, const float* flat, const char* name, void* host_out, int64_t nbytes) {
   if (!t || !name || !host_out) return t ? t->fail(DTX_ERR_INVALID, "null argument") : DTX_ERR_INVALID;
   cudaSetDevice(t->device);
   const int64_t d = t->mc.hidden, r = t->tc.lora_r;
@@ -1188,8 +1188,8 @@ int32_t dtx_export_adapter(dtx_trainer* t, const char* name, void* host_out, int
   const int64_t d_out = t->tg[ti].d_out;
   const bool is_a = strstr(rest, "lora_A") != nullptr;
   if (nbytes < (is_a ? d : d_out) * r * 4) return t->fail(DTX_ERR_INVALID, "%s: output buffer too small", name);
-  const float* base = t->params + static_cast<int64_t>(layer) * t->per_layer + t->tg[ti].off;
-  cudaStreamSynchronize(t->stream);
+  const float* base = flat + static_cast<int64_t>(layer) * t->per_layer + t->tg[ti].off;
+  CKM(cudaStreamSynchronize(t->stream));
   std::vector<float> tmp(d * r);
   float* out = static_cast<float*>(host_out);
   if (strstr(rest, "lora_A")) {
@@ -1202,6 +1202,13 @@ int32_t dtx_export_adapter(dtx_trainer* t, const char* name, void* host_out, int
     return t->fail(DTX_ERR_INVALID, "%s: expected lora_A or lora_B", name);
   }
   return DTX_OK;
+}
+
+int32_t dtx_export_adapter(dtx_trainer* t, const char* name, void* host_out, int64_t nbytes) {
+  return export_lora_tensor(t, t ? t->params : nullptr, name, host_out, nbytes);
+}
+int32_t dtx_export_adapter_grad(dtx_trainer* t, const char* name, void* host_out, int64_t nbytes) {
+  return export_lora_tensor(t, t ? t->grads : nullptr, name, host_out, nbytes);
 }
 
 int64_t dtx_num_trainable(const dtx_trainer* t) { return t ? t->n_train : 0; }

@@ -51,6 +51,22 @@ class Rendezvous:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t[0]) / self.world
 
+    def sum_over_ranks(self, x: float) -> float:
+        if self.dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t[0])
+
+    def gather_objects(self, obj) -> list:
+        """Every rank's `obj`, in rank order, on every rank."""
+        if self.dist is None:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
     def close(self) -> None:
         if self.dist is not None and self.dist.is_initialized():
             self.dist.destroy_process_group()

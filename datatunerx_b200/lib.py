@@ -47,7 +47,7 @@ class TrainCfg(C.Structure):
 ABI_SYMBOLS = [
     "dtx_abi_version", "dtx_last_global_error", "dtx_last_error", "dtx_trainer_create", "dtx_trainer_destroy",
     "dtx_get_nccl_unique_id", "dtx_load_tensor", "dtx_init_random_weights", "dtx_init_lora", "dtx_quantize_base", "dtx_step",
-    "dtx_step_device", "dtx_eval_loss", "dtx_allreduce_host", "dtx_export_adapter", "dtx_num_trainable", "dtx_launch_count",
+    "dtx_step_device", "dtx_eval_loss", "dtx_allreduce_host", "dtx_export_adapter", "dtx_export_adapter_grad", "dtx_num_trainable", "dtx_launch_count",
     "dtx_base_weight_bytes", "dtx_last_step_ms", "dtx_last_step_timings", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16",
     "dtx_gemm_fused", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
     "dtx_rope_table", "dtx_rope_qk", "dtx_swiglu_fwd", "dtx_swiglu_bwd", "dtx_lora_dropout_fwd", "dtx_lora_dropout_bwd_add",
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
     lib.dtx_gemm_fused.argtypes = [vp, i64, vp, i64, i32, vp, i64, vp, i64, i32, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32,
                                    i32, vp]
     lib.dtx_export_adapter.argtypes = [vp, C.c_char_p, vp, i64]
+    lib.dtx_export_adapter_grad.argtypes = [vp, C.c_char_p, vp, i64]
     lib.dtx_num_trainable.argtypes = [vp]
     lib.dtx_num_trainable.restype = i64
     lib.dtx_launch_count.argtypes = [vp]
@@ -309,16 +310,18 @@ class Trainer:
                 for ab in ("lora_A", "lora_B"):
                     yield f"base_model.model.model.layers.{l}.self_attn.{t}.{ab}.weight"
 
-    def export_adapter(self) -> Dict[str, np.ndarray]:
-        """PEFT state dict (fp32): lora_A [r, in], lora_B [out, r] per target module."""
+    def export_adapter(self, grads: bool = False) -> Dict[str, np.ndarray]:
+        """PEFT state dict (fp32): lora_A [r, in], lora_B [out, r] per target module.  grads=True returns, under the same
+        names, the summed gradient the last optimizer step consumed."""
         out = {}
+        fn = self.lib.dtx_export_adapter_grad if grads else self.lib.dtx_export_adapter
         d, r = self.model.hidden, self.train.lora_r
         dkv = (self.model.n_kv_heads or self.model.n_heads) * self.model.head_dim
         for name in self.adapter_names():
             d_out = d if ".q_proj." in name else dkv
             shape = (r, d) if "lora_A" in name else (d_out, r)
             buf = np.empty(shape, dtype=np.float32)
-            check(self.lib.dtx_export_adapter(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes), self._h)
+            check(fn(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes), self._h)
             out[name] = buf
         return out
 

@@ -139,6 +139,9 @@ DTX_API int32_t dtx_allreduce_host(dtx_trainer* t, double* inout, int32_t n);
 /* ---- export: trainer.save_model writes the PEFT adapter (train.py:300).  hf_name as in
  * dtx_load_tensor ("...lora_A.weight" / "...lora_B.weight"); fp32, row-major, caller-sized. */
 DTX_API int32_t dtx_export_adapter(dtx_trainer* t, const char* hf_name, void* host_out, int64_t nbytes);
+/* The gradient the last optimizer step consumed, in the same naming and layout: the SUM over ranks and accumulated
+ * micro-batches of d(mean token loss)/d(tensor), before the 1/(world*grad_accum) scaling and clipping (parity tests). */
+DTX_API int32_t dtx_export_adapter_grad(dtx_trainer* t, const char* hf_name, void* host_out, int64_t nbytes);
 DTX_API int64_t dtx_num_trainable(const dtx_trainer* t);
 /* kernels launched by this trainer since creation (bench.py's gpu_launches) */
 DTX_API int64_t dtx_launch_count(const dtx_trainer* t);

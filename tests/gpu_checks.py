@@ -255,12 +255,22 @@ def check_nf4(n=64 * 5000):
 
 
 def check_trainer_qlora(steps=6):
-    """--quantization int4: native trainer with device-side NF4 round trip == oracle trained on nf4_roundtrip'ed weights."""
+    """--quantization int4: native trainer on PACKED NF4 base weights == oracle trained on nf4_roundtrip'ed weights; the packed
+    base is 0.5625 / 2 of the bf16 one; int8 is refused loudly."""
     ocfg, mc, tc = tiny_configs(steps=steps)
     w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
     tr = L.Trainer(mc, tc)
     tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+    bytes_bf16 = tr.base_weight_bytes
+    try:
+        tr.quantize_base("int8")
+        raise AssertionError("int8 must be refused")
+    except L.DtxError as e:
+        assert e.code == -5, e
     tr.quantize_base("int4")
+    bytes_nf4 = tr.base_weight_bytes
+    lin = sum(v.numel() for k, v in w.items() if k.endswith(O.QUANTIZED_SUFFIXES))
+    assert bytes_bf16 - bytes_nf4 == lin * 2 - (lin // 2 + lin // 64 * 4), (bytes_bf16, bytes_nf4, lin)
     tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
     orc = O.OracleTrainer(ocfg, O.quantize_base_nf4(w), lora)
     worst_l = worst_g = 0.0
@@ -272,7 +282,8 @@ def check_trainer_qlora(steps=6):
     tr.close()
     plain = O.OracleTrainer(ocfg, w, lora).step([O.synthetic_batch(0, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)]).loss
     assert worst_l < 1e-3 and worst_g < 3e-2, (worst_l, worst_g)
-    return {"loss": worst_l, "gnorm": worst_g, "loss_shift_vs_unquantized": abs(plain - ref.loss)}
+    return {"loss": worst_l, "gnorm": worst_g, "loss_shift_vs_unquantized": abs(plain - ref.loss), "base_bytes_bf16": bytes_bf16,
+            "base_bytes_nf4": bytes_nf4}
 
 
 def check_embedding(M=500, d=256, V=1000):
@@ -367,7 +378,7 @@ def check_attn_fwd(B=2, S=256, H=2, Hkv=None, growing=False):
     qkv = _growing_scores_qkv(B, S, H, Hkv, D) if growing else _rand(B * S, (H + 2 * Hkv) * D, seed=11)
     out = torch.full((B * S, H * D), float("nan"), dtype=torch.bfloat16, device=DEV)
     lse2 = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
-    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, 1.0 / math.sqrt(D), STREAM()))
+    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, 1.0 / math.sqrt(D), None, 0, STREAM()))
     torch.cuda.synchronize()
     ref, lse = _attn_ref(qkv, B, S, H, D, Hkv)
     e = rel_err(out, ref)
@@ -375,28 +386,6 @@ def check_attn_fwd(B=2, S=256, H=2, Hkv=None, growing=False):
     assert e < 8e-3, f"attn fwd {e}"
     assert e_l < 2e-3, f"attn lse {e_l}"
     return {"out": e, "lse": e_l}
-
-
-def check_attn_fwd_one_tile():
-    """The one-tile forward kernel (output in registers) stays available behind an option: same parity bar."""
-    L.set_option("attn_fwd_two_tiles", 0)
-    try:
-        return {"s384": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "s1024": check_attn_fwd(B=1, S=1024, H=1)}
-    finally:
-        L.set_option("attn_fwd_two_tiles", 1)
-
-
-def check_attn_bwd_variants():
-    """The alternative backward kernels kept behind options (two-group dQ kernel, 16-warp dK/dV kernel): same parity bar."""
-    out = {}
-    for opt, val in (("attn_dq_tmem_operands", 0), ("attn_bwd_warps16", 1)):
-        default = 1 - val
-        L.set_option(opt, val)
-        try:
-            out[f"{opt}={val}"] = {"s384": check_attn_bwd(B=2, S=384, H=4, Hkv=2), "s1024": check_attn_bwd(B=1, S=1024, H=1)}
-        finally:
-            L.set_option(opt, default)
-    return out
 
 
 def check_attn_bwd(B=2, S=256, H=2, Hkv=None):
@@ -410,8 +399,8 @@ def check_attn_bwd(B=2, S=256, H=2, Hkv=None):
     delta = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
     dqkv = torch.full((B * S, (H + 2 * Hkv) * D), float("nan"), dtype=torch.bfloat16, device=DEV)
     sc = 1.0 / math.sqrt(D)
-    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, sc, STREAM()))
-    ok(lib.dtx_attn_bwd(P(qkv), P(out), P(dout), P(lse2), P(delta), P(dqkv), B, S, H, Hkv, sc, STREAM()))
+    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, sc, None, 0, STREAM()))
+    ok(lib.dtx_attn_bwd(P(qkv), P(out), P(dout), P(lse2), P(delta), P(dqkv), B, S, H, Hkv, sc, None, 0, None, 0, STREAM()))
     torch.cuda.synchronize()
     x = qkv.float().requires_grad_(True)
     ref, _ = _attn_ref(x, B, S, H, D, Hkv)
@@ -423,6 +412,375 @@ def check_attn_bwd(B=2, S=256, H=2, Hkv=None):
     for n, e in errs.items():
         assert e < 1.5e-2, f"attn bwd {n} {e}"
     return errs
+
+
+def check_nf4_pack(n=64 * 4096):
+    """Packed NF4 storage: codes and absmax equal the oracle's restatement of bitsandbytes quantize_4bit (first element of a
+    pair in the high nibble), and pack -> dequant is bit-identical to the one-kernel round trip and to the oracle."""
+    lib = L.load()
+    w = _rand(n, scale=0.02, seed=33)
+    w[128:192] = 0
+    packed = torch.empty(n // 2, dtype=torch.uint8, device=DEV)
+    absmax = torch.empty(n // 64, dtype=torch.float32, device=DEV)
+    out = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    ok(lib.dtx_nf4_pack(P(w), P(packed), P(absmax), n, STREAM()))
+    ok(lib.dtx_nf4_dequant(P(packed), P(absmax), P(out), n, STREAM()))
+    rt = w.clone()
+    ok(lib.dtx_nf4_roundtrip(P(rt), n, STREAM()))
+    torch.cuda.synchronize()
+    x = w.float().cpu().numpy().reshape(-1, 64)
+    amax = np.abs(x).max(axis=1, keepdims=True).astype(np.float32)
+    inv = np.where(amax > 0, np.float32(1.0) / np.where(amax > 0, amax, 1), 0).astype(np.float32)
+    mids = (np.float32(0.5) * (O.NF4_LEVELS[:-1] + O.NF4_LEVELS[1:])).astype(np.float32)
+    code = (((x * inv)[..., None] > mids).sum(-1)).astype(np.uint8).reshape(-1)
+    ref_bytes = (code[0::2] << 4) | code[1::2]
+    assert np.array_equal(packed.cpu().numpy(), ref_bytes), "packed NF4 codes differ from the oracle"
+    assert np.array_equal(absmax.cpu().numpy(), amax.reshape(-1)), "absmax differs"
+    ref = O.nf4_roundtrip(w.float().cpu().view(-1, 64)).view(-1)
+    assert torch.equal(out.float().cpu(), ref) and torch.equal(rt, out), "dequantised values differ"
+    return {"bytes_per_weight": (packed.numel() + absmax.numel() * 4) / n}
+
+
+def _rope_table(S, D=128):
+    lib = L.load()
+    cs = torch.empty(S, D // 2, 2, dtype=torch.float32, device=DEV)
+    ok(lib.dtx_rope_table(P(cs), S, D, 10000.0, STREAM()))
+    return cs
+
+
+def _rope_ref(x, S, n_rot_heads, D=128):
+    """x: [M, W] fp32 packed heads; rotary (HF rotate_half) on the first n_rot_heads heads, position = row % S."""
+    M, W = x.shape
+    cos, sin = O.rope_cos_sin(S, D, 10000.0)
+    cos, sin = cos.to(x.device), sin.to(x.device)
+    pos = torch.arange(M, device=x.device) % S
+    h = x[:, : n_rot_heads * D].reshape(M, n_rot_heads, D)
+    rot = h * cos[pos][:, None, :] + O.rotate_half(h) * sin[pos][:, None, :]
+    return torch.cat([rot.reshape(M, -1), x[:, n_rot_heads * D:]], dim=1)
+
+
+def gemm_fused(A, B, epi, *, b_mn=False, A2=None, B2=None, C_cols=None, aux=None, ld_aux=0, rope_cs=None, rope_S=0, rope_cols=0, N=None):
+    lib = L.load()
+    M, K = A.shape
+    if N is None:
+        N = B.shape[1] if b_mn else B.shape[0]
+    K2 = A2.shape[1] if A2 is not None else 0
+    Cm = torch.full((M, C_cols or N), float("nan"), dtype=torch.bfloat16, device=A.device)
+    ok(lib.dtx_gemm_fused(P(A), A.stride(0), P(B), B.stride(0), int(b_mn), P(A2), A2.stride(0) if A2 is not None else 0, P(B2),
+                          B2.stride(0) if B2 is not None else 0, K2, P(Cm), Cm.stride(0), P(aux), ld_aux, P(rope_cs), rope_S, rope_cols,
+                          M, N, K, epi, STREAM()))
+    torch.cuda.synchronize()
+    return Cm
+
+
+def check_gemm_rope_epilogue(S=640, B=3, H=16, Hkv=4, K=1024, ragged=True):
+    """EPI_ROPE as the qkv projection runs it: wide N (many 256-column tiles, two heads per tile), LoRA K-extension, ragged M,
+    GQA widths (rope on q and k heads only, v untouched)."""
+    D = 128
+    M = B * S - (37 if ragged else 0)
+    W = (H + 2 * Hkv) * D
+    A, Bw = _rand(M, K, seed=41), _rand(W, K, scale=0.05, seed=42)
+    A2, B2 = _rand(M, 64, seed=43), _rand(W, 64, scale=0.05, seed=44)
+    cs = _rope_table(S)
+    got = gemm_fused(A, Bw, L.EPI_ROPE, A2=A2, B2=B2, rope_cs=cs, rope_S=S, rope_cols=(H + Hkv) * D)
+    acc = A.float() @ Bw.float().t() + A2.float() @ B2.float().t()
+    ref = _rope_ref(acc, S, H + Hkv)
+    e = rel_err(got, ref)
+    e_v = rel_err(got[:, (H + Hkv) * D:], acc[:, (H + Hkv) * D:])
+    assert e < 6e-3 and e_v < 6e-3, f"EPI_ROPE rel_err {e} (v part {e_v})"
+    worst_tile = max(rel_err(got[:, c:c + 256], ref[:, c:c + 256]) for c in range(0, W, 256))
+    assert worst_tile < 8e-3, f"EPI_ROPE worst 256-column tile {worst_tile}"
+    return {"rel_err": e, "worst_tile": worst_tile, "shape": [M, W, K]}
+
+
+def _interleave_gu(wg, wu):
+    """[F, d] gate and up weights -> the trainer's GU-interleaved [2F, d] layout (128 gate rows | 128 up rows per 128 features)."""
+    F, d = wg.shape
+    return torch.stack([wg.view(F // 128, 128, d), wu.view(F // 128, 128, d)], dim=1).reshape(2 * F, d).contiguous()
+
+
+def _deinterleave_cols(x, F):
+    """[M, 2F] interleaved columns -> (gate [M, F], up [M, F])."""
+    M = x.shape[0]
+    v = x.reshape(M, F // 128, 2, 128)
+    return v[:, :, 0].reshape(M, F), v[:, :, 1].reshape(M, F)
+
+
+def check_gemm_swiglu_epilogues(M=1500, d=1024, F=11008):
+    """EPI_SWIGLU_FWD / EPI_SWIGLU_BWD at the 7B feature width (86 column tiles) with ragged M, against fp32 torch."""
+    A = _rand(M, d, seed=51)
+    wg, wu = _rand(F, d, scale=0.04, seed=52), _rand(F, d, scale=0.04, seed=53)
+    wgu = _interleave_gu(wg, wu)
+    act = torch.full((M, F), float("nan"), dtype=torch.bfloat16, device=DEV)
+    gu = gemm_fused(A, wgu, L.EPI_SWIGLU_FWD, aux=act, ld_aux=F)
+    g_ref, u_ref = A.float() @ wg.float().t(), A.float() @ wu.float().t()
+    g_got, u_got = _deinterleave_cols(gu, F)
+    e_g, e_u = rel_err(g_got, g_ref), rel_err(u_got, u_ref)
+    act_ref = torch.nn.functional.silu(g_ref) * u_ref
+    e_a = rel_err(act, act_ref)
+    assert max(e_g, e_u) < 6e-3 and e_a < 8e-3, f"EPI_SWIGLU_FWD gate {e_g} up {e_u} act {e_a}"
+    # backward: acc = dx * Wdown (Wdown [d, F] row-major = MN-major B), saved gu -> d(gate|up)
+    dx = _rand(M, d, seed=54)
+    wdown = _rand(d, F, scale=0.04, seed=55)
+    dgu = gemm_fused(dx, wdown, L.EPI_SWIGLU_BWD, b_mn=True, C_cols=2 * F, aux=gu, ld_aux=2 * F, N=F)
+    dact = (dx.float() @ wdown.float()).to(torch.bfloat16).float()  # the kernel rounds d(act) to bf16 like the unfused path
+    g = g_got.float().requires_grad_(True)
+    u = u_got.float().requires_grad_(True)
+    (torch.nn.functional.silu(g) * u).backward(dact)
+    dg_got, du_got = _deinterleave_cols(dgu, F)
+    e_dg, e_du = rel_err(dg_got, g.grad), rel_err(du_got, u.grad)
+    assert max(e_dg, e_du) < 8e-3, f"EPI_SWIGLU_BWD dgate {e_dg} dup {e_du}"
+    worst_tile = max(rel_err(dg_got[:, c:c + 128], g.grad[:, c:c + 128]) for c in range(0, F, 128))
+    assert worst_tile < 1.2e-2, f"EPI_SWIGLU_BWD worst tile {worst_tile}"
+    return {"gate": e_g, "up": e_u, "act": e_a, "dgate": e_dg, "dup": e_du, "worst_tile": worst_tile}
+
+
+def _attn_ref_heads(qkv, B, S, H, Hkv, q_heads, D=128, seq_lens=None):
+    """fp32 reference on a subset of query heads (and the kv heads they read): returns out [B, S, len(q_heads), D]."""
+    x = qkv.float().view(B, S, H + 2 * Hkv, D)
+    g = H // Hkv
+    outs = []
+    mask = torch.full((S, S), float("-inf"), device=qkv.device).triu(1)
+    for h in q_heads:
+        q, k, v = x[:, :, h], x[:, :, H + h // g], x[:, :, H + Hkv + h // g]
+        sc = torch.einsum("bqd,bkd->bqk", q, k) / math.sqrt(D) + mask
+        outs.append(torch.softmax(sc, dim=-1) @ v)
+    return torch.stack(outs, dim=2)
+
+
+def check_attn_bench_shape(B=1, S=2048, H=32, Hkv=32, kv_heads=(0, 13, 31)):
+    """Attention forward AND backward at the benchmarked geometry (S=2048 H=32; S=4096 H=32/Hkv=8 for the Mistral shape): the
+    kernels run on all heads, the fp32 torch reference on the query heads of a few kv heads (full score matrices do not fit
+    otherwise).  The backward reference differentiates through those heads only, so dO is zero elsewhere."""
+    lib = L.load()
+    D, g = 128, H // Hkv
+    W = (H + 2 * Hkv) * D
+    qkv = _rand(B * S, W, seed=61)
+    q_heads = [kh * g + i for kh in kv_heads for i in range(g)]
+    dout = torch.zeros(B * S, H * D, dtype=torch.bfloat16, device=DEV)
+    dsub = _rand(B * S, len(q_heads) * D, seed=62)
+    for i, h in enumerate(q_heads):
+        dout[:, h * D:(h + 1) * D] = dsub[:, i * D:(i + 1) * D]
+    out = torch.full((B * S, H * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lse2 = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
+    delta = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
+    dqkv = torch.full((B * S, W), float("nan"), dtype=torch.bfloat16, device=DEV)
+    sc = 1.0 / math.sqrt(D)
+    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, sc, None, 0, STREAM()))
+    ok(lib.dtx_attn_bwd(P(qkv), P(out), P(dout), P(lse2), P(delta), P(dqkv), B, S, H, Hkv, sc, None, 0, None, 0, STREAM()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(dqkv.float()).all()
+    x = qkv.float().requires_grad_(True)
+    ref = _attn_ref_heads(x, B, S, H, Hkv, q_heads)
+    ref.backward(dsub.float().view(B, S, len(q_heads), D))
+    got = out.float().view(B, S, H, D)[:, :, q_heads]
+    e_o = rel_err(got, ref)
+    assert e_o < 8e-3, f"attention forward at S={S} H={H}/{Hkv}: {e_o}"
+    gr = x.grad.view(B, S, H + 2 * Hkv, D)
+    gg = dqkv.float().view(B, S, H + 2 * Hkv, D)
+    k_idx = [H + kh for kh in kv_heads]
+    v_idx = [H + Hkv + kh for kh in kv_heads]
+    errs = {"out": e_o, "dq": rel_err(gg[:, :, q_heads], gr[:, :, q_heads]), "dk": rel_err(gg[:, :, k_idx], gr[:, :, k_idx]),
+            "dv": rel_err(gg[:, :, v_idx], gr[:, :, v_idx])}
+    for n_, e in errs.items():
+        assert e < 1.5e-2, f"attention at S={S} H={H}/{Hkv}: {n_} {e}"
+    # heads that received no dO have exactly zero dq; kv heads none of whose query heads did have exactly zero dk / dv
+    others = [h for h in range(H) if h not in q_heads][:4]
+    assert float(gg[:, :, others].abs().max()) == 0.0
+    return errs
+
+
+def check_attn_bwd_rope(B=2, S=384, H=4, Hkv=2):
+    """The inverse rotary inside the dQ / dK store epilogues (what the fused training step runs): gradients with respect to the
+    PRE-rotary q, k of  attention(rope(q), rope(k), v)  against fp32 autograd."""
+    lib = L.load()
+    D = 128
+    W = (H + 2 * Hkv) * D
+    pre = _rand(B * S, W, seed=71)
+    cs = _rope_table(S)
+    cs_t = cs.permute(1, 0, 2).contiguous()  # [64][S] (cos, sin): the transposed table the backward kernels read
+    rot = _rope_ref(pre.float(), S, H + Hkv).to(torch.bfloat16)
+    dout = _rand(B * S, H * D, seed=72)
+    out = torch.empty(B * S, H * D, dtype=torch.bfloat16, device=DEV)
+    lse2 = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
+    delta = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
+    dqkv = torch.full((B * S, W), float("nan"), dtype=torch.bfloat16, device=DEV)
+    sc = 1.0 / math.sqrt(D)
+    ok(lib.dtx_attn_fwd(P(rot), P(out), P(lse2), B, S, H, Hkv, sc, None, 0, STREAM()))
+    ok(lib.dtx_attn_bwd(P(rot), P(out), P(dout), P(lse2), P(delta), P(dqkv), B, S, H, Hkv, sc, None, 0, P(cs_t), S, STREAM()))
+    torch.cuda.synchronize()
+    x = pre.float().requires_grad_(True)
+    ref, _ = _attn_ref(_rope_ref(x, S, H + Hkv), B, S, H, D, Hkv)
+    ref.backward(dout.float())
+    g = x.grad.view(B, S, H + 2 * Hkv, D)
+    got = dqkv.float().view(B, S, H + 2 * Hkv, D)
+    errs = {"dq": rel_err(got[:, :, :H], g[:, :, :H]), "dk": rel_err(got[:, :, H:H + Hkv], g[:, :, H:H + Hkv]),
+            "dv": rel_err(got[:, :, H + Hkv:], g[:, :, H + Hkv:])}
+    for n_, e in errs.items():
+        assert e < 1.5e-2, f"attention backward with fused inverse rotary: {n_} {e}"
+    return errs
+
+
+def check_attn_varlen(B=4, S=640, H=4, Hkv=2, lens=(640, 1, 129, 300)):
+    """Row lengths: rows are right-padded beyond seq_lens[b].  Outputs / gradients of the real tokens equal the reference run on
+    the truncated rows; tiles that lie entirely in the padding come back as exact zeros; nothing is NaN."""
+    lib = L.load()
+    D = 128
+    W = (H + 2 * Hkv) * D
+    qkv = _rand(B * S, W, seed=81)
+    dout = _rand(B * S, H * D, seed=82).view(B, S, H * D)
+    for b, n_ in enumerate(lens):
+        dout[b, n_:] = 0  # the loss never reaches a padded token
+    dout = dout.reshape(B * S, H * D).contiguous()
+    sl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    out = torch.full((B * S, H * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lse2 = torch.full((B, H, S), float("nan"), dtype=torch.float32, device=DEV)
+    delta = torch.full((B, H, S), float("nan"), dtype=torch.float32, device=DEV)
+    dqkv = torch.full((B * S, W), float("nan"), dtype=torch.bfloat16, device=DEV)
+    sc = 1.0 / math.sqrt(D)
+    ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, sc, P(sl), 0, STREAM()))
+    ok(lib.dtx_attn_bwd(P(qkv), P(out), P(dout), P(lse2), P(delta), P(dqkv), B, S, H, Hkv, sc, P(sl), 0, None, 0, STREAM()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(dqkv.float()).all(), "padding must stay finite"
+    x = qkv.float().requires_grad_(True)
+    ref, _ = _attn_ref(x, B, S, H, D, Hkv)
+    ref.backward(dout.float())
+    o3, r3 = out.float().view(B, S, -1), ref.view(B, S, -1)
+    g3, rg3 = dqkv.float().view(B, S, -1), x.grad.view(B, S, -1)
+    worst_o = worst_g = 0.0
+    for b, n_ in enumerate(lens):
+        worst_o = max(worst_o, rel_err(o3[b, :n_], r3[b, :n_]))
+        worst_g = max(worst_g, rel_err(g3[b, :n_], rg3[b, :n_]))
+        t0 = (n_ + 127) // 128 * 128  # first tile that holds only padding
+        assert float(o3[b, t0:].abs().max() if t0 < S else 0.0) == 0.0, f"row {b}: skipped output tiles must be zero"
+        assert float(g3[b, t0:].abs().max() if t0 < S else 0.0) == 0.0, f"row {b}: skipped gradient tiles must be zero"
+        assert float(g3[b, n_:t0].abs().max() if n_ < t0 else 0.0) == 0.0, f"row {b}: padded rows inside a live tile have zero gradient"
+    assert worst_o < 8e-3 and worst_g < 1.5e-2, (worst_o, worst_g)
+    return {"out": worst_o, "grad": worst_g}
+
+
+def check_trainer_varlen(steps=4):
+    """dtx_step with per-batch padded length + true row lengths == the oracle on the same (right-padded, -100-labelled) rows:
+    loss, grad-norm and every adapter gradient; and == the same batch padded to the static length without row lengths."""
+    ocfg, orc, tr = make_tiny_pair(S=512, B=4, steps=steps)
+    worst_l = worst_g = worst_grad = 0.0
+    rng = np.random.default_rng(7)
+    for s_ in range(steps):
+        ids, labels = O.synthetic_batch(s_, 0, 4, 512, ocfg.vocab)
+        lens = np.array([[384, 130, 7, 257], [512, 1, 128, 129], [100, 100, 100, 100], [256, 384, 64, 0]][s_ % 4], dtype=np.int32)
+        cur = max(128, int(-(-int(lens.max()) // 128) * 128))
+        for b in range(4):
+            ids[b, lens[b]:] = 0
+            labels[b, lens[b]:] = -100
+            if lens[b] > 0:
+                labels[b, :max(1, lens[b] // 3)] = -100
+        ref = orc.step([(ids[:, :cur], labels[:, :cur])])
+        loss, gn, _, stepped = tr.step(ids[:, :cur], labels[:, :cur], lens)
+        assert stepped
+        worst_l, worst_g = max(worst_l, abs(loss - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
+    # gradient tensors of one more step against the oracle's autograd gradients
+    ids, labels = O.synthetic_batch(99, 0, 4, 512, ocfg.vocab)
+    lens = np.array([300, 5, 200, 129], dtype=np.int32)
+    for b in range(4):
+        ids[b, lens[b]:] = 0
+        labels[b, lens[b]:] = -100
+    _, g_ref = orc.loss_and_grads(ids[:, :384], labels[:, :384])
+    tr.step(ids[:, :384], labels[:, :384], lens)
+    got = tr.export_adapter(grads=True)
+    for k, v in got.items():
+        r = g_ref[k.replace("base_model.model.", "")].numpy()
+        worst_grad = max(worst_grad, float(np.linalg.norm(v - r) / max(np.linalg.norm(r), 1e-12)))
+    tr.close()
+    assert worst_l < 1e-3 and worst_g < 3e-2 and worst_grad < 4e-2, (worst_l, worst_g, worst_grad)
+    return {"loss": worst_l, "gnorm": worst_g, "adapter_grads": worst_grad}
+
+
+def check_eval_rows_and_force_step():
+    """dtx_eval_loss row statistics compose to the batch loss; DTX_STEP_FORCE steps before grad_accum micro-batches are in."""
+    ocfg, mc, tc = tiny_configs(steps=4)
+    ocfg.grad_accum = 4
+    tc.grad_accum = 4
+    w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
+    tr = L.Trainer(mc, tc)
+    tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+    tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+    ids, labels = O.synthetic_batch(0, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)
+    sums, cnts = tr.eval_rows(ids, labels)
+    loss = tr.eval_loss(ids, labels)
+    assert abs(float(sums.sum()) / int(cnts.sum()) - loss) < 1e-5 * loss, (sums, cnts, loss)
+    assert cnts.tolist() == [int((labels[b, 1:] >= 0).sum()) for b in range(tc.micro_batch)]
+    _, _, _, st0 = tr.step(ids, labels)
+    _, gn, _, st1 = tr.step(ids, labels, force_step=True)
+    assert not st0 and st1, "the forced step must run after 2 of 4 micro-batches"
+    # HF divides every micro-batch loss by grad_accum whatever the number accumulated: the norm is 2/4 of one batch's
+    orc = O.OracleTrainer(O.OracleConfig(**{**ocfg.__dict__, "grad_accum": 1}), w, lora)
+    orc.fwd_count = 2
+    ref = orc.step([(ids, labels)])
+    assert abs(gn - 0.5 * ref.grad_norm) / ref.grad_norm < 2e-2, (gn, ref.grad_norm)
+    tr.close()
+    return {"gnorm_forced": gn, "oracle_full": ref.grad_norm}
+
+
+def check_missing_weight_is_refused():
+    """A checkpoint with a hole must fail loudly (DTX_ERR_STATE), never train on uninitialised memory."""
+    ocfg, mc, tc = tiny_configs(steps=2)
+    w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
+    tr = L.Trainer(mc, tc)
+    tr.load_state_dict({k: v.numpy() for k, v in w.items() if k != "model.layers.1.mlp.up_proj.weight"})
+    tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+    ids, labels = O.synthetic_batch(0, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)
+    try:
+        tr.step(ids, labels)
+        raise AssertionError("step must be refused")
+    except L.DtxError as e:
+        assert e.code == -4 and "model.layers.1.mlp.up_proj.weight" in str(e), e
+    tr.load_tensor("model.layers.1.mlp.up_proj.weight", w["model.layers.1.mlp.up_proj.weight"].numpy())
+    loss = tr.step(ids, labels)[0]
+    tr.close()
+    assert np.isfinite(loss)
+    return {"loss": loss}
+
+
+def check_layer_7b_shape(B=2, S=2048):
+    """One Llama-2-7B-shaped decoder layer (d=4096, H=32, F=11008) + lm_head (V=32000) + CE through the native trainer at the
+    benchmark's sequence length, against the fp32 oracle on the host cores: forward loss, step loss, grad-norm and every
+    adapter gradient tensor.  This is the geometry bench.py times (86-tile N sweeps, split-K choices, 2048 attention CTAs
+    per launch, the fused RoPE / SwiGLU epilogues) - only the layer count is reduced."""
+    ocfg = O.OracleConfig(vocab=32000, hidden=4096, n_layers=1, n_heads=32, ffn=11008, lora_r=16, lora_alpha=32.0, lr=1e-4, total_steps=100)
+    mc = L.ModelConfig(vocab=32000, hidden=4096, n_layers=1, n_heads=32, ffn=11008)
+    tc = L.TrainConfig(micro_batch=B, seq_len=S, total_steps=100, lora_r=16, lora_alpha=32.0, lora_dropout=0.0, lr=1e-4)
+    t0 = time.time()
+    w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
+    # B = 0 at init would leave the A gradients identically zero: give B a small random value so that every gradient is exercised
+    g = torch.Generator().manual_seed(99)
+    for k in lora:
+        if "lora_B" in k:
+            lora[k] = torch.randn(lora[k].shape, generator=g) * 0.01
+    tr = L.Trainer(mc, tc)
+    tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+    tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+    orc = O.OracleTrainer(ocfg, w, lora)
+    t_init = time.time() - t0
+    ids, labels = O.synthetic_batch(0, 0, B, S, ocfg.vocab)
+    t0 = time.time()
+    ref_loss, g_ref = orc.loss_and_grads(ids, labels)
+    t_cpu = time.time() - t0
+    e_eval = abs(tr.eval_loss(ids, labels) - ref_loss) / ref_loss
+    loss, gn, _, stepped = tr.step(ids, labels)
+    ref_norm = math.sqrt(sum(float((v.double() ** 2).sum()) for v in g_ref.values()))
+    got = tr.export_adapter(grads=True)
+    errs = {}
+    for k, v in got.items():
+        r = g_ref[k.replace("base_model.model.", "")].numpy()
+        errs[k.split("layers.0.")[1]] = float(np.linalg.norm(v - r) / max(np.linalg.norm(r), 1e-12))
+    tr.close()
+    res = {"eval_loss_rel": e_eval, "step_loss_rel": abs(loss - ref_loss) / ref_loss, "gnorm_rel": abs(gn - ref_norm) / ref_norm,
+           "adapter_grad_rel": errs, "oracle_loss": ref_loss, "native_loss": loss, "sec_init": t_init, "sec_oracle_fwd_bwd": t_cpu}
+    assert e_eval < 1e-3 and res["step_loss_rel"] < 1e-3, res
+    assert res["gnorm_rel"] < 3e-2 and max(errs.values()) < 4e-2, res
+    return res
+
+
 
 
 def tiny_configs(S=256, B=2, steps=20, L_layers=2, vocab=2048, heads=2, kv_heads=None, dropout=0.0, targets=("q_proj", "v_proj")):
@@ -658,11 +1016,18 @@ ALL = {
     "gemm_nn_bn64": lambda: check_gemm_nn(N=64, block_n=64), "gemm_tn": check_gemm_tn,
     "gemm_tn_nosplit": lambda: check_gemm_tn(split_k=1), "gemm_kext": check_gemm_kext, "gemm_ragged": check_gemm_ragged,
     "gemm_large": check_gemm_large, "gemm_single_cta": check_gemm_single_cta, "gemm_pair_vs_single": check_gemm_pair_vs_single, "rmsnorm": check_rmsnorm, "rmsnorm_small": lambda: check_rmsnorm(M=64, d=256),
-    "rope": check_rope, "swiglu": check_swiglu, "lora_dropout": check_lora_dropout, "nf4": check_nf4, "trainer_qlora": check_trainer_qlora, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
+    "rope": check_rope, "swiglu": check_swiglu, "lora_dropout": check_lora_dropout, "nf4": check_nf4, "nf4_pack": check_nf4_pack,
+    "gemm_rope_epilogue": check_gemm_rope_epilogue,
+    "gemm_rope_epilogue_7b": lambda: check_gemm_rope_epilogue(S=2048, B=2, H=32, Hkv=32, K=4096, ragged=False),
+    "gemm_swiglu_epilogues": check_gemm_swiglu_epilogues,
+    "attn_bench_shape_s2048": check_attn_bench_shape,
+    "attn_bench_shape_s4096_gqa": lambda: check_attn_bench_shape(B=1, S=4096, H=32, Hkv=8, kv_heads=(0, 5)),
+    "attn_bwd_rope": check_attn_bwd_rope, "attn_varlen": check_attn_varlen,
+    "trainer_varlen": check_trainer_varlen, "eval_rows_force_step": check_eval_rows_and_force_step,
+    "missing_weight_refused": check_missing_weight_is_refused, "layer_7b_shape": check_layer_7b_shape, "trainer_qlora": check_trainer_qlora, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
-    "attn_fwd_rescale": lambda: check_attn_fwd(B=1, S=1024, H=2, growing=True), "attn_fwd_one_tile": check_attn_fwd_one_tile,
+    "attn_fwd_rescale": lambda: check_attn_fwd(B=1, S=1024, H=2, growing=True),
     "attn_fwd_odd_tiles": lambda: {"s640": check_attn_fwd(B=1, S=640, H=2), "s128": check_attn_fwd(B=3, S=128, H=2)},
-    "attn_bwd_variants": check_attn_bwd_variants,
     "attn_bwd_single_tile": lambda: check_attn_bwd(B=3, S=128, H=2),
     "attn_bwd": check_attn_bwd, "attn_bwd_long": lambda: check_attn_bwd(B=1, S=1024, H=1),
     "attn_gqa": lambda: {"fwd": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "bwd": check_attn_bwd(B=2, S=384, H=4, Hkv=1)},

@@ -1,0 +1,31 @@
+#!/bin/bash
+# One GPU-box session: parity checks, bench lines, ncu launch list + full captures of the hot kernels.
+# usage: bash tools/gpu_round.sh <tag> [steps...]   (steps: diag bench varlen qlora launches ncu_attn ncu_gemm pytest)
+set -u
+TAG=${1:-run}; shift || true
+STEPS=${*:-"diag bench varlen qlora launches ncu_attn ncu_gemm"}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
+for s in $STEPS; do
+  case $s in
+    diag) timeout 1500 python tools/gpu_diag.py > $OUT/diag.log 2>&1; cp gpurun_out/diag.json $OUT/diag.json 2>/dev/null;;
+    pytest) timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1;;
+    smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1;;
+    bench) timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err;;
+    benchcpu) timeout 900 python bench.py --steps 8 --warmup 3 > $OUT/bench_cpu.json 2> $OUT/bench_cpu.err;;
+    refarm) timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_reference.json 2> $OUT/bench_reference.err;;
+    varlen) timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen.json 2> $OUT/bench_varlen.err;;
+    qlora) timeout 600 python bench.py --config mistral7b_qlora --steps 5 --warmup 3 > $OUT/bench_qlora.json 2> $OUT/bench_qlora.err;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches.csv \
+                python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1;;
+    ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_ --launch-skip 12 --launch-count 3 -o $OUT/attn -f \
+                python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_attn.log 2>&1;;
+    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel --launch-skip 40 --launch-count 12 -o $OUT/gemm -f \
+                python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_gemm.log 2>&1;;
+    *) echo "unknown step $s";;
+  esac
+  echo "$s done rc=$? $(date +%T)" >> $OUT/steps.log
+done
+tail -3 $OUT/diag.log 2>/dev/null
+cat $OUT/bench.json 2>/dev/null | head -c 1500
