@@ -107,3 +107,55 @@ def test_total_optimizer_steps_follow_hf_trainer_arithmetic():
     assert total_optimizer_steps(n_examples=672, world=2, batch=8, grad_accum=2, epochs=3, max_steps=-1) == 63
     assert total_optimizer_steps(n_examples=5, world=1, batch=8, grad_accum=4, epochs=2, max_steps=-1) == 2
     assert total_optimizer_steps(n_examples=672, world=1, batch=8, grad_accum=1, epochs=1, max_steps=7) == 7
+
+
+def test_eval_mean_follows_hf_batching():
+    """SFTTrainer.evaluate (cmd/tuning/trainer.py:324-327 on HF Trainer.evaluation_loop): each eval batch's token-mean loss is
+    repeated once per sample, gathered and averaged.  The native step returns per-row (loss sum, valid tokens); the host forms
+    the per_device_eval_batch_size batches from them."""
+    import numpy as np
+    from datatunerx_b200.tuning import train as T
+
+    rows = [(3.0, 3), (8.0, 4), (1.0, 1), (0.0, 0), (10.0, 5)]  # (sum of token losses, valid tokens) per example
+
+    class FakeTrainer:
+        def __init__(self):
+            self.i = 0
+
+        def eval_rows(self, ids, lab, lens):
+            k = int((lens > 0).sum())
+            part = rows[self.i:self.i + k]
+            self.i += k
+            pad = ids.shape[0] - k
+            return (np.array([r[0] for r in part] + [0.0] * pad, dtype=np.float32), np.array([r[1] for r in part] + [0] * pad, dtype=np.int32))
+
+        def allreduce_host(self, v):
+            return np.asarray(v, dtype=np.float64)
+
+    ds = [([1] * 5, [-100, 1, 1, 1, 1])] * len(rows)
+    got = T.evaluate(FakeTrainer(), ds, rank=0, world=1, B=4, seq_len=128, pad_id=0, eval_batch=2, seed=0)
+    # HF with eval batch 2: batches (r0,r1) (r2,r3) (r4): token-mean 11/7, 1/1, 10/5, weighted by batch size 2, 2, 1
+    want = (2 * (11 / 7) + 2 * 1.0 + 1 * 2.0) / 5
+    assert abs(got - want) < 1e-12, (got, want)
+
+
+def test_child_rank_failure_takes_the_job_down(tmp_path):
+    """A rank that dies must not leave its peers blocked in NCCL: the watchdog thread exits the whole job non-zero."""
+    import subprocess
+    import sys
+    code = (
+        "import subprocess, sys, threading, time\n"
+        "from datatunerx_b200.tuning import train as T\n"
+        "kids = [subprocess.Popen([sys.executable, '-c', 'import time; time.sleep(60)']),\n"
+        "        subprocess.Popen([sys.executable, '-c', 'import sys, time; time.sleep(1); sys.exit(7)'])]\n"
+        "threading.Thread(target=T._watch_children, args=(kids, threading.Event()), daemon=True).start()\n"
+        "time.sleep(45)\n"   # stands for rank 0 blocked inside ncclAllReduce
+        "sys.exit(0)\n")
+    import os
+    import time
+    t0 = time.time()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 7, (p.returncode, p.stderr[-500:])
+    assert time.time() - t0 < 30, "the watchdog must fire within seconds"
+    assert "aborting the job" in p.stderr
