@@ -69,9 +69,11 @@ __device__ __forceinline__ float block_sum_128(float v, float* sh4) {
 template <int NCH>
 __global__ void __launch_bounds__(RMS_THREADS) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                                   bf16* __restrict__ y, float* __restrict__ rstd, int d,
-                                                                  float eps) {
+                                                                  float eps, const int32_t* __restrict__ row_map) {
   __shared__ float sh[4];
   const int row = blockIdx.x;
+  const int out_row = row_map ? row_map[row] : row;
+  if (out_row < 0) return;  // this token is not needed downstream (block-uniform)
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d);
   const int nvec = d >> 3;
   uint4 buf[NCH];
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(RMS_THREADS) rmsnorm_fwd_kernel(const bf16* __
   const float r = rsqrtf(ss / static_cast<float>(d) + eps);
   if (threadIdx.x == 0 && rstd) rstd[row] = r;
   const uint4* wr = reinterpret_cast<const uint4*>(w);
-  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * d);
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(out_row) * d);
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int v = i * RMS_THREADS + threadIdx.x;
@@ -114,11 +116,19 @@ __global__ void __launch_bounds__(RMS_THREADS) rmsnorm_fwd_kernel(const bf16* __
 template <int NCH>
 __global__ void __launch_bounds__(RMS_THREADS) rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                                   const bf16* __restrict__ w, const float* __restrict__ rstd,
-                                                                  const bf16* __restrict__ dres, bf16* __restrict__ dx, int d) {
+                                                                  const bf16* __restrict__ dres, bf16* __restrict__ dx, int d,
+                                                                  const int32_t* __restrict__ row_map) {
   __shared__ float sh[4];
   const int row = blockIdx.x;
   const size_t off = static_cast<size_t>(row) * d;
-  const uint4* dyr = reinterpret_cast<const uint4*>(dy + off);
+  const int src_row = row_map ? row_map[row] : row;
+  if (src_row < 0) {  // no gradient arrives for this token: dx = dres (or 0)
+    const int nv = d >> 3;
+    for (int v = threadIdx.x; v < nv; v += RMS_THREADS)
+      reinterpret_cast<uint4*>(dx + off)[v] = dres ? ldg_stream(reinterpret_cast<const uint4*>(dres + off) + v) : make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(src_row) * d);
   const uint4* xr = reinterpret_cast<const uint4*>(x + off);
   const uint4* wr = reinterpret_cast<const uint4*>(w);
   const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + off) : nullptr;
@@ -265,24 +275,41 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
 // K9: shifted-label cross entropy (HF ForCausalLMLoss: logits[..., :-1] vs labels[..., 1:],
 // ignore_index -100, mean over valid tokens).
 // ------------------------------------------------------------------------------------------
-__global__ void shift_labels_kernel(const int32_t* __restrict__ labels, int32_t* __restrict__ shifted,
-                                    int32_t* __restrict__ n_valid, int B, int S) {
-  __shared__ int sh[32];
-  int cnt = 0;
+__global__ void __launch_bounds__(1024) shift_labels_kernel(const int32_t* __restrict__ labels, int32_t* __restrict__ shifted,
+                                                            int32_t* __restrict__ n_valid, int B, int S,
+                                                            int32_t* __restrict__ row_map, int32_t* __restrict__ valid_idx) {
+  // one block; thread t owns the contiguous token range [t*c, (t+1)*c): counts, block-wide exclusive scan, ordered positions
+  __shared__ int sh[1024];
   const int total = B * S;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  const int c = (total + blockDim.x - 1) / blockDim.x;
+  const int lo = min(total, static_cast<int>(threadIdx.x) * c), hi = min(total, lo + c);
+  int cnt = 0;
+  for (int i = lo; i < hi; ++i) {
     const int t = i % S;
-    int v = (t == S - 1) ? -100 : labels[i + 1];
+    const int v = (t == S - 1) ? -100 : labels[i + 1];
     shifted[i] = v;
     cnt += (v >= 0) ? 1 : 0;
   }
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
+  sh[threadIdx.x] = cnt;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
-    *n_valid = t;
+  for (int o = 1; o < static_cast<int>(blockDim.x); o <<= 1) {  // Hillis-Steele inclusive scan
+    const int add = (static_cast<int>(threadIdx.x) >= o) ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += add;
+    __syncthreads();
+  }
+  if (threadIdx.x == blockDim.x - 1) *n_valid = sh[threadIdx.x];
+  if (row_map) {
+    int pos = sh[threadIdx.x] - cnt;
+    for (int i = lo; i < hi; ++i) {
+      if (shifted[i] >= 0) {
+        row_map[i] = pos;
+        valid_idx[pos] = i;
+        ++pos;
+      } else {
+        row_map[i] = -1;
+      }
+    }
   }
 }
 
@@ -290,15 +317,17 @@ __global__ void shift_labels_kernel(const int32_t* __restrict__ labels, int32_t*
 __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logits, long long ldl,
                                                  const int32_t* __restrict__ labels, const int32_t* __restrict__ n_valid,
                                                  float* __restrict__ row_loss, bf16* __restrict__ dlogits, long long ldd,
-                                                 int V) {
+                                                 int V, const int32_t* __restrict__ valid_idx) {
   __shared__ float shm[8], shs[8];
   __shared__ float s_max, s_sum;
-  const int row = blockIdx.x;
-  const int label = labels[row];
+  const int row = blockIdx.x;  // row of logits / dlogits
+  if (valid_idx && row >= *n_valid) return;
+  const int tok = valid_idx ? valid_idx[row] : row;  // token whose label / row_loss this is
+  const int label = labels[tok];
   bf16* drow = dlogits ? dlogits + static_cast<long long>(row) * ldd : nullptr;
   const int nv4 = V >> 2;
   if (label < 0 || label >= V) {  // ignored token: zero gradient row, zero loss
-    if (threadIdx.x == 0) row_loss[row] = 0.f;
+    if (threadIdx.x == 0) row_loss[tok] = 0.f;
     if (drow) {
       uint2 z = make_uint2(0u, 0u);
       for (int i = threadIdx.x; i < nv4; i += blockDim.x) reinterpret_cast<uint2*>(drow)[i] = z;
@@ -339,7 +368,7 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logit
     }
     s_max = M0;
     s_sum = S0;
-    row_loss[row] = (M0 + logf(S0)) - lrow[label];
+    row_loss[tok] = (M0 + logf(S0)) - lrow[label];
   }
   __syncthreads();
   if (!drow) return;
@@ -698,24 +727,25 @@ cudaError_t embedding_fwd(const int32_t* ids, const bf16* table, bf16* out, int 
   return cudaGetLastError();
 }
 
-cudaError_t rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int M, int d, float eps, cudaStream_t s) {
+cudaError_t rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int M, int d, float eps, cudaStream_t s,
+                        const int32_t* row_map) {
   if (d % 8 || d > 8192) return cudaErrorInvalidValue;
   const int nch = (d / 8 + RMS_THREADS - 1) / RMS_THREADS;
-  if (nch <= 1) rmsnorm_fwd_kernel<1><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps);
-  else if (nch <= 2) rmsnorm_fwd_kernel<2><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps);
-  else if (nch <= 4) rmsnorm_fwd_kernel<4><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps);
-  else rmsnorm_fwd_kernel<8><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps);
+  if (nch <= 1) rmsnorm_fwd_kernel<1><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps, row_map);
+  else if (nch <= 2) rmsnorm_fwd_kernel<2><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps, row_map);
+  else if (nch <= 4) rmsnorm_fwd_kernel<4><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps, row_map);
+  else rmsnorm_fwd_kernel<8><<<M, RMS_THREADS, 0, s>>>(x, w, y, rstd, d, eps, row_map);
   return cudaGetLastError();
 }
 
 cudaError_t rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx, int M,
-                        int d, cudaStream_t s) {
+                        int d, cudaStream_t s, const int32_t* row_map) {
   if (d % 8 || d > 8192) return cudaErrorInvalidValue;
   const int nch = (d / 8 + RMS_THREADS - 1) / RMS_THREADS;
-  if (nch <= 1) rmsnorm_bwd_kernel<1><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d);
-  else if (nch <= 2) rmsnorm_bwd_kernel<2><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d);
-  else if (nch <= 4) rmsnorm_bwd_kernel<4><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d);
-  else rmsnorm_bwd_kernel<8><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d);
+  if (nch <= 1) rmsnorm_bwd_kernel<1><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d, row_map);
+  else if (nch <= 2) rmsnorm_bwd_kernel<2><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d, row_map);
+  else if (nch <= 4) rmsnorm_bwd_kernel<4><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d, row_map);
+  else rmsnorm_bwd_kernel<8><<<M, RMS_THREADS, 0, s>>>(dy, x, w, rstd, dres, dx, d, row_map);
   return cudaGetLastError();
 }
 
@@ -738,15 +768,18 @@ cudaError_t swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int M, int F
   return cudaGetLastError();
 }
 
-cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_valid, int B, int S, cudaStream_t s) {
-  shift_labels_kernel<<<1, 1024, 0, s>>>(labels, shifted, n_valid, B, S);
+cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_valid, int B, int S, cudaStream_t s,
+                         int32_t* row_map, int32_t* valid_idx) {
+  if ((row_map == nullptr) != (valid_idx == nullptr)) return cudaErrorInvalidValue;
+  shift_labels_kernel<<<1, 1024, 0, s>>>(labels, shifted, n_valid, B, S, row_map, valid_idx);
   return cudaGetLastError();
 }
 
 cudaError_t cross_entropy_fwd_bwd(const float* logits, int64_t ldl, const int32_t* labels, const int32_t* n_valid,
-                                  float* row_loss, bf16* dlogits, int64_t ldd, int M, int V, cudaStream_t s) {
+                                  float* row_loss, bf16* dlogits, int64_t ldd, int M, int V, cudaStream_t s,
+                                  const int32_t* valid_idx) {
   if ((ldl & 3) || (ldd & 3)) return cudaErrorInvalidValue;
-  ce_kernel<<<M, 256, 0, s>>>(logits, ldl, labels, n_valid, row_loss, dlogits, ldd, V);
+  ce_kernel<<<M, 256, 0, s>>>(logits, ldl, labels, n_valid, row_loss, dlogits, ldd, V, valid_idx);
   return cudaGetLastError();
 }
 

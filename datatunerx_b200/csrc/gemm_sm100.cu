@@ -41,6 +41,7 @@ struct GemmKParams {
   long long ld_aux;
   const float2* rope_cs;
   int rope_S, rope_cols, rope_inverse;
+  const int32_t* m_eff;  // pair kernel: device-side row count; 256-row tiles that start at or beyond it are skipped
 };
 
 template <int BN>
@@ -342,6 +343,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int kb_total = p.kb1 + p.kb2;
   const int total_tiles = p.m_tiles * p.n_tiles;  // m_tiles counts 256-row tiles here
+  // rows that exist on the device only (e.g. the number of unmasked tokens of this batch): every role skips the same tiles
+  const int m_eff = p.m_eff ? min(p.M, __ldg(p.m_eff)) : p.M;
 
   auto decode = [&](int tile, int& m_blk, int& n_blk) {
     const int per_group = p.group_m * p.n_tiles;
@@ -361,6 +364,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         int m_blk, n_blk;
         decode(tile, m_blk, n_blk);
+        if (m_blk * 256 >= m_eff) continue;
         const int m0 = m_blk * 256 + 128 * static_cast<int>(rank);
         const int n0 = n_blk * 256 + 128 * static_cast<int>(rank);
         for (int kb = 0; kb < kb_total; ++kb) {
@@ -395,6 +399,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
+        {
+          int m_blk, n_blk;
+          decode(tile, m_blk, n_blk);
+          if (m_blk * 256 >= m_eff) continue;
+        }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -424,6 +433,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int tile = pair; tile < total_tiles; tile += npairs) {
       int m_blk, n_blk;
       decode(tile, m_blk, n_blk);
+      if (m_blk * 256 >= m_eff) continue;
       const int m0 = m_blk * 256 + 128 * static_cast<int>(rank);
       const int n0 = n_blk * 256;
       const int row = m0 + q * 32 + lane;
@@ -717,6 +727,7 @@ cudaError_t launch(const GemmArgs& a, cudaStream_t s) {
   p.ld_aux = 0;
   p.rope_cs = nullptr;
   p.rope_S = p.rope_cols = p.rope_inverse = 0;
+  p.m_eff = nullptr;  // the single-CTA kernel computes every row (rows beyond the device-side count are dead, not wrong)
   int total = p.m_tiles * p.n_tiles * p.split_k;
   int grid = total < gemm_num_sms() ? total : gemm_num_sms();
   if (grid <= 0) return cudaSuccess;
@@ -780,6 +791,7 @@ cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
   p.rope_S = a.rope_S;
   p.rope_cols = a.rope_cols;
   p.rope_inverse = a.rope_inverse;
+  p.m_eff = a.m_eff;
   const int total = p.m_tiles * p.n_tiles;
   int pairs = gemm_num_sms() / 2;
   if (pairs > total) pairs = total;

@@ -36,6 +36,10 @@ struct GemmArgs {
   void* aux = nullptr; int64_t ld_aux = 0;             // EPI_SWIGLU_FWD: act out; EPI_SWIGLU_BWD: gu in (ld = 2F)
   const float2* rope_cs = nullptr; int rope_S = 0, rope_cols = 0, rope_inverse = 0;  // EPI_ROPE
   int M = 0, N = 0, K = 0;
+  // optional device-side row count (<= M): the CTA-pair kernel skips 256-row tiles that start at or beyond it (rows up to the
+  // end of the last live tile are still computed).  Lets the lm_head GEMMs run over the unmasked tokens only without a
+  // device-to-host round trip for their number.
+  const int32_t* m_eff = nullptr;
   int epilogue = EPI_BF16;
   int split_k = 1;  // >1 requires EPI_F32; C is [split_k][M][ldc] partial sums
   int block_n = 0;  // 0 = auto (256 for wide N, 64 for N <= 64)
@@ -81,11 +85,14 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s);
 // HBM-bound kernels
 // ---------------------------------------------------------------------------------------------
 cudaError_t embedding_fwd(const int32_t* ids, const bf16* table, bf16* out, int M, int d, int vocab, cudaStream_t s);
-// y = w * x * rsqrt(mean(x^2) + eps);  rstd saved for backward
-cudaError_t rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int M, int d, float eps, cudaStream_t s);
+// y = w * x * rsqrt(mean(x^2) + eps);  rstd saved for backward.
+// row_map (optional, [M]): row m of x is written to row row_map[m] of y; rows with row_map[m] < 0 are skipped (their rstd too).
+cudaError_t rmsnorm_fwd(const bf16* x, const bf16* w, bf16* y, float* rstd, int M, int d, float eps, cudaStream_t s,
+                        const int32_t* row_map = nullptr);
 // dx = rstd * (w*dy) - x * rstd^3 * mean(w*dy*x)  (+ dres if not null)
+// row_map (optional, [M]): the gradient of row m sits in row row_map[m] of dy; rows with row_map[m] < 0 get dx = dres (or 0).
 cudaError_t rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx,
-                        int M, int d, cudaStream_t s);
+                        int M, int d, cudaStream_t s, const int32_t* row_map = nullptr);
 // half-split rotary embedding applied in place to the first n_rot_heads heads (q heads then k heads) of every row of
 // packed qkv (row stride W elements). inverse=1 applies R^T (backward).  cs = [S][D/2] float2(cos, sin) table
 cudaError_t rope_qk_inplace_table(bf16* qkv, const float2* cs, int B, int S, int n_rot_heads, int W, int D, int inverse,
@@ -95,11 +102,17 @@ cudaError_t rope_qk_inplace_table(bf16* qkv, const float2* cs, int B, int S, int
 cudaError_t swiglu_fwd(const bf16* gu, bf16* act, int M, int F, int interleaved, cudaStream_t s);
 // dgu[M,2F] from dact[M,F] and saved gu
 cudaError_t swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int M, int F, int interleaved, cudaStream_t s);
-// labels_shift[b,t] = labels[b,t+1] (last = -100); n_valid counted into *n_valid (int32)
-cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_valid, int B, int S, cudaStream_t s);
-// softmax cross-entropy over fp32 logits [M,V]; row_loss[M] (0 for ignored rows); dlogits bf16 = (p - onehot)/n_valid
+// labels_shift[b,t] = labels[b,t+1] (last = -100); n_valid counted into *n_valid (int32).
+// With row_map / valid_idx (both or neither): row_map[m] = position of row m among the rows with a label (in order), or -1;
+// valid_idx[k] = the k-th such row.
+cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_valid, int B, int S, cudaStream_t s,
+                         int32_t* row_map = nullptr, int32_t* valid_idx = nullptr);
+// softmax cross-entropy over fp32 logits [M,V]; row_loss[M] (0 for ignored rows); dlogits bf16 = (p - onehot)/n_valid.
+// valid_idx (optional): COMPACT mode - logits / dlogits row k belongs to token valid_idx[k] (k < *n_valid; other blocks
+// return), labels and row_loss stay indexed by token; row_loss of unlabelled tokens must have been zeroed by the caller.
 cudaError_t cross_entropy_fwd_bwd(const float* logits, int64_t ldl, const int32_t* labels, const int32_t* n_valid,
-                                  float* row_loss, bf16* dlogits, int64_t ldd, int M, int V, cudaStream_t s);
+                                  float* row_loss, bf16* dlogits, int64_t ldd, int M, int V, cudaStream_t s,
+                                  const int32_t* valid_idx = nullptr);
 // loss = sum(row_loss)/n_valid, fixed summation order
 cudaError_t loss_reduce(const float* row_loss, const int32_t* n_valid, float* loss, int M, cudaStream_t s);
 // out[i] = sum_s partial[s][i]  (fixed order)

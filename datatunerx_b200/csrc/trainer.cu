@@ -184,6 +184,7 @@ struct dtx_trainer {
   float *logits = nullptr, *rstdf = nullptr, *row_loss = nullptr, *delta = nullptr, *part_b = nullptr, *part_a = nullptr;
   float *d_loss = nullptr, *d_sumsq = nullptr, *d_gnorm = nullptr, *d_scratch = nullptr;
   int32_t *d_ids = nullptr, *d_labels = nullptr, *d_shift = nullptr, *d_nvalid = nullptr, *d_seq_lens = nullptr;
+  int32_t *d_row_map = nullptr, *d_valid_idx = nullptr;  // token -> position among the labelled tokens (-1: none) and back
   float* d_row_sum = nullptr;     // [micro_batch] per-row summed token loss (evaluation)
   int32_t* d_row_valid = nullptr; // [micro_batch] per-row valid-token count
   double* d_host_red = nullptr;   // staging for dtx_allreduce_host
@@ -344,6 +345,7 @@ int create_buffers(dtx_trainer* t) {
   if (t->dropout) ok = ok && t->alloc(&t->glora, M * KA);
   ok = ok && t->alloc(&t->d_loss, 4) && t->alloc(&t->d_sumsq, 4) && t->alloc(&t->d_gnorm, 4) && t->alloc(&t->d_scratch, 1024);
   ok = ok && t->alloc(&t->d_ids, M) && t->alloc(&t->d_labels, M) && t->alloc(&t->d_shift, M) && t->alloc(&t->d_nvalid, 4);
+  ok = ok && t->alloc(&t->d_row_map, M) && t->alloc(&t->d_valid_idx, M);
   ok = ok && t->alloc(&t->d_seq_lens, static_cast<size_t>(tc.micro_batch)) && t->alloc(&t->d_row_sum, static_cast<size_t>(tc.micro_batch)) &&
        t->alloc(&t->d_row_valid, static_cast<size_t>(tc.micro_batch)) && t->alloc(&t->d_host_red, 64);
   ok = ok && t->alloc(&t->rope_cs, static_cast<size_t>(tc.seq_len) * (mc.head_dim / 2));
@@ -497,25 +499,31 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       CK(gemm_bf16(g, s), 1);
     }
   }
-  CK(rmsnorm_fwd(t->xs[L], t->normf, t->h2, t->rstdf, M, d, mc.rms_eps, s), 1);
+  // lm_head, CE and their backward only over the tokens that carry a label (shifted label >= 0): prompt tokens and padding
+  // (27 % of the synthetic batch, far more on real instruction data) have zero loss and zero gradient.  The labelled rows
+  // are compacted by the final norm (row map from an ordered scan inside shift_labels), the two lm_head GEMMs take the row
+  // count from device memory and skip the dead 256-row tiles, the norm backward scatters the gradient back.
+  CK(shift_labels(t->d_labels, t->d_shift, t->d_nvalid, B, S, s, t->d_row_map, t->d_valid_idx), 1);
+  CK(rmsnorm_fwd(t->xs[L], t->normf, t->h2, t->rstdf, M, d, mc.rms_eps, s, t->d_row_map), 1);
   {  // fp32 logits (the reference patches lm_head to return fp32: cmd/tuning/train.py:256-264)
     GemmArgs g;
     g.A = t->h2; g.lda = d; g.B = t->lm_head; g.ldb = d; g.C = t->logits; g.ldc = V;
-    g.M = M; g.N = V; g.K = d; g.epilogue = EPI_F32;
+    g.M = M; g.N = V; g.K = d; g.epilogue = EPI_F32; g.m_eff = t->d_nvalid;
     CK(gemm_bf16(g, s), 1);
   }
-  CK(shift_labels(t->d_labels, t->d_shift, t->d_nvalid, B, S, s), 1);
-  CK(cross_entropy_fwd_bwd(t->logits, V, t->d_shift, t->d_nvalid, t->row_loss, backward ? t->dlogits : nullptr, V, M, V, s), 1);
+  CKM(cudaMemsetAsync(t->row_loss, 0, static_cast<size_t>(M) * sizeof(float), s));
+  CK(cross_entropy_fwd_bwd(t->logits, V, t->d_shift, t->d_nvalid, t->row_loss, backward ? t->dlogits : nullptr, V, M, V, s,
+                           t->d_valid_idx), 1);
   CK(loss_reduce(t->row_loss, t->d_nvalid, t->d_loss, M, s), 1);
   if (!backward) return DTX_OK;
 
-  {  // d h_f = dlogits * W_lm
+  {  // d h_f = dlogits * W_lm  (compact rows)
     GemmArgs g;
     g.A = t->dlogits; g.lda = V; g.B = t->lm_head; g.ldb = d; g.b_mn_major = 1; g.C = t->dh; g.ldc = d;
-    g.M = M; g.N = d; g.K = V; g.epilogue = EPI_BF16;
+    g.M = M; g.N = d; g.K = V; g.epilogue = EPI_BF16; g.m_eff = t->d_nvalid;
     CK(gemm_bf16(g, s), 1);
   }
-  CK(rmsnorm_bwd(t->dh, t->xs[L], t->normf, t->rstdf, nullptr, t->dx_a, M, d, s), 1);
+  CK(rmsnorm_bwd(t->dh, t->xs[L], t->normf, t->rstdf, nullptr, t->dx_a, M, d, s, t->d_row_map), 1);
   bf16* cur = t->dx_a;
   bf16* other = t->dx_b;
   const int accumulate = t->micro_idx > 0 ? 1 : 0;
