@@ -51,6 +51,18 @@ namespace {
 #define ISSUER_WAIT(bar, parity) mbar_wait_backoff(bar, parity)
 #endif
 
+// clock64() phase instrumentation (make EXTRA_NVFLAGS=-DDTX_ATTN_TIMING, tools/attn_timing.py): compiled out by default
+#ifdef DTX_ATTN_TIMING
+#define TM_DECL(...) long long __VA_ARGS__
+#define TM_SET(v) v = clock64()
+#define TM_ACC(acc, since) acc += clock64() - (since)
+#define TM_BLOCK(b) ((b) == 3 || (b) == (int)gridDim.x / 2 || (b) == (int)gridDim.x - 40)
+#else
+#define TM_DECL(...)
+#define TM_SET(v)
+#define TM_ACC(acc, since)
+#endif
+
 constexpr int HD = 128;      // head dim
 constexpr int DKV_THREADS = 320;  // backward kernels: 8 compute warps + MMA issuer warp (8) + TMA loader warp (9)
 constexpr float LOG2E = 1.4426950408889634f;
@@ -224,9 +236,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 0, 1);
     const uint32_t loQ = umma_desc_lo(smem_u32(smem + FW2_SQ), 16), loK = umma_desc_lo(smem_u32(smem + FW2_SK), 16),
                    loVm = umma_desc_lo(smem_u32(smem + FW2_SV), 8192);
+    TM_DECL(ti_kv = 0, ti_s = 0, ti_p = 0, ti_pv = 0, ti_0, ti_a, ti_b);
+    TM_SET(ti_0);
     auto issue_s = [&](const int t, const int slot, const int buf, const uint32_t parity) {  // S_t = Q_t K^T into buffer buf
+      TM_SET(ti_a);
       ISSUER_WAIT(&bar_kv[slot], parity);
       tc_fence_after();
+      TM_ACC(ti_kv, ti_a);
+      TM_SET(ti_b);
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < 8; ++k16)
@@ -234,8 +251,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     umma_desc_pack(loK + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
         umma_commit(&bar_s[t * 2 + buf]);
       }
+      TM_ACC(ti_s, ti_b);
     };
     ISSUER_WAIT(bar_q, 0);
+#ifdef DTX_ATTN_TIMING
+    const long long ti_q = clock64() - ti_0;
+#endif
     issue_s(0, 0, 0, 0);
     if (n1 > 0) issue_s(1, 0, 0, 0);
     if (n0 > 1) issue_s(0, 1, 1, 0);
@@ -249,8 +270,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (j < nt(t)) {
+              TM_SET(ti_a);
               ISSUER_WAIT(&bar_p[t * 2 + (u & 1)], (j >> 1) & 1);  // P_t(j) sits bf16-packed in the first 32 columns of score buffer j&1
               tc_fence_after();
+              TM_ACC(ti_p, ti_a);
+              TM_SET(ti_b);
               if (leader) {
                 const uint32_t acc0 = j > 0 ? 1u : 0u;
 #pragma unroll
@@ -260,6 +284,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 umma_commit(&bar_o[t]);
                 if (j == nt(t) - 1) umma_commit(&bar_fin[t]);
               }
+              TM_ACC(ti_pv, ti_b);
               if (j + 2 < nt(t)) issue_s(t, (u + 2) & 3, u & 1, (u + 2 >= FW2_NS) ? (rp ^ 1u) : rp);
             }
           }
@@ -267,6 +292,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     }
+#ifdef DTX_ATTN_TIMING
+    if (leader && TM_BLOCK((int)blockIdx.x))
+      printf("[fwd2 issuer] block %d n %d total %lld wait_q %lld | per block-step: wait_p %lld wait_kv %lld issue_s %lld issue_pv %lld\n", (int)blockIdx.x,
+             n, clock64() - ti_0, ti_q, ti_p / n, ti_kv / n, ti_s / n, ti_pv / n);
+#endif
   } else {
     // ------------------------------------------ softmax warps ------------------------------------------
     const int t = warp >> 2, w = warp & 3;
@@ -278,11 +308,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t T_O = 128;
     uint64_t *my_s = bar_s + t * 2, *my_o = bar_o + t, *my_p = bar_p + t * 2;
     float m_ref = -INFINITY, l_run = 0.f;
+    TM_DECL(tc_w = 0, tc_l = 0, tc_m = 0, tc_s = 0, tc_0, tc_a, tc_b, tc_c, tc_d);
+    TM_SET(tc_0);
 
     for (int j = 0; j < n_mine; ++j) {
       const int kv0 = j * 64;
+      TM_SET(tc_a);
       mbar_wait(&my_s[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      TM_SET(tc_b);
       uint32_t sv[64];
       {
         uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
@@ -291,6 +325,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld32(t_lane + (j & 1) * 64 + 32, hi);
         tmem_ld_wait();
       }
+      TM_SET(tc_c);
       if (kv0 + 63 > q0) {  // diagonal blocks: causal mask
 #pragma unroll
         for (int c = 0; c < 64; ++c)
@@ -338,14 +373,24 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         pk[c >> 1] = pack_bf16x2(pr.x, pr.y);
       }
       l_run += rs.x + rs.y;
+      TM_SET(tc_d);
       tmem_st32(t_lane + (j & 1) * 64, pk);  // A operand of the P V MMA, read straight from tensor memory
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&my_p[j & 1]);
+#ifdef DTX_ATTN_TIMING
+      tc_w += tc_b - tc_a; tc_l += tc_c - tc_b; tc_m += tc_d - tc_c; tc_s += clock64() - tc_d;
+#endif
     }
+#ifdef DTX_ATTN_TIMING
+    const long long tc_loop = clock64() - tc_0;
+#endif
     if (n_mine > 0) {
       mbar_wait(&bar_fin[t], 0);
       tc_fence_after();
+#ifdef DTX_ATTN_TIMING
+      const long long tc_fin = clock64() - tc_0 - tc_loop;
+#endif
       const float inv_l = 1.f / l_run;
       // output tile -> bf16 -> 128B-swizzled staging tile (this tile's Q buffer: every S MMA has completed) -> TMA store
       uint8_t* stage = smem + FW2_SQ + t * 32768;
@@ -372,6 +417,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_store_wait_read0();
       }
       if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = m_ref + log2f(l_run);
+#ifdef DTX_ATTN_TIMING
+      if (r == 0 && TM_BLOCK((int)blockIdx.x))
+        printf("[fwd2 softmax] block %d tile %d n %d loop %lld (incl. first wait) wait_fin %lld epilogue %lld | per block: wait_s %lld ld %lld math %lld st+arrive %lld\n",
+               (int)blockIdx.x, t, n_mine, tc_loop, tc_fin, clock64() - tc_0 - tc_loop - tc_fin, tc_w / n_mine, tc_l / n_mine, tc_m / n_mine, tc_s / n_mine);
+#endif
     } else if (q0 < p.S) {  // this tile holds only padding: zeros (see zero_tile_128)
       zero_tile_128(p.out, static_cast<long long>(p.H) * HD, row_base + q0, h * HD, r, 128);
       if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = 0.f;
@@ -544,7 +594,7 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
 #ifdef DTX_ATTN_TIMING
-    if (leader && (blockIdx.x == 3 || blockIdx.x == 1500))
+    if (leader && TM_BLOCK((int)blockIdx.x))
       printf("[dq1 issuer] block %d n %d total %lld wait_qt %lld per block: wait_p %lld wait_kv %lld issue_s %lld\n", (int)blockIdx.x, n,
              clock64() - ti_t0, ti_qt, ti_p / n, ti_kv / n, ti_mma / n);
 #endif
@@ -645,7 +695,7 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #endif
     }
 #ifdef DTX_ATTN_TIMING
-    if ((tid == 0 || tid == 128) && (blockIdx.x == 3 || blockIdx.x == 1500))
+    if ((tid == 0 || tid == 128) && TM_BLOCK((int)blockIdx.x))
       printf("[dq1 compute] block %d tid %d n %d loop %lld per block: wait_s %lld ld %lld math %lld st+arrive %lld\n", (int)blockIdx.x, tid, n,
              clock64() - tc_t0, tc_wait / n, tc_ld / n, tc_math / n, tc_st / n);
 #endif
@@ -803,9 +853,14 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     const uint32_t loK = umma_desc_lo(smem_u32(smem + DKV_SK), 16), loV = umma_desc_lo(smem_u32(smem + DKV_SV), 16),
                    loQ = umma_desc_lo(smem_u32(smem + DKV_SQ), 16), loDO = umma_desc_lo(smem_u32(smem + DKV_SDO), 16),
                    loQm = umma_desc_lo(smem_u32(smem + DKV_SQ), 8192), loDOm = umma_desc_lo(smem_u32(smem + DKV_SDO), 8192);
+    TM_DECL(ti_q = 0, ti_s = 0, ti_p = 0, ti_acc = 0, ti_0, ti_a, ti_b);
+    TM_SET(ti_0);
     auto issue_s = [&](const int slot, const int buf, const uint32_t parity) {  // S^T = K Q^T, dP^T = V dO^T into buffer buf
+      TM_SET(ti_a);
       ISSUER_WAIT(&bar_q[slot], parity);
       tc_fence_after();
+      TM_ACC(ti_q, ti_a);
+      TM_SET(ti_b);
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < 8; ++k16)
@@ -817,8 +872,12 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
                     umma_desc_pack(loDO + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
         umma_commit(&bar_s[buf]);
       }
+      TM_ACC(ti_s, ti_b);
     };
     ISSUER_WAIT(bar_kv, 0);
+#ifdef DTX_ATTN_TIMING
+    const long long ti_kv = clock64() - ti_0;
+#endif
     issue_s(0, 0, 0);
     if (n > 1) issue_s(1, 1, 0);
     for (int base = 0; base < n; base += DKV_NS) {
@@ -829,8 +888,11 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
         if (ii < n) {
           // P^T / dS^T of pair ii sit bf16-packed in the score buffers u&1 themselves (the CPT query columns of column group c
           // -> TMEM columns CPT*c .. CPT*c + CPT/2 - 1): the A operands of the accumulating MMAs come straight from tensor memory.
+          TM_SET(ti_a);
           ISSUER_WAIT(&bar_p[u & 1], (ii >> 1) & 1);
           tc_fence_after();
+          TM_ACC(ti_p, ti_a);
+          TM_SET(ti_b);
           if (leader) {
             const uint32_t acc0 = ii > 0 ? 1u : 0u;
             const uint32_t aP = tmem + T_ST + (u & 1) * 64, aDS = tmem + T_DPT + (u & 1) * 64;
@@ -844,6 +906,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
                            idesc_g, kk > 0 ? 1u : acc0);
             umma_commit(&bar_free[u]);  // ring slot u may be refilled once these have read it
           }
+          TM_ACC(ti_acc, ti_b);
           if (ii + 2 < n) issue_s((u + 2) & (DKV_NS - 1), u & 1, (u + 2 >= DKV_NS) ? (rp ^ 1u) : rp);
         }
       }
@@ -851,18 +914,27 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
     // the compute warps do not follow the MMA completions phase by phase (parity waits are only safe one phase behind):
     // a dedicated single-phase barrier reports that every MMA of this CTA has completed
     if (leader) umma_commit(bar_fin);
+#ifdef DTX_ATTN_TIMING
+    if (leader && TM_BLOCK((int)blockIdx.x))
+      printf("[dkv issuer] block %d n %d total %lld wait_kv %lld | per pair: wait_p %lld wait_q %lld issue_s %lld issue_acc %lld\n", (int)blockIdx.x, n,
+             clock64() - ti_0, ti_kv, ti_p / n, ti_q / n, ti_s / n, ti_acc / n);
+#endif
   } else {
     const int rw = warp & 3, cq = warp >> 2;
     const int r = rw * 32 + (tid & 31);
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(rw * 32) << 16);
     const int kvrow = kv0 + r;
     int qi = 0;
+    TM_DECL(tc_w = 0, tc_l = 0, tc_m = 0, tc_s = 0, tc_0, tc_a, tc_b, tc_c, tc_d);
+    TM_SET(tc_0);
     for (int ii = 0; ii < n; ++ii) {
       const int qs = (i0 + qi) * 64;
       if (++qi == nq) qi = 0;
+      TM_SET(tc_a);
       mbar_wait(&bar_q[ii % DKV_NS], (ii / DKV_NS) & 1);  // acquire the TMA-written row statistics of this ring slot
       mbar_wait(&bar_s[ii & 1], (ii >> 1) & 1);
       tc_fence_after();
+      TM_SET(tc_b);
       const uint32_t st = smem_u32(smem + DKV_STAT + (ii % DKV_NS) * 512) + cq * (CPT * 4);
       uint32_t sv[CPT], dv[CPT], ppk[CPT / 2], dpk[CPT / 2];
       if constexpr (CPT == 32) {
@@ -873,6 +945,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
         tmem_ld16(t_lane + T_DPT + (ii & 1) * 64 + cq * CPT, dv);
       }
       tmem_ld_wait();
+      TM_SET(tc_c);
       const bool need_mask = (qs < kv0 + 127);
       // packed fp32 pairs (FFMA2 / FMUL2); every other pair of exponentials on the FMA pipe (exp2_fma2)
       const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale), nsc2 = make_float2(-p.scale, -p.scale);
@@ -896,6 +969,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
           dpk[(e + u) >> 1] = pack_bf16x2(ds.x, ds.y);
         }
       }
+      TM_SET(tc_d);
       // overwrite this thread's own (already loaded) score columns with the packed operands
       if constexpr (CPT == 32) {
         tmem_st16(t_lane + T_ST + (ii & 1) * 64 + cq * CPT, ppk);
@@ -907,9 +981,18 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_p[ii & 1]);
+#ifdef DTX_ATTN_TIMING
+      tc_w += tc_b - tc_a; tc_l += tc_c - tc_b; tc_m += tc_d - tc_c; tc_s += clock64() - tc_d;
+#endif
     }
+#ifdef DTX_ATTN_TIMING
+    const long long tc_loop = clock64() - tc_0;
+#endif
     mbar_wait(bar_fin, 0);
     tc_fence_after();
+#ifdef DTX_ATTN_TIMING
+    const long long tc_fin = clock64() - tc_0 - tc_loop;
+#endif
     // Hand dV and dK to the TMA: the eight 32-column chunks (dV 0-3, dK 4-7) are dealt to the column groups; each thread
     // converts its part of row r to bf16 into a 128B-swizzled staging tile (the Q/dO ring is free now), one thread per matrix
     // issues two bulk tensor stores.  (Direct 16-byte stores of one row per thread touch 32 different 128-byte lines per
@@ -973,6 +1056,11 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
       tma_store_commit();
       tma_store_wait_read0();  // the CTA's shared memory must stay valid until the bulk stores have read it
     }
+#ifdef DTX_ATTN_TIMING
+    if ((tid == 0 || tid == 128) && TM_BLOCK((int)blockIdx.x))
+      printf("[dkv compute] block %d tid %d n %d loop %lld (incl. first wait) wait_fin %lld epilogue %lld | per pair: wait %lld ld %lld math %lld st+arrive %lld\n",
+             (int)blockIdx.x, tid, n, tc_loop, tc_fin, clock64() - tc_0 - tc_loop - tc_fin, tc_w / n, tc_l / n, tc_m / n, tc_s / n);
+#endif
   }
   tc_fence_before();
   __syncthreads();

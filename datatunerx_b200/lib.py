@@ -14,7 +14,8 @@ from typing import Dict, Iterable, Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdtxtune.so")
+# DTX_LIB_PATH selects another build of the same library (e.g. the clock64()-instrumented libdtxtune_timing.so of tools/attn_timing.py)
+LIB_PATH = os.environ.get("DTX_LIB_PATH") or os.path.join(_HERE, "libdtxtune.so")
 
 DTX_F32, DTX_BF16, DTX_F16 = 0, 1, 2
 SCHED = {"linear": 0, "cosine": 1, "constant": 2, "constant_with_warmup": 3}

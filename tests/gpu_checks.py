@@ -678,7 +678,14 @@ def check_trainer_varlen(steps=4):
         loss, gn, _, stepped = tr.step(ids[:, :cur], labels[:, :cur], lens)
         assert stepped
         worst_l, worst_g = max(worst_l, abs(loss - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
-    # gradient tensors of one more step against the oracle's autograd gradients
+    # gradient tensors of one more step against the oracle's autograd gradients, from adapters with a sizeable B (B = 0 at init
+    # makes dA vanish; after a few Adam steps it is ~1e-3 and the comparison would measure bf16 noise on tiny numbers)
+    gen = torch.Generator().manual_seed(5)
+    fresh = {k: (torch.randn(v.shape, generator=gen) * 0.02 if "lora_B" in k else v.detach().clone()) for k, v in orc.lora.items()}
+    tr.load_state_dict({k: v.numpy() for k, v in fresh.items()})
+    with torch.no_grad():
+        for k, v in fresh.items():
+            orc.lora[k].copy_(v)
     ids, labels = O.synthetic_batch(99, 0, 4, 512, ocfg.vocab)
     lens = np.array([300, 5, 200, 129], dtype=np.int32)
     for b in range(4):
@@ -687,12 +694,14 @@ def check_trainer_varlen(steps=4):
     _, g_ref = orc.loss_and_grads(ids[:, :384], labels[:, :384])
     tr.step(ids[:, :384], labels[:, :384], lens)
     got = tr.export_adapter(grads=True)
+    per = {}
     for k, v in got.items():
         r = g_ref[k.replace("base_model.model.", "")].numpy()
-        worst_grad = max(worst_grad, float(np.linalg.norm(v - r) / max(np.linalg.norm(r), 1e-12)))
+        per[k.split("layers.")[1]] = float(np.linalg.norm(v - r) / max(np.linalg.norm(r), 1e-12))
+    worst_grad = max(per.values())
     tr.close()
-    assert worst_l < 1e-3 and worst_g < 3e-2 and worst_grad < 4e-2, (worst_l, worst_g, worst_grad)
-    return {"loss": worst_l, "gnorm": worst_g, "adapter_grads": worst_grad}
+    assert worst_l < 1e-3 and worst_g < 3e-2 and worst_grad < 4e-2, (worst_l, worst_g, per)
+    return {"loss": worst_l, "gnorm": worst_g, "adapter_grads": per}
 
 
 def check_eval_rows_and_force_step():
