@@ -9,7 +9,12 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
 for s in $STEPS; do
   case $s in
-    diag) timeout 1500 python tools/gpu_diag.py > $OUT/diag.log 2>&1; cp gpurun_out/diag.json $OUT/diag.json 2>/dev/null;;
+    diag) timeout 1500 python tools/gpu_diag.py ${DIAG_NAMES:-} > $OUT/diag.log 2>&1; cp gpurun_out/diag.json $OUT/diag.json 2>/dev/null;;
+    timing) DTX_LIB_PATH=$PWD/datatunerx_b200/libdtxtune_timing.so timeout 300 python tools/attn_timing.py > $OUT/attn_timing.log 2>&1;;
+    ncu_attn_bwd) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_d --launch-skip 192 --launch-count 2 -o $OUT/attn_bwd -f \
+                python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_attn_bwd.log 2>&1;;
+    sweep_gm) for g in 8 16 32; do DTX_GROUP_M=$g timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/bench_gm$g.json 2> $OUT/bench_gm$g.err; done;;
+    parity7b) timeout 1200 python tools/parity_7b.py --steps 3 --out $OUT/parity_7b.json > $OUT/parity_7b.log 2>&1;;
     pytest) timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1;;
     bench) timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err;;
