@@ -126,10 +126,6 @@ __device__ __forceinline__ float2 exp2_fma2(float2 x) {
   q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
   return q;
 }
-#ifndef DTX_FWD_EXP_FMA_EVERY
-#define DTX_FWD_EXP_FMA_EVERY 0
-#endif
-constexpr int FWD_EXP_FMA_EVERY = DTX_FWD_EXP_FMA_EVERY;  // forward softmax: every N-th pair of exponentials on the FMA pipe (0 = none; 4 measured: 302.9 vs 302.5 us, no gain)
 // exponentials of pair number `pair_idx` of a row: every FMA_EVERY-th pair on the FMA pipe (0 = none), the rest on the MUFU
 template <int FMA_EVERY = 0>
 __device__ __forceinline__ float2 exp2_pair(float2 x, int pair_idx) {
@@ -151,7 +147,12 @@ __device__ __forceinline__ float2 exp2_pair(float2 x, int pair_idx) {
 // (r01: the one-tile kernel kept O in registers (255 registers, spills) and folded 128 FMAs per row per block - it was
 // bound by its one softmax warp per scheduler, tensor pipe 25 % busy; a two-tile version of THAT design spilled and was
 // 2.8x slower.)
-constexpr int FW2_THREADS = 320;             // 8 softmax warps (4 per tile) + MMA issuer warp (8) + TMA loader warp (9)
+// r02 (profiles/r02_attn_phase_timing.txt): with ONE issuer warp the kernel was bound by that warp, not by the tensor pipe or the
+// softmax: a tcgen05.mma issue blocks for the MMA's duration (the pipe's queue is ~1 deep), so the issuer's own overhead per
+// block - four mbarrier checks of ~90 cycles each even when already complete, commits, fences: ~750 of 1780 cycles - left
+// the pipe idle.  Each tile now has its OWN issuer warp: while one sits in a barrier check the other feeds the pipe.  The
+// tiles share nothing but the K/V ring (its slots are released when both issuers have committed).
+constexpr int FW2_THREADS = 352;             // 8 softmax warps (4 per tile) + one MMA issuer warp per tile (8, 9) + TMA loader warp (10)
 constexpr int FW2_NS = 4;
 constexpr int FW2_SQ = 0;                    // 2 tiles x (2 x [128 x 128B])
 constexpr int FW2_SK = 65536;                // FW2_NS x (2 x [64 x 128B])
@@ -159,6 +160,7 @@ constexpr int FW2_SV = FW2_SK + FW2_NS * 16384;
 constexpr int FW2_BAR = FW2_SV + FW2_NS * 16384;
 constexpr int FW2_SMEM = FW2_BAR + 256 + 1024;
 
+template <int EXP_FMA_EVERY>  // every N-th pair of exponentials on the FMA pipe instead of the MUFU (0 = none)
 __global__ void __launch_bounds__(FW2_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
@@ -195,6 +197,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmOut);
     for (int i = 0; i < 17; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < FW2_NS; ++i) mbar_init(&bar_free[i], n1 > 0 ? 2 : 1);  // one commit / arrive per issuer warp with a live tile
     // "P_t(j) is in tensor memory": one barrier per score buffer, like bar_s.  With a single barrier per tile a tile whose
     // next score block is already there (double buffering) can complete TWO phases while the issuer is still serving the
     // other tile, and a parity wait that misses a phase never returns.
@@ -208,7 +211,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem = *tmem_ptr;
   // TMEM columns of tile t: score buffers 256t, 256t + 64; output 256t + 128
 
-  if (warp == 9) {
+  if (warp == 10) {
     // ------------------------------------------ TMA loader ------------------------------------------
     if ((tid & 31) == 0) {
       mbar_arrive_expect_tx(bar_q, n1 > 0 ? 65536 : 32768);
@@ -229,16 +232,20 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_load_2d(smem + FW2_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
       }
     }
-  } else if (warp == 8) {
-    // ------------------------------------------ MMA issuer (lean: see attn_dkv_kernel) ------------------------------------------
+  } else if (warp >= 8) {
+    // ------------------------------------------ MMA issuer of tile t (lean: see attn_dkv_kernel) ------------------------------------------
+    const int t = warp - 8;
+    const int nm = nt(t);
     const bool leader = elect_one();
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 0, 1);
-    const uint32_t loQ = umma_desc_lo(smem_u32(smem + FW2_SQ), 16), loK = umma_desc_lo(smem_u32(smem + FW2_SK), 16),
+    const uint32_t loQ = umma_desc_lo(smem_u32(smem + FW2_SQ + t * 32768), 16), loK = umma_desc_lo(smem_u32(smem + FW2_SK), 16),
                    loVm = umma_desc_lo(smem_u32(smem + FW2_SV), 8192);
+    const uint32_t tS = tmem + t * 256, tO = tmem + t * 256 + 128;
+    uint64_t *my_s = bar_s + t * 2, *my_p = bar_p + t * 2;
     TM_DECL(ti_kv = 0, ti_s = 0, ti_p = 0, ti_pv = 0, ti_0, ti_a, ti_b);
     TM_SET(ti_0);
-    auto issue_s = [&](const int t, const int slot, const int buf, const uint32_t parity) {  // S_t = Q_t K^T into buffer buf
+    auto issue_s = [&](const int slot, const int buf, const uint32_t parity) {  // S_t = Q_t K^T of the block in ring slot `slot` into buffer buf
       TM_SET(ti_a);
       ISSUER_WAIT(&bar_kv[slot], parity);
       tc_fence_after();
@@ -247,56 +254,52 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < 8; ++k16)
-          umma_bf16(tmem + t * 256 + buf * 64, umma_desc_pack(loQ + t * 2048 + kmaj_lo(k16, 16384)),
-                    umma_desc_pack(loK + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s, k16 > 0 ? 1u : 0u);
-        umma_commit(&bar_s[t * 2 + buf]);
+          umma_bf16(tS + buf * 64, umma_desc_pack(loQ + kmaj_lo(k16, 16384)), umma_desc_pack(loK + slot * 1024 + kmaj_lo(k16, 8192)), idesc_s,
+                    k16 > 0 ? 1u : 0u);
+        umma_commit(&my_s[buf]);
       }
       TM_ACC(ti_s, ti_b);
     };
-    ISSUER_WAIT(bar_q, 0);
+    if (nm > 0) {
+      ISSUER_WAIT(bar_q, 0);
 #ifdef DTX_ATTN_TIMING
-    const long long ti_q = clock64() - ti_0;
+      const long long ti_q = clock64() - ti_0;
 #endif
-    issue_s(0, 0, 0, 0);
-    if (n1 > 0) issue_s(1, 0, 0, 0);
-    if (n0 > 1) issue_s(0, 1, 1, 0);
-    if (n1 > 1) issue_s(1, 1, 1, 0);
-    for (int base = 0; base < n; base += FW2_NS) {
-      const uint32_t rp = (base >> 2) & 1;
+      issue_s(0, 0, 0);
+      if (nm > 1) issue_s(1, 1, 0);
+      for (int base = 0; base < n; base += FW2_NS) {
+        const uint32_t rp = (base >> 2) & 1;
 #pragma unroll
-      for (int u = 0; u < FW2_NS; ++u) {
-        const int j = base + u;
-        if (j < n) {
+        for (int u = 0; u < FW2_NS; ++u) {
+          const int j = base + u;
+          if (j < nm) {
+            TM_SET(ti_a);
+            ISSUER_WAIT(&my_p[u & 1], (j >> 1) & 1);  // P_t(j) sits bf16-packed in the first 32 columns of score buffer j&1
+            tc_fence_after();
+            TM_ACC(ti_p, ti_a);
+            TM_SET(ti_b);
+            if (leader) {
+              const uint32_t acc0 = j > 0 ? 1u : 0u;
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (j < nt(t)) {
-              TM_SET(ti_a);
-              ISSUER_WAIT(&bar_p[t * 2 + (u & 1)], (j >> 1) & 1);  // P_t(j) sits bf16-packed in the first 32 columns of score buffer j&1
-              tc_fence_after();
-              TM_ACC(ti_p, ti_a);
-              TM_SET(ti_b);
-              if (leader) {
-                const uint32_t acc0 = j > 0 ? 1u : 0u;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma_bf16_ts(tmem + t * 256 + 128, tmem + t * 256 + (u & 1) * 64 + kk * 8, umma_desc_pack(loVm + u * 1024 + kk * 128),
-                               idesc_o, kk > 0 ? 1u : acc0);
-                umma_commit(&bar_o[t]);
-                if (j == nt(t) - 1) umma_commit(&bar_fin[t]);
-              }
-              TM_ACC(ti_pv, ti_b);
-              if (j + 2 < nt(t)) issue_s(t, (u + 2) & 3, u & 1, (u + 2 >= FW2_NS) ? (rp ^ 1u) : rp);
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16_ts(tO, tS + (u & 1) * 64 + kk * 8, umma_desc_pack(loVm + u * 1024 + kk * 128), idesc_o, kk > 0 ? 1u : acc0);
+              umma_commit(&bar_o[t]);
+              if (j == nm - 1) umma_commit(&bar_fin[t]);
+              umma_commit(&bar_free[u]);  // this tile's S(j) and P V(j) are the only MMAs of this warp that read ring slot u
             }
+            TM_ACC(ti_pv, ti_b);
+            if (j + 2 < nm) issue_s((u + 2) & 3, u & 1, (u + 2 >= FW2_NS) ? (rp ^ 1u) : rp);
+          } else if (j < n) {
+            if (leader) mbar_arrive(&bar_free[u]);  // the other tile's block only (it reaches two blocks further): nothing to read here
           }
-          if (leader) umma_commit(&bar_free[u]);  // every MMA that reads ring slot u has been issued
         }
       }
-    }
 #ifdef DTX_ATTN_TIMING
-    if (leader && TM_BLOCK((int)blockIdx.x))
-      printf("[fwd2 issuer] block %d n %d total %lld wait_q %lld | per block-step: wait_p %lld wait_kv %lld issue_s %lld issue_pv %lld\n", (int)blockIdx.x,
-             n, clock64() - ti_0, ti_q, ti_p / n, ti_kv / n, ti_s / n, ti_pv / n);
+      if (leader && TM_BLOCK((int)blockIdx.x))
+        printf("[fwd2 issuer] block %d tile %d n %d total %lld wait_q %lld | per block: wait_p %lld wait_kv %lld issue_s %lld issue_pv %lld\n",
+               (int)blockIdx.x, t, nm, clock64() - ti_0, ti_q, ti_p / nm, ti_kv / nm, ti_s / nm, ti_pv / nm);
 #endif
+    }
   } else {
     // ------------------------------------------ softmax warps ------------------------------------------
     const int t = warp >> 2, w = warp & 3;
@@ -368,7 +371,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {  // packed fp32 pairs; every other pair of exponentials on the FMA pipe (exp2_fma2)
-        const float2 pr = exp2_pair<FWD_EXP_FMA_EVERY>(__ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), c >> 1);
+        const float2 pr = exp2_pair<EXP_FMA_EVERY>(__ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), c >> 1);
         rs = __fadd2_rn(rs, pr);
         pk[c >> 1] = pack_bf16x2(pr.x, pr.y);
       }
@@ -855,10 +858,16 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
                    loQm = umma_desc_lo(smem_u32(smem + DKV_SQ), 8192), loDOm = umma_desc_lo(smem_u32(smem + DKV_SDO), 8192);
     TM_DECL(ti_q = 0, ti_s = 0, ti_p = 0, ti_acc = 0, ti_0, ti_a, ti_b);
     TM_SET(ti_0);
-    auto issue_s = [&](const int slot, const int buf, const uint32_t parity) {  // S^T = K Q^T, dP^T = V dO^T into buffer buf
+    // S^T = K Q^T, dP^T = V dO^T into buffer buf.  Only the two prologue calls wait for the ring slot themselves: inside the
+    // loop the compute warps have already waited for the slot of pair ii + 2 before they arrive on bar_p(ii) (an mbarrier
+    // check costs this warp ~90 cycles even when the phase is long complete, and every cycle it spends outside a
+    // tcgen05.mma issue is a cycle the tensor pipe idles - profiles/r02_attn_phase_timing.txt).
+    auto issue_s = [&](const int slot, const int buf, const uint32_t parity, const bool wait_slot) {
       TM_SET(ti_a);
-      ISSUER_WAIT(&bar_q[slot], parity);
-      tc_fence_after();
+      if (wait_slot) {
+        ISSUER_WAIT(&bar_q[slot], parity);
+        tc_fence_after();
+      }
       TM_ACC(ti_q, ti_a);
       TM_SET(ti_b);
       if (leader) {
@@ -878,8 +887,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
 #ifdef DTX_ATTN_TIMING
     const long long ti_kv = clock64() - ti_0;
 #endif
-    issue_s(0, 0, 0);
-    if (n > 1) issue_s(1, 1, 0);
+    issue_s(0, 0, 0, true);
+    if (n > 1) issue_s(1, 1, 0, true);
     for (int base = 0; base < n; base += DKV_NS) {
       const uint32_t rp = (base >> 2) & 1;  // ring round parity of this group of four pairs
 #pragma unroll
@@ -907,7 +916,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
             umma_commit(&bar_free[u]);  // ring slot u may be refilled once these have read it
           }
           TM_ACC(ti_acc, ti_b);
-          if (ii + 2 < n) issue_s((u + 2) & (DKV_NS - 1), u & 1, (u + 2 >= DKV_NS) ? (rp ^ 1u) : rp);
+          if (ii + 2 < n) issue_s((u + 2) & (DKV_NS - 1), u & 1, (u + 2 >= DKV_NS) ? (rp ^ 1u) : rp, false);
         }
       }
     }
@@ -979,6 +988,9 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
         tmem_st8(t_lane + T_DPT + (ii & 1) * 64 + cq * CPT, dpk);
       }
       tmem_st_wait();
+      // the issuer starts S^T / dP^T of pair ii + 2 right after the accumulate MMAs of this pair without looking at the ring:
+      // make sure that pair's Q / dO block has landed before telling it so (these warps have slack, the issuer has none)
+      if (ii + 2 < n) mbar_wait(&bar_q[(ii + 2) % DKV_NS], ((ii + 2) / DKV_NS) & 1);
       tc_fence_before();
       mbar_arrive(&bar_p[ii & 1]);
 #ifdef DTX_ATTN_TIMING
@@ -1076,6 +1088,8 @@ cudaError_t set_smem(const void* fn, int bytes) {
 
 }  // namespace
 
+int g_fwd_exp_fma_every = 0;
+void attn_set_fwd_exp_fma_every(int n) { g_fwd_exp_fma_every = (n == 2 || n == 3 || n == 4) ? n : 0; }
 int attn_bwd_launches() { return 2; }
 bool attn_bwd_can_rope() { return true; }
 
@@ -1089,7 +1103,10 @@ cudaError_t attn_init_device() {
   if (e != cudaSuccess) return e;
   std::lock_guard<std::mutex> lk(mu);
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-  if ((e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel), FW2_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel<0>), FW2_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel<2>), FW2_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel<3>), FW2_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel<4>), FW2_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(reinterpret_cast<const void*>(attn_dq1_kernel), DQ1_SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<8>), DKV_SMEM)) != cudaSuccess) return e;
   if (dev >= 0 && dev < 64) done[dev] = true;
@@ -1118,7 +1135,13 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   p.lse2 = a.lse;
   p.out = a.out;
   p.seq_lens = a.seq_lens;
-  attn_fwd2_kernel<<<a.B * a.H * ((a.S + 255) / 256), FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p);
+  const int grid = a.B * a.H * ((a.S + 255) / 256);
+  switch (g_fwd_exp_fma_every) {
+    case 2: attn_fwd2_kernel<2><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); break;
+    case 3: attn_fwd2_kernel<3><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); break;
+    case 4: attn_fwd2_kernel<4><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); break;
+    default: attn_fwd2_kernel<0><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); break;
+  }
   return cudaGetLastError();
 }
 

@@ -51,6 +51,10 @@ int32_t dtx_set_option(const char* name, int32_t value) {
     gemm_set_pair_group_m(value);
     return DTX_OK;
   }
+  if (strcmp(name, "attn_fwd_exp_fma_every") == 0) {
+    attn_set_fwd_exp_fma_every(value);
+    return DTX_OK;
+  }
   if (strcmp(name, "fused_epilogues") == 0) {
     trainer_set_fused_epilogues(value);
     return DTX_OK;

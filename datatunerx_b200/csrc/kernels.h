@@ -50,6 +50,9 @@ int gemm_num_sms();
 void gemm_set_pair_kernel(int on);
 bool attn_bwd_can_rope();  // the backward kernels apply the inverse rotary themselves when AttnArgs::rope_cs is set
 int attn_bwd_launches();   // kernels one attn_bwd() call launches (dQ (+ delta) and dK/dV)
+// forward softmax: every N-th pair of exponentials (N = 2, 3, 4) is computed on the FMA pipe with a cubic polynomial instead of
+// MUFU.EX2 (max. relative error 7.5e-5, far below bf16 resolution); 0 = all on the MUFU
+void attn_set_fwd_exp_fma_every(int n);
 void gemm_set_pair_group_m(int tiles);  // rasterisation group height of the pair kernel, in 256-row tiles
 // 1 (default): RoPE / SwiGLU run inside GEMM and attention epilogues; 0: separate HBM-bound kernels (A/B, tiny M)
 void trainer_set_fused_epilogues(int on);
