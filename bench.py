@@ -298,6 +298,8 @@ def run_native(args, rank: int, local_rank: int, world: int):
     total = args.warmup + 2 * args.steps + 2
     tc = L.TrainConfig(micro_batch=B, seq_len=S, total_steps=max(total, 100), lora_r=lora_r, lora_alpha=32.0, lora_dropout=0.0, lr=1e-4)
     nccl_id = rv.broadcast_bytes(L.nccl_unique_id)
+    if os.environ.get("DTX_FWD_EXP_FMA"):  # A/B of the forward softmax's FMA-pipe exp2 fraction
+        L.set_option("attn_fwd_exp_fma_every", int(os.environ["DTX_FWD_EXP_FMA"]))
     if os.environ.get("DTX_GROUP_M"):  # rasterisation sweep of the CTA-pair GEMM (tools/gpu_round.sh sweep_gm)
         L.set_option("gemm_group_m", int(os.environ["DTX_GROUP_M"]))
     tr = L.Trainer(mc, tc, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)

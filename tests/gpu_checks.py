@@ -388,6 +388,18 @@ def check_attn_fwd(B=2, S=256, H=2, Hkv=None, growing=False):
     return {"out": e, "lse": e_l}
 
 
+def check_attn_fwd_exp_fma():
+    """Forward softmax with part of the exponentials on the FMA pipe (cubic polynomial, rel. error 7.5e-5): same parity bar."""
+    out = {}
+    try:
+        for every in (2, 3, 4):
+            L.set_option("attn_fwd_exp_fma_every", every)
+            out[f"every{every}"] = {"s384": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "rescale": check_attn_fwd(B=1, S=1024, H=2, growing=True)}
+    finally:
+        L.set_option("attn_fwd_exp_fma_every", 0)
+    return out
+
+
 def check_attn_bwd(B=2, S=256, H=2, Hkv=None):
     lib = L.load()
     D = 128
@@ -1037,6 +1049,7 @@ ALL = {
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
     "attn_fwd_rescale": lambda: check_attn_fwd(B=1, S=1024, H=2, growing=True),
     "attn_fwd_odd_tiles": lambda: {"s640": check_attn_fwd(B=1, S=640, H=2), "s128": check_attn_fwd(B=3, S=128, H=2)},
+    "attn_fwd_exp_fma": check_attn_fwd_exp_fma,
     "attn_bwd_single_tile": lambda: check_attn_bwd(B=3, S=128, H=2),
     "attn_bwd": check_attn_bwd, "attn_bwd_long": lambda: check_attn_bwd(B=1, S=1024, H=1),
     "attn_gqa": lambda: {"fwd": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "bwd": check_attn_bwd(B=2, S=384, H=4, Hkv=1)},

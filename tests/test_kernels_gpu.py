@@ -26,7 +26,7 @@ def test_hbm_kernels(name):
     _run(name)
 
 
-@pytest.mark.parametrize("name", ["attn_fwd", "attn_fwd_long", "attn_fwd_rescale", "attn_fwd_odd_tiles", "attn_bwd_single_tile", "attn_bwd", "attn_bwd_long",
+@pytest.mark.parametrize("name", ["attn_fwd", "attn_fwd_long", "attn_fwd_rescale", "attn_fwd_odd_tiles", "attn_fwd_exp_fma", "attn_bwd_single_tile", "attn_bwd", "attn_bwd_long",
                                   "attn_gqa", "attn_bwd_rope", "attn_varlen", "attn_bench_shape_s2048", "attn_bench_shape_s4096_gqa"])
 def test_attention(name):
     _run(name)

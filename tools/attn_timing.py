@@ -31,6 +31,17 @@ def main(B=8, S=2048, H=32, Hkv=32):
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     sc = 1.0 / math.sqrt(D)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for every in (0, 4, 3, 2):  # forward softmax: fraction of exponentials on the FMA pipe
+        L.set_option("attn_fwd_exp_fma_every", every)
+        ts = []
+        for it in range(4):
+            ev[0].record()
+            L.check(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, sc, None, 0, st))
+            ev[1].record()
+            torch.cuda.synchronize()
+            ts.append(ev[0].elapsed_time(ev[1]) * 1000)
+        print(f"ATTN_TIMING fwd exp_fma_every={every}: {min(ts[1:]):.1f} us (runs {[round(t, 1) for t in ts]})", flush=True)
+    L.set_option("attn_fwd_exp_fma_every", int(os.environ.get("DTX_FWD_EXP_FMA", "0")))
     for it in range(2):
         ev[0].record()
         L.check(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, sc, None, 0, st))

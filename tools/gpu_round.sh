@@ -14,6 +14,7 @@ for s in $STEPS; do
     ncu_attn_bwd) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_d --launch-skip 192 --launch-count 2 -o $OUT/attn_bwd -f \
                 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_attn_bwd.log 2>&1;;
     sweep_gm) for g in 8 16 32; do DTX_GROUP_M=$g timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/bench_gm$g.json 2> $OUT/bench_gm$g.err; done;;
+    bench_fma) for e in 0 4 3; do DTX_FWD_EXP_FMA=$e timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/bench_fma$e.json 2> $OUT/bench_fma$e.err; done;;
     parity7b) timeout 1200 python tools/parity_7b.py --steps 3 --out $OUT/parity_7b.json > $OUT/parity_7b.log 2>&1;;
     pytest) timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1;;
