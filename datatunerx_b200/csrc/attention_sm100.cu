@@ -534,12 +534,16 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #ifdef DTX_ATTN_TIMING
     long long ti_kv = 0, ti_mma = 0;
 #endif
-    auto issue_s = [&](const int slot, const int buf, const uint32_t parity) {  // S = Q K^T, dP = dO V^T (A operands from TMEM)
+    // S = Q K^T, dP = dO V^T (A operands from TMEM).  wait_slot: only the two prologue calls look at the K/V ring themselves - in
+    // the loop the compute warps wait for block j + 2's slot before they arrive on bar_p(j) (see attn_dkv_kernel)
+    auto issue_s = [&](const int slot, const int buf, const uint32_t parity, const bool wait_slot) {
 #ifdef DTX_ATTN_TIMING
       const long long tk0 = clock64();
 #endif
-      ISSUER_WAIT(&bar_kv[slot], parity);
-      tc_fence_after();
+      if (wait_slot) {
+        ISSUER_WAIT(&bar_kv[slot], parity);
+        tc_fence_after();
+      }
 #ifdef DTX_ATTN_TIMING
       const long long tk1 = clock64();
       ti_kv += tk1 - tk0;
@@ -567,8 +571,8 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #ifdef DTX_ATTN_TIMING
     const long long ti_qt = clock64() - ti_t0;
 #endif
-    issue_s(0, 0, 0);
-    if (n > 1) issue_s(1, 1, 0);
+    issue_s(0, 0, 0, true);
+    if (n > 1) issue_s(1, 1, 0, true);
     for (int base = 0; base < n; base += DQ1_NS) {
       const uint32_t rp = (base >> 2) & 1;
 #pragma unroll
@@ -592,7 +596,7 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_commit(&bar_free[u]);
             if (j == n - 1) umma_commit(bar_fin);
           }
-          if (j + 2 < n) issue_s((u + 2) & 3, u & 1, (u + 2 >= DQ1_NS) ? (rp ^ 1u) : rp);
+          if (j + 2 < n) issue_s((u + 2) & 3, u & 1, (u + 2 >= DQ1_NS) ? (rp ^ 1u) : rp, false);
         }
       }
     }
@@ -691,6 +695,7 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #endif
       tmem_st16(t_lane + T_S + (j & 1) * 64 + half * 32, pk);  // over this thread's own (already loaded) score columns
       tmem_st_wait();
+      if (j + 2 < n) mbar_wait(&bar_kv[(j + 2) & 3], ((j + 2) >> 2) & 1);  // the issuer no longer checks the ring slot of block j + 2
       tc_fence_before();
       mbar_arrive(&bar_p[j & 1]);
 #ifdef DTX_ATTN_TIMING
