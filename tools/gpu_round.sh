@@ -15,6 +15,10 @@ for s in $STEPS; do
                 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_attn_bwd.log 2>&1;;
     sweep_gm) for g in 8 16 32; do DTX_GROUP_M=$g timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/bench_gm$g.json 2> $OUT/bench_gm$g.err; done;;
     bench_fma) for e in 0 4 3; do DTX_FWD_EXP_FMA=$e timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/bench_fma$e.json 2> $OUT/bench_fma$e.err; done;;
+    attn_events) timeout 300 python tools/attn_timing.py > $OUT/attn_events.log 2>&1;;
+    sanitizer) for c in gemm_nt gemm_kext rmsnorm cross_entropy adamw attn_fwd attn_bwd attn_varlen trainer_tiny; do
+                 timeout 900 compute-sanitizer --tool racecheck --print-limit 5 python -m tests.gpu_checks $c > $OUT/racecheck_$c.log 2>&1; echo "$c rc=$?" >> $OUT/sanitizer_summary.txt; done
+               timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python -m tests.gpu_checks attn_varlen trainer_varlen > $OUT/memcheck_varlen.log 2>&1; echo "memcheck_varlen rc=$?" >> $OUT/sanitizer_summary.txt;;
     parity7b) timeout 1200 python tools/parity_7b.py --steps 3 --out $OUT/parity_7b.json > $OUT/parity_7b.log 2>&1;;
     pytest) timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1;;
