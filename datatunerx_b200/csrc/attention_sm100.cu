@@ -82,6 +82,7 @@ struct AttnKParams {
   const float2* rope_cs;  // backward: transposed rotary table [64][rope_stride] (cos, sin), or null
   int rope_stride;
   const int32_t* seq_lens;  // [B] true row lengths (right padding beyond), or null = S
+  int window;               // sliding-window attention: query i sees keys i - window .. i; 0 = plain causal
 };
 
 // true length of batch row b (tiles that start at or beyond it hold only padding)
@@ -182,7 +183,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
   const int q00 = qp * 256, q01 = qp * 256 + 128;
   const int len = row_len(p, b);
-  const int n0 = q00 < len ? (q00 + 128) / 64 : 0, n1 = q01 < len ? (q01 + 128) / 64 : 0;  // KV blocks each tile needs (0: padding only)
+  // Sliding window: keys before q00 - window are invisible to every row of this CTA: the K/V ring starts at block jlo (both tiles
+  // start there - the at most two leading blocks that only tile 0 can see are fully masked for tile 1).  Block counts below are
+  // relative to jlo; a row may then meet blocks in which it sees nothing (handled by the -inf-safe softmax reference).
+  const int jlo = p.window > 0 ? max(0, (q00 - p.window) / 64) : 0;
+  const int n0 = q00 < len ? (q00 + 128) / 64 - jlo : 0, n1 = q01 < len ? (q01 + 128) / 64 - jlo : 0;  // KV blocks each tile needs (0: padding only)
   const int n = max(n0, n1);
   auto nt = [&](int t) { return t ? n1 : n0; };
   if (n0 == 0) {  // both tiles lie in this row's padding (n1 > 0 implies n0 > 0)
@@ -226,10 +231,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int slot = j & 3;
         if (j >= FW2_NS) mbar_wait_backoff(&bar_free[slot], ((j >> 2) - 1) & 1);  // both tiles' P V(j - 4) have read the slot
         mbar_arrive_expect_tx(&bar_kv[slot], 32768);
-        tma_load_2d(smem + FW2_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
-        tma_load_2d(smem + FW2_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
-        tma_load_2d(smem + FW2_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
-        tma_load_2d(smem + FW2_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
+        tma_load_2d(smem + FW2_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + (jlo + j) * 64);
+        tma_load_2d(smem + FW2_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + (jlo + j) * 64);
+        tma_load_2d(smem + FW2_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + (jlo + j) * 64);
+        tma_load_2d(smem + FW2_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + (jlo + j) * 64);
       }
     }
   } else if (warp >= 8) {
@@ -315,7 +320,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     TM_SET(tc_0);
 
     for (int j = 0; j < n_mine; ++j) {
-      const int kv0 = j * 64;
+      const int kv0 = (jlo + j) * 64;
       TM_SET(tc_a);
       mbar_wait(&my_s[j & 1], (j >> 1) & 1);
       tc_fence_after();
@@ -334,6 +339,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int c = 0; c < 64; ++c)
           if (kv0 + c > qrow) sv[c] = 0xff800000u;  // -inf
       }
+      if (p.window > 0 && kv0 < q0 + 127 - p.window) {  // blocks that straddle the far edge of the window
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (kv0 + c < qrow - p.window) sv[c] = 0xff800000u;
+      }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 64; c += 4) {
@@ -344,12 +354,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;  // scale > 0: max commutes with the scaling
       if (j == 0) {
-        m_ref = mx;  // block 0 always holds column 0 <= qrow: finite
+        m_ref = mx;  // plain causal: block 0 always holds column 0 <= qrow (finite); with a window the row may see nothing yet (-inf)
       } else {
-        const bool grow = mx > m_ref + FW2_RESCALE_T;
+        const bool grow = mx > m_ref + FW2_RESCALE_T;  // also the first visible key of a windowed row (m_ref = -inf): alpha = 0, O = 0 so far
         if (__any_sync(0xffffffffu, grow)) {  // rare: move the reference of the rows that need it and rescale their output
           const float m_new = grow ? mx : m_ref;
-          const float alpha = fast_exp2(m_ref - m_new);
+          const float alpha = grow ? fast_exp2(m_ref - m_new) : 1.f;  // (-inf) - (-inf) of a windowed row that still sees nothing would be NaN
           mbar_wait(my_o, (j - 1) & 1);  // P V(j-1) (and every earlier one) has landed in the output tile
           tc_fence_after();
 #pragma unroll
@@ -368,7 +378,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       uint32_t pk[32];
       float2 rs = make_float2(0.f, 0.f);
-      const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+      // a row that has not met a visible key yet keeps m_ref = -inf: every score is -inf and must give exp2(-inf) = 0, not
+      // exp2(-inf + inf) = NaN
+      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+      const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_use, -m_use);
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {  // packed fp32 pairs; every other pair of exponentials on the FMA pipe (exp2_fma2)
         const float2 pr = exp2_pair<EXP_FMA_EVERY>(__ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sl2, nm2), c >> 1);
@@ -475,7 +488,8 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int h = bh % p.H, b = bh / p.H;
   const int q0 = qb * 128;
   const int row_base = b * p.S;
-  const int n = (q0 + 128) / 64;
+  const int jlo = p.window > 0 ? max(0, (q0 - p.window) / 64) : 0;  // sliding window: first K/V block any row of the tile can see
+  const int n = (q0 + 128) / 64 - jlo;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int hk = h / (p.H / p.Hkv);
   const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
@@ -518,10 +532,10 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int slot = j & 3;
         if (j >= DQ1_NS) mbar_wait_backoff(&bar_free[slot], ((j >> 2) - 1) & 1);  // dQ MMA of block j - 4 has read the slot
         mbar_arrive_expect_tx(&bar_kv[slot], 32768);
-        tma_load_2d(smem + DQ1_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + j * 64);
-        tma_load_2d(smem + DQ1_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + j * 64);
-        tma_load_2d(smem + DQ1_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + j * 64);
-        tma_load_2d(smem + DQ1_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + j * 64);
+        tma_load_2d(smem + DQ1_SK + slot * 16384, &tmKV, &bar_kv[slot], colK, row_base + (jlo + j) * 64);
+        tma_load_2d(smem + DQ1_SK + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colK + 64, row_base + (jlo + j) * 64);
+        tma_load_2d(smem + DQ1_SV + slot * 16384, &tmKV, &bar_kv[slot], colV, row_base + (jlo + j) * 64);
+        tma_load_2d(smem + DQ1_SV + slot * 16384 + 8192, &tmKV, &bar_kv[slot], colV + 64, row_base + (jlo + j) * 64);
       }
     }
   } else if (warp == 8) {
@@ -658,7 +672,7 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const long long tc_t0 = clock64();
 #endif
     for (int j = 0; j < n; ++j) {
-      const int kv0 = j * 64;
+      const int kv0 = (jlo + j) * 64;
 #ifdef DTX_ATTN_TIMING
       const long long t_a = clock64();
 #endif
@@ -674,7 +688,8 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #ifdef DTX_ATTN_TIMING
       const long long t_c = clock64();
 #endif
-      const bool need_mask = (kv0 + 63 > q0);
+      const bool need_mask = (kv0 + 63 > q0) || (p.window > 0 && kv0 < q0 + 127 - p.window);
+      const int klo = p.window > 0 ? qrow - p.window : -(1 << 30);  // first visible key of this row
       // packed fp32 pairs (FFMA2 / FMUL2): dS = P o (dP * scale - delta * scale), P = 2^(S * scale_log2 - lse2)
       const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nl2 = make_float2(-lse2, -lse2), sc2 = make_float2(p.scale, p.scale),
                    nd2 = make_float2(-delta * p.scale, -delta * p.scale);
@@ -683,8 +698,9 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2, nl2);
         float2 pr = exp2_pair(x, e >> 1);
         if (need_mask) {
-          if (kv0 + half * 32 + e > qrow) pr.x = 0.f;
-          if (kv0 + half * 32 + e + 1 > qrow) pr.y = 0.f;
+          const int k0 = kv0 + half * 32 + e;
+          if (k0 > qrow || k0 < klo) pr.x = 0.f;
+          if (k0 + 1 > qrow || k0 + 1 < klo) pr.y = 0.f;
         }
         const float2 dd = __ffma2_rn(make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sc2, nd2);
         const float2 ds = __fmul2_rn(pr, dd);
@@ -795,7 +811,10 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
   const int row_base = b * p.S;
   const int i0 = kv0 / 64;
   const int len = row_len(p, b);
-  const int nq = (len + 63) / 64 - i0;        // query blocks per query head that see this KV block and hold a real token
+  // query blocks per query head that see this KV block and hold a real token; with a sliding window the last query row that
+  // sees any key of the tile is kv0 + 127 + window
+  const int q_end = p.window > 0 ? min((len + 63) / 64, (kv0 + 127 + p.window) / 64 + 1) : (len + 63) / 64;
+  const int nq = q_end - i0;
   const int n = nq * grp;                     // streamed (head, query block) pairs; it -> head it / nq, block it % nq
   const int tid = threadIdx.x, warp = tid >> 5;
   const int colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
@@ -960,7 +979,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
       }
       tmem_ld_wait();
       TM_SET(tc_c);
-      const bool need_mask = (qs < kv0 + 127);
+      const bool need_mask = (qs < kv0 + 127) || (p.window > 0 && qs + 63 > kv0 + p.window);
       // packed fp32 pairs (FFMA2 / FMUL2); every other pair of exponentials on the FMA pipe (exp2_fma2)
       const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale), nsc2 = make_float2(-p.scale, -p.scale);
 #pragma unroll
@@ -974,8 +993,10 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
           const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[e + u]), __uint_as_float(sv[e + u + 1])), sl2, nl);
           float2 pr = exp2_pair(x, (e + u) >> 1);
           if (need_mask) {
-            if (kvrow > qs + cq * CPT + e + u) pr.x = 0.f;
-            if (kvrow > qs + cq * CPT + e + u + 1) pr.y = 0.f;
+            const int qa = qs + cq * CPT + e + u;  // query row of pr.x (pr.y: qa + 1); visible iff kvrow <= q <= kvrow + window
+            const int qhi = p.window > 0 ? kvrow + p.window : (1 << 30);
+            if (kvrow > qa || qa > qhi) pr.x = 0.f;
+            if (kvrow > qa + 1 || qa + 1 > qhi) pr.y = 0.f;
           }
           const float2 dd = __ffma2_rn(make_float2(__uint_as_float(dv[e + u]), __uint_as_float(dv[e + u + 1])), sc2, __fmul2_rn(dl, nsc2));
           const float2 ds = __fmul2_rn(pr, dd);
@@ -1121,7 +1142,7 @@ cudaError_t attn_init_device() {
 
 cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   if (a.S % 128 || a.B <= 0 || a.H <= 0) return cudaErrorInvalidValue;
-  if (a.window != 0) return cudaErrorInvalidValue;  // sliding-window masks are not implemented (the host refuses seq_len > window)
+  if (a.window < 0) return cudaErrorInvalidValue;
   cudaError_t e = attn_init_device();
   if (e != cudaSuccess) return e;
   const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
@@ -1140,6 +1161,7 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   p.lse2 = a.lse;
   p.out = a.out;
   p.seq_lens = a.seq_lens;
+  p.window = a.window;
   const int grid = a.B * a.H * ((a.S + 255) / 256);
   switch (g_fwd_exp_fma_every) {
     case 2: attn_fwd2_kernel<2><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); break;
@@ -1152,7 +1174,7 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
 
 cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (a.S % 128 || a.B <= 0 || a.H <= 0 || !a.delta || !a.lse || !a.dout || !a.dqkv) return cudaErrorInvalidValue;
-  if (a.window != 0) return cudaErrorInvalidValue;
+  if (a.window < 0) return cudaErrorInvalidValue;
   cudaError_t e = attn_init_device();
   if (e != cudaSuccess) return e;
   const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
@@ -1180,6 +1202,7 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   p.rope_cs = a.rope_cs;
   p.rope_stride = a.rope_stride > 0 ? a.rope_stride : a.S;
   p.seq_lens = a.seq_lens;
+  p.window = a.window;
   attn_dq1_kernel<<<a.B * a.H * (a.S / 128), DKV_THREADS, DQ1_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmO128, tmDqkv, p);
   attn_dkv_kernel<8><<<a.B * Hkv * (a.S / 128), 10 * 32, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
   return cudaGetLastError();

@@ -861,7 +861,8 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
   t->cur_S = tc->seq_len;
   t->cur_M = t->M;
   // Mistral-style sliding window: only a different mask once the sequence is longer than the window
-  t->window = (mc->sliding_window > 0 && mc->sliding_window < tc->seq_len) ? mc->sliding_window : 0;
+  // (transformers 4.34.0 _make_sliding_window_causal_mask: triu(diagonal=-sliding_window), i.e. query i sees keys i - sw .. i)
+  t->window = (mc->sliding_window > 0 && tc->seq_len > mc->sliding_window + 1) ? mc->sliding_window : 0;
   cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
   cudaEventCreate(&t->ev0);
   cudaEventCreate(&t->ev1);

@@ -35,12 +35,9 @@ def load_model_config(model_dir: str) -> ModelConfig:
 
 
 def check_attention_window(model_dir: str, seq_len: int) -> None:
-    """Mistral-style sliding-window attention equals plain causal attention while seq_len <= sliding_window (4096 for
-    Mistral-7B); longer sequences would need the windowed mask, which the native kernels do not implement."""
-    cfg = json.load(open(os.path.join(model_dir, "config.json")))
-    win = cfg.get("sliding_window")
-    if win is not None and seq_len > int(win):
-        raise ValueError(f"seq_len {seq_len} exceeds the model's sliding_window {win}: windowed attention is not implemented")
+    """Kept for callers of the r01 API: sliding-window attention (Mistral `sliding_window`) is implemented natively - the
+    window travels in ModelConfig.sliding_window and only changes the mask once seq_len exceeds it."""
+    return None
 
 
 def iter_safetensors(path: str) -> Iterator[Tuple[str, np.ndarray, bool]]:

@@ -46,6 +46,7 @@ class OracleConfig:
     n_heads: int = 2
     ffn: int = 768
     n_kv_heads: Optional[int] = None   # grouped-query attention when < n_heads (Mistral, Llama-2-70B)
+    sliding_window: int = 0            # Mistral: query i attends keys i - sliding_window .. i (transformers 4.34.0 mask); 0 = none
     head_dim: int = 128
     rms_eps: float = 1e-5
     rope_theta: float = 10000.0
@@ -178,11 +179,17 @@ def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.T
     return x * cos[None, None] + rotate_half(x) * sin[None, None]
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
-    # eager_attention_forward, modeling_llama.py:197-221: fp32 softmax(QK^T/sqrt(D) + causal) V
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window: int = 0) -> torch.Tensor:
+    # eager_attention_forward, modeling_llama.py:197-221: fp32 softmax(QK^T/sqrt(D) + causal) V.
+    # window > 0: Mistral sliding window as transformers 4.34.0 (the version the reference pins, requirements.txt:9) builds
+    # it - modeling_mistral.py _make_sliding_window_causal_mask: tril(diagonal=0) & triu(diagonal=-sliding_window), i.e. query
+    # i sees keys i - window .. i (window + 1 keys).  Newer transformers (5.x, installed here) use i - window < j: one key
+    # fewer; tests/test_oracle_pin.py pins this function against the installed version with window - 1.
     S, D = q.shape[-2], q.shape[-1]
     scores = q @ k.transpose(-1, -2) / math.sqrt(D)
     mask = torch.full((S, S), float("-inf")).triu(1)
+    if window > 0:
+        mask = mask + torch.full((S, S), float("-inf")).tril(-(window + 1))
     p = torch.softmax(scores + mask, dim=-1, dtype=torch.float32)
     return p @ v
 
@@ -255,7 +262,7 @@ def forward_logits(cfg: OracleConfig, w: Dict[str, torch.Tensor], lora: Dict[str
         if Hkv != H:  # HF repeat_kv: kv head i serves query heads i*g .. (i+1)*g-1
             k = k.repeat_interleave(H // Hkv, dim=1)
             v = v.repeat_interleave(H // Hkv, dim=1)
-        o = attention(q, k, v).transpose(1, 2).reshape(B, S, H * D)
+        o = attention(q, k, v, cfg.sliding_window if S > cfg.sliding_window + 1 else 0).transpose(1, 2).reshape(B, S, H * D)
         x = x + o @ w[p + "self_attn.o_proj.weight"].t()
         h = rmsnorm(x, w[p + "post_attention_layernorm.weight"], cfg.rms_eps)
         g = h @ w[p + "mlp.gate_proj.weight"].t()

@@ -348,7 +348,7 @@ def check_adamw(n=100003 * 4):
     return out
 
 
-def _attn_ref(qkv, B, S, H, D, Hkv=None):
+def _attn_ref(qkv, B, S, H, D, Hkv=None, window=0):
     Hkv = Hkv or H
     x = qkv.float().view(B, S, H + 2 * Hkv, D)
     q = x[:, :, :H].transpose(1, 2)
@@ -356,6 +356,8 @@ def _attn_ref(qkv, B, S, H, D, Hkv=None):
     v = x[:, :, H + Hkv:].transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
     scores = q @ k.transpose(-1, -2) / math.sqrt(D)
     mask = torch.full((S, S), float("-inf"), device=qkv.device).triu(1)
+    if window > 0:  # query i sees keys i - window .. i
+        mask = mask + torch.full((S, S), float("-inf"), device=qkv.device).tril(-(window + 1))
     p = torch.softmax(scores + mask, dim=-1)
     return (p @ v).transpose(1, 2).reshape(B * S, H * D), torch.logsumexp(scores + mask, dim=-1)
 
@@ -631,6 +633,59 @@ def check_attn_bwd_rope(B=2, S=384, H=4, Hkv=2):
     for n_, e in errs.items():
         assert e < 1.5e-2, f"attention backward with fused inverse rotary: {n_} {e}"
     return errs
+
+
+def check_attn_window(B=2, S=768, H=4, Hkv=2, windows=(1, 63, 64, 200, 511, 5000)):
+    """Sliding-window attention (Mistral): forward, lse and all three gradients against fp32 torch for windows smaller than a
+    block, block-aligned, straddling several blocks, and wider than the sequence (= plain causal)."""
+    lib = L.load()
+    D = 128
+    W = (H + 2 * Hkv) * D
+    qkv = _rand(B * S, W, seed=91)
+    dout = _rand(B * S, H * D, seed=92)
+    sc = 1.0 / math.sqrt(D)
+    res = {}
+    for win in windows:
+        out = torch.full((B * S, H * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+        lse2 = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
+        delta = torch.empty(B, H, S, dtype=torch.float32, device=DEV)
+        dqkv = torch.full((B * S, W), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ok(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, sc, None, win, STREAM()))
+        ok(lib.dtx_attn_bwd(P(qkv), P(out), P(dout), P(lse2), P(delta), P(dqkv), B, S, H, Hkv, sc, None, win, None, 0, STREAM()))
+        torch.cuda.synchronize()
+        x = qkv.float().requires_grad_(True)
+        ref, lse = _attn_ref(x, B, S, H, D, Hkv, window=win)
+        ref.backward(dout.float())
+        e_o, e_l, e_g = rel_err(out, ref), max_err(lse2 * math.log(2.0), lse.detach()), rel_err(dqkv, x.grad)
+        assert torch.isfinite(out.float()).all() and torch.isfinite(dqkv.float()).all(), f"window {win}: non-finite"
+        assert e_o < 8e-3 and e_l < 2e-3 and e_g < 1.5e-2, f"window {win}: out {e_o} lse {e_l} grad {e_g}"
+        res[f"w{win}"] = {"out": e_o, "lse": e_l, "grad": e_g}
+    return res
+
+
+def check_trainer_window(steps=4):
+    """Mistral-style model whose sliding_window is shorter than the sequence: native step == oracle (4.34.0 mask width)."""
+    ocfg, mc, tc = tiny_configs(S=512, B=2, steps=steps, heads=4, kv_heads=2)
+    ocfg.sliding_window = 150
+    mc.sliding_window = 150
+    w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
+    tr = L.Trainer(mc, tc)
+    tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+    tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+    orc = O.OracleTrainer(ocfg, w, lora)
+    plain = O.OracleTrainer(O.OracleConfig(**{**ocfg.__dict__, "sliding_window": 0}), w, lora)
+    worst_l = worst_g = 0.0
+    for s_ in range(steps):
+        ids, labels = O.synthetic_batch(s_, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)
+        ref = orc.step([(ids, labels)])
+        loss, gn, _, _ = tr.step(ids, labels)
+        worst_l, worst_g = max(worst_l, abs(loss - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
+    ids, labels = O.synthetic_batch(0, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)
+    shift = abs(plain.eval_loss(ids, labels) - O.OracleTrainer(ocfg, w, lora).eval_loss(ids, labels))
+    tr.close()
+    assert worst_l < 1e-3 and worst_g < 3e-2, (worst_l, worst_g)
+    assert shift > 1e-5, "the window must change the loss at this length"
+    return {"loss": worst_l, "gnorm": worst_g, "loss_shift_vs_causal": shift}
 
 
 def check_attn_varlen(B=4, S=640, H=4, Hkv=2, lens=(640, 1, 129, 300)):
@@ -1043,7 +1098,8 @@ ALL = {
     "gemm_swiglu_epilogues": check_gemm_swiglu_epilogues,
     "attn_bench_shape_s2048": check_attn_bench_shape,
     "attn_bench_shape_s4096_gqa": lambda: check_attn_bench_shape(B=1, S=4096, H=32, Hkv=8, kv_heads=(0, 5)),
-    "attn_bwd_rope": check_attn_bwd_rope, "attn_varlen": check_attn_varlen,
+    "attn_bwd_rope": check_attn_bwd_rope, "attn_varlen": check_attn_varlen, "attn_window": check_attn_window,
+    "trainer_window": check_trainer_window,
     "trainer_varlen": check_trainer_varlen, "eval_rows_force_step": check_eval_rows_and_force_step,
     "missing_weight_refused": check_missing_weight_is_refused, "layer_7b_shape": check_layer_7b_shape, "trainer_qlora": check_trainer_qlora, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),

@@ -27,12 +27,12 @@ def test_hbm_kernels(name):
 
 
 @pytest.mark.parametrize("name", ["attn_fwd", "attn_fwd_long", "attn_fwd_rescale", "attn_fwd_odd_tiles", "attn_fwd_exp_fma", "attn_bwd_single_tile", "attn_bwd", "attn_bwd_long",
-                                  "attn_gqa", "attn_bwd_rope", "attn_varlen", "attn_bench_shape_s2048", "attn_bench_shape_s4096_gqa"])
+                                  "attn_gqa", "attn_bwd_rope", "attn_varlen", "attn_window", "attn_bench_shape_s2048", "attn_bench_shape_s4096_gqa"])
 def test_attention(name):
     _run(name)
 
 
 @pytest.mark.parametrize("name", ["trainer_tiny", "trainer_gqa", "trainer_dropout", "trainer_qlora", "trainer_unfused", "trainer_deterministic", "trainer_grad_accum", "trainer_100_steps",
-                                  "trainer_varlen", "eval_rows_force_step", "missing_weight_refused", "layer_7b_shape", "worker_end_to_end"])
+                                  "trainer_varlen", "trainer_window", "eval_rows_force_step", "missing_weight_refused", "layer_7b_shape", "worker_end_to_end"])
 def test_training_step(name):
     _run(name)

@@ -153,3 +153,34 @@ def test_oracle_loss_decreases_and_is_deterministic():
     assert runs[0] == runs[1]
     assert runs[0][-1] < runs[0][0]
     assert abs(runs[0][0] - math.log(cfg.vocab)) < 0.2
+
+
+def test_oracle_sliding_window_matches_hf_mistral():
+    """Mistral sliding-window attention against the installed HF MistralForCausalLM.  The installed transformers (5.x) lets query
+    i see keys i - sw + 1 .. i; 4.34.0 - what the reference pins, cmd/tuning/requirements.txt:9 - builds
+    triu(diagonal=-sliding_window), one key more (i - sw .. i).  The oracle takes the 4.34.0 width as its parameter, so the
+    installed model with sliding_window = sw pins oracle.attention(window = sw - 1)."""
+    from transformers import MistralConfig, MistralForCausalLM
+    sw = 24
+    cfg = O.OracleConfig(vocab=512, hidden=512, n_layers=2, n_heads=4, n_kv_heads=2, ffn=384, lora_r=8, sliding_window=sw - 1)
+    w = O.init_base_weights(cfg, seed=27)
+    hc = MistralConfig(vocab_size=cfg.vocab, hidden_size=cfg.hidden, intermediate_size=cfg.ffn, num_hidden_layers=cfg.n_layers,
+                       num_attention_heads=cfg.n_heads, num_key_value_heads=cfg.n_kv_heads, head_dim=cfg.head_dim,
+                       max_position_embeddings=4096, rms_norm_eps=cfg.rms_eps, rope_theta=cfg.rope_theta, sliding_window=sw,
+                       tie_word_embeddings=False, attn_implementation="eager")
+    m = MistralForCausalLM(hc).float()
+    missing, unexpected = m.load_state_dict(w, strict=False)
+    assert not [k for k in missing if "rotary" not in k] and not unexpected
+    ids, _ = O.synthetic_batch(step=2, rank=0, batch=2, seq_len=96, vocab=cfg.vocab)
+    t_ids = torch.from_numpy(ids).long()
+    with torch.no_grad():
+        ref = m.eval()(input_ids=t_ids).logits.float()
+        got = O.forward_logits(cfg, w, {}, t_ids)
+        plain = O.forward_logits(O.OracleConfig(**{**cfg.__dict__, "sliding_window": 0}), w, {}, t_ids)
+    assert torch.allclose(got, ref, atol=3e-5, rtol=1e-4), float((got - ref).abs().max())
+    assert float((plain - ref).abs().max()) > 1e-3, "the window must matter at this length"
+    # the 4.34.0 width sees exactly one key more than the installed version
+    S = 8
+    q = torch.randn(1, 1, S, 16)
+    a = O.attention(q, q, torch.eye(S).view(1, 1, S, S), window=3)  # V = identity: the output row IS the probability row
+    assert [(a[0, 0, i] > 0).sum().item() for i in range(S)] == [min(i + 1, 4) for i in range(S)]
