@@ -1114,8 +1114,8 @@ cudaError_t set_smem(const void* fn, int bytes) {
 
 }  // namespace
 
-int g_fwd_exp_fma_every = 0;
-void attn_set_fwd_exp_fma_every(int n) { g_fwd_exp_fma_every = (n == 2 || n == 3 || n == 4) ? n : 0; }
+int g_fwd_exp_fma_every = 3;  // measured (profiles/r02_attn_events.txt): 330 us (0) / 301 (4) / 292 (3) / 294 (2) per layer at the 7B shape
+void attn_set_fwd_exp_fma_every(int n) { g_fwd_exp_fma_every = (n == 2 || n == 3 || n == 4) ? n : 0; }  // 0 = all on the MUFU
 int attn_bwd_launches() { return 2; }
 bool attn_bwd_can_rope() { return true; }
 

@@ -157,7 +157,7 @@ DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, 
  * 0: the single-CTA kernel everywhere (used for A/B measurements in profiles/).  "fused_epilogues" = 1 (default): RoPE and
  * SwiGLU run inside the GEMM / attention epilogues; 0: separate HBM-bound kernels.  "gemm_group_m": rasterisation group of the
  * CTA-pair GEMM in 256-row tiles (default 16).  "attn_fwd_exp_fma_every" = N in {0, 2, 3, 4}: every N-th pair of the forward
- * softmax's exponentials is computed on the FMA pipe (cubic polynomial) instead of MUFU.EX2 (0 = none).
+ * softmax's exponentials is computed on the FMA pipe (cubic polynomial) instead of MUFU.EX2 (default 3; 0 = none).
  * Unknown names return DTX_ERR_INVALID. */
 DTX_API int32_t dtx_set_option(const char* name, int32_t value);
 

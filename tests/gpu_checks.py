@@ -394,11 +394,11 @@ def check_attn_fwd_exp_fma():
     """Forward softmax with part of the exponentials on the FMA pipe (cubic polynomial, rel. error 7.5e-5): same parity bar."""
     out = {}
     try:
-        for every in (2, 3, 4):
+        for every in (0, 2, 4):  # 3 is the default every other forward check runs with
             L.set_option("attn_fwd_exp_fma_every", every)
             out[f"every{every}"] = {"s384": check_attn_fwd(B=2, S=384, H=4, Hkv=2), "rescale": check_attn_fwd(B=1, S=1024, H=2, growing=True)}
     finally:
-        L.set_option("attn_fwd_exp_fma_every", 0)
+        L.set_option("attn_fwd_exp_fma_every", 3)
     return out
 
 

@@ -41,7 +41,7 @@ def main(B=8, S=2048, H=32, Hkv=32):
             torch.cuda.synchronize()
             ts.append(ev[0].elapsed_time(ev[1]) * 1000)
         print(f"ATTN_TIMING fwd exp_fma_every={every}: {min(ts[1:]):.1f} us (runs {[round(t, 1) for t in ts]})", flush=True)
-    L.set_option("attn_fwd_exp_fma_every", int(os.environ.get("DTX_FWD_EXP_FMA", "0")))
+    L.set_option("attn_fwd_exp_fma_every", int(os.environ.get("DTX_FWD_EXP_FMA", "3")))
     for it in range(2):
         ev[0].record()
         L.check(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, sc, None, 0, st))
