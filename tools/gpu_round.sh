@@ -19,6 +19,11 @@ for s in $STEPS; do
     sanitizer) for c in gemm_nt gemm_kext rmsnorm cross_entropy adamw attn_fwd attn_bwd attn_varlen trainer_tiny; do
                  timeout 900 compute-sanitizer --tool racecheck --print-limit 5 python -m tests.gpu_checks $c > $OUT/racecheck_$c.log 2>&1; echo "$c rc=$?" >> $OUT/sanitizer_summary.txt; done
                timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python -m tests.gpu_checks attn_varlen trainer_varlen > $OUT/memcheck_varlen.log 2>&1; echo "memcheck_varlen rc=$?" >> $OUT/sanitizer_summary.txt;;
+    mgpu_check) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29541 tests/multi_gpu_check.py > $OUT/multi_gpu_check_n${NGPU:-2}.log 2>&1;;
+    bench_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus ${NGPU:-2} --steps 8 --warmup 3 > $OUT/bench_n${NGPU:-2}.json 2> $OUT/bench_n${NGPU:-2}.err;;
+    qlora_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29543 bench.py --config mistral7b_qlora --gpus ${NGPU:-2} --steps 5 --warmup 3 > $OUT/bench_qlora_n${NGPU:-2}.json 2> $OUT/bench_qlora_n${NGPU:-2}.err;;
+    jobs_tiny) timeout 600 python tools/concurrent_jobs.py --jobs ${NJOBS:-1} --gpus-per-job 2 --model tiny --steps 12 --out $OUT/concurrent_jobs_tiny.json > $OUT/concurrent_jobs_tiny.log 2>&1;;
+    jobs_7b) timeout 900 python tools/concurrent_jobs.py --jobs ${NJOBS:-4} --gpus-per-job 2 --model 7b --steps 8 --out $OUT/concurrent_jobs_7b.json > $OUT/concurrent_jobs_7b.log 2>&1;;
     parity7b) timeout 1200 python tools/parity_7b.py --steps 3 --out $OUT/parity_7b.json > $OUT/parity_7b.log 2>&1;;
     pytest) timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1;;
