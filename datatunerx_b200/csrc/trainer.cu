@@ -50,7 +50,9 @@ NcclApi* nccl_api() {
     tried = true;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
-      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      // RTLD_LOCAL: a host that imports PyTorch AFTER this call must still resolve ITS bundled NCCL's newer symbols - with
+      // RTLD_GLOBAL the system libnccl (2.27) shadowed them and `import torch` died with "undefined symbol: ncclDevCommCreate"
+      api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
       if (api.handle) break;
     }
     if (api.handle) {

@@ -210,6 +210,8 @@ class Trainer:
         self.model, self.train = model, train
         self._h = C.c_void_p()
         mc, tc = model.to_c(), train.to_c()
+        if world > 1:
+            preload_nccl()
         idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
         check(self.lib.dtx_trainer_create(C.byref(mc), C.byref(tc), device, rank, world, idbuf, C.byref(self._h)))
 
@@ -350,7 +352,31 @@ class Trainer:
         return int(self.lib.dtx_base_weight_bytes(self._h))
 
 
+_nccl_preloaded = False
+
+
+def preload_nccl() -> Optional[str]:
+    """libdtxtune dlopen()s "libnccl.so.2" by soname.  A Python host that later imports PyTorch (the tokenizer does) needs the
+    NCCL its wheel bundles (nvidia/nccl/lib/libnccl.so.2, newer than the system copy): the dynamic loader keeps ONE object per
+    soname, so whichever copy is loaded first serves both.  Loading the newest copy first keeps the process consistent."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return None
+    _nccl_preloaded = True
+    import sys
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return cand
+            except OSError:
+                pass
+    return None
+
+
 def nccl_unique_id() -> bytes:
+    preload_nccl()
     buf = C.create_string_buffer(128)
     check(load().dtx_get_nccl_unique_id(buf))
     return buf.raw
