@@ -712,6 +712,97 @@ __global__ void fill_const_kernel(bf16* __restrict__ p, long long n, float v) {
     p[i] = __float2bfloat16_rn(v);
 }
 
+// ------------------------------------------------------------------------------------------
+// full-parameter SFT: RMSNorm weight gradient, embedding gradient, sharded AdamW on bf16 gradients
+// ------------------------------------------------------------------------------------------
+constexpr int NDW_ROWBLOCKS = 64;
+// stage 1: block (cb, rb) sums columns [64*cb, +64) over its row range: 256 threads = 64 columns x 4 row lanes
+__global__ void __launch_bounds__(256) rmsnorm_dw_stage1(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                          const float* __restrict__ rstd, int M, int d, float* __restrict__ part) {
+  __shared__ float sh[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), lane_r = threadIdx.x >> 6;
+  const int rows_per = (M + NDW_ROWBLOCKS - 1) / NDW_ROWBLOCKS;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float acc = 0.f;
+  if (c < d)
+    for (int m = r0 + lane_r; m < r1; m += 4)
+      acc += __bfloat162float(dy[static_cast<size_t>(m) * d + c]) * __bfloat162float(x[static_cast<size_t>(m) * d + c]) * rstd[m];
+  sh[lane_r][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (lane_r == 0 && c < d) part[static_cast<size_t>(blockIdx.y) * d + c] = (sh[0][threadIdx.x] + sh[1][threadIdx.x]) + (sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+}
+__global__ void rmsnorm_dw_stage2(const float* __restrict__ part, int d, bf16* __restrict__ dw, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float s = 0.f;
+  for (int r = 0; r < NDW_ROWBLOCKS; ++r) s += part[static_cast<size_t>(r) * d + c];
+  if (accumulate) s += __bfloat162float(dw[c]);
+  dw[c] = __float2bfloat16_rn(s);
+}
+__global__ void embedding_bwd_kernel(const int32_t* __restrict__ ids, const bf16* __restrict__ dx, float* __restrict__ dE, int d, int vocab) {
+  const int m = blockIdx.x;
+  const int id = ids[m];
+  if (id < 0 || id >= vocab) return;
+  const bf16* src = dx + static_cast<size_t>(m) * d;
+  float* dst = dE + static_cast<size_t>(id) * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(dst + c, __bfloat162float(src[c]));
+}
+__global__ void add_f32_into_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n, int accumulate) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = src[i];
+    if (accumulate) v += __bfloat162float(dst[i]);
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void cast_bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
+__global__ void sumsq_bf16_stage1(const bf16* __restrict__ g, long long n, float* __restrict__ scratch) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = __bfloat162float(g[i]);
+    acc += v * v;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = acc;
+}
+__global__ void sumsq_acc_stage2(const float* __restrict__ scratch, int nblocks, float* __restrict__ out, int first) {
+  if (threadIdx.x == 0) {
+    double s = first ? 0.0 : static_cast<double>(*out);
+    for (int i = 0; i < nblocks; ++i) s += static_cast<double>(scratch[i]);
+    *out = static_cast<float>(s);
+  }
+}
+// torch.optim.AdamW + clip_grad_norm_ as adamw_kernel, on fp32 master weights with bf16 gradients; the bf16 working copy of the
+// weights is refreshed in the same pass (DeepSpeed bf16 optimizer semantics: fp32 master + state, bf16 model weights)
+__global__ void adamw_shard_kernel(AdamWShardArgs a) {
+  float gs = a.grad_scale;
+  if (a.sumsq) {
+    const float norm = sqrtf(*a.sumsq) * a.grad_scale;
+    if (a.grad_norm_out && blockIdx.x == 0 && threadIdx.x == 0) *a.grad_norm_out = norm;
+    if (a.max_grad_norm > 0.f) {
+      const float coef = a.max_grad_norm / (norm + 1e-6f);
+      if (coef < 1.f) gs *= coef;
+    }
+  }
+  const float step = a.lr / a.bias1;
+  const float rs2 = rsqrtf(a.bias2);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < a.n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float g = __bfloat162float(a.g[i]) * gs;
+    const float decay = (i >= a.nodecay_from) ? 1.f : 1.f - a.lr * a.weight_decay;
+    float p = a.master[i] * decay;
+    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+    p -= step * (m / (sqrtf(v) * rs2 + a.eps));
+    a.master[i] = p;
+    a.m[i] = m;
+    a.v[i] = v;
+    a.w[i] = __float2bfloat16_rn(p);
+  }
+}
+
 inline int grid_for(long long work, int block, int max_blocks = 148 * 16) {
   long long g = (work + block - 1) / block;
   if (g < 1) g = 1;
@@ -851,6 +942,35 @@ cudaError_t cast_f32_to_bf16_2d(const float* src, int64_t lds, bf16* dst, int64_
                                 int transpose, cudaStream_t s) {
   cast2d_kernel<<<grid_for(static_cast<long long>(rows) * cols, 256), 256, 0, s>>>(src, lds, dst, ldd, rows, cols, scale,
                                                                                   transpose);
+  return cudaGetLastError();
+}
+
+cudaError_t rmsnorm_dw(const bf16* dy, const bf16* x, const float* rstd, int M, int d, float* scratch, bf16* dw, int accumulate,
+                       cudaStream_t s) {
+  rmsnorm_dw_stage1<<<dim3((d + 63) / 64, NDW_ROWBLOCKS), 256, 0, s>>>(dy, x, rstd, M, d, scratch);
+  rmsnorm_dw_stage2<<<(d + 255) / 256, 256, 0, s>>>(scratch, d, dw, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t embedding_bwd(const int32_t* ids, const bf16* dx, float* dE32, int M, int d, int vocab, cudaStream_t s) {
+  embedding_bwd_kernel<<<M, 256, 0, s>>>(ids, dx, dE32, d, vocab);
+  return cudaGetLastError();
+}
+cudaError_t add_f32_into_bf16(const float* src, bf16* dst, int64_t n, int accumulate, cudaStream_t s) {
+  add_f32_into_bf16_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, dst, n, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t cast_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t s) {
+  cast_bf16_to_f32_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, dst, n);
+  return cudaGetLastError();
+}
+cudaError_t sumsq_bf16_acc(const bf16* g, int64_t n, float* scratch, float* out, int first, cudaStream_t s) {
+  sumsq_bf16_stage1<<<SUMSQ_BLOCKS, 256, 0, s>>>(g, n, scratch);
+  sumsq_acc_stage2<<<1, 32, 0, s>>>(scratch, SUMSQ_BLOCKS, out, first);
+  return cudaGetLastError();
+}
+cudaError_t adamw_shard_step(const AdamWShardArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  adamw_shard_kernel<<<grid_for(a.n, 256, 148 * 8), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 

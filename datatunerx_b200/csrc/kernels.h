@@ -149,6 +149,28 @@ cudaError_t nf4_dequant_bf16(const uint8_t* q, const float* absmax, bf16* w, int
 // per sequence: row_sum[b] = sum of row_loss over the S tokens of sequence b, row_valid[b] = tokens with a label >= 0
 cudaError_t row_loss_stats(const float* row_loss, const int32_t* shifted_labels, int B, int S, float* row_sum, int32_t* row_valid,
                            cudaStream_t s);
+// ---- full-parameter SFT (BASELINE.json configs[3]) ----
+// RMSNorm weight gradient: dw[c] (+)= sum_m dy[m,c] * x[m,c] * rstd[m]   (two-stage, fixed order; scratch >= 64 * d floats)
+cudaError_t rmsnorm_dw(const bf16* dy, const bf16* x, const float* rstd, int M, int d, float* scratch, bf16* dw, int accumulate,
+                       cudaStream_t s);
+// embedding gradient: dE32[ids[m], :] += dx[m, :]  (fp32 atomics: the one reduction of the step whose order is not fixed)
+cudaError_t embedding_bwd(const int32_t* ids, const bf16* dx, float* dE32, int M, int d, int vocab, cudaStream_t s);
+// dst[i] = (accumulate ? dst[i] : 0) + src[i]   fp32 -> bf16
+cudaError_t add_f32_into_bf16(const float* src, bf16* dst, int64_t n, int accumulate, cudaStream_t s);
+// *out (+)= sum g[i]^2 over a bf16 buffer (two-stage, fixed order; first = 1 overwrites)
+cudaError_t sumsq_bf16_acc(const bf16* g, int64_t n, float* scratch, float* out, int first, cudaStream_t s);
+cudaError_t cast_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t s);
+// AdamW on a shard of fp32 master weights fed by bf16 gradients; writes the updated weights back as bf16.
+// Elements with index >= nodecay_from (RMSNorm weights at the end of a layer block) get no weight decay.
+struct AdamWShardArgs {
+  float* master; float* m; float* v; const bf16* g; bf16* w; int64_t n; int64_t nodecay_from;
+  float lr, beta1, beta2, eps, weight_decay, bias1, bias2, grad_scale;
+  const float* sumsq;  // device: sum of squares of the unscaled global gradient
+  float max_grad_norm;
+  float* grad_norm_out;
+};
+cudaError_t adamw_shard_step(const AdamWShardArgs& a, cudaStream_t s);
+
 cudaError_t fill_normal_bf16(bf16* p, int64_t n, float std, uint64_t seed, cudaStream_t s);
 cudaError_t fill_const_bf16(bf16* p, int64_t n, float v, cudaStream_t s);
 

@@ -40,6 +40,8 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, UidByValue, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;  // (send, recv, recvcount, dtype, op, comm, stream)
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;           // (send, recv, sendcount, dtype, comm, stream)
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -60,6 +62,9 @@ NcclApi* nccl_api() {
       api.CommInitRank = reinterpret_cast<int (*)(void**, int, UidByValue, int)>(dlsym(api.handle, "ncclCommInitRank"));
       api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
           dlsym(api.handle, "ncclAllReduce"));
+      api.ReduceScatter = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
+          dlsym(api.handle, "ncclReduceScatter"));
+      api.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(api.handle, "ncclAllGather"));
       api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.handle, "ncclCommDestroy"));
       api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.handle, "ncclGetErrorString"));
     }
@@ -69,6 +74,7 @@ NcclApi* nccl_api() {
 }
 constexpr int kNcclFloat32 = 7;
 constexpr int kNcclFloat64 = 8;
+constexpr int kNcclBfloat16 = 9;
 constexpr int kNcclSum = 0;
 
 thread_local std::string g_error;
@@ -191,6 +197,22 @@ struct dtx_trainer {
   int32_t* d_row_valid = nullptr; // [micro_batch] per-row valid-token count
   double* d_host_red = nullptr;   // staging for dtx_allreduce_host
   int window = 0;                 // sliding-window attention span (0 = plain causal)
+  // ---- full-parameter SFT (train.full_finetune): every weight trains, no adapters (BASELINE.json configs[3]) ----
+  // Weights live in ONE flat bf16 buffer - L layer blocks [wqkv | wo | wgu | wdown | norm1 | norm2] then a globals block
+  // [embed | lm_head | final norm], each padded to a multiple of world * 128 elements - with a gradient buffer of the same
+  // layout.  Rank r owns elements [r, r + 1) * block / world of every block: the block's bf16 gradients are reduce-scattered
+  // in place (NCCL, on a side stream, as soon as the backward pass has finished the layer), the fp32 master weights and Adam
+  // moments exist for the owned slices only (ZeRO-1 style), and the updated bf16 slices are all-gathered in place.
+  bool full = false;
+  int64_t layer_elems = 0, glob_elems = 0;
+  int64_t off_wo = 0, off_wgu = 0, off_wdown = 0, off_n1 = 0, off_n2 = 0, goff_lm = 0, goff_nf = 0, layer_used = 0, glob_used = 0;
+  bf16 *w_flat = nullptr, *g_flat = nullptr;
+  float *master = nullptr, *fm = nullptr, *fv = nullptr, *embed_g32 = nullptr, *ndw_scratch = nullptr;
+  bool master_valid = false;
+  bool rs_now = false;  // this backward pass ends an accumulation group: finished layers go to the reduce-scatter stream
+  cudaStream_t comm_stream = nullptr;
+  std::vector<cudaEvent_t> ev_layer;
+  cudaEvent_t ev_comm = nullptr;
   bool quant4 = false;
   bf16* scratch_w[4] = {nullptr, nullptr, nullptr, nullptr};  // dequantised wqkv / wo / wgu / wdown of the layer in flight
   int64_t base_bytes = 0;
@@ -303,11 +325,43 @@ int create_buffers(dtx_trainer* t) {
   const dtx_train_cfg& tc = t->tc;
   const size_t d = mc.hidden, F = mc.ffn, V = mc.vocab, L = mc.n_layers, M = t->M, RP = t->RP, W = t->W, KA = t->KA;
   bool ok = true;
-  ok = ok && t->alloc(&t->embed, V * d) && t->alloc(&t->lm_head, V * d) && t->alloc(&t->normf, d);
-  ok = ok && t->alloc(&t->a_cat_all, L * RP * KA) && t->alloc(&t->b_ext_all, L * W * RP);
-  if (!ok) return DTX_ERR_CUDA;
-  CKM(cudaMemset(t->a_cat_all, 0, L * RP * KA * sizeof(bf16)));
-  CKM(cudaMemset(t->b_ext_all, 0, L * W * RP * sizeof(bf16)));
+  const bool full = t->full;
+  if (full) {
+    // one flat weight buffer + one flat gradient buffer; every block padded so that it splits evenly over the ranks
+    const size_t unit = static_cast<size_t>(t->world) * 128;
+    auto pad = [&](size_t n) { return (n + unit - 1) / unit * unit; };
+    t->off_wo = W * d;
+    t->off_wgu = t->off_wo + d * d;
+    t->off_wdown = t->off_wgu + 2 * F * d;
+    t->off_n1 = t->off_wdown + d * F;
+    t->off_n2 = t->off_n1 + d;
+    t->layer_used = t->off_n2 + d;
+    t->layer_elems = pad(t->layer_used);
+    t->goff_lm = V * d;
+    t->goff_nf = 2 * V * d;
+    t->glob_used = 2 * V * d + d;
+    t->glob_elems = pad(t->glob_used);
+    const size_t total = L * t->layer_elems + t->glob_elems, shard = total / t->world;
+    ok = ok && t->alloc(&t->w_flat, total) && t->alloc(&t->g_flat, total);
+    ok = ok && t->alloc(&t->master, shard) && t->alloc(&t->fm, shard) && t->alloc(&t->fv, shard);
+    ok = ok && t->alloc(&t->embed_g32, V * d) && t->alloc(&t->ndw_scratch, 64 * d);
+    if (!ok) return DTX_ERR_CUDA;
+    CKM(cudaMemset(t->w_flat, 0, total * sizeof(bf16)));
+    CKM(cudaMemset(t->g_flat, 0, total * sizeof(bf16)));
+    CKM(cudaMemset(t->fm, 0, shard * sizeof(float)));
+    CKM(cudaMemset(t->fv, 0, shard * sizeof(float)));
+    bf16* gl = t->w_flat + L * t->layer_elems;
+    t->embed = gl;
+    t->lm_head = gl + t->goff_lm;
+    t->normf = gl + t->goff_nf;
+    t->n_train = static_cast<int64_t>(L * t->layer_used + t->glob_used);
+  } else {
+    ok = ok && t->alloc(&t->embed, V * d) && t->alloc(&t->lm_head, V * d) && t->alloc(&t->normf, d);
+    ok = ok && t->alloc(&t->a_cat_all, L * RP * KA) && t->alloc(&t->b_ext_all, L * W * RP);
+    if (!ok) return DTX_ERR_CUDA;
+    CKM(cudaMemset(t->a_cat_all, 0, L * RP * KA * sizeof(bf16)));
+    CKM(cudaMemset(t->b_ext_all, 0, L * W * RP * sizeof(bf16)));
+  }
   t->base_bytes = static_cast<int64_t>((2 * V * d + d) * sizeof(bf16));
   t->loaded.assign(3 + 9 * L, 0);
   t->layers.resize(L);
@@ -315,35 +369,45 @@ int create_buffers(dtx_trainer* t) {
   for (size_t l = 0; l <= L; ++l) ok = ok && t->alloc(&t->xs[l], M * d);
   for (size_t l = 0; l < L && ok; ++l) {
     Layer& y = t->layers[l];
-    ok = ok && t->alloc(&y.wqkv, W * d) && t->alloc(&y.wo, d * d) && t->alloc(&y.wgu, 2 * F * d) &&
-         t->alloc(&y.wdown, d * F) && t->alloc(&y.norm1, d) && t->alloc(&y.norm2, d);
+    if (full) {
+      bf16* blk = t->w_flat + l * t->layer_elems;
+      y.wqkv = blk; y.wo = blk + t->off_wo; y.wgu = blk + t->off_wgu; y.wdown = blk + t->off_wdown;
+      y.norm1 = blk + t->off_n1; y.norm2 = blk + t->off_n2;
+    } else {
+      ok = ok && t->alloc(&y.wqkv, W * d) && t->alloc(&y.wo, d * d) && t->alloc(&y.wgu, 2 * F * d) &&
+           t->alloc(&y.wdown, d * F) && t->alloc(&y.norm1, d) && t->alloc(&y.norm2, d);
+      y.a_cat = t->a_cat_all + l * RP * KA;
+      y.b_ext = t->b_ext_all + l * W * RP;
+      ok = ok && t->alloc(&y.t, M * RP);
+    }
     t->base_bytes += static_cast<int64_t>((W * d + d * d + 3 * F * d + 2 * d) * sizeof(bf16));
-    y.a_cat = t->a_cat_all + l * RP * KA;
-    y.b_ext = t->b_ext_all + l * W * RP;
-    ok = ok && t->alloc(&y.h1, M * d) && t->alloc(&y.t, M * RP) && t->alloc(&y.qkv, M * W) &&
+    ok = ok && t->alloc(&y.h1, M * d) && t->alloc(&y.qkv, M * W) &&
          t->alloc(&y.attn, M * d) && t->alloc(&y.x_mid, M * d) && t->alloc(&y.gu, M * 2 * F);
     if (t->dropout) ok = ok && t->alloc(&y.hd, M * KA);
     ok = ok && t->alloc(&y.lse, static_cast<size_t>(tc.micro_batch) * mc.n_heads * tc.seq_len) && t->alloc(&y.rstd1, M) &&
          t->alloc(&y.rstd2, M);
   }
   if (!ok) return DTX_ERR_CUDA;
-  ok = ok && t->alloc(&t->params, t->n_train) && t->alloc(&t->grads, t->n_train) && t->alloc(&t->adam_m, t->n_train) &&
-       t->alloc(&t->adam_v, t->n_train);
-  if (!ok) return DTX_ERR_CUDA;
-  CKM(cudaMemset(t->params, 0, t->n_train * sizeof(float)));
-  CKM(cudaMemset(t->grads, 0, t->n_train * sizeof(float)));
-  CKM(cudaMemset(t->adam_m, 0, t->n_train * sizeof(float)));
-  CKM(cudaMemset(t->adam_v, 0, t->n_train * sizeof(float)));
+  if (!full) {
+    ok = ok && t->alloc(&t->params, t->n_train) && t->alloc(&t->grads, t->n_train) && t->alloc(&t->adam_m, t->n_train) &&
+         t->alloc(&t->adam_v, t->n_train);
+    if (!ok) return DTX_ERR_CUDA;
+    CKM(cudaMemset(t->params, 0, t->n_train * sizeof(float)));
+    CKM(cudaMemset(t->grads, 0, t->n_train * sizeof(float)));
+    CKM(cudaMemset(t->adam_m, 0, t->n_train * sizeof(float)));
+    CKM(cudaMemset(t->adam_v, 0, t->n_train * sizeof(float)));
+  }
   ok = ok && t->alloc(&t->h2, M * d) && t->alloc(&t->act, M * F) && t->alloc(&t->dact, M * F) && t->alloc(&t->dgu, M * 2 * F) &&
        t->alloc(&t->dx_a, M * d) && t->alloc(&t->dx_b, M * d) && t->alloc(&t->dh, M * d) && t->alloc(&t->dattn, M * d) &&
-       t->alloc(&t->dqkv, M * W) && t->alloc(&t->dt, M * RP) && t->alloc(&t->dlogits, M * V) && t->alloc(&t->logits, M * V) &&
+       t->alloc(&t->dqkv, M * W) && (full || t->alloc(&t->dt, M * RP)) && t->alloc(&t->dlogits, M * V) && t->alloc(&t->logits, M * V) &&
        t->alloc(&t->rstdf, M) && t->alloc(&t->row_loss, M) &&
        t->alloc(&t->delta, static_cast<size_t>(tc.micro_batch) * mc.n_heads * tc.seq_len);
   const int kb_tok = (static_cast<int>(M) + 63) / 64;
   t->split_b = pick_split((static_cast<int>(W) + 127) / 128, kb_tok);
   t->split_a = pick_split((static_cast<int>(KA) + 127) / 128, kb_tok);
-  ok = ok && t->alloc(&t->part_b, static_cast<size_t>(t->split_b) * W * RP) &&
-       t->alloc(&t->part_a, static_cast<size_t>(t->split_a) * KA * RP);
+  if (!full)
+    ok = ok && t->alloc(&t->part_b, static_cast<size_t>(t->split_b) * W * RP) &&
+         t->alloc(&t->part_a, static_cast<size_t>(t->split_a) * KA * RP);
   if (t->dropout) ok = ok && t->alloc(&t->glora, M * KA);
   ok = ok && t->alloc(&t->d_loss, 4) && t->alloc(&t->d_sumsq, 4) && t->alloc(&t->d_gnorm, 4) && t->alloc(&t->d_scratch, 1024);
   ok = ok && t->alloc(&t->d_ids, M) && t->alloc(&t->d_labels, M) && t->alloc(&t->d_shift, M) && t->alloc(&t->d_nvalid, 4);
@@ -421,6 +485,22 @@ int base_weight(dtx_trainer* t, Layer& y, int which, const bf16** out) {
     if (_rc) return _rc;                            \
   } while (0)
 
+// full-parameter SFT, world > 1: reduce-scatter one gradient block in place on the side stream once the main stream has
+// produced it (event), so that the transfer overlaps the rest of the backward pass
+int reduce_scatter_block(dtx_trainer* t, bf16* block, int64_t elems, int ev_idx) {
+  NcclApi* api = nccl_api();
+  if (!api || !api->ReduceScatter || !t->nccl_comm) return t->fail(DTX_ERR_NCCL, "ncclReduceScatter unavailable for world=%d", t->world);
+  cudaEvent_t ev = t->ev_layer[ev_idx];
+  CKM(cudaEventRecord(ev, t->stream));
+  CKM(cudaStreamWaitEvent(t->comm_stream, ev, 0));
+  const int64_t shard = elems / t->world;
+  int rc = api->ReduceScatter(block, block + static_cast<int64_t>(t->rank) * shard, static_cast<size_t>(shard), kNcclBfloat16, kNcclSum,
+                              t->nccl_comm, t->comm_stream);
+  if (rc != 0) return t->fail(DTX_ERR_NCCL, "ncclReduceScatter failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
+  t->launches += 1;
+  return DTX_OK;
+}
+
 // forward (+ backward) of one micro-batch whose ids / labels (/ row lengths) are already in t->d_ids / t->d_labels (/ t->d_seq_lens).
 // The batch is [micro_batch, cur_S]: cur_S <= seq_len is this batch's own padded length (DataCollatorForSeq2Seq pads to the
 // longest row of the batch, cmd/tuning/train.py:282-286); every buffer was sized for seq_len.
@@ -437,7 +517,8 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   cudaStream_t s = t->stream;
   const float att_scale = 1.0f / sqrtf(static_cast<float>(D));
   const bool fused = g_fused_epilogues && M > 128 && ((t->dq + t->dkv) % 256 == 0) && (W % 256 == 0);  // whole 256-column tiles
-  const bool drop = t->dropout;  // adapters laid out for per-target dropped inputs (KA = nt*d)
+  const bool lora = !t->full;    // full-parameter SFT: no adapters, every weight gets a gradient
+  const bool drop = lora && t->dropout;  // adapters laid out for per-target dropped inputs (KA = nt*d)
   const float p_drop = backward ? tc.lora_dropout : 0.f;  // eval (model.eval()) runs the same path with p = 0
   t->fwd_count += 1;
 
@@ -450,7 +531,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       CK(lora_dropout_fwd(y.h1, y.hd, M, d, t->nt, p_drop, dropout_key(t, l), s), 1);
       lora_in = y.hd;
     }
-    {  // LoRA down-projection of all targets at once: t = lora_in * A_cat^T   [M, RP]
+    if (lora) {  // LoRA down-projection of all targets at once: t = lora_in * A_cat^T   [M, RP]
       GemmArgs g;
       g.A = lora_in; g.lda = t->KA; g.B = y.a_cat; g.ldb = t->KA; g.C = y.t; g.ldc = RP;
       g.M = M; g.N = RP; g.K = t->KA; g.epilogue = EPI_BF16; g.block_n = 64;
@@ -460,7 +541,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       BASEW(W_QKV, wqkv);
       GemmArgs g;
       g.A = y.h1; g.lda = d; g.B = wqkv; g.ldb = d;
-      g.A2 = y.t; g.lda2 = RP; g.B2 = y.b_ext; g.ldb2 = RP; g.K2 = RP;
+      if (lora) { g.A2 = y.t; g.lda2 = RP; g.B2 = y.b_ext; g.ldb2 = RP; g.K2 = RP; }
       g.C = y.qkv; g.ldc = W; g.M = M; g.N = W; g.K = d; g.epilogue = EPI_BF16;
       if (fused) {  // rotary embedding of q and k applied to the fp32 accumulator in the epilogue
         g.epilogue = EPI_ROPE; g.rope_cs = t->rope_cs; g.rope_S = S; g.rope_cols = t->dq + t->dkv;
@@ -505,32 +586,54 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   // (27 % of the synthetic batch, far more on real instruction data) have zero loss and zero gradient.  The labelled rows
   // are compacted by the final norm (row map from an ordered scan inside shift_labels), the two lm_head GEMMs take the row
   // count from device memory and skip the dead 256-row tiles, the norm backward scatters the gradient back.
-  CK(shift_labels(t->d_labels, t->d_shift, t->d_nvalid, B, S, s, t->d_row_map, t->d_valid_idx), 1);
-  CK(rmsnorm_fwd(t->xs[L], t->normf, t->h2, t->rstdf, M, d, mc.rms_eps, s, t->d_row_map), 1);
+  // (full-parameter SFT keeps every row: the lm_head weight gradient contracts over tokens, and its operands must then be zero
+  // - not stale - on the unlabelled rows)
+  int32_t* row_map = lora ? t->d_row_map : nullptr;
+  int32_t* valid_idx = lora ? t->d_valid_idx : nullptr;
+  const int32_t* m_eff = lora ? t->d_nvalid : nullptr;
+  CK(shift_labels(t->d_labels, t->d_shift, t->d_nvalid, B, S, s, row_map, valid_idx), 1);
+  CK(rmsnorm_fwd(t->xs[L], t->normf, t->h2, t->rstdf, M, d, mc.rms_eps, s, row_map), 1);
   {  // fp32 logits (the reference patches lm_head to return fp32: cmd/tuning/train.py:256-264)
     GemmArgs g;
     g.A = t->h2; g.lda = d; g.B = t->lm_head; g.ldb = d; g.C = t->logits; g.ldc = V;
-    g.M = M; g.N = V; g.K = d; g.epilogue = EPI_F32; g.m_eff = t->d_nvalid;
+    g.M = M; g.N = V; g.K = d; g.epilogue = EPI_F32; g.m_eff = m_eff;
     CK(gemm_bf16(g, s), 1);
   }
   CKM(cudaMemsetAsync(t->row_loss, 0, static_cast<size_t>(M) * sizeof(float), s));
-  CK(cross_entropy_fwd_bwd(t->logits, V, t->d_shift, t->d_nvalid, t->row_loss, backward ? t->dlogits : nullptr, V, M, V, s,
-                           t->d_valid_idx), 1);
+  CK(cross_entropy_fwd_bwd(t->logits, V, t->d_shift, t->d_nvalid, t->row_loss, backward ? t->dlogits : nullptr, V, M, V, s, valid_idx), 1);
   CK(loss_reduce(t->row_loss, t->d_nvalid, t->d_loss, M, s), 1);
   if (!backward) return DTX_OK;
 
-  {  // d h_f = dlogits * W_lm  (compact rows)
+  const int accumulate = t->micro_idx > 0 ? 1 : 0;
+  // weight gradient of a Linear: dW[out, in] (+)= dY^T X - a token-contraction GEMM with both operands MN-major
+  auto dw_gemm = [&](const bf16* dY, int n_out, const bf16* X, int n_in, bf16* dW) -> cudaError_t {
+    GemmArgs g;
+    g.A = dY; g.lda = n_out; g.a_mn_major = 1; g.B = X; g.ldb = n_in; g.b_mn_major = 1;
+    g.C = dW; g.ldc = n_in; g.M = n_out; g.N = n_in; g.K = M;
+    g.epilogue = accumulate ? EPI_BF16_ADD : EPI_BF16; g.R = accumulate ? dW : nullptr; g.ldr = n_in;
+    return gemm_bf16(g, s);
+  };
+  bf16* gglob = t->full ? t->g_flat + static_cast<int64_t>(L) * t->layer_elems : nullptr;
+  if (t->full) {  // lm_head weight gradient (h2 still holds the final-norm output) and the final norm's weight gradient
+    CK(dw_gemm(t->dlogits, V, t->h2, d, gglob + t->goff_lm), 1);
+  }
+  {  // d h_f = dlogits * W_lm  (compact rows in LoRA mode)
     GemmArgs g;
     g.A = t->dlogits; g.lda = V; g.B = t->lm_head; g.ldb = d; g.b_mn_major = 1; g.C = t->dh; g.ldc = d;
-    g.M = M; g.N = d; g.K = V; g.epilogue = EPI_BF16; g.m_eff = t->d_nvalid;
+    g.M = M; g.N = d; g.K = V; g.epilogue = EPI_BF16; g.m_eff = m_eff;
     CK(gemm_bf16(g, s), 1);
   }
-  CK(rmsnorm_bwd(t->dh, t->xs[L], t->normf, t->rstdf, nullptr, t->dx_a, M, d, s, t->d_row_map), 1);
+  if (t->full) CK(rmsnorm_dw(t->dh, t->xs[L], t->rstdf, M, d, t->ndw_scratch, gglob + t->goff_nf, accumulate, s), 2);
+  CK(rmsnorm_bwd(t->dh, t->xs[L], t->normf, t->rstdf, nullptr, t->dx_a, M, d, s, row_map), 1);
   bf16* cur = t->dx_a;
   bf16* other = t->dx_b;
-  const int accumulate = t->micro_idx > 0 ? 1 : 0;
   for (int l = L - 1; l >= 0; --l) {
     Layer& y = t->layers[l];
+    bf16* gl_w = t->full ? t->g_flat + static_cast<int64_t>(l) * t->layer_elems : nullptr;  // this layer's gradient block
+    if (t->full) {  // dWdown = d x_out^T * act: act = silu(gate) * up is recomputed from the saved gate|up (one HBM-bound pass)
+      CK(swiglu_fwd(y.gu, t->act, M, F, 1, s), 1);
+      CK(dw_gemm(cur, d, t->act, F, gl_w + t->off_wdown), 1);
+    }
     {  // dact = dx * Wdown ; fused: d[gate|up] straight from the accumulator, dact never touches HBM
       BASEW(W_DOWN, wdown);
       GemmArgs g;
@@ -549,6 +652,11 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       g.M = M; g.N = d; g.K = 2 * F; g.epilogue = EPI_BF16;
       CK(gemm_bf16(g, s), 1);
     }
+    if (t->full) {  // dWgu = d[gate|up]^T * h2 (h2 = norm2(x_mid) recomputed) and the norm's own weight gradient
+      CK(rmsnorm_fwd(y.x_mid, y.norm2, t->h2, nullptr, M, d, mc.rms_eps, s), 1);
+      CK(dw_gemm(t->dgu, 2 * F, t->h2, d, gl_w + t->off_wgu), 1);
+      CK(rmsnorm_dw(t->dh, y.x_mid, y.rstd2, M, d, t->ndw_scratch, gl_w + t->off_n2, accumulate, s), 2);
+    }
     CK(rmsnorm_bwd(t->dh, y.x_mid, y.norm2, y.rstd2, cur, other, M, d, s), 1);  // other = d x_mid
     {  // dattn = dx_mid * Wo
       BASEW(W_O, wo);
@@ -557,6 +665,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       g.M = M; g.N = d; g.K = d; g.epilogue = EPI_BF16;
       CK(gemm_bf16(g, s), 1);
     }
+    if (t->full) CK(dw_gemm(other, d, y.attn, d, gl_w + t->off_wo), 1);  // dWo = d x_mid^T * attn
     {
       AttnArgs a;
       a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.Hkv = Hkv; a.scale = att_scale;
@@ -570,29 +679,32 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       CK(attn_bwd(a, s), attn_bwd_launches());
       if (!rope_in_attn) CK(rope_qk_inplace_table(t->dqkv, t->rope_cs, B, S, H + Hkv, W, D, 1, s), 1);
     }
-    {  // dt = dqkv * B_ext   [M, RP]
+    if (lora) {  // dt = dqkv * B_ext   [M, RP]
       GemmArgs g;
       g.A = t->dqkv; g.lda = W; g.B = y.b_ext; g.ldb = RP; g.b_mn_major = 1; g.C = t->dt; g.ldc = RP;
       g.M = M; g.N = RP; g.K = W; g.epilogue = EPI_BF16; g.block_n = 64;
       CK(gemm_bf16(g, s), 1);
     }
-    // Layer 0's input gradient has no consumer (the embedding is frozen): its dh1 GEMM, the dropout-branch
-    // gradient and the norm-1 backward are skipped.
-    if (l > 0) {  // dh1 = dqkv * Wqkv (+ dt * A_cat in the same accumulator when there is no dropout between h1 and A)
+    if (t->full) CK(dw_gemm(t->dqkv, W, y.h1, d, gl_w), 1);  // dWqkv = dqkv^T * h1 (dqkv already carries the inverse rotary)
+    // LoRA: layer 0's input gradient has no consumer (the embedding is frozen): its dh1 GEMM, the dropout-branch
+    // gradient and the norm-1 backward are skipped.  Full-parameter SFT trains the embedding and needs them.
+    const bool need_dx = l > 0 || t->full;
+    if (need_dx) {  // dh1 = dqkv * Wqkv (+ dt * A_cat in the same accumulator when there is no dropout between h1 and A)
       BASEW(W_QKV, wqkv);
       GemmArgs g;
       g.A = t->dqkv; g.lda = W; g.B = wqkv; g.ldb = d; g.b_mn_major = 1;
-      if (!drop) { g.A2 = t->dt; g.lda2 = RP; g.B2 = y.a_cat; g.ldb2 = t->KA; g.K2 = RP; }
+      if (lora && !drop) { g.A2 = t->dt; g.lda2 = RP; g.B2 = y.a_cat; g.ldb2 = t->KA; g.K2 = RP; }
       g.C = t->dh; g.ldc = d; g.M = M; g.N = d; g.K = W; g.epilogue = EPI_BF16;
       CK(gemm_bf16(g, s), 1);
     }
-    if (drop && l > 0) {  // dh1 += sum_t mask_t o (dt_t * A_t) / (1 - p): the masks are regenerated from the counter-based RNG
+    if (drop && need_dx) {  // dh1 += sum_t mask_t o (dt_t * A_t) / (1 - p): the masks are regenerated from the counter-based RNG
       GemmArgs g;
       g.A = t->dt; g.lda = RP; g.B = y.a_cat; g.ldb = t->KA; g.b_mn_major = 1; g.C = t->glora; g.ldc = t->KA;
       g.M = M; g.N = t->KA; g.K = RP; g.epilogue = EPI_BF16;
       CK(gemm_bf16(g, s), 1);
       CK(lora_dropout_bwd_add(t->dh, t->glora, M, d, t->nt, p_drop, dropout_key(t, l), s), 1);
     }
+    if (lora) {
     {  // grad of B_ext (all rows): dqkv^T * t   [W, RP], split over tokens
       GemmArgs g;
       g.A = t->dqkv; g.lda = W; g.a_mn_major = 1; g.B = y.t; g.ldb = RP; g.b_mn_major = 1;
@@ -619,7 +731,19 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
                                                                 accumulate, tc.lora_alpha / static_cast<float>(r));
       CK(cudaGetLastError(), 2);
     }
-    if (l > 0) CK(rmsnorm_bwd(t->dh, t->xs[l], y.norm1, y.rstd1, other, cur, M, d, s), 1);  // cur = d x_in
+    }  // lora
+    if (t->full) CK(rmsnorm_dw(t->dh, t->xs[l], y.rstd1, M, d, t->ndw_scratch, gl_w + t->off_n1, accumulate, s), 2);
+    if (need_dx) CK(rmsnorm_bwd(t->dh, t->xs[l], y.norm1, y.rstd1, other, cur, M, d, s), 1);  // cur = d x_in
+    if (t->full && t->rs_now && t->world > 1) {  // this layer's gradients are final: reduce-scatter them while the backward pass goes on
+      int rc = reduce_scatter_block(t, gl_w, t->layer_elems, l);
+      if (rc) return rc;
+    }
+  }
+  if (t->full) {  // embedding gradient: rows of d x_0 scattered by token id (fp32 atomics), then folded into the bf16 gradient block
+    const size_t vd = static_cast<size_t>(V) * d;
+    CKM(cudaMemsetAsync(t->embed_g32, 0, vd * sizeof(float), s));
+    CK(embedding_bwd(t->d_ids, cur, t->embed_g32, M, d, V, s), 1);
+    CK(add_f32_into_bf16(t->embed_g32, gglob, static_cast<int64_t>(vd), accumulate, s), 1);
   }
   return DTX_OK;
 }
@@ -655,6 +779,88 @@ int optimizer_step(dtx_trainer* t, float* lr_used) {
   return DTX_OK;
 }
 
+// Full-parameter SFT: the blocks' bf16 gradients have been (or are now) reduce-scattered in place; every rank then runs
+// clip + AdamW on the slices it owns (fp32 master weights + moments, ZeRO-1 style) and the updated bf16 slices are
+// all-gathered in place.  HF's no-decay set (RMSNorm weights) sits at the end of every block.
+int optimizer_step_full(dtx_trainer* t, float* lr_used) {
+  const dtx_train_cfg& tc = t->tc;
+  cudaStream_t s = t->stream;
+  const int L = t->mc.n_layers, N = t->world;
+  NcclApi* api = N > 1 ? nccl_api() : nullptr;
+  if (N > 1 && (!api || !api->ReduceScatter || !api->AllGather || !t->nccl_comm))
+    return t->fail(DTX_ERR_NCCL, "NCCL reduce-scatter / all-gather unavailable for world=%d", N);
+  bf16* gglob = t->g_flat + static_cast<int64_t>(L) * t->layer_elems;
+  if (N > 1) {
+    if (!t->rs_now)  // gradients of earlier micro-batches only: nothing was sent during the backward pass
+      for (int l = L - 1; l >= 0; --l) {
+        int rc = reduce_scatter_block(t, t->g_flat + static_cast<int64_t>(l) * t->layer_elems, t->layer_elems, l);
+        if (rc) return rc;
+      }
+    int rc = reduce_scatter_block(t, gglob, t->glob_elems, L);
+    if (rc) return rc;
+    CKM(cudaEventRecord(t->ev_comm, t->comm_stream));
+    CKM(cudaStreamWaitEvent(s, t->ev_comm, 0));
+  }
+  cudaEventRecord(t->ev_ar, s);
+  const int64_t lsh = t->layer_elems / N, gsh = t->glob_elems / N;  // slice lengths
+  auto slice = [&](int blk, bf16* base, int64_t* n, int64_t* moff) {  // this rank's slice of block blk (L = globals)
+    const int64_t sh = blk < L ? lsh : gsh;
+    *n = sh;
+    *moff = static_cast<int64_t>(blk) * lsh;  // offset inside the master / moment shards
+    return base + (blk < L ? static_cast<int64_t>(blk) * t->layer_elems : static_cast<int64_t>(L) * t->layer_elems) + static_cast<int64_t>(t->rank) * sh;
+  };
+  if (!t->master_valid) {  // first step (or weights re-loaded): fp32 master copies of the owned bf16 slices
+    for (int blk = 0; blk <= L; ++blk) {
+      int64_t n, moff;
+      bf16* w = slice(blk, t->w_flat, &n, &moff);
+      CK(cast_bf16_to_f32(w, t->master + moff, n, s), 1);
+    }
+    t->master_valid = true;
+  }
+  for (int blk = 0; blk <= L; ++blk) {
+    int64_t n, moff;
+    bf16* g = slice(blk, t->g_flat, &n, &moff);
+    CK(sumsq_bf16_acc(g, n, t->d_scratch, t->d_sumsq, blk == 0 ? 1 : 0, s), 2);
+  }
+  if (N > 1) {
+    int rc = api->AllReduce(t->d_sumsq, t->d_sumsq, 1, kNcclFloat32, kNcclSum, t->nccl_comm, s);
+    if (rc != 0) return t->fail(DTX_ERR_NCCL, "ncclAllReduce failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
+    t->launches += 1;
+  }
+  const double lam = dtx_lr_lambda(tc.sched, t->opt_step, tc.warmup_steps, tc.total_steps);
+  const float lr = static_cast<float>(static_cast<double>(tc.lr) * lam);
+  const int step1 = t->opt_step + 1;
+  for (int blk = 0; blk <= L; ++blk) {
+    int64_t n, moff;
+    bf16* g = slice(blk, t->g_flat, &n, &moff);
+    bf16* w = slice(blk, t->w_flat, &n, &moff);
+    AdamWShardArgs a;
+    a.master = t->master + moff; a.m = t->fm + moff; a.v = t->fv + moff; a.g = g; a.w = w; a.n = n;
+    // RMSNorm weights (no weight decay): the tail [off_n1, layer_used) of a layer block, [goff_nf, glob_used) of the globals
+    const int64_t nd_begin = blk < L ? t->off_n1 : t->goff_nf, first = static_cast<int64_t>(t->rank) * n;
+    a.nodecay_from = nd_begin - first < 0 ? 0 : nd_begin - first;
+    a.lr = lr; a.beta1 = tc.beta1; a.beta2 = tc.beta2; a.eps = tc.eps; a.weight_decay = tc.weight_decay;
+    a.bias1 = static_cast<float>(1.0 - pow(static_cast<double>(tc.beta1), step1));
+    a.bias2 = static_cast<float>(1.0 - pow(static_cast<double>(tc.beta2), step1));
+    a.grad_scale = 1.0f / static_cast<float>(N * (tc.grad_accum > 0 ? tc.grad_accum : 1));
+    a.sumsq = t->d_sumsq; a.max_grad_norm = tc.max_grad_norm; a.grad_norm_out = t->d_gnorm;
+    CK(adamw_shard_step(a, s), 1);
+  }
+  if (N > 1) {  // every rank gets every updated slice (in place: the send slice sits at its final position)
+    for (int blk = 0; blk <= L; ++blk) {
+      int64_t n, moff;
+      bf16* w = slice(blk, t->w_flat, &n, &moff);
+      bf16* base = w - static_cast<int64_t>(t->rank) * n;
+      int rc = api->AllGather(w, base, static_cast<size_t>(n), kNcclBfloat16, t->nccl_comm, s);
+      if (rc != 0) return t->fail(DTX_ERR_NCCL, "ncclAllGather failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
+      t->launches += 1;
+    }
+  }
+  t->opt_step += 1;
+  if (lr_used) *lr_used = lr;
+  return DTX_OK;
+}
+
 // validate and record the shape of the batch about to be processed
 int set_batch_shape(dtx_trainer* t, int32_t seq_len_batch, bool have_lens) {
   const int S = seq_len_batch > 0 ? seq_len_batch : t->tc.seq_len;
@@ -670,21 +876,22 @@ int check_ready(dtx_trainer* t) {
   char buf[160];
   if (const char* m = t->missing_weight(buf, sizeof(buf)))
     return t->fail(DTX_ERR_STATE, "base weight %s was never loaded (dtx_load_tensor / dtx_init_random_weights)", m);
-  if (!t->have_lora) return t->fail(DTX_ERR_STATE, "LoRA adapters not initialised (dtx_init_lora / dtx_load_tensor)");
+  if (!t->full && !t->have_lora) return t->fail(DTX_ERR_STATE, "LoRA adapters not initialised (dtx_init_lora / dtx_load_tensor)");
   return DTX_OK;
 }
 
 int do_step(dtx_trainer* t, int32_t flags, float* loss_out, float* gnorm_out, float* lr_out, int32_t* stepped_out) {
   cudaEventRecord(t->ev0, t->stream);
+  const int accum = t->tc.grad_accum > 0 ? t->tc.grad_accum : 1;
+  t->rs_now = t->full && (t->micro_idx + 1 >= accum || (flags & DTX_STEP_FORCE));
   int rc = fwd_bwd(t, true);
   if (rc) return rc;
   cudaEventRecord(t->ev_fb, t->stream);
   t->micro_idx += 1;
   int stepped = 0;
   float lr = 0.f;
-  const int accum = t->tc.grad_accum > 0 ? t->tc.grad_accum : 1;
   if (t->micro_idx >= accum || (flags & DTX_STEP_FORCE)) {
-    rc = optimizer_step(t, &lr);
+    rc = t->full ? optimizer_step_full(t, &lr) : optimizer_step(t, &lr);
     if (rc) return rc;
     t->micro_idx = 0;
     stepped = 1;
@@ -811,9 +1018,9 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
     return bad("hidden must be a multiple of 64, ffn a multiple of 128 (GU-interleaved layout), vocab a multiple of 8");
   if (tc->seq_len % 128 || tc->seq_len <= 0 || tc->micro_batch <= 0) return bad("seq_len must be a positive multiple of 128");
   if (tc->seq_len > mc->max_seq) return bad("seq_len exceeds max_seq");
-  if (tc->lora_r <= 0 || tc->lora_r % 8) return bad("lora_r must be a positive multiple of 8");
+  if (!tc->full_finetune && (tc->lora_r <= 0 || tc->lora_r % 8)) return bad("lora_r must be a positive multiple of 8");
   if (tc->lora_dropout < 0.0f || tc->lora_dropout >= 1.0f) return bad("lora_dropout must be in [0, 1)");
-  if ((tc->target_mask & ~(DTX_TARGET_Q | DTX_TARGET_K | DTX_TARGET_V)) || tc->target_mask == 0)
+  if (!tc->full_finetune && ((tc->target_mask & ~(DTX_TARGET_Q | DTX_TARGET_K | DTX_TARGET_V)) || tc->target_mask == 0))
     { g_error = "lora_target must be a non-empty subset of q_proj,k_proj,v_proj"; return DTX_ERR_UNSUPPORTED; }
   if (world < 1 || rank < 0 || rank >= world) return bad("bad rank/world");
   if (world > 1 && !nccl_unique_id) return bad("world > 1 needs an NCCL unique id");
@@ -839,10 +1046,11 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
   t->dq = mc->n_heads * mc->head_dim;
   t->dkv = mc->n_kv_heads * mc->head_dim;
   t->W = t->dq + 2 * t->dkv;
-  t->dropout = tc->lora_dropout > 0.0f;
+  t->full = tc->full_finetune != 0;
+  t->dropout = !t->full && tc->lora_dropout > 0.0f;
   t->nt = 0;
   t->per_layer = 0;
-  {
+  if (!t->full) {
     const unsigned bits[3] = {DTX_TARGET_Q, DTX_TARGET_K, DTX_TARGET_V};
     const char names[3] = {'q', 'k', 'v'};
     const int row0[3] = {0, t->dq, t->dq + t->dkv};
@@ -870,6 +1078,12 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
   cudaEventCreate(&t->ev1);
   cudaEventCreate(&t->ev_fb);
   cudaEventCreate(&t->ev_ar);
+  if (t->full) {
+    cudaStreamCreateWithFlags(&t->comm_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&t->ev_comm, cudaEventDisableTiming);
+    t->ev_layer.resize(mc->n_layers + 1);
+    for (auto& e : t->ev_layer) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  }
   int rc = create_buffers(t);
   if (rc) {
     g_error = t->err;
@@ -915,6 +1129,9 @@ void dtx_trainer_destroy(dtx_trainer* t) {
   if (t->ev1) cudaEventDestroy(t->ev1);
   if (t->ev_fb) cudaEventDestroy(t->ev_fb);
   if (t->ev_ar) cudaEventDestroy(t->ev_ar);
+  if (t->ev_comm) cudaEventDestroy(t->ev_comm);
+  for (auto e : t->ev_layer) cudaEventDestroy(e);
+  if (t->comm_stream) cudaStreamDestroy(t->comm_stream);
   if (t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
@@ -922,6 +1139,7 @@ void dtx_trainer_destroy(dtx_trainer* t) {
 int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int32_t dtype, const int64_t* shape, int32_t nd) {
   if (!t || !name || !host || !shape || nd < 1 || nd > 2) return t ? t->fail(DTX_ERR_INVALID, "bad argument") : DTX_ERR_INVALID;
   cudaSetDevice(t->device);
+  t->master_valid = false;  // full-parameter SFT: the fp32 master copies are rebuilt from the bf16 weights at the next step
   const int64_t d = t->mc.hidden, F = t->mc.ffn, V = t->mc.vocab, r = t->tc.lora_r, dq = t->dq, dkv = t->dkv;
   const int64_t rows = shape[0], cols = nd == 2 ? shape[1] : 1;
   auto expect = [&](int64_t er, int64_t ec) { return rows == er && cols == ec; };
@@ -1021,6 +1239,7 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
 int32_t dtx_init_random_weights(dtx_trainer* t, uint64_t seed) {
   if (!t) return DTX_ERR_INVALID;
   if (t->quant4) return t->fail(DTX_ERR_STATE, "init_random_weights: the base weights are already NF4-packed");
+  t->master_valid = false;
   cudaSetDevice(t->device);
   const int64_t d = t->mc.hidden, F = t->mc.ffn, V = t->mc.vocab;
   cudaStream_t s = t->stream;
@@ -1050,6 +1269,7 @@ int32_t dtx_quantize_base(dtx_trainer* t, int32_t mode) {
     return t->fail(DTX_ERR_UNSUPPORTED, "--quantization int8 (bitsandbytes LLM.int8 with runtime outlier decomposition, "
                                          "cmd/tuning/train.py:231-232) is not implemented natively; use int4 or no quantization");
   if (mode != 4) return t->fail(DTX_ERR_INVALID, "quantize_base: mode must be 4 (nf4)");
+  if (t->full) return t->fail(DTX_ERR_INVALID, "quantize_base: full-parameter SFT trains the bf16 weights themselves");
   if (t->quant4) return t->fail(DTX_ERR_STATE, "quantize_base: already quantised");
   {
     char buf[160];
@@ -1085,6 +1305,7 @@ int64_t dtx_base_weight_bytes(const dtx_trainer* t) { return t ? t->base_bytes :
 
 int32_t dtx_init_lora(dtx_trainer* t, uint64_t seed) {
   if (!t) return DTX_ERR_INVALID;
+  if (t->full) return t->fail(DTX_ERR_STATE, "init_lora: this trainer was created for full-parameter SFT (no adapters)");
   cudaSetDevice(t->device);
   const int64_t d = t->mc.hidden, r = t->tc.lora_r;
   std::vector<float> host(t->n_train, 0.f);
@@ -1184,6 +1405,7 @@ int32_t dtx_allreduce_host(dtx_trainer* t, double* inout, int32_t n) {
 
 static int32_t export_lora_tensor(dtx_trainer* t, const float* flat, const char* name, void* host_out, int64_t nbytes) {
   if (!t || !name || !host_out) return t ? t->fail(DTX_ERR_INVALID, "null argument") : DTX_ERR_INVALID;
+  if (t->full || !flat) return t->fail(DTX_ERR_STATE, "no adapters: this trainer was created for full-parameter SFT");
   cudaSetDevice(t->device);
   const int64_t d = t->mc.hidden, r = t->tc.lora_r;
   int layer = -1;
@@ -1220,6 +1442,51 @@ int32_t dtx_export_adapter(dtx_trainer* t, const char* name, void* host_out, int
 }
 int32_t dtx_export_adapter_grad(dtx_trainer* t, const char* name, void* host_out, int64_t nbytes) {
   return export_lora_tensor(t, t ? t->grads : nullptr, name, host_out, nbytes);
+}
+
+// Full-parameter SFT: one weight (grad = 0) or its accumulated gradient (grad = 1) by HF name, as bf16 bit patterns in the HF
+// layout (gate / up rows taken back out of the GU-interleaved storage).  Gradients are only complete on a single rank.
+int32_t dtx_export_weight(dtx_trainer* t, const char* name, void* host_out, int64_t nbytes, int32_t grad) {
+  if (!t || !name || !host_out) return t ? t->fail(DTX_ERR_INVALID, "null argument") : DTX_ERR_INVALID;
+  if (!t->full) return t->fail(DTX_ERR_STATE, "export_weight: only for full-parameter SFT trainers (LoRA: dtx_export_adapter)");
+  cudaSetDevice(t->device);
+  CKM(cudaStreamSynchronize(t->stream));
+  const int64_t d = t->mc.hidden, F = t->mc.ffn, V = t->mc.vocab, dq = t->dq, dkv = t->dkv, L = t->mc.n_layers;
+  const bf16* flat = grad ? t->g_flat : t->w_flat;
+  const bf16* gl = flat + L * t->layer_elems;
+  auto copy = [&](const bf16* src, int64_t n) -> int32_t {
+    if (nbytes < n * 2) return t->fail(DTX_ERR_INVALID, "%s: output buffer too small", name);
+    CKM(cudaMemcpy(host_out, src, n * 2, cudaMemcpyDeviceToHost));
+    return DTX_OK;
+  };
+  if (strstr(name, "embed_tokens.weight")) return copy(gl, V * d);
+  if (strstr(name, "lm_head.weight")) return copy(gl + t->goff_lm, V * d);
+  int layer = -1;
+  const char* rest = nullptr;
+  if (!parse_layer(name, &layer, &rest)) {
+    if (strstr(name, "norm.weight")) return copy(gl + t->goff_nf, d);
+    return t->fail(DTX_ERR_INVALID, "unknown tensor name %s", name);
+  }
+  if (layer < 0 || layer >= L) return t->fail(DTX_ERR_INVALID, "%s: layer out of range", name);
+  const bf16* blk = flat + layer * t->layer_elems;
+  for (int which = 0; which < 2; ++which) {
+    if (!strstr(rest, which ? "mlp.up_proj.weight" : "mlp.gate_proj.weight")) continue;
+    if (nbytes < F * d * 2) return t->fail(DTX_ERR_INVALID, "%s: output buffer too small", name);
+    for (int64_t b = 0; b < F / 128; ++b)
+      CKM(cudaMemcpy(static_cast<bf16*>(host_out) + b * 128 * d, blk + t->off_wgu + (b * 256 + which * 128) * d, 128 * d * 2,
+                     cudaMemcpyDeviceToHost));
+    return DTX_OK;
+  }
+  struct Slot { const char* key; int64_t off, n; };
+  const Slot slots[] = {
+      {"self_attn.q_proj.weight", 0, dq * d}, {"self_attn.k_proj.weight", dq * d, dkv * d},
+      {"self_attn.v_proj.weight", (dq + dkv) * d, dkv * d}, {"self_attn.o_proj.weight", t->off_wo, d * d},
+      {"mlp.down_proj.weight", t->off_wdown, d * F}, {"input_layernorm.weight", t->off_n1, d},
+      {"post_attention_layernorm.weight", t->off_n2, d},
+  };
+  for (const Slot& sl : slots)
+    if (strstr(rest, sl.key)) return copy(blk + sl.off, sl.n);
+  return t->fail(DTX_ERR_INVALID, "unknown tensor name %s", name);
 }
 
 int64_t dtx_num_trainable(const dtx_trainer* t) { return t ? t->n_train : 0; }

@@ -41,14 +41,15 @@ class TrainCfg(C.Structure):
                 ("target_mask", C.c_uint32), ("lr", C.c_float), ("weight_decay", C.c_float), ("beta1", C.c_float),
                 ("beta2", C.c_float), ("eps", C.c_float), ("max_grad_norm", C.c_float), ("sched", C.c_int32),
                 ("warmup_steps", C.c_int32), ("total_steps", C.c_int32), ("grad_accum", C.c_int32),
-                ("micro_batch", C.c_int32), ("seq_len", C.c_int32), ("seed", C.c_uint64)]
+                ("micro_batch", C.c_int32), ("seq_len", C.c_int32), ("seed", C.c_uint64), ("full_finetune", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 # every symbol include/dtxtune.h declares (tests/test_abi.py checks the .so exports all of them)
 ABI_SYMBOLS = [
     "dtx_abi_version", "dtx_last_global_error", "dtx_last_error", "dtx_trainer_create", "dtx_trainer_destroy",
     "dtx_get_nccl_unique_id", "dtx_load_tensor", "dtx_init_random_weights", "dtx_init_lora", "dtx_quantize_base", "dtx_step",
-    "dtx_step_device", "dtx_eval_loss", "dtx_allreduce_host", "dtx_export_adapter", "dtx_export_adapter_grad", "dtx_num_trainable", "dtx_launch_count",
+    "dtx_step_device", "dtx_eval_loss", "dtx_allreduce_host", "dtx_export_adapter", "dtx_export_adapter_grad", "dtx_export_weight", "dtx_num_trainable", "dtx_launch_count",
     "dtx_base_weight_bytes", "dtx_last_step_ms", "dtx_last_step_timings", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16",
     "dtx_gemm_fused", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
     "dtx_rope_table", "dtx_rope_qk", "dtx_swiglu_fwd", "dtx_swiglu_bwd", "dtx_lora_dropout_fwd", "dtx_lora_dropout_bwd_add",
@@ -95,6 +96,7 @@ def load() -> C.CDLL:
                                    i32, vp]
     lib.dtx_export_adapter.argtypes = [vp, C.c_char_p, vp, i64]
     lib.dtx_export_adapter_grad.argtypes = [vp, C.c_char_p, vp, i64]
+    lib.dtx_export_weight.argtypes = [vp, C.c_char_p, vp, i64, i32]
     lib.dtx_num_trainable.argtypes = [vp]
     lib.dtx_num_trainable.restype = i64
     lib.dtx_launch_count.argtypes = [vp]
@@ -186,6 +188,7 @@ class TrainConfig:
     warmup_steps: int = 0               # --warmup_ratio is dropped by the reference (train.py:204)
     grad_accum: int = 1
     seed: int = 42
+    full_finetune: bool = False         # every weight trains, no adapters (BASELINE.json configs[3]; beyond the reference)
 
     def to_c(self) -> TrainCfg:
         mask = 0
@@ -195,7 +198,7 @@ class TrainConfig:
             mask |= TARGET_BITS[t]
         return TrainCfg(self.lora_r, self.lora_alpha, self.lora_dropout, mask, self.lr, self.weight_decay, self.beta1,
                         self.beta2, self.eps, self.max_grad_norm, SCHED[self.sched], self.warmup_steps, self.total_steps,
-                        self.grad_accum, self.micro_batch, self.seq_len, self.seed)
+                        self.grad_accum, self.micro_batch, self.seq_len, self.seed, 1 if self.full_finetune else 0, 0)
 
 
 _NP_DTYPES = {np.dtype(np.float32): DTX_F32, np.dtype(np.float16): DTX_F16}
@@ -325,6 +328,34 @@ class Trainer:
             shape = (r, d) if "lora_A" in name else (d_out, r)
             buf = np.empty(shape, dtype=np.float32)
             check(fn(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes), self._h)
+            out[name] = buf
+        return out
+
+    def weight_names(self) -> Iterable[Tuple[str, Tuple[int, ...]]]:
+        """(HF name, shape) of every tensor of the model, in checkpoint order."""
+        m = self.model
+        d, F, V, dkv = m.hidden, m.ffn, m.vocab, (m.n_kv_heads or m.n_heads) * m.head_dim
+        yield "model.embed_tokens.weight", (V, d)
+        for l in range(m.n_layers):
+            p = f"model.layers.{l}."
+            yield p + "self_attn.q_proj.weight", (d, d)
+            yield p + "self_attn.k_proj.weight", (dkv, d)
+            yield p + "self_attn.v_proj.weight", (dkv, d)
+            yield p + "self_attn.o_proj.weight", (d, d)
+            yield p + "mlp.gate_proj.weight", (F, d)
+            yield p + "mlp.up_proj.weight", (F, d)
+            yield p + "mlp.down_proj.weight", (d, F)
+            yield p + "input_layernorm.weight", (d,)
+            yield p + "post_attention_layernorm.weight", (d,)
+        yield "model.norm.weight", (d,)
+        yield "lm_head.weight", (V, d)
+
+    def export_weights(self, grads: bool = False) -> Dict[str, np.ndarray]:
+        """Full-parameter SFT: every weight (or its accumulated gradient) as uint16 bf16 bit patterns, HF names and layout."""
+        out = {}
+        for name, shape in self.weight_names():
+            buf = np.empty(shape, dtype=np.uint16)
+            check(self.lib.dtx_export_weight(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes, 1 if grads else 0), self._h)
             out[name] = buf
         return out
 

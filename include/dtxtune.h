@@ -71,6 +71,12 @@ typedef struct {
   int32_t grad_accum;
   int32_t micro_batch, seq_len;
   uint64_t seed;
+  /* 1 = full-parameter SFT (BASELINE.json configs[3]; beyond the reference, whose worker always wraps LoRA - train.py:277):
+   * every weight trains, lora_* / target_mask are ignored.  bf16 weights and gradients, fp32 master weights + Adam moments
+   * sharded over the data-parallel ranks (ZeRO-1), gradients reduce-scattered per layer while the backward pass runs,
+   * updated weights all-gathered; AdamW weight decay skips the RMSNorm weights (HF Trainer.get_decay_parameter_names). */
+  int32_t full_finetune;
+  int32_t reserved;
 } dtx_train_cfg;
 
 typedef struct dtx_trainer dtx_trainer;
@@ -142,6 +148,9 @@ DTX_API int32_t dtx_export_adapter(dtx_trainer* t, const char* hf_name, void* ho
 /* The gradient the last optimizer step consumed, in the same naming and layout: the SUM over ranks and accumulated
  * micro-batches of d(mean token loss)/d(tensor), before the 1/(world*grad_accum) scaling and clipping (parity tests). */
 DTX_API int32_t dtx_export_adapter_grad(dtx_trainer* t, const char* hf_name, void* host_out, int64_t nbytes);
+/* Full-parameter SFT: one weight (grad = 0) or its accumulated gradient (grad = 1) by HF checkpoint name, as bf16 bit patterns
+ * in the HF layout - what trainer.save_model writes for a full fine-tune. */
+DTX_API int32_t dtx_export_weight(dtx_trainer* t, const char* hf_name, void* host_out_bf16, int64_t nbytes, int32_t grad);
 DTX_API int64_t dtx_num_trainable(const dtx_trainer* t);
 /* kernels launched by this trainer since creation (bench.py's gpu_launches) */
 DTX_API int64_t dtx_launch_count(const dtx_trainer* t);

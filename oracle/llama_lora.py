@@ -66,6 +66,9 @@ class OracleConfig:
     warmup_steps: int = 0
     total_steps: int = 100
     grad_accum: int = 1
+    # full-parameter SFT (BASELINE.json configs[3]; beyond the reference, which always wraps LoRA - cmd/tuning/train.py:277):
+    # every weight trains, no adapters; AdamW weight decay skips the RMSNorm weights like HF Trainer.get_decay_parameter_names
+    full_finetune: bool = False
 
     @staticmethod
     def llama2_7b(**kw) -> "OracleConfig":
@@ -325,11 +328,17 @@ class StepLog:
 
 
 class OracleTrainer:
-    """fp32 CPU restatement of the reference worker's training loop for one data-parallel group."""
+    """fp32 CPU restatement of the reference worker's training loop for one data-parallel group.
+    `self.lora` is the dict of TRAINABLE tensors: the adapters, or - with cfg.full_finetune - every model weight (then `lora`
+    passed in is ignored and no adapter exists)."""
 
     def __init__(self, cfg: OracleConfig, weights: Dict[str, torch.Tensor], lora: Dict[str, torch.Tensor], world: int = 1):
         self.cfg, self.w, self.world = cfg, weights, world
-        self.lora = {k: v.clone().float().requires_grad_(True) for k, v in lora.items()}
+        if cfg.full_finetune:
+            self.lora = {k: v.clone().float().requires_grad_(True) for k, v in weights.items()}
+            self.w = self.lora  # forward_logits reads the live (trainable) weights; it finds no adapter keys in them
+        else:
+            self.lora = {k: v.clone().float().requires_grad_(True) for k, v in lora.items()}
         self.m = {k: torch.zeros_like(v) for k, v in self.lora.items()}
         self.v = {k: torch.zeros_like(v) for k, v in self.lora.items()}
         self.opt_step = 0
@@ -379,8 +388,8 @@ class OracleTrainer:
         self.opt_step += 1
         with torch.no_grad():
             for k, p in self.lora.items():
-                adamw_update(p, acc[k] * coef, self.m[k], self.v[k], self.opt_step, lr, cfg.beta1, cfg.beta2, cfg.eps,
-                             cfg.weight_decay)
+                wd = 0.0 if (cfg.full_finetune and k.endswith("norm.weight") or k.endswith("layernorm.weight")) else cfg.weight_decay
+                adamw_update(p, acc[k] * coef, self.m[k], self.v[k], self.opt_step, lr, cfg.beta1, cfg.beta2, cfg.eps, wd)
         return StepLog(loss=float(np.mean(losses)), grad_norm=total_norm, lr=lr)
 
     def state_dict(self) -> Dict[str, np.ndarray]:

@@ -817,6 +817,85 @@ def check_missing_weight_is_refused():
     return {"loss": loss}
 
 
+def _bf16_bits_to_f32(a: np.ndarray) -> np.ndarray:
+    return (a.astype(np.uint32) << 16).view(np.float32)
+
+
+def check_trainer_full(steps=8, grad_accum=1, weight_decay=0.01):
+    """Full-parameter SFT (BASELINE.json configs[3]): every weight trains.  Native (bf16 weights / gradients, fp32 master + Adam
+    state) against the fp32 oracle with all weights trainable: per-tensor gradients of the first step, loss and grad-norm
+    traces, and the weights after `steps` optimizer steps."""
+    ocfg, mc, tc = tiny_configs(steps=steps)
+    ocfg.full_finetune, tc.full_finetune = True, True
+    ocfg.grad_accum, tc.grad_accum = grad_accum, grad_accum
+    ocfg.weight_decay, tc.weight_decay = weight_decay, weight_decay
+    w = O.init_base_weights(ocfg, 1234)
+    g = torch.Generator().manual_seed(3)
+    for k in w:  # norm weights away from 1 so that their gradients and the no-decay rule are exercised
+        if k.endswith("norm.weight"):
+            w[k] = O.bf16_round(1.0 + 0.1 * torch.randn(w[k].shape, generator=g))
+    tr = L.Trainer(mc, tc)
+    tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+    assert tr.num_trainable == sum(v.numel() for v in w.values()), (tr.num_trainable, sum(v.numel() for v in w.values()))
+    orc = O.OracleTrainer(ocfg, w, {})
+    S, B = tc.seq_len, tc.micro_batch
+    worst_l = worst_g = 0.0
+    grad_errs = {}
+    for s_ in range(steps):
+        batches = [O.synthetic_batch(grad_accum * s_ + i, 0, B, S, ocfg.vocab) for i in range(grad_accum)]
+        if s_ == 0:
+            _, g_ref = O.OracleTrainer(ocfg, w, {}).loss_and_grads(*batches[0])
+        ref = orc.step(batches)
+        losses = []
+        for i, (ids, labels) in enumerate(batches):
+            loss, gn, lr, stepped = tr.step(ids, labels)
+            losses.append(loss)
+            if s_ == 0 and i == 0:  # gradients of the first micro-batch, before anything else touches the buffer
+                got = tr.export_weights(grads=True)
+                for k, v in got.items():
+                    r = g_ref[k].numpy()
+                    grad_errs[k] = float(np.linalg.norm(_bf16_bits_to_f32(v) - r) / max(np.linalg.norm(r), 1e-12))
+            assert stepped == (i == grad_accum - 1)
+        assert abs(lr - ref.lr) <= 1e-9 + 1e-6 * ref.lr, (lr, ref.lr)
+        worst_l = max(worst_l, abs(float(np.mean(losses)) - ref.loss) / ref.loss)
+        worst_g = max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
+    wts = tr.export_weights()
+    drift = {}
+    for k, v in wts.items():
+        r = orc.lora[k].detach().numpy()
+        drift[k] = float(np.linalg.norm(_bf16_bits_to_f32(v) - r) / max(np.linalg.norm(r), 1e-12))
+    moved = float(np.linalg.norm(_bf16_bits_to_f32(wts["model.layers.0.mlp.down_proj.weight"]) - w["model.layers.0.mlp.down_proj.weight"].numpy()))
+    tr.close()
+    worst_grad = max(grad_errs.values())
+    worst_tensor = max(grad_errs, key=grad_errs.get)
+    assert worst_grad < 5e-2, f"gradient of {worst_tensor}: {worst_grad}; all {grad_errs}"
+    assert worst_l < 2e-3 and worst_g < 3e-2, (worst_l, worst_g)
+    assert max(drift.values()) < 1e-2 and moved > 0, (max(drift.values()), moved)  # bf16 weights: 2^-9 relative rounding
+    return {"loss": worst_l, "gnorm": worst_g, "worst_grad": [worst_tensor, worst_grad], "weight_drift": max(drift.values()), "moved": moved}
+
+
+def check_trainer_full_gqa(steps=4):
+    """Full-parameter SFT on a grouped-query model at a ragged batch (row lengths): the dK / dV width differs from dQ."""
+    ocfg, mc, tc = tiny_configs(S=384, B=2, steps=steps, heads=4, kv_heads=2)
+    ocfg.full_finetune, tc.full_finetune = True, True
+    w = O.init_base_weights(ocfg, 77)
+    tr = L.Trainer(mc, tc)
+    tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+    orc = O.OracleTrainer(ocfg, w, {})
+    worst_l = worst_g = 0.0
+    for s_ in range(steps):
+        ids, labels = O.synthetic_batch(s_, 0, 2, 384, ocfg.vocab)
+        lens = np.array([384, 200], dtype=np.int32)
+        ids[1, 200:] = 0
+        labels[1, 200:] = -100
+        ref = orc.step([(ids, labels)])
+        loss, gn, _, _ = tr.step(ids, labels, lens)
+        worst_l, worst_g = max(worst_l, abs(loss - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
+    tr.close()
+    assert worst_l < 2e-3 and worst_g < 3e-2, (worst_l, worst_g)
+    return {"loss": worst_l, "gnorm": worst_g}
+
+
 def check_layer_7b_shape(B=2, S=2048):
     """One Llama-2-7B-shaped decoder layer (d=4096, H=32, F=11008) + lm_head (V=32000) + CE through the native trainer at the
     benchmark's sequence length, against the fp32 oracle on the host cores: forward loss, step loss, grad-norm and every
@@ -1101,7 +1180,9 @@ ALL = {
     "attn_bwd_rope": check_attn_bwd_rope, "attn_varlen": check_attn_varlen, "attn_window": check_attn_window,
     "trainer_window": check_trainer_window,
     "trainer_varlen": check_trainer_varlen, "eval_rows_force_step": check_eval_rows_and_force_step,
-    "missing_weight_refused": check_missing_weight_is_refused, "layer_7b_shape": check_layer_7b_shape, "trainer_qlora": check_trainer_qlora, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
+    "missing_weight_refused": check_missing_weight_is_refused, "layer_7b_shape": check_layer_7b_shape,
+    "trainer_full": check_trainer_full, "trainer_full_accum": lambda: check_trainer_full(steps=4, grad_accum=2, weight_decay=0.0),
+    "trainer_full_gqa": lambda: check_trainer_full_gqa(), "trainer_qlora": check_trainer_qlora, "embedding": check_embedding, "cross_entropy": check_cross_entropy,
     "adamw": check_adamw, "attn_fwd": check_attn_fwd, "attn_fwd_long": lambda: check_attn_fwd(B=1, S=1024, H=1),
     "attn_fwd_rescale": lambda: check_attn_fwd(B=1, S=1024, H=2, growing=True),
     "attn_fwd_odd_tiles": lambda: {"s640": check_attn_fwd(B=1, S=640, H=2), "s128": check_attn_fwd(B=3, S=128, H=2)},

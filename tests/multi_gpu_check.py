@@ -18,6 +18,47 @@ from datatunerx_b200.dist import Rendezvous  # noqa: E402
 from oracle import llama_lora as O  # noqa: E402
 
 
+def main_full(steps=4):
+    """Full-parameter SFT across N ranks: per-layer reduce-scatter of bf16 gradients, sharded fp32 AdamW, all-gather of the
+    updated bf16 weights - against the oracle with world = N and every weight trainable; replicas must end bitwise equal."""
+    rv = Rendezvous()
+    ocfg = O.OracleConfig(vocab=2048, hidden=256, n_layers=2, n_heads=2, ffn=768, lr=1e-3, total_steps=steps, full_finetune=True,
+                          weight_decay=0.01)
+    mc = L.ModelConfig(vocab=2048, hidden=256, n_layers=2, n_heads=2, ffn=768)
+    tc = L.TrainConfig(micro_batch=2, seq_len=256, total_steps=steps, lr=1e-3, full_finetune=True, weight_decay=0.01, lora_dropout=0.0)
+    w = O.init_base_weights(ocfg, 1234)
+    nccl_id = rv.broadcast_bytes(L.nccl_unique_id)
+    tr = L.Trainer(mc, tc, device=rv.local_rank, rank=rv.rank, world=rv.world, nccl_id=nccl_id)
+    tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+    orc = O.OracleTrainer(ocfg, w, {}, world=rv.world)
+    worst_l = worst_g = 0.0
+    for s in range(steps):
+        shards = [O.synthetic_batch(s, r, 2, 256, ocfg.vocab) for r in range(rv.world)]
+        ref_losses = [orc.eval_loss(*b) for b in shards]
+        ref = orc.step(shards)
+        loss, gn, lr, stepped = tr.step(*shards[rv.rank])
+        assert stepped
+        worst_l = max(worst_l, abs(loss - ref_losses[rv.rank]) / ref_losses[rv.rank])
+        worst_g = max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
+    wts = tr.export_weights()
+    f32 = lambda a: (a.astype(np.uint32) << 16).view(np.float32)
+    drift = max(float(np.linalg.norm(f32(v) - orc.lora[k].detach().numpy()) / max(np.linalg.norm(orc.lora[k].detach().numpy()), 1e-12))
+                for k, v in wts.items())
+    digest = hashlib.sha256(b"".join(wts[k].tobytes() for k in sorted(wts))).hexdigest()
+    digests = [None] * rv.world
+    if rv.dist is not None:
+        rv.dist.all_gather_object(digests, digest)
+    else:
+        digests = [digest]
+    tr.close()
+    ok = worst_l < 2e-3 and worst_g < 3e-2 and drift < 1e-2 and len(set(digests)) == 1
+    if rv.rank == 0:
+        print("MULTI_GPU_CHECK_FULL " + json.dumps({"world": rv.world, "ok": ok, "loss_rel": worst_l, "gnorm_rel": worst_g,
+                                                    "weight_drift": drift, "replicas_bitwise_equal": len(set(digests)) == 1}), flush=True)
+    rv.close()
+    sys.exit(0 if ok else 1)
+
+
 def main(steps=5):
     rv = Rendezvous()
     ocfg = O.OracleConfig(vocab=2048, hidden=256, n_layers=2, n_heads=2, ffn=768, lora_r=16, lora_alpha=32.0, lr=1e-3,
@@ -60,4 +101,7 @@ def main(steps=5):
 
 
 if __name__ == "__main__":
-    main()
+    if "--full" in sys.argv:
+        main_full()
+    else:
+        main()

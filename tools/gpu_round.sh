@@ -20,6 +20,7 @@ for s in $STEPS; do
                  timeout 900 compute-sanitizer --tool racecheck --print-limit 5 python -m tests.gpu_checks $c > $OUT/racecheck_$c.log 2>&1; echo "$c rc=$?" >> $OUT/sanitizer_summary.txt; done
                timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python -m tests.gpu_checks attn_varlen trainer_varlen > $OUT/memcheck_varlen.log 2>&1; echo "memcheck_varlen rc=$?" >> $OUT/sanitizer_summary.txt;;
     mgpu_check) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29541 tests/multi_gpu_check.py > $OUT/multi_gpu_check_n${NGPU:-2}.log 2>&1;;
+    mgpu_full) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29544 tests/multi_gpu_check.py --full > $OUT/multi_gpu_check_full_n${NGPU:-2}.log 2>&1;;
     bench_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus ${NGPU:-2} --steps 8 --warmup 3 > $OUT/bench_n${NGPU:-2}.json 2> $OUT/bench_n${NGPU:-2}.err;;
     qlora_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29543 bench.py --config mistral7b_qlora --gpus ${NGPU:-2} --steps 5 --warmup 3 > $OUT/bench_qlora_n${NGPU:-2}.json 2> $OUT/bench_qlora_n${NGPU:-2}.err;;
     jobs_tiny) timeout 600 python tools/concurrent_jobs.py --jobs ${NJOBS:-1} --gpus-per-job 2 --model tiny --steps 12 --out $OUT/concurrent_jobs_tiny.json > $OUT/concurrent_jobs_tiny.log 2>&1;;
