@@ -28,6 +28,7 @@ for s in $STEPS; do
     determinism) timeout 600 python tools/diag_determinism.py > $OUT/determinism.log 2>&1;;
     step_repeat) timeout 600 python tools/diag_step_repeat.py > $OUT/step_repeat.log 2>&1;;
     initcheck) timeout 900 compute-sanitizer --tool initcheck --print-limit 20 python -m tests.gpu_checks trainer_tiny > $OUT/initcheck_trainer_tiny.log 2>&1;;
+    load_paths) timeout 600 python tools/diag_load_paths.py > $OUT/load_paths.log 2>&1;;
     diag7b) timeout 600 python tools/diag_layer7b.py > $OUT/diag7b.log 2>&1;;
     parity7b) timeout 1200 python tools/parity_7b.py --steps 3 --out $OUT/parity_7b.json > $OUT/parity_7b.log 2>&1;;
     pytest) timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1;;
