@@ -299,6 +299,17 @@ namespace {
     if (_e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+// Host -> device copies of weights / adapters go through the TRAINER'S stream and are waited for: cudaMemcpy() from pageable
+// memory returns once the data is staged - the DMA may still be in flight - and it runs on the legacy default stream, with
+// which the trainer's non-blocking stream does not synchronise.  A kernel launched right behind it (the adapter shadow
+// refresh) then read stale parameters: the first step after loading adapters from the host differed from run to run
+// (profiles/r02_load_race.txt).
+inline cudaError_t upload_sync(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);
+}
+
 // key of the dropout masks of one (forward pass, layer): the per-element keep decision is
 // splitmix64(key + target * 0x9E3779B97F4A7C15 + m * d + c) >> 40 >= p * 2^24  (restated in oracle/llama_lora.py)
 uint64_t dropout_key(const dtx_trainer* t, int layer) {
@@ -1146,7 +1157,7 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
   auto upload = [&](bf16* dst, size_t n) -> int {
     std::vector<bf16> tmp;
     to_bf16_host(host, dtype, n, tmp);
-    cudaError_t e = cudaMemcpy(dst, tmp.data(), n * sizeof(bf16), cudaMemcpyHostToDevice);
+    cudaError_t e = upload_sync(dst, tmp.data(), n * sizeof(bf16), t->stream);
     if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "upload %s: %s", name, cudaGetErrorString(e));
     return DTX_OK;
   };
@@ -1190,11 +1201,11 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
       std::vector<float> tr(d * r);
       for (int64_t j = 0; j < r; ++j)
         for (int64_t c = 0; c < d; ++c) tr[c * r + j] = f[j * d + c];
-      CKM(cudaMemcpy(base, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice));
+      CKM(upload_sync(base, tr.data(), tr.size() * 4, t->stream));
     } else {
       if (!expect(d_out, r)) return t->fail(DTX_ERR_INVALID, "%s: expected [%lld,%lld]", name, (long long)d_out, (long long)r);
       to_f32_host(host, dtype, d_out * r, f);
-      CKM(cudaMemcpy(base + d * r, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+      CKM(upload_sync(base + d * r, f.data(), f.size() * 4, t->stream));
     }
     t->have_lora = true;
     int rc = refresh_shadows(t);
@@ -1211,10 +1222,11 @@ int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int3
     std::vector<bf16> tmp;
     to_bf16_host(host, dtype, static_cast<size_t>(F) * d, tmp);
     for (int64_t b = 0; b < F / 128; ++b) {
-      cudaError_t e = cudaMemcpy(y.wgu + (b * 256 + which * 128) * d, tmp.data() + b * 128 * d, 128 * d * sizeof(bf16),
-                                 cudaMemcpyHostToDevice);
+      cudaError_t e = cudaMemcpyAsync(y.wgu + (b * 256 + which * 128) * d, tmp.data() + b * 128 * d, 128 * d * sizeof(bf16),
+                                      cudaMemcpyHostToDevice, t->stream);
       if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "upload %s: %s", name, cudaGetErrorString(e));
     }
+    CKM(cudaStreamSynchronize(t->stream));  // `tmp` dies at the end of this scope
     lmap[4 + which] = 1;
     return DTX_OK;
   }
@@ -1325,7 +1337,7 @@ int32_t dtx_init_lora(dtx_trainer* t, uint64_t seed) {
       float* a = host.data() + l * t->per_layer + t->tg[ti].off;
       for (int64_t i = 0; i < d * r; ++i) a[i] = (2.f * next() - 1.f) * bound;
     }
-  CKM(cudaMemcpy(t->params, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+  CKM(upload_sync(t->params, host.data(), host.size() * 4, t->stream));
   CKM(cudaMemsetAsync(t->adam_m, 0, t->n_train * 4, t->stream));
   CKM(cudaMemsetAsync(t->adam_v, 0, t->n_train * 4, t->stream));
   t->opt_step = 0;
@@ -1426,11 +1438,13 @@ static int32_t export_lora_tensor(dtx_trainer* t, const float* flat, const char*
   std::vector<float> tmp(d * r);
   float* out = static_cast<float*>(host_out);
   if (strstr(rest, "lora_A")) {
-    CKM(cudaMemcpy(tmp.data(), base, d * r * 4, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpyAsync(tmp.data(), base, d * r * 4, cudaMemcpyDeviceToHost, t->stream));
+    CKM(cudaStreamSynchronize(t->stream));
     for (int64_t c = 0; c < d; ++c)
       for (int64_t j = 0; j < r; ++j) out[j * d + c] = tmp[c * r + j];
   } else if (strstr(rest, "lora_B")) {
-    CKM(cudaMemcpy(out, base + d * r, d_out * r * 4, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpyAsync(out, base + d * r, d_out * r * 4, cudaMemcpyDeviceToHost, t->stream));
+    CKM(cudaStreamSynchronize(t->stream));
   } else {
     return t->fail(DTX_ERR_INVALID, "%s: expected lora_A or lora_B", name);
   }
@@ -1456,7 +1470,8 @@ int32_t dtx_export_weight(dtx_trainer* t, const char* name, void* host_out, int6
   const bf16* gl = flat + L * t->layer_elems;
   auto copy = [&](const bf16* src, int64_t n) -> int32_t {
     if (nbytes < n * 2) return t->fail(DTX_ERR_INVALID, "%s: output buffer too small", name);
-    CKM(cudaMemcpy(host_out, src, n * 2, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpyAsync(host_out, src, n * 2, cudaMemcpyDeviceToHost, t->stream));
+    CKM(cudaStreamSynchronize(t->stream));
     return DTX_OK;
   };
   if (strstr(name, "embed_tokens.weight")) return copy(gl, V * d);
@@ -1473,8 +1488,9 @@ int32_t dtx_export_weight(dtx_trainer* t, const char* name, void* host_out, int6
     if (!strstr(rest, which ? "mlp.up_proj.weight" : "mlp.gate_proj.weight")) continue;
     if (nbytes < F * d * 2) return t->fail(DTX_ERR_INVALID, "%s: output buffer too small", name);
     for (int64_t b = 0; b < F / 128; ++b)
-      CKM(cudaMemcpy(static_cast<bf16*>(host_out) + b * 128 * d, blk + t->off_wgu + (b * 256 + which * 128) * d, 128 * d * 2,
-                     cudaMemcpyDeviceToHost));
+      CKM(cudaMemcpyAsync(static_cast<bf16*>(host_out) + b * 128 * d, blk + t->off_wgu + (b * 256 + which * 128) * d, 128 * d * 2,
+                          cudaMemcpyDeviceToHost, t->stream));
+    CKM(cudaStreamSynchronize(t->stream));
     return DTX_OK;
   }
   struct Slot { const char* key; int64_t off, n; };
