@@ -284,8 +284,14 @@ def run_native(args, rank: int, local_rank: int, world: int):
     rv = Rendezvous()
     torch.cuda.set_device(local_rank)
 
-    lora_r, quant, varlen = 16, None, False
-    if args.config in ("7b", "7b_varlen"):
+    lora_r, quant, varlen, full = 16, None, False, False
+    if args.config == "13b_full":  # BASELINE.json configs[3]: Llama-2-13B full-parameter SFT bf16, seq 2048, data-parallel (beyond the reference)
+        mc = L.ModelConfig(vocab=32000, hidden=5120, n_layers=40, n_heads=40, ffn=13824)
+        B, S, full = 4, 2048, True
+    elif args.config == "small_full":  # the same path at a size that fits one GPU with its whole optimizer state
+        mc = L.ModelConfig(vocab=32000, hidden=2048, n_layers=8, n_heads=16, ffn=5504)
+        B, S, full = 8, 2048, True
+    elif args.config in ("7b", "7b_varlen"):
         mc = L.ModelConfig.llama2_7b()
         B, S = 8, 2048
         varlen = args.config == "7b_varlen"
@@ -296,7 +302,8 @@ def run_native(args, rank: int, local_rank: int, world: int):
         mc = L.ModelConfig(vocab=2048, hidden=256, n_layers=2, n_heads=2, ffn=768)
         B, S = 2, 256
     total = args.warmup + 2 * args.steps + 2
-    tc = L.TrainConfig(micro_batch=B, seq_len=S, total_steps=max(total, 100), lora_r=lora_r, lora_alpha=32.0, lora_dropout=0.0, lr=1e-4)
+    tc = L.TrainConfig(micro_batch=B, seq_len=S, total_steps=max(total, 100), lora_r=lora_r, lora_alpha=32.0, lora_dropout=0.0, lr=1e-4 if not full else 1e-5,
+                       full_finetune=full)
     nccl_id = rv.broadcast_bytes(L.nccl_unique_id)
     if os.environ.get("DTX_FWD_EXP_FMA"):  # A/B of the forward softmax's FMA-pipe exp2 fraction
         L.set_option("attn_fwd_exp_fma_every", int(os.environ["DTX_FWD_EXP_FMA"]))
@@ -307,7 +314,8 @@ def run_native(args, rank: int, local_rank: int, world: int):
     if quant:
         tr.quantize_base(quant)
     base_bytes = tr.base_weight_bytes
-    tr.init_lora(4321)
+    if not full:
+        tr.init_lora(4321)
 
     n_batches = 4
     host, lens_host = [], []
@@ -393,9 +401,14 @@ def run_native(args, rank: int, local_rank: int, world: int):
     gemms = time_step_gemms(torch, L) if args.config == "7b" else None
     tr.close()
     per_gpu_tflops = (value / world) * FLOP_PER_TOKEN / 1e12
-    metric = {"7b": "tokens/sec Llama-2-7B LoRA SFT seq2048", "7b_varlen": "real (unpadded) tokens/sec Llama-2-7B LoRA SFT, variable-length rows <= 2048",
+    metric = {"13b_full": "tokens/sec Llama-2-13B full-parameter SFT seq2048", "small_full": "tokens/sec 0.6B Llama-arch full-parameter SFT seq2048",
+              "7b": "tokens/sec Llama-2-7B LoRA SFT seq2048", "7b_varlen": "real (unpadded) tokens/sec Llama-2-7B LoRA SFT, variable-length rows <= 2048",
               "mistral7b_qlora": "tokens/sec Mistral-7B QLoRA nf4 r=32 seq4096", "tiny": "tokens/sec tiny-Llama smoke"}[args.config]
-    workload = {"7b": "Llama-2-7B (random-init N(0,0.02)) LoRA r=16 alpha=32 q_proj,v_proj, seq 2048, batch 8/GPU, "
+    workload = {"13b_full": "Llama-2-13B shape (L=40, d=5120, H=40, F=13824), FULL-parameter SFT: bf16 weights and gradients, per-layer NCCL reduce-scatter "
+                            "overlapped with the backward pass, fp32 master weights + AdamW state sharded over the ranks, all-gather of the updated "
+                            "weights; seq 2048, batch 4/GPU (BASELINE.json configs[3]; beyond the reference, NOT the headline metric)",
+                "small_full": "Llama-architecture 0.6B (L=8, d=2048, F=5504), full-parameter SFT, seq 2048, batch 8/GPU (NOT the headline metric)",
+                "7b": "Llama-2-7B (random-init N(0,0.02)) LoRA r=16 alpha=32 q_proj,v_proj, seq 2048, batch 8/GPU, "
                       "AdamW + clip 1.0 + linear schedule, bf16 compute / fp32 accumulate / fp32 adapters",
                 "7b_varlen": "Llama-2-7B LoRA r=16 as in the headline config, but log-normal row lengths (median 512, clipped to [16, 2048]), "
                              "each batch padded to its longest row (128-rounded) with true row lengths passed to the step; NOT the headline metric",
@@ -444,7 +457,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--config", default="7b", choices=["7b", "7b_varlen", "mistral7b_qlora", "tiny"])
+    ap.add_argument("--config", default="7b", choices=["7b", "7b_varlen", "mistral7b_qlora", "13b_full", "small_full", "tiny"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

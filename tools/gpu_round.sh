@@ -23,6 +23,9 @@ for s in $STEPS; do
     mgpu_full) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29544 tests/multi_gpu_check.py --full > $OUT/multi_gpu_check_full_n${NGPU:-2}.log 2>&1;;
     bench_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus ${NGPU:-2} --steps 8 --warmup 3 > $OUT/bench_n${NGPU:-2}.json 2> $OUT/bench_n${NGPU:-2}.err;;
     qlora_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29543 bench.py --config mistral7b_qlora --gpus ${NGPU:-2} --steps 5 --warmup 3 > $OUT/bench_qlora_n${NGPU:-2}.json 2> $OUT/bench_qlora_n${NGPU:-2}.err;;
+    full13b_n) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-8} --master-addr 127.0.0.1 --master-port 29545 bench.py --config 13b_full --gpus ${NGPU:-8} --steps 6 --warmup 3 > $OUT/bench_13b_full_n${NGPU:-8}.json 2> $OUT/bench_13b_full_n${NGPU:-8}.err;;
+    small_full) timeout 600 python bench.py --config small_full --steps 6 --warmup 3 > $OUT/bench_small_full.json 2> $OUT/bench_small_full.err;;
+    small_full_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29546 bench.py --config small_full --gpus ${NGPU:-2} --steps 6 --warmup 3 > $OUT/bench_small_full_n${NGPU:-2}.json 2> $OUT/bench_small_full_n${NGPU:-2}.err;;
     jobs_tiny) timeout 600 python tools/concurrent_jobs.py --jobs ${NJOBS:-1} --gpus-per-job 2 --model tiny --steps 12 --out $OUT/concurrent_jobs_tiny.json > $OUT/concurrent_jobs_tiny.log 2>&1;;
     jobs_7b) timeout 900 python tools/concurrent_jobs.py --jobs ${NJOBS:-4} --gpus-per-job 2 --model 7b --steps 8 --out $OUT/concurrent_jobs_7b.json > $OUT/concurrent_jobs_7b.log 2>&1;;
     determinism) timeout 600 python tools/diag_determinism.py > $OUT/determinism.log 2>&1;;
