@@ -117,6 +117,46 @@ def write_safetensors(path: str, tensors: Dict[str, np.ndarray]) -> None:
             f.write(b)
 
 
+def save_full_model(out_dir: str, weights: Dict[str, np.ndarray], model_dir: str, shard_bytes: int = 5 << 30) -> None:
+    """trainer.save_model of a full fine-tune: HF checkpoint directory - bf16 `model-0000x-of-0000y.safetensors` shards (uint16 bit
+    patterns straight from the device), `model.safetensors.index.json`, and the base model's config / tokenizer files."""
+    import shutil
+    os.makedirs(out_dir, exist_ok=True)
+    shards, cur, size = [], {}, 0
+    for k, a in weights.items():
+        if cur and size + a.nbytes > shard_bytes:
+            shards.append(cur)
+            cur, size = {}, 0
+        cur[k] = a
+        size += a.nbytes
+    shards.append(cur)
+    index = {"metadata": {"total_size": int(sum(a.nbytes for a in weights.values()))}, "weight_map": {}}
+    for i, sh in enumerate(shards):
+        name = "model.safetensors" if len(shards) == 1 else f"model-{i + 1:05d}-of-{len(shards):05d}.safetensors"
+        header, off, blobs = {}, 0, []
+        for k in sh:
+            a = np.ascontiguousarray(sh[k], dtype=np.uint16)
+            header[k] = {"dtype": "BF16", "shape": list(a.shape), "data_offsets": [off, off + a.nbytes]}
+            blobs.append(a)
+            off += a.nbytes
+            index["weight_map"][k] = name
+        header["__metadata__"] = {"format": "pt"}
+        h = json.dumps(header, separators=(",", ":")).encode()
+        h += b" " * ((8 - len(h) % 8) % 8)
+        with open(os.path.join(out_dir, name), "wb") as f:
+            f.write(struct.pack("<Q", len(h)))
+            f.write(h)
+            for b in blobs:
+                f.write(b.tobytes())
+    if len(shards) > 1:
+        json.dump(index, open(os.path.join(out_dir, "model.safetensors.index.json"), "w"), indent=2)
+    for fn in os.listdir(model_dir):
+        if fn.endswith(".json") and not fn.endswith(".index.json") or fn.endswith(".model") or fn.startswith("tokenizer"):
+            src = os.path.join(model_dir, fn)
+            if os.path.isfile(src):
+                shutil.copy(src, os.path.join(out_dir, fn))
+
+
 def save_peft_adapter(out_dir: str, adapter: Dict[str, np.ndarray], *, base_model: str, r: int, alpha: float, dropout: float,
                       target_modules) -> None:
     os.makedirs(out_dir, exist_ok=True)

@@ -88,10 +88,16 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
     model_io.check_attention_window(a.model_name_or_path, seq_len)
     B, GA = a.per_device_train_batch_size, max(1, a.gradient_accumulation_steps)
     total = total_optimizer_steps(len(dataset), world, B, GA, a.num_train_epochs, a.max_steps)
+    # The reference parses --finetuning_type and then wraps LoRA regardless (cmd/tuning/train.py:266-280): a drop-in must do the
+    # same.  Full-parameter SFT (BASELINE.json configs[3]) is an explicit opt-in on top: DTX_HONOR_FINETUNING_TYPE=1.
+    full = a.finetuning_type == "full" and os.environ.get("DTX_HONOR_FINETUNING_TYPE") == "1"
+    if a.finetuning_type != "lora" and not full and rank == 0:
+        print(f"[dtx] --finetuning_type {a.finetuning_type} is ignored like in the reference worker (LoRA is always applied); "
+              "set DTX_HONOR_FINETUNING_TYPE=1 for native full-parameter SFT", flush=True)
     tc = L.TrainConfig(micro_batch=B, seq_len=seq_len, total_steps=total, lora_r=a.lora_rank, lora_alpha=a.lora_alpha,
                        lora_dropout=a.lora_dropout, lora_target=tuple(a.lora_target), lr=a.learning_rate, weight_decay=a.weight_decay,
                        beta1=a.adam_beta1, beta2=a.adam_beta2, eps=a.adam_epsilon, max_grad_norm=a.max_grad_norm,
-                       sched=a.lr_scheduler_type, warmup_steps=a.warmup_steps, grad_accum=GA, seed=a.seed)
+                       sched=a.lr_scheduler_type, warmup_steps=a.warmup_steps, grad_accum=GA, seed=a.seed, full_finetune=full)
     device = int(os.environ.get("DTX_DEVICE", rank))
     tr = L.Trainer(mc, tc, device=device, rank=rank, world=world, nccl_id=nccl_id)
     if os.environ.get("DTX_RANDOM_INIT"):  # benchmarking / scheduling harnesses: config.json only, N(0, 0.02) weights on the device
@@ -100,7 +106,8 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
         model_io.load_weights_into(tr, a.model_name_or_path)
     if a.quantization:  # QLoRA: packed NF4 base (train.py:224-230); int8 is refused by the library
         tr.quantize_base(a.quantization)
-    tr.init_lora(a.seed)
+    if not full:
+        tr.init_lora(a.seed)
     cb = LogCallback(a.output_dir, total, a.metrics_export_address, a.uid) if rank == 0 else None
 
     pad_id = tokenizer.pad_token_id
@@ -142,10 +149,15 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
     if rank == 0:
         name = f"TorchTrainer_{time.strftime('%Y-%m-%d_%H-%M-%S')}/checkpoint_000000"
         ckpt = os.path.join(a.storage_path, name)
-        adapter = tr.export_adapter()
-        for out in (ckpt, a.output_dir):
-            model_io.save_peft_adapter(out, adapter, base_model=a.model_name_or_path, r=a.lora_rank, alpha=a.lora_alpha,
-                                       dropout=a.lora_dropout, target_modules=a.lora_target)
+        if full:  # trainer.save_model of a full fine-tune writes the whole model
+            weights = tr.export_weights()
+            for out in (ckpt, a.output_dir):
+                model_io.save_full_model(out, weights, a.model_name_or_path)
+        else:
+            adapter = tr.export_adapter()
+            for out in (ckpt, a.output_dir):
+                model_io.save_peft_adapter(out, adapter, base_model=a.model_name_or_path, r=a.lora_rank, alpha=a.lora_alpha,
+                                           dropout=a.lora_dropout, target_modules=a.lora_target)
         dt = time.time() - t0
         print(f"train_runtime {dt:.1f}s, {step} optimizer steps, {tokens} real tokens on rank 0 ({tokens / max(dt, 1e-9):.1f} tokens/s/rank)",
               flush=True)
