@@ -213,6 +213,10 @@ struct dtx_trainer {
   cudaStream_t comm_stream = nullptr;
   std::vector<cudaEvent_t> ev_layer;
   cudaEvent_t ev_comm = nullptr;
+  // all-gather of the updated weights runs on the side stream, block by block in the order the NEXT forward pass needs them
+  // (globals, layer 0, 1, ...); ag_pending[b] = the main stream has not yet been told to wait for block b (L = globals)
+  std::vector<cudaEvent_t> ev_ag;
+  std::vector<uint8_t> ag_pending;
   bool quant4 = false;
   bf16* scratch_w[4] = {nullptr, nullptr, nullptr, nullptr};  // dequantised wqkv / wo / wgu / wdown of the layer in flight
   int64_t base_bytes = 0;
@@ -496,6 +500,18 @@ int base_weight(dtx_trainer* t, Layer& y, int which, const bf16** out) {
     if (_rc) return _rc;                            \
   } while (0)
 
+// full-parameter SFT, world > 1: the updated weights of block b (L = globals) are being all-gathered on the side stream;
+// make the main stream wait for it right before the block's first use
+inline void wait_weights(dtx_trainer* t, int b) {
+  if (!t->ag_pending.empty() && t->ag_pending[b]) {
+    cudaStreamWaitEvent(t->stream, t->ev_ag[b], 0);
+    t->ag_pending[b] = 0;
+  }
+}
+inline void wait_all_weights(dtx_trainer* t) {
+  for (size_t b = 0; b < t->ag_pending.size(); ++b) wait_weights(t, static_cast<int>(b));
+}
+
 // full-parameter SFT, world > 1: reduce-scatter one gradient block in place on the side stream once the main stream has
 // produced it (event), so that the transfer overlaps the rest of the backward pass
 int reduce_scatter_block(dtx_trainer* t, bf16* block, int64_t elems, int ev_idx) {
@@ -533,9 +549,11 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   const float p_drop = backward ? tc.lora_dropout : 0.f;  // eval (model.eval()) runs the same path with p = 0
   t->fwd_count += 1;
 
+  wait_weights(t, L);  // globals (embedding, lm_head, final norm)
   CK(embedding_fwd(t->d_ids, t->embed, t->xs[0], M, d, V, s), 1);
   for (int l = 0; l < L; ++l) {
     Layer& y = t->layers[l];
+    wait_weights(t, l);
     CK(rmsnorm_fwd(t->xs[l], y.norm1, y.h1, y.rstd1, M, d, mc.rms_eps, s), 1);
     const bf16* lora_in = y.h1;
     if (drop) {  // peft: lora_A(lora_dropout(x)) with one nn.Dropout per wrapped module -> one dropped copy per target
@@ -857,13 +875,21 @@ int optimizer_step_full(dtx_trainer* t, float* lr_used) {
     a.sumsq = t->d_sumsq; a.max_grad_norm = tc.max_grad_norm; a.grad_norm_out = t->d_gnorm;
     CK(adamw_shard_step(a, s), 1);
   }
-  if (N > 1) {  // every rank gets every updated slice (in place: the send slice sits at its final position)
-    for (int blk = 0; blk <= L; ++blk) {
+  if (N > 1) {
+    // Every rank gets every updated slice (in place: the send slice sits at its final position).  The all-gathers run on the
+    // side stream in the order the next forward pass consumes the blocks, so that they overlap it: measured on 8 GPUs (13B),
+    // the 26 GB all-gather was 58 of the step's 658 ms when it sat on the main stream.
+    CKM(cudaEventRecord(t->ev_comm, s));
+    CKM(cudaStreamWaitEvent(t->comm_stream, t->ev_comm, 0));
+    for (int i = 0; i <= L; ++i) {
+      const int blk = i == 0 ? L : i - 1;  // globals first, then layer 0, 1, ...
       int64_t n, moff;
       bf16* w = slice(blk, t->w_flat, &n, &moff);
       bf16* base = w - static_cast<int64_t>(t->rank) * n;
-      int rc = api->AllGather(w, base, static_cast<size_t>(n), kNcclBfloat16, t->nccl_comm, s);
+      int rc = api->AllGather(w, base, static_cast<size_t>(n), kNcclBfloat16, t->nccl_comm, t->comm_stream);
       if (rc != 0) return t->fail(DTX_ERR_NCCL, "ncclAllGather failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
+      CKM(cudaEventRecord(t->ev_ag[blk], t->comm_stream));
+      t->ag_pending[blk] = 1;
       t->launches += 1;
     }
   }
@@ -1094,6 +1120,9 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
     cudaEventCreateWithFlags(&t->ev_comm, cudaEventDisableTiming);
     t->ev_layer.resize(mc->n_layers + 1);
     for (auto& e : t->ev_layer) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    t->ev_ag.resize(mc->n_layers + 1);
+    for (auto& e : t->ev_ag) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    t->ag_pending.assign(mc->n_layers + 1, 0);
   }
   int rc = create_buffers(t);
   if (rc) {
@@ -1130,7 +1159,7 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
 void dtx_trainer_destroy(dtx_trainer* t) {
   if (!t) return;
   cudaSetDevice(t->device);
-  cudaDeviceSynchronize();
+  cudaDeviceSynchronize();  // includes the side stream's collectives
   if (t->nccl_comm) {
     NcclApi* api = nccl_api();
     if (api) api->CommDestroy(t->nccl_comm);
@@ -1142,6 +1171,7 @@ void dtx_trainer_destroy(dtx_trainer* t) {
   if (t->ev_ar) cudaEventDestroy(t->ev_ar);
   if (t->ev_comm) cudaEventDestroy(t->ev_comm);
   for (auto e : t->ev_layer) cudaEventDestroy(e);
+  for (auto e : t->ev_ag) cudaEventDestroy(e);
   if (t->comm_stream) cudaStreamDestroy(t->comm_stream);
   if (t->stream) cudaStreamDestroy(t->stream);
   delete t;
@@ -1150,7 +1180,8 @@ void dtx_trainer_destroy(dtx_trainer* t) {
 int32_t dtx_load_tensor(dtx_trainer* t, const char* name, const void* host, int32_t dtype, const int64_t* shape, int32_t nd) {
   if (!t || !name || !host || !shape || nd < 1 || nd > 2) return t ? t->fail(DTX_ERR_INVALID, "bad argument") : DTX_ERR_INVALID;
   cudaSetDevice(t->device);
-  t->master_valid = false;  // full-parameter SFT: the fp32 master copies are rebuilt from the bf16 weights at the next step
+  wait_all_weights(t);      // full-parameter SFT: no all-gather may still be writing the weight buffer
+  t->master_valid = false;  // ... and the fp32 master copies are rebuilt from the bf16 weights at the next step
   const int64_t d = t->mc.hidden, F = t->mc.ffn, V = t->mc.vocab, r = t->tc.lora_r, dq = t->dq, dkv = t->dkv;
   const int64_t rows = shape[0], cols = nd == 2 ? shape[1] : 1;
   auto expect = [&](int64_t er, int64_t ec) { return rows == er && cols == ec; };
@@ -1464,6 +1495,7 @@ int32_t dtx_export_weight(dtx_trainer* t, const char* name, void* host_out, int6
   if (!t || !name || !host_out) return t ? t->fail(DTX_ERR_INVALID, "null argument") : DTX_ERR_INVALID;
   if (!t->full) return t->fail(DTX_ERR_STATE, "export_weight: only for full-parameter SFT trainers (LoRA: dtx_export_adapter)");
   cudaSetDevice(t->device);
+  wait_all_weights(t);
   CKM(cudaStreamSynchronize(t->stream));
   const int64_t d = t->mc.hidden, F = t->mc.ffn, V = t->mc.vocab, dq = t->dq, dkv = t->dkv, L = t->mc.n_layers;
   const bf16* flat = grad ? t->g_flat : t->w_flat;
