@@ -299,7 +299,7 @@ constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
 __host__ __device__ constexpr int g2_out_stage_bytes(int epi) { return epi == EPI_SWIGLU_BWD ? 32768 : 0; }
 constexpr int G2_GROUP_M = 16;  // in 256-row tiles (swept in tools/sweep_group_m.py: 16 >= 8 on every step shape)
 
-template <bool B_MN, int EPI>
+template <bool B_MN, int EPI, bool A_MN = false>  // A_MN: A is row-major [K, M] (weight-gradient GEMMs: dW = dY^T X)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -379,7 +379,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const CUtensorMap* ma = seg2 ? &tmA2 : &tmA;
           const CUtensorMap* mb = seg2 ? &tmB2 : &tmB;
           if (leader) {
-            tma_load_2d_pair(a_dst, ma, leader_full, kk, m0);
+            if (!A_MN) {
+              tma_load_2d_pair(a_dst, ma, leader_full, kk, m0);
+            } else {  // two [64 k x 64 m] boxes
+              tma_load_2d_pair(a_dst, ma, leader_full, m0, kk);
+              tma_load_2d_pair(a_dst + 8192, ma, leader_full, m0 + 64, kk);
+            }
             if (!B_MN) {
               tma_load_2d_pair(b_dst, mb, leader_full, kk, n0);
             } else {
@@ -394,7 +399,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     if (rank == 0) {
       const bool leader = elect_one();
-      constexpr uint32_t idesc = umma_idesc_bf16(256, 256, 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(256, 256, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -415,7 +420,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t b_base = a_base + G2_A_BYTES;
 #pragma unroll
           for (int k16 = 0; k16 < BK / 16; ++k16) {
-            const uint64_t da = umma_desc_kmajor(a_base + k16 * 32);
+            const uint64_t da = A_MN ? umma_desc_mnmajor(a_base + k16 * 2048, 8192) : umma_desc_kmajor(a_base + k16 * 32);
             const uint64_t db = B_MN ? umma_desc_mnmajor(b_base + k16 * 2048, 8192) : umma_desc_kmajor(b_base + k16 * 32);
             if (leader) umma_bf16_pair(d_tmem, da, db, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
           }
@@ -749,9 +754,9 @@ cudaError_t launch_epi(const GemmArgs& a, cudaStream_t s) {
 int g_use_pair_kernel = 1;
 int g_pair_group_m = G2_GROUP_M;
 
-template <bool B_MN, int EPI>
+template <bool B_MN, int EPI, bool A_MN = false>
 cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
-  auto kern = gemm2_kernel<B_MN, EPI>;
+  auto kern = gemm2_kernel<B_MN, EPI, A_MN>;
   static DeviceOnce attr;
   if (cudaError_t e = attr.run([&] {
         return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES + g2_out_stage_bytes(EPI));
@@ -762,8 +767,9 @@ cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
   bool ok = true;
   if (EPI == EPI_SWIGLU_BWD)  // d(gate|up) [M, 2N] bf16, stored in [128 x 64] boxes
     ok &= make_tmap_2d_bf16(&tC, a.C, 2ull * static_cast<uint64_t>(a.N), a.M, a.ldc, 64, 128);
-  ok &= make_tmap_2d_bf16(&tA, a.A, a.K, a.M, a.lda, 64, 128);
+  ok &= A_MN ? make_tmap_2d_bf16(&tA, a.A, a.M, a.K, a.lda, 64, 64) : make_tmap_2d_bf16(&tA, a.A, a.K, a.M, a.lda, 64, 128);
   ok &= B_MN ? make_tmap_2d_bf16(&tB, a.B, a.N, a.K, a.ldb, 64, 64) : make_tmap_2d_bf16(&tB, a.B, a.K, a.N, a.ldb, 64, 128);
+  if (A_MN && a.K2 > 0) return cudaErrorInvalidValue;
   if (a.K2 > 0) {
     ok &= make_tmap_2d_bf16(&tA2, a.A2, a.K2, a.M, a.lda2, 64, 128);
     ok &= B_MN ? make_tmap_2d_bf16(&tB2, a.B2, a.N, a.K2, a.ldb2, 64, 64) : make_tmap_2d_bf16(&tB2, a.B2, a.K2, a.N, a.ldb2, 64, 128);
@@ -847,6 +853,12 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t s) {
   if (bn == 0) bn = (a.N <= 64) ? 64 : ((a.N <= 128) ? 128 : 256);
   if (bn == 256 && !a.a_mn_major && a.split_k <= 1 && g_use_pair_kernel && a.M > 128)
     return a.b_mn_major ? launch2_epi<true>(a, s) : launch2_epi<false>(a, s);
+  // weight-gradient GEMMs of full-parameter SFT (A and B MN-major, no K-extension, wide in both dimensions): CTA-pair kernel too
+  if (bn == 256 && a.a_mn_major && a.b_mn_major && a.split_k <= 1 && g_use_pair_kernel && a.M > 128 && a.N >= 256 && a.K2 == 0 &&
+      (a.lda & 7) == 0 && (a.ldb & 7) == 0) {
+    if (a.epilogue == EPI_BF16) return launch2<true, EPI_BF16, true>(a, s);
+    if (a.epilogue == EPI_BF16_ADD) return launch2<true, EPI_BF16_ADD, true>(a, s);
+  }
   switch (bn) {
     case 64: return launch_major<64>(a, s);
     case 128: return launch_major<128>(a, s);

@@ -103,6 +103,30 @@ def check_gemm_tn(Mp=384, N=64, K=1024, split_k=4):
     return {"f32": e}
 
 
+def check_gemm_tn_pair(Mp=1000, N=768, K=2048):
+    """Weight-gradient shape through the CTA-pair kernel with BOTH operands MN-major: C[Mp, N] = A^T B (A [K, Mp], B [K, N]),
+    plain and accumulating (EPI_BF16_ADD in place), ragged Mp; bitwise equal to the single-CTA kernel."""
+    A, B = _rand(K, Mp, seed=36), _rand(K, N, seed=37)
+    ref = A.float().t() @ B.float()
+    out = gemm(A, B, a_mn=True, b_mn=True)
+    e = rel_err(out, ref)
+    assert e < 6e-3, f"TN pair rel_err {e}"
+    R = _rand(Mp, N, seed=38)
+    acc = R.clone()
+    lib = L.load()
+    ok(lib.dtx_gemm_bf16(P(A), A.stride(0), 1, P(B), B.stride(0), 1, None, 0, None, 0, 0, P(acc), N, P(acc), N, Mp, N, K, L.EPI_BF16_ADD, 1, 0, STREAM()))
+    torch.cuda.synchronize()
+    e_acc = rel_err(acc, ref + R.float())
+    assert e_acc < 6e-3, f"TN pair accumulate rel_err {e_acc}"
+    L.set_option("gemm_pair_kernel", 0)
+    try:
+        single = gemm(A, B, a_mn=True, b_mn=True)
+    finally:
+        L.set_option("gemm_pair_kernel", 1)
+    assert torch.equal(out, single), "pair and single-CTA kernels must agree bitwise"
+    return {"bf16": e, "accumulate": e_acc}
+
+
 def check_gemm_kext():
     M, N, K, K2 = 256, 768, 256, 64
     A, B, A2, B2 = _rand(M, K, seed=8), _rand(N, K, seed=9), _rand(M, K2, seed=10), _rand(N, K2, seed=11)
@@ -1169,7 +1193,7 @@ ALL = {
     "gemm_nt": check_gemm_nt, "gemm_nt_bn64": lambda: check_gemm_nt(N=64, block_n=64),
     "gemm_nt_bn128": lambda: check_gemm_nt(N=384, block_n=128), "gemm_nn": check_gemm_nn,
     "gemm_nn_bn64": lambda: check_gemm_nn(N=64, block_n=64), "gemm_tn": check_gemm_tn,
-    "gemm_tn_nosplit": lambda: check_gemm_tn(split_k=1), "gemm_kext": check_gemm_kext, "gemm_ragged": check_gemm_ragged,
+    "gemm_tn_nosplit": lambda: check_gemm_tn(split_k=1), "gemm_tn_pair": check_gemm_tn_pair, "gemm_kext": check_gemm_kext, "gemm_ragged": check_gemm_ragged,
     "gemm_large": check_gemm_large, "gemm_single_cta": check_gemm_single_cta, "gemm_pair_vs_single": check_gemm_pair_vs_single, "rmsnorm": check_rmsnorm, "rmsnorm_small": lambda: check_rmsnorm(M=64, d=256),
     "rope": check_rope, "swiglu": check_swiglu, "lora_dropout": check_lora_dropout, "nf4": check_nf4, "nf4_pack": check_nf4_pack,
     "gemm_rope_epilogue": check_gemm_rope_epilogue,

@@ -15,7 +15,7 @@ def _run(name):
 
 
 @pytest.mark.parametrize("name", ["gemm_nt", "gemm_nt_bn64", "gemm_nt_bn128", "gemm_nn", "gemm_nn_bn64", "gemm_tn",
-                                  "gemm_tn_nosplit", "gemm_kext", "gemm_ragged", "gemm_large", "gemm_single_cta", "gemm_pair_vs_single",
+                                  "gemm_tn_nosplit", "gemm_tn_pair", "gemm_kext", "gemm_ragged", "gemm_large", "gemm_single_cta", "gemm_pair_vs_single",
                                   "gemm_rope_epilogue", "gemm_rope_epilogue_7b", "gemm_swiglu_epilogues"])
 def test_gemm(name):
     _run(name)
