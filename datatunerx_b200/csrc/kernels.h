@@ -56,6 +56,8 @@ void attn_set_fwd_exp_fma_every(int n);
 void gemm_set_pair_group_m(int tiles);  // rasterisation group height of the pair kernel, in 256-row tiles
 // 1 (default): RoPE / SwiGLU run inside GEMM and attention epilogues; 0: separate HBM-bound kernels (A/B, tiny M)
 void trainer_set_fused_epilogues(int on);
+// 1 (default): --quantization int4 expands the next NF4 matrix on a side stream under the current GEMM; 0: inline
+void trainer_set_nf4_prefetch(int on);
 
 // ---------------------------------------------------------------------------------------------
 // flash attention (causal, head_dim 128), packed qkv layout [B*S, (H + 2*Hkv)*128] (q heads | k heads | v heads per token)

@@ -78,6 +78,7 @@ constexpr int kNcclBfloat16 = 9;
 constexpr int kNcclSum = 0;
 
 thread_local std::string g_error;
+int g_nf4_prefetch = 1;     // expand the next NF4 matrix on a side stream while the current GEMM runs (0: inline, for A/B runs)
 int g_fused_epilogues = 1;  // RoPE / SwiGLU fused into the GEMM and attention epilogues (needs M > 128: CTA-pair GEMM)
 
 // ------------------------------------------------------------------------------------------------
@@ -154,6 +155,7 @@ enum { W_QKV = 0, W_O = 1, W_GU = 2, W_DOWN = 3 };
 
 }  // namespace
 void trainer_set_fused_epilogues(int on) { g_fused_epilogues = on; }
+void trainer_set_nf4_prefetch(int on) { g_nf4_prefetch = on; }
 }  // namespace dtx
 
 using namespace dtx;
@@ -219,6 +221,9 @@ struct dtx_trainer {
   std::vector<uint8_t> ag_pending;
   bool quant4 = false;
   bf16* scratch_w[4] = {nullptr, nullptr, nullptr, nullptr};  // dequantised wqkv / wo / wgu / wdown of the layer in flight
+  cudaEvent_t ev_deq[4] = {nullptr, nullptr, nullptr, nullptr}, ev_scr[4] = {nullptr, nullptr, nullptr, nullptr};
+  int deq_layer[4] = {-1, -1, -1, -1};       // layer whose matrix of that type sits (or is being expanded) in the scratch
+  uint8_t deq_pending[4] = {0, 0, 0, 0};     // expansion launched on the side stream, main stream not yet told to wait
   int64_t base_bytes = 0;
   float2* rope_cs = nullptr;
   float2* rope_cs_t = nullptr;  // the same table transposed to [D/2][S]: coalesced when thread r needs position q0 + r (attention backward epilogues)
@@ -477,27 +482,70 @@ int refresh_shadows(dtx_trainer* t) {
   return DTX_OK;
 }
 
-// Frozen base weight `which` of layer y for the next GEMM.  bf16-resident: the pointer.  --quantization int4: the packed NF4
-// codes are expanded into the per-trainer scratch first (HBM-bound: 0.56 B read + 2 B written per weight, ~85 us per layer
-// of a 7B model and direction) - the values are exactly bitsandbytes' dequantize_4bit output, so the GEMM sees what the
-// reference's 4-bit matmul multiplies with.
-int base_weight(dtx_trainer* t, Layer& y, int which, const bf16** out) {
+// Frozen base weight `which` of layer l for the next GEMM.  bf16-resident: the pointer.  --quantization int4: the packed NF4
+// codes are expanded into the per-trainer scratch of that matrix type (HBM-bound: 0.56 B read + 2 B written per weight, ~85 us
+// per layer of a 7B model and direction) - the values are exactly bitsandbytes' dequantize_4bit output, so the GEMM sees what
+// the reference's 4-bit matmul multiplies with.  The expansion of the NEXT matrix in program order is launched on a side
+// stream as soon as the current one is handed out: its small CTAs (no shared memory) co-reside with the persistent GEMM
+// CTAs and use HBM bandwidth the tensor-bound GEMM leaves idle, so that the expansion disappears from the critical path.
+int nf4_expand(dtx_trainer* t, int l, int which, cudaStream_t s) {
+  Layer& y = t->layers[l];
+  const int64_t d = t->mc.hidden, F = t->mc.ffn;
+  const int64_t n[4] = {static_cast<int64_t>(t->W) * d, d * d, 2 * F * d, d * F};
+  CK(nf4_dequant_bf16(y.q4[which], y.absmax[which], t->scratch_w[which], n[which], s), 1);
+  return DTX_OK;
+}
+// next (layer, matrix) the step will ask for after (l, which); backward = the step is in (or about to enter) its backward pass
+bool next_weight(const dtx_trainer* t, int l, int which, bool backward, bool will_backward, int* nl, int* nw) {
+  const int L = t->mc.n_layers;
+  if (!backward) {  // forward order: qkv, o, gu, down
+    if (which < W_DOWN) { *nl = l; *nw = which + 1; return true; }
+    if (l + 1 < L) { *nl = l + 1; *nw = W_QKV; return true; }
+    if (will_backward) { *nl = L - 1; *nw = W_DOWN; return true; }
+    return false;
+  }
+  // backward order: down, gu, o, qkv (layer 0's qkv is never asked for: no consumer of its input gradient)
+  if (which > W_QKV) {
+    if (which - 1 == W_QKV && l == 0) return false;
+    *nl = l; *nw = which - 1; return true;
+  }
+  if (l - 1 >= 0) { *nl = l - 1; *nw = W_DOWN; return true; }
+  return false;
+}
+int base_weight(dtx_trainer* t, int l, int which, bool backward, bool will_backward, const bf16** out) {
+  Layer& y = t->layers[l];
   bf16* res[4] = {y.wqkv, y.wo, y.wgu, y.wdown};
   if (!t->quant4) {
     *out = res[which];
     return DTX_OK;
   }
-  const int64_t d = t->mc.hidden, F = t->mc.ffn;
-  const int64_t n[4] = {static_cast<int64_t>(t->W) * d, d * d, 2 * F * d, d * F};
-  CK(nf4_dequant_bf16(y.q4[which], y.absmax[which], t->scratch_w[which], n[which], t->stream), 1);
+  if (t->deq_layer[which] == l) {  // already in the scratch (the frozen weights never change), or on its way there
+    if (t->deq_pending[which]) CKM(cudaStreamWaitEvent(t->stream, t->ev_deq[which], 0));
+  } else {
+    int rc = nf4_expand(t, l, which, t->stream);
+    if (rc) return rc;
+  }
+  t->deq_pending[which] = 0;
+  t->deq_layer[which] = l;
   *out = t->scratch_w[which];
+  int nl, nw;
+  if (t->copy_stream && next_weight(t, l, which, backward, will_backward, &nl, &nw) && t->deq_layer[nw] != nl) {
+    // the scratch of type nw was last read by a GEMM launched earlier on the main stream: order the overwrite behind it
+    CKM(cudaEventRecord(t->ev_scr[nw], t->stream));
+    CKM(cudaStreamWaitEvent(t->copy_stream, t->ev_scr[nw], 0));
+    int rc = nf4_expand(t, nl, nw, t->copy_stream);
+    if (rc) return rc;
+    CKM(cudaEventRecord(t->ev_deq[nw], t->copy_stream));
+    t->deq_pending[nw] = 1;
+    t->deq_layer[nw] = nl;
+  }
   return DTX_OK;
 }
-#define BASEW(which, ptr)                           \
-  const bf16* ptr = nullptr;                        \
-  do {                                              \
-    int _rc = base_weight(t, y, which, &ptr);       \
-    if (_rc) return _rc;                            \
+#define BASEW(which, ptr)                                                        \
+  const bf16* ptr = nullptr;                                                     \
+  do {                                                                           \
+    int _rc = base_weight(t, l, which, in_backward, backward, &ptr);             \
+    if (_rc) return _rc;                                                         \
   } while (0)
 
 // full-parameter SFT, world > 1: the updated weights of block b (L = globals) are being all-gathered on the side stream;
@@ -545,6 +593,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   const float att_scale = 1.0f / sqrtf(static_cast<float>(D));
   const bool fused = g_fused_epilogues && M > 128 && ((t->dq + t->dkv) % 256 == 0) && (W % 256 == 0);  // whole 256-column tiles
   const bool lora = !t->full;    // full-parameter SFT: no adapters, every weight gets a gradient
+  bool in_backward = false;      // which half of the step asks for a base weight (prefetch order of the NF4 expansion)
   const bool drop = lora && t->dropout;  // adapters laid out for per-target dropped inputs (KA = nt*d)
   const float p_drop = backward ? tc.lora_dropout : 0.f;  // eval (model.eval()) runs the same path with p = 0
   t->fwd_count += 1;
@@ -632,6 +681,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   CK(cross_entropy_fwd_bwd(t->logits, V, t->d_shift, t->d_nvalid, t->row_loss, backward ? t->dlogits : nullptr, V, M, V, s, valid_idx), 1);
   CK(loss_reduce(t->row_loss, t->d_nvalid, t->d_loss, M, s), 1);
   if (!backward) return DTX_OK;
+  in_backward = true;
 
   const int accumulate = t->micro_idx > 0 ? 1 : 0;
   // weight gradient of a Linear: dW[out, in] (+)= dY^T X - a token-contraction GEMM with both operands MN-major
@@ -1173,6 +1223,11 @@ void dtx_trainer_destroy(dtx_trainer* t) {
   for (auto e : t->ev_layer) cudaEventDestroy(e);
   for (auto e : t->ev_ag) cudaEventDestroy(e);
   if (t->comm_stream) cudaStreamDestroy(t->comm_stream);
+  if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+  for (int i = 0; i < 4; ++i) {
+    if (t->ev_deq[i]) cudaEventDestroy(t->ev_deq[i]);
+    if (t->ev_scr[i]) cudaEventDestroy(t->ev_scr[i]);
+  }
   if (t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
@@ -1340,6 +1395,13 @@ int32_t dtx_quantize_base(dtx_trainer* t, int32_t mode) {
   }
   for (int i = 0; i < 4; ++i)
     if (!t->alloc(&t->scratch_w[i], static_cast<size_t>(n[i]))) return DTX_ERR_CUDA;
+  if (g_nf4_prefetch) {
+    CKM(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) {
+      CKM(cudaEventCreateWithFlags(&t->ev_deq[i], cudaEventDisableTiming));
+      CKM(cudaEventCreateWithFlags(&t->ev_scr[i], cudaEventDisableTiming));
+    }
+  }
   t->quant4 = true;
   return DTX_OK;
 }
