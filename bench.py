@@ -307,6 +307,8 @@ def run_native(args, rank: int, local_rank: int, world: int):
     nccl_id = rv.broadcast_bytes(L.nccl_unique_id)
     if os.environ.get("DTX_FWD_EXP_FMA"):  # A/B of the forward softmax's FMA-pipe exp2 fraction
         L.set_option("attn_fwd_exp_fma_every", int(os.environ["DTX_FWD_EXP_FMA"]))
+    if os.environ.get("DTX_NF4_PREFETCH"):  # A/B of the side-stream NF4 expansion
+        L.set_option("nf4_prefetch", int(os.environ["DTX_NF4_PREFETCH"]))
     if os.environ.get("DTX_GROUP_M"):  # rasterisation sweep of the CTA-pair GEMM (tools/gpu_round.sh sweep_gm)
         L.set_option("gemm_group_m", int(os.environ["DTX_GROUP_M"]))
     tr = L.Trainer(mc, tc, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)

@@ -41,8 +41,13 @@ for s in $STEPS; do
     refarm) timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_reference.json 2> $OUT/bench_reference.err;;
     varlen) timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen.json 2> $OUT/bench_varlen.err;;
     qlora) timeout 600 python bench.py --config mistral7b_qlora --steps 5 --warmup 3 > $OUT/bench_qlora.json 2> $OUT/bench_qlora.err;;
-    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches.csv \
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1600 -c 2000 --csv --log-file $OUT/launches.csv \
                 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1;;
+    ncu_gemm_bwd) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel --launch-skip 660 --launch-count 10 -o $OUT/gemm_bwd -f \
+                python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_gemm_bwd.log 2>&1;;
+    ncu_attn3) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_ --launch-skip 318 --launch-count 4 -o $OUT/attn3 -f \
+                python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_attn3.log 2>&1;;
+    qlora_ab) for pf in 1 0; do DTX_NF4_PREFETCH=$pf timeout 600 python bench.py --config mistral7b_qlora --steps 6 --warmup 3 > $OUT/bench_qlora_prefetch$pf.json 2> $OUT/bench_qlora_prefetch$pf.err; done;;
     ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_ --launch-skip 12 --launch-count 3 -o $OUT/attn -f \
                 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_attn.log 2>&1;;
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel --launch-skip 40 --launch-count 12 -o $OUT/gemm -f \

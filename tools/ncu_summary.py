@@ -18,12 +18,17 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "launch__
         "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
-def launches(path, first_n=None):
+def launches(path, first_n=None, one_step=False):
     lines = open(path).read().splitlines()
     i = [k for k, l in enumerate(lines) if l.startswith('"ID"')][0]
     rows = list(csv.DictReader(lines[i:]))
     if first_n:
         rows = rows[:first_n]
+    if one_step:  # exactly one training step: from one embedding gather (the first kernel of a step) to the next
+        marks = [k for k, r in enumerate(rows) if "embedding_kernel" in r["Kernel Name"]]
+        if len(marks) >= 2:
+            rows = rows[marks[-2]:marks[-1]]
+            print(f"# one training step: launches {marks[-2]}..{marks[-1] - 1} of the capture (embedding gather to embedding gather)")
     agg, tot = collections.OrderedDict(), 0.0
     for r in rows:
         n = re.sub(r"\(.*", "", r["Kernel Name"]).replace("<unnamed>::", "").replace("unnamed>::", "").replace("void ", "")
@@ -53,5 +58,7 @@ def rep(path):
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else None)
+    elif sys.argv[1] == "step":
+        launches(sys.argv[2], None, one_step=True)
     else:
         rep(sys.argv[2])
