@@ -9,17 +9,22 @@
 // lse2 [B,H,S] = log2-domain log-sum-exp of the scaled scores (m + log2 l).
 //
 // Kernels (one CTA per SM).  Roles are warp-specialised: compute warps where thread r owns TMEM lane r = one row of a score
-// tile, ONE MMA issuer warp (warp-uniform code, an elected lane issues every tcgen05.mma) and ONE TMA loader warp:
-//   attn_fwd2_kernel  : CTA = two 128-row query tiles sharing one K/V ring of 64-row blocks.  S = Q K^T (UMMA 128x64x16) in two
-//                       score buffers per tile, softmax in registers, P is written bf16-packed over the score columns it came
-//                       from and is the TENSOR-MEMORY A operand of O += P V; O accumulates in tensor memory (lazy rescale).
-//                       (attn_fwd_kernel: one tile per CTA, two CTAs per SM, separate K and V rings - same arithmetic, same speed,
-//                       bitwise the same result; behind the "attn_fwd_two_tiles" = 0 option.)
-//   attn_dq_kernel    : CTA = two 128-row query tiles (groups).  S, dP = dO V^T, dS = P o (dP - delta) * scale -> TMEM operand,
-//                       dQ += dS K (K as MN-major B) accumulates in TMEM over the whole KV loop.
+// tile, MMA issuer warp(s) (warp-uniform code, an elected lane issues every tcgen05.mma) and ONE TMA loader warp:
+//   attn_fwd2_kernel  : CTA = two 128-row query tiles sharing one K/V ring of 64-row blocks, ONE ISSUER WARP PER TILE.  S = Q K^T
+//                       (UMMA 128x64x16) in two score buffers per tile, softmax in registers (a third of the exponentials on the
+//                       FMA pipe), P is written bf16-packed over the score columns it came from and is the TENSOR-MEMORY A
+//                       operand of O += P V; O accumulates in tensor memory (lazy rescale).
+//   attn_dq1_kernel   : CTA = one 128-row query tile with Q and dO resident in tensor memory.  S, dP = dO V^T (double-buffered),
+//                       dS = P o (dP - delta) * scale -> TMEM operand, dQ += dS K (K as MN-major B) accumulates in TMEM; delta =
+//                       rowsum(dO o O) and the inverse rotary of dQ are computed here.
 //   attn_dkv_kernel   : CTA = 128 KV rows, loops over 64-row Q blocks of every query head of its KV group.  S^T = K Q^T,
 //                       dP^T = V dO^T (double-buffered), P^T / dS^T -> TMEM operands, dV += P^T dO, dK += dS^T Q.
-// What shaped them (profiles/r01_ncu_attn_issue_bound.txt, r01_ubench_mma_latency.txt):
+// All three take optional true row lengths (tiles that hold only right padding are skipped and written as zeros) and an
+// optional sliding window (query i sees keys i - window .. i).
+// What shaped them (profiles/r01_ncu_attn_issue_bound.txt, r01_ubench_mma_latency.txt, r02_attn_phase_timing_*.txt):
+//   * a tcgen05.mma issue blocks for the MMA's duration (the pipe's queue is ~1 deep): whatever else the issuing warp does -
+//     mbarrier checks cost ~90 cycles each even when the phase is long complete - is time the tensor pipe idles.  The forward
+//     has one issuer per tile; in the backward kernels the ring-slot checks moved to the compute warps, which have slack;
 //   * a single warp can feed the tensor pipe only if its loop is tiny: the issuers are unrolled over the ring (slot, buffer,
 //     parity are immediates) and add constants to precomputed descriptor low words; loads live in a separate warp;
 //   * P / dS never touch shared memory (tcgen05.mma with A in TMEM): no st.shared + proxy fence, no operand re-read, and the
