@@ -214,8 +214,10 @@ def run_reference(args, rank: int):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the profiled GEMMs at the bench shapes (ncu --set full):
-# profiles/r01_ncu_dominant_gemm_final.txt (gate|up NT shape, plain epilogue); round-2 captures update this table.
-GEMM_DRAM_BYTES = {"nt_gate_up": 2.0769e9}
+# profiles/r01_ncu_dominant_gemm_final.txt (gate|up NT shape, plain epilogue), profiles/r02_ncu_gemm.txt (the backward variants:
+# dX of gate|up with K = 22016 re-reads its operands 5.6x from DRAM at 99.5 % tensor activity - DESIGN.md 4.1 on why that
+# costs neither time nor measurable energy).
+GEMM_DRAM_BYTES = {"nt_gate_up": 2.0769e9, "nn_dh2": 5.2065e9, "nn_swiglu_bwd": 2.8669e9}
 
 
 def time_step_gemms(torch, L):

@@ -38,6 +38,7 @@
 #include "kernels.h"
 
 #include <mutex>
+#include <type_traits>
 
 namespace dtx {
 
@@ -166,7 +167,10 @@ constexpr int FW2_SV = FW2_SK + FW2_NS * 16384;
 constexpr int FW2_BAR = FW2_SV + FW2_NS * 16384;
 constexpr int FW2_SMEM = FW2_BAR + 256 + 1024;
 
-template <int EXP_FMA_EVERY>  // every N-th pair of exponentials on the FMA pipe instead of the MUFU (0 = none)
+// WIN: sliding-window instantiation (p.window > 0).  The plain causal instantiation carries none of the window code: in the
+// backward kernels the extra compares in the (if-converted) mask path cost 100-260 cycles per block on EVERY block
+// (profiles/r02_attn_window_regression.txt).
+template <int EXP_FMA_EVERY, bool WIN>  // every N-th pair of exponentials on the FMA pipe instead of the MUFU (0 = none)
 __global__ void __launch_bounds__(FW2_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
@@ -191,7 +195,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // Sliding window: keys before q00 - window are invisible to every row of this CTA: the K/V ring starts at block jlo (both tiles
   // start there - the at most two leading blocks that only tile 0 can see are fully masked for tile 1).  Block counts below are
   // relative to jlo; a row may then meet blocks in which it sees nothing (handled by the -inf-safe softmax reference).
-  const int jlo = p.window > 0 ? max(0, (q00 - p.window) / 64) : 0;
+  const int window = WIN ? p.window : 0;
+  const int jlo = WIN ? max(0, (q00 - window) / 64) : 0;
   const int n0 = q00 < len ? (q00 + 128) / 64 - jlo : 0, n1 = q01 < len ? (q01 + 128) / 64 - jlo : 0;  // KV blocks each tile needs (0: padding only)
   const int n = max(n0, n1);
   auto nt = [&](int t) { return t ? n1 : n0; };
@@ -344,10 +349,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int c = 0; c < 64; ++c)
           if (kv0 + c > qrow) sv[c] = 0xff800000u;  // -inf
       }
-      if (p.window > 0 && kv0 < q0 + 127 - p.window) {  // blocks that straddle the far edge of the window
+      if (WIN && kv0 < q0 + 127 - window) {  // blocks that straddle the far edge of the window
 #pragma unroll
         for (int c = 0; c < 64; ++c)
-          if (kv0 + c < qrow - p.window) sv[c] = 0xff800000u;
+          if (kv0 + c < qrow - window) sv[c] = 0xff800000u;
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -364,7 +369,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const bool grow = mx > m_ref + FW2_RESCALE_T;  // also the first visible key of a windowed row (m_ref = -inf): alpha = 0, O = 0 so far
         if (__any_sync(0xffffffffu, grow)) {  // rare: move the reference of the rows that need it and rescale their output
           const float m_new = grow ? mx : m_ref;
-          const float alpha = grow ? fast_exp2(m_ref - m_new) : 1.f;  // (-inf) - (-inf) of a windowed row that still sees nothing would be NaN
+          // (-inf) - (-inf) of a windowed row that still sees nothing would be NaN
+          const float alpha = (!WIN || grow) ? fast_exp2(m_ref - m_new) : 1.f;
           mbar_wait(my_o, (j - 1) & 1);  // P V(j-1) (and every earlier one) has landed in the output tile
           tc_fence_after();
 #pragma unroll
@@ -385,7 +391,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       float2 rs = make_float2(0.f, 0.f);
       // a row that has not met a visible key yet keeps m_ref = -inf: every score is -inf and must give exp2(-inf) = 0, not
       // exp2(-inf + inf) = NaN
-      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+      const float m_use = (WIN && m_ref == -INFINITY) ? 0.f : m_ref;
       const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_use, -m_use);
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {  // packed fp32 pairs; every other pair of exponentials on the FMA pipe (exp2_fma2)
@@ -475,6 +481,12 @@ constexpr int DQ1_BAR = DQ1_SV + DQ1_NS * 16384;
 constexpr int DQ1_XD = DQ1_BAR + 256;           // [2 halves][128] partial delta sums
 constexpr int DQ1_SMEM = DQ1_XD + 1024 + 1024;
 
+// WIN: see attn_fwd2_kernel.  EXP_FMA: every N-th pair of exponentials on the FMA pipe (A/B switch "attn_dq_exp_fma_every").
+// The MMA issuer checks the K/V ring slot of block j + 2 itself: letting the compute warps do it before they report block j
+// (as in the dK/dV kernel, whose compute warps have slack) was measured 4 % slower here - the block is not there yet when
+// they look (st+arrive 45 -> 240 cycles), and the exp / dS phase is on this kernel's critical chain
+// S(j) -> dS(j) -> dQ(j) -> S(j+2) (profiles/r02_attn_window_regression.txt).
+template <bool WIN, int EXP_FMA>
 __global__ void __launch_bounds__(DKV_THREADS, 1)
 attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmO,
@@ -493,7 +505,8 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int h = bh % p.H, b = bh / p.H;
   const int q0 = qb * 128;
   const int row_base = b * p.S;
-  const int jlo = p.window > 0 ? max(0, (q0 - p.window) / 64) : 0;  // sliding window: first K/V block any row of the tile can see
+  const int window = WIN ? p.window : 0;
+  const int jlo = WIN ? max(0, (q0 - window) / 64) : 0;  // sliding window: first K/V block any row of the tile can see
   const int n = (q0 + 128) / 64 - jlo;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int hk = h / (p.H / p.Hkv);
@@ -553,8 +566,7 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #ifdef DTX_ATTN_TIMING
     long long ti_kv = 0, ti_mma = 0;
 #endif
-    // S = Q K^T, dP = dO V^T (A operands from TMEM).  wait_slot: only the two prologue calls look at the K/V ring themselves - in
-    // the loop the compute warps wait for block j + 2's slot before they arrive on bar_p(j) (see attn_dkv_kernel)
+    // S = Q K^T, dP = dO V^T (A operands from TMEM)
     auto issue_s = [&](const int slot, const int buf, const uint32_t parity, const bool wait_slot) {
 #ifdef DTX_ATTN_TIMING
       const long long tk0 = clock64();
@@ -615,7 +627,7 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_commit(&bar_free[u]);
             if (j == n - 1) umma_commit(bar_fin);
           }
-          if (j + 2 < n) issue_s((u + 2) & 3, u & 1, (u + 2 >= DQ1_NS) ? (rp ^ 1u) : rp, false);
+          if (j + 2 < n) issue_s((u + 2) & 3, u & 1, (u + 2 >= DQ1_NS) ? (rp ^ 1u) : rp, true);
         }
       }
     }
@@ -693,30 +705,33 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #ifdef DTX_ATTN_TIMING
       const long long t_c = clock64();
 #endif
-      const bool need_mask = (kv0 + 63 > q0) || (p.window > 0 && kv0 < q0 + 127 - p.window);
-      const int klo = p.window > 0 ? qrow - p.window : -(1 << 30);  // first visible key of this row
+      const bool need_mask = (kv0 + 63 > q0) || (WIN && kv0 < q0 + 127 - window);
+      const int klo = WIN ? qrow - window : -(1 << 30);  // first visible key of this row
       // packed fp32 pairs (FFMA2 / FMUL2): dS = P o (dP * scale - delta * scale), P = 2^(S * scale_log2 - lse2)
       const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nl2 = make_float2(-lse2, -lse2), sc2 = make_float2(p.scale, p.scale),
                    nd2 = make_float2(-delta * p.scale, -delta * p.scale);
+      // two copies of the loop, the mask branch outside: inside, the compiler predicates the compares into every block
+      auto ds_math = [&](auto masked) {
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2, nl2);
-        float2 pr = exp2_pair(x, e >> 1);
-        if (need_mask) {
-          const int k0 = kv0 + half * 32 + e;
-          if (k0 > qrow || k0 < klo) pr.x = 0.f;
-          if (k0 + 1 > qrow || k0 + 1 < klo) pr.y = 0.f;
+        for (int e = 0; e < 32; e += 2) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2, nl2);
+          float2 pr = exp2_pair<EXP_FMA>(x, e >> 1);
+          if constexpr (decltype(masked)::value) {
+            const int k0 = kv0 + half * 32 + e;
+            if (k0 > qrow || (WIN && k0 < klo)) pr.x = 0.f;
+            if (k0 + 1 > qrow || (WIN && k0 + 1 < klo)) pr.y = 0.f;
+          }
+          const float2 dd = __ffma2_rn(make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sc2, nd2);
+          const float2 ds = __fmul2_rn(pr, dd);
+          pk[e >> 1] = pack_bf16x2(ds.x, ds.y);
         }
-        const float2 dd = __ffma2_rn(make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sc2, nd2);
-        const float2 ds = __fmul2_rn(pr, dd);
-        pk[e >> 1] = pack_bf16x2(ds.x, ds.y);
-      }
+      };
+      if (need_mask) ds_math(std::true_type{}); else ds_math(std::false_type{});
 #ifdef DTX_ATTN_TIMING
       const long long t_d = clock64();
 #endif
       tmem_st16(t_lane + T_S + (j & 1) * 64 + half * 32, pk);  // over this thread's own (already loaded) score columns
       tmem_st_wait();
-      if (j + 2 < n) mbar_wait(&bar_kv[(j + 2) & 3], ((j + 2) >> 2) & 1);  // the issuer no longer checks the ring slot of block j + 2
       tc_fence_before();
       mbar_arrive(&bar_p[j & 1]);
 #ifdef DTX_ATTN_TIMING
@@ -794,7 +809,7 @@ constexpr int DKV_SMEM = DKV_BAR + 256 + 1024;
 // NCW compute warps (8 or 16): warp w owns TMEM lanes (kv rows) 32*(w&3)..+31 and the query columns of column group w>>2
 // (64 / (NCW/4) columns per thread).  16 warps halve the latency of the exp / dS phase of a block (four warps per scheduler
 // to interleave instead of two) - it sits on the critical path between the score MMAs and the accumulating MMAs.
-template <int NCW>
+template <int NCW, bool WIN>
 __global__ void __launch_bounds__((NCW + 2) * 32, 1)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmQ64,
                 const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmOut, const AttnKParams p) {
@@ -818,7 +833,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
   const int len = row_len(p, b);
   // query blocks per query head that see this KV block and hold a real token; with a sliding window the last query row that
   // sees any key of the tile is kv0 + 127 + window
-  const int q_end = p.window > 0 ? min((len + 63) / 64, (kv0 + 127 + p.window) / 64 + 1) : (len + 63) / 64;
+  const int window = WIN ? p.window : 0;
+  const int q_end = WIN ? min((len + 63) / 64, (kv0 + 127 + window) / 64 + 1) : (len + 63) / 64;
   const int nq = q_end - i0;
   const int n = nq * grp;                     // streamed (head, query block) pairs; it -> head it / nq, block it % nq
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -984,31 +1000,35 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
       }
       tmem_ld_wait();
       TM_SET(tc_c);
-      const bool need_mask = (qs < kv0 + 127) || (p.window > 0 && qs + 63 > kv0 + p.window);
-      // packed fp32 pairs (FFMA2 / FMUL2); every other pair of exponentials on the FMA pipe (exp2_fma2)
+      const bool need_mask = (qs < kv0 + 127) || (WIN && qs + 63 > kv0 + window);
+      const int qhi = WIN ? kvrow + window : (1 << 30);  // last query row that sees this key
+      // packed fp32 pairs (FFMA2 / FMUL2)
       const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale), nsc2 = make_float2(-p.scale, -p.scale);
+      // two copies of the loop, the mask branch outside (see attn_dq1_kernel)
+      auto ds_math = [&](auto masked) {
 #pragma unroll
-      for (int e = 0; e < CPT; e += 4) {
-        const float4 l4 = lds128f(st + e * 4);
-        const float4 d4 = lds128f(st + 256 + e * 4);
+        for (int e = 0; e < CPT; e += 4) {
+          const float4 l4 = lds128f(st + e * 4);
+          const float4 d4 = lds128f(st + 256 + e * 4);
 #pragma unroll
-        for (int u = 0; u < 4; u += 2) {
-          const float2 nl = u ? make_float2(-l4.z, -l4.w) : make_float2(-l4.x, -l4.y);
-          const float2 dl = u ? make_float2(d4.z, d4.w) : make_float2(d4.x, d4.y);
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[e + u]), __uint_as_float(sv[e + u + 1])), sl2, nl);
-          float2 pr = exp2_pair(x, (e + u) >> 1);
-          if (need_mask) {
-            const int qa = qs + cq * CPT + e + u;  // query row of pr.x (pr.y: qa + 1); visible iff kvrow <= q <= kvrow + window
-            const int qhi = p.window > 0 ? kvrow + p.window : (1 << 30);
-            if (kvrow > qa || qa > qhi) pr.x = 0.f;
-            if (kvrow > qa + 1 || qa + 1 > qhi) pr.y = 0.f;
+          for (int u = 0; u < 4; u += 2) {
+            const float2 nl = u ? make_float2(-l4.z, -l4.w) : make_float2(-l4.x, -l4.y);
+            const float2 dl = u ? make_float2(d4.z, d4.w) : make_float2(d4.x, d4.y);
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[e + u]), __uint_as_float(sv[e + u + 1])), sl2, nl);
+            float2 pr = exp2_pair(x, (e + u) >> 1);
+            if constexpr (decltype(masked)::value) {
+              const int qa = qs + cq * CPT + e + u;  // query row of pr.x (pr.y: qa + 1); visible iff kvrow <= q <= kvrow + window
+              if (kvrow > qa || (WIN && qa > qhi)) pr.x = 0.f;
+              if (kvrow > qa + 1 || (WIN && qa + 1 > qhi)) pr.y = 0.f;
+            }
+            const float2 dd = __ffma2_rn(make_float2(__uint_as_float(dv[e + u]), __uint_as_float(dv[e + u + 1])), sc2, __fmul2_rn(dl, nsc2));
+            const float2 ds = __fmul2_rn(pr, dd);
+            ppk[(e + u) >> 1] = pack_bf16x2(pr.x, pr.y);
+            dpk[(e + u) >> 1] = pack_bf16x2(ds.x, ds.y);
           }
-          const float2 dd = __ffma2_rn(make_float2(__uint_as_float(dv[e + u]), __uint_as_float(dv[e + u + 1])), sc2, __fmul2_rn(dl, nsc2));
-          const float2 ds = __fmul2_rn(pr, dd);
-          ppk[(e + u) >> 1] = pack_bf16x2(pr.x, pr.y);
-          dpk[(e + u) >> 1] = pack_bf16x2(ds.x, ds.y);
         }
-      }
+      };
+      if (need_mask) ds_math(std::true_type{}); else ds_math(std::false_type{});
       TM_SET(tc_d);
       // overwrite this thread's own (already loaded) score columns with the packed operands
       if constexpr (CPT == 32) {
@@ -1120,6 +1140,8 @@ cudaError_t set_smem(const void* fn, int bytes) {
 }  // namespace
 
 int g_fwd_exp_fma_every = 3;  // measured (profiles/r02_attn_events.txt): 330 us (0) / 301 (4) / 292 (3) / 294 (2) per layer at the 7B shape
+int g_dq_exp_fma_every = 0;  // dQ kernel: every N-th pair of exponentials on the FMA pipe (0 = none, 3, 4)
+void attn_set_dq_exp_fma_every(int n) { g_dq_exp_fma_every = (n == 3 || n == 4) ? n : 0; }
 void attn_set_fwd_exp_fma_every(int n) { g_fwd_exp_fma_every = (n == 2 || n == 3 || n == 4) ? n : 0; }  // 0 = all on the MUFU
 int attn_bwd_launches() { return 2; }
 bool attn_bwd_can_rope() { return true; }
@@ -1134,12 +1156,19 @@ cudaError_t attn_init_device() {
   if (e != cudaSuccess) return e;
   std::lock_guard<std::mutex> lk(mu);
   if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-  if ((e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel<0>), FW2_SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel<2>), FW2_SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel<3>), FW2_SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(reinterpret_cast<const void*>(attn_fwd2_kernel<4>), FW2_SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(reinterpret_cast<const void*>(attn_dq1_kernel), DQ1_SMEM)) != cudaSuccess) return e;
-  if ((e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<8>), DKV_SMEM)) != cudaSuccess) return e;
+  const void* fwd[] = {reinterpret_cast<const void*>(attn_fwd2_kernel<0, false>), reinterpret_cast<const void*>(attn_fwd2_kernel<2, false>),
+                       reinterpret_cast<const void*>(attn_fwd2_kernel<3, false>), reinterpret_cast<const void*>(attn_fwd2_kernel<4, false>),
+                       reinterpret_cast<const void*>(attn_fwd2_kernel<0, true>), reinterpret_cast<const void*>(attn_fwd2_kernel<2, true>),
+                       reinterpret_cast<const void*>(attn_fwd2_kernel<3, true>), reinterpret_cast<const void*>(attn_fwd2_kernel<4, true>)};
+  for (const void* f : fwd)
+    if ((e = set_smem(f, FW2_SMEM)) != cudaSuccess) return e;
+  const void* dq[] = {reinterpret_cast<const void*>(attn_dq1_kernel<false, 0>), reinterpret_cast<const void*>(attn_dq1_kernel<false, 3>),
+                      reinterpret_cast<const void*>(attn_dq1_kernel<false, 4>), reinterpret_cast<const void*>(attn_dq1_kernel<true, 0>),
+                      reinterpret_cast<const void*>(attn_dq1_kernel<true, 3>), reinterpret_cast<const void*>(attn_dq1_kernel<true, 4>)};
+  for (const void* f : dq)
+    if ((e = set_smem(f, DQ1_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<8, false>), DKV_SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(reinterpret_cast<const void*>(attn_dkv_kernel<8, true>), DKV_SMEM)) != cudaSuccess) return e;
   if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
 }
@@ -1168,12 +1197,16 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   p.seq_lens = a.seq_lens;
   p.window = a.window;
   const int grid = a.B * a.H * ((a.S + 255) / 256);
+#define DTX_FWD_LAUNCH(E)                                                                          \
+  if (a.window > 0) attn_fwd2_kernel<E, true><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); \
+  else attn_fwd2_kernel<E, false><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p)
   switch (g_fwd_exp_fma_every) {
-    case 2: attn_fwd2_kernel<2><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); break;
-    case 3: attn_fwd2_kernel<3><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); break;
-    case 4: attn_fwd2_kernel<4><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); break;
-    default: attn_fwd2_kernel<0><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); break;
+    case 2: DTX_FWD_LAUNCH(2); break;
+    case 3: DTX_FWD_LAUNCH(3); break;
+    case 4: DTX_FWD_LAUNCH(4); break;
+    default: DTX_FWD_LAUNCH(0); break;
   }
+#undef DTX_FWD_LAUNCH
   return cudaGetLastError();
 }
 
@@ -1208,8 +1241,14 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   p.rope_stride = a.rope_stride > 0 ? a.rope_stride : a.S;
   p.seq_lens = a.seq_lens;
   p.window = a.window;
-  attn_dq1_kernel<<<a.B * a.H * (a.S / 128), DKV_THREADS, DQ1_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmO128, tmDqkv, p);
-  attn_dkv_kernel<8><<<a.B * Hkv * (a.S / 128), 10 * 32, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
+  const int gq = a.B * a.H * (a.S / 128), gkv = a.B * Hkv * (a.S / 128);
+  const bool win = a.window > 0;
+#define DTX_DQ_LAUNCH(W, I) attn_dq1_kernel<W, I><<<gq, DKV_THREADS, DQ1_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmO128, tmDqkv, p)
+  if (win) { if (g_dq_exp_fma_every == 3) DTX_DQ_LAUNCH(true, 3); else if (g_dq_exp_fma_every == 4) DTX_DQ_LAUNCH(true, 4); else DTX_DQ_LAUNCH(true, 0); }
+  else { if (g_dq_exp_fma_every == 3) DTX_DQ_LAUNCH(false, 3); else if (g_dq_exp_fma_every == 4) DTX_DQ_LAUNCH(false, 4); else DTX_DQ_LAUNCH(false, 0); }
+#undef DTX_DQ_LAUNCH
+  if (win) attn_dkv_kernel<8, true><<<gkv, 10 * 32, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
+  else attn_dkv_kernel<8, false><<<gkv, 10 * 32, DKV_SMEM, s>>>(tmKV128, tmQ64, tmDO64, tmDqkv, p);
   return cudaGetLastError();
 }
 

@@ -55,6 +55,10 @@ int32_t dtx_set_option(const char* name, int32_t value) {
     attn_set_fwd_exp_fma_every(value);
     return DTX_OK;
   }
+  if (strcmp(name, "attn_dq_exp_fma_every") == 0) {
+    attn_set_dq_exp_fma_every(value);
+    return DTX_OK;
+  }
   if (strcmp(name, "nf4_prefetch") == 0) {
     trainer_set_nf4_prefetch(value);
     return DTX_OK;

@@ -53,6 +53,7 @@ int attn_bwd_launches();   // kernels one attn_bwd() call launches (dQ (+ delta)
 // forward softmax: every N-th pair of exponentials (N = 2, 3, 4) is computed on the FMA pipe with a cubic polynomial instead of
 // MUFU.EX2 (max. relative error 7.5e-5, far below bf16 resolution); 0 = all on the MUFU
 void attn_set_fwd_exp_fma_every(int n);
+void attn_set_dq_exp_fma_every(int n);  // dQ kernel: every n-th pair of exponentials on the FMA pipe (0 = none: default; 3, 4)
 void gemm_set_pair_group_m(int tiles);  // rasterisation group height of the pair kernel, in 256-row tiles
 // 1 (default): RoPE / SwiGLU run inside GEMM and attention epilogues; 0: separate HBM-bound kernels (A/B, tiny M)
 void trainer_set_fused_epilogues(int on);

@@ -114,6 +114,7 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
     steps_in_epoch = D.steps_per_epoch(len(dataset), world, B)  # len(dataloader)
     step, window, micro_losses, t0 = 0, [], [], time.time()
     batched, tokens = 0, 0  # HF total_batched_samples: accumulation runs across epoch boundaries
+    t_first, tok_first, t_last = None, 0, None  # steady state: from the end of the first optimizer step to the end of the last
     epoch = 0
     while step < total:
         for i, (ids, labels, lens) in enumerate(D.epoch_batches(dataset, rank, world, B, seq_len, pad_id, epoch, a.seed, varlen=True)):
@@ -128,6 +129,9 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
             if not stepped:
                 continue
             step += 1
+            t_last = time.time()
+            if t_first is None:
+                t_first, tok_first = t_last, tokens
             window.append(float(np.sum(micro_losses)) / GA)  # HF divides every micro-batch loss by GA
             micro_losses = []
             frac_epoch = epoch + (i + 1) / steps_in_epoch
@@ -161,6 +165,9 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
         dt = time.time() - t0
         print(f"train_runtime {dt:.1f}s, {step} optimizer steps, {tokens} real tokens on rank 0 ({tokens / max(dt, 1e-9):.1f} tokens/s/rank)",
               flush=True)
+        if step > 1 and t_last > t_first:  # without the first step (lazy CUDA / NCCL initialisation) and the checkpoint writes
+            print(f"steady_state {t_last - t_first:.3f}s, {step - 1} optimizer steps, {tokens - tok_first} real tokens on rank 0 "
+                  f"({(tokens - tok_first) / (t_last - t_first):.1f} tokens/s/rank)", flush=True)
     tr.close()
     return ckpt
 

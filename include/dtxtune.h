@@ -167,6 +167,7 @@ DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, 
  * SwiGLU run inside the GEMM / attention epilogues; 0: separate HBM-bound kernels.  "gemm_group_m": rasterisation group of the
  * CTA-pair GEMM in 256-row tiles (default 16).  "attn_fwd_exp_fma_every" = N in {0, 2, 3, 4}: every N-th pair of the forward
  * softmax's exponentials is computed on the FMA pipe (cubic polynomial) instead of MUFU.EX2 (default 3; 0 = none).
+ * "attn_dq_exp_fma_every" = N in {0, 3, 4}: the same for the dQ kernel's exp / dS phase (default 0).
  * "nf4_prefetch" = 1 (default): with --quantization int4 the next matrix is expanded on a side stream under the current GEMM
  * (read at dtx_quantize_base time); 0: expansion inline on the main stream.  Unknown names return DTX_ERR_INVALID. */
 DTX_API int32_t dtx_set_option(const char* name, int32_t value);

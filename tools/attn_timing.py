@@ -42,6 +42,17 @@ def main(B=8, S=2048, H=32, Hkv=32):
             ts.append(ev[0].elapsed_time(ev[1]) * 1000)
         print(f"ATTN_TIMING fwd exp_fma_every={every}: {min(ts[1:]):.1f} us (runs {[round(t, 1) for t in ts]})", flush=True)
     L.set_option("attn_fwd_exp_fma_every", int(os.environ.get("DTX_FWD_EXP_FMA", "3")))
+    for ring in (0, 4, 3, 0):  # dQ kernel: fraction of the exponentials on the FMA pipe
+        L.set_option("attn_dq_exp_fma_every", ring)
+        ts = []
+        for it in range(4):
+            ev[1].record()
+            L.check(lib.dtx_attn_bwd(P(qkv), P(out), P(dout), P(lse2), P(delta), P(dqkv), B, S, H, Hkv, sc, None, 0, None, 0, st))
+            ev[2].record()
+            torch.cuda.synchronize()
+            ts.append(ev[1].elapsed_time(ev[2]) * 1000)
+        print(f"ATTN_TIMING bwd dq_exp_fma_every={ring}: {min(ts[1:]):.1f} us (runs {[round(t, 1) for t in ts]})", flush=True)
+    L.set_option("attn_dq_exp_fma_every", int(os.environ.get("DTX_DQ_EXP_FMA", "0")))
     for it in range(2):
         ev[0].record()
         L.check(lib.dtx_attn_fwd(P(qkv), P(out), P(lse2), B, S, H, Hkv, sc, None, 0, st))

@@ -103,6 +103,9 @@ def main():
         if mt:
             dt, steps, toks = float(mt.group(1)), int(mt.group(2)), int(mt.group(3))
             rec.update(train_runtime_s=dt, optimizer_steps=steps, tokens_per_s=toks * args.gpus_per_job / dt)
+            ms = re.search(r"steady_state ([0-9.]+)s, (\d+) optimizer steps, (\d+) real tokens on rank 0", out)
+            if ms:  # from the end of the first optimizer step to the end of the last: no lazy initialisation, no checkpoint writes
+                rec.update(steady_state_s=float(ms.group(1)), steady_tokens_per_s=int(ms.group(3)) * args.gpus_per_job / float(ms.group(1)))
             logs = os.path.join(jdir, "result", "watch", "trainer_log.jsonl")
             if os.path.exists(logs):
                 rec["logged_losses"] = [json.loads(l)["loss"] for l in open(logs)]
@@ -112,7 +115,8 @@ def main():
     wall = time.time() - t0
     ok = all(r["rc"] == 0 and r["checkpoint_written"] for r in jobs)
     res = {"config": f"{args.jobs} concurrent {args.model} LoRA jobs x {args.gpus_per_job} GPUs, hyper-parameter sweep (BASELINE.json configs[4])",
-           "ok": ok, "wall_s": wall, "aggregate_tokens_per_s": sum(r.get("tokens_per_s", 0.0) for r in jobs), "jobs": jobs}
+           "ok": ok, "wall_s": wall, "aggregate_tokens_per_s": sum(r.get("tokens_per_s", 0.0) for r in jobs),
+           "aggregate_steady_tokens_per_s": sum(r.get("steady_tokens_per_s", 0.0) for r in jobs), "jobs": jobs}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
     print("CONCURRENT_JOBS " + json.dumps(res))

@@ -16,6 +16,7 @@ for s in $STEPS; do
     sweep_gm) for g in 8 16 32; do DTX_GROUP_M=$g timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/bench_gm$g.json 2> $OUT/bench_gm$g.err; done;;
     bench_fma) for e in 0 4 3; do DTX_FWD_EXP_FMA=$e timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/bench_fma$e.json 2> $OUT/bench_fma$e.err; done;;
     attn_events) timeout 300 python tools/attn_timing.py > $OUT/attn_events.log 2>&1;;
+    attn_launches) timeout 600 ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.max --clock-control none -k regex:attn_ --csv --log-file $OUT/attn_launches.csv python tools/attn_timing.py > $OUT/attn_launches.log 2>&1;;
     sanitizer) for c in gemm_nt gemm_kext rmsnorm cross_entropy adamw attn_fwd attn_bwd attn_varlen trainer_tiny; do
                  timeout 900 compute-sanitizer --tool racecheck --print-limit 5 python -m tests.gpu_checks $c > $OUT/racecheck_$c.log 2>&1; echo "$c rc=$?" >> $OUT/sanitizer_summary.txt; done
                timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python -m tests.gpu_checks attn_varlen trainer_varlen > $OUT/memcheck_varlen.log 2>&1; echo "memcheck_varlen rc=$?" >> $OUT/sanitizer_summary.txt;;
@@ -24,10 +25,11 @@ for s in $STEPS; do
     bench_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus ${NGPU:-2} --steps 8 --warmup 3 > $OUT/bench_n${NGPU:-2}.json 2> $OUT/bench_n${NGPU:-2}.err;;
     qlora_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29543 bench.py --config mistral7b_qlora --gpus ${NGPU:-2} --steps 5 --warmup 3 > $OUT/bench_qlora_n${NGPU:-2}.json 2> $OUT/bench_qlora_n${NGPU:-2}.err;;
     full13b_n) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-8} --master-addr 127.0.0.1 --master-port 29545 bench.py --config 13b_full --gpus ${NGPU:-8} --steps 6 --warmup 3 > $OUT/bench_13b_full_n${NGPU:-8}.json 2> $OUT/bench_13b_full_n${NGPU:-8}.err;;
+    full13b_ctas) NCCL_MAX_CTAS=${NCCL_CTAS:-8} timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-8} --master-addr 127.0.0.1 --master-port 29547 bench.py --config 13b_full --gpus ${NGPU:-8} --steps 6 --warmup 3 > $OUT/bench_13b_full_n${NGPU:-8}_ctas${NCCL_CTAS:-8}.json 2> $OUT/bench_13b_full_n${NGPU:-8}_ctas${NCCL_CTAS:-8}.err;;
     small_full) timeout 600 python bench.py --config small_full --steps 6 --warmup 3 > $OUT/bench_small_full.json 2> $OUT/bench_small_full.err;;
     small_full_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29546 bench.py --config small_full --gpus ${NGPU:-2} --steps 6 --warmup 3 > $OUT/bench_small_full_n${NGPU:-2}.json 2> $OUT/bench_small_full_n${NGPU:-2}.err;;
     jobs_tiny) timeout 600 python tools/concurrent_jobs.py --jobs ${NJOBS:-1} --gpus-per-job 2 --model tiny --steps 12 --out $OUT/concurrent_jobs_tiny.json > $OUT/concurrent_jobs_tiny.log 2>&1;;
-    jobs_7b) timeout 900 python tools/concurrent_jobs.py --jobs ${NJOBS:-4} --gpus-per-job 2 --model 7b --steps 8 --out $OUT/concurrent_jobs_7b.json > $OUT/concurrent_jobs_7b.log 2>&1;;
+    jobs_7b) timeout 900 python tools/concurrent_jobs.py --jobs ${NJOBS:-4} --gpus-per-job 2 --model 7b --steps ${JOB_STEPS:-24} --out $OUT/concurrent_jobs_7b.json > $OUT/concurrent_jobs_7b.log 2>&1;;
     determinism) timeout 600 python tools/diag_determinism.py > $OUT/determinism.log 2>&1;;
     step_repeat) timeout 600 python tools/diag_step_repeat.py > $OUT/step_repeat.log 2>&1;;
     initcheck) timeout 900 compute-sanitizer --tool initcheck --print-limit 20 python -m tests.gpu_checks trainer_tiny > $OUT/initcheck_trainer_tiny.log 2>&1;;
