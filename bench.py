@@ -319,6 +319,10 @@ def run_native(args, rank: int, local_rank: int, world: int):
         L.set_option("attn_fwd_exp_fma_every", int(os.environ["DTX_FWD_EXP_FMA"]))
     if os.environ.get("DTX_NF4_PREFETCH"):  # A/B of the side-stream NF4 expansion
         L.set_option("nf4_prefetch", int(os.environ["DTX_NF4_PREFETCH"]))
+    if os.environ.get("DTX_VARLEN_SPLIT"):  # A/B of the length-group execution of ragged micro-batches
+        L.set_option("varlen_split", int(os.environ["DTX_VARLEN_SPLIT"]))
+    if os.environ.get("DTX_VARLEN_GROUP_COST"):
+        L.set_option("varlen_group_cost", int(os.environ["DTX_VARLEN_GROUP_COST"]))
     if os.environ.get("DTX_GROUP_M"):  # rasterisation sweep of the CTA-pair GEMM (tools/gpu_round.sh sweep_gm)
         L.set_option("gemm_group_m", int(os.environ["DTX_GROUP_M"]))
     tr = L.Trainer(mc, tc, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
@@ -370,10 +374,11 @@ def run_native(args, rank: int, local_rank: int, world: int):
     barrier()
     e0 = meter.read_j()
     t0 = time.perf_counter()
-    dev_ms, segs = [], []
+    dev_ms, segs, groups = [], [], []
     real_tokens = padded_tokens = 0
     for i in range(args.steps):
         losses.append(run(i, True))
+        groups.append(tr.last_step_groups)
         dev_ms.append(tr.last_step_ms)
         segs.append(tr.last_step_timings)
         real_tokens += int(lens_host[i % n_batches][0].sum())
@@ -449,6 +454,9 @@ def run_native(args, rank: int, local_rank: int, world: int):
     if varlen:
         line["padded_tokens_per_s"] = padded_all / dt
         line["real_over_padded"] = real_all / padded_all
+        # rows sorted by length and cut into groups by the library's cost model; each group runs at its own padded length
+        line["length_groups_per_step"] = float(np.mean(groups))
+        line["losses_first_batches"] = losses[:n_batches]
     if gemms:
         g = gemms["nn_dh2"]
         line["roofline"] = {"bound": "tensor", "achieved": g["tflops"], "peak": peaks["burst"], "unit": "TFLOP/s",

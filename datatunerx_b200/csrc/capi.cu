@@ -59,6 +59,14 @@ int32_t dtx_set_option(const char* name, int32_t value) {
     attn_set_dq_exp_fma_every(value);
     return DTX_OK;
   }
+  if (strcmp(name, "varlen_split") == 0) {
+    trainer_set_varlen_split(value);
+    return DTX_OK;
+  }
+  if (strcmp(name, "varlen_group_cost") == 0) {
+    trainer_set_varlen_group_cost(value);
+    return DTX_OK;
+  }
   if (strcmp(name, "nf4_prefetch") == 0) {
     trainer_set_nf4_prefetch(value);
     return DTX_OK;

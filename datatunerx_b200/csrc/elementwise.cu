@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(1024) shift_labels_kernel(const int32_t* __res
 __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logits, long long ldl,
                                                  const int32_t* __restrict__ labels, const int32_t* __restrict__ n_valid,
                                                  float* __restrict__ row_loss, bf16* __restrict__ dlogits, long long ldd,
-                                                 int V, const int32_t* __restrict__ valid_idx) {
+                                                 int V, const int32_t* __restrict__ valid_idx, int n_div) {
   __shared__ float shm[8], shs[8];
   __shared__ float s_max, s_sum;
   const int row = blockIdx.x;  // row of logits / dlogits
@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logit
   if (!drow) return;
   const float M0 = s_max;
   const float inv = 1.f / s_sum;
-  const float scale = 1.f / static_cast<float>(max(*n_valid, 1));
+  // n_div > 0: this launch covers one length group of a micro-batch; the mean runs over the labelled tokens of ALL its groups
+  const float scale = 1.f / static_cast<float>(max(n_div > 0 ? n_div : *n_valid, 1));
   for (int i = threadIdx.x; i < nv4; i += blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(lrow) + i);
     float p0 = __expf(v.x - M0) * inv, p1 = __expf(v.y - M0) * inv, p2 = __expf(v.z - M0) * inv, p3 = __expf(v.w - M0) * inv;
@@ -395,14 +396,14 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logit
 }
 
 __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ n_valid,
-                                   float* __restrict__ loss, int M) {
+                                   float* __restrict__ loss, int M, int n_div, int accumulate) {
   __shared__ float sh[32];
   // fixed assignment of rows to threads + fixed-order combine => bitwise reproducible
   double acc = 0.0;
   for (int i = threadIdx.x; i < M; i += blockDim.x) acc += static_cast<double>(row_loss[i]);
   float v = static_cast<float>(acc);
   v = block_sum(v, sh);
-  if (threadIdx.x == 0) *loss = v / static_cast<float>(max(*n_valid, 1));
+  if (threadIdx.x == 0) *loss = (accumulate ? *loss : 0.f) + v / static_cast<float>(max(n_div > 0 ? n_div : *n_valid, 1));
 }
 
 __global__ void sum_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n, int splits) {
@@ -868,14 +869,32 @@ cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_val
 
 cudaError_t cross_entropy_fwd_bwd(const float* logits, int64_t ldl, const int32_t* labels, const int32_t* n_valid,
                                   float* row_loss, bf16* dlogits, int64_t ldd, int M, int V, cudaStream_t s,
-                                  const int32_t* valid_idx) {
+                                  const int32_t* valid_idx, int n_div) {
   if ((ldl & 3) || (ldd & 3)) return cudaErrorInvalidValue;
-  ce_kernel<<<M, 256, 0, s>>>(logits, ldl, labels, n_valid, row_loss, dlogits, ldd, V, valid_idx);
+  ce_kernel<<<M, 256, 0, s>>>(logits, ldl, labels, n_valid, row_loss, dlogits, ldd, V, valid_idx, n_div);
   return cudaGetLastError();
 }
 
-cudaError_t loss_reduce(const float* row_loss, const int32_t* n_valid, float* loss, int M, cudaStream_t s) {
-  loss_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, n_valid, loss, M);
+cudaError_t loss_reduce(const float* row_loss, const int32_t* n_valid, float* loss, int M, cudaStream_t s, int n_div, int accumulate) {
+  loss_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, n_valid, loss, M, n_div, accumulate);
+  return cudaGetLastError();
+}
+
+__global__ void gather_rows_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ labels, const int32_t* __restrict__ lens,
+                                   int S_src, RowList rows, int S_dst, int32_t* __restrict__ ids_out, int32_t* __restrict__ labels_out,
+                                   int32_t* __restrict__ lens_out) {
+  const int i = blockIdx.y, src = rows.rows[i];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < S_dst; c += gridDim.x * blockDim.x) {
+    ids_out[static_cast<long long>(i) * S_dst + c] = ids[static_cast<long long>(src) * S_src + c];
+    labels_out[static_cast<long long>(i) * S_dst + c] = labels[static_cast<long long>(src) * S_src + c];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) lens_out[i] = lens[src];
+}
+
+cudaError_t gather_rows(const int32_t* ids, const int32_t* labels, const int32_t* lens, int S_src, RowList rows, int S_dst,
+                        int32_t* ids_out, int32_t* labels_out, int32_t* lens_out, cudaStream_t s) {
+  if (rows.n <= 0 || rows.n > 64 || S_dst > S_src || S_dst <= 0) return cudaErrorInvalidValue;
+  gather_rows_kernel<<<dim3((S_dst + 255) / 256, rows.n), 256, 0, s>>>(ids, labels, lens, S_src, rows, S_dst, ids_out, labels_out, lens_out);
   return cudaGetLastError();
 }
 

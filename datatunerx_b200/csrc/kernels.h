@@ -59,6 +59,8 @@ void gemm_set_pair_group_m(int tiles);  // rasterisation group height of the pai
 void trainer_set_fused_epilogues(int on);
 // 1 (default): --quantization int4 expands the next NF4 matrix on a side stream under the current GEMM; 0: inline
 void trainer_set_nf4_prefetch(int on);
+void trainer_set_varlen_group_cost(int permille);  // fixed cost per length group in the partition's cost model
+void trainer_set_varlen_split(int on);  // ragged micro-batches run as length groups (default 1)
 
 // ---------------------------------------------------------------------------------------------
 // flash attention (causal, head_dim 128), packed qkv layout [B*S, (H + 2*Hkv)*128] (q heads | k heads | v heads per token)
@@ -118,9 +120,14 @@ cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_val
 // return), labels and row_loss stay indexed by token; row_loss of unlabelled tokens must have been zeroed by the caller.
 cudaError_t cross_entropy_fwd_bwd(const float* logits, int64_t ldl, const int32_t* labels, const int32_t* n_valid,
                                   float* row_loss, bf16* dlogits, int64_t ldd, int M, int V, cudaStream_t s,
-                                  const int32_t* valid_idx = nullptr);
-// loss = sum(row_loss)/n_valid, fixed summation order
-cudaError_t loss_reduce(const float* row_loss, const int32_t* n_valid, float* loss, int M, cudaStream_t s);
+                                  const int32_t* valid_idx = nullptr, int n_div = 0);
+// loss = sum(row_loss)/n_valid, fixed summation order.  n_div > 0 (here and above): divide by this count instead of *n_valid
+// (one length group of a micro-batch: the mean runs over the labelled tokens of all its groups); accumulate: add to *loss.
+cudaError_t loss_reduce(const float* row_loss, const int32_t* n_valid, float* loss, int M, cudaStream_t s, int n_div = 0, int accumulate = 0);
+// rows[i] of the [*, S_src] int32 matrices ids / labels -> row i of the [n, S_dst] outputs (S_dst <= S_src), lens_out[i] = lens[rows[i]]
+struct RowList { int32_t n; int32_t rows[64]; };
+cudaError_t gather_rows(const int32_t* ids, const int32_t* labels, const int32_t* lens, int S_src, RowList rows, int S_dst,
+                        int32_t* ids_out, int32_t* labels_out, int32_t* lens_out, cudaStream_t s);
 // out[i] = sum_s partial[s][i]  (fixed order)
 cudaError_t sum_partials(const float* partial, float* out, int64_t n, int splits, cudaStream_t s);
 // sumsq of a flat fp32 buffer, deterministic two-stage; result in *out (fp32)

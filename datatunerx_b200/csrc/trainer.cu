@@ -79,6 +79,9 @@ constexpr int kNcclSum = 0;
 
 thread_local std::string g_error;
 int g_nf4_prefetch = 1;     // expand the next NF4 matrix on a side stream while the current GEMM runs (0: inline, for A/B runs)
+int g_varlen_split = 1;     // ragged micro-batches run as length groups (rows sorted by length, partition chosen by a cost model);
+                            // 2: always cut where the 128-rounded lengths differ (parity tests at shapes too small for the model to split)
+int g_varlen_fix_permille = 2000;  // fixed cost charged per length group, in thousandths of "one wave of every GEMM of a layer"
 int g_fused_epilogues = 1;  // RoPE / SwiGLU fused into the GEMM and attention epilogues (needs M > 128: CTA-pair GEMM)
 
 // ------------------------------------------------------------------------------------------------
@@ -156,6 +159,8 @@ enum { W_QKV = 0, W_O = 1, W_GU = 2, W_DOWN = 3 };
 }  // namespace
 void trainer_set_fused_epilogues(int on) { g_fused_epilogues = on; }
 void trainer_set_nf4_prefetch(int on) { g_nf4_prefetch = on; }
+void trainer_set_varlen_split(int on) { g_varlen_split = on; }
+void trainer_set_varlen_group_cost(int permille) { g_varlen_fix_permille = permille < 0 ? 0 : permille; }
 }  // namespace dtx
 
 using namespace dtx;
@@ -173,6 +178,11 @@ struct dtx_trainer {
 
   int M = 0, RP = 0, nt = 0;    // M = micro_batch * seq_len: the largest batch this trainer was created for
   int cur_S = 0, cur_M = 0;     // padded length / token count of the batch being processed (<= seq_len / M)
+  int cur_B = 0;                // its rows: micro_batch, or the rows of one length group (SubPlan)
+  bool sub_accum = false;       // a later length group of the same micro-batch: gradients and loss add to the earlier groups'
+  int sub_ndiv = 0;             // > 0: labelled tokens of the WHOLE micro-batch (the divisor of the token-mean loss of every group)
+  int n_sms = 148;
+  int last_groups = 1;          // length groups of the last training micro-batch (diagnostics)
   bool use_seq_lens = false;    // d_seq_lens holds this batch's true row lengths
   int dq = 0, dkv = 0, W = 0;  // q width (= hidden), k/v width (n_kv_heads*128), packed qkv row width
   int KA = 0;                  // contraction length of the LoRA down-projection: d, or nt*d with dropout
@@ -195,6 +205,8 @@ struct dtx_trainer {
   float *d_loss = nullptr, *d_sumsq = nullptr, *d_gnorm = nullptr, *d_scratch = nullptr;
   int32_t *d_ids = nullptr, *d_labels = nullptr, *d_shift = nullptr, *d_nvalid = nullptr, *d_seq_lens = nullptr;
   int32_t *d_row_map = nullptr, *d_valid_idx = nullptr;  // token -> position among the labelled tokens (-1: none) and back
+  int32_t *d_ids_full = nullptr, *d_labels_full = nullptr, *d_lens_full = nullptr;  // the whole ragged micro-batch (length groups gather from it)
+  std::vector<int32_t> h_labels, h_lens;  // host copies of a device-resident ragged batch (the partition is planned on the host)
   float* d_row_sum = nullptr;     // [micro_batch] per-row summed token loss (evaluation)
   int32_t* d_row_valid = nullptr; // [micro_batch] per-row valid-token count
   double* d_host_red = nullptr;   // staging for dtx_allreduce_host
@@ -432,6 +444,7 @@ int create_buffers(dtx_trainer* t) {
   ok = ok && t->alloc(&t->d_loss, 4) && t->alloc(&t->d_sumsq, 4) && t->alloc(&t->d_gnorm, 4) && t->alloc(&t->d_scratch, 1024);
   ok = ok && t->alloc(&t->d_ids, M) && t->alloc(&t->d_labels, M) && t->alloc(&t->d_shift, M) && t->alloc(&t->d_nvalid, 4);
   ok = ok && t->alloc(&t->d_row_map, M) && t->alloc(&t->d_valid_idx, M);
+  if (!full) ok = ok && t->alloc(&t->d_ids_full, M) && t->alloc(&t->d_labels_full, M) && t->alloc(&t->d_lens_full, static_cast<size_t>(tc.micro_batch));
   ok = ok && t->alloc(&t->d_seq_lens, static_cast<size_t>(tc.micro_batch)) && t->alloc(&t->d_row_sum, static_cast<size_t>(tc.micro_batch)) &&
        t->alloc(&t->d_row_valid, static_cast<size_t>(tc.micro_batch)) && t->alloc(&t->d_host_red, 64);
   ok = ok && t->alloc(&t->rope_cs, static_cast<size_t>(tc.seq_len) * (mc.head_dim / 2));
@@ -584,7 +597,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   const dtx_train_cfg& tc = t->tc;
   const int d = mc.hidden, F = mc.ffn, V = mc.vocab, L = mc.n_layers, M = t->cur_M, RP = t->RP, H = mc.n_heads, D = mc.head_dim;
   const int Hkv = mc.n_kv_heads, W = t->W;
-  const int B = tc.micro_batch, S = t->cur_S;
+  const int B = t->cur_B, S = t->cur_S;
   const int32_t* seq_lens = t->use_seq_lens ? t->d_seq_lens : nullptr;
   const int kb_tok = (M + 63) / 64;
   const int split_b = std::min(t->split_b, pick_split((W + 127) / 128, kb_tok));
@@ -678,12 +691,14 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
     CK(gemm_bf16(g, s), 1);
   }
   CKM(cudaMemsetAsync(t->row_loss, 0, static_cast<size_t>(M) * sizeof(float), s));
-  CK(cross_entropy_fwd_bwd(t->logits, V, t->d_shift, t->d_nvalid, t->row_loss, backward ? t->dlogits : nullptr, V, M, V, s, valid_idx), 1);
-  CK(loss_reduce(t->row_loss, t->d_nvalid, t->d_loss, M, s), 1);
+  // one length group of a ragged micro-batch (t->sub_ndiv > 0): the token mean runs over the labelled tokens of all its groups
+  CK(cross_entropy_fwd_bwd(t->logits, V, t->d_shift, t->d_nvalid, t->row_loss, backward ? t->dlogits : nullptr, V, M, V, s, valid_idx,
+                           t->sub_ndiv), 1);
+  CK(loss_reduce(t->row_loss, t->d_nvalid, t->d_loss, M, s, t->sub_ndiv, t->sub_accum ? 1 : 0), 1);
   if (!backward) return DTX_OK;
   in_backward = true;
 
-  const int accumulate = t->micro_idx > 0 ? 1 : 0;
+  const int accumulate = (t->micro_idx > 0 || t->sub_accum) ? 1 : 0;
   // weight gradient of a Linear: dW[out, in] (+)= dY^T X - a token-contraction GEMM with both operands MN-major
   auto dw_gemm = [&](const bf16* dY, int n_out, const bf16* X, int n_in, bf16* dW) -> cudaError_t {
     GemmArgs g;
@@ -954,9 +969,83 @@ int set_batch_shape(dtx_trainer* t, int32_t seq_len_batch, bool have_lens) {
   if (S % 128 || S > t->tc.seq_len)
     return t->fail(DTX_ERR_INVALID, "seq_len_batch %d must be a multiple of 128 and <= seq_len %d", S, t->tc.seq_len);
   t->cur_S = S;
+  t->cur_B = t->tc.micro_batch;
   t->cur_M = S * t->tc.micro_batch;
   t->use_seq_lens = have_lens;
   return DTX_OK;
+}
+
+// ---- ragged micro-batches as length groups -------------------------------------------------------------------------
+// The reference pads a batch to its longest row (DataCollatorForSeq2Seq, cmd/tuning/train.py:282-286) and computes over the
+// padding.  Here the attention kernels already skip padding tiles; the GEMMs, norms and CE do not - on instruction data with a
+// long tail of row lengths more than half of their rows are padding.  A micro-batch with row lengths is therefore run as
+// LENGTH GROUPS: rows sorted by length, cut into contiguous groups, each group padded to its own longest row (128-rounded)
+// and sent through forward + backward on its own; gradients accumulate, and every group's loss and dlogits are divided by the
+// labelled-token count of the WHOLE micro-batch, so the result is the same token mean (up to summation order).  The cut is
+// chosen by dynamic programming over a cost model of the step's GEMMs (256-row tiles x column tiles in waves of one CTA pair
+// per two SMs) plus a fixed cost per group: few long groups waste rows on padding, many short ones waste waves.
+struct SubPlan {
+  int n = 0;            // groups (1: run the micro-batch as it is)
+  int start[65] = {0};  // group g = order[start[g] .. start[g+1])
+  int S[64] = {0};      // padded length of group g
+  int order[64] = {0};  // rows sorted by length, longest first
+  int n_div = 0;        // labelled tokens of the whole micro-batch, counted the way the groups' shift_labels kernels will
+};
+
+double group_cost(const dtx_trainer* t, int rows, int S) {
+  const int d = t->mc.hidden, F = t->mc.ffn, W = t->W;
+  const long long mt = (static_cast<long long>(rows) * S + 255) / 256;
+  const long long slots = std::max(1, t->n_sms / 2);
+  auto waves = [&](int n_cols, int k) { return static_cast<double>((mt * ((n_cols + 255) / 256) + slots - 1) / slots) * k; };
+  // forward: qkv, o, gate|up, down; backward dX: through down (N = F), gate|up, o, qkv
+  return waves(W, d) + waves(d, d) + waves(2 * F, d) + waves(d, F) + waves(F, d) + waves(d, 2 * F) + waves(d, d) + waves(d, W);
+}
+
+void plan_groups(const dtx_trainer* t, const int32_t* lens, const int32_t* labels, int S_batch, SubPlan* p) {
+  const int B = t->tc.micro_batch;
+  p->n = 1;
+  if (!g_varlen_split || t->full || !lens || B < 2 || B > 64) return;
+  auto c128 = [&](int len) { return std::min(S_batch, std::max(128, (std::min(std::max(len, 0), S_batch) + 127) / 128 * 128)); };
+  for (int i = 0; i < B; ++i) p->order[i] = i;
+  std::stable_sort(p->order, p->order + B, [&](int a, int b) { return lens[a] > lens[b]; });
+  const bool force = g_varlen_split == 2;  // tests: minimise padded rows, no fixed cost
+  const double fix = force ? 0.0 : 0.001 * g_varlen_fix_permille * group_cost(t, 1, 256);
+  auto cost = [&](int rows, int S) { return force ? static_cast<double>(rows) * S : group_cost(t, rows, S); };
+  double best[65];
+  int cut[65];
+  best[0] = 0.0;
+  for (int j = 1; j <= B; ++j) {
+    best[j] = 1e300;
+    for (int i = 0; i < j; ++i) {  // group = sorted rows i .. j-1, padded to the longest of them (row i); at least 256 rows of tokens
+      int S = c128(lens[p->order[i]]);
+      if ((j - i) * S < 256) {  // every group keeps M >= 256 (whole 256-row GEMM tiles, the fused-epilogue kernels)
+        if (S_batch < 256) continue;
+        S = 256;
+      }
+      const double c = best[i] + cost(j - i, S) + fix;
+      if (c < best[j]) { best[j] = c; cut[j] = i; }
+    }
+  }
+  if (best[B] > 1e299 || best[B] >= cost(B, S_batch) + fix) return;  // one group at the batch's own padded length is as good
+  int ends[65], n = 0;
+  for (int j = B; j > 0; j = cut[j]) ends[n++] = j;
+  p->n = n;
+  p->start[0] = 0;
+  for (int g = 0; g < n; ++g) {
+    p->start[g + 1] = ends[n - 1 - g];
+    int S = c128(lens[p->order[p->start[g]]]);
+    if ((p->start[g + 1] - p->start[g]) * S < 256) S = 256;
+    p->S[g] = S;
+  }
+  if (n < 2) { p->n = 1; return; }
+  long long cnt = 0;  // positions 1 .. S_g - 1 of every row carry the shifted label of the position before them
+  for (int g = 0; g < n; ++g)
+    for (int k = p->start[g]; k < p->start[g + 1]; ++k) {
+      const int32_t* row = labels + static_cast<size_t>(p->order[k]) * S_batch;
+      for (int j = 1; j < p->S[g]; ++j) cnt += row[j] >= 0 ? 1 : 0;
+    }
+  p->n_div = static_cast<int>(cnt);
+  if (p->n_div <= 0) p->n = 1;  // nothing carries a label: the plain path handles the degenerate batch
 }
 
 int check_ready(dtx_trainer* t) {
@@ -967,11 +1056,36 @@ int check_ready(dtx_trainer* t) {
   return DTX_OK;
 }
 
-int do_step(dtx_trainer* t, int32_t flags, float* loss_out, float* gnorm_out, float* lr_out, int32_t* stepped_out) {
+// plan (optional, n > 1): run the micro-batch as length groups gathered from src_* (device, [micro_batch, S_src] / [micro_batch])
+int do_step(dtx_trainer* t, int32_t flags, float* loss_out, float* gnorm_out, float* lr_out, int32_t* stepped_out,
+            const SubPlan* plan = nullptr, const int32_t* src_ids = nullptr, const int32_t* src_labels = nullptr,
+            const int32_t* src_lens = nullptr, int S_src = 0) {
   cudaEventRecord(t->ev0, t->stream);
   const int accum = t->tc.grad_accum > 0 ? t->tc.grad_accum : 1;
   t->rs_now = t->full && (t->micro_idx + 1 >= accum || (flags & DTX_STEP_FORCE));
-  int rc = fwd_bwd(t, true);
+  int rc = DTX_OK;
+  t->last_groups = 1;
+  if (plan && plan->n > 1) {
+    t->last_groups = plan->n;
+    for (int g = 0; g < plan->n && rc == DTX_OK; ++g) {
+      RowList rl;
+      rl.n = plan->start[g + 1] - plan->start[g];
+      for (int k = 0; k < rl.n; ++k) rl.rows[k] = plan->order[plan->start[g] + k];
+      cudaError_t ge = gather_rows(src_ids, src_labels, src_lens, S_src, rl, plan->S[g], t->d_ids, t->d_labels, t->d_seq_lens, t->stream);
+      if (ge != cudaSuccess) return t->fail(DTX_ERR_CUDA, "gather_rows: %s", cudaGetErrorString(ge));
+      t->cur_B = rl.n;
+      t->cur_S = plan->S[g];
+      t->cur_M = rl.n * plan->S[g];
+      t->use_seq_lens = true;
+      t->sub_accum = g > 0;
+      t->sub_ndiv = plan->n_div;
+      rc = fwd_bwd(t, true);
+    }
+    t->sub_accum = false;
+    t->sub_ndiv = 0;
+  } else {
+    rc = fwd_bwd(t, true);
+  }
   if (rc) return rc;
   cudaEventRecord(t->ev_fb, t->stream);
   t->micro_idx += 1;
@@ -1129,6 +1243,7 @@ int32_t dtx_trainer_create(const dtx_model_cfg* mc, const dtx_train_cfg* tc, int
   t->device = device;
   t->rank = rank;
   t->world = world;
+  if (prop.multiProcessorCount > 0) t->n_sms = prop.multiProcessorCount;
   t->M = tc->micro_batch * tc->seq_len;
   t->dq = mc->n_heads * mc->head_dim;
   t->dkv = mc->n_kv_heads * mc->head_dim;
@@ -1449,6 +1564,15 @@ int32_t dtx_step(dtx_trainer* t, const int32_t* ids, const int32_t* labels, cons
   int rc = check_ready(t);
   if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, seq_lens != nullptr);
   if (rc) return rc;
+  SubPlan plan;
+  plan_groups(t, seq_lens, labels, t->cur_S, &plan);
+  if (plan.n > 1) {  // ragged batch: the whole batch goes to the staging buffers, the length groups gather from there
+    const int S_src = t->cur_S;
+    CKM(cudaMemcpyAsync(t->d_ids_full, ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+    CKM(cudaMemcpyAsync(t->d_labels_full, labels, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+    CKM(cudaMemcpyAsync(t->d_lens_full, seq_lens, static_cast<size_t>(t->tc.micro_batch) * 4, cudaMemcpyHostToDevice, t->stream));
+    return do_step(t, flags, loss, gnorm, lr, stepped, &plan, t->d_ids_full, t->d_labels_full, t->d_lens_full, S_src);
+  }
   CKM(cudaMemcpyAsync(t->d_ids, ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
   CKM(cudaMemcpyAsync(t->d_labels, labels, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
   if (seq_lens) CKM(cudaMemcpyAsync(t->d_seq_lens, seq_lens, static_cast<size_t>(t->tc.micro_batch) * 4, cudaMemcpyHostToDevice, t->stream));
@@ -1462,6 +1586,19 @@ int32_t dtx_step_device(dtx_trainer* t, const void* d_ids, const void* d_labels,
   int rc = check_ready(t);
   if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, d_seq_lens != nullptr);
   if (rc) return rc;
+  if (d_seq_lens && g_varlen_split && !t->full && t->tc.micro_batch > 1 && t->tc.micro_batch <= 64) {
+    // the partition is planned on the host: fetch the row lengths and the labels (B*S*4 bytes, tens of microseconds)
+    t->h_lens.resize(static_cast<size_t>(t->tc.micro_batch));
+    t->h_labels.resize(static_cast<size_t>(t->cur_M));
+    CKM(cudaMemcpyAsync(t->h_lens.data(), d_seq_lens, t->h_lens.size() * 4, cudaMemcpyDeviceToHost, t->stream));
+    CKM(cudaMemcpyAsync(t->h_labels.data(), d_labels, t->h_labels.size() * 4, cudaMemcpyDeviceToHost, t->stream));
+    CKM(cudaStreamSynchronize(t->stream));
+    SubPlan plan;
+    plan_groups(t, t->h_lens.data(), t->h_labels.data(), t->cur_S, &plan);
+    if (plan.n > 1)
+      return do_step(t, flags, loss, gnorm, lr, stepped, &plan, static_cast<const int32_t*>(d_ids), static_cast<const int32_t*>(d_labels),
+                     static_cast<const int32_t*>(d_seq_lens), t->cur_S);
+  }
   CKM(cudaMemcpyAsync(t->d_ids, d_ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyDeviceToDevice, t->stream));
   CKM(cudaMemcpyAsync(t->d_labels, d_labels, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyDeviceToDevice, t->stream));
   if (d_seq_lens) CKM(cudaMemcpyAsync(t->d_seq_lens, d_seq_lens, static_cast<size_t>(t->tc.micro_batch) * 4, cudaMemcpyDeviceToDevice, t->stream));
@@ -1602,6 +1739,8 @@ int32_t dtx_export_weight(dtx_trainer* t, const char* name, void* host_out, int6
 int64_t dtx_num_trainable(const dtx_trainer* t) { return t ? t->n_train : 0; }
 int64_t dtx_launch_count(const dtx_trainer* t) { return t ? t->launches : 0; }
 float dtx_last_step_ms(const dtx_trainer* t) { return t ? t->last_ms : 0.f; }
+int32_t dtx_last_step_groups(const dtx_trainer* t) { return t ? t->last_groups : 0; }
+
 int32_t dtx_last_step_timings(const dtx_trainer* t, float* out4) {
   if (!t || !out4) return DTX_ERR_INVALID;
   for (int i = 0; i < 4; ++i) out4[i] = t->seg_ms[i];

@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "dtx_abi_version", "dtx_last_global_error", "dtx_last_error", "dtx_trainer_create", "dtx_trainer_destroy",
     "dtx_get_nccl_unique_id", "dtx_load_tensor", "dtx_init_random_weights", "dtx_init_lora", "dtx_quantize_base", "dtx_step",
     "dtx_step_device", "dtx_eval_loss", "dtx_allreduce_host", "dtx_export_adapter", "dtx_export_adapter_grad", "dtx_export_weight", "dtx_num_trainable", "dtx_launch_count",
-    "dtx_base_weight_bytes", "dtx_last_step_ms", "dtx_last_step_timings", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16",
+    "dtx_base_weight_bytes", "dtx_last_step_ms", "dtx_last_step_timings", "dtx_last_step_groups", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16",
     "dtx_gemm_fused", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
     "dtx_rope_table", "dtx_rope_qk", "dtx_swiglu_fwd", "dtx_swiglu_bwd", "dtx_lora_dropout_fwd", "dtx_lora_dropout_bwd_add",
     "dtx_nf4_roundtrip", "dtx_nf4_pack", "dtx_nf4_dequant", "dtx_cross_entropy", "dtx_sumsq", "dtx_adamw",
@@ -92,6 +92,7 @@ def load() -> C.CDLL:
     lib.dtx_base_weight_bytes.argtypes = [vp]
     lib.dtx_base_weight_bytes.restype = i64
     lib.dtx_last_step_timings.argtypes = [vp, vp]
+    lib.dtx_last_step_groups.argtypes = [vp]
     lib.dtx_gemm_fused.argtypes = [vp, i64, vp, i64, i32, vp, i64, vp, i64, i32, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32,
                                    i32, vp]
     lib.dtx_export_adapter.argtypes = [vp, C.c_char_p, vp, i64]
@@ -377,6 +378,11 @@ class Trainer:
         out = (C.c_float * 4)()
         check(self.lib.dtx_last_step_timings(self._h, out), self._h)
         return {"step": out[0], "fwd_bwd": out[1], "allreduce": out[2], "optimizer": out[3]}
+
+    @property
+    def last_step_groups(self) -> int:
+        """Length groups the last training micro-batch was run as (1 = one pass at the batch's padded length)."""
+        return int(self.lib.dtx_last_step_groups(self._h))
 
     @property
     def base_weight_bytes(self) -> int:

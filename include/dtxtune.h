@@ -159,6 +159,8 @@ DTX_API float dtx_last_step_ms(const dtx_trainer* t);
 /* event-timed segments of the most recent dtx_step in ms: out[0] whole step, out[1] forward + backward, out[2] gradient
  * all-reduce (0 when world == 1 or no optimizer step ran), out[3] grad-norm + clip + AdamW + adapter refresh */
 DTX_API int32_t dtx_last_step_timings(const dtx_trainer* t, float* out4);
+/* Length groups the last training micro-batch was run as (1: one pass; > 1: see "varlen_split" below). */
+DTX_API int32_t dtx_last_step_groups(const dtx_trainer* t);
 /* HF get_scheduler value: lr multiplier after `step` optimizer steps (host arithmetic, no device). */
 DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, int32_t total_steps);
 
@@ -168,6 +170,9 @@ DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, 
  * CTA-pair GEMM in 256-row tiles (default 16).  "attn_fwd_exp_fma_every" = N in {0, 2, 3, 4}: every N-th pair of the forward
  * softmax's exponentials is computed on the FMA pipe (cubic polynomial) instead of MUFU.EX2 (default 3; 0 = none).
  * "attn_dq_exp_fma_every" = N in {0, 3, 4}: the same for the dQ kernel's exp / dS phase (default 0).
+ * "varlen_split" = 1 (default): a LoRA micro-batch that comes with row lengths is run as length groups (rows sorted by length,
+ * partition chosen by a cost model; same token-mean loss and gradients up to summation order); 0: one pass at the batch's length.
+ * "varlen_group_cost" = N: fixed cost the partition's cost model charges per group, in thousandths of one wave of every GEMM of a layer.
  * "nf4_prefetch" = 1 (default): with --quantization int4 the next matrix is expanded on a side stream under the current GEMM
  * (read at dtx_quantize_base time); 0: expansion inline on the main stream.  Unknown names return DTX_ERR_INVALID. */
 DTX_API int32_t dtx_set_option(const char* name, int32_t value);

@@ -795,6 +795,77 @@ def check_trainer_varlen(steps=4):
     return {"loss": worst_l, "gnorm": worst_g, "adapter_grads": per}
 
 
+def check_trainer_varlen_groups():
+    """A ragged micro-batch run as LENGTH GROUPS (rows sorted by length, each group padded to its own longest row, gradients
+    accumulated, every group's loss divided by the labelled tokens of the whole micro-batch) == the oracle on the batch as a
+    whole: loss, grad-norm, adapter gradients - with gradient accumulation over two ragged micro-batches, through both the
+    host-buffer and the device-pointer entry points.  "varlen_split" = 2 forces the cut wherever 128-rounded lengths differ
+    (the cost model would not split a model this small)."""
+    ocfg, mc, tc = tiny_configs(S=512, B=4, steps=6)
+    ocfg.grad_accum = 2
+    tc.grad_accum = 2
+    w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
+    gen = torch.Generator().manual_seed(5)
+    lora = {k: (torch.randn(v.shape, generator=gen) * 0.02 if "lora_B" in k else v) for k, v in lora.items()}
+    orc = O.OracleTrainer(ocfg, w, lora)
+    L.set_option("varlen_split", 2)
+    try:
+        tr = L.Trainer(mc, tc)
+        tr.load_state_dict({k: v.numpy() for k, v in w.items()})
+        tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+        patterns = [[384, 130, 7, 257], [512, 1, 128, 129], [100, 100, 100, 100], [256, 384, 64, 0], [500, 20, 300, 300], [129, 128, 127, 1]]
+        worst_l = worst_g = 0.0
+        groups = []
+
+        def ragged(step, lens):
+            ids, labels = O.synthetic_batch(step, 0, 4, 512, ocfg.vocab)
+            cur = max(128, int(-(-int(max(lens)) // 128) * 128))
+            for b in range(4):
+                ids[b, lens[b]:] = 0
+                labels[b, lens[b]:] = -100
+                if lens[b] > 0:
+                    labels[b, :max(1, lens[b] // 3)] = -100
+            return np.ascontiguousarray(ids[:, :cur]), np.ascontiguousarray(labels[:, :cur]), np.array(lens, dtype=np.int32)
+
+        for it in range(3):
+            mbs = [ragged(2 * it + k, patterns[(2 * it + k) % len(patterns)]) for k in range(2)]
+            ref = orc.step([(m[0], m[1]) for m in mbs])
+            losses = []
+            for k, (ids, labels, lens) in enumerate(mbs):
+                if it == 1:  # device-pointer entry point
+                    d_ids, d_lab, d_len = (torch.from_numpy(a).cuda() for a in (ids, labels, lens))
+                    loss, gn, _, stepped = tr.step_ptr(d_ids.data_ptr(), d_lab.data_ptr(), True, d_len.data_ptr(), ids.shape[1])
+                else:
+                    loss, gn, _, stepped = tr.step(ids, labels, lens)
+                groups.append(tr.last_step_groups)
+                losses.append(loss)
+                assert stepped == (k == 1)
+            got = float(np.sum(losses)) / 2  # HF: every micro-batch loss divided by grad_accum
+            worst_l, worst_g = max(worst_l, abs(got - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
+        assert max(groups) >= 3 and groups[2] == 1, groups  # [100,100,100,100] stays one group
+        # adapter gradients of one ragged micro-batch pair against the oracle's autograd gradients (fresh adapters as above)
+        tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+        with torch.no_grad():
+            for k, v in lora.items():
+                orc.lora[k].copy_(v)
+        a, b = ragged(50, [300, 5, 200, 129]), ragged(51, [64, 511, 128, 260])
+        _, g_a = orc.loss_and_grads(a[0], a[1])
+        _, g_b = orc.loss_and_grads(b[0], b[1])
+        tr.step(*a)
+        tr.step(*b)  # the exported buffer holds the SUM over the micro-batches (1 / grad_accum is applied inside the optimizer kernel)
+        got = tr.export_adapter(grads=True)
+        per = {}
+        for k, v in got.items():
+            kk = k.replace("base_model.model.", "")
+            r = g_a[kk].numpy() + g_b[kk].numpy()
+            per[k.split("layers.")[1]] = float(np.linalg.norm(v - r) / max(np.linalg.norm(r), 1e-12))
+        tr.close()
+    finally:
+        L.set_option("varlen_split", 1)
+    assert worst_l < 1e-3 and worst_g < 3e-2 and max(per.values()) < 4e-2, (worst_l, worst_g, per)
+    return {"loss": worst_l, "gnorm": worst_g, "groups": groups, "adapter_grads": per}
+
+
 def check_eval_rows_and_force_step():
     """dtx_eval_loss row statistics compose to the batch loss; DTX_STEP_FORCE steps before grad_accum micro-batches are in."""
     ocfg, mc, tc = tiny_configs(steps=4)
@@ -1203,7 +1274,7 @@ ALL = {
     "attn_bench_shape_s4096_gqa": lambda: check_attn_bench_shape(B=1, S=4096, H=32, Hkv=8, kv_heads=(0, 5)),
     "attn_bwd_rope": check_attn_bwd_rope, "attn_varlen": check_attn_varlen, "attn_window": check_attn_window,
     "trainer_window": check_trainer_window,
-    "trainer_varlen": check_trainer_varlen, "eval_rows_force_step": check_eval_rows_and_force_step,
+    "trainer_varlen": check_trainer_varlen, "trainer_varlen_groups": check_trainer_varlen_groups, "eval_rows_force_step": check_eval_rows_and_force_step,
     "missing_weight_refused": check_missing_weight_is_refused, "layer_7b_shape": check_layer_7b_shape,
     "trainer_full": check_trainer_full, "trainer_full_accum": lambda: check_trainer_full(steps=4, grad_accum=2, weight_decay=0.0),
     "trainer_full_gqa": lambda: check_trainer_full_gqa(), "trainer_qlora": check_trainer_qlora, "embedding": check_embedding, "cross_entropy": check_cross_entropy,

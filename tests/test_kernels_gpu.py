@@ -33,7 +33,7 @@ def test_attention(name):
 
 
 @pytest.mark.parametrize("name", ["trainer_tiny", "trainer_gqa", "trainer_dropout", "trainer_qlora", "trainer_unfused", "trainer_deterministic", "trainer_grad_accum", "trainer_100_steps",
-                                  "trainer_varlen", "trainer_window", "eval_rows_force_step", "missing_weight_refused", "layer_7b_shape", "trainer_full", "trainer_full_accum", "trainer_full_gqa",
+                                  "trainer_varlen", "trainer_varlen_groups", "trainer_window", "eval_rows_force_step", "missing_weight_refused", "layer_7b_shape", "trainer_full", "trainer_full_accum", "trainer_full_gqa",
                                   "worker_end_to_end"])
 def test_training_step(name):
     _run(name)

@@ -42,6 +42,8 @@ for s in $STEPS; do
     benchcpu) timeout 900 python bench.py --steps 8 --warmup 3 > $OUT/bench_cpu.json 2> $OUT/bench_cpu.err;;
     refarm) timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_reference.json 2> $OUT/bench_reference.err;;
     varlen) timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen.json 2> $OUT/bench_varlen.err;;
+    varlen_cost) for v in ${COSTS:-250 500 1000}; do DTX_VARLEN_GROUP_COST=$v timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen_cost$v.json 2> $OUT/bench_varlen_cost$v.err; done;;
+    varlen_ab) for v in 0 1; do DTX_VARLEN_SPLIT=$v timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen_split$v.json 2> $OUT/bench_varlen_split$v.err; done;;
     qlora) timeout 600 python bench.py --config mistral7b_qlora --steps 5 --warmup 3 > $OUT/bench_qlora.json 2> $OUT/bench_qlora.err;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1600 -c 2000 --csv --log-file $OUT/launches.csv \
                 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1;;
