@@ -81,7 +81,7 @@ thread_local std::string g_error;
 int g_nf4_prefetch = 1;     // expand the next NF4 matrix on a side stream while the current GEMM runs (0: inline, for A/B runs)
 int g_varlen_split = 1;     // ragged micro-batches run as length groups (rows sorted by length, partition chosen by a cost model);
                             // 2: always cut where the 128-rounded lengths differ (parity tests at shapes too small for the model to split)
-int g_varlen_fix_permille = 2000;  // fixed cost charged per length group, in thousandths of "one wave of every GEMM of a layer"
+int g_varlen_fix_permille = 200;   // fixed cost charged per length group, in thousandths of "one wave of every GEMM of a layer"
 int g_fused_epilogues = 1;  // RoPE / SwiGLU fused into the GEMM and attention epilogues (needs M > 128: CTA-pair GEMM)
 
 // ------------------------------------------------------------------------------------------------

@@ -1023,9 +1023,31 @@ def check_layer_7b_shape(B=2, S=2048):
     for k, v in got.items():
         r = g_ref[k.replace("base_model.model.", "")].numpy()
         errs[k.split("layers.0.")[1]] = float(np.linalg.norm(v - r) / max(np.linalg.norm(r), 1e-12))
+    # the same geometry with RAGGED rows run as two length groups (rows of 2048 and 700 tokens -> rectangles [1, 2048] and
+    # [1, 768]) against the oracle on the padded batch as a whole; the adapters are reset to the ones the oracle holds
+    ragged = {}
+    if B == 2 and S >= 1024:
+        tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+        lens = np.array([S, 700], dtype=np.int32)
+        ids2, labels2 = O.synthetic_batch(1, 0, B, S, ocfg.vocab)
+        ids2[1, 700:] = 0
+        labels2[1, 700:] = -100
+        ref2, g2 = orc.loss_and_grads(ids2, labels2)
+        L.set_option("varlen_split", 2)
+        try:
+            loss2, _, _, _ = tr.step(ids2, labels2, lens)
+            n_groups = tr.last_step_groups
+        finally:
+            L.set_option("varlen_split", 1)
+        got2 = tr.export_adapter(grads=True)
+        errs2 = {k.split("layers.0.")[1]: float(np.linalg.norm(v - g2[k.replace("base_model.model.", "")].numpy()) /
+                                                max(np.linalg.norm(g2[k.replace("base_model.model.", "")].numpy()), 1e-12)) for k, v in got2.items()}
+        ragged = {"groups": n_groups, "loss_rel": abs(loss2 - ref2) / ref2, "adapter_grad_rel": errs2}
+        assert n_groups == 2 and ragged["loss_rel"] < 1e-3 and max(errs2.values()) < 4e-2, ragged
     tr.close()
     res = {"eval_loss_rel": e_eval, "step_loss_rel": abs(loss - ref_loss) / ref_loss, "gnorm_rel": abs(gn - ref_norm) / ref_norm,
-           "adapter_grad_rel": errs, "oracle_loss": ref_loss, "native_loss": loss, "sec_init": t_init, "sec_oracle_fwd_bwd": t_cpu}
+           "adapter_grad_rel": errs, "oracle_loss": ref_loss, "native_loss": loss, "sec_init": t_init, "sec_oracle_fwd_bwd": t_cpu,
+           "ragged_length_groups": ragged}
     assert e_eval < 1e-3 and res["step_loss_rel"] < 1e-3, res
     assert res["gnorm_rel"] < 3e-2 and max(errs.values()) < 4e-2, res
     return res
