@@ -337,7 +337,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   if (warp == 1) tmem_alloc_pair(tmem_ptr_smem, G2_TMEM_COLS);
   tc_fence_before();
-  __syncthreads();     // CTA-local ordering of the allocator's shared-memory write (racecheck does not see barrier.cluster as one)
+  __syncthreads();     // CTA-local ordering of the allocator's shared-memory write before the cluster barrier (racecheck still reports the
+                       // cta_group::2 allocation instruction against itself: profiles/r02_sanitizer.txt)
   cluster_sync_all();  // both CTAs' barriers are initialised and their TMEM allocated before anyone signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
