@@ -992,19 +992,22 @@ struct SubPlan {
   int n_div = 0;        // labelled tokens of the whole micro-batch, counted the way the groups' shift_labels kernels will
 };
 
-double group_cost(const dtx_trainer* t, int rows, int S) {
-  const int d = t->mc.hidden, F = t->mc.ffn, W = t->W;
+struct PlanDims { int hidden, ffn, W, n_sms, B; };  // what the cost model needs of the model / device / batch
+
+double group_cost(const PlanDims& t, int rows, int S) {
+  const int d = t.hidden, F = t.ffn, W = t.W;
   const long long mt = (static_cast<long long>(rows) * S + 255) / 256;
-  const long long slots = std::max(1, t->n_sms / 2);
+  const long long slots = std::max(1, t.n_sms / 2);
   auto waves = [&](int n_cols, int k) { return static_cast<double>((mt * ((n_cols + 255) / 256) + slots - 1) / slots) * k; };
   // forward: qkv, o, gate|up, down; backward dX: through down (N = F), gate|up, o, qkv
   return waves(W, d) + waves(d, d) + waves(2 * F, d) + waves(d, F) + waves(F, d) + waves(d, 2 * F) + waves(d, d) + waves(d, W);
 }
 
-void plan_groups(const dtx_trainer* t, const int32_t* lens, const int32_t* labels, int S_batch, SubPlan* p) {
-  const int B = t->tc.micro_batch;
+// labels may be null (planning only: n_div stays 0)
+void plan_groups(const PlanDims& t, const int32_t* lens, const int32_t* labels, int S_batch, SubPlan* p) {
+  const int B = t.B;
   p->n = 1;
-  if (!g_varlen_split || t->full || !lens || B < 2 || B > 64) return;
+  if (!g_varlen_split || !lens || B < 2 || B > 64) return;
   auto c128 = [&](int len) { return std::min(S_batch, std::max(128, (std::min(std::max(len, 0), S_batch) + 127) / 128 * 128)); };
   for (int i = 0; i < B; ++i) p->order[i] = i;
   std::stable_sort(p->order, p->order + B, [&](int a, int b) { return lens[a] > lens[b]; });
@@ -1038,6 +1041,7 @@ void plan_groups(const dtx_trainer* t, const int32_t* lens, const int32_t* label
     p->S[g] = S;
   }
   if (n < 2) { p->n = 1; return; }
+  if (!labels) return;
   long long cnt = 0;  // positions 1 .. S_g - 1 of every row carry the shifted label of the position before them
   for (int g = 0; g < n; ++g)
     for (int k = p->start[g]; k < p->start[g + 1]; ++k) {
@@ -1565,7 +1569,7 @@ int32_t dtx_step(dtx_trainer* t, const int32_t* ids, const int32_t* labels, cons
   if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, seq_lens != nullptr);
   if (rc) return rc;
   SubPlan plan;
-  plan_groups(t, seq_lens, labels, t->cur_S, &plan);
+  if (!t->full) plan_groups(PlanDims{t->mc.hidden, t->mc.ffn, t->W, t->n_sms, t->tc.micro_batch}, seq_lens, labels, t->cur_S, &plan);
   if (plan.n > 1) {  // ragged batch: the whole batch goes to the staging buffers, the length groups gather from there
     const int S_src = t->cur_S;
     CKM(cudaMemcpyAsync(t->d_ids_full, ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
@@ -1594,7 +1598,7 @@ int32_t dtx_step_device(dtx_trainer* t, const void* d_ids, const void* d_labels,
     CKM(cudaMemcpyAsync(t->h_labels.data(), d_labels, t->h_labels.size() * 4, cudaMemcpyDeviceToHost, t->stream));
     CKM(cudaStreamSynchronize(t->stream));
     SubPlan plan;
-    plan_groups(t, t->h_lens.data(), t->h_labels.data(), t->cur_S, &plan);
+    plan_groups(PlanDims{t->mc.hidden, t->mc.ffn, t->W, t->n_sms, t->tc.micro_batch}, t->h_lens.data(), t->h_labels.data(), t->cur_S, &plan);
     if (plan.n > 1)
       return do_step(t, flags, loss, gnorm, lr, stepped, &plan, static_cast<const int32_t*>(d_ids), static_cast<const int32_t*>(d_labels),
                      static_cast<const int32_t*>(d_seq_lens), t->cur_S);
@@ -1740,6 +1744,27 @@ int64_t dtx_num_trainable(const dtx_trainer* t) { return t ? t->n_train : 0; }
 int64_t dtx_launch_count(const dtx_trainer* t) { return t ? t->launches : 0; }
 float dtx_last_step_ms(const dtx_trainer* t) { return t ? t->last_ms : 0.f; }
 int32_t dtx_last_step_groups(const dtx_trainer* t) { return t ? t->last_groups : 0; }
+
+int32_t dtx_plan_length_groups(const dtx_model_cfg* mc, int32_t micro_batch, int32_t n_sms, const int32_t* seq_lens, int32_t seq_len_batch,
+                               int32_t* order_out, int32_t* group_start_out, int32_t* group_len_out) {
+  if (!mc || !seq_lens || !order_out || !group_start_out || !group_len_out || micro_batch < 1 || seq_len_batch < 128 || seq_len_batch % 128)
+    return DTX_ERR_INVALID;
+  const int hkv = mc->n_kv_heads > 0 ? mc->n_kv_heads : mc->n_heads;
+  SubPlan plan;
+  plan_groups(PlanDims{mc->hidden, mc->ffn, (mc->n_heads + 2 * hkv) * mc->head_dim, n_sms > 0 ? n_sms : 148, micro_batch}, seq_lens, nullptr,
+              seq_len_batch, &plan);
+  if (plan.n <= 1) {  // one pass at the batch's padded length, rows in their own order
+    for (int i = 0; i < micro_batch; ++i) order_out[i] = i;
+    group_start_out[0] = 0;
+    group_start_out[1] = micro_batch;
+    group_len_out[0] = seq_len_batch;
+    return 1;
+  }
+  for (int i = 0; i < micro_batch; ++i) order_out[i] = plan.order[i];
+  for (int g = 0; g <= plan.n; ++g) group_start_out[g] = plan.start[g];
+  for (int g = 0; g < plan.n; ++g) group_len_out[g] = plan.S[g];
+  return plan.n;
+}
 
 int32_t dtx_last_step_timings(const dtx_trainer* t, float* out4) {
   if (!t || !out4) return DTX_ERR_INVALID;

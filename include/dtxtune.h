@@ -161,6 +161,12 @@ DTX_API float dtx_last_step_ms(const dtx_trainer* t);
 DTX_API int32_t dtx_last_step_timings(const dtx_trainer* t, float* out4);
 /* Length groups the last training micro-batch was run as (1: one pass; > 1: see "varlen_split" below). */
 DTX_API int32_t dtx_last_step_groups(const dtx_trainer* t);
+/* The partition dtx_step would choose for a LoRA micro-batch of `micro_batch` rows with these true lengths, padded to
+ * seq_len_batch (host arithmetic, no device; n_sms <= 0: 148).  order_out[micro_batch]: rows sorted by length, longest first;
+ * group g = order_out[group_start_out[g] .. group_start_out[g+1]) run at padded length group_len_out[g] (arrays of micro_batch + 1
+ * and micro_batch entries).  Returns the number of groups (1 = one pass at seq_len_batch) or a negative status. */
+DTX_API int32_t dtx_plan_length_groups(const dtx_model_cfg* mc, int32_t micro_batch, int32_t n_sms, const int32_t* seq_lens,
+                                       int32_t seq_len_batch, int32_t* order_out, int32_t* group_start_out, int32_t* group_len_out);
 /* HF get_scheduler value: lr multiplier after `step` optimizer steps (host arithmetic, no device). */
 DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, int32_t total_steps);
 

@@ -280,8 +280,9 @@ def check_nf4(n=64 * 5000):
 
 def check_trainer_qlora(steps=6):
     """--quantization int4: native trainer on PACKED NF4 base weights == oracle trained on nf4_roundtrip'ed weights; the packed
-    base is 0.5625 / 2 of the bf16 one; int8 is refused loudly."""
-    ocfg, mc, tc = tiny_configs(steps=steps)
+    base is 0.5625 / 2 of the bf16 one; int8 is refused loudly.  The last two steps are ragged and run as two length groups
+    (the NF4 expansion / prefetch state carries across the groups' forward+backward passes)."""
+    ocfg, mc, tc = tiny_configs(S=512, steps=steps)
     w, lora = O.init_base_weights(ocfg, 1234), O.init_lora(ocfg, 4321)
     tr = L.Trainer(mc, tc)
     tr.load_state_dict({k: v.numpy() for k, v in w.items()})
@@ -298,12 +299,24 @@ def check_trainer_qlora(steps=6):
     tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
     orc = O.OracleTrainer(ocfg, O.quantize_base_nf4(w), lora)
     worst_l = worst_g = 0.0
+    groups = []
     for s_ in range(steps):
         ids, labels = O.synthetic_batch(s_, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)
+        lens = None
+        if s_ >= steps - 2:
+            lens = np.array([512, 100 + 30 * s_], dtype=np.int32)
+            ids[1, lens[1]:] = 0
+            labels[1, lens[1]:] = -100
+            L.set_option("varlen_split", 2)
         ref = orc.step([(ids, labels)])
-        loss, gn, _, _ = tr.step(ids, labels)
+        try:
+            loss, gn, _, _ = tr.step(ids, labels, lens)
+        finally:
+            L.set_option("varlen_split", 1)
+        groups.append(tr.last_step_groups)
         worst_l, worst_g = max(worst_l, abs(loss - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
     tr.close()
+    assert groups[-2:] == [2, 2] and groups[0] == 1, groups
     plain = O.OracleTrainer(ocfg, w, lora).step([O.synthetic_batch(0, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)]).loss
     assert worst_l < 1e-3 and worst_g < 3e-2, (worst_l, worst_g)
     return {"loss": worst_l, "gnorm": worst_g, "loss_shift_vs_unquantized": abs(plain - ref.loss), "base_bytes_bf16": bytes_bf16,

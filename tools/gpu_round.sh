@@ -22,6 +22,7 @@ for s in $STEPS; do
                timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python -m tests.gpu_checks attn_varlen trainer_varlen > $OUT/memcheck_varlen.log 2>&1; echo "memcheck_varlen rc=$?" >> $OUT/sanitizer_summary.txt;;
     mgpu_check) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29541 tests/multi_gpu_check.py > $OUT/multi_gpu_check_n${NGPU:-2}.log 2>&1;;
     mgpu_full) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29544 tests/multi_gpu_check.py --full > $OUT/multi_gpu_check_full_n${NGPU:-2}.log 2>&1;;
+    mgpu_ragged) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29548 tests/multi_gpu_check.py --ragged > $OUT/multi_gpu_check_ragged_n${NGPU:-2}.log 2>&1;;
     bench_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus ${NGPU:-2} --steps 8 --warmup 3 > $OUT/bench_n${NGPU:-2}.json 2> $OUT/bench_n${NGPU:-2}.err;;
     qlora_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29543 bench.py --config mistral7b_qlora --gpus ${NGPU:-2} --steps 5 --warmup 3 > $OUT/bench_qlora_n${NGPU:-2}.json 2> $OUT/bench_qlora_n${NGPU:-2}.err;;
     full13b_n) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-8} --master-addr 127.0.0.1 --master-port 29545 bench.py --config 13b_full --gpus ${NGPU:-8} --steps 6 --warmup 3 > $OUT/bench_13b_full_n${NGPU:-8}.json 2> $OUT/bench_13b_full_n${NGPU:-8}.err;;
