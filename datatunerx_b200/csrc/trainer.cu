@@ -1076,7 +1076,11 @@ int do_step(dtx_trainer* t, int32_t flags, float* loss_out, float* gnorm_out, fl
       rl.n = plan->start[g + 1] - plan->start[g];
       for (int k = 0; k < rl.n; ++k) rl.rows[k] = plan->order[plan->start[g] + k];
       cudaError_t ge = gather_rows(src_ids, src_labels, src_lens, S_src, rl, plan->S[g], t->d_ids, t->d_labels, t->d_seq_lens, t->stream);
-      if (ge != cudaSuccess) return t->fail(DTX_ERR_CUDA, "gather_rows: %s", cudaGetErrorString(ge));
+      if (ge != cudaSuccess) {
+        t->sub_accum = false;
+        t->sub_ndiv = 0;
+        return t->fail(DTX_ERR_CUDA, "gather_rows: %s", cudaGetErrorString(ge));
+      }
       t->cur_B = rl.n;
       t->cur_S = plan->S[g];
       t->cur_M = rl.n * plan->S[g];
