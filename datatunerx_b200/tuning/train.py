@@ -98,6 +98,9 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
                        lora_dropout=a.lora_dropout, lora_target=tuple(a.lora_target), lr=a.learning_rate, weight_decay=a.weight_decay,
                        beta1=a.adam_beta1, beta2=a.adam_beta2, eps=a.adam_epsilon, max_grad_norm=a.max_grad_norm,
                        sched=a.lr_scheduler_type, warmup_steps=a.warmup_steps, grad_accum=GA, seed=a.seed, full_finetune=full)
+    for kv in filter(None, os.environ.get("DTX_OPTIONS", "").split(",")):  # library A/B switches, e.g. DTX_OPTIONS=varlen_split=0
+        name, _, value = kv.partition("=")
+        L.set_option(name.strip(), int(value))
     device = int(os.environ.get("DTX_DEVICE", rank))
     tr = L.Trainer(mc, tc, device=device, rank=rank, world=world, nccl_id=nccl_id)
     if os.environ.get("DTX_RANDOM_INIT"):  # benchmarking / scheduling harnesses: config.json only, N(0, 0.02) weights on the device
@@ -115,6 +118,7 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
     step, window, micro_losses, t0 = 0, [], [], time.time()
     batched, tokens = 0, 0  # HF total_batched_samples: accumulation runs across epoch boundaries
     t_first, tok_first, t_last = None, 0, None  # steady state: from the end of the first optimizer step to the end of the last
+    groups_sum = 0  # length groups the ragged micro-batches were run as
     epoch = 0
     while step < total:
         for i, (ids, labels, lens) in enumerate(D.epoch_batches(dataset, rank, world, B, seq_len, pad_id, epoch, a.seed, varlen=True)):
@@ -125,6 +129,7 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
             boundary = batched % GA == 0 or last_of_short_epoch
             loss, gnorm, lr, stepped = tr.step(ids, labels, lens, force_step=boundary)
             tokens += int(lens.sum())
+            groups_sum += tr.last_step_groups
             micro_losses.append(loss)
             if not stepped:
                 continue
@@ -167,7 +172,8 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
               flush=True)
         if step > 1 and t_last > t_first:  # without the first step (lazy CUDA / NCCL initialisation) and the checkpoint writes
             print(f"steady_state {t_last - t_first:.3f}s, {step - 1} optimizer steps, {tokens - tok_first} real tokens on rank 0 "
-                  f"({(tokens - tok_first) / (t_last - t_first):.1f} tokens/s/rank)", flush=True)
+                  f"({(tokens - tok_first) / (t_last - t_first):.1f} tokens/s/rank), {groups_sum / max(batched, 1):.2f} length groups per micro-batch",
+                  flush=True)
     tr.close()
     return ckpt
 

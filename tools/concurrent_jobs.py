@@ -46,13 +46,19 @@ def make_model_dir(path: str, m: dict) -> None:
     json.dump(cfg, open(os.path.join(path, "config.json"), "w"))
 
 
-def make_csv(path: str, rows: int, block: int) -> None:
-    # ~0.66 tokens per character with the tiny tokenizer: make every row longer than the block so that truncation fills it
-    q = "Explain step by step how the following numbers add up and why the answer is what it is. " * max(1, block // 120)
-    a = "The answer follows from adding the numbers one after another and carrying where needed. " * max(1, block // 60)
+def make_csv(path: str, rows: int, block: int, ragged: bool = False) -> None:
+    # ~0.66 tokens per character with the tiny tokenizer: make every row longer than the block so that truncation fills it;
+    # ragged: log-normal row lengths around a quarter of the block (the shape of real instruction data)
+    import numpy as np
+    rng = np.random.default_rng(11)
+    qs, as_ = "Explain step by step how the following numbers add up and why the answer is what it is. ", \
+        "The answer follows from adding the numbers one after another and carrying where needed. "
     with open(path, "w") as f:
         f.write("q,a\n")
         for i in range(rows):
+            scale = float(np.clip(np.exp(rng.normal(np.log(0.25), 0.6)), 0.02, 1.5)) if ragged else 1.5
+            q = qs * max(1, int(scale * block / 120))
+            a = as_ * max(1, int(scale * block / 60))
             f.write(f"\"{i}: {q}\",\"{i}: {a}\"\n")
 
 
@@ -62,6 +68,7 @@ def main():
     ap.add_argument("--gpus-per-job", type=int, default=2)
     ap.add_argument("--model", default="7b", choices=sorted(MODELS))
     ap.add_argument("--steps", type=int, default=12, help="optimizer steps per job (one epoch)")
+    ap.add_argument("--ragged", action="store_true", help="log-normal row lengths instead of rows that fill the block")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "concurrent_jobs.json"))
     args = ap.parse_args()
     from datatunerx_b200.tuning import parser as TP
@@ -72,7 +79,7 @@ def main():
     make_model_dir(mdir, m)
     rows = args.steps * m["batch"] * args.gpus_per_job
     csv_path = os.path.join(tmp, "train.csv")
-    make_csv(csv_path, rows, m["block"])
+    make_csv(csv_path, rows, m["block"], args.ragged)
     # the hyper-parameter sweep of the experiment: one (lr, lora_r, scheduler) per job
     sweep = [("1e-4", "16", "linear"), ("2e-4", "16", "cosine"), ("5e-5", "8", "linear"), ("1e-4", "32", "cosine"),
              ("3e-4", "16", "linear"), ("1e-4", "8", "cosine"), ("2e-4", "32", "linear"), ("5e-5", "16", "cosine")]
@@ -103,6 +110,9 @@ def main():
         if mt:
             dt, steps, toks = float(mt.group(1)), int(mt.group(2)), int(mt.group(3))
             rec.update(train_runtime_s=dt, optimizer_steps=steps, tokens_per_s=toks * args.gpus_per_job / dt)
+            mg = re.search(r"([0-9.]+) length groups per micro-batch", out)
+            if mg:
+                rec["length_groups_per_micro_batch"] = float(mg.group(1))
             ms = re.search(r"steady_state ([0-9.]+)s, (\d+) optimizer steps, (\d+) real tokens on rank 0", out)
             if ms:  # from the end of the first optimizer step to the end of the last: no lazy initialisation, no checkpoint writes
                 rec.update(steady_state_s=float(ms.group(1)), steady_tokens_per_s=int(ms.group(3)) * args.gpus_per_job / float(ms.group(1)))
