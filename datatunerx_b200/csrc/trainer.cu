@@ -207,6 +207,8 @@ struct dtx_trainer {
   int32_t *d_row_map = nullptr, *d_valid_idx = nullptr;  // token -> position among the labelled tokens (-1: none) and back
   int32_t *d_ids_full = nullptr, *d_labels_full = nullptr, *d_lens_full = nullptr;  // the whole ragged micro-batch (length groups gather from it)
   std::vector<int32_t> h_labels, h_lens;  // host copies of a device-resident ragged batch (the partition is planned on the host)
+  std::vector<float> h_row_sum;           // per-row evaluation statistics of the length groups, in group order
+  std::vector<int32_t> h_row_valid;
   float* d_row_sum = nullptr;     // [micro_batch] per-row summed token loss (evaluation)
   int32_t* d_row_valid = nullptr; // [micro_batch] per-row valid-token count
   double* d_host_red = nullptr;   // staging for dtx_allreduce_host
@@ -1081,6 +1083,7 @@ int do_step(dtx_trainer* t, int32_t flags, float* loss_out, float* gnorm_out, fl
         t->sub_ndiv = 0;
         return t->fail(DTX_ERR_CUDA, "gather_rows: %s", cudaGetErrorString(ge));
       }
+      t->launches += 1;
       t->cur_B = rl.n;
       t->cur_S = plan->S[g];
       t->cur_M = rl.n * plan->S[g];
@@ -1621,12 +1624,61 @@ int32_t dtx_eval_loss(dtx_trainer* t, const int32_t* ids, const int32_t* labels,
   if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, seq_lens != nullptr);
   if (rc) return rc;
   const int B = t->tc.micro_batch;
+  SubPlan plan;
+  if (!t->full) plan_groups(PlanDims{t->mc.hidden, t->mc.ffn, t->W, t->n_sms, B}, seq_lens, labels, t->cur_S, &plan);
+  float h = 0.f;
+  if (plan.n > 1) {
+    // ragged batch as length groups (forward only): the per-row statistics come back in group order and are put back in
+    // the caller's row order; the batch loss accumulates over the groups with the whole batch's labelled-token count
+    const int S_src = t->cur_S;
+    CKM(cudaMemcpyAsync(t->d_ids_full, ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+    CKM(cudaMemcpyAsync(t->d_labels_full, labels, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+    CKM(cudaMemcpyAsync(t->d_lens_full, seq_lens, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, t->stream));
+    t->h_row_sum.assign(static_cast<size_t>(B), 0.f);
+    t->h_row_valid.assign(static_cast<size_t>(B), 0);
+    for (int g = 0; g < plan.n && rc == DTX_OK; ++g) {
+      RowList rl;
+      rl.n = plan.start[g + 1] - plan.start[g];
+      for (int k = 0; k < rl.n; ++k) rl.rows[k] = plan.order[plan.start[g] + k];
+      cudaError_t ge = gather_rows(t->d_ids_full, t->d_labels_full, t->d_lens_full, S_src, rl, plan.S[g], t->d_ids, t->d_labels,
+                                   t->d_seq_lens, t->stream);
+      if (ge != cudaSuccess) rc = t->fail(DTX_ERR_CUDA, "gather_rows: %s", cudaGetErrorString(ge));
+      if (rc) break;
+      t->launches += 1;
+      t->cur_B = rl.n;
+      t->cur_S = plan.S[g];
+      t->cur_M = rl.n * plan.S[g];
+      t->use_seq_lens = true;
+      t->sub_accum = g > 0;
+      t->sub_ndiv = plan.n_div;
+      rc = fwd_bwd(t, false);
+      if (rc == DTX_OK && (row_sum_out || row_valid_out)) {
+        cudaError_t e2 = row_loss_stats(t->row_loss, t->d_shift, rl.n, t->cur_S, t->d_row_sum, t->d_row_valid, t->stream);
+        if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(t->h_row_sum.data() + plan.start[g], t->d_row_sum, static_cast<size_t>(rl.n) * 4, cudaMemcpyDeviceToHost, t->stream);
+        if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(t->h_row_valid.data() + plan.start[g], t->d_row_valid, static_cast<size_t>(rl.n) * 4, cudaMemcpyDeviceToHost, t->stream);
+        // d_row_sum / d_row_valid are reused by the next group: the copies above are stream-ordered in front of its kernels
+        if (e2 != cudaSuccess) rc = t->fail(DTX_ERR_CUDA, "eval row statistics: %s", cudaGetErrorString(e2));
+        t->launches += 1;
+      }
+    }
+    t->sub_accum = false;
+    t->sub_ndiv = 0;
+    if (rc) return rc;
+    CKM(cudaMemcpyAsync(&h, t->d_loss, 4, cudaMemcpyDeviceToHost, t->stream));
+    cudaError_t e = cudaStreamSynchronize(t->stream);
+    if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "eval failed on device: %s", cudaGetErrorString(e));
+    for (int k = 0; k < B; ++k) {
+      if (row_sum_out) row_sum_out[plan.order[k]] = t->h_row_sum[static_cast<size_t>(k)];
+      if (row_valid_out) row_valid_out[plan.order[k]] = t->h_row_valid[static_cast<size_t>(k)];
+    }
+    if (loss_out) *loss_out = h;
+    return DTX_OK;
+  }
   CKM(cudaMemcpyAsync(t->d_ids, ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
   CKM(cudaMemcpyAsync(t->d_labels, labels, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
   if (seq_lens) CKM(cudaMemcpyAsync(t->d_seq_lens, seq_lens, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, t->stream));
   rc = fwd_bwd(t, false);
   if (rc) return rc;
-  float h = 0.f;
   CKM(cudaMemcpyAsync(&h, t->d_loss, 4, cudaMemcpyDeviceToHost, t->stream));
   if (row_sum_out || row_valid_out) {
     CK(row_loss_stats(t->row_loss, t->d_shift, B, t->cur_S, t->d_row_sum, t->d_row_valid, t->stream), 1);

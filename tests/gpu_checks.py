@@ -840,6 +840,17 @@ def check_trainer_varlen_groups():
                     labels[b, :max(1, lens[b] // 3)] = -100
             return np.ascontiguousarray(ids[:, :cur]), np.ascontiguousarray(labels[:, :cur]), np.array(lens, dtype=np.int32)
 
+        # forward-only evaluation of a ragged batch: per-row statistics come back in the caller's row order whatever the grouping
+        e_ids, e_lab, e_len = ragged(77, patterns[0])
+        s_grp, c_grp = tr.eval_rows(e_ids, e_lab, e_len)
+        l_grp = tr.eval_loss(e_ids, e_lab, e_len)
+        L.set_option("varlen_split", 0)
+        s_one, c_one = tr.eval_rows(e_ids, e_lab, e_len)
+        l_one = tr.eval_loss(e_ids, e_lab, e_len)
+        L.set_option("varlen_split", 2)
+        assert c_grp.tolist() == c_one.tolist() == [int((e_lab[b, 1:] >= 0).sum()) for b in range(4)], (c_grp, c_one)
+        eval_rel = float(np.max(np.abs(s_grp - s_one) / np.maximum(np.abs(s_one), 1e-6)))
+        assert eval_rel < 2e-3 and abs(l_grp - l_one) < 1e-4 * l_one and abs(l_grp - orc.eval_loss(e_ids, e_lab)) < 1e-3 * l_one, (s_grp, s_one, l_grp, l_one)
         for it in range(3):
             mbs = [ragged(2 * it + k, patterns[(2 * it + k) % len(patterns)]) for k in range(2)]
             ref = orc.step([(m[0], m[1]) for m in mbs])
@@ -876,7 +887,7 @@ def check_trainer_varlen_groups():
     finally:
         L.set_option("varlen_split", 1)
     assert worst_l < 1e-3 and worst_g < 3e-2 and max(per.values()) < 4e-2, (worst_l, worst_g, per)
-    return {"loss": worst_l, "gnorm": worst_g, "groups": groups, "adapter_grads": per}
+    return {"loss": worst_l, "gnorm": worst_g, "groups": groups, "adapter_grads": per, "eval_row_sums_rel": eval_rel}
 
 
 def check_eval_rows_and_force_step():
