@@ -321,6 +321,8 @@ def run_native(args, rank: int, local_rank: int, world: int):
         L.set_option("nf4_prefetch", int(os.environ["DTX_NF4_PREFETCH"]))
     if os.environ.get("DTX_VARLEN_SPLIT"):  # A/B of the length-group execution of ragged micro-batches
         L.set_option("varlen_split", int(os.environ["DTX_VARLEN_SPLIT"]))
+    if os.environ.get("DTX_VARLEN_PACK"):  # A/B: packed single pass (default) vs length groups
+        L.set_option("varlen_pack", int(os.environ["DTX_VARLEN_PACK"]))
     if os.environ.get("DTX_VARLEN_GROUP_COST"):
         L.set_option("varlen_group_cost", int(os.environ["DTX_VARLEN_GROUP_COST"]))
     if os.environ.get("DTX_GROUP_M"):  # rasterisation sweep of the CTA-pair GEMM (tools/gpu_round.sh sweep_gm)
@@ -456,6 +458,7 @@ def run_native(args, rank: int, local_rank: int, world: int):
         line["real_over_padded"] = real_all / padded_all
         # rows sorted by length and cut into groups by the library's cost model; each group runs at its own padded length
         line["length_groups_per_step"] = float(np.mean(groups))
+        line["packed_steps"] = int(sum(1 for g in groups if g == 0))  # steps run packed: sequences back to back, one pass
         line["losses_first_batches"] = losses[:n_batches]
     if gemms:
         g = gemms["nn_dh2"]

@@ -89,7 +89,19 @@ struct AttnKParams {
   int rope_stride;
   const int32_t* seq_lens;  // [B] true row lengths (right padding beyond), or null = S
   int window;               // sliding-window attention: query i sees keys i - window .. i; 0 = plain causal
+  const int32_t* row_start; // [B+1] packed ragged batch: sequence b owns rows row_start[b] .. row_start[b+1]) (multiples of 128); null: b*S ..
 };
+
+// first row of sequence b and the number of rows it owns (S, or its 128-rounded length in a packed batch)
+__device__ __forceinline__ int seq_base(const AttnKParams& p, int b, int* cap) {
+  if (p.row_start) {
+    const int r0 = p.row_start[b];
+    *cap = p.row_start[b + 1] - r0;
+    return r0;
+  }
+  *cap = p.S;
+  return b * p.S;
+}
 
 // true length of batch row b (tiles that start at or beyond it hold only padding)
 __device__ __forceinline__ int row_len(const AttnKParams& p, int b) {
@@ -186,12 +198,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int qp = npair - 1 - (blockIdx.x % npair);  // heavy (late) query pairs first
   const int bh = blockIdx.x / npair;
   const int h = bh % p.H, b = bh / p.H;
-  const int row_base = b * p.S;
+  int cap;
+  const int row_base = seq_base(p, b, &cap);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int hk = h / (p.H / p.Hkv);
   const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
   const int q00 = qp * 256, q01 = qp * 256 + 128;
-  const int len = row_len(p, b);
+  if (q00 >= cap) return;  // packed batch: this sequence has no such tile (the rows there belong to the next sequence)
+  const int len = min(row_len(p, b), cap);
   // Sliding window: keys before q00 - window are invisible to every row of this CTA: the K/V ring starts at block jlo (both tiles
   // start there - the at most two leading blocks that only tile 0 can see are fully masked for tile 1).  Block counts below are
   // relative to jlo; a row may then meet blocks in which it sees nothing (handled by the -inf-safe softmax reference).
@@ -202,8 +216,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   auto nt = [&](int t) { return t ? n1 : n0; };
   if (n0 == 0) {  // both tiles lie in this row's padding (n1 > 0 implies n0 > 0)
     zero_tile_128(p.out, static_cast<long long>(p.H) * HD, row_base + q00, h * HD, tid, FW2_THREADS);
-    if (q01 < p.S) zero_tile_128(p.out, static_cast<long long>(p.H) * HD, row_base + q01, h * HD, tid, FW2_THREADS);
-    if (p.lse2 && tid < 256 && q00 + tid < p.S) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + q00 + tid] = 0.f;
+    if (q01 < cap) zero_tile_128(p.out, static_cast<long long>(p.H) * HD, row_base + q01, h * HD, tid, FW2_THREADS);
+    if (p.lse2 && tid < 256 && q00 + tid < cap) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + q00 + tid] = 0.f;
     return;
   }
 
@@ -449,7 +463,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         printf("[fwd2 softmax] block %d tile %d n %d loop %lld (incl. first wait) wait_fin %lld epilogue %lld | per block: wait_s %lld ld %lld math %lld st+arrive %lld\n",
                (int)blockIdx.x, t, n_mine, tc_loop, tc_fin, clock64() - tc_0 - tc_loop - tc_fin, tc_w / n_mine, tc_l / n_mine, tc_m / n_mine, tc_s / n_mine);
 #endif
-    } else if (q0 < p.S) {  // this tile holds only padding: zeros (see zero_tile_128)
+    } else if (q0 < cap) {  // this tile holds only padding: zeros (see zero_tile_128)
       zero_tile_128(p.out, static_cast<long long>(p.H) * HD, row_base + q0, h * HD, r, 128);
       if (p.lse2) p.lse2[(static_cast<size_t>(b) * p.H + h) * p.S + qrow] = 0.f;
     }
@@ -504,14 +518,16 @@ attn_dq1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int bh = blockIdx.x / nqb;
   const int h = bh % p.H, b = bh / p.H;
   const int q0 = qb * 128;
-  const int row_base = b * p.S;
+  int cap;
+  const int row_base = seq_base(p, b, &cap);
+  if (q0 >= cap) return;  // packed batch: not a tile of this sequence
   const int window = WIN ? p.window : 0;
   const int jlo = WIN ? max(0, (q0 - window) / 64) : 0;  // sliding window: first K/V block any row of the tile can see
   const int n = (q0 + 128) / 64 - jlo;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int hk = h / (p.H / p.Hkv);
   const int colQ = h * HD, colK = p.colK0 + hk * HD, colV = p.colV0 + hk * HD;
-  if (q0 >= row_len(p, b)) {  // the tile holds only padding: dQ = 0, delta = 0
+  if (q0 >= min(row_len(p, b), cap)) {  // the tile holds only padding: dQ = 0, delta = 0
     zero_tile_128(p.dqkv, p.W, row_base + q0, colQ, tid, DKV_THREADS);
     if (tid < 128) p.delta_w[(static_cast<size_t>(b) * p.H + h) * p.S + q0 + tid] = 0.f;
     return;
@@ -828,9 +844,11 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_consta
   const int hk = bh % p.Hkv, b = bh / p.Hkv;  // one CTA per (batch, KV head, 128-row KV block)
   const int grp = p.H / p.Hkv;                // query heads sharing this KV head (1 = multi-head attention)
   const int kv0 = kb * 128;
-  const int row_base = b * p.S;
+  int cap;
+  const int row_base = seq_base(p, b, &cap);
+  if (kv0 >= cap) return;  // packed batch: not a tile of this sequence
   const int i0 = kv0 / 64;
-  const int len = row_len(p, b);
+  const int len = min(row_len(p, b), cap);
   // query blocks per query head that see this KV block and hold a real token; with a sliding window the last query row that
   // sees any key of the tile is kv0 + 127 + window
   const int window = WIN ? p.window : 0;
@@ -1181,7 +1199,8 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
   if (a.H % Hkv) return cudaErrorInvalidValue;
-  const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD;
+  if (a.row_start && (a.total_rows <= 0 || a.total_rows % 128 || a.window > 0)) return cudaErrorInvalidValue;
+  const uint64_t M = a.row_start ? static_cast<uint64_t>(a.total_rows) : static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD;
   CUtensorMap tmQ, tmKV, tmOut;
   const uint64_t WO = static_cast<uint64_t>(a.H) * HD;
   if (!make_tmap_2d_bf16(&tmQ, a.qkv, W, M, W, 64, 128) || !make_tmap_2d_bf16(&tmKV, a.qkv, W, M, W, 64, 64) ||
@@ -1196,6 +1215,7 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   p.out = a.out;
   p.seq_lens = a.seq_lens;
   p.window = a.window;
+  p.row_start = a.row_start;
   const int grid = a.B * a.H * ((a.S + 255) / 256);
 #define DTX_FWD_LAUNCH(E)                                                                          \
   if (a.window > 0) attn_fwd2_kernel<E, true><<<grid, FW2_THREADS, FW2_SMEM, s>>>(tmQ, tmKV, tmOut, p); \
@@ -1217,7 +1237,8 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
   if (a.H % Hkv) return cudaErrorInvalidValue;
-  const uint64_t M = static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD,
+  if (a.row_start && (a.total_rows <= 0 || a.total_rows % 128 || a.window > 0)) return cudaErrorInvalidValue;
+  const uint64_t M = a.row_start ? static_cast<uint64_t>(a.total_rows) : static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD,
                  WO = static_cast<uint64_t>(a.H) * HD;
   CUtensorMap tmQ128, tmKV64, tmDO128, tmKV128, tmQ64, tmDO64, tmDqkv, tmO128;
   if (!make_tmap_2d_bf16(&tmO128, a.out, WO, M, WO, 64, 128)) return cudaErrorInvalidValue;
@@ -1241,6 +1262,7 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   p.rope_stride = a.rope_stride > 0 ? a.rope_stride : a.S;
   p.seq_lens = a.seq_lens;
   p.window = a.window;
+  p.row_start = a.row_start;
   const int gq = a.B * a.H * (a.S / 128), gkv = a.B * Hkv * (a.S / 128);
   const bool win = a.window > 0;
 #define DTX_DQ_LAUNCH(W, I) attn_dq1_kernel<W, I><<<gq, DKV_THREADS, DQ1_SMEM, s>>>(tmQ128, tmKV64, tmDO128, tmO128, tmDqkv, p)

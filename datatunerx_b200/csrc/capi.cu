@@ -63,6 +63,10 @@ int32_t dtx_set_option(const char* name, int32_t value) {
     trainer_set_varlen_split(value);
     return DTX_OK;
   }
+  if (strcmp(name, "varlen_pack") == 0) {
+    trainer_set_varlen_pack(value);
+    return DTX_OK;
+  }
   if (strcmp(name, "varlen_group_cost") == 0) {
     trainer_set_varlen_group_cost(value);
     return DTX_OK;

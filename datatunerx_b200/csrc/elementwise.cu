@@ -277,7 +277,8 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) shift_labels_kernel(const int32_t* __restrict__ labels, int32_t* __restrict__ shifted,
                                                             int32_t* __restrict__ n_valid, int B, int S,
-                                                            int32_t* __restrict__ row_map, int32_t* __restrict__ valid_idx) {
+                                                            int32_t* __restrict__ row_map, int32_t* __restrict__ valid_idx,
+                                                            const int32_t* __restrict__ pos) {
   // one block; thread t owns the contiguous token range [t*c, (t+1)*c): counts, block-wide exclusive scan, ordered positions
   __shared__ int sh[1024];
   const int total = B * S;
@@ -285,8 +286,9 @@ __global__ void __launch_bounds__(1024) shift_labels_kernel(const int32_t* __res
   const int lo = min(total, static_cast<int>(threadIdx.x) * c), hi = min(total, lo + c);
   int cnt = 0;
   for (int i = lo; i < hi; ++i) {
-    const int t = i % S;
-    const int v = (t == S - 1) ? -100 : labels[i + 1];
+    // last token of its sequence: nothing to predict.  Packed ragged batch: the next token starts a new sequence (position 0)
+    const bool last = pos ? (i + 1 >= total || pos[i + 1] == 0) : (i % S == S - 1);
+    const int v = last ? -100 : labels[i + 1];
     shifted[i] = v;
     cnt += (v >= 0) ? 1 : 0;
   }
@@ -861,9 +863,9 @@ cudaError_t swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int M, int F
 }
 
 cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_valid, int B, int S, cudaStream_t s,
-                         int32_t* row_map, int32_t* valid_idx) {
+                         int32_t* row_map, int32_t* valid_idx, const int32_t* pos) {
   if ((row_map == nullptr) != (valid_idx == nullptr)) return cudaErrorInvalidValue;
-  shift_labels_kernel<<<1, 1024, 0, s>>>(labels, shifted, n_valid, B, S, row_map, valid_idx);
+  shift_labels_kernel<<<1, 1024, 0, s>>>(labels, shifted, n_valid, B, S, row_map, valid_idx, pos);
   return cudaGetLastError();
 }
 
@@ -889,6 +891,32 @@ __global__ void gather_rows_kernel(const int32_t* __restrict__ ids, const int32_
     labels_out[static_cast<long long>(i) * S_dst + c] = labels[static_cast<long long>(src) * S_src + c];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) lens_out[i] = lens[src];
+}
+
+__global__ void pack_rows_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ labels, int S_src, RowStarts rs,
+                                 int32_t* __restrict__ ids_out, int32_t* __restrict__ labels_out, int32_t* __restrict__ pos_out,
+                                 int32_t* __restrict__ start_out) {
+  const int b = blockIdx.y, r0 = rs.start[b], cap = rs.start[b + 1] - r0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cap; c += gridDim.x * blockDim.x) {
+    ids_out[r0 + c] = ids[static_cast<long long>(b) * S_src + c];
+    labels_out[r0 + c] = labels[static_cast<long long>(b) * S_src + c];
+    pos_out[r0 + c] = c;
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0)
+    for (int i = threadIdx.x; i <= rs.n; i += blockDim.x) start_out[i] = rs.start[i];
+}
+
+cudaError_t pack_rows(const int32_t* ids, const int32_t* labels, int S_src, RowStarts rs, int32_t* ids_out, int32_t* labels_out,
+                      int32_t* pos_out, int32_t* start_out, cudaStream_t s) {
+  if (rs.n <= 0 || rs.n > 64 || S_src <= 0) return cudaErrorInvalidValue;
+  int max_cap = 0;
+  for (int b = 0; b < rs.n; ++b) {
+    const int cap = rs.start[b + 1] - rs.start[b];
+    if (cap <= 0 || cap > S_src || (cap & 127) || (rs.start[b] & 127)) return cudaErrorInvalidValue;
+    max_cap = cap > max_cap ? cap : max_cap;
+  }
+  pack_rows_kernel<<<dim3((max_cap + 255) / 256, rs.n), 256, 0, s>>>(ids, labels, S_src, rs, ids_out, labels_out, pos_out, start_out);
+  return cudaGetLastError();
 }
 
 cudaError_t gather_rows(const int32_t* ids, const int32_t* labels, const int32_t* lens, int S_src, RowList rows, int S_dst,

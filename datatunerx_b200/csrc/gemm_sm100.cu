@@ -41,6 +41,7 @@ struct GemmKParams {
   long long ld_aux;
   const float2* rope_cs;
   int rope_S, rope_cols, rope_inverse;
+  const int32_t* rope_pos;  // optional per-row position (packed ragged batches); null: row % rope_S
   const int32_t* m_eff;  // pair kernel: device-side row count; 256-row tiles that start at or beyond it are skipped
 };
 
@@ -481,7 +482,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (EPI == EPI_ROPE) {
         // two heads per tile (chunks 0-3 / 4-7); rotary pairs column i with i+64: chunk c with chunk c+2
         const bool rot = n0 < p.rope_cols;
-        const float2* cs = p.rope_cs + static_cast<long long>(row_ok ? (row % p.rope_S) : 0) * 64;
+        const float2* cs = p.rope_cs + static_cast<long long>(row_ok ? (p.rope_pos ? __ldg(p.rope_pos + row) : row % p.rope_S) : 0) * 64;
 #pragma unroll 1
         for (int hc = 0; hc < 4; ++hc) {
           const int c = (hc >> 1) * 4 + (hc & 1);
@@ -734,6 +735,7 @@ cudaError_t launch(const GemmArgs& a, cudaStream_t s) {
   p.ld_aux = 0;
   p.rope_cs = nullptr;
   p.rope_S = p.rope_cols = p.rope_inverse = 0;
+  p.rope_pos = nullptr;
   p.m_eff = nullptr;  // the single-CTA kernel computes every row (rows beyond the device-side count are dead, not wrong)
   int total = p.m_tiles * p.n_tiles * p.split_k;
   int grid = total < gemm_num_sms() ? total : gemm_num_sms();
@@ -799,6 +801,7 @@ cudaError_t launch2(const GemmArgs& a, cudaStream_t s) {
   p.rope_S = a.rope_S;
   p.rope_cols = a.rope_cols;
   p.rope_inverse = a.rope_inverse;
+  p.rope_pos = a.rope_pos;
   p.m_eff = a.m_eff;
   const int total = p.m_tiles * p.n_tiles;
   int pairs = gemm_num_sms() / 2;

@@ -35,6 +35,7 @@ struct GemmArgs {
   const bf16* R = nullptr; int64_t ldr = 0;
   void* aux = nullptr; int64_t ld_aux = 0;             // EPI_SWIGLU_FWD: act out; EPI_SWIGLU_BWD: gu in (ld = 2F)
   const float2* rope_cs = nullptr; int rope_S = 0, rope_cols = 0, rope_inverse = 0;  // EPI_ROPE
+  const int32_t* rope_pos = nullptr;  // EPI_ROPE, optional [M]: position of every row inside its sequence (packed ragged batches); null: row % rope_S
   int M = 0, N = 0, K = 0;
   // optional device-side row count (<= M): the CTA-pair kernel skips 256-row tiles that start at or beyond it (rows up to the
   // end of the last live tile are still computed).  Lets the lm_head GEMMs run over the unmasked tokens only without a
@@ -60,6 +61,7 @@ void trainer_set_fused_epilogues(int on);
 // 1 (default): --quantization int4 expands the next NF4 matrix on a side stream under the current GEMM; 0: inline
 void trainer_set_nf4_prefetch(int on);
 void trainer_set_varlen_group_cost(int permille);  // fixed cost per length group in the partition's cost model
+void trainer_set_varlen_pack(int on);   // ragged LoRA micro-batches run packed in one pass (default 1; 0: length groups)
 void trainer_set_varlen_split(int on);  // ragged micro-batches run as length groups (default 1)
 
 // ---------------------------------------------------------------------------------------------
@@ -79,6 +81,11 @@ struct AttnArgs {
   // Sliding-window attention (Mistral): query i sees keys j with i - window <= j <= i  (transformers 4.34.0
   // _make_sliding_window_causal_mask: triu(diagonal=-sliding_window)); 0 = plain causal.
   int window = 0;
+  // PACKED ragged batch (optional, device int32 [B+1]): sequence b occupies rows row_start[b] .. row_start[b+1]) of qkv / out
+  // (multiples of 128) instead of b*S .. (b+1)*S; S is then only the tile-grid extent and the stride of lse / delta per (b, h),
+  // total_rows = row_start[B] (host copy, for the tensor maps).  Tiles beyond a sequence's rows do nothing.
+  const int32_t* row_start = nullptr;
+  int total_rows = 0;
   // backward
   int rope_stride = 0;              // row stride (positions) of the transposed rope table; 0 = S
   const float2* rope_cs = nullptr;  // backward only: TRANSPOSED table [64][S] (cos, sin); if set, dq and dk get the inverse rotary applied before the store
@@ -113,8 +120,10 @@ cudaError_t swiglu_bwd(const bf16* dact, const bf16* gu, bf16* dgu, int M, int F
 // labels_shift[b,t] = labels[b,t+1] (last = -100); n_valid counted into *n_valid (int32).
 // With row_map / valid_idx (both or neither): row_map[m] = position of row m among the rows with a label (in order), or -1;
 // valid_idx[k] = the k-th such row.
+// pos (optional, [B*S]): position of every token inside its sequence (packed ragged batches: sequences of different lengths
+// back to back) - a token is the last of its sequence when the next token's position is 0; null: rows of S tokens.
 cudaError_t shift_labels(const int32_t* labels, int32_t* shifted, int32_t* n_valid, int B, int S, cudaStream_t s,
-                         int32_t* row_map = nullptr, int32_t* valid_idx = nullptr);
+                         int32_t* row_map = nullptr, int32_t* valid_idx = nullptr, const int32_t* pos = nullptr);
 // softmax cross-entropy over fp32 logits [M,V]; row_loss[M] (0 for ignored rows); dlogits bf16 = (p - onehot)/n_valid.
 // valid_idx (optional): COMPACT mode - logits / dlogits row k belongs to token valid_idx[k] (k < *n_valid; other blocks
 // return), labels and row_loss stay indexed by token; row_loss of unlabelled tokens must have been zeroed by the caller.
@@ -126,6 +135,12 @@ cudaError_t cross_entropy_fwd_bwd(const float* logits, int64_t ldl, const int32_
 cudaError_t loss_reduce(const float* row_loss, const int32_t* n_valid, float* loss, int M, cudaStream_t s, int n_div = 0, int accumulate = 0);
 // rows[i] of the [*, S_src] int32 matrices ids / labels -> row i of the [n, S_dst] outputs (S_dst <= S_src), lens_out[i] = lens[rows[i]]
 struct RowList { int32_t n; int32_t rows[64]; };
+// PACKED ragged batch: sequence b of the [B, S_src] inputs occupies rows start[b] .. start[b+1]) of the outputs (its length
+// rounded up to 128; the padding inside keeps the source's padding ids / -100 labels), pos_out = position inside the sequence,
+// start_out[B+1] = the same offsets on the device for the attention kernels.
+struct RowStarts { int32_t n; int32_t start[65]; };
+cudaError_t pack_rows(const int32_t* ids, const int32_t* labels, int S_src, RowStarts rs, int32_t* ids_out, int32_t* labels_out,
+                      int32_t* pos_out, int32_t* start_out, cudaStream_t s);
 cudaError_t gather_rows(const int32_t* ids, const int32_t* labels, const int32_t* lens, int S_src, RowList rows, int S_dst,
                         int32_t* ids_out, int32_t* labels_out, int32_t* lens_out, cudaStream_t s);
 // out[i] = sum_s partial[s][i]  (fixed order)

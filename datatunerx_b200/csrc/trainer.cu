@@ -81,6 +81,7 @@ thread_local std::string g_error;
 int g_nf4_prefetch = 1;     // expand the next NF4 matrix on a side stream while the current GEMM runs (0: inline, for A/B runs)
 int g_varlen_split = 1;     // ragged micro-batches run as length groups (rows sorted by length, partition chosen by a cost model);
                             // 2: always cut where the 128-rounded lengths differ (parity tests at shapes too small for the model to split)
+int g_varlen_pack = 1;      // ragged LoRA micro-batches run PACKED: sequences back to back at 128-rounded lengths, one pass (0: length groups)
 int g_varlen_fix_permille = 200;   // fixed cost charged per length group, in thousandths of "one wave of every GEMM of a layer"
 int g_fused_epilogues = 1;  // RoPE / SwiGLU fused into the GEMM and attention epilogues (needs M > 128: CTA-pair GEMM)
 
@@ -160,6 +161,7 @@ enum { W_QKV = 0, W_O = 1, W_GU = 2, W_DOWN = 3 };
 void trainer_set_fused_epilogues(int on) { g_fused_epilogues = on; }
 void trainer_set_nf4_prefetch(int on) { g_nf4_prefetch = on; }
 void trainer_set_varlen_split(int on) { g_varlen_split = on; }
+void trainer_set_varlen_pack(int on) { g_varlen_pack = on; }
 void trainer_set_varlen_group_cost(int permille) { g_varlen_fix_permille = permille < 0 ? 0 : permille; }
 }  // namespace dtx
 
@@ -182,7 +184,8 @@ struct dtx_trainer {
   bool sub_accum = false;       // a later length group of the same micro-batch: gradients and loss add to the earlier groups'
   int sub_ndiv = 0;             // > 0: labelled tokens of the WHOLE micro-batch (the divisor of the token-mean loss of every group)
   int n_sms = 148;
-  int last_groups = 1;          // length groups of the last training micro-batch (diagnostics)
+  int last_groups = 1;          // length groups of the last training micro-batch (diagnostics; 0 = packed)
+  bool packed = false;          // the batch in d_ids / d_labels is PACKED: sequence b owns rows d_row_start[b] .. d_row_start[b+1])
   bool use_seq_lens = false;    // d_seq_lens holds this batch's true row lengths
   int dq = 0, dkv = 0, W = 0;  // q width (= hidden), k/v width (n_kv_heads*128), packed qkv row width
   int KA = 0;                  // contraction length of the LoRA down-projection: d, or nt*d with dropout
@@ -206,6 +209,7 @@ struct dtx_trainer {
   int32_t *d_ids = nullptr, *d_labels = nullptr, *d_shift = nullptr, *d_nvalid = nullptr, *d_seq_lens = nullptr;
   int32_t *d_row_map = nullptr, *d_valid_idx = nullptr;  // token -> position among the labelled tokens (-1: none) and back
   int32_t *d_ids_full = nullptr, *d_labels_full = nullptr, *d_lens_full = nullptr;  // the whole ragged micro-batch (length groups gather from it)
+  int32_t *d_pos = nullptr, *d_row_start = nullptr;  // packed batch: position of every row inside its sequence; first row of every sequence
   std::vector<int32_t> h_labels, h_lens;  // host copies of a device-resident ragged batch (the partition is planned on the host)
   std::vector<float> h_row_sum;           // per-row evaluation statistics of the length groups, in group order
   std::vector<int32_t> h_row_valid;
@@ -446,7 +450,8 @@ int create_buffers(dtx_trainer* t) {
   ok = ok && t->alloc(&t->d_loss, 4) && t->alloc(&t->d_sumsq, 4) && t->alloc(&t->d_gnorm, 4) && t->alloc(&t->d_scratch, 1024);
   ok = ok && t->alloc(&t->d_ids, M) && t->alloc(&t->d_labels, M) && t->alloc(&t->d_shift, M) && t->alloc(&t->d_nvalid, 4);
   ok = ok && t->alloc(&t->d_row_map, M) && t->alloc(&t->d_valid_idx, M);
-  if (!full) ok = ok && t->alloc(&t->d_ids_full, M) && t->alloc(&t->d_labels_full, M) && t->alloc(&t->d_lens_full, static_cast<size_t>(tc.micro_batch));
+  if (!full) ok = ok && t->alloc(&t->d_ids_full, M) && t->alloc(&t->d_labels_full, M) && t->alloc(&t->d_lens_full, static_cast<size_t>(tc.micro_batch)) &&
+                   t->alloc(&t->d_pos, M) && t->alloc(&t->d_row_start, static_cast<size_t>(tc.micro_batch) + 1);
   ok = ok && t->alloc(&t->d_seq_lens, static_cast<size_t>(tc.micro_batch)) && t->alloc(&t->d_row_sum, static_cast<size_t>(tc.micro_batch)) &&
        t->alloc(&t->d_row_valid, static_cast<size_t>(tc.micro_batch)) && t->alloc(&t->d_host_red, 64);
   ok = ok && t->alloc(&t->rope_cs, static_cast<size_t>(tc.seq_len) * (mc.head_dim / 2));
@@ -638,14 +643,17 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       g.C = y.qkv; g.ldc = W; g.M = M; g.N = W; g.K = d; g.epilogue = EPI_BF16;
       if (fused) {  // rotary embedding of q and k applied to the fp32 accumulator in the epilogue
         g.epilogue = EPI_ROPE; g.rope_cs = t->rope_cs; g.rope_S = S; g.rope_cols = t->dq + t->dkv;
+        g.rope_pos = t->packed ? t->d_pos : nullptr;  // packed batch: a row's position is its offset inside its own sequence
       }
       CK(gemm_bf16(g, s), 1);
     }
+    if (!fused && t->packed) return t->fail(DTX_ERR_STATE, "packed batches need the fused RoPE epilogue");
     if (!fused) CK(rope_qk_inplace_table(y.qkv, t->rope_cs, B, S, H + Hkv, W, D, 0, s), 1);
     {
       AttnArgs a;
       a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.Hkv = Hkv; a.scale = att_scale;
       a.seq_lens = seq_lens; a.window = t->window;
+      if (t->packed) { a.row_start = t->d_row_start; a.total_rows = M; }
       CK(attn_fwd(a, s), 1);
     }
     {  // x_mid = x + attn * Wo^T
@@ -684,7 +692,8 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
   int32_t* row_map = lora ? t->d_row_map : nullptr;
   int32_t* valid_idx = lora ? t->d_valid_idx : nullptr;
   const int32_t* m_eff = lora ? t->d_nvalid : nullptr;
-  CK(shift_labels(t->d_labels, t->d_shift, t->d_nvalid, B, S, s, row_map, valid_idx), 1);
+  if (t->packed) CK(shift_labels(t->d_labels, t->d_shift, t->d_nvalid, 1, M, s, row_map, valid_idx, t->d_pos), 1);
+  else CK(shift_labels(t->d_labels, t->d_shift, t->d_nvalid, B, S, s, row_map, valid_idx), 1);
   CK(rmsnorm_fwd(t->xs[L], t->normf, t->h2, t->rstdf, M, d, mc.rms_eps, s, row_map), 1);
   {  // fp32 logits (the reference patches lm_head to return fp32: cmd/tuning/train.py:256-264)
     GemmArgs g;
@@ -767,6 +776,7 @@ int fwd_bwd(dtx_trainer* t, bool backward) {
       a.qkv = y.qkv; a.out = y.attn; a.lse = y.lse; a.B = B; a.S = S; a.H = H; a.Hkv = Hkv; a.scale = att_scale;
       a.dout = t->dattn; a.dqkv = t->dqkv; a.delta = t->delta;
       a.seq_lens = seq_lens; a.window = t->window; a.rope_stride = tc.seq_len;
+      if (t->packed) { a.row_start = t->d_row_start; a.total_rows = M; }
       // The dQ / dK kernels apply the inverse rotary in their store epilogues from the TRANSPOSED table (thread r of a tile
       // reads position q0 + r: one coalesced 256-byte line per frequency and warp).  A first attempt with the [S][64] table
       // (32 uncoalesced 8-byte reads per thread) cost +270 us/layer, the standalone HBM-bound kernel 92 us.
@@ -974,6 +984,7 @@ int set_batch_shape(dtx_trainer* t, int32_t seq_len_batch, bool have_lens) {
   t->cur_B = t->tc.micro_batch;
   t->cur_M = S * t->tc.micro_batch;
   t->use_seq_lens = have_lens;
+  t->packed = false;
   return DTX_OK;
 }
 
@@ -993,6 +1004,23 @@ struct SubPlan {
   int order[64] = {0};  // rows sorted by length, longest first
   int n_div = 0;        // labelled tokens of the whole micro-batch, counted the way the groups' shift_labels kernels will
 };
+
+// PACKED layout of a ragged LoRA micro-batch: sequence b gets its length rounded up to 128 rows, sequences back to back - one
+// pass over sum_b ceil128(len_b) rows instead of B * S_batch (or one pass per length group).  GEMMs, norms and CE simply see
+// fewer rows; the attention kernels take the first row of every sequence from a table; RoPE takes a row's position and the
+// label shift a sequence's end from a per-row position array.  Returns false when packing does not apply or saves nothing.
+bool plan_packed(const dtx_trainer* t, const int32_t* lens, int S_batch, RowStarts* rs) {
+  const int B = t->tc.micro_batch;
+  if (!g_varlen_pack || g_varlen_split == 0 || g_varlen_split == 2 || t->full || t->window > 0 || !lens || B < 1 || B > 64) return false;
+  if (!g_fused_epilogues || ((t->dq + t->dkv) % 256) || (t->W % 256)) return false;  // RoPE must run in the GEMM epilogue (per-row positions)
+  rs->n = B;
+  rs->start[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    const int len = std::min(std::max(lens[b], 0), S_batch);
+    rs->start[b + 1] = rs->start[b] + std::min(S_batch, std::max(128, (len + 127) / 128 * 128));
+  }
+  return rs->start[B] < B * S_batch && rs->start[B] > 128;
+}
 
 struct PlanDims { int hidden, ffn, W, n_sms, B; };  // what the cost model needs of the model / device / batch
 
@@ -1070,7 +1098,7 @@ int do_step(dtx_trainer* t, int32_t flags, float* loss_out, float* gnorm_out, fl
   const int accum = t->tc.grad_accum > 0 ? t->tc.grad_accum : 1;
   t->rs_now = t->full && (t->micro_idx + 1 >= accum || (flags & DTX_STEP_FORCE));
   int rc = DTX_OK;
-  t->last_groups = 1;
+  t->last_groups = t->packed ? 0 : 1;
   if (plan && plan->n > 1) {
     t->last_groups = plan->n;
     for (int g = 0; g < plan->n && rc == DTX_OK; ++g) {
@@ -1575,6 +1603,18 @@ int32_t dtx_step(dtx_trainer* t, const int32_t* ids, const int32_t* labels, cons
   int rc = check_ready(t);
   if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, seq_lens != nullptr);
   if (rc) return rc;
+  RowStarts rs;
+  if (plan_packed(t, seq_lens, t->cur_S, &rs)) {  // ragged batch, packed: staging buffers -> sequences back to back
+    CKM(cudaMemcpyAsync(t->d_ids_full, ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+    CKM(cudaMemcpyAsync(t->d_labels_full, labels, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+    CKM(cudaMemcpyAsync(t->d_seq_lens, seq_lens, static_cast<size_t>(t->tc.micro_batch) * 4, cudaMemcpyHostToDevice, t->stream));
+    CK(pack_rows(t->d_ids_full, t->d_labels_full, t->cur_S, rs, t->d_ids, t->d_labels, t->d_pos, t->d_row_start, t->stream), 1);
+    t->cur_M = rs.start[rs.n];
+    t->packed = true;
+    rc = do_step(t, flags, loss, gnorm, lr, stepped);
+    t->packed = false;
+    return rc;
+  }
   SubPlan plan;
   if (!t->full) plan_groups(PlanDims{t->mc.hidden, t->mc.ffn, t->W, t->n_sms, t->tc.micro_batch}, seq_lens, labels, t->cur_S, &plan);
   if (plan.n > 1) {  // ragged batch: the whole batch goes to the staging buffers, the length groups gather from there
@@ -1597,6 +1637,23 @@ int32_t dtx_step_device(dtx_trainer* t, const void* d_ids, const void* d_labels,
   int rc = check_ready(t);
   if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, d_seq_lens != nullptr);
   if (rc) return rc;
+  if (d_seq_lens && g_varlen_pack && g_varlen_split == 1 && !t->full && t->window == 0 && t->tc.micro_batch <= 64) {
+    // the packed layout is planned on the host from the row lengths (B * 4 bytes)
+    t->h_lens.resize(static_cast<size_t>(t->tc.micro_batch));
+    CKM(cudaMemcpyAsync(t->h_lens.data(), d_seq_lens, t->h_lens.size() * 4, cudaMemcpyDeviceToHost, t->stream));
+    CKM(cudaStreamSynchronize(t->stream));
+    RowStarts rs;
+    if (plan_packed(t, t->h_lens.data(), t->cur_S, &rs)) {
+      CKM(cudaMemcpyAsync(t->d_seq_lens, d_seq_lens, static_cast<size_t>(t->tc.micro_batch) * 4, cudaMemcpyDeviceToDevice, t->stream));
+      CK(pack_rows(static_cast<const int32_t*>(d_ids), static_cast<const int32_t*>(d_labels), t->cur_S, rs, t->d_ids, t->d_labels, t->d_pos,
+                   t->d_row_start, t->stream), 1);
+      t->cur_M = rs.start[rs.n];
+      t->packed = true;
+      rc = do_step(t, flags, loss, gnorm, lr, stepped);
+      t->packed = false;
+      return rc;
+    }
+  }
   if (d_seq_lens && g_varlen_split && !t->full && t->tc.micro_batch > 1 && t->tc.micro_batch <= 64) {
     // the partition is planned on the host: fetch the row lengths and the labels (B*S*4 bytes, tens of microseconds)
     t->h_lens.resize(static_cast<size_t>(t->tc.micro_batch));

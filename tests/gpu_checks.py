@@ -781,6 +781,10 @@ def check_trainer_varlen(steps=4):
         ref = orc.step([(ids[:, :cur], labels[:, :cur])])
         loss, gn, _, stepped = tr.step(ids[:, :cur], labels[:, :cur], lens)
         assert stepped
+        # default execution of a ragged LoRA micro-batch: PACKED (sequences back to back at 128-rounded lengths, one pass) whenever
+        # that saves rows; 0 = packed, 1 = one pass at the padded shape
+        saves = int(sum(max(128, -(-int(l) // 128) * 128) for l in lens)) < 4 * cur
+        assert tr.last_step_groups == (0 if saves else 1), (lens, tr.last_step_groups)
         worst_l, worst_g = max(worst_l, abs(loss - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
     # gradient tensors of one more step against the oracle's autograd gradients, from adapters with a sizeable B (B = 0 at init
     # makes dA vanish; after a few Adam steps it is ~1e-3 and the comparison would measure bf16 noise on tiny numbers)
@@ -1057,17 +1061,24 @@ def check_layer_7b_shape(B=2, S=2048):
         ids2[1, 700:] = 0
         labels2[1, 700:] = -100
         ref2, g2 = orc.loss_and_grads(ids2, labels2)
+        def rel_errs(got):
+            return {k.split("layers.0.")[1]: float(np.linalg.norm(v - g2[k.replace("base_model.model.", "")].numpy()) /
+                                                   max(np.linalg.norm(g2[k.replace("base_model.model.", "")].numpy()), 1e-12)) for k, v in got.items()}
         L.set_option("varlen_split", 2)
         try:
             loss2, _, _, _ = tr.step(ids2, labels2, lens)
             n_groups = tr.last_step_groups
         finally:
             L.set_option("varlen_split", 1)
-        got2 = tr.export_adapter(grads=True)
-        errs2 = {k.split("layers.0.")[1]: float(np.linalg.norm(v - g2[k.replace("base_model.model.", "")].numpy()) /
-                                                max(np.linalg.norm(g2[k.replace("base_model.model.", "")].numpy()), 1e-12)) for k, v in got2.items()}
+        errs2 = rel_errs(tr.export_adapter(grads=True))
         ragged = {"groups": n_groups, "loss_rel": abs(loss2 - ref2) / ref2, "adapter_grad_rel": errs2}
         assert n_groups == 2 and ragged["loss_rel"] < 1e-3 and max(errs2.values()) < 4e-2, ragged
+        # and PACKED (the default): one pass over 2048 + 768 rows, the second sequence starting at row 2048
+        tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
+        loss3, _, _, _ = tr.step(ids2, labels2, lens)
+        errs3 = rel_errs(tr.export_adapter(grads=True))
+        ragged["packed"] = {"mode": tr.last_step_groups, "loss_rel": abs(loss3 - ref2) / ref2, "adapter_grad_rel": errs3}
+        assert tr.last_step_groups == 0 and ragged["packed"]["loss_rel"] < 1e-3 and max(errs3.values()) < 4e-2, ragged
     tr.close()
     res = {"eval_loss_rel": e_eval, "step_loss_rel": abs(loss - ref_loss) / ref_loss, "gnorm_rel": abs(gn - ref_norm) / ref_norm,
            "adapter_grad_rel": errs, "oracle_loss": ref_loss, "native_loss": loss, "sec_init": t_init, "sec_oracle_fwd_bwd": t_cpu,

@@ -59,16 +59,17 @@ def main_full(steps=4):
     sys.exit(0 if ok else 1)
 
 
-def main(steps=5, ragged=False):
+def main(steps=5, ragged=False, packed=False):
     """ragged: every rank's micro-batch has its own row lengths and runs as length groups ("varlen_split" = 2 cuts wherever the
     128-rounded lengths differ): even ranks split into two groups, odd ranks stay one - the all-reduce still happens once per step."""
+    ragged = ragged or packed  # packed: the same ragged shards in the default execution mode (sequences back to back, one pass)
     rv = Rendezvous()
     S = 512 if ragged else 256
     ocfg = O.OracleConfig(vocab=2048, hidden=256, n_layers=2, n_heads=2, ffn=768, lora_r=16, lora_alpha=32.0, lr=1e-3,
                           total_steps=steps)
     mc = L.ModelConfig(vocab=2048, hidden=256, n_layers=2, n_heads=2, ffn=768)
     tc = L.TrainConfig(micro_batch=2, seq_len=S, total_steps=steps, lora_r=16, lora_alpha=32.0, lora_dropout=0.0, lr=1e-3)
-    if ragged:
+    if ragged and not packed:
         L.set_option("varlen_split", 2)
 
     def shard(s, r):
@@ -97,8 +98,8 @@ def main(steps=5, ragged=False):
         groups.append(tr.last_step_groups)
         worst_l = max(worst_l, abs(loss - ref_losses[rv.rank]) / ref_losses[rv.rank])
         worst_g = max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
-    if ragged:
-        assert groups == [2 if rv.rank % 2 == 0 else 1] * steps, (rv.rank, groups)
+    if ragged:  # even ranks: two length groups (or packed = 0); odd ranks: both rows round to the full length, one pass
+        assert groups == [(0 if packed else 2) if rv.rank % 2 == 0 else 1] * steps, (rv.rank, groups)
     ad = tr.export_adapter()
     ref_ad = orc.state_dict()
     drift = max(float(np.linalg.norm(v - ref_ad[k.replace("base_model.model.", "")]) /
@@ -113,7 +114,7 @@ def main(steps=5, ragged=False):
     # adapters after a few Adam steps: Adam normalises tiny bf16-noisy gradients, so a few % relative drift is expected
     ok = worst_l < 1e-3 and worst_g < 3e-2 and drift < 0.15 and len(set(digests)) == 1
     if rv.rank == 0:
-        print(("MULTI_GPU_CHECK_RAGGED " if ragged else "MULTI_GPU_CHECK ") + json.dumps({"world": rv.world, "ok": ok, "groups_rank0": groups, "loss_rel": worst_l, "gnorm_rel": worst_g,
+        print(("MULTI_GPU_CHECK_PACKED " if packed else "MULTI_GPU_CHECK_RAGGED " if ragged else "MULTI_GPU_CHECK ") + json.dumps({"world": rv.world, "ok": ok, "groups_rank0": groups, "loss_rel": worst_l, "gnorm_rel": worst_g,
                                                "adapter_drift": drift, "replicas_bitwise_equal": len(set(digests)) == 1}), flush=True)
     rv.close()
     sys.exit(0 if ok else 1)
@@ -123,4 +124,4 @@ if __name__ == "__main__":
     if "--full" in sys.argv:
         main_full()
     else:
-        main(ragged="--ragged" in sys.argv)
+        main(ragged="--ragged" in sys.argv, packed="--packed" in sys.argv)

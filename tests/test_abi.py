@@ -63,7 +63,7 @@ def test_option_switches_are_known_and_unknown_names_rejected(lib):
     """Every A/B switch documented in include/dtxtune.h / kernels.h is accepted (host-side flags, no device needed)."""
     from datatunerx_b200 import lib as L
     defaults = {"gemm_pair_kernel": 1, "gemm_group_m": 16, "fused_epilogues": 1, "attn_fwd_exp_fma_every": 3, "nf4_prefetch": 1,
-                "attn_dq_exp_fma_every": 0, "varlen_split": 1, "varlen_group_cost": 200}
+                "attn_dq_exp_fma_every": 0, "varlen_split": 1, "varlen_group_cost": 200, "varlen_pack": 1}
     for name, value in defaults.items():
         L.set_option(name, value)  # restores the default: raises DtxError on an unknown name
     with pytest.raises(L.DtxError):

@@ -23,6 +23,7 @@ for s in $STEPS; do
     mgpu_check) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29541 tests/multi_gpu_check.py > $OUT/multi_gpu_check_n${NGPU:-2}.log 2>&1;;
     mgpu_full) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29544 tests/multi_gpu_check.py --full > $OUT/multi_gpu_check_full_n${NGPU:-2}.log 2>&1;;
     mgpu_ragged) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29548 tests/multi_gpu_check.py --ragged > $OUT/multi_gpu_check_ragged_n${NGPU:-2}.log 2>&1;;
+    mgpu_packed) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29549 tests/multi_gpu_check.py --packed > $OUT/multi_gpu_check_packed_n${NGPU:-2}.log 2>&1;;
     bench_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus ${NGPU:-2} --steps 8 --warmup 3 > $OUT/bench_n${NGPU:-2}.json 2> $OUT/bench_n${NGPU:-2}.err;;
     qlora_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29543 bench.py --config mistral7b_qlora --gpus ${NGPU:-2} --steps 5 --warmup 3 > $OUT/bench_qlora_n${NGPU:-2}.json 2> $OUT/bench_qlora_n${NGPU:-2}.err;;
     full13b_n) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-8} --master-addr 127.0.0.1 --master-port 29545 bench.py --config 13b_full --gpus ${NGPU:-8} --steps 6 --warmup 3 > $OUT/bench_13b_full_n${NGPU:-8}.json 2> $OUT/bench_13b_full_n${NGPU:-8}.err;;
@@ -47,6 +48,7 @@ for s in $STEPS; do
     refarm) timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_reference.json 2> $OUT/bench_reference.err;;
     varlen) timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen.json 2> $OUT/bench_varlen.err;;
     varlen_cost) for v in ${COSTS:-250 500 1000}; do DTX_VARLEN_GROUP_COST=$v timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen_cost$v.json 2> $OUT/bench_varlen_cost$v.err; done;;
+    varlen_pack) for v in 0 1; do DTX_VARLEN_PACK=$v timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen_pack$v.json 2> $OUT/bench_varlen_pack$v.err; done;;
     varlen_ab) for v in 0 1; do DTX_VARLEN_SPLIT=$v timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen_split$v.json 2> $OUT/bench_varlen_split$v.err; done;;
     qlora) timeout 600 python bench.py --config mistral7b_qlora --steps 5 --warmup 3 > $OUT/bench_qlora.json 2> $OUT/bench_qlora.err;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1600 -c 2000 --csv --log-file $OUT/launches.csv \
