@@ -33,6 +33,8 @@ for s in $STEPS; do
     jobs_tiny) timeout 600 python tools/concurrent_jobs.py --jobs ${NJOBS:-1} --gpus-per-job 2 --model tiny --steps 12 --out $OUT/concurrent_jobs_tiny.json > $OUT/concurrent_jobs_tiny.log 2>&1;;
     jobs_7b) timeout 900 python tools/concurrent_jobs.py --jobs ${NJOBS:-4} --gpus-per-job 2 --model 7b --steps ${JOB_STEPS:-24} --out $OUT/concurrent_jobs_7b.json > $OUT/concurrent_jobs_7b.log 2>&1;;
     jobs_ragged) for v in 0 1; do DTX_OPTIONS=varlen_split=$v timeout 900 python tools/concurrent_jobs.py --jobs 1 --gpus-per-job ${NGPU:-1} --model 7b --steps ${JOB_STEPS:-12} --ragged --out $OUT/worker_ragged_split$v.json > $OUT/worker_ragged_split$v.log 2>&1; done;;
+    memcheck_packed) timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python -m tests.gpu_checks trainer_varlen > $OUT/memcheck_varlen_packed.log 2>&1
+                     timeout 900 compute-sanitizer --tool racecheck --print-limit 5 python -m tests.gpu_checks trainer_varlen > $OUT/racecheck_varlen_packed.log 2>&1;;
     memcheck_groups) timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python -m tests.gpu_checks trainer_varlen_groups > $OUT/memcheck_varlen_groups.log 2>&1
                      timeout 900 compute-sanitizer --tool racecheck --print-limit 5 python -m tests.gpu_checks trainer_varlen_groups > $OUT/racecheck_varlen_groups.log 2>&1;;
     determinism) timeout 600 python tools/diag_determinism.py > $OUT/determinism.log 2>&1;;
