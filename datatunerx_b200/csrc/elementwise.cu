@@ -666,15 +666,18 @@ __global__ void __launch_bounds__(256) nf4_dequant_kernel(const uint8_t* __restr
 
 // per-sequence loss sum / valid-token count (evaluation: lets the host form HF's eval batches of any size)
 __global__ void row_loss_stats_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ labels, int S,
-                                      float* __restrict__ row_sum, int32_t* __restrict__ row_valid) {
+                                      float* __restrict__ row_sum, int32_t* __restrict__ row_valid, const int32_t* __restrict__ row_start) {
   __shared__ float sh[32];
   __shared__ int shc[32];
   const int b = blockIdx.x;
+  // packed batch: sequence b owns rows row_start[b] .. row_start[b+1]); otherwise rows b*S .. (b+1)*S
+  const size_t r0 = row_start ? static_cast<size_t>(row_start[b]) : static_cast<size_t>(b) * S;
+  const int n = row_start ? row_start[b + 1] - row_start[b] : S;
   double acc = 0.0;
   int cnt = 0;
-  for (int i = threadIdx.x; i < S; i += blockDim.x) {
-    acc += static_cast<double>(row_loss[static_cast<size_t>(b) * S + i]);
-    cnt += labels[static_cast<size_t>(b) * S + i] >= 0 ? 1 : 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    acc += static_cast<double>(row_loss[r0 + i]);
+    cnt += labels[r0 + i] >= 0 ? 1 : 0;
   }
   float v = block_sum(static_cast<float>(acc), sh);
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -961,8 +964,8 @@ cudaError_t nf4_dequant_bf16(const uint8_t* q, const float* absmax, bf16* w, int
   return cudaGetLastError();
 }
 cudaError_t row_loss_stats(const float* row_loss, const int32_t* shifted_labels, int B, int S, float* row_sum, int32_t* row_valid,
-                           cudaStream_t s) {
-  row_loss_stats_kernel<<<B, 256, 0, s>>>(row_loss, shifted_labels, S, row_sum, row_valid);
+                           cudaStream_t s, const int32_t* row_start) {
+  row_loss_stats_kernel<<<B, 256, 0, s>>>(row_loss, shifted_labels, S, row_sum, row_valid, row_start);
   return cudaGetLastError();
 }
 

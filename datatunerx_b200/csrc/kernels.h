@@ -173,7 +173,7 @@ cudaError_t nf4_quantize_pack(const bf16* w, uint8_t* q, float* absmax, int64_t 
 cudaError_t nf4_dequant_bf16(const uint8_t* q, const float* absmax, bf16* w, int64_t n, cudaStream_t s);
 // per sequence: row_sum[b] = sum of row_loss over the S tokens of sequence b, row_valid[b] = tokens with a label >= 0
 cudaError_t row_loss_stats(const float* row_loss, const int32_t* shifted_labels, int B, int S, float* row_sum, int32_t* row_valid,
-                           cudaStream_t s);
+                           cudaStream_t s, const int32_t* row_start = nullptr);  // row_start: packed batch ([B+1] first rows)
 // ---- full-parameter SFT (BASELINE.json configs[3]) ----
 // RMSNorm weight gradient: dw[c] (+)= sum_m dy[m,c] * x[m,c] * rstd[m]   (two-stage, fixed order; scratch >= 64 * d floats)
 cudaError_t rmsnorm_dw(const bf16* dy, const bf16* x, const float* rstd, int M, int d, float* scratch, bf16* dw, int accumulate,

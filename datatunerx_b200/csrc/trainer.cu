@@ -1681,9 +1681,31 @@ int32_t dtx_eval_loss(dtx_trainer* t, const int32_t* ids, const int32_t* labels,
   if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, seq_lens != nullptr);
   if (rc) return rc;
   const int B = t->tc.micro_batch;
+  float h = 0.f;
+  RowStarts rs;
+  if (plan_packed(t, seq_lens, t->cur_S, &rs)) {  // ragged batch, packed: one forward pass over the sequences back to back
+    CKM(cudaMemcpyAsync(t->d_ids_full, ids, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+    CKM(cudaMemcpyAsync(t->d_labels_full, labels, static_cast<size_t>(t->cur_M) * 4, cudaMemcpyHostToDevice, t->stream));
+    CKM(cudaMemcpyAsync(t->d_seq_lens, seq_lens, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, t->stream));
+    CK(pack_rows(t->d_ids_full, t->d_labels_full, t->cur_S, rs, t->d_ids, t->d_labels, t->d_pos, t->d_row_start, t->stream), 1);
+    t->cur_M = rs.start[rs.n];
+    t->packed = true;
+    rc = fwd_bwd(t, false);
+    t->packed = false;
+    if (rc) return rc;
+    CKM(cudaMemcpyAsync(&h, t->d_loss, 4, cudaMemcpyDeviceToHost, t->stream));
+    if (row_sum_out || row_valid_out) {
+      CK(row_loss_stats(t->row_loss, t->d_shift, B, t->cur_S, t->d_row_sum, t->d_row_valid, t->stream, t->d_row_start), 1);
+      if (row_sum_out) CKM(cudaMemcpyAsync(row_sum_out, t->d_row_sum, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, t->stream));
+      if (row_valid_out) CKM(cudaMemcpyAsync(row_valid_out, t->d_row_valid, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, t->stream));
+    }
+    cudaError_t e = cudaStreamSynchronize(t->stream);
+    if (e != cudaSuccess) return t->fail(DTX_ERR_CUDA, "eval failed on device: %s", cudaGetErrorString(e));
+    if (loss_out) *loss_out = h;
+    return DTX_OK;
+  }
   SubPlan plan;
   if (!t->full) plan_groups(PlanDims{t->mc.hidden, t->mc.ffn, t->W, t->n_sms, B}, seq_lens, labels, t->cur_S, &plan);
-  float h = 0.f;
   if (plan.n > 1) {
     // ragged batch as length groups (forward only): the per-row statistics come back in group order and are put back in
     // the caller's row order; the batch loss accumulates over the groups with the whole batch's labelled-token count

@@ -785,6 +785,12 @@ def check_trainer_varlen(steps=4):
         # that saves rows; 0 = packed, 1 = one pass at the padded shape
         saves = int(sum(max(128, -(-int(l) // 128) * 128) for l in lens)) < 4 * cur
         assert tr.last_step_groups == (0 if saves else 1), (lens, tr.last_step_groups)
+        if s_ == 0:  # forward-only evaluation of the same ragged batch, packed vs one pass at the padded shape: per-row statistics
+            s_pk, c_pk = tr.eval_rows(ids[:, :cur], labels[:, :cur], lens)
+            L.set_option("varlen_split", 0)
+            s_one, c_one = tr.eval_rows(ids[:, :cur], labels[:, :cur], lens)
+            L.set_option("varlen_split", 1)
+            assert c_pk.tolist() == c_one.tolist() and float(np.max(np.abs(s_pk - s_one) / np.maximum(np.abs(s_one), 1e-6))) < 2e-3, (s_pk, s_one, c_pk, c_one)
         worst_l, worst_g = max(worst_l, abs(loss - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
     # gradient tensors of one more step against the oracle's autograd gradients, from adapters with a sizeable B (B = 0 at init
     # makes dA vanish; after a few Adam steps it is ~1e-3 and the comparison would measure bf16 noise on tiny numbers)
