@@ -450,8 +450,8 @@ int create_buffers(dtx_trainer* t) {
   ok = ok && t->alloc(&t->d_loss, 4) && t->alloc(&t->d_sumsq, 4) && t->alloc(&t->d_gnorm, 4) && t->alloc(&t->d_scratch, 1024);
   ok = ok && t->alloc(&t->d_ids, M) && t->alloc(&t->d_labels, M) && t->alloc(&t->d_shift, M) && t->alloc(&t->d_nvalid, 4);
   ok = ok && t->alloc(&t->d_row_map, M) && t->alloc(&t->d_valid_idx, M);
-  if (!full) ok = ok && t->alloc(&t->d_ids_full, M) && t->alloc(&t->d_labels_full, M) && t->alloc(&t->d_lens_full, static_cast<size_t>(tc.micro_batch)) &&
-                   t->alloc(&t->d_pos, M) && t->alloc(&t->d_row_start, static_cast<size_t>(tc.micro_batch) + 1);
+  ok = ok && t->alloc(&t->d_ids_full, M) && t->alloc(&t->d_labels_full, M) && t->alloc(&t->d_lens_full, static_cast<size_t>(tc.micro_batch)) &&
+       t->alloc(&t->d_pos, M) && t->alloc(&t->d_row_start, static_cast<size_t>(tc.micro_batch) + 1);
   ok = ok && t->alloc(&t->d_seq_lens, static_cast<size_t>(tc.micro_batch)) && t->alloc(&t->d_row_sum, static_cast<size_t>(tc.micro_batch)) &&
        t->alloc(&t->d_row_valid, static_cast<size_t>(tc.micro_batch)) && t->alloc(&t->d_host_red, 64);
   ok = ok && t->alloc(&t->rope_cs, static_cast<size_t>(tc.seq_len) * (mc.head_dim / 2));
@@ -1005,13 +1005,13 @@ struct SubPlan {
   int n_div = 0;        // labelled tokens of the whole micro-batch, counted the way the groups' shift_labels kernels will
 };
 
-// PACKED layout of a ragged LoRA micro-batch: sequence b gets its length rounded up to 128 rows, sequences back to back - one
+// PACKED layout of a ragged micro-batch (LoRA or full-parameter): sequence b gets its length rounded up to 128 rows, sequences back to back - one
 // pass over sum_b ceil128(len_b) rows instead of B * S_batch (or one pass per length group).  GEMMs, norms and CE simply see
 // fewer rows; the attention kernels take the first row of every sequence from a table; RoPE takes a row's position and the
 // label shift a sequence's end from a per-row position array.  Returns false when packing does not apply or saves nothing.
 bool plan_packed(const dtx_trainer* t, const int32_t* lens, int S_batch, RowStarts* rs) {
   const int B = t->tc.micro_batch;
-  if (!g_varlen_pack || g_varlen_split == 0 || g_varlen_split == 2 || t->full || t->window > 0 || !lens || B < 1 || B > 64) return false;
+  if (!g_varlen_pack || g_varlen_split == 0 || g_varlen_split == 2 || t->window > 0 || !lens || B < 1 || B > 64) return false;
   if (!g_fused_epilogues || ((t->dq + t->dkv) % 256) || (t->W % 256)) return false;  // RoPE must run in the GEMM epilogue (per-row positions)
   rs->n = B;
   rs->start[0] = 0;
@@ -1637,7 +1637,7 @@ int32_t dtx_step_device(dtx_trainer* t, const void* d_ids, const void* d_labels,
   int rc = check_ready(t);
   if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, d_seq_lens != nullptr);
   if (rc) return rc;
-  if (d_seq_lens && g_varlen_pack && g_varlen_split == 1 && !t->full && t->window == 0 && t->tc.micro_batch <= 64) {
+  if (d_seq_lens && g_varlen_pack && g_varlen_split == 1 && t->window == 0 && t->tc.micro_batch <= 64) {
     // the packed layout is planned on the host from the row lengths (B * 4 bytes)
     t->h_lens.resize(static_cast<size_t>(t->tc.micro_batch));
     CKM(cudaMemcpyAsync(t->h_lens.data(), d_seq_lens, t->h_lens.size() * 4, cudaMemcpyDeviceToHost, t->stream));

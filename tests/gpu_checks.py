@@ -1004,7 +1004,8 @@ def check_trainer_full(steps=8, grad_accum=1, weight_decay=0.01):
 
 
 def check_trainer_full_gqa(steps=4):
-    """Full-parameter SFT on a grouped-query model at a ragged batch (row lengths): the dK / dV width differs from dQ."""
+    """Full-parameter SFT on a grouped-query model at a ragged batch (row lengths): the dK / dV width differs from dQ.  The batch
+    runs PACKED (384 + 256 rows instead of 2 x 384): the weight-gradient GEMMs contract over the packed token rows."""
     ocfg, mc, tc = tiny_configs(S=384, B=2, steps=steps, heads=4, kv_heads=2)
     ocfg.full_finetune, tc.full_finetune = True, True
     w = O.init_base_weights(ocfg, 77)
@@ -1019,10 +1020,14 @@ def check_trainer_full_gqa(steps=4):
         labels[1, 200:] = -100
         ref = orc.step([(ids, labels)])
         loss, gn, _, _ = tr.step(ids, labels, lens)
+        assert tr.last_step_groups == 0, tr.last_step_groups  # packed
         worst_l, worst_g = max(worst_l, abs(loss - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
+    wts = tr.export_weights()
+    drift = max(float(np.linalg.norm(_bf16_bits_to_f32(v) - orc.lora[k].detach().numpy()) / max(np.linalg.norm(orc.lora[k].detach().numpy()), 1e-12))
+                for k, v in wts.items())
     tr.close()
-    assert worst_l < 2e-3 and worst_g < 3e-2, (worst_l, worst_g)
-    return {"loss": worst_l, "gnorm": worst_g}
+    assert worst_l < 2e-3 and worst_g < 3e-2 and drift < 1e-2, (worst_l, worst_g, drift)
+    return {"loss": worst_l, "gnorm": worst_g, "weight_drift": drift}
 
 
 def check_layer_7b_shape(B=2, S=2048):
