@@ -1199,7 +1199,7 @@ cudaError_t attn_fwd(const AttnArgs& a, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
   if (a.H % Hkv) return cudaErrorInvalidValue;
-  if (a.row_start && (a.total_rows <= 0 || a.total_rows % 128 || a.window > 0)) return cudaErrorInvalidValue;
+  if (a.row_start && (a.total_rows <= 0 || a.total_rows % 128)) return cudaErrorInvalidValue;
   const uint64_t M = a.row_start ? static_cast<uint64_t>(a.total_rows) : static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD;
   CUtensorMap tmQ, tmKV, tmOut;
   const uint64_t WO = static_cast<uint64_t>(a.H) * HD;
@@ -1237,7 +1237,7 @@ cudaError_t attn_bwd(const AttnArgs& a, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   const int Hkv = a.Hkv > 0 ? a.Hkv : a.H;
   if (a.H % Hkv) return cudaErrorInvalidValue;
-  if (a.row_start && (a.total_rows <= 0 || a.total_rows % 128 || a.window > 0)) return cudaErrorInvalidValue;
+  if (a.row_start && (a.total_rows <= 0 || a.total_rows % 128)) return cudaErrorInvalidValue;
   const uint64_t M = a.row_start ? static_cast<uint64_t>(a.total_rows) : static_cast<uint64_t>(a.B) * a.S, W = static_cast<uint64_t>(a.H + 2 * Hkv) * HD,
                  WO = static_cast<uint64_t>(a.H) * HD;
   CUtensorMap tmQ128, tmKV64, tmDO128, tmKV128, tmQ64, tmDO64, tmDqkv, tmO128;

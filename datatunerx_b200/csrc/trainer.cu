@@ -1011,7 +1011,7 @@ struct SubPlan {
 // label shift a sequence's end from a per-row position array.  Returns false when packing does not apply or saves nothing.
 bool plan_packed(const dtx_trainer* t, const int32_t* lens, int S_batch, RowStarts* rs) {
   const int B = t->tc.micro_batch;
-  if (!g_varlen_pack || g_varlen_split == 0 || g_varlen_split == 2 || t->window > 0 || !lens || B < 1 || B > 64) return false;
+  if (!g_varlen_pack || g_varlen_split == 0 || g_varlen_split == 2 || !lens || B < 1 || B > 64) return false;
   if (!g_fused_epilogues || ((t->dq + t->dkv) % 256) || (t->W % 256)) return false;  // RoPE must run in the GEMM epilogue (per-row positions)
   rs->n = B;
   rs->start[0] = 0;
@@ -1637,7 +1637,7 @@ int32_t dtx_step_device(dtx_trainer* t, const void* d_ids, const void* d_labels,
   int rc = check_ready(t);
   if (rc == DTX_OK) rc = set_batch_shape(t, seq_len_batch, d_seq_lens != nullptr);
   if (rc) return rc;
-  if (d_seq_lens && g_varlen_pack && g_varlen_split == 1 && t->window == 0 && t->tc.micro_batch <= 64) {
+  if (d_seq_lens && g_varlen_pack && g_varlen_split == 1 && t->tc.micro_batch <= 64) {
     // the packed layout is planned on the host from the row lengths (B * 4 bytes)
     t->h_lens.resize(static_cast<size_t>(t->tc.micro_batch));
     CKM(cudaMemcpyAsync(t->h_lens.data(), d_seq_lens, t->h_lens.size() * 4, cudaMemcpyDeviceToHost, t->stream));

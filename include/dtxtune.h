@@ -178,8 +178,8 @@ DTX_API double dtx_lr_lambda(int32_t sched, int32_t step, int32_t warmup_steps, 
  * "attn_dq_exp_fma_every" = N in {0, 3, 4}: the same for the dQ kernel's exp / dS phase (default 0).
  * "varlen_split" = 1 (default): a LoRA micro-batch that comes with row lengths is run as length groups (rows sorted by length,
  * partition chosen by a cost model; same token-mean loss and gradients up to summation order); 0: one pass at the batch's length.
- * "varlen_pack" = 1 (default): such a micro-batch is instead run PACKED - sequences back to back at their 128-rounded lengths, one
- * pass - when the model has no sliding window and the fused RoPE epilogue applies; 0: length groups.
+ * "varlen_pack" = 1 (default): such a micro-batch (LoRA or full-parameter) is instead run PACKED - sequences back to back at their
+ * 128-rounded lengths, one pass - whenever the fused RoPE epilogue applies (q|k|v width a multiple of 256); 0: length groups.
  * "varlen_group_cost" = N: fixed cost the partition's cost model charges per group, in thousandths of one wave of every GEMM of a layer.
  * "nf4_prefetch" = 1 (default): with --quantization int4 the next matrix is expanded on a side stream under the current GEMM
  * (read at dtx_quantize_base time); 0: expansion inline on the main stream.  Unknown names return DTX_ERR_INVALID. */

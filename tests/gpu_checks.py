@@ -712,11 +712,19 @@ def check_trainer_window(steps=4):
     orc = O.OracleTrainer(ocfg, w, lora)
     plain = O.OracleTrainer(O.OracleConfig(**{**ocfg.__dict__, "sliding_window": 0}), w, lora)
     worst_l = worst_g = 0.0
+    modes = []
     for s_ in range(steps):
         ids, labels = O.synthetic_batch(s_, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)
+        lens = None
+        if s_ >= steps - 2:  # ragged rows (the second one shorter than / around twice the window): packed, windows inside every sequence
+            lens = np.array([512, 140 + 200 * (s_ - (steps - 2))], dtype=np.int32)
+            ids[1, lens[1]:] = 0
+            labels[1, lens[1]:] = -100
         ref = orc.step([(ids, labels)])
-        loss, gn, _, _ = tr.step(ids, labels)
+        loss, gn, _, _ = tr.step(ids, labels, lens)
+        modes.append(tr.last_step_groups)
         worst_l, worst_g = max(worst_l, abs(loss - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
+    assert modes[-2:] == [0, 0] and modes[0] == 1, modes
     ids, labels = O.synthetic_batch(0, 0, tc.micro_batch, tc.seq_len, ocfg.vocab)
     shift = abs(plain.eval_loss(ids, labels) - O.OracleTrainer(ocfg, w, lora).eval_loss(ids, labels))
     tr.close()
