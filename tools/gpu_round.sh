@@ -50,6 +50,7 @@ for s in $STEPS; do
     refarm) timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_reference.json 2> $OUT/bench_reference.err;;
     varlen) timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen.json 2> $OUT/bench_varlen.err;;
     varlen_cost) for v in ${COSTS:-250 500 1000}; do DTX_VARLEN_GROUP_COST=$v timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen_cost$v.json 2> $OUT/bench_varlen_cost$v.err; done;;
+    varlen_n) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-8} --master-addr 127.0.0.1 --master-port 29550 bench.py --config 7b_varlen --gpus ${NGPU:-8} --steps 8 --warmup 3 > $OUT/bench_varlen_n${NGPU:-8}.json 2> $OUT/bench_varlen_n${NGPU:-8}.err;;
     varlen_pack) for v in 0 1; do DTX_VARLEN_PACK=$v timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen_pack$v.json 2> $OUT/bench_varlen_pack$v.err; done;;
     varlen_ab) for v in 0 1; do DTX_VARLEN_SPLIT=$v timeout 600 python bench.py --config 7b_varlen --steps 8 --warmup 3 > $OUT/bench_varlen_split$v.json 2> $OUT/bench_varlen_split$v.err; done;;
     qlora) timeout 600 python bench.py --config mistral7b_qlora --steps 5 --warmup 3 > $OUT/bench_qlora.json 2> $OUT/bench_qlora.err;;
