@@ -141,3 +141,32 @@ def test_empty_ragged_and_oversized_inputs(tmp_path):
     p = tmp_path / "d.csv"
     p.write_text("q,a\n\"what, exactly?\",\"this\"\n")
     assert D.read_csv_rows(str(p), {"q": "instruction", "a": "response"}) == [{"instruction": "what, exactly?", "response": "this"}]
+
+
+def test_collation_matches_the_installed_data_collator():
+    """a12: DataCollatorForSeq2Seq(pad_to_multiple_of=4, label_pad_token_id=-100) (cmd/tuning/train.py:282-286) against
+    tuning.data.collate on the same examples: identical ids / labels over the collator's own width, and only padding
+    (pad id, -100) beyond it.  The installed transformers (5.x) stands in for the reference's pinned 4.34.0."""
+    import os
+    from transformers import DataCollatorForSeq2Seq, PreTrainedTokenizerFast
+    from datatunerx_b200.tuning import data as D
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_tokenizer.json")
+    tok = PreTrainedTokenizerFast(tokenizer_file=gold, bos_token="<s>", eos_token="</s>", unk_token="<unk>")
+    D.fix_tokenizer(tok)
+    assert tok.padding_side == "right"
+    rng = np.random.default_rng(3)
+    examples = []
+    for n in (37, 5, 130, 64):
+        x = rng.integers(3, 300, size=n).tolist()
+        y = [-100] * (n // 3) + x[n // 3:]
+        examples.append((x, y))
+    hf = DataCollatorForSeq2Seq(tokenizer=tok, pad_to_multiple_of=4, label_pad_token_id=-100)(
+        [{"input_ids": x, "attention_mask": [1] * len(x), "labels": y} for x, y in examples], return_tensors="np")
+    width = hf["input_ids"].shape[1]
+    assert width == 132  # longest row 130 rounded up to a multiple of 4
+    cur = D.batch_seq_len([len(x) for x, _ in examples], 2048)
+    assert cur == 256  # the native step rounds to the 128-row attention tile instead and passes the true lengths
+    ids, lab = D.collate(examples, cur, tok.pad_token_id)
+    assert np.array_equal(ids[:, :width], hf["input_ids"]) and np.array_equal(lab[:, :width], hf["labels"])
+    assert (ids[:, width:] == tok.pad_token_id).all() and (lab[:, width:] == -100).all()
+    assert [int(r.sum()) for r in hf["attention_mask"]] == [len(x) for x, _ in examples]  # = the seq_lens handed to dtx_step
