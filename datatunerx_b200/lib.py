@@ -396,7 +396,7 @@ class Trainer:
 
     @property
     def last_step_groups(self) -> int:
-        """Length groups the last training micro-batch was run as (1 = one pass at the batch's padded length)."""
+        """How the last training micro-batch was run: 0 = packed, 1 = one pass at the padded shape, > 1 = that many length groups."""
         return int(self.lib.dtx_last_step_groups(self._h))
 
     @property

@@ -159,7 +159,8 @@ DTX_API float dtx_last_step_ms(const dtx_trainer* t);
 /* event-timed segments of the most recent dtx_step in ms: out[0] whole step, out[1] forward + backward, out[2] gradient
  * all-reduce (0 when world == 1 or no optimizer step ran), out[3] grad-norm + clip + AdamW + adapter refresh */
 DTX_API int32_t dtx_last_step_timings(const dtx_trainer* t, float* out4);
-/* Length groups the last training micro-batch was run as (1: one pass; > 1: see "varlen_split" below). */
+/* How the last training micro-batch was run: 0 = packed (sequences back to back, one pass), 1 = one pass at the padded shape,
+ * > 1 = that many length groups (see "varlen_pack" / "varlen_split" below). */
 DTX_API int32_t dtx_last_step_groups(const dtx_trainer* t);
 /* The partition dtx_step would choose for a LoRA micro-batch of `micro_batch` rows with these true lengths, padded to
  * seq_len_batch (host arithmetic, no device; n_sms <= 0: 148).  order_out[micro_batch]: rows sorted by length, longest first;
