@@ -1009,10 +1009,8 @@ struct SubPlan {
 // pass over sum_b ceil128(len_b) rows instead of B * S_batch (or one pass per length group).  GEMMs, norms and CE simply see
 // fewer rows; the attention kernels take the first row of every sequence from a table; RoPE takes a row's position and the
 // label shift a sequence's end from a per-row position array.  Returns false when packing does not apply or saves nothing.
-bool plan_packed(const dtx_trainer* t, const int32_t* lens, int S_batch, RowStarts* rs) {
-  const int B = t->tc.micro_batch;
-  if (!g_varlen_pack || g_varlen_split == 0 || g_varlen_split == 2 || !lens || B < 1 || B > 64) return false;
-  if (!g_fused_epilogues || ((t->dq + t->dkv) % 256) || (t->W % 256)) return false;  // RoPE must run in the GEMM epilogue (per-row positions)
+// the layout alone (host arithmetic): first row of every sequence; true when it is smaller than the padded rectangle
+bool packed_rows(const int32_t* lens, int B, int S_batch, RowStarts* rs) {
   rs->n = B;
   rs->start[0] = 0;
   for (int b = 0; b < B; ++b) {
@@ -1020,6 +1018,12 @@ bool plan_packed(const dtx_trainer* t, const int32_t* lens, int S_batch, RowStar
     rs->start[b + 1] = rs->start[b] + std::min(S_batch, std::max(128, (len + 127) / 128 * 128));
   }
   return rs->start[B] < B * S_batch && rs->start[B] > 128;
+}
+bool plan_packed(const dtx_trainer* t, const int32_t* lens, int S_batch, RowStarts* rs) {
+  const int B = t->tc.micro_batch;
+  if (!g_varlen_pack || g_varlen_split == 0 || g_varlen_split == 2 || !lens || B < 1 || B > 64) return false;
+  if (!g_fused_epilogues || ((t->dq + t->dkv) % 256) || (t->W % 256)) return false;  // RoPE must run in the GEMM epilogue (per-row positions)
+  return packed_rows(lens, B, S_batch, rs);
 }
 
 struct PlanDims { int hidden, ffn, W, n_sms, B; };  // what the cost model needs of the model / device / batch
@@ -1879,6 +1883,14 @@ int64_t dtx_num_trainable(const dtx_trainer* t) { return t ? t->n_train : 0; }
 int64_t dtx_launch_count(const dtx_trainer* t) { return t ? t->launches : 0; }
 float dtx_last_step_ms(const dtx_trainer* t) { return t ? t->last_ms : 0.f; }
 int32_t dtx_last_step_groups(const dtx_trainer* t) { return t ? t->last_groups : 0; }
+
+int32_t dtx_plan_packed_rows(int32_t micro_batch, const int32_t* seq_lens, int32_t seq_len_batch, int32_t* row_start_out) {
+  if (!seq_lens || !row_start_out || micro_batch < 1 || micro_batch > 64 || seq_len_batch < 128 || seq_len_batch % 128) return DTX_ERR_INVALID;
+  RowStarts rs;
+  const bool saves = packed_rows(seq_lens, micro_batch, seq_len_batch, &rs);
+  for (int b = 0; b <= micro_batch; ++b) row_start_out[b] = rs.start[b];
+  return saves ? 1 : 0;
+}
 
 int32_t dtx_plan_length_groups(const dtx_model_cfg* mc, int32_t micro_batch, int32_t n_sms, const int32_t* seq_lens, int32_t seq_len_batch,
                                int32_t* order_out, int32_t* group_start_out, int32_t* group_len_out) {

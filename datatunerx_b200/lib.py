@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "dtx_abi_version", "dtx_last_global_error", "dtx_last_error", "dtx_trainer_create", "dtx_trainer_destroy",
     "dtx_get_nccl_unique_id", "dtx_load_tensor", "dtx_init_random_weights", "dtx_init_lora", "dtx_quantize_base", "dtx_step",
     "dtx_step_device", "dtx_eval_loss", "dtx_allreduce_host", "dtx_export_adapter", "dtx_export_adapter_grad", "dtx_export_weight", "dtx_num_trainable", "dtx_launch_count",
-    "dtx_base_weight_bytes", "dtx_last_step_ms", "dtx_last_step_timings", "dtx_last_step_groups", "dtx_plan_length_groups", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16",
+    "dtx_base_weight_bytes", "dtx_last_step_ms", "dtx_last_step_timings", "dtx_last_step_groups", "dtx_plan_length_groups", "dtx_plan_packed_rows", "dtx_lr_lambda", "dtx_set_option", "dtx_gemm_bf16",
     "dtx_gemm_fused", "dtx_embedding_fwd", "dtx_rmsnorm_fwd", "dtx_rmsnorm_bwd",
     "dtx_rope_table", "dtx_rope_qk", "dtx_swiglu_fwd", "dtx_swiglu_bwd", "dtx_lora_dropout_fwd", "dtx_lora_dropout_bwd_add",
     "dtx_nf4_roundtrip", "dtx_nf4_pack", "dtx_nf4_dequant", "dtx_cross_entropy", "dtx_sumsq", "dtx_adamw",
@@ -94,6 +94,7 @@ def load() -> C.CDLL:
     lib.dtx_last_step_timings.argtypes = [vp, vp]
     lib.dtx_last_step_groups.argtypes = [vp]
     lib.dtx_plan_length_groups.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp]
+    lib.dtx_plan_packed_rows.argtypes = [i32, vp, i32, vp]
     lib.dtx_gemm_fused.argtypes = [vp, i64, vp, i64, i32, vp, i64, vp, i64, i32, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32,
                                    i32, vp]
     lib.dtx_export_adapter.argtypes = [vp, C.c_char_p, vp, i64]
@@ -141,6 +142,17 @@ def check(code: int, handle=None) -> None:
 
 def set_option(name: str, value: int) -> None:
     check(load().dtx_set_option(name.encode(), value))
+
+
+def plan_packed_rows(seq_lens, seq_len_batch: int):
+    """The packed layout of a ragged micro-batch (host arithmetic inside the library): (first row of every sequence + total rows,
+    whether packing saves rows over the padded rectangle)."""
+    lens = np.ascontiguousarray(seq_lens, dtype=np.int32)
+    starts = np.zeros(int(lens.shape[0]) + 1, np.int32)
+    rc = load().dtx_plan_packed_rows(int(lens.shape[0]), lens.ctypes.data_as(C.c_void_p), seq_len_batch, starts.ctypes.data_as(C.c_void_p))
+    if rc < 0:
+        raise DtxError(rc, "dtx_plan_packed_rows")
+    return starts.tolist(), bool(rc)
 
 
 def plan_length_groups(model: "ModelConfig", seq_lens, seq_len_batch: int, n_sms: int = 0):

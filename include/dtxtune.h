@@ -162,6 +162,11 @@ DTX_API int32_t dtx_last_step_timings(const dtx_trainer* t, float* out4);
 /* How the last training micro-batch was run: 0 = packed (sequences back to back, one pass), 1 = one pass at the padded shape,
  * > 1 = that many length groups (see "varlen_pack" / "varlen_split" below). */
 DTX_API int32_t dtx_last_step_groups(const dtx_trainer* t);
+/* The PACKED layout dtx_step uses for a ragged micro-batch (host arithmetic, no device): sequence b occupies rows
+ * row_start_out[b] .. row_start_out[b+1]) - its length rounded up to 128, at least 128 - of one pass over row_start_out[micro_batch]
+ * rows (array of micro_batch + 1 entries, micro_batch <= 64).  Returns 1 when that is fewer rows than micro_batch * seq_len_batch (the
+ * step packs), 0 when packing saves nothing (one pass at the padded shape), or a negative status. */
+DTX_API int32_t dtx_plan_packed_rows(int32_t micro_batch, const int32_t* seq_lens, int32_t seq_len_batch, int32_t* row_start_out);
 /* The partition dtx_step would choose for a LoRA micro-batch of `micro_batch` rows with these true lengths, padded to
  * seq_len_batch (host arithmetic, no device; n_sms <= 0: 148).  order_out[micro_batch]: rows sorted by length, longest first;
  * group g = order_out[group_start_out[g] .. group_start_out[g+1]) run at padded length group_len_out[g] (arrays of micro_batch + 1

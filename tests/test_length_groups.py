@@ -86,3 +86,26 @@ def test_group_cost_moves_the_cut_and_force_mode_minimises_padding(llama7b):
 def test_bad_arguments_are_refused(llama7b):
     with pytest.raises(L.DtxError):
         L.plan_length_groups(llama7b, [10, 20], 100)  # padded length must be a multiple of 128
+
+
+def test_packed_layout(lib):
+    """dtx_plan_packed_rows: sequences back to back at 128-rounded lengths (at least one tile each), the default execution of a
+    ragged micro-batch."""
+    starts, saves = L.plan_packed_rows([384, 130, 7, 257, 0], 384)
+    assert starts == [0, 384, 640, 768, 1152, 1280] and saves
+    assert all(s % 128 == 0 for s in starts)
+    starts, saves = L.plan_packed_rows([100, 100, 100, 100], 128)
+    assert starts == [0, 128, 256, 384, 512] and not saves  # as many rows as the padded rectangle: one pass at the padded shape
+    starts, saves = L.plan_packed_rows([5000, 2048], 2048)  # lengths are clamped to the batch's padded length
+    assert starts == [0, 2048, 4096] and not saves
+    rng = np.random.default_rng(1)
+    tot_real = tot_packed = tot_padded = 0
+    for _ in range(200):  # the bench's distribution: packing keeps less than 12 % padding where the rectangle has 54 %
+        lens = np.clip(np.exp(rng.normal(np.log(512.0), 0.6, size=8)), 16, 2048).astype(np.int32)
+        S_batch = c128(lens.max(), 2048)
+        starts, _ = L.plan_packed_rows(lens, S_batch)
+        assert all(b - a >= max(128, int(n)) and (b - a) % 128 == 0 for a, b, n in zip(starts, starts[1:], lens))
+        tot_real, tot_packed, tot_padded = tot_real + int(lens.sum()), tot_packed + starts[-1], tot_padded + 8 * S_batch
+    assert tot_real / tot_packed > 0.88 and tot_real / tot_padded < 0.5
+    with pytest.raises(L.DtxError):
+        L.plan_packed_rows([10, 20], 100)
