@@ -19,8 +19,10 @@
 //                       rowsum(dO o O) and the inverse rotary of dQ are computed here.
 //   attn_dkv_kernel   : CTA = 128 KV rows, loops over 64-row Q blocks of every query head of its KV group.  S^T = K Q^T,
 //                       dP^T = V dO^T (double-buffered), P^T / dS^T -> TMEM operands, dV += P^T dO, dK += dS^T Q.
-// All three take optional true row lengths (tiles that hold only right padding are skipped and written as zeros) and an
-// optional sliding window (query i sees keys i - window .. i).
+// All three take optional true row lengths (tiles that hold only right padding are skipped and written as zeros), an
+// optional sliding window (query i sees keys i - window .. i) and an optional table of first rows (PACKED ragged batches:
+// sequence b owns rows row_start[b] .. row_start[b+1]) instead of b*S .. (b+1)*S; everything else in the kernels was
+// relative to the sequence start already, a tile beyond a sequence's rows returns without touching memory).
 // What shaped them (profiles/r01_ncu_attn_issue_bound.txt, r01_ubench_mma_latency.txt, r02_attn_phase_timing_*.txt):
 //   * a tcgen05.mma issue blocks for the MMA's duration (the pipe's queue is ~1 deep): whatever else the issuing warp does -
 //     mbarrier checks cost ~90 cycles each even when the phase is long complete - is time the tensor pipe idles.  The forward
