@@ -885,6 +885,19 @@ def check_trainer_varlen_groups():
             got = float(np.sum(losses)) / 2  # HF: every micro-batch loss divided by grad_accum
             worst_l, worst_g = max(worst_l, abs(got - ref.loss) / ref.loss), max(worst_g, abs(gn - ref.grad_norm) / ref.grad_norm)
         assert max(groups) >= 3 and groups[2] == 1, groups  # [100,100,100,100] stays one group
+        # one more optimizer step in the DEFAULT mode (packed) with the same gradient accumulation: two ragged micro-batches of
+        # different packed sizes accumulate into one step
+        L.set_option("varlen_split", 1)
+        mbs = [ragged(20 + k, patterns[k]) for k in range(2)]
+        ref = orc.step([(m[0], m[1]) for m in mbs])
+        losses, modes = [], []
+        for ids, labels, lens in mbs:
+            loss, gn, _, stepped = tr.step(ids, labels, lens)
+            losses.append(loss)
+            modes.append(tr.last_step_groups)
+        packed_l, packed_g = abs(float(np.sum(losses)) / 2 - ref.loss) / ref.loss, abs(gn - ref.grad_norm) / ref.grad_norm
+        assert stepped and modes == [0, 0] and packed_l < 1e-3 and packed_g < 3e-2, (modes, packed_l, packed_g)
+        L.set_option("varlen_split", 2)
         # adapter gradients of one ragged micro-batch pair against the oracle's autograd gradients (fresh adapters as above)
         tr.load_state_dict({k: v.numpy() for k, v in lora.items()})
         with torch.no_grad():
@@ -905,7 +918,8 @@ def check_trainer_varlen_groups():
     finally:
         L.set_option("varlen_split", 1)
     assert worst_l < 1e-3 and worst_g < 3e-2 and max(per.values()) < 4e-2, (worst_l, worst_g, per)
-    return {"loss": worst_l, "gnorm": worst_g, "groups": groups, "adapter_grads": per, "eval_row_sums_rel": eval_rel}
+    return {"loss": worst_l, "gnorm": worst_g, "groups": groups, "adapter_grads": per, "eval_row_sums_rel": eval_rel,
+            "packed_with_grad_accum": {"loss": packed_l, "gnorm": packed_g}}
 
 
 def check_eval_rows_and_force_step():
