@@ -19,7 +19,10 @@ A "step" = forward + backward + (NCCL all-reduce) + clip + AdamW on one batch of
             (CUDA events inside libdtxtune) and the rank's median SM clock during the timed region - what explains the
             1 -> N curve (the step is lock-step: the slowest GPU's clock sets the pace).
 `--config 7b_varlen`: the same model on a length-distributed synthetic set (rows padded to the longest of their batch like
-            DataCollatorForSeq2Seq, true row lengths passed to the step): reports real (unpadded) tokens/s.
+            DataCollatorForSeq2Seq, true row lengths passed to the step, which runs the batch packed - DESIGN.md 2.2): reports
+            real (unpadded) tokens/s, `packed_steps`, `length_groups_per_step`.  DTX_VARLEN_SPLIT=0 / DTX_VARLEN_PACK=0: one pass
+            at the padded shape / length groups, for A/B runs.
+Other configs (not the headline metric): mistral7b_qlora (BASELINE configs[2]), 13b_full (configs[3], 8 GPUs), small_full, tiny.
 """
 from __future__ import annotations
 
