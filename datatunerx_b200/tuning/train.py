@@ -98,9 +98,11 @@ def run_rank(a: TrainArgs, rank: int, world: int, nccl_id: Optional[bytes], toke
                        lora_dropout=a.lora_dropout, lora_target=tuple(a.lora_target), lr=a.learning_rate, weight_decay=a.weight_decay,
                        beta1=a.adam_beta1, beta2=a.adam_beta2, eps=a.adam_epsilon, max_grad_norm=a.max_grad_norm,
                        sched=a.lr_scheduler_type, warmup_steps=a.warmup_steps, grad_accum=GA, seed=a.seed, full_finetune=full)
-    for kv in filter(None, os.environ.get("DTX_OPTIONS", "").split(",")):  # library A/B switches, e.g. DTX_OPTIONS=varlen_split=0
-        name, _, value = kv.partition("=")
-        L.set_option(name.strip(), int(value))
+    for kv in filter(None, os.environ.get("DTX_OPTIONS", "").split(",")):  # library A/B switches, e.g. DTX_OPTIONS=varlen_pack=0
+        name, sep, value = kv.partition("=")
+        if not sep or not value.strip().lstrip("-").isdigit():
+            raise L.DtxError(-1, f"DTX_OPTIONS entry {kv!r}: expected name=integer")
+        L.set_option(name.strip(), int(value))  # an unknown name raises (DTX_ERR_INVALID)
     device = int(os.environ.get("DTX_DEVICE", rank))
     tr = L.Trainer(mc, tc, device=device, rank=rank, world=world, nccl_id=nccl_id)
     if os.environ.get("DTX_RANDOM_INIT"):  # benchmarking / scheduling harnesses: config.json only, N(0, 0.02) weights on the device
